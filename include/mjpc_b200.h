@@ -1,0 +1,157 @@
+/* mjpc_b200.h - C ABI of the B200 rollout engine (libmjpc_b200.so).
+ *
+ * The engine replaces the data-parallel hot path of MJPC and nothing else.  std::function policies and
+ * virtual ResidualFn objects cannot cross to the device, so every entry point takes *data* and sits exactly
+ * where the reference fans work out over its ThreadPool:
+ *
+ *   mjpc_b200_rollout_spline    <- SamplingPlanner::Rollouts            mjpc/planners/sampling/planner.cc:355-393
+ *                                  (+ Trajectory::Rollout/NoisyRollout  mjpc/trajectory.cc:92-210,
+ *                                     SamplingPolicy::Action            mjpc/planners/sampling/policy.cc:52-59,
+ *                                     UpdateReturn                      mjpc/trajectory.cc:312-326,
+ *                                     partial_sort by return            mjpc/planners/sampling/planner.cc:184-188)
+ *   mjpc_b200_rollout_feedback  <- iLQGPlanner::FeedbackRollouts / ActionRollouts
+ *                                                                       mjpc/planners/ilqg/planner.cc:630-724
+ *                                  (+ iLQGPolicy::Action                mjpc/planners/ilqg/policy.cc:82-161,
+ *                                     Trajectory::RolloutDiscrete       mjpc/trajectory.cc:213-309)
+ *   mjpc_b200_model_derivatives <- ModelDerivatives::Compute            mjpc/planners/model_derivatives.cc:45-165
+ *   mjpc_b200_cost_derivatives  <- CostDerivatives::Compute             mjpc/planners/cost_derivatives.cc:112-230
+ *   mjpc_b200_backward_pass     <- RiccatiStep recursion                mjpc/planners/ilqg/planner.cc:429-520,
+ *                                                                       mjpc/planners/ilqg/backward_pass.cc:65-250
+ *   mjpc_b200_set_task          <- residual_fn_ snapshot per PlanIteration  mjpc/agent.cc:316-319, task.cc:112-128
+ *   mjpc_b200_fetch_trajectory  <- fills a mjpc::Trajectory             mjpc/trajectory.h:74-86
+ *   create / destroy            <- Planner::Initialize/Allocate + ResizeMjData  mjpc/planners/planner.cc:23-33;
+ *                                  precedent for a C surface: mjpc/interface.h:44-49
+ *
+ * Conventions: all pointers are HOST memory owned by the caller; the handle owns every device buffer and
+ * stream.  All calls come from the single plan thread (as Agent::PlanIteration does today).  Functions return
+ * 0 on success or a negative mjpc_b200_error; they never throw or abort.  Per-candidate divergence is
+ * reported through failure[i] (= Trajectory::failure) with returns[i] = 1e6 (mjpc/trajectory.cc:29,169-173).
+ * Arithmetic on the device is fp32; time is carried relative to the rollout start and returned as double.
+ */
+#ifndef MJPC_B200_H_
+#define MJPC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mjpc_b200 mjpc_b200_t;
+
+typedef enum {
+  MJPC_B200_OK = 0,
+  MJPC_B200_ERR_BAD_ARGUMENT = -1,
+  MJPC_B200_ERR_BAD_BLOB = -2,
+  MJPC_B200_ERR_CAPACITY = -3,   /* N / H above what create() reserved, or model too large for shared memory */
+  MJPC_B200_ERR_CUDA = -4,       /* no device, launch or copy failure: the engine has NO CPU fallback */
+  MJPC_B200_ERR_UNSUPPORTED = -5 /* model feature outside the implemented subset */
+} mjpc_b200_error;
+
+/* Flat model + task description (field names = mjModel's); written by mujoco_mpc_b200/blob.py, or by a
+ * maintainer from an mjModel* (INTEGRATION.md).  The engine copies what it needs during create(). */
+typedef struct {
+  const void* data;
+  size_t nbytes;
+} mjpc_model_blob;
+
+/* Live task snapshot (BaseResidualFn::Update, mjpc/task.cc:112-123). NULL members keep the current value. */
+typedef struct {
+  const double* weight;      /* [num_term]                         Task::weight        */
+  const double* parameters;  /* [num_parameters]                   Task::parameters    */
+  const double* task_state;  /* residual-specific state block (e.g. quadruped mode/gait/phase), see DESIGN.md */
+  double risk;               /* Task::risk                                              */
+} mjpc_task_desc;
+
+typedef struct {
+  int nq, nv, nu, na, nmocap, nuserdata;
+  int dim_state;        /* nq + nv + na   */
+  int dim_dstate;       /* 2*nv + na      */
+  int num_residual, num_term, num_trace, num_parameters, task_state_size;
+  int max_candidates, max_horizon;
+  int device;           /* CUDA device ordinal in use */
+  int smem_bytes_per_warp;
+} mjpc_b200_info;
+
+/* interp: 0 zero-order, 1 linear, 2 cubic (mjpc/spline/spline.h SplineInterpolation) */
+/* feedback mode: 0/1/2 time-indexed with that interpolation (iLQGPolicy::representation), 3 step-indexed */
+
+const char* mjpc_b200_version(void);
+const char* mjpc_b200_last_error(void);
+
+int mjpc_b200_create(const mjpc_model_blob* model, int max_candidates, int max_horizon, int device,
+                     mjpc_b200_t** out);
+void mjpc_b200_destroy(mjpc_b200_t* h);
+int mjpc_b200_get_info(const mjpc_b200_t* h, mjpc_b200_info* info);
+
+int mjpc_b200_set_task(mjpc_b200_t* h, const mjpc_task_desc* task);
+
+/* N candidate splines -> N rollouts of H steps. knots [N][P][nu]; knot_times [P] (absolute seconds).
+ * candidate_offset: global index of this handle's first candidate (multi-GPU sharding; only used for bookkeeping).
+ * returns [N], failure [N]; order [N] = candidate indices sorted by return (ties: lower index first), may be NULL. */
+int mjpc_b200_rollout_spline(mjpc_b200_t* h, const float* state, double time, const float* mocap,
+                             const float* userdata, const float* knots, const double* knot_times, int interp,
+                             int P, int N, int H, float* returns, uint8_t* failure, int* order);
+
+/* K line-search rollouts of the iLQG policy. u_nom [H][nu], x_nom [H][dim_state], t_nom [H] (absolute),
+ * gains [H][nu][dim_dstate], du [H][nu] (may be NULL), step_sizes [K]. */
+int mjpc_b200_rollout_feedback(mjpc_b200_t* h, const float* state, double time, const float* mocap,
+                               const float* userdata, const float* u_nom, const float* x_nom, const double* t_nom,
+                               const float* gains, const float* du, const float* step_sizes, int mode, int K, int H,
+                               float* returns, uint8_t* failure, int* order);
+
+/* Copy candidate i of the last rollout into Trajectory-shaped host arrays (any pointer may be NULL):
+ * states [H][dim_state], actions [H][nu], times [H], residual [H][num_residual], costs [H], trace [H][3*num_trace] */
+int mjpc_b200_fetch_trajectory(mjpc_b200_t* h, int candidate, float* states, float* actions, double* times,
+                               float* residual, float* costs, float* trace);
+/* Bulk variant: every candidate of the last rollout ([N] leading dimension). */
+int mjpc_b200_fetch_all(mjpc_b200_t* h, float* states, float* actions, double* times, float* residual,
+                        float* costs, float* trace);
+
+/* Finite-difference transition / residual Jacobians along a trajectory (one-sided, step `tol`).
+ * x [H][dim_state], u [H][nu], t [H]; A [H][n][n], B [H][n][nu], C [H][nr][n], D [H][nr][nu], n = dim_dstate,
+ * nr = num_residual (the rows CostDerivatives reads).  Row H-1 of A, B, D is left zero (model_derivatives.cc:89-93). */
+int mjpc_b200_model_derivatives(mjpc_b200_t* h, const float* x, const float* u, const double* t,
+                                const float* mocap, int H, float tol, float* A, float* B, float* C, float* D);
+
+/* Gauss-Newton cost derivatives. residual [H][nr], C, D as above -> cx [H][n], cu [H][nu], cxx [H][n][n],
+ * cuu [H][nu][nu], cxu [H][n][nu]. */
+int mjpc_b200_cost_derivatives(mjpc_b200_t* h, const float* residual, const float* C, const float* D, int H,
+                               float* cx, float* cu, float* cxx, float* cuu, float* cxu);
+
+/* One Riccati sweep at fixed regularisation. status_out: 1 success, 0 failure (caller scales mu and retries).
+ * reg_type 0 control, 1 state-control, 2 value, 3 none; limits 1 = box-QP within ctrlrange - action.
+ * Outputs: K [H][nu][n], du [H][nu], dV[2], and (optional, may be NULL) Vx [H][n], Vxx [H][n][n]. */
+int mjpc_b200_backward_pass(mjpc_b200_t* h, const float* A, const float* B, const float* cx, const float* cu,
+                            const float* cxx, const float* cxu, const float* cuu, const float* actions, int H,
+                            float mu, int reg_type, int limits, float* K, float* du, float* dV, float* Vx,
+                            float* Vxx, int* status_out);
+
+/* Debug / parity hook: one forward-dynamics evaluation + Euler step for a single state through the same
+ * device code the rollout kernel runs. qacc[nv], residual[nr], next_qpos[nq], next_qvel[nv], counts[4] =
+ * {ncon, nefc, solver iterations, warning}. */
+int mjpc_b200_step_debug(mjpc_b200_t* h, const float* qpos, const float* qvel, const float* ctrl,
+                         const float* mocap, double time, const float* warmstart, float* qacc, float* residual,
+                         float* next_qpos, float* next_qvel, float* qM, float* efc_force, int* counts);
+
+/* Number of CUDA kernels this handle has launched so far (bench.py reports it as gpu_launches). */
+int64_t mjpc_b200_launch_count(const mjpc_b200_t* h);
+/* Device time (ms, CUDA events on the engine's stream) of the kernels of the last call. */
+float mjpc_b200_last_kernel_ms(const mjpc_b200_t* h);
+
+/* Resident-input path used for the device-timed bench value: upload once, then launch repeatedly. */
+int mjpc_b200_upload_spline_inputs(mjpc_b200_t* h, const float* state, double time, const float* mocap,
+                                   const float* userdata, const float* knots, const double* knot_times, int interp,
+                                   int P, int N, int H);
+int mjpc_b200_launch_resident(mjpc_b200_t* h);          /* async on the engine stream */
+int mjpc_b200_sync(mjpc_b200_t* h);
+int mjpc_b200_read_returns(mjpc_b200_t* h, float* returns, uint8_t* failure, int* order);
+/* Raw stream / device pointers for multi-GPU plumbing (NCCL all-gather of returns runs on this stream). */
+void* mjpc_b200_stream(mjpc_b200_t* h);
+float* mjpc_b200_device_returns(mjpc_b200_t* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MJPC_B200_H_ */

@@ -1,0 +1,223 @@
+// dev_data.cuh - per-trajectory simulation state ("mjData") as it lives in shared memory, one block of
+// floats per warp, plus the small device math kit.  One warp owns one trajectory: every array below is
+// private to that warp, phases are separated by __syncwarp(), and lanes split work by body / dof /
+// constraint row / matrix entry.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "dev_model.h"
+
+namespace mjpc_dev {
+
+// name, element count (expression over M = DevModel, P = spline points)
+#define MJPC_D_ARRAYS(X)                                                                                          \
+  X(qpos, M.nq) X(qvel, M.nv) X(ctrl, M.nu) X(qacc, M.nv) X(qacc_warmstart, M.nv) X(mocap_pos, 3 * M.nmocap)      \
+  X(mocap_quat, 4 * M.nmocap) X(xpos, 3 * M.nbody) X(xquat, 4 * M.nbody) X(xmat, 9 * M.nbody)                     \
+  X(xipos, 3 * M.nbody) X(ximat, 9 * M.nbody) X(xanchor, 3 * M.njnt) X(xaxis, 3 * M.njnt)                         \
+  X(geom_xpos, 3 * M.ngeom) X(geom_xmat, 9 * M.ngeom) X(site_xpos, 3 * M.nsite) X(subtree_com, 3 * M.nbody)       \
+  X(cinert, 10 * M.nbody) X(crb, 10 * M.nbody) X(cdof, 6 * M.nv) X(cdof_dot, 6 * M.nv) X(cvel, 6 * M.nbody)       \
+  X(cacc, 6 * M.nbody) X(cfrc, 6 * M.nbody) X(cfrc_sub, 6 * M.nbody) X(subtree_linvel, 3 * M.nbody)               \
+  X(body_linvel, 3 * M.nbody) X(qM, M.nv * M.nv) X(qLD, M.nv * M.nv) X(qH, M.nv * M.nv) X(dofbuf, 6 * M.nv)       \
+  X(ldinv, M.nv) X(hinv, M.nv) X(qfrc_bias, M.nv) X(qfrc_passive, M.nv) X(qfrc_actuator, M.nv)                    \
+  X(qfrc_smooth, M.nv) X(qacc_smooth, M.nv) X(qfrc_constraint, M.nv) X(actuator_force, M.nu) X(Ma, M.nv)          \
+  X(grad, M.nv) X(search, M.nv) X(Mv, M.nv) X(vtmp, M.nv) X(con_dist, M.maxcon) X(con_pos, 3 * M.maxcon)          \
+  X(con_frame, 9 * M.maxcon) X(con_friction, 5 * M.maxcon) X(con_solref, 2 * M.maxcon)                            \
+  X(con_solimp, 5 * M.maxcon) X(con_mu, M.maxcon) X(con_margin, M.maxcon) X(con_dim, M.maxcon)                    \
+  X(con_g1, M.maxcon) X(con_g2, M.maxcon) X(con_adr, M.maxcon) X(efc_J, M.maxefc * M.nv)                          \
+  X(efc_W, M.maxefc * M.nv) X(efc_pos, M.maxefc) X(efc_margin, M.maxefc) X(efc_diag, M.maxefc)                    \
+  X(efc_R, M.maxefc) X(efc_D, M.maxefc) X(efc_K, M.maxefc) X(efc_B, M.maxefc) X(efc_imp, M.maxefc)                \
+  X(efc_aref, M.maxefc) X(efc_force, M.maxefc) X(efc_jar, M.maxefc) X(efc_Jv, M.maxefc) X(efc_floss, M.maxefc)    \
+  X(efc_type, M.maxefc) X(efc_id, M.maxefc) X(efc_state, M.maxefc) X(efc_item, M.maxefc) X(efc_hc, 36 * M.maxcon) \
+  X(residual, M.num_residual) X(knots, P * M.nu) X(knot_times, P) X(xnom, M.nq + M.nv) X(dx, 2 * M.nv)
+
+enum DataArrayId {
+#define X(n, sz) D_##n,
+  MJPC_D_ARRAYS(X)
+#undef X
+      D_COUNT
+};
+
+struct DevLayout {
+  int off[D_COUNT];
+  int total;  // floats per warp (multiple of 4)
+};
+
+inline DevLayout make_layout(const DevModel& M, int P) {
+  DevLayout L;
+  int o = 0;
+#define X(n, sz) L.off[D_##n] = o; o += (((sz) + 3) / 4) * 4;
+  MJPC_D_ARRAYS(X)
+#undef X
+  L.total = o;
+  return L;
+}
+
+#ifdef __CUDACC__
+constexpr unsigned kFull = 0xffffffffu;
+constexpr float kMinVal = 1e-15f;
+constexpr float kMaxVal = 1e10f;
+constexpr float kMinImp = 0.0001f, kMaxImp = 0.9999f, kMinMu = 1e-5f;
+enum { CNSTR_FRICTION_DOF = 0, CNSTR_LIMIT_JOINT, CNSTR_CONTACT_FRICTIONLESS, CNSTR_CONTACT_ELLIPTIC };
+enum { STATE_SATISFIED = 0, STATE_QUADRATIC, STATE_LINEARNEG, STATE_LINEARPOS, STATE_CONE };
+
+struct Ctx {
+  const DevModel* M;
+  const DevLayout* L;
+  const float* mf;  // model floats (shared memory)
+  const int* mi;    // model ints (shared memory)
+  float* d;         // this warp's data block (shared memory)
+  int lane;
+  int ncon, nefc, nitem, niter;
+  int warn;
+  float time;
+};
+#define MF(n) (c.mf + c.M->fo[F_##n])
+#define MI(n) (c.mi + c.M->io[I_##n])
+#define DF(n) (c.d + c.L->off[D_##n])
+#define DI(n) (reinterpret_cast<int*>(c.d + c.L->off[D_##n]))
+
+// ---------------------------------------------------------------------------------------- small math
+__device__ __forceinline__ float dot3(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+__device__ __forceinline__ void cross3(float* r, const float* a, const float* b) {
+  float x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+__device__ __forceinline__ float norm3(const float* a) { return sqrtf(dot3(a, a)); }
+__device__ __forceinline__ float normalize3(float* a) {
+  float n = norm3(a);
+  if (n < kMinVal) { a[0] = 1; a[1] = 0; a[2] = 0; return n; }
+  a[0] /= n; a[1] /= n; a[2] /= n;
+  return n;
+}
+__device__ __forceinline__ void quat_mul(float* r, const float* a, const float* b) {
+  float w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  float x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  float y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+  float z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+  r[0] = w; r[1] = x; r[2] = y; r[3] = z;
+}
+__device__ __forceinline__ void quat_normalize(float* q) {
+  float n = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  if (n < kMinVal) { q[0] = 1; q[1] = q[2] = q[3] = 0; return; }
+  q[0] /= n; q[1] /= n; q[2] /= n; q[3] /= n;
+}
+__device__ __forceinline__ void quat2mat(float* m, const float* q) {
+  float w = q[0], x = q[1], y = q[2], z = q[3];
+  m[0] = w * w + x * x - y * y - z * z; m[1] = 2 * (x * y - w * z); m[2] = 2 * (x * z + w * y);
+  m[3] = 2 * (x * y + w * z); m[4] = w * w - x * x + y * y - z * z; m[5] = 2 * (y * z - w * x);
+  m[6] = 2 * (x * z - w * y); m[7] = 2 * (y * z + w * x); m[8] = w * w - x * x - y * y + z * z;
+}
+__device__ __forceinline__ void rot_vec(float* r, const float* m, const float* v) {
+  float x = m[0] * v[0] + m[1] * v[1] + m[2] * v[2], y = m[3] * v[0] + m[4] * v[1] + m[5] * v[2],
+        z = m[6] * v[0] + m[7] * v[1] + m[8] * v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+__device__ __forceinline__ void rot_vec_T(float* r, const float* m, const float* v) {
+  float x = m[0] * v[0] + m[3] * v[1] + m[6] * v[2], y = m[1] * v[0] + m[4] * v[1] + m[7] * v[2],
+        z = m[2] * v[0] + m[5] * v[1] + m[8] * v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+__device__ __forceinline__ void axis_angle_quat(float* q, const float* axis, float angle) {
+  float s, co;
+  sincosf(angle * 0.5f, &s, &co);
+  q[0] = co; q[1] = axis[0] * s; q[2] = axis[1] * s; q[3] = axis[2] * s;
+}
+__device__ __forceinline__ void quat_integrate(float* q, const float* w, float h) {
+  float ax[3] = {w[0], w[1], w[2]};
+  float n = norm3(ax);
+  if (n < kMinVal) return;
+  ax[0] /= n; ax[1] /= n; ax[2] /= n;
+  float dq[4], r[4];
+  axis_angle_quat(dq, ax, n * h);
+  quat_mul(r, q, dq);
+  quat_normalize(r);
+  q[0] = r[0]; q[1] = r[1]; q[2] = r[2]; q[3] = r[3];
+}
+__device__ __forceinline__ void cross_motion(float* r, const float* v, const float* m) {
+  float a[3], b[3], cc[3];
+  cross3(a, v, m); cross3(b, v, m + 3); cross3(cc, v + 3, m);
+  for (int k = 0; k < 3; k++) { r[k] = a[k]; r[3 + k] = b[k] + cc[k]; }
+}
+__device__ __forceinline__ void cross_force(float* r, const float* v, const float* f) {
+  float a[3], b[3], cc[3];
+  cross3(a, v, f); cross3(b, v + 3, f + 3); cross3(cc, v, f + 3);
+  for (int k = 0; k < 3; k++) { r[k] = a[k] + b[k]; r[3 + k] = cc[k]; }
+}
+__device__ __forceinline__ void mul_inert_vec(float* r, const float* I, const float* v) {
+  const float* w = v; const float* l = v + 3; const float* mo = I + 6;
+  float a[3], b[3];
+  cross3(a, mo, l); cross3(b, mo, w);
+  r[0] = I[0] * w[0] + I[3] * w[1] + I[4] * w[2] + a[0];
+  r[1] = I[3] * w[0] + I[1] * w[1] + I[5] * w[2] + a[1];
+  r[2] = I[4] * w[0] + I[5] * w[1] + I[2] * w[2] + a[2];
+  r[3] = I[9] * l[0] - b[0]; r[4] = I[9] * l[1] - b[1]; r[5] = I[9] * l[2] - b[2];
+}
+__device__ __forceinline__ void make_frame(float* f) {
+  float* x = f; float* y = f + 3; float* z = f + 6;
+  if (x[1] > -0.5f && x[1] < 0.5f) { y[0] = 0; y[1] = 1; y[2] = 0; } else { y[0] = 0; y[1] = 0; y[2] = 1; }
+  float dd = dot3(x, y);
+  for (int k = 0; k < 3; k++) y[k] -= dd * x[k];
+  normalize3(y);
+  cross3(z, x, y);
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int n = __shfl_up_sync(kFull, v, o);
+    if (lane >= o) v += n;
+  }
+  return v;
+}
+
+// ---- warp-cooperative dense Cholesky (left-looking), A = L L^T in place (lower), n x n row-major in
+// shared memory; inv[n] receives 1/L[i][i].  All 32 lanes must call.
+__device__ __noinline__ void warp_chol(float* A, float* inv, int n, int lane) {
+  for (int j = 0; j < n; j++) {
+    float piv = 0.f;
+    for (int base = j; base < n; base += 32) {
+      int i = base + lane;
+      float s = 0.f;
+      if (i < n) {
+        s = A[i * n + j];
+        for (int k = 0; k < j; k++) s -= A[i * n + k] * A[j * n + k];
+      }
+      if (base == j) {
+        piv = __shfl_sync(kFull, s, 0);
+        if (piv < kMinVal) piv = kMinVal;
+        piv = sqrtf(piv);
+      }
+      if (i < n) A[i * n + j] = (i == j) ? piv : s / piv;
+    }
+    if (lane == 0) inv[j] = 1.0f / piv;
+    __syncwarp();
+  }
+}
+// solve L L^T x = b; x and b in shared memory (may alias); n <= 64
+__device__ __noinline__ void warp_chol_solve(float* x, const float* Lm, const float* inv, const float* b, int n,
+                                             int lane) {
+  float r0 = lane < n ? b[lane] : 0.f;
+  float r1 = lane + 32 < n ? b[lane + 32] : 0.f;
+  for (int i = 0; i < n; i++) {  // forward: L y = b
+    float yi = __shfl_sync(kFull, i < 32 ? r0 : r1, i & 31) * inv[i];
+    if (lane == (i & 31)) { if (i < 32) r0 = yi; else r1 = yi; }
+    if (lane > i && lane < n) r0 -= Lm[lane * n + i] * yi;
+    if (lane + 32 > i && lane + 32 < n) r1 -= Lm[(lane + 32) * n + i] * yi;
+  }
+  for (int i = n - 1; i >= 0; i--) {  // backward: L^T x = y
+    float xi = __shfl_sync(kFull, i < 32 ? r0 : r1, i & 31) * inv[i];
+    if (lane == (i & 31)) { if (i < 32) r0 = xi; else r1 = xi; }
+    if (lane < i) r0 -= Lm[i * n + lane] * xi;
+    if (lane + 32 < i) r1 -= Lm[i * n + lane + 32] * xi;
+  }
+  if (lane < n) x[lane] = r0;
+  if (lane + 32 < n) x[lane + 32] = r1;
+  __syncwarp();
+}
+#endif  // __CUDACC__
+
+}  // namespace mjpc_dev

@@ -1,0 +1,1147 @@
+// dev_physics.cuh - warp-cooperative forward dynamics: the device restatement of what MJPC reaches through
+// mj_step / mj_forward (mjpc/trajectory.cc:158,198).  Same pipeline and constants as the CPU oracle
+// (oracle/physics.h) but laid out for 32 lanes: lanes split bodies of one tree level, dofs, candidate geom
+// pairs, constraint rows and matrix entries; reductions use warp shuffles; every phase ends in __syncwarp().
+#pragma once
+#include "dev_data.cuh"
+
+namespace mjpc_dev {
+
+// ------------------------------------------------------------------------------------------ position stage
+__device__ __noinline__ void k_kinematics(Ctx& c) {
+  const DevModel& M = *c.M;
+  const int lane = c.lane;
+  float *xpos = DF(xpos), *xquat = DF(xquat), *xmat = DF(xmat), *xipos = DF(xipos), *ximat = DF(ximat);
+  float *xanchor = DF(xanchor), *xaxis = DF(xaxis);
+  const float* qpos = DF(qpos);
+  if (lane < 3) { xpos[lane] = 0; xipos[lane] = 0; }
+  if (lane < 4) xquat[lane] = lane == 0 ? 1.f : 0.f;
+  if (lane < 9) { float v = (lane % 4 == 0) ? 1.f : 0.f; xmat[lane] = v; ximat[lane] = v; }
+  __syncwarp();
+  const int *level_adr = MI(level_adr), *level_body = MI(level_body), *parentid = MI(body_parentid),
+            *mocapid = MI(body_mocapid), *jntadr = MI(body_jntadr), *jntnum = MI(body_jntnum),
+            *jtype = MI(jnt_type), *jqadr = MI(jnt_qposadr);
+  const float *bpos = MF(body_pos), *bquat = MF(body_quat), *bipos = MF(body_ipos), *biquat = MF(body_iquat),
+              *jpos = MF(jnt_pos), *jaxis = MF(jnt_axis), *qpos0 = MF(qpos0);
+  for (int l = 0; l < M.nlevel; l++) {
+    const int a = level_adr[l], e = level_adr[l + 1];
+    for (int k = a + lane; k < e; k += 32) {
+      const int b = level_body[k];
+      const int p = parentid[b];
+      float pos[3], quat[4];
+      if (mocapid[b] >= 0) {
+        const int mk = mocapid[b];
+        for (int q = 0; q < 3; q++) pos[q] = DF(mocap_pos)[3 * mk + q];
+        for (int q = 0; q < 4; q++) quat[q] = DF(mocap_quat)[4 * mk + q];
+        quat_normalize(quat);
+      } else {
+        rot_vec(pos, xmat + 9 * p, bpos + 3 * b);
+        for (int q = 0; q < 3; q++) pos[q] += xpos[3 * p + q];
+        quat_mul(quat, xquat + 4 * p, bquat + 4 * b);
+      }
+      for (int j = jntadr[b]; j < jntadr[b] + jntnum[b]; j++) {
+        const int qa = jqadr[j];
+        const int t = jtype[j];
+        if (t == JNT_FREE) {
+          for (int q = 0; q < 3; q++) pos[q] = qpos[qa + q];
+          for (int q = 0; q < 4; q++) quat[q] = qpos[qa + 3 + q];
+          quat_normalize(quat);
+          for (int q = 0; q < 3; q++) { xanchor[3 * j + q] = pos[q]; xaxis[3 * j + q] = (q == 2) ? 1.f : 0.f; }
+          continue;
+        }
+        float R[9], anchor[3], axis[3];
+        quat2mat(R, quat);
+        rot_vec(anchor, R, jpos + 3 * j);
+        for (int q = 0; q < 3; q++) anchor[q] += pos[q];
+        rot_vec(axis, R, jaxis + 3 * j);
+        for (int q = 0; q < 3; q++) { xanchor[3 * j + q] = anchor[q]; xaxis[3 * j + q] = axis[q]; }
+        if (t == JNT_SLIDE) {
+          const float qq = qpos[qa] - qpos0[qa];
+          for (int q = 0; q < 3; q++) pos[q] += axis[q] * qq;
+        } else {
+          float ql[4], qn[4], off[3];
+          if (t == JNT_HINGE) {
+            axis_angle_quat(ql, jaxis + 3 * j, qpos[qa] - qpos0[qa]);
+          } else {
+            for (int q = 0; q < 4; q++) ql[q] = qpos[qa + q];
+            quat_normalize(ql);
+          }
+          quat_mul(qn, quat, ql);
+          for (int q = 0; q < 4; q++) quat[q] = qn[q];
+          quat2mat(R, quat);
+          rot_vec(off, R, jpos + 3 * j);
+          for (int q = 0; q < 3; q++) pos[q] = anchor[q] - off[q];
+        }
+      }
+      quat_normalize(quat);
+      for (int q = 0; q < 3; q++) xpos[3 * b + q] = pos[q];
+      for (int q = 0; q < 4; q++) xquat[4 * b + q] = quat[q];
+      float R[9], ip[3], iq[4];
+      quat2mat(R, quat);
+      for (int q = 0; q < 9; q++) xmat[9 * b + q] = R[q];
+      rot_vec(ip, R, bipos + 3 * b);
+      for (int q = 0; q < 3; q++) xipos[3 * b + q] = pos[q] + ip[q];
+      quat_mul(iq, quat, biquat + 4 * b);
+      quat2mat(R, iq);
+      for (int q = 0; q < 9; q++) ximat[9 * b + q] = R[q];
+    }
+    __syncwarp();
+  }
+  const int* gbody = MI(geom_bodyid);
+  const float *gpos = MF(geom_pos), *gquat = MF(geom_quat);
+  float *gxpos = DF(geom_xpos), *gxmat = DF(geom_xmat);
+  for (int g = lane; g < M.ngeom; g += 32) {
+    const int b = gbody[g];
+    float p[3], q[4], R[9];
+    rot_vec(p, xmat + 9 * b, gpos + 3 * g);
+    for (int k = 0; k < 3; k++) gxpos[3 * g + k] = xpos[3 * b + k] + p[k];
+    quat_mul(q, xquat + 4 * b, gquat + 4 * g);
+    quat2mat(R, q);
+    for (int k = 0; k < 9; k++) gxmat[9 * g + k] = R[k];
+  }
+  const int* sbody = MI(site_bodyid);
+  const float* spos = MF(site_pos);
+  float* sxpos = DF(site_xpos);
+  for (int s = lane; s < M.nsite; s += 32) {
+    const int b = sbody[s];
+    float p[3];
+    rot_vec(p, xmat + 9 * b, spos + 3 * s);
+    for (int k = 0; k < 3; k++) sxpos[3 * s + k] = xpos[3 * b + k] + p[k];
+  }
+  __syncwarp();
+}
+
+__device__ __noinline__ void k_com_pos(Ctx& c) {
+  const DevModel& M = *c.M;
+  const int lane = c.lane;
+  const int *subend = MI(body_subtreeend), *rootid = MI(body_rootid);
+  const float *mass = MF(body_mass), *submass = MF(body_subtreemass), *inertia = MF(body_inertia);
+  float *scom = DF(subtree_com), *xipos = DF(xipos), *ximat = DF(ximat), *cinert = DF(cinert);
+  // DFS body order: the subtree of b is the contiguous id range [b, subend[b])
+  for (int b = lane; b < M.nbody; b += 32) {
+    float s[3] = {0, 0, 0};
+    if (submass[b] < kMinVal) {
+      for (int k = 0; k < 3; k++) s[k] = xipos[3 * b + k];
+    } else {
+      for (int q = subend[b] - 1; q >= b; q--)
+        for (int k = 0; k < 3; k++) s[k] += mass[q] * xipos[3 * q + k];
+      for (int k = 0; k < 3; k++) s[k] /= submass[b];
+    }
+    for (int k = 0; k < 3; k++) scom[3 * b + k] = s[k];
+  }
+  __syncwarp();
+  for (int b = 1 + lane; b < M.nbody; b += 32) {
+    const float* R = ximat + 9 * b;
+    const float* I = inertia + 3 * b;
+    const float m = mass[b];
+    float o[3];
+    for (int k = 0; k < 3; k++) o[k] = xipos[3 * b + k] - scom[3 * rootid[b] + k];
+    float W[9];
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++)
+        W[3 * i + j] = R[3 * i] * I[0] * R[3 * j] + R[3 * i + 1] * I[1] * R[3 * j + 1] + R[3 * i + 2] * I[2] * R[3 * j + 2];
+    const float oo = dot3(o, o);
+    float* ci = cinert + 10 * b;
+    ci[0] = W[0] + m * (oo - o[0] * o[0]); ci[1] = W[4] + m * (oo - o[1] * o[1]); ci[2] = W[8] + m * (oo - o[2] * o[2]);
+    ci[3] = W[1] - m * o[0] * o[1]; ci[4] = W[2] - m * o[0] * o[2]; ci[5] = W[5] - m * o[1] * o[2];
+    ci[6] = m * o[0]; ci[7] = m * o[1]; ci[8] = m * o[2]; ci[9] = m;
+  }
+  const int *jbody = MI(jnt_bodyid), *jdof = MI(jnt_dofadr), *jtype = MI(jnt_type);
+  float *cdof = DF(cdof), *xanchor = DF(xanchor), *xaxis = DF(xaxis), *xmat = DF(xmat);
+  for (int j = lane; j < M.njnt; j += 32) {
+    const int b = jbody[j];
+    int da = jdof[j];
+    float off[3];
+    for (int k = 0; k < 3; k++) off[k] = scom[3 * rootid[b] + k] - xanchor[3 * j + k];
+    const float* ax = xaxis + 3 * j;
+    const int t = jtype[j];
+    if (t == JNT_FREE) {
+      for (int k = 0; k < 3; k++) {
+        float* cd = cdof + 6 * (da + k);
+        for (int q = 0; q < 6; q++) cd[q] = 0;
+        cd[3 + k] = 1;
+      }
+      da += 3;
+    }
+    if (t == JNT_FREE || t == JNT_BALL) {
+      for (int k = 0; k < 3; k++) {
+        float* cd = cdof + 6 * (da + k);
+        float col[3] = {xmat[9 * b + k], xmat[9 * b + 3 + k], xmat[9 * b + 6 + k]};
+        for (int q = 0; q < 3; q++) cd[q] = col[q];
+        cross3(cd + 3, col, off);
+      }
+    } else if (t == JNT_SLIDE) {
+      float* cd = cdof + 6 * da;
+      for (int q = 0; q < 3; q++) { cd[q] = 0; cd[3 + q] = ax[q]; }
+    } else {
+      float* cd = cdof + 6 * da;
+      for (int q = 0; q < 3; q++) cd[q] = ax[q];
+      cross3(cd + 3, ax, off);
+    }
+  }
+  __syncwarp();
+}
+
+// composite rigid body inertia -> dense joint-space inertia qM, then its Cholesky factor qLD
+__device__ __noinline__ void k_crb(Ctx& c) {
+  const DevModel& M = *c.M;
+  const int lane = c.lane, nv = M.nv;
+  const int* subend = MI(body_subtreeend);
+  float *cinert = DF(cinert), *crb = DF(crb), *cdof = DF(cdof), *dofbuf = DF(dofbuf), *qM = DF(qM), *qLD = DF(qLD);
+  for (int b = 1 + lane; b < M.nbody; b += 32) {
+    float s[10];
+    for (int k = 0; k < 10; k++) s[k] = 0;
+    for (int q = subend[b] - 1; q >= b; q--)
+      for (int k = 0; k < 10; k++) s[k] += cinert[10 * q + k];
+    for (int k = 0; k < 10; k++) crb[10 * b + k] = s[k];
+  }
+  __syncwarp();
+  const int* dbody = MI(dof_bodyid);
+  for (int i = lane; i < nv; i += 32) mul_inert_vec(dofbuf + 6 * i, crb + 10 * dbody[i], cdof + 6 * i);
+  __syncwarp();
+  const int *mpi = MI(mpair_i), *mpj = MI(mpair_j);
+  const float* arm = MF(dof_armature);
+  for (int k = lane; k < M.nmpair; k += 32) {
+    const int i = mpi[k], j = mpj[k];
+    float s = 0;
+    for (int q = 0; q < 6; q++) s += cdof[6 * j + q] * dofbuf[6 * i + q];
+    if (i == j) s += arm[i];
+    qM[i * nv + j] = s; qM[j * nv + i] = s;
+  }
+  __syncwarp();
+  // entries of qM outside the (dof, ancestor) pattern stay zero (zeroed once per rollout); the factor
+  // fills in, so the whole matrix is re-copied before every factorisation
+  for (int w = lane; w < nv * nv; w += 32) qLD[w] = qM[w];
+  __syncwarp();
+  warp_chol(qLD, DF(ldinv), nv, lane);
+}
+
+// ------------------------------------------------------------------------------------------ collision
+struct RawContact { float dist, pos[3], normal[3]; };
+
+__device__ __forceinline__ int collide_plane_sphere(RawContact* out, const float* pp, const float* pm,
+                                                    const float* sp, float r) {
+  float n[3] = {pm[2], pm[5], pm[8]};
+  float diff[3] = {sp[0] - pp[0], sp[1] - pp[1], sp[2] - pp[2]};
+  float dist = dot3(diff, n) - r;
+  out->dist = dist;
+  for (int k = 0; k < 3; k++) { out->normal[k] = n[k]; out->pos[k] = sp[k] - n[k] * (r + dist * 0.5f); }
+  return 1;
+}
+__device__ __forceinline__ int collide_plane_capsule(RawContact* out, const float* pp, const float* pm,
+                                                     const float* cp, const float* cm, const float* size) {
+  float axis[3] = {cm[2], cm[5], cm[8]};
+  int n = 0;
+  for (int s = -1; s <= 1; s += 2) {
+    float e[3];
+    for (int k = 0; k < 3; k++) e[k] = cp[k] + (float)s * size[1] * axis[k];
+    n += collide_plane_sphere(out + n, pp, pm, e, size[0]);
+  }
+  return n;
+}
+__device__ __forceinline__ int collide_plane_box(RawContact* out, const float* pp, const float* pm, const float* bp,
+                                                 const float* bm, const float* size, float margin) {
+  float nrm[3] = {pm[2], pm[5], pm[8]};
+  int n = 0;
+  for (int k = 0; k < 8 && n < 4; k++) {
+    float loc[3] = {(k & 1 ? size[0] : -size[0]), (k & 2 ? size[1] : -size[1]), (k & 4 ? size[2] : -size[2])};
+    float w[3], corner[3], diff[3];
+    rot_vec(w, bm, loc);
+    for (int q = 0; q < 3; q++) { corner[q] = bp[q] + w[q]; diff[q] = corner[q] - pp[q]; }
+    float dist = dot3(diff, nrm);
+    if (dist > margin) continue;
+    out[n].dist = dist;
+    for (int q = 0; q < 3; q++) { out[n].normal[q] = nrm[q]; out[n].pos[q] = corner[q] - nrm[q] * dist * 0.5f; }
+    n++;
+  }
+  return n;
+}
+__device__ __forceinline__ int collide_plane_cylinder(RawContact* out, const float* pp, const float* pm,
+                                                      const float* cp, const float* cm, const float* size,
+                                                      float margin) {
+  float nrm[3] = {pm[2], pm[5], pm[8]};
+  float axis[3] = {cm[2], cm[5], cm[8]};
+  const float r = size[0], h = size[1];
+  float prj = dot3(axis, nrm);
+  if (prj > 0) { for (int k = 0; k < 3; k++) axis[k] = -axis[k]; prj = -prj; }
+  float vec[3];
+  for (int k = 0; k < 3; k++) vec[k] = -nrm[k] + axis[k] * prj;
+  float len = norm3(vec);
+  if (len < 1e-6f) { vec[0] = cm[0]; vec[1] = cm[3]; vec[2] = cm[6]; len = 1; }
+  for (int k = 0; k < 3; k++) vec[k] *= r / len;
+  float side[3];
+  cross3(side, vec, axis);
+  float diff[3] = {cp[0] - pp[0], cp[1] - pp[1], cp[2] - pp[2]};
+  const float dist0 = dot3(diff, nrm);
+  int n = 0;
+  for (int k = 0; k < 4; k++) {
+    float cand[3];
+    for (int q = 0; q < 3; q++) {
+      if (k == 0) cand[q] = axis[q] * h + vec[q];
+      else if (k == 1) cand[q] = -axis[q] * h + vec[q];
+      else if (k == 2) cand[q] = axis[q] * h - vec[q] * 0.5f + side[q] * 0.8660254037844386f;
+      else cand[q] = axis[q] * h - vec[q] * 0.5f - side[q] * 0.8660254037844386f;
+    }
+    float dist = dist0 + dot3(cand, nrm);
+    if (dist > margin) continue;
+    out[n].dist = dist;
+    for (int q = 0; q < 3; q++) { out[n].normal[q] = nrm[q]; out[n].pos[q] = cp[q] + cand[q] - nrm[q] * dist * 0.5f; }
+    n++;
+  }
+  return n;
+}
+__device__ __forceinline__ int collide_sphere_sphere(RawContact* out, const float* p1, float r1, const float* p2,
+                                                     float r2) {
+  float dv[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+  float len = norm3(dv);
+  float n[3] = {1, 0, 0};
+  if (len >= kMinVal) { n[0] = dv[0] / len; n[1] = dv[1] / len; n[2] = dv[2] / len; }
+  float dist = len - r1 - r2;
+  out->dist = dist;
+  for (int k = 0; k < 3; k++) { out->normal[k] = n[k]; out->pos[k] = p1[k] + n[k] * (r1 + dist * 0.5f); }
+  return 1;
+}
+__device__ __forceinline__ int collide_sphere_capsule(RawContact* out, const float* sp, float sr, const float* cp,
+                                                      const float* cm, const float* csize) {
+  float axis[3] = {cm[2], cm[5], cm[8]};
+  float dv[3] = {sp[0] - cp[0], sp[1] - cp[1], sp[2] - cp[2]};
+  float x = fmaxf(-csize[1], fminf(csize[1], dot3(dv, axis)));
+  float q[3] = {cp[0] + axis[0] * x, cp[1] + axis[1] * x, cp[2] + axis[2] * x};
+  return collide_sphere_sphere(out, sp, sr, q, csize[0]);
+}
+__device__ __forceinline__ int collide_sphere_box(RawContact* out, const float* sp, float sr, const float* bp,
+                                                  const float* bm, const float* bs) {
+  float dv[3] = {sp[0] - bp[0], sp[1] - bp[1], sp[2] - bp[2]};
+  float loc[3], cl[3];
+  rot_vec_T(loc, bm, dv);
+  bool inside = true;
+  for (int k = 0; k < 3; k++) {
+    cl[k] = fmaxf(-bs[k], fminf(bs[k], loc[k]));
+    if (cl[k] != loc[k]) inside = false;
+  }
+  float nl[3], dist, pl[3];
+  if (!inside) {
+    float dd[3] = {cl[0] - loc[0], cl[1] - loc[1], cl[2] - loc[2]};
+    float len = norm3(dd);
+    for (int k = 0; k < 3; k++) nl[k] = dd[k] / len;
+    dist = len - sr;
+    for (int k = 0; k < 3; k++) pl[k] = cl[k] - nl[k] * dist * 0.5f;
+  } else {
+    int kk = 0;
+    float best = bs[0] - fabsf(loc[0]);
+    for (int k = 1; k < 3; k++) { float g = bs[k] - fabsf(loc[k]); if (g < best) { best = g; kk = k; } }
+    float sgn = loc[kk] >= 0 ? 1.f : -1.f;
+    nl[0] = nl[1] = nl[2] = 0;
+    dist = -best - sr;
+    for (int k = 0; k < 3; k++) pl[k] = loc[k];
+    for (int k = 0; k < 3; k++)
+      if (k == kk) { nl[k] = -sgn; pl[k] = 0.5f * (sgn * bs[k] + loc[k] - sgn * sr); }
+  }
+  float nw[3], pw[3];
+  rot_vec(nw, bm, nl);
+  rot_vec(pw, bm, pl);
+  out->dist = dist;
+  for (int k = 0; k < 3; k++) { out->normal[k] = nw[k]; out->pos[k] = bp[k] + pw[k]; }
+  return 1;
+}
+
+__device__ __noinline__ void k_collision(Ctx& c) {
+  const DevModel& M = *c.M;
+  const int lane = c.lane;
+  c.ncon = 0;
+  if (M.disable_contact) return;
+  const int *pg1 = MI(pair_geom1), *pg2 = MI(pair_geom2), *gtype = MI(geom_type), *gprio = MI(geom_priority),
+            *gcondim = MI(geom_condim);
+  const float *gmargin = MF(geom_margin), *ggap = MF(geom_gap), *gsize = MF(geom_size), *grbound = MF(geom_rbound),
+              *gfric = MF(geom_friction), *gsolmix = MF(geom_solmix), *gsolref = MF(geom_solref),
+              *gsolimp = MF(geom_solimp);
+  const float *gxpos = DF(geom_xpos), *gxmat = DF(geom_xmat);
+  int ncon = 0;
+  for (int base = 0; base < M.npair; base += 32) {
+    const int p = base + lane;
+    RawContact raw[4];
+    int cnt = 0, g1 = 0, g2 = 0;
+    float margin = 0, gap = 0;
+    if (p < M.npair) {
+      g1 = pg1[p]; g2 = pg2[p];
+      const int t1 = gtype[g1], t2 = gtype[g2];
+      margin = fmaxf(gmargin[g1], gmargin[g2]);
+      gap = fmaxf(ggap[g1], ggap[g2]);
+      const float *p1 = gxpos + 3 * g1, *p2 = gxpos + 3 * g2, *m1 = gxmat + 9 * g1, *m2 = gxmat + 9 * g2;
+      const float *s1 = gsize + 3 * g1, *s2 = gsize + 3 * g2;
+      bool pass;
+      float dv[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+      if (t1 == GEOM_PLANE) {
+        float n[3] = {m1[2], m1[5], m1[8]};
+        pass = !(dot3(dv, n) > grbound[g2] + margin);
+      } else {
+        float bound = grbound[g1] + grbound[g2] + margin;
+        pass = !(dot3(dv, dv) > bound * bound);
+      }
+      int n = 0;
+      if (pass) {
+        if (t1 == GEOM_PLANE && t2 == GEOM_SPHERE) n = collide_plane_sphere(raw, p1, m1, p2, s2[0]);
+        else if (t1 == GEOM_PLANE && t2 == GEOM_CAPSULE) n = collide_plane_capsule(raw, p1, m1, p2, m2, s2);
+        else if (t1 == GEOM_PLANE && t2 == GEOM_BOX) n = collide_plane_box(raw, p1, m1, p2, m2, s2, margin);
+        else if (t1 == GEOM_PLANE && t2 == GEOM_CYLINDER) n = collide_plane_cylinder(raw, p1, m1, p2, m2, s2, margin);
+        else if (t1 == GEOM_SPHERE && t2 == GEOM_SPHERE) n = collide_sphere_sphere(raw, p1, s1[0], p2, s2[0]);
+        else if (t1 == GEOM_SPHERE && t2 == GEOM_CAPSULE) n = collide_sphere_capsule(raw, p1, s1[0], p2, m2, s2);
+        else if (t1 == GEOM_SPHERE && t2 == GEOM_BOX) n = collide_sphere_box(raw, p1, s1[0], p2, m2, s2);
+      }
+      for (int k = 0; k < n; k++)
+        if (raw[k].dist < margin) { if (cnt != k) raw[cnt] = raw[k]; cnt++; }
+    }
+    const int incl = warp_incl_scan(cnt, lane);
+    const int total = __shfl_sync(kFull, incl, 31);
+    const int excl = incl - cnt;
+    for (int k = 0; k < cnt; k++) {
+      const int idx = ncon + excl + k;
+      if (idx >= M.maxcon) break;  // capacity: later contacts are dropped (same rule as the oracle)
+      DF(con_dist)[idx] = raw[k].dist;
+      float fr[9];
+      for (int q = 0; q < 3; q++) { DF(con_pos)[3 * idx + q] = raw[k].pos[q]; fr[q] = raw[k].normal[q]; }
+      make_frame(fr);
+      for (int q = 0; q < 9; q++) DF(con_frame)[9 * idx + q] = fr[q];
+      DF(con_margin)[idx] = margin - gap;
+      DI(con_g1)[idx] = g1; DI(con_g2)[idx] = g2;
+      float f3[3], solref[2], solimp[5];
+      int dim;
+      if (gprio[g1] != gprio[g2]) {
+        const int gp = gprio[g1] > gprio[g2] ? g1 : g2;
+        dim = gcondim[gp];
+        for (int q = 0; q < 2; q++) solref[q] = gsolref[2 * gp + q];
+        for (int q = 0; q < 5; q++) solimp[q] = gsolimp[5 * gp + q];
+        for (int q = 0; q < 3; q++) f3[q] = gfric[3 * gp + q];
+      } else {
+        dim = max(gcondim[g1], gcondim[g2]);
+        const float w1 = gsolmix[g1], w2 = gsolmix[g2];
+        float mix;
+        if (w1 >= kMinVal && w2 >= kMinVal) mix = w1 / (w1 + w2);
+        else if (w1 < kMinVal && w2 < kMinVal) mix = 0.5f;
+        else mix = w1 < kMinVal ? 0.f : 1.f;
+        const float *r1 = gsolref + 2 * g1, *r2 = gsolref + 2 * g2;
+        if (r1[0] > 0 && r2[0] > 0) { for (int q = 0; q < 2; q++) solref[q] = mix * r1[q] + (1 - mix) * r2[q]; }
+        else { for (int q = 0; q < 2; q++) solref[q] = fminf(r1[q], r2[q]); }
+        for (int q = 0; q < 5; q++) solimp[q] = mix * gsolimp[5 * g1 + q] + (1 - mix) * gsolimp[5 * g2 + q];
+        for (int q = 0; q < 3; q++) f3[q] = fmaxf(gfric[3 * g1 + q], gfric[3 * g2 + q]);
+      }
+      for (int q = 0; q < 3; q++) f3[q] = fmaxf(f3[q], kMinMu);
+      float* cf = DF(con_friction) + 5 * idx;
+      cf[0] = cf[1] = f3[0]; cf[2] = f3[1]; cf[3] = cf[4] = f3[2];
+      for (int q = 0; q < 2; q++) DF(con_solref)[2 * idx + q] = solref[q];
+      for (int q = 0; q < 5; q++) DF(con_solimp)[5 * idx + q] = solimp[q];
+      DI(con_dim)[idx] = dim;
+      DF(con_mu)[idx] = 0;
+      DI(con_adr)[idx] = -1;
+    }
+    ncon = min(ncon + total, M.maxcon);
+    __syncwarp();
+  }
+  c.ncon = ncon;
+}
+
+// ------------------------------------------------------------------------------------------ constraints
+__device__ __forceinline__ float get_impedance(const float* solimp, float pos, float margin) {
+  const float dmin = fminf(kMaxImp, fmaxf(kMinImp, solimp[0]));
+  const float dmax = fminf(kMaxImp, fmaxf(kMinImp, solimp[1]));
+  const float width = fmaxf(0.f, solimp[2]);
+  const float mid = fminf(kMaxImp, fmaxf(kMinImp, solimp[3]));
+  const float power = fmaxf(1.f, solimp[4]);
+  if (dmin == dmax || width <= kMinVal) return 0.5f * (dmin + dmax);
+  float x = (pos - margin) / width;
+  if (x < 0) x = -x;
+  if (x >= 1) return dmax;
+  if (x == 0) return dmin;
+  float y;
+  if (power == 1) y = x;
+  else if (x <= mid) y = powf(x, power) / powf(mid, power - 1);
+  else y = 1 - powf(1 - x, power) / powf(1 - mid, power - 1);
+  return dmin + y * (dmax - dmin);
+}
+
+__device__ __noinline__ void k_make_constraint(Ctx& c) {
+  const DevModel& M = *c.M;
+  const int lane = c.lane, nv = M.nv;
+  float *J = DF(efc_J), *epos = DF(efc_pos), *emargin = DF(efc_margin), *ediag = DF(efc_diag), *efloss = DF(efc_floss);
+  int *etype = DI(efc_type), *eid = DI(efc_id), *eitem = DI(efc_item);
+  const float *dinvw = MF(dof_invweight0), *qpos = DF(qpos);
+  int ne = 0, nitem = 0;
+  // --- dof friction loss rows (static list)
+  {
+    const int* fl = MI(floss_dof);
+    const float* flv = MF(dof_frictionloss);
+    const int nf = M.nfloss;
+    for (int k = lane; k < nf * nv; k += 32) J[k] = 0;
+    __syncwarp();
+    for (int k = lane; k < nf; k += 32) {
+      const int dof = fl[k];
+      J[k * nv + dof] = 1;
+      epos[k] = 0; emargin[k] = 0; ediag[k] = dinvw[dof]; etype[k] = CNSTR_FRICTION_DOF; eid[k] = dof;
+      efloss[k] = flv[dof]; eitem[k] = k;
+    }
+    ne = nf; nitem = nf;
+  }
+  // --- joint limits (slide / hinge): lane per limited joint, ordered compaction
+  {
+    const int *lj = MI(limit_jnt), *jqadr = MI(jnt_qposadr), *jdadr = MI(jnt_dofadr);
+    const float *jrange = MF(jnt_range), *jmargin = MF(jnt_margin);
+    for (int base = 0; base < M.nlimit; base += 32) {
+      const int k = base + lane;
+      int cnt = 0, j = 0;
+      float dist[2], sgn[2];
+      if (k < M.nlimit) {
+        j = lj[k];
+        const float q = qpos[jqadr[j]];
+        for (int side = -1; side <= 1; side += 2) {
+          const float dd = side * (jrange[2 * j + (side + 1) / 2] - q);
+          if (dd < jmargin[j]) { dist[cnt] = dd; sgn[cnt] = (float)-side; cnt++; }
+        }
+      }
+      const int incl = warp_incl_scan(cnt, lane);
+      const int total = __shfl_sync(kFull, incl, 31);
+      for (int q = 0; q < cnt; q++) {
+        const int r = ne + incl - cnt + q;
+        if (r >= M.maxefc) break;
+        for (int i = 0; i < nv; i++) J[r * nv + i] = 0;
+        J[r * nv + jdadr[j]] = sgn[q];
+        epos[r] = dist[q]; emargin[r] = jmargin[j]; ediag[r] = dinvw[jdadr[j]]; etype[r] = CNSTR_LIMIT_JOINT;
+        eid[r] = j; efloss[r] = 0; eitem[nitem + incl - cnt + q] = r;
+      }
+      const int added = min(total, M.maxefc - ne);
+      ne += added; nitem += added;
+      __syncwarp();
+    }
+  }
+  // --- contacts: row addresses are assigned sequentially (a contact that does not fit is dropped, later
+  //     smaller ones may still fit: same rule as the oracle)
+  int *cadr = DI(con_adr), *cdim = DI(con_dim);
+  if (lane == 0) {
+    int r = ne, it = nitem;
+    for (int ci = 0; ci < c.ncon; ci++) {
+      const int dim = cdim[ci];
+      if (r + dim > M.maxefc) { cadr[ci] = -1; continue; }
+      cadr[ci] = r;
+      eitem[it++] = r;  // one work item per contact
+      r += dim;
+    }
+    ne = r; nitem = it;
+  }
+  ne = __shfl_sync(kFull, ne, 0);
+  nitem = __shfl_sync(kFull, nitem, 0);
+  __syncwarp();
+  {
+    const int *g1a = DI(con_g1), *g2a = DI(con_g2), *gbody = MI(geom_bodyid), *rootid = MI(body_rootid),
+              *mlo = MI(body_dofmask_lo), *mhi = MI(body_dofmask_hi);
+    const float *cpos = DF(con_pos), *cframe = DF(con_frame), *scom = DF(subtree_com), *cdof = DF(cdof),
+                *binvw = MF(body_invweight0);
+    // Jacobian entries: one (contact, dof) pair per lane
+    const int nwork = c.ncon * nv;
+    for (int w = lane; w < nwork; w += 32) {
+      const int ci = w / nv, i = w - ci * nv;
+      const int adr = cadr[ci];
+      if (adr < 0) continue;
+      const int dim = cdim[ci];
+      const int b1 = gbody[g1a[ci]], b2 = gbody[g2a[ci]];
+      float jp[3] = {0, 0, 0}, jr[3] = {0, 0, 0};
+      const float* cd = cdof + 6 * i;
+      for (int s = 0; s < 2; s++) {
+        const int b = s ? b2 : b1;
+        if (b <= 0) continue;
+        const unsigned lo = (unsigned)mlo[b], hi = (unsigned)mhi[b];
+        const bool on = i < 32 ? ((lo >> i) & 1u) : ((hi >> (i - 32)) & 1u);
+        if (!on) continue;
+        float off[3], t[3];
+        for (int q = 0; q < 3; q++) off[q] = cpos[3 * ci + q] - scom[3 * rootid[b] + q];
+        cross3(t, cd, off);
+        const float sg = s ? 1.f : -1.f;
+        for (int q = 0; q < 3; q++) { jp[q] += sg * (cd[3 + q] + t[q]); jr[q] += sg * cd[q]; }
+      }
+      const float* fr = cframe + 9 * ci;
+      for (int k = 0; k < dim; k++) {
+        const float* ax = fr + 3 * (k % 3);
+        J[(adr + k) * nv + i] = k < 3 ? dot3(ax, jp) : dot3(ax, jr);
+      }
+    }
+    // per-row scalars: one contact per lane
+    for (int ci = lane; ci < c.ncon; ci += 32) {
+      const int adr = cadr[ci];
+      if (adr < 0) continue;
+      const int dim = cdim[ci];
+      const int b1 = gbody[g1a[ci]], b2 = gbody[g2a[ci]];
+      const float tran = binvw[2 * b1] + binvw[2 * b2], rot = binvw[2 * b1 + 1] + binvw[2 * b2 + 1];
+      for (int k = 0; k < dim; k++) {
+        const int r = adr + k;
+        epos[r] = k == 0 ? DF(con_dist)[ci] : 0.f;
+        emargin[r] = DF(con_margin)[ci];
+        ediag[r] = k >= 3 ? rot : tran;
+        etype[r] = dim == 1 ? CNSTR_CONTACT_FRICTIONLESS : CNSTR_CONTACT_ELLIPTIC;
+        eid[r] = ci; efloss[r] = 0;
+      }
+    }
+  }
+  __syncwarp();
+  // --- impedance / regularisation per row
+  {
+    float *R = DF(efc_R), *K = DF(efc_K), *B = DF(efc_B), *imp_a = DF(efc_imp);
+    for (int i = lane; i < ne; i += 32) {
+      const float *solref, *solimp;
+      const int id = eid[i];
+      bool friction_row = false;
+      const int ty = etype[i];
+      if (ty == CNSTR_FRICTION_DOF) { solref = MF(dof_solref) + 2 * id; solimp = MF(dof_solimp) + 5 * id; friction_row = true; }
+      else if (ty == CNSTR_LIMIT_JOINT) { solref = MF(jnt_solref) + 2 * id; solimp = MF(jnt_solimp) + 5 * id; }
+      else {
+        solref = DF(con_solref) + 2 * id; solimp = DF(con_solimp) + 5 * id;
+        friction_row = (ty == CNSTR_CONTACT_ELLIPTIC && i > cadr[id]);
+      }
+      const float imp = get_impedance(solimp, epos[i], emargin[i]);
+      const float dmax = fminf(kMaxImp, fmaxf(kMinImp, solimp[1]));
+      float Kk, Bb;
+      if (solref[0] > 0) {
+        float tc = solref[0];
+        const float dr = solref[1];
+        if (!M.disable_refsafe) tc = fmaxf(tc, 2 * M.timestep);
+        Kk = 1 / fmaxf(kMinVal, dmax * dmax * tc * tc * dr * dr);
+        Bb = 2 / fmaxf(kMinVal, dmax * tc);
+      } else {
+        Kk = -solref[0] / fmaxf(kMinVal, dmax * dmax);
+        Bb = -solref[1] / fmaxf(kMinVal, dmax);
+      }
+      if (friction_row) Kk = 0;
+      K[i] = Kk; B[i] = Bb; imp_a[i] = imp;
+      R[i] = fmaxf(kMinVal, (1 - imp) * ediag[i] / imp);
+    }
+    __syncwarp();
+    for (int ci = lane; ci < c.ncon; ci += 32) {
+      const int a = cadr[ci], dim = cdim[ci];
+      if (a < 0 || dim == 1) continue;
+      const float* fr = DF(con_friction) + 5 * ci;
+      R[a + 1] = R[a] / fmaxf(kMinVal, M.impratio);
+      DF(con_mu)[ci] = fr[0] * sqrtf(R[a + 1] / R[a]);
+      for (int j = 1; j < dim - 1; j++) R[a + j + 1] = R[a + 1] * fr[0] * fr[0] / (fr[j] * fr[j]);
+    }
+    __syncwarp();
+    float* D = DF(efc_D);
+    for (int i = lane; i < ne; i += 32) D[i] = 1 / R[i];
+  }
+  c.nefc = ne;
+  c.nitem = nitem;
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------ velocity stage
+__device__ __noinline__ void k_com_vel(Ctx& c) {
+  const DevModel& M = *c.M;
+  const int lane = c.lane;
+  float *cvel = DF(cvel), *cdof = DF(cdof), *cdof_dot = DF(cdof_dot), *qvel = DF(qvel);
+  if (lane < 6) cvel[lane] = 0;
+  __syncwarp();
+  const int *level_adr = MI(level_adr), *level_body = MI(level_body), *parentid = MI(body_parentid),
+            *jntadr = MI(body_jntadr), *jntnum = MI(body_jntnum), *jtype = MI(jnt_type), *jdadr = MI(jnt_dofadr);
+  for (int l = 0; l < M.nlevel; l++) {
+    const int a = level_adr[l], e = level_adr[l + 1];
+    for (int k = a + lane; k < e; k += 32) {
+      const int b = level_body[k];
+      float v[6];
+      for (int q = 0; q < 6; q++) v[q] = cvel[6 * parentid[b] + q];
+      for (int j = jntadr[b]; j < jntadr[b] + jntnum[b]; j++) {
+        int da = jdadr[j];
+        const int t = jtype[j];
+        if (t == JNT_FREE) {
+          for (int kk = 0; kk < 3; kk++)
+            for (int q = 0; q < 6; q++) { cdof_dot[6 * (da + kk) + q] = 0; v[q] += cdof[6 * (da + kk) + q] * qvel[da + kk]; }
+          da += 3;
+        }
+        if (t == JNT_FREE || t == JNT_BALL) {
+          for (int kk = 0; kk < 3; kk++) cross_motion(cdof_dot + 6 * (da + kk), v, cdof + 6 * (da + kk));
+          for (int kk = 0; kk < 3; kk++)
+            for (int q = 0; q < 6; q++) v[q] += cdof[6 * (da + kk) + q] * qvel[da + kk];
+        } else {
+          cross_motion(cdof_dot + 6 * da, v, cdof + 6 * da);
+          for (int q = 0; q < 6; q++) v[q] += cdof[6 * da + q] * qvel[da];
+        }
+      }
+      for (int q = 0; q < 6; q++) cvel[6 * b + q] = v[q];
+    }
+    __syncwarp();
+  }
+  // subtree linear velocity
+  const int *rootid = MI(body_rootid), *subend = MI(body_subtreeend);
+  const float *mass = MF(body_mass), *submass = MF(body_subtreemass);
+  float *blin = DF(body_linvel), *slin = DF(subtree_linvel), *xipos = DF(xipos), *scom = DF(subtree_com);
+  for (int b = lane; b < M.nbody; b += 32) {
+    float off[3], wx[3];
+    for (int q = 0; q < 3; q++) off[q] = xipos[3 * b + q] - scom[3 * rootid[b] + q];
+    cross3(wx, cvel + 6 * b, off);
+    for (int q = 0; q < 3; q++) blin[3 * b + q] = mass[b] * (cvel[6 * b + 3 + q] + wx[q]);
+  }
+  __syncwarp();
+  for (int b = lane; b < M.nbody; b += 32) {
+    float s[3] = {0, 0, 0};
+    for (int q = subend[b] - 1; q >= b; q--)
+      for (int k = 0; k < 3; k++) s[k] += blin[3 * q + k];
+    for (int k = 0; k < 3; k++) slin[3 * b + k] = s[k] / fmaxf(kMinVal, submass[b]);
+  }
+  __syncwarp();
+}
+
+// passive forces, RNE bias, actuation, qfrc_smooth, qacc_smooth
+__device__ __noinline__ void k_smooth_forces(Ctx& c) {
+  const DevModel& M = *c.M;
+  const int lane = c.lane, nv = M.nv;
+  float *qvel = DF(qvel), *qpos = DF(qpos), *passive = DF(qfrc_passive);
+  const float* damping = MF(dof_damping);
+  for (int i = lane; i < nv; i += 32) passive[i] = -damping[i] * qvel[i];
+  __syncwarp();
+  {
+    const float *stiff = MF(jnt_stiffness), *qspring = MF(qpos_spring);
+    const int *jtype = MI(jnt_type), *jdadr = MI(jnt_dofadr), *jqadr = MI(jnt_qposadr);
+    for (int j = lane; j < M.njnt; j += 32) {
+      if (stiff[j] == 0) continue;
+      const int t = jtype[j];
+      if (t == JNT_SLIDE || t == JNT_HINGE) passive[jdadr[j]] -= stiff[j] * (qpos[jqadr[j]] - qspring[jqadr[j]]);
+    }
+  }
+  // RNE with qacc = 0
+  float *cacc = DF(cacc), *cfrc = DF(cfrc), *cfs = DF(cfrc_sub), *cvel = DF(cvel), *cdof_dot = DF(cdof_dot),
+        *cinert = DF(cinert), *cdof = DF(cdof);
+  if (lane < 6) cacc[lane] = lane < 3 ? 0.f : -M.gravity[lane - 3];
+  __syncwarp();
+  const int *level_adr = MI(level_adr), *level_body = MI(level_body), *parentid = MI(body_parentid),
+            *dofadr = MI(body_dofadr), *dofnum = MI(body_dofnum), *subend = MI(body_subtreeend);
+  for (int l = 0; l < M.nlevel; l++) {
+    const int a = level_adr[l], e = level_adr[l + 1];
+    for (int k = a + lane; k < e; k += 32) {
+      const int b = level_body[k];
+      float acc[6];
+      for (int q = 0; q < 6; q++) acc[q] = cacc[6 * parentid[b] + q];
+      for (int i = dofadr[b]; i < dofadr[b] + dofnum[b]; i++)
+        for (int q = 0; q < 6; q++) acc[q] += cdof_dot[6 * i + q] * qvel[i];
+      for (int q = 0; q < 6; q++) cacc[6 * b + q] = acc[q];
+      float f1[6], iv[6], f2[6];
+      mul_inert_vec(f1, cinert + 10 * b, acc);
+      mul_inert_vec(iv, cinert + 10 * b, cvel + 6 * b);
+      cross_force(f2, cvel + 6 * b, iv);
+      for (int q = 0; q < 6; q++) cfrc[6 * b + q] = f1[q] + f2[q];
+    }
+    __syncwarp();
+  }
+  for (int b = 1 + lane; b < M.nbody; b += 32) {
+    float s[6] = {0, 0, 0, 0, 0, 0};
+    for (int q = subend[b] - 1; q >= b; q--)
+      for (int k = 0; k < 6; k++) s[k] += cfrc[6 * q + k];
+    for (int k = 0; k < 6; k++) cfs[6 * b + k] = s[k];
+  }
+  __syncwarp();
+  const int* dbody = MI(dof_bodyid);
+  float* bias = DF(qfrc_bias);
+  for (int i = lane; i < nv; i += 32) {
+    float s = 0;
+    for (int q = 0; q < 6; q++) s += cdof[6 * i + q] * cfs[6 * dbody[i] + q];
+    bias[i] = s;
+  }
+  // actuation (joint transmission; one actuator per joint assumed not required: atomics avoided by per-dof gather)
+  float *qact = DF(qfrc_actuator), *aforce = DF(actuator_force), *ctrl = DF(ctrl);
+  {
+    const int *trnid = MI(actuator_trnid), *biastype = MI(actuator_biastype), *ctrllim = MI(actuator_ctrllimited),
+              *frclim = MI(actuator_forcelimited), *jqadr = MI(jnt_qposadr), *jdadr = MI(jnt_dofadr);
+    const float *gear = MF(actuator_gear), *gainprm = MF(actuator_gainprm), *biasprm = MF(actuator_biasprm),
+                *ctrlrange = MF(actuator_ctrlrange), *frcrange = MF(actuator_forcerange);
+    for (int i = lane; i < M.nu; i += 32) {
+      float u = ctrl[i];
+      if (ctrllim[i]) u = fmaxf(ctrlrange[2 * i], fminf(ctrlrange[2 * i + 1], u));
+      const int j = trnid[i];
+      float force = gainprm[3 * i] * u;
+      if (biastype[i] == 1) {
+        const float length = gear[i] * qpos[jqadr[j]], vel = gear[i] * qvel[jdadr[j]];
+        force += biasprm[3 * i] + biasprm[3 * i + 1] * length + biasprm[3 * i + 2] * vel;
+      }
+      if (frclim[i]) force = fmaxf(frcrange[2 * i], fminf(frcrange[2 * i + 1], force));
+      aforce[i] = force;
+    }
+    __syncwarp();
+    for (int d = lane; d < nv; d += 32) {
+      float s = 0;
+      for (int i = 0; i < M.nu; i++)
+        if (jdadr[trnid[i]] == d) s += gear[i] * aforce[i];
+      qact[d] = s;
+    }
+  }
+  __syncwarp();
+  float* smooth = DF(qfrc_smooth);
+  for (int i = lane; i < nv; i += 32) smooth[i] = passive[i] - bias[i] + qact[i];
+  __syncwarp();
+  warp_chol_solve(DF(qacc_smooth), DF(qLD), DF(ldinv), smooth, nv, lane);
+}
+
+// constraint reference acceleration aref = -B*vel - K*imp*(pos - margin)
+__device__ __noinline__ void k_reference(Ctx& c) {
+  const int lane = c.lane, nv = c.M->nv;
+  const float *J = DF(efc_J), *qvel = DF(qvel), *K = DF(efc_K), *B = DF(efc_B), *imp = DF(efc_imp),
+              *pos = DF(efc_pos), *margin = DF(efc_margin);
+  float* aref = DF(efc_aref);
+  for (int i = lane; i < c.nefc; i += 32) {
+    float v = 0;
+    for (int j = 0; j < nv; j++) v += J[i * nv + j] * qvel[j];
+    aref[i] = -B[i] * v - K[i] * imp[i] * (pos[i] - margin[i]);
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------ primal Newton solver
+// Evaluate constraint cost at jar; writes force/state; returns warp-uniform cost. If hess, also fills
+// W (= per-row Hessian action on J: D*J for quadratic rows, hc*J for cone contacts, 0 otherwise).
+__device__ __noinline__ float k_update_constraint(Ctx& c, bool hess) {
+  const DevModel& M = *c.M;
+  const int lane = c.lane, nv = M.nv;
+  const float *jar = DF(efc_jar), *D = DF(efc_D), *R = DF(efc_R), *floss = DF(efc_floss), *J = DF(efc_J);
+  float *force = DF(efc_force), *W = DF(efc_W), *hc = DF(efc_hc);
+  int *state = DI(efc_state);
+  const int *etype = DI(efc_type), *eid = DI(efc_id), *item = DI(efc_item), *cdim = DI(con_dim);
+  float cost = 0;
+  for (int it = lane; it < c.nitem; it += 32) {
+    const int i = item[it];
+    const int ty = etype[i];
+    const float Di = D[i], x = jar[i];
+    if (ty == CNSTR_FRICTION_DOF) {
+      const float f = floss[i], rf = R[i] * f;
+      if (x <= -rf) { cost += f * (-0.5f * rf - x); force[i] = f; state[i] = STATE_LINEARNEG; }
+      else if (x >= rf) { cost += f * (-0.5f * rf + x); force[i] = -f; state[i] = STATE_LINEARPOS; }
+      else { cost += 0.5f * Di * x * x; force[i] = -Di * x; state[i] = STATE_QUADRATIC; }
+    } else if (ty == CNSTR_LIMIT_JOINT || ty == CNSTR_CONTACT_FRICTIONLESS) {
+      if (x < 0) { cost += 0.5f * Di * x * x; force[i] = -Di * x; state[i] = STATE_QUADRATIC; }
+      else { force[i] = 0; state[i] = STATE_SATISFIED; }
+    } else {
+      const int ci = eid[i];
+      const int dim = cdim[ci];
+      const float mu = DF(con_mu)[ci];
+      const float* fr = DF(con_friction) + 5 * ci;
+      float u[6];
+      u[0] = jar[i] * mu;
+      float tt = 0;
+      for (int j = 1; j < dim; j++) { u[j] = jar[i + j] * fr[j - 1]; tt += u[j] * u[j]; }
+      const float N = u[0], Tn = sqrtf(tt);
+      if (N >= mu * Tn || (Tn <= 0 && N >= 0)) {
+        for (int j = 0; j < dim; j++) { force[i + j] = 0; state[i + j] = STATE_SATISFIED; }
+      } else if (mu * N + Tn <= 0 || (Tn <= 0 && N < 0)) {
+        for (int j = 0; j < dim; j++) {
+          cost += 0.5f * D[i + j] * jar[i + j] * jar[i + j];
+          force[i + j] = -D[i + j] * jar[i + j];
+          state[i + j] = STATE_QUADRATIC;
+        }
+      } else {
+        const float Dm = Di / (mu * mu * (1 + mu * mu));
+        const float NmT = N - mu * Tn;
+        cost += 0.5f * Dm * NmT * NmT;
+        const float f0 = -Dm * NmT * mu;
+        force[i] = f0;
+        for (int j = 1; j < dim; j++) force[i + j] = -f0 / Tn * u[j] * fr[j - 1];
+        for (int j = 0; j < dim; j++) state[i + j] = STATE_CONE;
+        if (hess) {
+          float* h = hc + 36 * ci;
+          for (int a = 0; a < dim; a++)
+            for (int b = 0; b < dim; b++) {
+              float hv;
+              if (a == 0 && b == 0) hv = 1;
+              else if (a == 0) hv = -mu * u[b] / Tn;
+              else if (b == 0) hv = -mu * u[a] / Tn;
+              else hv = mu * N / (Tn * Tn * Tn) * u[a] * u[b] + (a == b ? (mu * mu - mu * N / Tn) : 0.f);
+              const float sa = a == 0 ? mu : fr[a - 1], sb = b == 0 ? mu : fr[b - 1];
+              h[a * 6 + b] = Dm * sa * sb * hv;
+            }
+        }
+      }
+    }
+  }
+  cost = warp_sum(cost);
+  __syncwarp();
+  if (hess) {
+    const int* cadr = DI(con_adr);
+    const int total = c.nefc * nv;
+    for (int w = lane; w < total; w += 32) {
+      const int r = w / nv, s = w - r * nv;
+      const int st = state[r];
+      float v = 0;
+      if (st == STATE_QUADRATIC) v = D[r] * J[r * nv + s];
+      else if (st == STATE_CONE) {
+        const int ci = eid[r];
+        const int a0 = cadr[ci], dim = cdim[ci], a = r - a0;
+        const float* h = hc + 36 * ci + 6 * a;
+        for (int b = 0; b < dim; b++) v += h[b] * J[(a0 + b) * nv + s];
+      }
+      W[w] = v;
+    }
+    __syncwarp();
+  }
+  return cost;
+}
+
+// Ma = M*qacc, jar = J*qacc - aref, gauss; returns total cost (uniform). If hess: qH = M + J^T W.
+__device__ __noinline__ float k_total_cost(Ctx& c, const float* qacc, bool hess, float* gauss_out) {
+  const DevModel& M = *c.M;
+  const int lane = c.lane, nv = M.nv;
+  const float *qM = DF(qM), *J = DF(efc_J), *aref = DF(efc_aref), *smooth = DF(qfrc_smooth), *qas = DF(qacc_smooth);
+  float *Ma = DF(Ma), *jar = DF(efc_jar);
+  float g = 0;
+  for (int i = lane; i < nv; i += 32) {
+    float a = 0;
+    for (int j = 0; j < nv; j++) a += qM[i * nv + j] * qacc[j];
+    Ma[i] = a;
+    g += (a - smooth[i]) * (qacc[i] - qas[i]);
+  }
+  for (int i = lane; i < c.nefc; i += 32) {
+    float a = 0;
+    for (int j = 0; j < nv; j++) a += J[i * nv + j] * qacc[j];
+    jar[i] = a - aref[i];
+  }
+  g = 0.5f * warp_sum(g);
+  __syncwarp();
+  const float cc = k_update_constraint(c, hess);
+  if (hess) {
+    const float* W = DF(efc_W);
+    float* H = DF(qH);
+    const int ne = c.nefc;
+    for (int w = lane; w < nv * nv; w += 32) {
+      const int r = w / nv, s = w - r * nv;
+      if (s > r) continue;
+      float a = qM[w];
+      for (int k = 0; k < ne; k++) a += J[k * nv + r] * W[k * nv + s];
+      H[w] = a;
+      H[s * nv + r] = a;
+    }
+    __syncwarp();
+  }
+  *gauss_out = g;
+  return cc + g;
+}
+
+struct LsPoint { float alpha, cost, d1, d2; };
+
+__device__ __noinline__ LsPoint k_ls_eval(Ctx& c, float g0, float g1, float g2, float alpha) {
+  const int lane = c.lane;
+  const float *jar = DF(efc_jar), *Jv = DF(efc_Jv), *D = DF(efc_D), *R = DF(efc_R), *floss = DF(efc_floss);
+  const int *etype = DI(efc_type), *eid = DI(efc_id), *item = DI(efc_item), *cdim = DI(con_dim);
+  float cost = 0, d1 = 0, d2 = 0;
+  for (int it = lane; it < c.nitem; it += 32) {
+    const int i = item[it];
+    const int ty = etype[i];
+    const float Di = D[i], jv = Jv[i], x = jar[i] + alpha * jv;
+    if (ty == CNSTR_FRICTION_DOF) {
+      const float f = floss[i], rf = R[i] * f;
+      if (x <= -rf) { cost += f * (-0.5f * rf - x); d1 += -f * jv; }
+      else if (x >= rf) { cost += f * (-0.5f * rf + x); d1 += f * jv; }
+      else { cost += 0.5f * Di * x * x; d1 += Di * x * jv; d2 += Di * jv * jv; }
+    } else if (ty == CNSTR_LIMIT_JOINT || ty == CNSTR_CONTACT_FRICTIONLESS) {
+      if (x < 0) { cost += 0.5f * Di * x * x; d1 += Di * x * jv; d2 += Di * jv * jv; }
+    } else {
+      const int ci = eid[i];
+      const int dim = cdim[ci];
+      const float mu = DF(con_mu)[ci];
+      const float* fr = DF(con_friction) + 5 * ci;
+      const float U0 = jar[i] * mu, V0 = Jv[i] * mu;
+      float UU = 0, UV = 0, VV = 0;
+      for (int j = 1; j < dim; j++) {
+        const float uj = jar[i + j] * fr[j - 1], vj = Jv[i + j] * fr[j - 1];
+        UU += uj * uj; UV += uj * vj; VV += vj * vj;
+      }
+      const float N = U0 + alpha * V0;
+      const float Tsqr = UU + alpha * (2 * UV + alpha * VV);
+      const float Tn = Tsqr <= 0 ? 0.f : sqrtf(Tsqr);
+      if (N >= mu * Tn || (Tn <= 0 && N >= 0)) {
+      } else if (mu * N + Tn <= 0 || (Tn <= 0 && N < 0)) {
+        for (int j = 0; j < dim; j++) {
+          const float Dj = D[i + j], vj = Jv[i + j], xj = jar[i + j] + alpha * vj;
+          cost += 0.5f * Dj * xj * xj; d1 += Dj * xj * vj; d2 += Dj * vj * vj;
+        }
+      } else {
+        const float Dm = Di / (mu * mu * (1 + mu * mu));
+        const float N1 = V0, T1 = (UV + alpha * VV) / Tn;
+        const float T2 = VV / Tn - (UV + alpha * VV) * T1 / (Tn * Tn);
+        const float NmT = N - mu * Tn;
+        cost += 0.5f * Dm * NmT * NmT;
+        d1 += Dm * NmT * (N1 - mu * T1);
+        d2 += Dm * ((N1 - mu * T1) * (N1 - mu * T1) + NmT * (-mu * T2));
+      }
+    }
+  }
+  LsPoint p;
+  p.alpha = alpha;
+  p.cost = g0 + alpha * g1 + alpha * alpha * g2 + warp_sum(cost);
+  p.d1 = g1 + 2 * alpha * g2 + warp_sum(d1);
+  p.d2 = 2 * g2 + warp_sum(d2);
+  return p;
+}
+
+__device__ __noinline__ float k_line_search(Ctx& c, float g0, float g1, float g2, float snorm, float scale_inv) {
+  const DevModel& M = *c.M;
+  if (snorm < kMinVal) return 0.f;
+  const LsPoint p0 = k_ls_eval(c, g0, g1, g2, 0.f);
+  const float gtol = fmaxf(M.tolerance * M.ls_tolerance * snorm * scale_inv, 64 * 1.1920929e-7f * fabsf(p0.d1));
+  if (p0.d2 <= kMinVal) return 0.f;
+  LsPoint p1 = k_ls_eval(c, g0, g1, g2, -p0.d1 / p0.d2);
+  if (p0.cost < p1.cost) p1 = p0;
+  if (fabsf(p1.d1) < gtol) return p1.alpha;
+  int iter = 0;
+  LsPoint p2 = p1;
+  bool bracket = false;
+  while (iter < M.ls_iterations) {
+    iter++;
+    p2 = p1;
+    if (p1.d2 <= kMinVal) break;
+    p1 = k_ls_eval(c, g0, g1, g2, p1.alpha - p1.d1 / p1.d2);
+    if (fabsf(p1.d1) < gtol) return p1.cost <= p0.cost ? p1.alpha : 0.f;
+    if ((p1.d1 > 0) != (p2.d1 > 0)) { bracket = true; break; }
+  }
+  if (!bracket) return p1.cost < p0.cost ? p1.alpha : 0.f;
+  LsPoint lo = p1.d1 < 0 ? p1 : p2, hi = p1.d1 < 0 ? p2 : p1;
+  while (iter < M.ls_iterations) {
+    iter++;
+    const LsPoint from = fabsf(lo.d1) < fabsf(hi.d1) ? lo : hi;
+    float a = from.d2 > kMinVal ? from.alpha - from.d1 / from.d2 : 0.5f * (lo.alpha + hi.alpha);
+    const float amin = fminf(lo.alpha, hi.alpha), amax = fmaxf(lo.alpha, hi.alpha);
+    if (!(a > amin && a < amax)) a = 0.5f * (lo.alpha + hi.alpha);
+    if (a == lo.alpha || a == hi.alpha) break;
+    const LsPoint pm = k_ls_eval(c, g0, g1, g2, a);
+    if (fabsf(pm.d1) < gtol) return pm.cost <= p0.cost ? pm.alpha : 0.f;
+    if (pm.d1 < 0) lo = pm; else hi = pm;
+  }
+  const LsPoint best = lo.cost < hi.cost ? lo : hi;
+  return best.cost < p0.cost ? best.alpha : 0.f;
+}
+
+__device__ __noinline__ void k_solve(Ctx& c) {
+  const DevModel& M = *c.M;
+  const int lane = c.lane, nv = M.nv, ne = c.nefc;
+  float *qacc = DF(qacc), *qas = DF(qacc_smooth), *qws = DF(qacc_warmstart), *qfc = DF(qfrc_constraint);
+  c.niter = 0;
+  if (ne == 0) {
+    for (int i = lane; i < nv; i += 32) { qacc[i] = qas[i]; qfc[i] = 0; }
+    __syncwarp();
+    return;
+  }
+  float gauss;
+  if (!M.disable_warmstart) {
+    const float cw = k_total_cost(c, qws, false, &gauss);
+    const float cs = k_total_cost(c, qas, false, &gauss);
+    for (int i = lane; i < nv; i += 32) qacc[i] = cw < cs ? qws[i] : qas[i];
+  } else {
+    for (int i = lane; i < nv; i += 32) qacc[i] = qas[i];
+  }
+  __syncwarp();
+  const float scale_inv = M.meaninertia * (float)max(1, nv);
+  float *grad = DF(grad), *search = DF(search), *Mv = DF(Mv), *Ma = DF(Ma), *smooth = DF(qfrc_smooth),
+        *J = DF(efc_J), *force = DF(efc_force), *Jv = DF(efc_Jv), *qM = DF(qM);
+  float cost = k_total_cost(c, qacc, true, &gauss);
+  float gnorm2;
+  auto grad_dir = [&]() {
+    float g2 = 0;
+    for (int i = lane; i < nv; i += 32) {
+      float a = Ma[i] - smooth[i];
+      for (int r = 0; r < ne; r++) a -= J[r * nv + i] * force[r];
+      grad[i] = a;
+      g2 += a * a;
+    }
+    gnorm2 = warp_sum(g2);
+    __syncwarp();
+    warp_chol(DF(qH), DF(hinv), nv, lane);
+    warp_chol_solve(search, DF(qH), DF(hinv), grad, nv, lane);
+    for (int i = lane; i < nv; i += 32) search[i] = -search[i];
+    __syncwarp();
+  };
+  grad_dir();
+  for (int iter = 0; iter < M.iterations; iter++) {
+    float q1 = 0, q2 = 0, sn = 0;
+    for (int i = lane; i < nv; i += 32) {
+      float a = 0;
+      for (int j = 0; j < nv; j++) a += qM[i * nv + j] * search[j];
+      Mv[i] = a;
+      q1 += search[i] * (Ma[i] - smooth[i]);
+      q2 += 0.5f * search[i] * a;
+      sn += search[i] * search[i];
+    }
+    for (int i = lane; i < ne; i += 32) {
+      float a = 0;
+      for (int j = 0; j < nv; j++) a += J[i * nv + j] * search[j];
+      Jv[i] = a;
+    }
+    q1 = warp_sum(q1); q2 = warp_sum(q2); sn = sqrtf(warp_sum(sn));
+    __syncwarp();
+    const float alpha = k_line_search(c, gauss, q1, q2, sn, scale_inv);
+    if (alpha == 0.f) break;
+    for (int i = lane; i < nv; i += 32) qacc[i] += alpha * search[i];
+    __syncwarp();
+    const float old = cost;
+    cost = k_total_cost(c, qacc, true, &gauss);
+    grad_dir();
+    c.niter = iter + 1;
+    const float improvement = (old - cost) / scale_inv, gradient = sqrtf(gnorm2) / scale_inv;
+    if (improvement < M.tolerance || gradient < M.tolerance) break;
+  }
+  for (int i = lane; i < nv; i += 32) {
+    float a = 0;
+    for (int r = 0; r < ne; r++) a += J[r * nv + i] * force[r];
+    qfc[i] = a;
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------ pipeline pieces
+__device__ __forceinline__ bool k_bad(Ctx& c, const float* v, int n) {
+  bool bad = false;
+  for (int i = c.lane; i < n; i += 32) bad |= !(fabsf(v[i]) < kMaxVal);
+  return __any_sync(kFull, bad);
+}
+
+// everything of mj_forward up to (not including) the sensor/residual callback
+__device__ __noinline__ void k_forward(Ctx& c) {
+  k_kinematics(c);
+  k_com_pos(c);
+  k_crb(c);
+  k_collision(c);
+  k_make_constraint(c);
+  k_com_vel(c);
+  k_smooth_forces(c);
+  k_reference(c);
+  k_solve(c);
+}
+
+// semi-implicit Euler with implicit joint damping
+__device__ __noinline__ void k_euler(Ctx& c) {
+  const DevModel& M = *c.M;
+  const int lane = c.lane, nv = M.nv;
+  const float h = M.timestep;
+  float *qacc = DF(qacc), *qvel = DF(qvel), *qpos = DF(qpos), *vt = DF(vtmp);
+  const float* acc = qacc;
+  if (M.any_damping && !M.disable_eulerdamp) {
+    float *H = DF(qH), *qM = DF(qM), *smooth = DF(qfrc_smooth), *qfc = DF(qfrc_constraint);
+    const float* damping = MF(dof_damping);
+    for (int w = lane; w < nv * nv; w += 32) {
+      const int r = w / nv, s = w - r * nv;
+      H[w] = qM[w] + (r == s ? h * damping[r] : 0.f);
+    }
+    for (int i = lane; i < nv; i += 32) vt[i] = smooth[i] + qfc[i];
+    __syncwarp();
+    warp_chol(H, DF(hinv), nv, lane);
+    warp_chol_solve(vt, H, DF(hinv), vt, nv, lane);
+    acc = vt;
+  }
+  for (int i = lane; i < nv; i += 32) qvel[i] += h * acc[i];
+  __syncwarp();
+  const int *jtype = MI(jnt_type), *jqadr = MI(jnt_qposadr), *jdadr = MI(jnt_dofadr);
+  for (int j = lane; j < M.njnt; j += 32) {
+    const int qa = jqadr[j], da = jdadr[j];
+    const int t = jtype[j];
+    if (t == JNT_FREE) {
+      for (int q = 0; q < 3; q++) qpos[qa + q] += h * qvel[da + q];
+      quat_integrate(qpos + qa + 3, qvel + da + 3, h);
+    } else if (t == JNT_BALL) {
+      quat_integrate(qpos + qa, qvel + da, h);
+    } else {
+      qpos[qa] += h * qvel[da];
+    }
+  }
+  c.time += h;
+  __syncwarp();
+}
+
+}  // namespace mjpc_dev

@@ -1,0 +1,213 @@
+// rollout_kernels.cuh - the CUDA kernels of the hot path (sm_100a).
+//
+//   rollout_kernel      one warp = one candidate trajectory (Trajectory::Rollout / RolloutDiscrete,
+//                       mjpc/trajectory.cc:92-309) incl. policy, mj_step restatement, residual, cost, return
+//   rank_kernel         order of candidates by return (partial_sort, sampling/planner.cc:184-188)
+//   step_debug_kernel   a single forward+Euler step through the same device functions (parity hook)
+//   fd_*_kernel         finite-difference transition/residual Jacobians (model_derivatives.cc:45-165)
+//
+// Shared memory per CTA: [model pack (floats | ints)] [warp 0 data] [warp 1 data] ...
+// The model pack is staged with ONE 1-D TMA bulk copy (cp.async.bulk -> SASS UBLKCP) signalled on an mbarrier.
+// Trajectory outputs are written time-major per candidate with lane-strided (coalesced) stores.
+#pragma once
+#include "dev_physics.cuh"
+#include "dev_task.cuh"
+
+namespace mjpc_dev {
+
+struct RolloutArgs {
+  DevModel M;
+  DevLayout L;
+  const float* pack;        // device: nf floats followed by ni ints
+  const float* state;       // [dim_state]
+  const float* mocap;       // [7*nmocap]
+  const float* task_state;  // [task_state_size] (times rebased to the rollout start) or nullptr
+  const float* knots;       // [N][P][nu]
+  const float* knot_times;  // [P], relative
+  FeedbackArgs fb;
+  const float* step_sizes;  // [N] for the feedback policy
+  int policy_kind;          // 0 spline, 1 feedback
+  int P, interp, N, H;
+  double time0;
+  float* states; float* actions; double* times; float* residual; float* costs; float* trace;
+  float* returns; unsigned char* failure;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// Stage the model pack into shared memory with a TMA bulk copy; all threads of the CTA must call.
+__device__ __forceinline__ void stage_model_pack(float* dst, const float* src, unsigned bytes) {
+  __shared__ __align__(8) unsigned long long bar;
+  const unsigned bar_a = smem_u32(&bar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_a), "r"(1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(bar_a) : "memory");
+  }
+  unsigned done = 0;
+  while (!done) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(bar_a), "r"(0) : "memory");
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void init_ctx(Ctx& c, const DevModel* M, const DevLayout* L, float* smem, int warp, int lane) {
+  c.M = M; c.L = L;
+  c.mf = smem;
+  c.mi = reinterpret_cast<const int*>(smem + M->nf);
+  c.d = smem + M->nf + M->ni + (size_t)warp * L->total;
+  c.lane = lane;
+  c.ncon = 0; c.nefc = 0; c.nitem = 0; c.niter = 0; c.warn = 0; c.time = 0.f;
+}
+
+// write the trace points (GetTraces, mjpc/utilities.cc:268-285)
+__device__ __forceinline__ void write_traces(Ctx& c, float* out) {
+  const DevModel& M = *c.M;
+  const int *ty = MI(task_trace_objtype), *id = MI(task_trace_objid);
+  for (int w = c.lane; w < 3 * M.num_trace; w += 32) {
+    const int k = w / 3, q = w - 3 * k;
+    const float* src = ty[k] == OBJ_SITE ? DF(site_xpos) : ty[k] == OBJ_GEOM ? DF(geom_xpos) : ty[k] == OBJ_XBODY ? DF(xpos) : DF(xipos);
+    out[w] = src[3 * id[k] + q];
+  }
+}
+
+extern "C" __global__ void __launch_bounds__(128) rollout_kernel(const __grid_constant__ RolloutArgs A) {
+  extern __shared__ __align__(16) float smem[];
+  const DevModel& M = A.M;
+  stage_model_pack(smem, A.pack, (unsigned)((M.nf + M.ni) * 4));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cand = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (cand >= A.N) return;
+  Ctx c;
+  init_ctx(c, &A.M, &A.L, smem, warp, lane);
+  const int nq = M.nq, nv = M.nv, nu = M.nu, ds = nq + nv, nr = M.num_residual, ntr = 3 * M.num_trace, H = A.H;
+  // per-iteration task state (time-rebased) overrides the packed copy: the pack in shared memory is per CTA,
+  // every warp writes the same values
+  if (A.task_state) {
+    float* ts = const_cast<float*>(MF(task_state));
+    for (int i = lane; i < M.task_state_size; i += 32) ts[i] = A.task_state[i];
+  }
+  // ---- initial conditions (trajectory.cc:108-137)
+  for (int i = lane; i < nq; i += 32) DF(qpos)[i] = A.state[i];
+  for (int i = lane; i < nv; i += 32) { DF(qvel)[i] = A.state[nq + i]; DF(qacc_warmstart)[i] = 0; }
+  for (int i = lane; i < 7 * M.nmocap; i += 32) {
+    const int k = i / 7, q = i - 7 * k;
+    if (q < 3) DF(mocap_pos)[3 * k + q] = A.mocap[i]; else DF(mocap_quat)[4 * k + q - 3] = A.mocap[i];
+  }
+  for (int i = lane; i < nv * nv; i += 32) DF(qM)[i] = 0;
+  float step_size = 0.f;
+  if (A.policy_kind == 0) {
+    for (int i = lane; i < A.P * nu; i += 32) DF(knots)[i] = A.knots[(size_t)cand * A.P * nu + i];
+    for (int i = lane; i < A.P; i += 32) DF(knot_times)[i] = A.knot_times[i];
+  } else {
+    step_size = A.step_sizes[cand];
+  }
+  __syncwarp();
+  float* o_states = A.states + (size_t)cand * H * ds;
+  float* o_actions = A.actions + (size_t)cand * H * nu;
+  double* o_times = A.times + (size_t)cand * H;
+  float* o_res = A.residual + (size_t)cand * H * nr;
+  float* o_costs = A.costs + (size_t)cand * H;
+  float* o_trace = A.trace + (size_t)cand * H * ntr;
+  for (int i = lane; i < ds; i += 32) o_states[i] = A.state[i];
+  if (lane == 0) o_times[0] = A.time0;
+  float total = 0.f;
+  bool failed = false;
+  for (int t = 0; t < H; t++) {
+    const bool last = t == H - 1;
+    if (!last) {
+      if (A.policy_kind == 0) k_policy_spline(c, A.P, A.interp);
+      else k_policy_feedback(c, A.fb, step_size, t);
+    }
+    // action record (the last row repeats the previous action; H == 1 -> zeros; trajectory.cc:190-196)
+    for (int i = lane; i < nu; i += 32) {
+      if (H == 1) DF(ctrl)[i] = 0;
+      o_actions[(size_t)t * nu + i] = DF(ctrl)[i];
+    }
+    if (!last && (k_bad(c, DF(qpos), nq) || k_bad(c, DF(qvel), nv))) { failed = true; break; }
+    k_forward(c);
+    k_residual(c);
+    if (!last && k_bad(c, DF(qacc), nv)) c.warn = 1;
+    for (int i = lane; i < nr; i += 32) o_res[(size_t)t * nr + i] = DF(residual)[i];
+    write_traces(c, o_trace + (size_t)t * ntr);
+    if (c.warn) { failed = true; break; }
+    const float cost = k_cost_value(c);
+    if (lane == 0) o_costs[t] = cost;
+    total += cost;
+    if (last) break;
+    for (int i = lane; i < nv; i += 32) DF(qacc_warmstart)[i] = DF(qacc)[i];
+    k_euler(c);
+    for (int i = lane; i < nq; i += 32) o_states[(size_t)(t + 1) * ds + i] = DF(qpos)[i];
+    for (int i = lane; i < nv; i += 32) o_states[(size_t)(t + 1) * ds + nq + i] = DF(qvel)[i];
+    if (lane == 0) o_times[t + 1] = A.time0 + (double)c.time;
+  }
+  if (lane == 0) {
+    A.returns[cand] = failed ? 1.0e6f : total / (float)max(H, 1);
+    A.failure[cand] = failed ? 1 : 0;
+  }
+}
+
+// order[rank] = i, ascending return, ties broken by index
+extern "C" __global__ void rank_kernel(const float* __restrict__ ret, int N, int* __restrict__ order) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    const float ri = ret[i];
+    int rank = 0;
+    for (int j = 0; j < N; j++) {
+      const float rj = ret[j];
+      rank += (rj < ri) || (rj == ri && j < i) || (ri != ri && rj == rj);
+    }
+    order[rank] = i;
+  }
+}
+
+struct DebugArgs {
+  DevModel M;
+  DevLayout L;
+  const float* pack;
+  const float* qpos; const float* qvel; const float* ctrl; const float* mocap; const float* warmstart;
+  const float* task_state;
+  float time;
+  float* qacc; float* residual; float* next_qpos; float* next_qvel; float* qM; float* efc_force; int* counts;
+};
+
+extern "C" __global__ void __launch_bounds__(32) step_debug_kernel(const __grid_constant__ DebugArgs A) {
+  extern __shared__ __align__(16) float smem[];
+  const DevModel& M = A.M;
+  stage_model_pack(smem, A.pack, (unsigned)((M.nf + M.ni) * 4));
+  Ctx c;
+  init_ctx(c, &A.M, &A.L, smem, 0, threadIdx.x);
+  const int lane = c.lane, nq = M.nq, nv = M.nv;
+  if (A.task_state) {
+    float* ts = const_cast<float*>(MF(task_state));
+    for (int i = lane; i < M.task_state_size; i += 32) ts[i] = A.task_state[i];
+  }
+  for (int i = lane; i < nq; i += 32) DF(qpos)[i] = A.qpos[i];
+  for (int i = lane; i < nv; i += 32) { DF(qvel)[i] = A.qvel[i]; DF(qacc_warmstart)[i] = A.warmstart ? A.warmstart[i] : 0.f; }
+  for (int i = lane; i < M.nu; i += 32) DF(ctrl)[i] = A.ctrl[i];
+  for (int i = lane; i < 7 * M.nmocap; i += 32) {
+    const int k = i / 7, q = i - 7 * k;
+    if (q < 3) DF(mocap_pos)[3 * k + q] = A.mocap[i]; else DF(mocap_quat)[4 * k + q - 3] = A.mocap[i];
+  }
+  for (int i = lane; i < nv * nv; i += 32) DF(qM)[i] = 0;
+  c.time = A.time;
+  __syncwarp();
+  k_forward(c);
+  k_residual(c);
+  if (k_bad(c, DF(qacc), nv)) c.warn = 1;
+  for (int i = lane; i < nv; i += 32) A.qacc[i] = DF(qacc)[i];
+  for (int i = lane; i < nv * nv; i += 32) A.qM[i] = DF(qM)[i];
+  for (int i = lane; i < M.num_residual; i += 32) A.residual[i] = DF(residual)[i];
+  for (int i = lane; i < c.nefc; i += 32) A.efc_force[i] = DF(efc_force)[i];
+  if (lane == 0) { A.counts[0] = c.ncon; A.counts[1] = c.nefc; A.counts[2] = c.niter; A.counts[3] = c.warn; }
+  k_euler(c);
+  for (int i = lane; i < nq; i += 32) A.next_qpos[i] = DF(qpos)[i];
+  for (int i = lane; i < nv; i += 32) A.next_qvel[i] = DF(qvel)[i];
+}
+
+}  // namespace mjpc_dev

@@ -1,0 +1,243 @@
+"""ctypes binding of libmjpc_b200.so - the reference-facing call a user makes.
+
+Every method goes through the C ABI in include/mjpc_b200.h; there is no Python/NumPy compute path and no
+CPU fallback: if the library is missing or no B200 is visible, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .blob import to_blob
+from .build import SO
+
+_fp = C.POINTER(C.c_float)
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_bp = C.POINTER(C.c_uint8)
+
+EXPORTS = ["mjpc_b200_version", "mjpc_b200_last_error", "mjpc_b200_create", "mjpc_b200_destroy",
+           "mjpc_b200_get_info", "mjpc_b200_set_task", "mjpc_b200_rollout_spline", "mjpc_b200_rollout_feedback",
+           "mjpc_b200_fetch_trajectory", "mjpc_b200_fetch_all", "mjpc_b200_model_derivatives",
+           "mjpc_b200_cost_derivatives", "mjpc_b200_backward_pass", "mjpc_b200_step_debug",
+           "mjpc_b200_launch_count", "mjpc_b200_last_kernel_ms", "mjpc_b200_upload_spline_inputs",
+           "mjpc_b200_launch_resident", "mjpc_b200_sync", "mjpc_b200_read_returns", "mjpc_b200_stream",
+           "mjpc_b200_device_returns"]
+
+
+class ModelBlob(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("nbytes", C.c_size_t)]
+
+
+class TaskDesc(C.Structure):
+    _fields_ = [("weight", _dp), ("parameters", _dp), ("task_state", _dp), ("risk", C.c_double)]
+
+
+class Info(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("nq", "nv", "nu", "na", "nmocap", "nuserdata", "dim_state", "dim_dstate",
+                                       "num_residual", "num_term", "num_trace", "num_parameters", "task_state_size",
+                                       "max_candidates", "max_horizon", "device", "smem_bytes_per_warp")]
+
+
+_LIB = None
+
+
+def load_library():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(SO):
+            raise RuntimeError(f"{SO} not built: run `python -m mujoco_mpc_b200.build` (no fallback path exists)")
+        lib = C.CDLL(SO)
+        lib.mjpc_b200_version.restype = C.c_char_p
+        lib.mjpc_b200_last_error.restype = C.c_char_p
+        lib.mjpc_b200_launch_count.restype = C.c_int64
+        lib.mjpc_b200_last_kernel_ms.restype = C.c_float
+        lib.mjpc_b200_stream.restype = C.c_void_p
+        lib.mjpc_b200_device_returns.restype = C.c_void_p
+        for n in ("mjpc_b200_destroy", "mjpc_b200_launch_count", "mjpc_b200_last_kernel_ms", "mjpc_b200_stream",
+                  "mjpc_b200_device_returns", "mjpc_b200_sync", "mjpc_b200_launch_resident"):
+            getattr(lib, n).argtypes = [C.c_void_p]
+        _LIB = lib
+    return _LIB
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def _f(a):
+    return None if a is None else np.ascontiguousarray(a, np.float32)
+
+
+def _d(a):
+    return None if a is None else np.ascontiguousarray(a, np.float64)
+
+
+def _pf(a):
+    return None if a is None else a.ctypes.data_as(_fp)
+
+
+def _pd(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+class Engine:
+    """One handle = one GPU's share of the candidates (Planner::Initialize/Allocate analogue)."""
+
+    def __init__(self, model, max_candidates=256, max_horizon=64, device=0):
+        self.lib = load_library()
+        self.m = model
+        self._blob = to_blob(model)
+        self._buf = C.create_string_buffer(self._blob, len(self._blob))
+        mb = ModelBlob(C.cast(self._buf, C.c_void_p), len(self._blob))
+        h = C.c_void_p()
+        rc = self.lib.mjpc_b200_create(C.byref(mb), int(max_candidates), int(max_horizon), int(device), C.byref(h))
+        if rc != 0:
+            raise EngineError(f"mjpc_b200_create failed ({rc}): {self.lib.mjpc_b200_last_error().decode()}")
+        self.h = h
+        info = Info()
+        self._check(self.lib.mjpc_b200_get_info(self.h, C.byref(info)))
+        self.info = info
+        self.ds, self.n, self.nu, self.nr = info.dim_state, info.dim_dstate, info.nu, info.num_residual
+        self.ntr = 3 * info.num_trace
+        self.lastN = self.lastH = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mjpc_b200_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc != 0:
+            raise EngineError(f"mjpc_b200 error {rc}: {self.lib.mjpc_b200_last_error().decode()}")
+
+    # ---- task snapshot (Agent::PlanIteration, agent.cc:316-319)
+    def set_task(self, weight=None, parameters=None, task_state=None, risk=None):
+        w, p, s = _d(weight), _d(parameters), _d(task_state)
+        td = TaskDesc(_pd(w), _pd(p), _pd(s), float(self.m.task_risk if risk is None else risk))
+        self._check(self.lib.mjpc_b200_set_task(self.h, C.byref(td)))
+
+    # ---- SamplingPlanner::Rollouts
+    def rollout_spline(self, state, time, mocap, knots, knot_times, interp, H, want_order=True):
+        knots = _f(knots)
+        N, P, nu = knots.shape
+        st, mc, kt = _f(state), _f(mocap), _d(knot_times)
+        ret = np.zeros(N, np.float32); fail = np.zeros(N, np.uint8); order = np.zeros(N, np.int32)
+        self._check(self.lib.mjpc_b200_rollout_spline(self.h, _pf(st), C.c_double(time), _pf(mc), None, _pf(knots),
+                                                      _pd(kt), int(interp), P, N, int(H), _pf(ret),
+                                                      fail.ctypes.data_as(_bp), order.ctypes.data_as(_ip)))
+        self.lastN, self.lastH = N, H
+        return ret, fail, order
+
+    def upload_spline_inputs(self, state, time, mocap, knots, knot_times, interp, H):
+        knots = _f(knots)
+        N, P, nu = knots.shape
+        st, mc, kt = _f(state), _f(mocap), _d(knot_times)
+        self._check(self.lib.mjpc_b200_upload_spline_inputs(self.h, _pf(st), C.c_double(time), _pf(mc), None,
+                                                            _pf(knots), _pd(kt), int(interp), P, N, int(H)))
+        self.lastN, self.lastH = N, H
+
+    def launch_resident(self):
+        self._check(self.lib.mjpc_b200_launch_resident(self.h))
+
+    def sync(self):
+        self._check(self.lib.mjpc_b200_sync(self.h))
+
+    def read_returns(self):
+        N = self.lastN
+        ret = np.zeros(N, np.float32); fail = np.zeros(N, np.uint8); order = np.zeros(N, np.int32)
+        self._check(self.lib.mjpc_b200_read_returns(self.h, _pf(ret), fail.ctypes.data_as(_bp), order.ctypes.data_as(_ip)))
+        return ret, fail, order
+
+    # ---- iLQGPlanner::FeedbackRollouts / ActionRollouts
+    def rollout_feedback(self, state, time, mocap, u_nom, x_nom, t_nom, gains, du, step_sizes, mode):
+        u, x, t, g = _f(u_nom), _f(x_nom), _d(t_nom), _f(gains)
+        dd = _f(du)
+        ss = _f(step_sizes)
+        K, H = len(ss), u.shape[0]
+        st, mc = _f(state), _f(mocap)
+        ret = np.zeros(K, np.float32); fail = np.zeros(K, np.uint8); order = np.zeros(K, np.int32)
+        self._check(self.lib.mjpc_b200_rollout_feedback(self.h, _pf(st), C.c_double(time), _pf(mc), None, _pf(u), _pf(x),
+                                                        _pd(t), _pf(g), _pf(dd), _pf(ss), int(mode), K, H, _pf(ret),
+                                                        fail.ctypes.data_as(_bp), order.ctypes.data_as(_ip)))
+        self.lastN, self.lastH = K, H
+        return ret, fail, order
+
+    def fetch_trajectory(self, i):
+        H = self.lastH
+        o = dict(states=np.zeros((H, self.ds), np.float32), actions=np.zeros((H, self.nu), np.float32),
+                 times=np.zeros(H), residual=np.zeros((H, self.nr), np.float32), costs=np.zeros(H, np.float32),
+                 trace=np.zeros((H, self.ntr), np.float32))
+        self._check(self.lib.mjpc_b200_fetch_trajectory(self.h, int(i), _pf(o["states"]), _pf(o["actions"]),
+                                                        _pd(o["times"]), _pf(o["residual"]), _pf(o["costs"]),
+                                                        _pf(o["trace"])))
+        return o
+
+    def fetch_all(self):
+        N, H = self.lastN, self.lastH
+        o = dict(states=np.zeros((N, H, self.ds), np.float32), actions=np.zeros((N, H, self.nu), np.float32),
+                 times=np.zeros((N, H)), residual=np.zeros((N, H, self.nr), np.float32),
+                 costs=np.zeros((N, H), np.float32), trace=np.zeros((N, H, self.ntr), np.float32))
+        self._check(self.lib.mjpc_b200_fetch_all(self.h, _pf(o["states"]), _pf(o["actions"]), _pd(o["times"]),
+                                                 _pf(o["residual"]), _pf(o["costs"]), _pf(o["trace"])))
+        return o
+
+    def step_debug(self, qpos, qvel, ctrl, mocap, time=0.0, warmstart=None):
+        nv, nq = self.info.nv, self.info.nq
+        o = dict(qacc=np.zeros(nv, np.float32), residual=np.zeros(max(self.nr, 1), np.float32),
+                 next_qpos=np.zeros(nq, np.float32), next_qvel=np.zeros(nv, np.float32),
+                 qM=np.zeros((nv, nv), np.float32), efc_force=np.zeros(256, np.float32))
+        counts = np.zeros(4, np.int32)
+        q, v, u, mc, ws = _f(qpos), _f(qvel), _f(ctrl), _f(mocap), _f(warmstart)
+        self._check(self.lib.mjpc_b200_step_debug(self.h, _pf(q), _pf(v), _pf(u), _pf(mc), C.c_double(time), _pf(ws),
+                                                  _pf(o["qacc"]), _pf(o["residual"]), _pf(o["next_qpos"]),
+                                                  _pf(o["next_qvel"]), _pf(o["qM"]), _pf(o["efc_force"]),
+                                                  counts.ctypes.data_as(_ip)))
+        o.update(ncon=int(counts[0]), nefc=int(counts[1]), niter=int(counts[2]), warning=int(counts[3]))
+        o["efc_force"] = o["efc_force"][: o["nefc"]]
+        return o
+
+    # ---- iLQG sweeps
+    def model_derivatives(self, x, u, t, mocap, tol):
+        x, u, t, mc = _f(x), _f(u), _d(t), _f(mocap)
+        H = x.shape[0]
+        n, nu, nr = self.n, self.nu, self.nr
+        A = np.zeros((H, n, n), np.float32); B = np.zeros((H, n, nu), np.float32)
+        Cm = np.zeros((H, nr, n), np.float32); D = np.zeros((H, nr, nu), np.float32)
+        self._check(self.lib.mjpc_b200_model_derivatives(self.h, _pf(x), _pf(u), _pd(t), _pf(mc), H, C.c_float(tol),
+                                                         _pf(A), _pf(B), _pf(Cm), _pf(D)))
+        return A, B, Cm, D
+
+    def cost_derivatives(self, residual, Cm, D):
+        r, c, d = _f(residual), _f(Cm), _f(D)
+        H = r.shape[0]
+        n, nu = self.n, self.nu
+        cx = np.zeros((H, n), np.float32); cu = np.zeros((H, nu), np.float32)
+        cxx = np.zeros((H, n, n), np.float32); cuu = np.zeros((H, nu, nu), np.float32)
+        cxu = np.zeros((H, n, nu), np.float32)
+        self._check(self.lib.mjpc_b200_cost_derivatives(self.h, _pf(r), _pf(c), _pf(d), H, _pf(cx), _pf(cu), _pf(cxx),
+                                                        _pf(cuu), _pf(cxu)))
+        return cx, cu, cxx, cuu, cxu
+
+    def backward_pass(self, A, B, cx, cu, cxx, cxu, cuu, actions, mu=0.0, reg_type=0, limits=1):
+        a = [_f(v) for v in (A, B, cx, cu, cxx, cxu, cuu, actions)]
+        H, n, nu = a[1].shape
+        K = np.zeros((H, nu, n), np.float32); du = np.zeros((H, nu), np.float32); dV = np.zeros(2, np.float32)
+        Vx = np.zeros((H, n), np.float32); Vxx = np.zeros((H, n, n), np.float32)
+        status = C.c_int(0)
+        self._check(self.lib.mjpc_b200_backward_pass(self.h, *[_pf(v) for v in a], H, C.c_float(mu), int(reg_type),
+                                                     int(limits), _pf(K), _pf(du), _pf(dV), _pf(Vx), _pf(Vxx),
+                                                     C.byref(status)))
+        return dict(K=K, du=du, dV=dV, Vx=Vx, Vxx=Vxx, status=status.value)
+
+    @property
+    def launch_count(self):
+        return int(self.lib.mjpc_b200_launch_count(self.h))
+
+    @property
+    def last_kernel_ms(self):
+        return float(self.lib.mjpc_b200_last_kernel_ms(self.h))

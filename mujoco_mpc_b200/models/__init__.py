@@ -1,0 +1,346 @@
+"""Model/task definitions for the BASELINE configs, generated as MJCF text.
+
+The reference builds its robot XMLs at configure time by patching Menagerie /
+dm_control files that are NOT vendored (finding 2), so the
+models are restated here programmatically from the numbers that *are* in the
+reference tree (the ``.patch`` hunks and the task XMLs); every number that had
+to be filled in from outside the tree is marked ``[GUESS]``.
+
+  particle  : mjpc/test/testdata/particle.xml:30-63, particle_task.xml:6-33 (fully in tree)
+  cartpole  : mjpc/tasks/cartpole/cartpole.xml.patch:4-31, task.xml:8-47 (pole default class and
+              actuator are outside the patch context -> [GUESS] = dm_control suite values)
+  quadruped : mjpc/tasks/quadruped/a1.xml.patch:4-205, task_flat.xml:6-161 (collision default
+              classes hip/thigh/calf and 4 trunk collision geoms are outside the patch context
+              -> [GUESS] = Menagerie unitree_a1 values)
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .. import task as T
+from ..mjcf import GEOM_PLANE, compile_xml
+
+
+# ----------------------------------------------------------------------------- particle
+def particle_xml(copy_task=False) -> str:
+    return """
+<mujoco model="Particle Control">
+  <option timestep="0.01"><flag contact="disable"/></option>
+  <default>
+    <joint type="hinge" axis="0 0 1" limited="true" range="-.29 .29" damping="1"/>
+    <motor gear=".1" ctrlrange="-1 1" ctrllimited="true"/>
+  </default>
+  <custom>
+    <numeric name="task_risk" data="1.0"/>
+    <numeric name="agent_planner" data="0"/>
+    <numeric name="agent_horizon" data="1"/>
+    <numeric name="agent_timestep" data="0.1"/>
+    <numeric name="sampling_spline_points" data="11"/>
+    <numeric name="sampling_exploration" data="0.01"/>
+    <numeric name="residual_dummy1" data="0.05"/>
+    <numeric name="residual_dummy2" data="-0.1"/>
+  </custom>
+  <worldbody>
+    <body name="goal" mocap="true" pos="0.25 0 0.01" quat="1 0 0 0">
+      <geom type="sphere" size=".01" contype="0" conaffinity="0"/>
+    </body>
+    <geom name="ground" type="plane" pos="0 0 0" size=".3 .3 .1"/>
+    <body name="pointmass" pos="0 0 .01">
+      <joint name="root_x" type="slide" pos="0 0 0" axis="1 0 0"/>
+      <joint name="root_y" type="slide" pos="0 0 0" axis="0 1 0"/>
+      <geom name="pointmass" type="sphere" size=".01" mass=".3"/>
+      <site name="tip" pos="0 0 0" size="0.01"/>
+    </body>
+  </worldbody>
+  <actuator>
+    <motor name="x_motor" joint="root_x" gear="1" ctrllimited="true" ctrlrange="-1 1"/>
+    <motor name="y_motor" joint="root_y" gear="1" ctrllimited="true" ctrlrange="-1 1"/>
+  </actuator>
+  <sensor>
+    <user name="Position" dim="2" user="0 5.0 0.0 10.0"/>
+    <user name="Velocity" dim="2" user="0 0.1 0.0 1.0"/>
+    <framepos name="trace0" objtype="site" objname="tip"/>
+    <framepos name="position" objtype="site" objname="tip"/>
+    <framelinvel name="velocity" objtype="site" objname="tip"/>
+    <framepos name="goal" objtype="body" objname="goal"/>
+  </sensor>
+  <keyframe>
+    <key name="home" qpos="1.0 2.0" qvel="-1.0 -2.0"/>
+    <key name="ctrl_test" ctrl="0.1 0.2"/>
+  </keyframe>
+</mujoco>
+"""
+
+
+# ----------------------------------------------------------------------------- cartpole
+def cartpole_xml() -> str:
+    # pole class + actuator: [GUESS] dm_control suite/cartpole.xml (hinge axis 0 1 0, damping 2e-6
+    # overridden to 1e-4 by the patch; capsule 0..1 m, r=.045, mass .1; motor gear 10, ctrl +-1)
+    return """
+<mujoco model="Cart-Pole Swing-Up">
+  <option timestep="0.001"><flag contact="disable"/></option>
+  <default>
+    <default class="pole">
+      <joint type="hinge" axis="0 1 0" damping="2e-6"/>
+      <geom type="capsule" fromto="0 0 0 0 0 1" size="0.045" mass=".1"/>
+    </default>
+  </default>
+  <custom>
+    <numeric name="agent_planner" data="0"/>
+    <numeric name="agent_horizon" data="0.31"/>
+    <numeric name="agent_timestep" data="0.01"/>
+    <numeric name="sampling_spline_points" data="10"/>
+    <numeric name="sampling_exploration" data="0.5"/>
+    <numeric name="sampling_trajectories" data="8"/>
+    <numeric name="residual_Goal" data="0.0 -1.5 1.5"/>
+  </custom>
+  <worldbody>
+    <geom name="floor" pos="0 0 -.05" size="4 4 .2" type="plane"/>
+    <body name="cart" pos="0 0 1">
+      <joint name="slider" type="slide" limited="true" axis="1 0 0" range="-1.8 1.8" solreflimit=".08 1" damping="1.0e-4"/>
+      <geom name="cart" type="box" size="0.2 0.15 0.1" mass="1"/>
+      <body name="pole_1" childclass="pole">
+        <joint name="hinge_1" damping="1.0e-4"/>
+        <geom name="pole_1"/>
+        <site name="tip" pos="0 0 1"/>
+      </body>
+    </body>
+  </worldbody>
+  <actuator>
+    <motor name="slide" joint="slider" gear="10" ctrllimited="true" ctrlrange="-1 1"/>
+  </actuator>
+  <sensor>
+    <user name="Vertical" dim="1" user="6 10.0 0 100.0 0.01"/>
+    <user name="Centered" dim="1" user="6 10.0 0 100.0 0.1"/>
+    <user name="Velocity" dim="1" user="0 0.1 0.0 1.0"/>
+    <user name="Control" dim="1" user="0 0.1 0.0 1.0"/>
+    <jointpos name="slider_pos" joint="slider"/>
+    <jointpos name="hinge_pos" joint="hinge_1"/>
+    <framepos name="trace0" objtype="site" objname="tip"/>
+    <framepos name="position" objtype="site" objname="tip"/>
+    <framelinvel name="velocity" objtype="site" objname="tip"/>
+  </sensor>
+  <keyframe>
+    <key name="home" qpos="1 0"/>
+  </keyframe>
+</mujoco>
+"""
+
+
+# ----------------------------------------------------------------------------- quadruped (A1, flat)
+_LEGS = (  # name, hip body name, x sign, y sign, joint prefix, foot geom name, site name
+    ("FR", "FR_hip", +1, -1, "FR", "FR", "FR"),
+    ("FL", "FL_hip", +1, +1, "FL", "FL", "FL"),
+    ("RR", "HR_hip", -1, -1, "RR", "HR", "RR"),
+    ("RL", "HL_hip", -1, +1, "RL", "HL", "RL"),
+)
+# hip inertial quaternions per leg (a1.xml.patch:87-190)
+_HIP_IQUAT = {"FR": "0.507528 0.506268 0.491507 0.494499", "FL": "0.494499 0.491507 0.506268 0.507528",
+              "RR": "0.491507 0.494499 0.507528 0.506268", "RL": "0.506268 0.507528 0.494499 0.491507"}
+
+
+def _leg_xml(name, hipbody, sx, sy, jp, footgeom, sitename):
+    side = "hip_left" if sy > 0 else "hip_right"
+    thigh_q = "0.999125 %g -0.0409531 %g" % (0.00256393 * sy, 0.00806091 * sy)
+    extra = ('<geom class="collision" size="0.04 0.04" pos="0 0.055 0" quat="1 1 0 0" type="cylinder"/>'
+             if name == "FL" else "")  # a1.xml.patch:121 (only FL has the explicit extra cylinder)
+    return f"""
+      <body name="{hipbody}" pos="{0.183 * sx:g} {0.047 * sy:g} 0">
+        <inertial mass="0.696" pos="{-0.003311 * sx:g} {0.000635 * sy:g} 3.1e-05" quat="{_HIP_IQUAT[name]}"
+            diaginertia="0.000807752 0.00055293 0.000468983"/>
+        <joint class="abduction" name="{jp}_hip_joint"/>
+        <geom class="{side}"/>
+        {extra}
+        <body name="{jp}_thigh" pos="0 {0.08505 * sy:g} 0">
+          <inertial mass="1.013" pos="-0.003237 {-0.022327 * sy:g} -0.027326" quat="{thigh_q}"
+              diaginertia="0.00555739 0.00513936 0.00133944"/>
+          <joint class="hip" name="{jp}_thigh_joint"/>
+          <geom class="thigh1"/><geom class="thigh2"/><geom class="thigh3"/>
+          <body name="{jp}_calf" pos="0 0 -0.2">
+            <inertial mass="0.226" pos="0.00472659 0 -0.131975" quat="0.706886 0.017653 0.017653 0.706886"
+                diaginertia="0.00340344 0.00339393 3.54834e-05"/>
+            <joint class="knee" name="{jp}_calf_joint"/>
+            <geom class="calf1"/><geom class="calf2"/>
+            <geom name="{footgeom}" class="foot"/>
+            <site name="{sitename}" pos="0 0 -0.2" type="sphere" size=".015"/>
+          </body>
+        </body>
+      </body>"""
+
+
+def quadruped_flat_xml(horizon=0.63, trajectories=256) -> str:
+    legs = "".join(_leg_xml(*leg) for leg in _LEGS)
+    acts = "".join(f'<general class="torque" name="{p}_{j}" joint="{p}_{j}_joint"/>'
+                   for p in ("FR", "FL", "RR", "RL") for j in ("hip", "thigh", "calf"))
+    return f"""
+<mujoco model="Quadruped">
+  <compiler angle="radian"/>
+  <option cone="elliptic" impratio="10"/>
+  <custom>
+    <numeric name="agent_planner" data="0"/>
+    <numeric name="agent_horizon" data="{horizon}"/>
+    <numeric name="agent_timestep" data="0.01"/>
+    <numeric name="sampling_spline_points" data="3"/>
+    <numeric name="sampling_trajectories" data="{trajectories}"/>
+    <numeric name="sampling_exploration" data="0.04"/>
+    <numeric name="residual_select_Gait" data="0"/>
+    <numeric name="residual_select_Gait switch" data="1"/>
+    <numeric name="residual_Cadence" data="2 0 4"/>
+    <numeric name="residual_Amplitude" data=".06 0 0.2"/>
+    <numeric name="residual_Duty ratio" data="0 0 1"/>
+    <numeric name="residual_Walk speed" data="0 0 4"/>
+    <numeric name="residual_Walk turn" data="0 -2 2"/>
+    <numeric name="residual_select_Flip dir" data="0"/>
+    <numeric name="residual_select_Biped type" data="0"/>
+    <numeric name="residual_Heading" data="0 -3.14 3.14"/>
+    <numeric name="residual_Arm posture" data=".03 0 1"/>
+  </custom>
+  <default>
+    <default class="torque">
+      <general gainprm="40" ctrllimited="true" ctrlrange="-1 1"/>
+    </default>
+    <default class="task"><site size=".02" group="5"/></default>
+    <default class="prop"><geom type="box"/></default>
+    <default class="a1">
+      <geom friction="0.6" margin="0.001" condim="1"/>
+      <joint axis="0 1 0" damping="2" armature="0.01" frictionloss="0.2" limited="true"/>
+      <default class="abduction"><joint axis="1 0 0" damping="1" range="-0.802851 0.802851"/></default>
+      <default class="hip"><joint range="-1.9472 3.28879" ref="-0.9"/></default>
+      <default class="knee"><joint range="-0.89653 0.883702" ref="1.8"/></default>
+      <default class="collision">
+        <geom group="3" type="capsule"/>  <!-- [GUESS] Menagerie unitree_a1 collision classes below -->
+        <default class="hip_left"><geom size="0.04 0.04" quat="1 1 0 0" type="cylinder" pos="0 0.055 0"/></default>
+        <default class="hip_right"><geom size="0.04 0.04" quat="1 1 0 0" type="cylinder" pos="0 -0.055 0"/></default>
+        <default class="thigh1"><geom size="0.015" fromto="-0.02 0 0 -0.02 0 -0.16"/></default>
+        <default class="thigh2"><geom size="0.015" fromto="0 0 0 -0.02 0 -0.1"/></default>
+        <default class="thigh3"><geom size="0.015" fromto="-0.02 0 -0.16 0 0 -0.2"/></default>
+        <default class="calf1"><geom size="0.01" fromto="0 0 0 0.02 0 -0.13"/></default>
+        <default class="calf2"><geom size="0.01" fromto="0.02 0 -0.13 0 0 -0.2"/></default>
+        <default class="foot">
+          <geom type="sphere" size="0.02" pos="0 0 -0.2" priority="1" solimp="0.015 1 0.031" condim="6"
+                friction="0.8 0.02 0.01"/>
+        </default>
+      </default>
+    </default>
+  </default>
+  <worldbody>
+    <geom name="floor" size="0 0 0.1" pos="0 0 -0.01" type="plane"/>
+    <body name="goal" mocap="true" pos=".3 0 0.26">
+      <geom size="0.12" contype="0" conaffinity="0" group="2"/>
+    </body>
+    <body name="box" mocap="true" pos="-2.5 0 0">
+      <geom name="box" class="prop" size="1 1 0.3"/>
+    </body>
+    <geom name="ramp" class="prop" pos="3.13 2.5 -.18" size="1.6 1 .5" euler="0 -0.2 0"/>
+    <geom name="hill" class="prop" pos="6 6 -5.5" size="6" type="sphere"/>
+    <body name="trunk" pos="0.0 0.0 0.5" quat="1 0 0 0" childclass="a1">
+      <site name="torso"/>
+      <site name="head" class="task" pos=".3 0 0"/>
+      <freejoint/>
+      <inertial mass="4.713" pos="0 0.0041 -0.0005"
+          fullinertia="0.0158533 0.0377999 0.0456542 -3.66e-05 -6.11e-05 -2.75e-05"/>
+      <geom class="collision" size="0.125 0.04 0.057" type="box"/>
+      <geom class="collision" quat="1 0 1 0" pos="0 -0.04 0" size="0.058 0.125" type="cylinder"/>
+      <!-- [GUESS] 4 trunk geoms outside the patch context (Menagerie unitree_a1) -->
+      <geom class="collision" quat="1 0 1 0" pos="0 0.04 0" size="0.058 0.125" type="cylinder"/>
+      <geom class="collision" pos="0.25 0 0" size="0.005 0.06 0.05" type="box"/>
+      <geom class="collision" pos="0.25 0.06 -0.01" size="0.009 0.035"/>
+      <geom class="collision" pos="0.25 -0.06 -0.01" size="0.009 0.035"/>
+      <geom class="collision" pos="0.25 0 -0.05" size="0.005 0.06" quat="1 1 0 0"/>
+      <geom class="collision" pos="0.255 0 0.0355" size="0.021 0.052" quat="1 1 0 0"/>
+      {legs}
+    </body>
+  </worldbody>
+  <actuator>{acts}</actuator>
+  <sensor>
+    <user name="Upright" dim="3" user="6 1 0 3 0.05"/>
+    <user name="Height" dim="1" user="6 1 0 3 0.04"/>
+    <user name="Position" dim="3" user="2 0.2 0 0.5 0.1"/>
+    <user name="Gait" dim="4" user="6 2 0 10 0.03"/>
+    <user name="Balance" dim="2" user="2 0.2 0 0.3 0.1"/>
+    <user name="Effort" dim="12" user="0 0.03 0.0 0.1"/>
+    <user name="Posture" dim="12" user="0 0.02 0.0 0.1"/>
+    <user name="Orientation" dim="2" user="0 0 0 .03"/>
+    <user name="Angmom" dim="3" user="0 0 0 .03"/>
+    <framepos name="torso_pos" objtype="site" objname="torso"/>
+    <framepos name="FR_pos" objtype="site" objname="FR"/>
+    <framepos name="FL_pos" objtype="site" objname="FL"/>
+    <framepos name="RR_pos" objtype="site" objname="RR"/>
+    <framepos name="RL_pos" objtype="site" objname="RL"/>
+    {"".join(f'<jointpos name="pos_{p}_{j}_joint" joint="{p}_{j}_joint"/>' for p in ("FR", "FL", "RR", "RL") for j in ("hip", "thigh", "calf"))}
+    <touch name="FR_touch" site="FR"/><touch name="FL_touch" site="FL"/>
+    <touch name="RR_touch" site="RR"/><touch name="RL_touch" site="RL"/>
+    <framepos name="trace0" objtype="site" objname="head"/>
+    <subtreecom name="torso_subtreecom" body="trunk"/>
+    <subtreelinvel name="torso_subtreelinvel" body="trunk"/>
+    <subtreelinvel name="torso_angmom" body="trunk"/>
+  </sensor>
+  <keyframe>
+    <key name="home" qpos="0 0 0.26 1 0 0 0
+         -0.000341931 0.0181576 -0.0268335 0.00160968 0.0247957 -0.0270045
+         0.00191398 -0.033048 -0.0675298 -0.00199489 -0.0374747 -0.0681862"/>
+    <key name="crouch" qpos="-0.0501827 0.00107117 0.143925 1 0 0 0 0 0 -0.5 0 0 -0.5 0 0 -0.5 0 0 -0.5"/>
+  </keyframe>
+</mujoco>
+"""
+
+
+def _robot_vs_world_only(m, g1, g2):
+    """Keep only pairs with exactly one static (world-welded) geom: robot self-collision pairs are
+    dropped (DESIGN.md 'Out of scope': most need capsule/cylinder/box convex tests)."""
+    s1 = m.body_weldid[m.geom_bodyid[g1]] == 0
+    s2 = m.body_weldid[m.geom_bodyid[g2]] == 0
+    return bool(s1) != bool(s2)
+
+
+def _ray_geoms(m):
+    """Group-0 geoms are what mjpc::Ground ray-casts against (utilities.cc:556-574)."""
+    return np.array([g for g in range(m.ngeom) if m.geom_group[g] == 0], np.int32)
+
+
+def load(name: str, agent_timestep: bool = True, **kw):
+    """Compile one of the built-in tasks. Returns the Model with task ids / state filled in.
+
+    agent_timestep=True applies Agent's override of opt.timestep by the ``agent_timestep`` numeric
+    (mjpc/agent.cc:288); False keeps the model's own <option timestep> (as mjpc/test/agent/rollout_test.cc does)."""
+    if name in ("particle", "particle_copy"):
+        m = compile_xml(particle_xml())
+        m.task_residual_id = T.RESIDUAL_PARTICLE if name == "particle" else T.RESIDUAL_PARTICLE_COPY
+        m.task_ids = np.zeros(1, np.int32)
+        m.task_state = np.zeros(1)
+    elif name == "cartpole":
+        m = compile_xml(cartpole_xml())
+        m.task_residual_id = T.RESIDUAL_CARTPOLE
+        m.task_ids = np.zeros(1, np.int32)
+        m.task_state = np.zeros(1)
+    elif name == "quadruped":
+        m = compile_xml(quadruped_flat_xml(**kw), pair_filter=_robot_vs_world_only)
+        m.task_residual_id = T.RESIDUAL_QUADRUPED_FLAT
+        ids = np.zeros(T.QI_SIZE, np.int32)
+        ids[T.QI_TORSO_BODY] = m.body_names.index("trunk")
+        ids[T.QI_HEAD_SITE] = m.site_names.index("head")
+        ids[T.QI_GOAL_MOCAP] = m.body_mocapid[m.body_names.index("goal")]
+        for k, f in enumerate(("FL", "HL", "FR", "HR")):  # quadruped.cc:560-566
+            ids[T.QI_FOOT_GEOM + k] = m.geom_names.index(f)
+        pn = [p[len("residual_"):] for p in m.task_parameter_names]
+        ids[T.QI_PARAM_GAIT] = pn.index("select_Gait")
+        ids[T.QI_PARAM_BIPED_TYPE] = pn.index("select_Biped type")
+        ids[T.QI_PARAM_CADENCE] = pn.index("Cadence")
+        ids[T.QI_PARAM_AMPLITUDE] = pn.index("Amplitude")
+        ids[T.QI_PARAM_DUTY] = pn.index("Duty ratio")
+        ids[T.QI_PARAM_ARM_POSTURE] = pn.index("Arm posture")
+        ids[T.QI_PARAM_HEADING] = pn.index("Heading")
+        ids[T.QI_PARAM_FLIP_DIR] = pn.index("select_Flip dir")
+        ids[T.QI_KEY_HOME] = m.key_names.index("home")
+        ids[T.QI_KEY_CROUCH] = m.key_names.index("crouch")
+        m.task_ids = ids
+        m.task_state = T.quadruped_state_block(float(np.linalg.norm(m.opt_gravity)),
+                                               float(m.task_parameters[pn.index("Cadence")]))
+    else:
+        raise KeyError(name)
+    m.task_name = name
+    # agent settings (mjpc/agent.cc:90-107): planning timestep / integrator / horizon
+    if agent_timestep and "agent_timestep" in m.numeric:
+        m.opt_timestep = float(m.numeric["agent_timestep"][0])
+    m.ray_geoms = _ray_geoms(m)
+    return m
