@@ -1,0 +1,271 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: Quadruped (flat) Predictive Sampling, 256 candidates x 64-step horizon, fp32.
+
+A "step" is one planning iteration's rollout batch (SamplingPlanner::Rollouts + ranking): 256 x 64 = 16384
+simulated environment steps per GPU.  Metric: env-steps/sec (BASELINE.json).  With --gpus N every rank rolls out
+its own shard of 256 candidates (weak scaling, candidates are independent units) and the per-candidate returns
+are exchanged with one NCCL all-gather per iteration.
+
+  value      device-timed throughput, inputs resident in HBM (CUDA events on the engine's stream, per launch)
+  e2e        same metric through the public call (Engine.rollout_spline + winner fetch) with HOST buffers:
+             H2D of state/mocap/knots and D2H of returns/order/winner trajectory inside the timed region
+  roofline   dominant kernel (rollout_kernel) vs the measured HBM copy peak; algorithmic bytes per env-step are
+             SURVEY.md 8(d)'s figure.  The kernel is latency-bound by construction.
+  cpu_baseline  the CPU oracle (a port, the reference binary cannot be built offline) on this box's host cores.
+
+--impl reference times that CPU path as its own arm.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+N_CAND, HORIZON, INTERP = 256, 64, 2
+METRIC, UNIT = "env-steps/sec", "env-steps/s"
+WORKLOAD = "Quadruped (flat) Predictive Sampling, 256 candidates x 64-step horizon, fp32"
+
+
+def load_inputs(n_iter, cand_offset=0, n_cand=N_CAND):
+    from conftest import get_model, mocap_of
+    from mujoco_mpc_b200.planner import candidate_knots
+    m = get_model("quadruped")
+    state = np.concatenate([m.key_qpos[0], np.zeros(m.nv)])
+    P = int(m.numeric["sampling_spline_points"][0])
+    sigma = float(m.numeric["sampling_exploration"][0])
+    kt = np.arange(P) * (HORIZON - 1) * m.opt_timestep / (P - 1)
+    cr = np.asarray(m.actuator_ctrlrange).reshape(-1, 2)
+    knots = []
+    for it in range(n_iter):
+        k = candidate_knots(np.zeros((P, m.nu)), sigma, cr, it, cand_offset + n_cand)[cand_offset:]
+        knots.append(k.astype(np.float32))
+    return m, state, mocap_of(m), knots, kt
+
+
+def algorithmic_bytes_per_env_step(m, P):
+    ds, nu, nr, ntr = m.nq + m.nv, m.nu, m.task_num_residual, m.task_num_trace
+    return 4 * (ds + nu + nr + 3 * ntr + 2) + 4 * (P * nu + ds + 7 * m.nmocap + m.nuserdata) / HORIZON
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_baseline_run(steps, warmup, threads):
+    """The reference's CPU ThreadPool path restated by the oracle (fp64 = the reference's arithmetic)."""
+    from mujoco_mpc_b200.blob import to_blob
+    from oracle import pyoracle
+    m, state, mocap, knots, kt = load_inputs(steps + warmup)
+    o = pyoracle.Oracle(to_blob(m), m, 64)
+    times = []
+    for it in range(steps + warmup):
+        t0 = time.perf_counter()
+        r = o.rollout_spline(state, 0.0, mocap, knots[it], kt, INTERP, HORIZON, nthreads=threads, full=False)
+        np.argsort(r["returns"], kind="stable")
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return float(np.mean(times)), r["returns"]
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    ms, _ = cpu_baseline_run(args.steps, args.warmup, threads)
+    value = N_CAND * HORIZON / ms
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "backend": "CPU oracle (restatement of mj_step + Trajectory::Rollout, ThreadPool dispatch); "
+                       "the reference binary cannot be built offline (MuJoCo is fetched at configure time)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": "full workload: 256 candidates x 64 steps per step"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", 0)); local = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the engine has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from mujoco_mpc_b200 import build
+    from mujoco_mpc_b200.engine import Engine
+    if rank == 0:
+        build.build()
+    if world > 1:
+        dist.barrier()
+    n_iter = args.steps + args.warmup
+    m, state, mocap, knots, kt = load_inputs(n_iter, cand_offset=rank * N_CAND)
+    P = knots[0].shape[1]
+    eng = Engine(m, N_CAND, HORIZON, device=local)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    gathered = torch.empty(world * N_CAND, dtype=torch.float32, device="cuda") if world > 1 else None
+    local_ret = torch.empty(N_CAND, dtype=torch.float32, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-timed region: inputs resident, one event pair per launch, L2 flushed in between
+    eng.upload_spline_inputs(state, 0.0, mocap, knots[0], kt, INTERP, HORIZON)
+    eng.sync()
+    clocks = ClockSampler(local)
+    kern_ms, coll_ms = [], []
+    launches0 = 0
+    for it in range(n_iter):
+        if it == args.warmup:
+            barrier()
+            clocks.start()
+            launches0 = eng.launch_count
+            t_wall0 = time.perf_counter()
+        flush.zero_()
+        torch.cuda.synchronize()
+        eng.launch_resident()
+        eng.sync()
+        k_ms = eng.last_kernel_ms
+        c_ms = 0.0
+        if world > 1:
+            ret, _, _ = eng.read_returns()
+            local_ret.copy_(torch.from_numpy(ret))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dist.all_gather_into_tensor(gathered, local_ret)
+            e1.record()
+            torch.cuda.synchronize()
+            c_ms = e0.elapsed_time(e1)
+        if it >= args.warmup:
+            kern_ms.append(k_ms); coll_ms.append(c_ms)
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    clk = clocks.stop()
+    gpu_launches = eng.launch_count - launches0
+    total_ms = float(np.sum(kern_ms) + np.sum(coll_ms))
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * N_CAND * HORIZON / (ms_per_step * 1e-3)
+
+    # ---------------- end-to-end through the public call with host buffers
+    ds, nu, nr, ntr = eng.ds, eng.nu, eng.nr, eng.ntr
+    h2d = 4 * (ds + 7 * m.nmocap + eng.info.task_state_size + N_CAND * P * nu + P)
+    d2h = N_CAND * (4 + 4 + 1) + HORIZON * (4 * (ds + nu + nr + ntr + 1) + 8)
+    for it in range(args.warmup):
+        eng.rollout_spline(state, 0.0, mocap, knots[it], kt, INTERP, HORIZON)
+    barrier()
+    t0 = time.perf_counter()
+    for it in range(args.steps):
+        ret, fail, order = eng.rollout_spline(state, 0.0, mocap, knots[args.warmup + it], kt, INTERP, HORIZON)
+        best = eng.fetch_trajectory(int(order[0]))
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * N_CAND * HORIZON / float(te.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---------------- parity + roofline + CPU baseline (rank 0)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    bytes_per_launch = algorithmic_bytes_per_env_step(m, P) * N_CAND * HORIZON
+    kernel_ms = float(np.mean(kern_ms))
+    achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": "rollout_kernel", "kernel_ms": kernel_ms, "peak_source": peak_src,
+                "algorithmic_bytes_per_env_step": algorithmic_bytes_per_env_step(m, P),
+                "note": "latency/occupancy-bound by construction: 256 warps, 64 dependent steps each (DESIGN.md)"}
+    prof = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    if os.path.exists(prof):
+        roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+    cpu = None
+    parity = None
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        cpu_s, cpu_ret = cpu_baseline_run(3, 1, threads)
+        cpu = {"value": N_CAND * HORIZON / cpu_s, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "3 full steps (256 candidates x 64 steps each), fp64 oracle, ThreadPool over all host threads"}
+        gret, _, _ = eng.rollout_spline(state, 0.0, mocap, knots[3], kt, INTERP, HORIZON)
+        rel = np.abs(gret - cpu_ret) / np.maximum(np.abs(cpu_ret), 1e-12)
+        parity = {"max_rel_return_err_vs_fp64_oracle": float(rel.max()), "mean_rel": float(rel.mean()),
+                  "argmin_agrees": bool(int(np.argmin(gret)) == int(np.argmin(cpu_ret)))}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "candidates_per_gpu": N_CAND, "horizon": HORIZON, "spline_points": P,
+                       "l2": "flushed between timed iterations (256 MB memset)", "sharding": "candidates, %d per GPU" % N_CAND,
+                       "e2e_call": "Engine.rollout_spline (mjpc_b200_rollout_spline) + fetch_trajectory(winner), host buffers"},
+            "clocks": clk, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(gpu_launches), "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
+            "wall_s_timed_region": wall}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

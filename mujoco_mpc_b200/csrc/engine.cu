@@ -152,7 +152,7 @@ int read_back(mjpc_b200* h, int N, float* returns, uint8_t* failure, int* order)
   CUDA_TRY(cudaMemcpyAsync(ho, h->d_order, (size_t)N * 4, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaMemcpyAsync(hf, h->d_failure, (size_t)N, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
-  cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
+  if (cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1) != cudaSuccess) cudaGetLastError();
   if (returns) std::memcpy(returns, hr, (size_t)N * 4);
   if (order) std::memcpy(order, ho, (size_t)N * 4);
   if (failure) std::memcpy(failure, hf, (size_t)N);
@@ -315,7 +315,7 @@ int mjpc_b200_launch_resident(mjpc_b200_t* h) {
 int mjpc_b200_sync(mjpc_b200_t* h) {
   if (!h) return fail(MJPC_B200_ERR_BAD_ARGUMENT, "sync: null");
   CUDA_TRY(cudaStreamSynchronize(h->stream));
-  cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
+  if (h->lastN > 0 && cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1) != cudaSuccess) cudaGetLastError();
   return 0;
 }
 
