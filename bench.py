@@ -36,20 +36,40 @@ METRIC, UNIT = "env-steps/sec", "env-steps/s"
 WORKLOAD = "Quadruped (flat) Predictive Sampling, 256 candidates x 64-step horizon, fp32"
 
 
-def load_inputs(n_iter, cand_offset=0, n_cand=N_CAND):
+BURN_IN = 30  # planning iterations (untimed, part of set-up) that take the zero policy to the steady-state nominal
+
+
+class OracleBackend:
+    """CPU oracle behind the same rollout_spline signature (only used by the CPU arms)."""
+
+    def __init__(self, m, threads):
+        from mujoco_mpc_b200.blob import to_blob
+        from oracle import pyoracle
+        self.o, self.threads = pyoracle.Oracle(to_blob(m), m, 64), threads
+
+    def rollout_spline(self, state, time, mocap, knots, kt, interp, H):
+        r = self.o.rollout_spline(state, time, mocap, knots, kt, interp, H, nthreads=self.threads, full=False)
+        return r["returns"], r["failure"], np.argsort(r["returns"], kind="stable")
+
+
+def load_inputs(backend, n_iter, rank=0, n_cand=N_CAND):
+    """Model at the home keyframe (testspeed.cc:71-76); nominal spline = the planner's steady state: BURN_IN
+    Predictive-Sampling iterations starting from the repeated initial action; candidates of timed
+    iteration i = nominal + Philox noise with counter (BURN_IN + i, candidate, knot, dof), candidate 0 un-noised."""
     from conftest import get_model, mocap_of
-    from mujoco_mpc_b200.planner import candidate_knots
+    from mujoco_mpc_b200.planner import SamplingPlanner, candidate_knots
     m = get_model("quadruped")
     state = np.concatenate([m.key_qpos[0], np.zeros(m.nv)])
-    P = int(m.numeric["sampling_spline_points"][0])
-    sigma = float(m.numeric["sampling_exploration"][0])
-    kt = np.arange(P) * (HORIZON - 1) * m.opt_timestep / (P - 1)
-    cr = np.asarray(m.actuator_ctrlrange).reshape(-1, 2)
-    knots = []
-    for it in range(n_iter):
-        k = candidate_knots(np.zeros((P, m.nu)), sigma, cr, it, cand_offset + n_cand)[cand_offset:]
-        knots.append(k.astype(np.float32))
-    return m, state, mocap_of(m), knots, kt
+    mocap = mocap_of(m)
+    pl = SamplingPlanner(m, backend, num_trajectory=n_cand, horizon=HORIZON, seed=0x5EED + 7919 * rank)
+    pl.reset()
+    pl.set_state(state, 0.0, mocap)
+    for _ in range(BURN_IN):
+        pl.optimize_policy()
+    pl.make_candidates()  # resample the winner onto the knot grid
+    knots = [candidate_knots(pl.values, pl.sigma, pl.ctrlrange, BURN_IN + it, n_cand, seed=pl.seed).astype(np.float32)
+             for it in range(n_iter)]
+    return m, state, mocap, knots, pl.times.copy(), float(np.min(pl.returns))
 
 
 def algorithmic_bytes_per_env_step(m, P):
@@ -90,19 +110,17 @@ class ClockSampler:
 
 def cpu_baseline_run(steps, warmup, threads):
     """The reference's CPU ThreadPool path restated by the oracle (fp64 = the reference's arithmetic)."""
-    from mujoco_mpc_b200.blob import to_blob
-    from oracle import pyoracle
-    m, state, mocap, knots, kt = load_inputs(steps + warmup)
-    o = pyoracle.Oracle(to_blob(m), m, 64)
+    from conftest import get_model
+    be = OracleBackend(get_model("quadruped"), threads)
+    m, state, mocap, knots, kt, _ = load_inputs(be, steps + warmup)
     times = []
     for it in range(steps + warmup):
         t0 = time.perf_counter()
-        r = o.rollout_spline(state, 0.0, mocap, knots[it], kt, INTERP, HORIZON, nthreads=threads, full=False)
-        np.argsort(r["returns"], kind="stable")
+        ret, _, _ = be.rollout_spline(state, 0.0, mocap, knots[it], kt, INTERP, HORIZON)
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
-    return float(np.mean(times)), r["returns"]
+    return float(np.mean(times)), (state, mocap, knots[-1], kt, ret)
 
 
 def run_reference(args, rank, world):
@@ -150,9 +168,10 @@ def main():
     if world > 1:
         dist.barrier()
     n_iter = args.steps + args.warmup
-    m, state, mocap, knots, kt = load_inputs(n_iter, cand_offset=rank * N_CAND)
+    from conftest import get_model
+    eng = Engine(get_model("quadruped"), N_CAND, HORIZON, device=local)
+    m, state, mocap, knots, kt, nominal_return = load_inputs(eng, n_iter, rank=rank)
     P = knots[0].shape[1]
-    eng = Engine(m, N_CAND, HORIZON, device=local)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     gathered = torch.empty(world * N_CAND, dtype=torch.float32, device="cuda") if world > 1 else None
     local_ret = torch.empty(N_CAND, dtype=torch.float32, device="cuda")
@@ -246,10 +265,12 @@ def main():
     parity = None
     if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        cpu_s, cpu_ret = cpu_baseline_run(3, 1, threads)
+        cpu_s, (c_state, c_mocap, c_knots, c_kt, cpu_ret) = cpu_baseline_run(3, 1, threads)
         cpu = {"value": N_CAND * HORIZON / cpu_s, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "3 full steps (256 candidates x 64 steps each), fp64 oracle, ThreadPool over all host threads"}
-        gret, _, _ = eng.rollout_spline(state, 0.0, mocap, knots[3], kt, INTERP, HORIZON)
+               "sample": "3 full steps (256 candidates x 64 steps each) after its own %d-iteration burn-in, fp64 oracle, "
+                         "ThreadPool over all host threads" % BURN_IN}
+        # parity on identical inputs: the CPU arm's last candidate set through the device path
+        gret, _, _ = eng.rollout_spline(c_state, 0.0, c_mocap, c_knots, c_kt, INTERP, HORIZON)
         rel = np.abs(gret - cpu_ret) / np.maximum(np.abs(cpu_ret), 1e-12)
         parity = {"max_rel_return_err_vs_fp64_oracle": float(rel.max()), "mean_rel": float(rel.mean()),
                   "argmin_agrees": bool(int(np.argmin(gret)) == int(np.argmin(cpu_ret)))}
@@ -257,6 +278,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "candidates_per_gpu": N_CAND, "horizon": HORIZON, "spline_points": P,
+                       "nominal": "steady-state policy after %d planning iterations from the zero policy (return %.4f)" % (BURN_IN, nominal_return),
                        "l2": "flushed between timed iterations (256 MB memset)", "sharding": "candidates, %d per GPU" % N_CAND,
                        "e2e_call": "Engine.rollout_spline (mjpc_b200_rollout_spline) + fetch_trajectory(winner), host buffers"},
             "clocks": clk, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

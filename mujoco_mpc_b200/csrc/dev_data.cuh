@@ -26,8 +26,8 @@ namespace mjpc_dev {
   X(con_g1, M.maxcon) X(con_g2, M.maxcon) X(con_adr, M.maxcon) X(efc_J, M.maxefc * M.nv)                          \
   X(efc_W, M.maxefc * M.nv) X(efc_pos, M.maxefc) X(efc_margin, M.maxefc) X(efc_diag, M.maxefc)                    \
   X(efc_R, M.maxefc) X(efc_D, M.maxefc) X(efc_K, M.maxefc) X(efc_B, M.maxefc) X(efc_imp, M.maxefc)                \
-  X(efc_aref, M.maxefc) X(efc_force, M.maxefc) X(efc_jar, M.maxefc) X(efc_Jv, M.maxefc) X(efc_floss, M.maxefc)    \
-  X(efc_type, M.maxefc) X(efc_id, M.maxefc) X(efc_state, M.maxefc) X(efc_item, M.maxefc) X(efc_hc, 36 * M.maxcon) \
+  X(efc_aref, M.maxefc) X(efc_hw, M.maxefc) X(efc_force, M.maxefc) X(efc_jar, M.maxefc) X(efc_Jv, M.maxefc) X(efc_floss, M.maxefc)    \
+  X(efc_type, M.maxefc) X(efc_id, M.maxefc) X(efc_state, M.maxefc) X(efc_item, M.maxefc) X(efc_hc, 36 * M.maxcon) X(con_mlo, M.maxcon) X(con_mhi, M.maxcon) \
   X(residual, M.num_residual) X(knots, P * M.nu) X(knot_times, P) X(xnom, M.nq + M.nv) X(dx, 2 * M.nv)
 
 enum DataArrayId {
@@ -56,6 +56,7 @@ inline DevLayout make_layout(const DevModel& M, int P) {
 constexpr unsigned kFull = 0xffffffffu;
 constexpr float kMinVal = 1e-15f;
 constexpr float kMaxVal = 1e10f;
+constexpr float kTolFloor = 1e-6f;  // fp32 floor on opt.tolerance (same rule as the oracle's fp32 instantiation)
 constexpr float kMinImp = 0.0001f, kMaxImp = 0.9999f, kMinMu = 1e-5f;
 enum { CNSTR_FRICTION_DOF = 0, CNSTR_LIMIT_JOINT, CNSTR_CONTACT_FRICTIONLESS, CNSTR_CONTACT_ELLIPTIC };
 enum { STATE_SATISFIED = 0, STATE_QUADRATIC, STATE_LINEARNEG, STATE_LINEARPOS, STATE_CONE };
@@ -67,7 +68,7 @@ struct Ctx {
   const int* mi;    // model ints (shared memory)
   float* d;         // this warp's data block (shared memory)
   int lane;
-  int ncon, nefc, nitem, niter;
+  int ncon, nefc, nitem, niter, nlim;
   int warn;
   float time;
 };
@@ -217,6 +218,59 @@ __device__ __noinline__ void warp_chol_solve(float* x, const float* Lm, const fl
   if (lane < n) x[lane] = r0;
   if (lane + 32 < n) x[lane + 32] = r1;
   __syncwarp();
+}
+// ---- register-resident variant for compile-time N <= 32: lane i keeps row i of the matrix in registers,
+// columns are broadcast with shuffles (N(N-1)/2 SHFL + FMA), then L is written back to shared memory and
+// L L^T x = b is solved (forward substitution from registers, backward substitution from shared memory rows).
+template <int N>
+__device__ __forceinline__ void warp_chol_factor_solve_reg(float* A, float* x, const float* b, int lane) {
+  float row[N], il[N];
+  const int li = lane < N ? lane : N - 1;
+#pragma unroll
+  for (int k = 0; k < N; k++) row[k] = A[li * N + k];
+  float y = b[li];
+#pragma unroll
+  for (int j = 0; j < N; j++) {
+    float p = __shfl_sync(kFull, row[j], j);
+    if (p < kMinVal) p = kMinVal;
+    const float l = sqrtf(p);
+    il[j] = 1.0f / l;
+    row[j] = (lane == j) ? l : row[j] * il[j];
+#pragma unroll
+    for (int k = j + 1; k < N; k++) {
+      const float lkj = __shfl_sync(kFull, row[j], k);
+      row[k] -= row[j] * lkj;
+    }
+  }
+  if (lane < N) {
+#pragma unroll
+    for (int k = 0; k < N; k++)
+      if (k <= lane) A[lane * N + k] = row[k];
+  }
+#pragma unroll
+  for (int i = 0; i < N; i++) {  // forward: L y = b
+    const float yi = __shfl_sync(kFull, y, i) * il[i];
+    if (lane == i) y = yi;
+    if (lane > i) y -= row[i] * yi;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = N - 1; i >= 0; i--) {  // backward: L^T x = y
+    const float xi = __shfl_sync(kFull, y, i) * il[i];
+    if (lane == i) y = xi;
+    if (lane < i) y -= A[i * N + lane] * xi;
+  }
+  if (lane < N) x[lane] = y;
+  __syncwarp();
+}
+
+// factor A (destroyed, holds L afterwards) and solve A x = b; dispatches to the register variant for the
+// dof counts of the built-in models
+__device__ __noinline__ void warp_chol_factor_solve(float* A, float* inv, float* x, const float* b, int n, int lane) {
+  if (n == 18) { warp_chol_factor_solve_reg<18>(A, x, b, lane); return; }
+  if (n == 2) { warp_chol_factor_solve_reg<2>(A, x, b, lane); return; }
+  warp_chol(A, inv, n, lane);
+  warp_chol_solve(x, A, inv, b, n, lane);
 }
 #endif  // __CUDACC__
 

@@ -37,9 +37,12 @@ namespace mjpc_dev {
 //   body_dofmask_lo/hi   : bitmask of the dofs on the chain from the root to the body
 //   mpair_i/mpair_j      : (dof, ancestor-or-self dof) pairs = the structurally non-zero entries of M
 //   floss_dof            : dofs with frictionloss > 0;  limit_jnt: limited slide/hinge joints
+//   hpair_i/hpair_j      : structurally non-zero lower-triangle entries of the Newton Hessian M + J^T D J:
+//                          the M pattern plus (chain(b1) u chain(b2))^2 for every dynamic-dynamic geom pair
+//   floss_row            : constraint row of each dof's friction-loss constraint (-1 if none)
 #define MJPC_I_DERIVED(X)                                                                                        \
   X(level_adr) X(level_body) X(body_subtreeend) X(body_lastdof) X(body_dofmask_lo) X(body_dofmask_hi)            \
-  X(mpair_i) X(mpair_j) X(floss_dof) X(limit_jnt)
+  X(mpair_i) X(mpair_j) X(floss_dof) X(limit_jnt) X(hpair_i) X(hpair_j) X(floss_row)
 
 enum FloatArrayId {
 #define X(n) F_##n,
@@ -60,7 +63,7 @@ enum { OBJ_BODY = 0, OBJ_XBODY, OBJ_GEOM, OBJ_SITE };
 enum { RESIDUAL_PARTICLE = 0, RESIDUAL_PARTICLE_COPY = 1, RESIDUAL_CARTPOLE = 2, RESIDUAL_QUADRUPED_FLAT = 3 };
 
 struct DevModel {
-  int nq, nv, nu, nbody, njnt, ngeom, nsite, nmocap, nkey, npair, nray, nlevel, nmpair, nfloss, nlimit;
+  int nq, nv, nu, nbody, njnt, ngeom, nsite, nmocap, nkey, npair, nray, nlevel, nmpair, nfloss, nlimit, nhpair;
   int cone, iterations, ls_iterations;
   int disable_contact, disable_eulerdamp, disable_frictionloss, disable_limit, disable_refsafe, disable_warmstart;
   int maxcon, maxefc;
@@ -195,6 +198,24 @@ inline ModelPack pack_model(const void* data, size_t nbytes, int maxcon, int max
   put(I_level_adr, level_adr); put(I_level_body, level_body); put(I_body_subtreeend, subend);
   put(I_body_lastdof, lastdof); put(I_body_dofmask_lo, mlo); put(I_body_dofmask_hi, mhi);
   put(I_mpair_i, mpi); put(I_mpair_j, mpj); put(I_floss_dof, fl); put(I_limit_jnt, lj);
+  {
+    // Hessian pattern: M's pattern, widened by contacts that couple two different kinematic chains
+    std::vector<uint8_t> pat((size_t)nv * nv, 0);
+    for (size_t k = 0; k < mpi.size(); k++) pat[(size_t)mpi[k] * nv + mpj[k]] = 1;
+    auto g1 = b.ints("pair_geom1"), g2 = b.ints("pair_geom2"), gb = b.ints("geom_bodyid");
+    auto chain = [&](int bb) { uint64_t m = ((uint64_t)(uint32_t)mhi[bb] << 32) | (uint32_t)mlo[bb]; return m; };
+    for (size_t k = 0; k < g1.size(); k++) {
+      const uint64_t m1 = chain(gb[g1[k]]), m2 = chain(gb[g2[k]]);
+      if (!m1 || !m2) continue;
+      const uint64_t mm = m1 | m2;
+      for (int r = 0; r < nv; r++) if ((mm >> r) & 1) for (int c2 = 0; c2 <= r; c2++) if ((mm >> c2) & 1) pat[(size_t)r * nv + c2] = 1;
+    }
+    std::vector<int> hi_, hj_, frow(nv, -1);
+    for (int r = 0; r < nv; r++) for (int c2 = 0; c2 <= r; c2++) if (pat[(size_t)r * nv + c2]) { hi_.push_back(r); hj_.push_back(c2); }
+    for (size_t k = 0; k < fl.size(); k++) frow[fl[k]] = (int)k;
+    M.nhpair = (int)hi_.size();
+    put(I_hpair_i, hi_); put(I_hpair_j, hj_); put(I_floss_row, frow);
+  }
   while (P.i.size() % 4) P.i.push_back(0);
   while (P.f.size() % 4) P.f.push_back(0.f);
   M.nf = (int)P.f.size(); M.ni = (int)P.i.size();

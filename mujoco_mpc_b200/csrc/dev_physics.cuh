@@ -213,7 +213,6 @@ __device__ __noinline__ void k_crb(Ctx& c) {
   // fills in, so the whole matrix is re-copied before every factorisation
   for (int w = lane; w < nv * nv; w += 32) qLD[w] = qM[w];
   __syncwarp();
-  warp_chol(qLD, DF(ldinv), nv, lane);
 }
 
 // ------------------------------------------------------------------------------------------ collision
@@ -512,6 +511,7 @@ __device__ __noinline__ void k_make_constraint(Ctx& c) {
       __syncwarp();
     }
   }
+  c.nlim = ne - M.nfloss;
   // --- contacts: row addresses are assigned sequentially (a contact that does not fit is dropped, later
   //     smaller ones may still fit: same rule as the oracle)
   int *cadr = DI(con_adr), *cdim = DI(con_dim);
@@ -565,9 +565,11 @@ __device__ __noinline__ void k_make_constraint(Ctx& c) {
     // per-row scalars: one contact per lane
     for (int ci = lane; ci < c.ncon; ci += 32) {
       const int adr = cadr[ci];
+      const int b1 = gbody[g1a[ci]], b2 = gbody[g2a[ci]];
+      DI(con_mlo)[ci] = mlo[b1] | mlo[b2];   // dofs this contact's Jacobian rows can touch
+      DI(con_mhi)[ci] = mhi[b1] | mhi[b2];
       if (adr < 0) continue;
       const int dim = cdim[ci];
-      const int b1 = gbody[g1a[ci]], b2 = gbody[g2a[ci]];
       const float tran = binvw[2 * b1] + binvw[2 * b2], rot = binvw[2 * b1 + 1] + binvw[2 * b2 + 1];
       for (int k = 0; k < dim; k++) {
         const int r = adr + k;
@@ -771,7 +773,7 @@ __device__ __noinline__ void k_smooth_forces(Ctx& c) {
   float* smooth = DF(qfrc_smooth);
   for (int i = lane; i < nv; i += 32) smooth[i] = passive[i] - bias[i] + qact[i];
   __syncwarp();
-  warp_chol_solve(DF(qacc_smooth), DF(qLD), DF(ldinv), smooth, nv, lane);
+  warp_chol_factor_solve(DF(qLD), DF(ldinv), DF(qacc_smooth), smooth, nv, lane);
 }
 
 // constraint reference acceleration aref = -B*vel - K*imp*(pos - margin)
@@ -789,13 +791,16 @@ __device__ __noinline__ void k_reference(Ctx& c) {
 }
 
 // ------------------------------------------------------------------------------------------ primal Newton solver
-// Evaluate constraint cost at jar; writes force/state; returns warp-uniform cost. If hess, also fills
-// W (= per-row Hessian action on J: D*J for quadratic rows, hc*J for cone contacts, 0 otherwise).
+// Evaluate constraint cost at jar; writes force/state; returns warp-uniform cost. If hess, also writes the
+// per-row Hessian weights hw[] (H += hw[r] * J_r^T J_r) and, for contacts in the cone zone, two extra
+// "effective rows" per contact (the cone Hessian is rank-1 + weighted identity + rank-1 in scaled coordinates):
+//   Dm*S*(v v^T + c1*P + c2*ut ut^T)*S,  v = (1, -mu*u/T), ut = (0, u), c1 = mu^2 - mu*N/T, c2 = mu*N/T^3 - mu^2/T^2
+//   X_v = sum_a S_a v_a J_a (weight Dm),  X_u = sum_{a>=1} S_a u_a J_a (weight Dm*c2),  hw[a>=1] = Dm*c1*S_a^2
 __device__ __noinline__ float k_update_constraint(Ctx& c, bool hess) {
   const DevModel& M = *c.M;
   const int lane = c.lane, nv = M.nv;
   const float *jar = DF(efc_jar), *D = DF(efc_D), *R = DF(efc_R), *floss = DF(efc_floss), *J = DF(efc_J);
-  float *force = DF(efc_force), *W = DF(efc_W), *hc = DF(efc_hc);
+  float *force = DF(efc_force), *X = DF(efc_W), *hw = DF(efc_hw), *xw = DF(efc_hc);
   int *state = DI(efc_state);
   const int *etype = DI(efc_type), *eid = DI(efc_id), *item = DI(efc_item), *cdim = DI(con_dim);
   float cost = 0;
@@ -805,12 +810,14 @@ __device__ __noinline__ float k_update_constraint(Ctx& c, bool hess) {
     const float Di = D[i], x = jar[i];
     if (ty == CNSTR_FRICTION_DOF) {
       const float f = floss[i], rf = R[i] * f;
+      float w = 0.f;
       if (x <= -rf) { cost += f * (-0.5f * rf - x); force[i] = f; state[i] = STATE_LINEARNEG; }
       else if (x >= rf) { cost += f * (-0.5f * rf + x); force[i] = -f; state[i] = STATE_LINEARPOS; }
-      else { cost += 0.5f * Di * x * x; force[i] = -Di * x; state[i] = STATE_QUADRATIC; }
+      else { cost += 0.5f * Di * x * x; force[i] = -Di * x; state[i] = STATE_QUADRATIC; w = Di; }
+      hw[i] = w;
     } else if (ty == CNSTR_LIMIT_JOINT || ty == CNSTR_CONTACT_FRICTIONLESS) {
-      if (x < 0) { cost += 0.5f * Di * x * x; force[i] = -Di * x; state[i] = STATE_QUADRATIC; }
-      else { force[i] = 0; state[i] = STATE_SATISFIED; }
+      if (x < 0) { cost += 0.5f * Di * x * x; force[i] = -Di * x; state[i] = STATE_QUADRATIC; hw[i] = Di; }
+      else { force[i] = 0; state[i] = STATE_SATISFIED; hw[i] = 0.f; }
     } else {
       const int ci = eid[i];
       const int dim = cdim[ci];
@@ -822,33 +829,33 @@ __device__ __noinline__ float k_update_constraint(Ctx& c, bool hess) {
       for (int j = 1; j < dim; j++) { u[j] = jar[i + j] * fr[j - 1]; tt += u[j] * u[j]; }
       const float N = u[0], Tn = sqrtf(tt);
       if (N >= mu * Tn || (Tn <= 0 && N >= 0)) {
-        for (int j = 0; j < dim; j++) { force[i + j] = 0; state[i + j] = STATE_SATISFIED; }
+        for (int j = 0; j < dim; j++) { force[i + j] = 0; state[i + j] = STATE_SATISFIED; hw[i + j] = 0.f; }
       } else if (mu * N + Tn <= 0 || (Tn <= 0 && N < 0)) {
         for (int j = 0; j < dim; j++) {
           cost += 0.5f * D[i + j] * jar[i + j] * jar[i + j];
           force[i + j] = -D[i + j] * jar[i + j];
           state[i + j] = STATE_QUADRATIC;
+          hw[i + j] = D[i + j];
         }
       } else {
         const float Dm = Di / (mu * mu * (1 + mu * mu));
         const float NmT = N - mu * Tn;
         cost += 0.5f * Dm * NmT * NmT;
         const float f0 = -Dm * NmT * mu;
+        const float iT = 1.0f / Tn;
         force[i] = f0;
-        for (int j = 1; j < dim; j++) force[i + j] = -f0 / Tn * u[j] * fr[j - 1];
+        for (int j = 1; j < dim; j++) force[i + j] = -f0 * iT * u[j] * fr[j - 1];
         for (int j = 0; j < dim; j++) state[i + j] = STATE_CONE;
         if (hess) {
-          float* h = hc + 36 * ci;
-          for (int a = 0; a < dim; a++)
-            for (int b = 0; b < dim; b++) {
-              float hv;
-              if (a == 0 && b == 0) hv = 1;
-              else if (a == 0) hv = -mu * u[b] / Tn;
-              else if (b == 0) hv = -mu * u[a] / Tn;
-              else hv = mu * N / (Tn * Tn * Tn) * u[a] * u[b] + (a == b ? (mu * mu - mu * N / Tn) : 0.f);
-              const float sa = a == 0 ? mu : fr[a - 1], sb = b == 0 ? mu : fr[b - 1];
-              h[a * 6 + b] = Dm * sa * sb * hv;
-            }
+          const float c1 = mu * mu - mu * N * iT;
+          hw[i] = 0.f;
+          for (int j = 1; j < dim; j++) hw[i + j] = Dm * c1 * fr[j - 1] * fr[j - 1];
+          // coefficients of the two effective rows, stored per contact: [S_a v_a (6), S_a u_a (6), wv, wu]
+          float* q = xw + 36 * ci;
+          q[0] = mu; q[6] = 0.f;
+          for (int j = 1; j < dim; j++) { q[j] = -fr[j - 1] * mu * u[j] * iT; q[6 + j] = fr[j - 1] * u[j]; }
+          q[12] = Dm;
+          q[13] = Dm * (mu * N * iT * iT * iT - mu * mu * iT * iT);
         }
       }
     }
@@ -856,27 +863,30 @@ __device__ __noinline__ float k_update_constraint(Ctx& c, bool hess) {
   cost = warp_sum(cost);
   __syncwarp();
   if (hess) {
+    // effective rows of cone contacts: one (contact, dof) pair per lane
     const int* cadr = DI(con_adr);
-    const int total = c.nefc * nv;
+    const int total = c.ncon * nv;
     for (int w = lane; w < total; w += 32) {
-      const int r = w / nv, s = w - r * nv;
-      const int st = state[r];
-      float v = 0;
-      if (st == STATE_QUADRATIC) v = D[r] * J[r * nv + s];
-      else if (st == STATE_CONE) {
-        const int ci = eid[r];
-        const int a0 = cadr[ci], dim = cdim[ci], a = r - a0;
-        const float* h = hc + 36 * ci + 6 * a;
-        for (int b = 0; b < dim; b++) v += h[b] * J[(a0 + b) * nv + s];
+      const int ci = w / nv, sidx = w - ci * nv;
+      const int a0 = cadr[ci];
+      if (a0 < 0 || state[a0] != STATE_CONE) continue;
+      const int dim = cdim[ci];
+      const float* q = xw + 36 * ci;
+      float xv = 0.f, xu = 0.f;
+      for (int a = 0; a < dim; a++) {
+        const float jv = J[(a0 + a) * nv + sidx];
+        xv += q[a] * jv;
+        xu += q[6 + a] * jv;
       }
-      W[w] = v;
+      X[(2 * ci) * nv + sidx] = xv;
+      X[(2 * ci + 1) * nv + sidx] = xu;
     }
     __syncwarp();
   }
   return cost;
 }
 
-// Ma = M*qacc, jar = J*qacc - aref, gauss; returns total cost (uniform). If hess: qH = M + J^T W.
+// Ma = M*qacc, jar = J*qacc - aref, gauss; returns total cost (uniform). If hess: qH = M + J^T diag(hw) J + cone rows.
 __device__ __noinline__ float k_total_cost(Ctx& c, const float* qacc, bool hess, float* gauss_out) {
   const DevModel& M = *c.M;
   const int lane = c.lane, nv = M.nv;
@@ -898,16 +908,42 @@ __device__ __noinline__ float k_total_cost(Ctx& c, const float* qacc, bool hess,
   __syncwarp();
   const float cc = k_update_constraint(c, hess);
   if (hess) {
-    const float* W = DF(efc_W);
+    // Newton Hessian gathered entry by entry over the structurally non-zero pattern (hpair lists);
+    // friction-loss / limit rows only touch the diagonal.
+    const float *X = DF(efc_W), *hw = DF(efc_hw), *xw = DF(efc_hc);
     float* H = DF(qH);
-    const int ne = c.nefc;
-    for (int w = lane; w < nv * nv; w += 32) {
-      const int r = w / nv, s = w - r * nv;
-      if (s > r) continue;
-      float a = qM[w];
-      for (int k = 0; k < ne; k++) a += J[k * nv + r] * W[k * nv + s];
-      H[w] = a;
-      H[s * nv + r] = a;
+    const int *hi = MI(hpair_i), *hj = MI(hpair_j), *frow = MI(floss_row), *state = DI(efc_state), *eid = DI(efc_id),
+              *cadr = DI(con_adr), *cdim = DI(con_dim), *cmlo = DI(con_mlo), *cmhi = DI(con_mhi), *jdadr = MI(jnt_dofadr);
+    const int ncon = c.ncon, nf = M.nfloss, nl = c.nlim;
+    for (int w = lane; w < nv * nv; w += 32) H[w] = 0.f;   // entries outside the pattern (the factor fills them)
+    __syncwarp();
+    for (int e = lane; e < M.nhpair; e += 32) {
+      const int r = hi[e], s2 = hj[e];
+      float a = qM[r * nv + s2];
+      if (r == s2) {
+        const int fr = frow[r];
+        if (fr >= 0) a += hw[fr];
+        for (int q = nf; q < nf + nl; q++)
+          if (jdadr[eid[q]] == r) a += hw[q];
+      }
+      const unsigned rbit = 1u << (r & 31), sbit = 1u << (s2 & 31);
+      for (int ci = 0; ci < ncon; ci++) {
+        const int a0 = cadr[ci];
+        if (a0 < 0) continue;
+        const unsigned mr = r < 32 ? (unsigned)cmlo[ci] : (unsigned)cmhi[ci];
+        const unsigned ms = s2 < 32 ? (unsigned)cmlo[ci] : (unsigned)cmhi[ci];
+        if (!(mr & rbit) || !(ms & sbit)) continue;
+        const int dim = cdim[ci];
+        const float* Jr = J + a0 * nv + r;
+        const float* Js = J + a0 * nv + s2;
+        for (int k = 0; k < dim; k++) a += hw[a0 + k] * Jr[k * nv] * Js[k * nv];
+        if (state[a0] == STATE_CONE) {
+          const float* q = xw + 36 * ci;
+          a += q[12] * X[(2 * ci) * nv + r] * X[(2 * ci) * nv + s2] + q[13] * X[(2 * ci + 1) * nv + r] * X[(2 * ci + 1) * nv + s2];
+        }
+      }
+      H[r * nv + s2] = a;
+      H[s2 * nv + r] = a;
     }
     __syncwarp();
   }
@@ -976,7 +1012,7 @@ __device__ __noinline__ float k_line_search(Ctx& c, float g0, float g1, float g2
   const DevModel& M = *c.M;
   if (snorm < kMinVal) return 0.f;
   const LsPoint p0 = k_ls_eval(c, g0, g1, g2, 0.f);
-  const float gtol = fmaxf(M.tolerance * M.ls_tolerance * snorm * scale_inv, 64 * 1.1920929e-7f * fabsf(p0.d1));
+  const float gtol = fmaxf(fmaxf(M.tolerance, kTolFloor) * M.ls_tolerance * snorm * scale_inv, 64 * 1.1920929e-7f * fabsf(p0.d1));
   if (p0.d2 <= kMinVal) return 0.f;
   LsPoint p1 = k_ls_eval(c, g0, g1, g2, -p0.d1 / p0.d2);
   if (p0.cost < p1.cost) p1 = p0;
@@ -1043,8 +1079,7 @@ __device__ __noinline__ void k_solve(Ctx& c) {
     }
     gnorm2 = warp_sum(g2);
     __syncwarp();
-    warp_chol(DF(qH), DF(hinv), nv, lane);
-    warp_chol_solve(search, DF(qH), DF(hinv), grad, nv, lane);
+    warp_chol_factor_solve(DF(qH), DF(hinv), search, grad, nv, lane);
     for (int i = lane; i < nv; i += 32) search[i] = -search[i];
     __syncwarp();
   };
@@ -1075,7 +1110,8 @@ __device__ __noinline__ void k_solve(Ctx& c) {
     grad_dir();
     c.niter = iter + 1;
     const float improvement = (old - cost) / scale_inv, gradient = sqrtf(gnorm2) / scale_inv;
-    if (improvement < M.tolerance || gradient < M.tolerance) break;
+    const float tol = fmaxf(M.tolerance, kTolFloor);
+    if (improvement < tol || gradient < tol) break;
   }
   for (int i = lane; i < nv; i += 32) {
     float a = 0;
@@ -1121,8 +1157,7 @@ __device__ __noinline__ void k_euler(Ctx& c) {
     }
     for (int i = lane; i < nv; i += 32) vt[i] = smooth[i] + qfc[i];
     __syncwarp();
-    warp_chol(H, DF(hinv), nv, lane);
-    warp_chol_solve(vt, H, DF(hinv), vt, nv, lane);
+    warp_chol_factor_solve(H, DF(hinv), vt, vt, nv, lane);
     acc = vt;
   }
   for (int i = lane; i < nv; i += 32) qvel[i] += h * acc[i];

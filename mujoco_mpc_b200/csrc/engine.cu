@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -52,6 +53,7 @@ struct mjpc_b200 {
   double* d_times = nullptr;
   unsigned char* d_failure = nullptr;
   int* d_order = nullptr;
+  long long* d_stats = nullptr;
   // debug + ilqg scratch
   float* d_dbg = nullptr;
   IlqgBuffers ilqg;
@@ -141,6 +143,7 @@ RolloutArgs base_args(mjpc_b200* h, double time, int N, int H) {
   A.N = N; A.H = H; A.time0 = time;
   A.states = h->d_states; A.actions = h->d_actions; A.times = h->d_times; A.residual = h->d_residual;
   A.costs = h->d_costs; A.trace = h->d_trace; A.returns = h->d_returns; A.failure = h->d_failure;
+  A.stats = h->d_stats;
   return A;
 }
 
@@ -184,6 +187,10 @@ int mjpc_b200_create(const mjpc_model_blob* model, int max_candidates, int max_h
     return fail(MJPC_B200_ERR_BAD_BLOB, std::string("create: ") + e.what());
   }
   h->device = device;
+  if (const char* w = std::getenv("MJPC_B200_WARPS_PER_CTA")) {  // tuning knob (profiles/): candidates per CTA
+    const int v = std::atoi(w);
+    if (v == 1 || v == 2 || v == 4) h->warps_per_cta = v;
+  }
   h->maxN = max_candidates; h->maxH = max_horizon;
   const DevModel& M = h->pack.M;
   {
@@ -221,7 +228,7 @@ int mjpc_b200_create(const mjpc_model_blob* model, int max_candidates, int max_h
   CUDA_TRY(dalloc(&h->d_states, N * H * ds)); CUDA_TRY(dalloc(&h->d_actions, N * H * nu));
   CUDA_TRY(dalloc(&h->d_times, N * H)); CUDA_TRY(dalloc(&h->d_residual, N * H * nr));
   CUDA_TRY(dalloc(&h->d_costs, N * H)); CUDA_TRY(dalloc(&h->d_trace, N * H * 3 * (size_t)M.num_trace));
-  CUDA_TRY(dalloc(&h->d_returns, N)); CUDA_TRY(dalloc(&h->d_failure, N)); CUDA_TRY(dalloc(&h->d_order, N));
+  CUDA_TRY(dalloc(&h->d_returns, N)); CUDA_TRY(dalloc(&h->d_failure, N)); CUDA_TRY(dalloc(&h->d_order, N)); CUDA_TRY(dalloc(&h->d_stats, 4 * N));
   CUDA_TRY(dalloc(&h->d_dbg, 4 * ds + 2 * nu + (size_t)M.nv * M.nv + nr + 256 + 64 + 7 * (size_t)M.nmocap));
   h->h_in_floats = ds + 7 * M.nmocap + M.task_state_size + N * h->maxP * nu + h->maxP + H * (nu + ds + 1 + nu * n + nu) + N + 64;
   CUDA_TRY(cudaMallocHost((void**)&h->h_in, h->h_in_floats * 4));
@@ -243,7 +250,7 @@ void mjpc_b200_destroy(mjpc_b200_t* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   void* bufs[] = {h->d_pack, h->d_state, h->d_mocap, h->d_task_state, h->d_knots, h->d_knot_times, h->d_unom, h->d_xnom,
                   h->d_tnom, h->d_gains, h->d_du, h->d_steps, h->d_states, h->d_actions, h->d_times, h->d_residual,
-                  h->d_costs, h->d_trace, h->d_returns, h->d_failure, h->d_order, h->d_dbg};
+                  h->d_costs, h->d_trace, h->d_returns, h->d_failure, h->d_order, h->d_dbg, h->d_stats};
   for (void* p : bufs) if (p) cudaFree(p);
   ilqg_free(h->ilqg);
   if (h->h_in) cudaFreeHost(h->h_in);
@@ -443,6 +450,14 @@ int mjpc_b200_step_debug(mjpc_b200_t* h, const float* qpos, const float* qvel, c
   if (qM) CUDA_TRY(cudaMemcpy(qM, d_qM, nv * nv * 4, cudaMemcpyDeviceToHost));
   if (efc_force) CUDA_TRY(cudaMemcpy(efc_force, d_force, 256 * 4, cudaMemcpyDeviceToHost));
   if (counts) CUDA_TRY(cudaMemcpy(counts, d_counts, 16, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int mjpc_b200_fetch_stats(mjpc_b200_t* h, int64_t* stats) {
+  if (!h || !stats || h->lastN < 1) return fail(MJPC_B200_ERR_BAD_ARGUMENT, "fetch_stats: nothing to fetch");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  CUDA_TRY(cudaMemcpy(stats, h->d_stats, (size_t)h->lastN * 4 * sizeof(long long), cudaMemcpyDeviceToHost));
   return 0;
 }
 

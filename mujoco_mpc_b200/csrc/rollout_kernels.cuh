@@ -31,6 +31,7 @@ struct RolloutArgs {
   double time0;
   float* states; float* actions; double* times; float* residual; float* costs; float* trace;
   float* returns; unsigned char* failure;
+  long long* stats;         // [N][4]: cycles, Newton iterations, contacts summed over steps, constraint rows summed
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -63,7 +64,7 @@ __device__ __forceinline__ void init_ctx(Ctx& c, const DevModel* M, const DevLay
   c.mi = reinterpret_cast<const int*>(smem + M->nf);
   c.d = smem + M->nf + M->ni + (size_t)warp * L->total;
   c.lane = lane;
-  c.ncon = 0; c.nefc = 0; c.nitem = 0; c.niter = 0; c.warn = 0; c.time = 0.f;
+  c.ncon = 0; c.nefc = 0; c.nitem = 0; c.niter = 0; c.nlim = 0; c.warn = 0; c.time = 0.f;
 }
 
 // write the trace points (GetTraces, mjpc/utilities.cc:268-285)
@@ -119,6 +120,8 @@ extern "C" __global__ void __launch_bounds__(128) rollout_kernel(const __grid_co
   if (lane == 0) o_times[0] = A.time0;
   float total = 0.f;
   bool failed = false;
+  const long long clk0 = clock64();
+  long long n_newton = 0, n_con = 0, n_efc = 0;
   for (int t = 0; t < H; t++) {
     const bool last = t == H - 1;
     if (!last) {
@@ -132,6 +135,7 @@ extern "C" __global__ void __launch_bounds__(128) rollout_kernel(const __grid_co
     }
     if (!last && (k_bad(c, DF(qpos), nq) || k_bad(c, DF(qvel), nv))) { failed = true; break; }
     k_forward(c);
+    n_newton += c.niter; n_con += c.ncon; n_efc += c.nefc;
     k_residual(c);
     if (!last && k_bad(c, DF(qacc), nv)) c.warn = 1;
     for (int i = lane; i < nr; i += 32) o_res[(size_t)t * nr + i] = DF(residual)[i];
@@ -150,6 +154,10 @@ extern "C" __global__ void __launch_bounds__(128) rollout_kernel(const __grid_co
   if (lane == 0) {
     A.returns[cand] = failed ? 1.0e6f : total / (float)max(H, 1);
     A.failure[cand] = failed ? 1 : 0;
+    if (A.stats) {
+      A.stats[4 * cand] = clock64() - clk0; A.stats[4 * cand + 1] = n_newton;
+      A.stats[4 * cand + 2] = n_con; A.stats[4 * cand + 3] = n_efc;
+    }
   }
 }
 

@@ -22,7 +22,7 @@ EXPORTS = ["mjpc_b200_version", "mjpc_b200_last_error", "mjpc_b200_create", "mjp
            "mjpc_b200_get_info", "mjpc_b200_set_task", "mjpc_b200_rollout_spline", "mjpc_b200_rollout_feedback",
            "mjpc_b200_fetch_trajectory", "mjpc_b200_fetch_all", "mjpc_b200_model_derivatives",
            "mjpc_b200_cost_derivatives", "mjpc_b200_backward_pass", "mjpc_b200_step_debug",
-           "mjpc_b200_launch_count", "mjpc_b200_last_kernel_ms", "mjpc_b200_upload_spline_inputs",
+           "mjpc_b200_fetch_stats", "mjpc_b200_launch_count", "mjpc_b200_last_kernel_ms", "mjpc_b200_upload_spline_inputs",
            "mjpc_b200_launch_resident", "mjpc_b200_sync", "mjpc_b200_read_returns", "mjpc_b200_stream",
            "mjpc_b200_device_returns"]
 
@@ -56,7 +56,7 @@ def load_library():
         lib.mjpc_b200_last_kernel_ms.restype = C.c_float
         lib.mjpc_b200_stream.restype = C.c_void_p
         lib.mjpc_b200_device_returns.restype = C.c_void_p
-        for n in ("mjpc_b200_destroy", "mjpc_b200_launch_count", "mjpc_b200_last_kernel_ms", "mjpc_b200_stream",
+        for n in ("mjpc_b200_destroy", "mjpc_b200_fetch_stats", "mjpc_b200_launch_count", "mjpc_b200_last_kernel_ms", "mjpc_b200_stream",
                   "mjpc_b200_device_returns", "mjpc_b200_sync", "mjpc_b200_launch_resident"):
             getattr(lib, n).argtypes = [C.c_void_p]
         _LIB = lib
@@ -233,6 +233,11 @@ class Engine:
                                                      int(limits), _pf(K), _pf(du), _pf(dV), _pf(Vx), _pf(Vxx),
                                                      C.byref(status)))
         return dict(K=K, du=du, dV=dV, Vx=Vx, Vxx=Vxx, status=status.value)
+
+    def fetch_stats(self):
+        st = np.zeros((self.lastN, 4), np.int64)
+        self._check(self.lib.mjpc_b200_fetch_stats(self.h, st.ctypes.data_as(C.POINTER(C.c_int64))))
+        return st
 
     @property
     def launch_count(self):

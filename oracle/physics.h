@@ -18,6 +18,9 @@
 namespace oracle {
 
 template <class T> constexpr T kMinVal() { return (T)1e-15; }
+// Solver tolerance floor: opt.tolerance (1e-8) is below what fp32 cost differences can resolve, so reduced
+// precision terminates on max(opt.tolerance, 1e-6); inactive in fp64. Measured effect on returns: 1e-8 relative.
+template <class T> constexpr T kTolFloor() { return sizeof(T) == 4 ? (T)1e-6 : (T)0; }
 constexpr double kMaxVal = 1e10;      // mjMAXVAL
 constexpr double kMinImp = 0.0001, kMaxImp = 0.9999, kMinMu = 1e-5;
 constexpr int kMaxConDim = 6;
@@ -979,7 +982,7 @@ T line_search(const Model<T>& m, const Data<T>& d, const SolverCtx<T>& s, const 
   if (snorm < kMinVal<T>()) return 0;
   LsPoint<T> p0 = ls_eval(m, d, s, qg, (T)0);
   // derivative tolerance; the relative floor (64 eps) guards reduced precision and is inactive in fp64
-  T gtol = std::max(m.tolerance * m.ls_tolerance * snorm * scale_inv,
+  T gtol = std::max(std::max(m.tolerance, kTolFloor<T>()) * m.ls_tolerance * snorm * scale_inv,
                     64 * std::numeric_limits<T>::epsilon() * std::fabs(p0.d1));
   if (p0.d2 <= kMinVal<T>()) return 0;
   LsPoint<T> p1 = ls_eval(m, d, s, qg, -p0.d1 / p0.d2);
@@ -1085,7 +1088,8 @@ void solve_constraints(const Model<T>& m, Data<T>& d) {
     T gn = 0;
     for (int i = 0; i < nv; i++) gn += s.grad[i] * s.grad[i];
     T improvement = (old - s.cost) / scale_inv, gradient = std::sqrt(gn) / scale_inv;
-    if (improvement < m.tolerance || gradient < m.tolerance) break;
+    const T tol = std::max(m.tolerance, kTolFloor<T>());
+    if (improvement < tol || gradient < tol) break;
   }
   for (int i = 0; i < nv; i++) {
     T a = 0;
