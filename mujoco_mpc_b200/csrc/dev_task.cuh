@@ -127,8 +127,12 @@ __device__ __forceinline__ void k_policy_spline(Ctx& c, int P, int interp) {
 }
 
 // ------------------------------------------------------------------------------------------ iLQG policy
+// FindInterval (mjpc/utilities.h:125-144).  Rollout time is accumulated in fp32 on the device while the nominal
+// times arrive as (double - time0): a sample that is meant to coincide with a node may land one ulp below it, which
+// would shift a zero-order hold by a whole step.  Nodes within 1e-5 s above the query therefore count as reached.
 __device__ __forceinline__ void find_interval(int* b, const float* seq, float value, int length) {
   int upper = 0;
+  value += 1e-5f;
   while (upper < length && !(value < seq[upper])) upper++;
   const int lower = upper - 1;
   if (lower < 0) { b[0] = b[1] = 0; }

@@ -96,8 +96,9 @@ int upload_task(mjpc_b200* h) {
   return 0;
 }
 
+// the dynamic shared-memory opt-in is per kernel (process-wide): only ever raise it, several handles may coexist
 int set_smem(const void* fn, size_t bytes) {
-  CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  CUDA_TRY(mjpc_dev::raise_smem_limit(fn, bytes));
   return 0;
 }
 

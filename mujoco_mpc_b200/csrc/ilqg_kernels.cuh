@@ -1,40 +1,696 @@
-// ilqg_kernels.cuh - iLQG sweeps on the device (finite-difference model derivatives, Gauss-Newton cost
-// derivatives, Riccati backward pass).  Reference: mjpc/planners/model_derivatives.cc:45-165,
-// mjpc/planners/cost_derivatives.cc:77-230, mjpc/planners/ilqg/backward_pass.cc:65-250.
+// ilqg_kernels.cuh - iLQG sweeps on the device.
+//
+//   fd_center_kernel / fd_column_kernel   ModelDerivatives::Compute (mjpc/planners/model_derivatives.cc:45-165):
+//       one warp per (timestep, perturbed column); every warp runs the same forward-dynamics device code as the
+//       rollout kernel ([EXT] mjd_transitionFD restated: one-sided differences, clamped control nudges,
+//       tangent-space state differences).  H*(2nv+nu) independent warps fill the machine.
+//   cost_derivatives_kernel               CostDerivatives::Compute (mjpc/planners/cost_derivatives.cc:77-230):
+//       one CTA per timestep, Gauss-Newton products accumulated in shared memory.
+//   backward_pass_kernel                  RiccatiStep recursion (mjpc/planners/ilqg/backward_pass.cc:65-250,
+//       mjpc/planners/ilqg/planner.cc:429-520): ONE CTA, strictly sequential in t (value function dependence),
+//       matrices resident in shared memory, box-QP ([EXT] mju_boxQP restated: projected Newton) on one warp.
+//       The n=36, m=12 products are fp32 CUDA-core FMAs: a tcgen05 tile is at least 64x8x8 per instruction with
+//       operands in swizzled shared-memory tiles and TF32 inputs, which for 36x36x36 products costs more in
+//       staging than the ~0.3 MFLOP per step it would accelerate, and TF32's 10-bit mantissa breaks the
+//       Riccati recursion's accuracy (DESIGN.md "tensor cores").
 #pragma once
 #include <cuda_runtime.h>
+
+#include <utility>
+#include <vector>
 
 #include "rollout_kernels.cuh"
 
 namespace mjpc_dev {
 
-struct IlqgBuffers {
-  int H = 0;
-  float* d_buf = nullptr;
+// ------------------------------------------------------------------------------------------ norms with derivatives
+// value; g[n]; H[n*n] (mjpc/norm.cc:50-210). Executed by ONE thread (n <= 16 per term in practice).
+__device__ inline float norm_full(float* g, float* Hn, const float* x, const float* params, int n, int type) {
+  float y = 0;
+  const float p = params[0], q = params[1];
+  for (int i = 0; i < n * n; i++) Hn[i] = 0;
+  switch (type) {
+    case kNull: y = x[0]; g[0] = 1; break;
+    case kQuadratic:
+      for (int i = 0; i < n; i++) { y += x[i] * x[i]; g[i] = x[i]; Hn[i * n + i] = 1; }
+      y *= 0.5f;
+      break;
+    case kL22: {
+      float cc = 0;
+      for (int i = 0; i < n; i++) cc += x[i] * x[i];
+      const float a = powf(cc, q / 2) + powf(p, q);
+      const float s = powf(a, 1 / q);
+      y = s - p;
+      const float dd = powf(cc, q / 2 - 1);
+      const float b = s / a * dd;
+      for (int i = 0; i < n; i++) g[i] = b * x[i];
+      const float c2 = (1 - q) * dd / a + (q - 2) / fmaxf(cc, 1e-15f);
+      for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) Hn[i + j * n] = b * ((i == j ? 1.f : 0.f) + x[i] * x[j] * c2);
+      break;
+    }
+    case kL2: {
+      float s = 0;
+      for (int i = 0; i < n; i++) s += x[i] * x[i];
+      s = sqrtf(s + p * p);
+      y = s - p;
+      for (int i = 0; i < n; i++) g[i] = s ? x[i] / s : 0.f;
+      if (s)
+        for (int i = 0; i < n; i++)
+          for (int j = 0; j < n; j++) Hn[i + j * n] = ((i == j ? 1.f : 0.f) - g[i] * g[j]) / s;
+      break;
+    }
+    case kCosh:
+      for (int i = 0; i < n; i++) {
+        y += p * p * (coshf(x[i] / p) - 1);
+        g[i] = p * sinhf(x[i] / p);
+        Hn[i * n + i] = coshf(x[i] / p);
+      }
+      break;
+    case kPowerLoss:
+      for (int i = 0; i < n; i++) {
+        const float s = fabsf(x[i]);
+        y += powf(s, p);
+        g[i] = (x[i] > 0 ? 1.f : (x[i] < 0 ? -1.f : 0.f)) * p * powf(s, p - 1);
+        Hn[i * n + i] = (p - 1) * p * powf(s, p - 2);
+      }
+      break;
+    case kSmoothAbsLoss:
+      for (int i = 0; i < n; i++) {
+        const float s = sqrtf(x[i] * x[i] + p * p);
+        y += s - p;
+        g[i] = s ? x[i] / s : 0.f;
+        Hn[n * i + i] = s ? (1 - g[i] * g[i]) / s : 0.f;
+      }
+      break;
+    case kSmoothAbs2Loss:
+      for (int i = 0; i < n; i++) {
+        const float a = fabsf(x[i]);
+        const float dd = powf(a, q);
+        const float e = dd + powf(p, q);
+        const float s = powf(e, 1 / q);
+        y += s - p;
+        const float c2 = s * powf(a, q - 2) / e;
+        g[i] = c2 * x[i];
+        Hn[i * n + i] = c2 * (q - 1) * (1 - dd / e);
+      }
+      break;
+    case kRectifyLoss:
+      for (int i = 0; i < n; i++) {
+        if (p > 0) {
+          const float s = expf(x[i] / p);
+          y += p * logf(1 + s);
+          g[i] = s / (1 + s);
+          Hn[i * n + i] = s / (p * (1 + s) * (1 + s));
+        } else {
+          y += x[i] > 0 ? x[i] : 0.f;
+          g[i] = x[i] > 0 ? 1.f : 0.f;
+        }
+      }
+      break;
+  }
+  return y;
+}
+
+// ------------------------------------------------------------------------------------------ model derivatives
+struct FdArgs {
+  DevModel M;
+  DevLayout L;
+  const float* pack;
+  const float* x;  // [H][ds]
+  const float* u;  // [H][nu]
+  const float* t;  // [H] relative times
+  const float* mocap;
+  const float* task_state;
+  int H;
+  float eps;
+  float* y0;  // [H][ds]   centre next state
+  float* r0;  // [H][nr]   centre residual
+  float* q0;  // [H][nv]   centre qacc (warm start of the perturbed solves)
+  float *A, *B, *C, *D;
 };
 
-inline int ilqg_init(IlqgBuffers& b, const DevModel& M, int H, size_t smem_debug) {
-  (void)M; (void)smem_debug;
-  b.H = H;
+__device__ __forceinline__ void fd_load_state(Ctx& c, const FdArgs& A, int t) {
+  const DevModel& M = *c.M;
+  const int lane = c.lane, nq = M.nq, nv = M.nv, ds = nq + nv;
+  if (A.task_state) {
+    float* ts = const_cast<float*>(MF(task_state));
+    for (int i = lane; i < M.task_state_size; i += 32) ts[i] = A.task_state[i];
+  }
+  for (int i = lane; i < nq; i += 32) DF(qpos)[i] = A.x[(size_t)t * ds + i];
+  for (int i = lane; i < nv; i += 32) DF(qvel)[i] = A.x[(size_t)t * ds + nq + i];
+  for (int i = lane; i < M.nu; i += 32) DF(ctrl)[i] = A.u[(size_t)t * M.nu + i];
+  for (int i = lane; i < 7 * M.nmocap; i += 32) {
+    const int k = i / 7, q = i - 7 * k;
+    if (q < 3) DF(mocap_pos)[3 * k + q] = A.mocap[i]; else DF(mocap_quat)[4 * k + q - 3] = A.mocap[i];
+  }
+  for (int i = lane; i < nv * nv; i += 32) DF(qM)[i] = 0;
+  c.time = A.t[t];
+  __syncwarp();
+}
+
+extern "C" __global__ void __launch_bounds__(32) fd_center_kernel(const __grid_constant__ FdArgs A) {
+  extern __shared__ __align__(16) float smem[];
+  const DevModel& M = A.M;
+  stage_model_pack(smem, A.pack, (unsigned)((M.nf + M.ni) * 4));
+  Ctx c;
+  init_ctx(c, &A.M, &A.L, smem, 0, threadIdx.x);
+  const int lane = c.lane, t = blockIdx.x, nq = M.nq, nv = M.nv, ds = nq + nv, nr = M.num_residual;
+  fd_load_state(c, A, t);
+  for (int i = lane; i < nv; i += 32) DF(qacc_warmstart)[i] = 0;
+  __syncwarp();
+  k_forward(c);
+  k_residual(c);
+  for (int i = lane; i < nr; i += 32) A.r0[(size_t)t * nr + i] = DF(residual)[i];
+  for (int i = lane; i < nv; i += 32) A.q0[(size_t)t * nv + i] = DF(qacc)[i];
+  k_euler(c);
+  for (int i = lane; i < nq; i += 32) A.y0[(size_t)t * ds + i] = DF(qpos)[i];
+  for (int i = lane; i < nv; i += 32) A.y0[(size_t)t * ds + nq + i] = DF(qvel)[i];
+}
+
+// one warp per (t, column). columns: [0, nu) controls, [nu, nu+nv) velocities, [nu+nv, nu+2nv) positions
+extern "C" __global__ void __launch_bounds__(32) fd_column_kernel(const __grid_constant__ FdArgs A) {
+  extern __shared__ __align__(16) float smem[];
+  const DevModel& M = A.M;
+  stage_model_pack(smem, A.pack, (unsigned)((M.nf + M.ni) * 4));
+  Ctx c;
+  init_ctx(c, &A.M, &A.L, smem, 0, threadIdx.x);
+  const int lane = c.lane, nq = M.nq, nv = M.nv, nu = M.nu, ds = nq + nv, n = 2 * nv, nr = M.num_residual;
+  const int ncol = nu + 2 * nv;
+  const int t = blockIdx.x / ncol, col = blockIdx.x - t * ncol;
+  const bool last = t == A.H - 1;
+  if (last && col < nu) return;  // only C is computed at the final time step (model_derivatives.cc:89-93)
+  fd_load_state(c, A, t);
+  for (int i = lane; i < nv; i += 32) DF(qacc_warmstart)[i] = A.q0[(size_t)t * nv + i];
+  __syncwarp();
+  float h = A.eps;  // signed step actually taken
+  if (col < nu) {
+    const int i = col;
+    const bool limited = MI(actuator_ctrllimited)[i] != 0;
+    const float lo = MF(actuator_ctrlrange)[2 * i], hi = MF(actuator_ctrlrange)[2 * i + 1];
+    const float u0 = DF(ctrl)[i];
+    const bool fwd = !limited || (u0 >= lo && u0 <= hi && u0 + A.eps >= lo && u0 + A.eps <= hi);
+    const bool back = !fwd && (!limited || (u0 - A.eps >= lo && u0 - A.eps <= hi && u0 >= lo && u0 <= hi));
+    if (!fwd && !back) {
+      for (int k = lane; k < n; k += 32) A.B[((size_t)t * n + k) * nu + i] = 0;
+      for (int k = lane; k < nr; k += 32) A.D[((size_t)t * nr + k) * nu + i] = 0;
+      return;
+    }
+    h = fwd ? A.eps : -A.eps;
+    if (lane == 0) DF(ctrl)[i] = u0 + h;
+  } else if (col < nu + nv) {
+    if (lane == 0) DF(qvel)[col - nu] += A.eps;
+  } else {
+    // tangent-space position perturbation ([EXT] mj_integratePos with a unit vector)
+    const int dof = col - nu - nv;
+    if (lane == 0) {
+      const int j = MI(dof_jntid)[dof];
+      const int qa = MI(jnt_qposadr)[j], da = MI(jnt_dofadr)[j], k = dof - da, ty = MI(jnt_type)[j];
+      float* qpos = DF(qpos);
+      if (ty == JNT_FREE) {
+        if (k < 3) qpos[qa + k] += A.eps;
+        else { float w[3] = {0, 0, 0}; w[k - 3] = 1; quat_integrate(qpos + qa + 3, w, A.eps); }
+      } else if (ty == JNT_BALL) {
+        float w[3] = {0, 0, 0}; w[k] = 1; quat_integrate(qpos + qa, w, A.eps);
+      } else {
+        qpos[qa] += A.eps;
+      }
+    }
+  }
+  __syncwarp();
+  k_forward(c);
+  k_residual(c);
+  const float ih = 1.0f / h;
+  // residual columns
+  float* Cout = col < nu ? A.D : A.C;
+  const int cw = col < nu ? nu : n;
+  const int cc = col < nu ? col : (col < nu + nv ? nv + (col - nu) : col - nu - nv);
+  for (int k = lane; k < nr; k += 32)
+    Cout[((size_t)t * nr + k) * cw + cc] = (DF(residual)[k] - A.r0[(size_t)t * nr + k]) * ih;
+  if (last) return;
+  k_euler(c);
+  // next-state difference in the tangent space (StateDiff / mj_differentiatePos)
+  float* Sout = col < nu ? A.B : A.A;
+  const float* y0 = A.y0 + (size_t)t * ds;
+  const int *jtype = MI(jnt_type), *jqadr = MI(jnt_qposadr), *jdadr = MI(jnt_dofadr);
+  const float *qpos = DF(qpos), *qvel = DF(qvel);
+  for (int j = lane; j < M.njnt; j += 32) {
+    const int qa = jqadr[j], da = jdadr[j], ty = jtype[j];
+    if (ty == JNT_FREE) {
+      for (int k = 0; k < 3; k++) Sout[((size_t)t * n + da + k) * cw + cc] = (qpos[qa + k] - y0[qa + k]) * ih;
+      float dq[3];
+      sub_quat(dq, qpos + qa + 3, y0 + qa + 3);
+      for (int k = 0; k < 3; k++) Sout[((size_t)t * n + da + 3 + k) * cw + cc] = dq[k] * ih;
+    } else if (ty == JNT_BALL) {
+      float dq[3];
+      sub_quat(dq, qpos + qa, y0 + qa);
+      for (int k = 0; k < 3; k++) Sout[((size_t)t * n + da + k) * cw + cc] = dq[k] * ih;
+    } else {
+      Sout[((size_t)t * n + da) * cw + cc] = (qpos[qa] - y0[qa]) * ih;
+    }
+  }
+  for (int i = lane; i < nv; i += 32) Sout[((size_t)t * n + nv + i) * cw + cc] = (qvel[i] - y0[nq + i]) * ih;
+}
+
+// ------------------------------------------------------------------------------------------ cost derivatives
+struct CostArgs {
+  DevModel M;
+  const float* pack;
+  const float* residual;  // [H][nr]
+  const float* C;         // [H][nr][n]
+  const float* D;         // [H][nr][m]
+  int H, n, m;
+  float *cx, *cu, *cxx, *cuu, *cxu;
+};
+
+// one CTA per time step; dynamic smem: g[nr] Hn[kmax^2] Sx[kmax*n] Su[kmax*m] acc[n + m + n*n + m*m + n*m] cval[1]
+extern "C" __global__ void __launch_bounds__(256) cost_derivatives_kernel(const __grid_constant__ CostArgs A) {
+  extern __shared__ __align__(16) float sm[];
+  const DevModel& M = A.M;
+  const int t = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, n = A.n, m = A.m, nr = M.num_residual;
+  const float* mf = A.pack;
+  const int* mi = reinterpret_cast<const int*>(A.pack + M.nf);
+  const int *dimr = mi + M.io[I_task_dim_norm_residual], *ntype = mi + M.io[I_task_norm], *npar = mi + M.io[I_task_num_norm_parameter];
+  const float *wgt = mf + M.fo[F_task_weight], *prm = mf + M.fo[F_task_norm_parameter];
+  int kmax = 1;
+  for (int i = 0; i < M.num_term; i++) kmax = max(kmax, dimr[i]);
+  float* g = sm;
+  float* Hn = g + nr;
+  float* Sx = Hn + kmax * kmax;
+  float* Su = Sx + kmax * n;
+  float* acc = Su + kmax * m;
+  float *aCx = acc, *aCu = aCx + n, *aCxx = aCu + m, *aCuu = aCxx + n * n, *aCxu = aCuu + m * m;
+  float* cval = aCxu + n * m;
+  const int nacc = n + m + n * n + m * m + n * m;
+  for (int i = tid; i < nacc; i += nt) acc[i] = 0;
+  if (tid == 0) *cval = 0;
+  __syncthreads();
+  int f = 0, p = 0;
+  for (int i = 0; i < M.num_term; i++) {
+    const int k = dimr[i];
+    const float w = wgt[i] / (float)A.H;
+    const float* r = A.residual + (size_t)t * nr + f;
+    const float* rx = A.C + ((size_t)t * nr + f) * n;
+    const float* ru = A.D + ((size_t)t * nr + f) * m;
+    if (tid == 0) {
+      float pr[2] = {npar[i] > 0 ? prm[p] : 0.f, npar[i] > 1 ? prm[p + 1] : 0.f};
+      *cval += w * norm_full(g, Hn, r, pr, k, ntype[i]);
+    }
+    __syncthreads();
+    for (int e = tid; e < k * n; e += nt) { const int a = e / n, b = e - a * n; float s = 0; for (int q = 0; q < k; q++) s += Hn[a * k + q] * rx[q * n + b]; Sx[e] = s; }
+    for (int e = tid; e < k * m; e += nt) { const int a = e / m, b = e - a * m; float s = 0; for (int q = 0; q < k; q++) s += Hn[a * k + q] * ru[q * m + b]; Su[e] = s; }
+    for (int a = tid; a < n; a += nt) { float s = 0; for (int b = 0; b < k; b++) s += rx[b * n + a] * g[b]; aCx[a] += w * s; }
+    for (int a = tid; a < m; a += nt) { float s = 0; for (int b = 0; b < k; b++) s += ru[b * m + a] * g[b]; aCu[a] += w * s; }
+    __syncthreads();
+    for (int e = tid; e < n * n; e += nt) { const int a = e / n, b = e - a * n; float s = 0; for (int q = 0; q < k; q++) s += Sx[q * n + a] * rx[q * n + b]; aCxx[e] += w * s; }
+    for (int e = tid; e < n * m; e += nt) { const int a = e / m, b = e - a * m; float s = 0; for (int q = 0; q < k; q++) s += Sx[q * n + a] * ru[q * m + b]; aCxu[e] += w * s; }
+    for (int e = tid; e < m * m; e += nt) { const int a = e / m, b = e - a * m; float s = 0; for (int q = 0; q < k; q++) s += Su[q * m + a] * ru[q * m + b]; aCuu[e] += w * s; }
+    __syncthreads();
+    f += k;
+    p += npar[i];
+  }
+  // risk transformation (cost_derivatives.cc:160-224): scale, then outer products of the SCALED gradients
+  if (fabsf(M.risk) >= 1e-6f) {
+    const float s = expf(M.risk * (*cval));
+    for (int a = tid; a < n; a += nt) aCx[a] *= s;
+    for (int a = tid; a < m; a += nt) aCu[a] *= s;
+    __syncthreads();
+    for (int e = tid; e < n * n; e += nt) { const int a = e / n, b = e - a * n; aCxx[e] = aCxx[e] * s + M.risk * s * aCx[a] * aCx[b]; }
+    for (int e = tid; e < n * m; e += nt) { const int a = e / m, b = e - a * m; aCxu[e] = aCxu[e] * s + M.risk * s * aCx[a] * aCu[b]; }
+    for (int e = tid; e < m * m; e += nt) { const int a = e / m, b = e - a * m; aCuu[e] = aCuu[e] * s + M.risk * s * aCu[a] * aCu[b]; }
+    __syncthreads();
+  }
+  for (int a = tid; a < n; a += nt) A.cx[(size_t)t * n + a] = aCx[a];
+  for (int a = tid; a < m; a += nt) A.cu[(size_t)t * m + a] = aCu[a];
+  for (int e = tid; e < n * n; e += nt) A.cxx[(size_t)t * n * n + e] = aCxx[e];
+  for (int e = tid; e < m * m; e += nt) A.cuu[(size_t)t * m * m + e] = aCuu[e];
+  for (int e = tid; e < n * m; e += nt) A.cxu[(size_t)t * n * m + e] = aCxu[e];
+}
+
+// ------------------------------------------------------------------------------------------ backward pass
+struct BackwardArgs {
+  const float *A, *B, *cx, *cu, *cxx, *cxu, *cuu, *actions, *ctrlrange;
+  int n, m, H, reg_type, limits;
+  float mu;
+  float *K, *du, *dV, *Vx, *Vxx;
+  int* status;
+};
+
+// dense Cholesky / solve for the tiny box-QP blocks, single thread
+__device__ inline float chol_serial(float* A, int n) {
+  float minp = 3.4e38f;
+  for (int j = 0; j < n; j++) {
+    float s = A[j * n + j];
+    for (int k = 0; k < j; k++) s -= A[j * n + k] * A[j * n + k];
+    minp = fminf(minp, s);
+    if (s < 1e-15f) s = 1e-15f;
+    const float l = sqrtf(s);
+    A[j * n + j] = l;
+    for (int i = j + 1; i < n; i++) {
+      float tt = A[i * n + j];
+      for (int k = 0; k < j; k++) tt -= A[i * n + k] * A[j * n + k];
+      A[i * n + j] = tt / l;
+    }
+  }
+  return minp;
+}
+__device__ inline void chol_solve_serial(float* x, const float* L, const float* b, int n) {
+  for (int i = 0; i < n; i++) { float s = b[i]; for (int k = 0; k < i; k++) s -= L[i * n + k] * x[k]; x[i] = s / L[i * n + i]; }
+  for (int i = n - 1; i >= 0; i--) { float s = x[i]; for (int k = i + 1; k < n; k++) s -= L[k * n + i] * x[k]; x[i] = s / L[i * n + i]; }
+}
+// projected-Newton box QP (same algorithm and constants as oracle/ilqg.h box_qp). scratch >= 6n floats + n ints
+__device__ inline int box_qp_serial(float* res, float* R, int* index, const float* Hm, const float* g, int n,
+                                    const float* lower, const float* upper, float* scratch) {
+  const int maxiter = 100;
+  const float mingrad = 1e-16f, backtrack = 0.5f, minstep = 1e-22f, armijo = 0.01f;
+  float *grad = scratch, *search = grad + n, *cand = search + n, *tmp = cand + n, *rhs = tmp + n, *sol = rhs + n;
+  int* clamped = reinterpret_cast<int*>(sol + n);
+  for (int i = 0; i < n; i++) { res[i] = fmaxf(lower[i], fminf(upper[i], res[i])); clamped[i] = 0; }
+  auto value_of = [&](const float* x) {
+    float v = 0;
+    for (int i = 0; i < n; i++) { float a = 0; for (int j = 0; j < n; j++) a += Hm[i * n + j] * x[j]; v += x[i] * (0.5f * a + g[i]); }
+    return v;
+  };
+  float value = value_of(res);
+  int nfree = 0;
+  for (int iter = 0; iter < maxiter; iter++) {
+    for (int i = 0; i < n; i++) { float a = g[i]; for (int j = 0; j < n; j++) a += Hm[i * n + j] * res[j]; grad[i] = a; }
+    bool changed = iter == 0;
+    nfree = 0;
+    for (int i = 0; i < n; i++) {
+      const int cl = (res[i] == lower[i] && grad[i] > 0) || (res[i] == upper[i] && grad[i] < 0);
+      if (cl != clamped[i]) changed = true;
+      clamped[i] = cl;
+      if (!cl) index[nfree++] = i;
+    }
+    if (nfree == 0) break;
+    if (changed) {
+      for (int a = 0; a < nfree; a++)
+        for (int b = 0; b < nfree; b++) R[a * nfree + b] = Hm[index[a] * n + index[b]];
+      if (!(chol_serial(R, nfree) > 1e-15f)) return -1;
+    }
+    float norm2 = 0;
+    for (int a = 0; a < nfree; a++) norm2 += grad[index[a]] * grad[index[a]];
+    if (norm2 < mingrad * mingrad) break;
+    for (int i = 0; i < n; i++) tmp[i] = clamped[i] ? res[i] : 0.f;
+    for (int a = 0; a < nfree; a++) {
+      const int i = index[a];
+      float s = g[i];
+      for (int j = 0; j < n; j++) s += Hm[i * n + j] * tmp[j];
+      rhs[a] = s;
+    }
+    chol_solve_serial(sol, R, rhs, nfree);
+    for (int i = 0; i < n; i++) search[i] = 0;
+    for (int a = 0; a < nfree; a++) search[index[a]] = -sol[a] - res[index[a]];
+    float sdotg = 0;
+    for (int i = 0; i < n; i++) sdotg += search[i] * grad[i];
+    if (sdotg >= 0) break;
+    float step = 1, vc = value;
+    bool accepted = false;
+    while (step > minstep) {
+      for (int i = 0; i < n; i++) cand[i] = fmaxf(lower[i], fminf(upper[i], res[i] + step * search[i]));
+      vc = value_of(cand);
+      if ((vc - value) / (step * sdotg) >= armijo) { accepted = true; break; }
+      step *= backtrack;
+    }
+    if (!accepted) break;
+    for (int i = 0; i < n; i++) res[i] = cand[i];
+    value = vc;
+  }
+  return nfree;
+}
+
+// dynamic smem layout (floats): At[n*n] Bt[n*m] W[n*n] T1[n*n] Qxx[n*n] Qxu[n*m] Quu[m*m] QxuR[n*m] QuuR[m*m]
+//   K[m*n] Wx[n] Qx[n] Qu[m] du[m] Qd[m] qp_res[m] qp_R[m*m] qp_lo[m] qp_hi[m] scratch[8m] + index[m] ints
+extern "C" __global__ void __launch_bounds__(256) backward_pass_kernel(const __grid_constant__ BackwardArgs P) {
+  extern __shared__ __align__(16) float sm[];
+  const int n = P.n, m = P.m, H = P.H, tid = threadIdx.x, nt = blockDim.x;
+  float* At = sm; float* Bt = At + n * n; float* W = Bt + n * m; float* T1 = W + n * n; float* Qxx = T1 + n * n;
+  float* Qxu = Qxx + n * n; float* Quu = Qxu + n * m; float* QxuR = Quu + m * m; float* QuuR = QxuR + n * m;
+  float* K = QuuR + m * m; float* Wx = K + m * n; float* Qx = Wx + n; float* Qu = Qx + n; float* du = Qu + m;
+  float* Qd = du + m; float* qp_res = Qd + m; float* qp_R = qp_res + m; float* qp_lo = qp_R + m * m; float* qp_hi = qp_lo + m;
+  float* scratch = qp_hi + m;
+  int* qp_index = reinterpret_cast<int*>(scratch + 8 * m);
+  __shared__ int s_mf, s_ok;
+  __shared__ float s_dV[2];
+  if (tid == 0) { s_dV[0] = s_dV[1] = 0; s_ok = 1; }
+  for (int i = tid; i < m; i += nt) qp_res[i] = 0;
+  // terminal value function
+  for (int i = tid; i < n; i += nt) { const float v = P.cx[(size_t)(H - 1) * n + i]; Wx[i] = v; if (P.Vx) P.Vx[(size_t)(H - 1) * n + i] = v; }
+  for (int i = tid; i < n * n; i += nt) { const float v = P.cxx[(size_t)(H - 1) * n * n + i]; W[i] = v; if (P.Vxx) P.Vxx[(size_t)(H - 1) * n * n + i] = v; }
+  __syncthreads();
+  for (int t = H - 2; t >= 0; t--) {
+    for (int i = tid; i < n * n; i += nt) At[i] = P.A[(size_t)t * n * n + i];
+    for (int i = tid; i < n * m; i += nt) Bt[i] = P.B[(size_t)t * n * m + i];
+    __syncthreads();
+    // T1 = At' W ; Qx, Qu
+    for (int e = tid; e < n * n; e += nt) { const int i = e / n, j = e - i * n; float s = 0; for (int k = 0; k < n; k++) s += At[k * n + i] * W[k * n + j]; T1[e] = s; }
+    for (int i = tid; i < n; i += nt) { float s = P.cx[(size_t)t * n + i]; for (int k = 0; k < n; k++) s += At[k * n + i] * Wx[k]; Qx[i] = s; }
+    for (int i = tid; i < m; i += nt) { float s = P.cu[(size_t)t * m + i]; for (int k = 0; k < n; k++) s += Bt[k * m + i] * Wx[k]; Qu[i] = s; }
+    __syncthreads();
+    for (int e = tid; e < n * n; e += nt) { const int i = e / n, j = e - i * n; float s = P.cxx[(size_t)t * n * n + e]; for (int k = 0; k < n; k++) s += T1[i * n + k] * At[k * n + j]; Qxx[e] = s; }
+    for (int e = tid; e < n * m; e += nt) { const int i = e / m, j = e - i * m; float s = P.cxu[(size_t)t * n * m + e]; for (int k = 0; k < n; k++) s += T1[i * n + k] * Bt[k * m + j]; Qxu[e] = s; }
+    __syncthreads();
+    // Quu = cuu + Bt' W Bt : T1[0:m*n] = Bt' W
+    for (int e = tid; e < m * n; e += nt) { const int i = e / n, j = e - i * n; float s = 0; for (int k = 0; k < n; k++) s += Bt[k * m + i] * W[k * n + j]; T1[e] = s; }
+    __syncthreads();
+    for (int e = tid; e < m * m; e += nt) { const int i = e / m, j = e - i * m; float s = P.cuu[(size_t)t * m * m + e]; for (int k = 0; k < n; k++) s += T1[i * n + k] * Bt[k * m + j]; Quu[e] = s; }
+    __syncthreads();
+    // regularisation (backward_pass.cc:115-153)
+    if (P.reg_type == 2) {
+      // value regularisation: Vreg = W + mu I ; QxuR = cxu + At' Vreg Bt ; QuuR = cuu + Bt' Vreg Bt
+      for (int e = tid; e < n * n; e += nt) { const int i = e / n, j = e - i * n; float s = 0; for (int k = 0; k < n; k++) s += At[k * n + i] * (W[k * n + j] + (k == j ? P.mu : 0.f)); T1[e] = s; }
+      __syncthreads();
+      for (int e = tid; e < n * m; e += nt) { const int i = e / m, j = e - i * m; float s = P.cxu[(size_t)t * n * m + e]; for (int k = 0; k < n; k++) s += T1[i * n + k] * Bt[k * m + j]; QxuR[e] = s; }
+      __syncthreads();
+      for (int e = tid; e < m * n; e += nt) { const int i = e / n, j = e - i * n; float s = 0; for (int k = 0; k < n; k++) s += Bt[k * m + i] * (W[k * n + j] + (k == j ? P.mu : 0.f)); T1[e] = s; }
+      __syncthreads();
+      for (int e = tid; e < m * m; e += nt) { const int i = e / m, j = e - i * m; float s = P.cuu[(size_t)t * m * m + e]; for (int k = 0; k < n; k++) s += T1[i * n + k] * Bt[k * m + j]; QuuR[e] = s; }
+    } else {
+      for (int e = tid; e < n * m; e += nt) QxuR[e] = Qxu[e];
+      for (int e = tid; e < m * m; e += nt) QuuR[e] = Quu[e];
+    }
+    __syncthreads();
+    if (P.mu != 0.f) {
+      if (P.reg_type == 0) {
+        for (int i = tid; i < m; i += nt) QuuR[i * m + i] += P.mu;
+      } else if (P.reg_type == 1) {
+        for (int e = tid; e < n * m; e += nt) { const int i = e / m, j = e - i * m; float s = 0; for (int k = 0; k < n; k++) s += At[k * n + i] * Bt[k * m + j]; QxuR[e] += P.mu * s; }
+        for (int e = tid; e < m * m; e += nt) { const int i = e / m, j = e - i * m; float s = 0; for (int k = 0; k < n; k++) s += Bt[k * m + i] * Bt[k * m + j]; QuuR[e] += P.mu * s; }
+      }
+    }
+    for (int e = tid; e < m * n; e += nt) K[e] = 0;
+    __syncthreads();
+    // control step: box QP (or plain solve) on one thread, gains on all threads
+    if (tid == 0) {
+      int mf;
+      if (P.limits == 1) {
+        for (int i = 0; i < m; i++) {
+          qp_lo[i] = P.ctrlrange[2 * i] - P.actions[(size_t)t * m + i];
+          qp_hi[i] = P.ctrlrange[2 * i + 1] - P.actions[(size_t)t * m + i];
+        }
+        mf = box_qp_serial(qp_res, qp_R, qp_index, QuuR, Qu, m, qp_lo, qp_hi, scratch);
+        if (mf >= 0) for (int i = 0; i < m; i++) du[i] = qp_res[i];
+      } else {
+        for (int i = 0; i < m * m; i++) qp_R[i] = QuuR[i];
+        mf = (chol_serial(qp_R, m) > 1e-15f) ? m : -1;
+        if (mf >= 0) {
+          for (int i = 0; i < m; i++) qp_index[i] = i;
+          chol_solve_serial(du, qp_R, Qu, m);
+          for (int i = 0; i < m; i++) du[i] = -du[i];
+        }
+      }
+      s_mf = mf;
+      if (mf < 0) s_ok = 0;
+    }
+    __syncthreads();
+    if (!s_ok) break;
+    const int mf = s_mf;
+    // K on the free dims: column j of -H_free^-1 Qxu_free' (unregularised Qxu, backward_pass.cc:176-192)
+    for (int j = tid; j < n; j += nt) {
+      float rhs[32], sol[32];
+      for (int i = 0; i < mf; i++) rhs[i] = Qxu[j * m + qp_index[i]];
+      chol_solve_serial(sol, qp_R, rhs, mf);
+      for (int i = 0; i < mf; i++) K[qp_index[i] * n + j] = -sol[i];
+    }
+    for (int i = tid; i < m; i += nt) { float s = 0; for (int j = 0; j < m; j++) s += Quu[i * m + j] * du[j]; Qd[i] = s; }
+    __syncthreads();
+    if (tid == 0) {
+      float d0 = 0, d1 = 0;
+      for (int i = 0; i < m; i++) { d0 += du[i] * Qu[i]; d1 += 0.5f * du[i] * Qd[i]; }
+      s_dV[0] += d0; s_dV[1] += d1;
+    }
+    // T1[0:m*n] = Quu K
+    for (int e = tid; e < m * n; e += nt) { const int i = e / n, j = e - i * n; float s = 0; for (int k = 0; k < m; k++) s += Quu[i * m + k] * K[k * n + j]; T1[e] = s; }
+    __syncthreads();
+    // new value function: Vx -> Wx, Vxx -> At (scratch) then symmetrised into W
+    for (int i = tid; i < n; i += nt) {
+      float s = Qx[i];
+      for (int k = 0; k < m; k++) s += K[k * n + i] * (Qd[k] + Qu[k]) + Qxu[i * m + k] * du[k];
+      Qx[i] = s;
+    }
+    for (int e = tid; e < n * n; e += nt) {
+      const int i = e / n, j = e - i * n;
+      float s = Qxx[e];
+      for (int k = 0; k < m; k++) s += K[k * n + i] * T1[k * n + j] + Qxu[i * m + k] * K[k * n + j] + K[k * n + i] * Qxu[j * m + k];
+      At[e] = s;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) { Wx[i] = Qx[i]; if (P.Vx) P.Vx[(size_t)t * n + i] = Qx[i]; }
+    for (int e = tid; e < n * n; e += nt) {
+      const int i = e / n, j = e - i * n;
+      const float v = 0.5f * (At[i * n + j] + At[j * n + i]);
+      W[e] = v;
+      if (P.Vxx) P.Vxx[(size_t)t * n * n + e] = v;
+    }
+    for (int e = tid; e < m * n; e += nt) P.K[(size_t)t * m * n + e] = K[e];
+    for (int i = tid; i < m; i += nt) P.du[(size_t)t * m + i] = du[i];
+    __syncthreads();
+  }
+  if (s_ok) {
+    for (int e = tid; e < m * n; e += nt) P.K[(size_t)(H - 1) * m * n + e] = P.K[(size_t)(H - 2) * m * n + e];
+    for (int i = tid; i < m; i += nt) P.du[(size_t)(H - 1) * m + i] = P.du[(size_t)(H - 2) * m + i];
+  }
+  if (tid == 0) { P.dV[0] = s_dV[0]; P.dV[1] = s_dV[1]; *P.status = s_ok; }
+}
+
+// ------------------------------------------------------------------------------------------ host launchers
+inline cudaError_t raise_smem_limit(const void* fn, size_t bytes) {
+  static std::vector<std::pair<const void*, size_t>> seen;
+  for (auto& e : seen)
+    if (e.first == fn) {
+      if (e.second >= bytes) return cudaSuccess;
+      e.second = bytes;
+      return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    }
+  seen.emplace_back(fn, bytes);
+  return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+struct IlqgBuffers {
+  int H = 0, ds = 0, n = 0, nu = 0, nr = 0, nv = 0;
+  float *x = nullptr, *u = nullptr, *t = nullptr, *mocap = nullptr, *ts = nullptr, *y0 = nullptr, *r0 = nullptr,
+        *q0 = nullptr, *A = nullptr, *B = nullptr, *C = nullptr, *D = nullptr, *res = nullptr, *cx = nullptr,
+        *cu = nullptr, *cxx = nullptr, *cuu = nullptr, *cxu = nullptr, *act = nullptr, *K = nullptr, *du = nullptr,
+        *dV = nullptr, *Vx = nullptr, *Vxx = nullptr, *range = nullptr;
+  int* status = nullptr;
+  std::vector<float**> all() {
+    return {&x, &u, &t, &mocap, &ts, &y0, &r0, &q0, &A, &B, &C, &D, &res, &cx, &cu, &cxx, &cuu, &cxu, &act, &K, &du,
+            &dV, &Vx, &Vxx, &range};
+  }
+};
+
+inline int ilqg_init(IlqgBuffers& b, const DevModel& M, int H, size_t smem_fd) {
+  b.H = H; b.nv = M.nv; b.ds = M.nq + M.nv; b.n = 2 * M.nv; b.nu = M.nu; b.nr = M.num_residual;
+  const size_t Hs = H, n = b.n, m = b.nu, nr = b.nr, ds = b.ds;
+  struct { float** p; size_t cnt; } plan[] = {
+      {&b.x, Hs * ds}, {&b.u, Hs * m}, {&b.t, Hs}, {&b.mocap, 7 * (size_t)M.nmocap + 1}, {&b.ts, (size_t)M.task_state_size + 1},
+      {&b.y0, Hs * ds}, {&b.r0, Hs * nr}, {&b.q0, Hs * M.nv}, {&b.A, Hs * n * n}, {&b.B, Hs * n * m}, {&b.C, Hs * nr * n},
+      {&b.D, Hs * nr * m}, {&b.res, Hs * nr}, {&b.cx, Hs * n}, {&b.cu, Hs * m}, {&b.cxx, Hs * n * n}, {&b.cuu, Hs * m * m},
+      {&b.cxu, Hs * n * m}, {&b.act, Hs * m}, {&b.K, Hs * m * n}, {&b.du, Hs * m}, {&b.dV, 2}, {&b.Vx, Hs * n},
+      {&b.Vxx, Hs * n * n}, {&b.range, 2 * m + 1}};
+  for (auto& e : plan)
+    if (cudaMalloc((void**)e.p, (e.cnt ? e.cnt : 1) * sizeof(float)) != cudaSuccess) return -4;
+  if (cudaMalloc((void**)&b.status, sizeof(int)) != cudaSuccess) return -4;
+  if (raise_smem_limit((const void*)fd_center_kernel, smem_fd) != cudaSuccess) return -4;
+  if (raise_smem_limit((const void*)fd_column_kernel, smem_fd) != cudaSuccess) return -4;
   return 0;
 }
 inline void ilqg_free(IlqgBuffers& b) {
-  if (b.d_buf) cudaFree(b.d_buf);
-  b.d_buf = nullptr;
+  for (float** p : b.all()) if (*p) { cudaFree(*p); *p = nullptr; }
+  if (b.status) { cudaFree(b.status); b.status = nullptr; }
 }
-inline int ilqg_model_derivatives(IlqgBuffers&, const DevModel&, const float*, cudaStream_t, const float*, const float*,
-                                  const float*, const float*, const float*, int, float, float*, float*, float*, float*,
-                                  size_t, int*) {
-  return -5;
+
+#define ILQG_TRY(e) do { if ((e) != cudaSuccess) { cudaGetLastError(); return -4; } } while (0)
+
+inline int ilqg_model_derivatives(IlqgBuffers& b, const DevModel& M, const float* d_pack, cudaStream_t st, const float* x,
+                                  const float* u, const float* trel, const float* mocap, const float* ts, int H, float eps,
+                                  float* A, float* B, float* C, float* D, size_t smem, int* launches) {
+  const size_t n = b.n, m = b.nu, nr = b.nr, ds = b.ds;
+  ILQG_TRY(cudaMemcpyAsync(b.x, x, H * ds * 4, cudaMemcpyHostToDevice, st));
+  ILQG_TRY(cudaMemcpyAsync(b.u, u, H * m * 4, cudaMemcpyHostToDevice, st));
+  ILQG_TRY(cudaMemcpyAsync(b.t, trel, (size_t)H * 4, cudaMemcpyHostToDevice, st));
+  if (M.nmocap) ILQG_TRY(cudaMemcpyAsync(b.mocap, mocap, 7 * M.nmocap * 4, cudaMemcpyHostToDevice, st));
+  if (M.task_state_size) ILQG_TRY(cudaMemcpyAsync(b.ts, ts, M.task_state_size * 4, cudaMemcpyHostToDevice, st));
+  ILQG_TRY(cudaMemsetAsync(b.A, 0, H * n * n * 4, st)); ILQG_TRY(cudaMemsetAsync(b.B, 0, H * n * m * 4, st));
+  ILQG_TRY(cudaMemsetAsync(b.C, 0, H * nr * n * 4, st)); ILQG_TRY(cudaMemsetAsync(b.D, 0, H * nr * m * 4, st));
+  FdArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.M = M; a.L = make_layout(M, 1); a.pack = d_pack; a.x = b.x; a.u = b.u; a.t = b.t; a.mocap = b.mocap;
+  a.task_state = M.task_state_size ? b.ts : nullptr; a.H = H; a.eps = eps; a.y0 = b.y0; a.r0 = b.r0; a.q0 = b.q0;
+  a.A = b.A; a.B = b.B; a.C = b.C; a.D = b.D;
+  fd_center_kernel<<<H, 32, smem, st>>>(a);
+  fd_column_kernel<<<H * (M.nu + 2 * M.nv), 32, smem, st>>>(a);
+  *launches += 2;
+  ILQG_TRY(cudaGetLastError());
+  ILQG_TRY(cudaMemcpyAsync(A, b.A, H * n * n * 4, cudaMemcpyDeviceToHost, st));
+  ILQG_TRY(cudaMemcpyAsync(B, b.B, H * n * m * 4, cudaMemcpyDeviceToHost, st));
+  ILQG_TRY(cudaMemcpyAsync(C, b.C, H * nr * n * 4, cudaMemcpyDeviceToHost, st));
+  ILQG_TRY(cudaMemcpyAsync(D, b.D, H * nr * m * 4, cudaMemcpyDeviceToHost, st));
+  ILQG_TRY(cudaStreamSynchronize(st));
+  return 0;
 }
-inline int ilqg_cost_derivatives(IlqgBuffers&, const DevModel&, const float*, cudaStream_t, const float*, const float*,
-                                 const float*, int, float*, float*, float*, float*, float*, int*) {
-  return -5;
+
+inline int ilqg_cost_derivatives(IlqgBuffers& b, const DevModel& M, const float* d_pack, cudaStream_t st,
+                                 const float* residual, const float* C, const float* D, int H, float* cx, float* cu,
+                                 float* cxx, float* cuu, float* cxu, int* launches) {
+  const size_t n = b.n, m = b.nu, nr = b.nr;
+  ILQG_TRY(cudaMemcpyAsync(b.res, residual, H * nr * 4, cudaMemcpyHostToDevice, st));
+  ILQG_TRY(cudaMemcpyAsync(b.C, C, H * nr * n * 4, cudaMemcpyHostToDevice, st));
+  ILQG_TRY(cudaMemcpyAsync(b.D, D, H * nr * m * 4, cudaMemcpyHostToDevice, st));
+  CostArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.M = M; a.pack = d_pack; a.residual = b.res; a.C = b.C; a.D = b.D; a.H = H; a.n = (int)n; a.m = (int)m;
+  a.cx = b.cx; a.cu = b.cu; a.cxx = b.cxx; a.cuu = b.cuu; a.cxu = b.cxu;
+  const size_t kmax = 32;
+  const size_t smem = (nr + kmax * kmax + kmax * n + kmax * m + n + m + n * n + m * m + n * m + 8) * 4;
+  ILQG_TRY(raise_smem_limit((const void*)cost_derivatives_kernel, smem));
+  cost_derivatives_kernel<<<H, 256, smem, st>>>(a);
+  *launches += 1;
+  ILQG_TRY(cudaGetLastError());
+  ILQG_TRY(cudaMemcpyAsync(cx, b.cx, H * n * 4, cudaMemcpyDeviceToHost, st));
+  ILQG_TRY(cudaMemcpyAsync(cu, b.cu, H * m * 4, cudaMemcpyDeviceToHost, st));
+  ILQG_TRY(cudaMemcpyAsync(cxx, b.cxx, H * n * n * 4, cudaMemcpyDeviceToHost, st));
+  ILQG_TRY(cudaMemcpyAsync(cuu, b.cuu, H * m * m * 4, cudaMemcpyDeviceToHost, st));
+  ILQG_TRY(cudaMemcpyAsync(cxu, b.cxu, H * n * m * 4, cudaMemcpyDeviceToHost, st));
+  ILQG_TRY(cudaStreamSynchronize(st));
+  return 0;
 }
-inline int ilqg_backward_pass(IlqgBuffers&, const DevModel&, const float*, cudaStream_t, const float*, const float*,
-                              const float*, const float*, const float*, const float*, const float*, const float*, int,
-                              float, int, int, float*, float*, float*, float*, float*, int*, int*) {
-  return -5;
+
+inline int ilqg_backward_pass(IlqgBuffers& b, const DevModel& M, const float* d_pack, cudaStream_t st, const float* A,
+                              const float* B, const float* cx, const float* cu, const float* cxx, const float* cxu,
+                              const float* cuu, const float* actions, int H, float mu, int reg_type, int limits, float* K,
+                              float* du, float* dV, float* Vx, float* Vxx, int* status_out, int* launches) {
+  (void)d_pack;
+  const size_t n = b.n, m = b.nu;
+  if (m > 32) return -5;
+  ILQG_TRY(cudaMemcpyAsync(b.A, A, H * n * n * 4, cudaMemcpyHostToDevice, st));
+  ILQG_TRY(cudaMemcpyAsync(b.B, B, H * n * m * 4, cudaMemcpyHostToDevice, st));
+  ILQG_TRY(cudaMemcpyAsync(b.cx, cx, H * n * 4, cudaMemcpyHostToDevice, st));
+  ILQG_TRY(cudaMemcpyAsync(b.cu, cu, H * m * 4, cudaMemcpyHostToDevice, st));
+  ILQG_TRY(cudaMemcpyAsync(b.cxx, cxx, H * n * n * 4, cudaMemcpyHostToDevice, st));
+  ILQG_TRY(cudaMemcpyAsync(b.cxu, cxu, H * n * m * 4, cudaMemcpyHostToDevice, st));
+  ILQG_TRY(cudaMemcpyAsync(b.cuu, cuu, H * m * m * 4, cudaMemcpyHostToDevice, st));
+  ILQG_TRY(cudaMemcpyAsync(b.act, actions, H * m * 4, cudaMemcpyHostToDevice, st));
+  BackwardArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.A = b.A; a.B = b.B; a.cx = b.cx; a.cu = b.cu; a.cxx = b.cxx; a.cxu = b.cxu; a.cuu = b.cuu; a.actions = b.act;
+  a.ctrlrange = d_pack + M.fo[F_actuator_ctrlrange];
+  a.n = (int)n; a.m = (int)m; a.H = H; a.reg_type = reg_type; a.limits = limits; a.mu = mu;
+  a.K = b.K; a.du = b.du; a.dV = b.dV; a.Vx = b.Vx; a.Vxx = b.Vxx; a.status = b.status;
+  const size_t smem = (4 * n * n + 3 * n * m + 3 * m * m + m * n + 2 * n + 12 * m + 9 * m + 16) * 4;
+  ILQG_TRY(raise_smem_limit((const void*)backward_pass_kernel, smem));
+  backward_pass_kernel<<<1, 256, smem, st>>>(a);
+  *launches += 1;
+  ILQG_TRY(cudaGetLastError());
+  ILQG_TRY(cudaMemcpyAsync(K, b.K, H * m * n * 4, cudaMemcpyDeviceToHost, st));
+  ILQG_TRY(cudaMemcpyAsync(du, b.du, H * m * 4, cudaMemcpyDeviceToHost, st));
+  ILQG_TRY(cudaMemcpyAsync(dV, b.dV, 2 * 4, cudaMemcpyDeviceToHost, st));
+  if (Vx) ILQG_TRY(cudaMemcpyAsync(Vx, b.Vx, H * n * 4, cudaMemcpyDeviceToHost, st));
+  if (Vxx) ILQG_TRY(cudaMemcpyAsync(Vxx, b.Vxx, H * n * n * 4, cudaMemcpyDeviceToHost, st));
+  ILQG_TRY(cudaMemcpyAsync(status_out, b.status, 4, cudaMemcpyDeviceToHost, st));
+  ILQG_TRY(cudaStreamSynchronize(st));
+  return 0;
 }
 
 }  // namespace mjpc_dev

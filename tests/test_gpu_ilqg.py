@@ -1,0 +1,134 @@
+"""GPU: iLQG sweeps (FD model derivatives, cost derivatives, Riccati backward pass, feedback rollouts) vs the oracle.
+
+Tolerances: fp32 finite differences need a much larger step than the reference's 1e-6 (fp64): with eps = 1e-3 the
+truncation error is O(eps) and round-off O(1e-7/eps); the device result is compared with the fp64 oracle run at the
+SAME eps (same secant), so what remains is fp32 round-off amplified by 1/eps ~ 1e-4 .. 1e-3 absolute on O(1) entries.
+"""
+import numpy as np
+import pytest
+
+from conftest import get_model, mocap_of, quadruped_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx(oracle_lib):
+    from mujoco_mpc_b200 import build
+    from mujoco_mpc_b200.blob import to_blob
+    from mujoco_mpc_b200.engine import Engine
+    build.build()
+    out = {}
+    for name in ("cartpole", "quadruped", "particle"):
+        m = get_model(name)
+        out[name] = (m, Engine(m, 64, 64), oracle_lib.Oracle(to_blob(m), m, 64))
+    yield out
+    for _, e, _ in out.values():
+        e.close()
+
+
+def _nominal(m, o, H, seed=0):
+    """A nominal trajectory from the oracle (spline rollout of small random knots)."""
+    from mujoco_mpc_b200.planner import candidate_knots
+    P = 3
+    cr = np.asarray(m.actuator_ctrlrange).reshape(-1, 2)
+    state = np.concatenate([m.key_qpos[0] if m.nkey else m.qpos0, np.zeros(m.nv)])
+    kt = np.arange(P) * (H - 1) * m.opt_timestep / (P - 1)
+    knots = candidate_knots(np.zeros((P, m.nu)), 0.3, cr, seed, 2)[1:2]
+    r = o.rollout_spline(state, 0.0, mocap_of(m), knots, kt, 2, H)
+    return state, r["states"][0], r["actions"][0], r["times"][0], r["residual"][0]
+
+
+def test_backward_pass_golden_on_device(ctx, oracle_lib):
+    """backward_pass_test.cc:29-140 through the device kernel: the n=2, m=1 LQR embedded in the cartpole-sized
+    problem (n=4, m=1) with two decoupled, cost-free extra states."""
+    m, e, _ = ctx["cartpole"]
+    H, n = 3, 4
+    A = np.tile(np.eye(n), (H, 1, 1)); A[:, 0, 1] = 1.0
+    B = np.zeros((H, n, 1)); B[:, 1, 0] = 1.0
+    u = np.full((H, 1), 0.5); x = np.zeros((H, n))
+    for t in range(H - 1):
+        x[t + 1, :2] = [x[t, 0] + x[t, 1], x[t, 1] + u[t, 0]]
+    cx = x.copy(); cu = u.copy(); cu[H - 1] = 0
+    cxx = np.zeros((H, n, n)); cxx[:, 0, 0] = cxx[:, 1, 1] = 1.0
+    cuu = np.ones((H, 1, 1)); cxu = np.zeros((H, n, 1))
+    o = e.backward_pass(A, B, cx, cu, cxx, cxu, cuu, u, mu=0.0, reg_type=0, limits=1)
+    assert o["status"] == 1
+    np.testing.assert_allclose(o["Vx"][:, :2].ravel(), [0.0, 0.0, 0.5, 1.25, 0.5, 1.0], atol=1e-5)
+    np.testing.assert_allclose(o["Vxx"][:, :2, :2].ravel(), [2.71428571, 2.0, 2.0, 4.0, 2.0, 1.0, 1.0, 2.5, 1.0, 0.0, 0.0, 1.0], atol=1e-5)
+    np.testing.assert_allclose(o["K"][:2, 0, :2].ravel(), [-0.285714285, -1.0, 0.0, -0.5], atol=1e-5)
+    np.testing.assert_allclose(o["du"][:2].ravel(), [-0.5, -0.75], atol=1e-5)
+    assert np.abs(o["K"][:, :, 2:]).max() == 0 and np.abs(o["Vxx"][:, 2:, :]).max() == 0
+
+
+@pytest.mark.parametrize("name,eps", [("cartpole", 1e-3), ("quadruped", 1e-3)])
+def test_model_derivatives(ctx, name, eps):
+    m, e, o = ctx[name]
+    H = 8
+    state, xs, us, ts, res = _nominal(m, o, H)
+    A, B, C, D = e.model_derivatives(xs, us, ts, mocap_of(m), eps)
+    Ao, Bo, Co, Do = o.model_derivatives(xs, us, ts, mocap_of(m), tol=eps)
+    # structure: last step has only C
+    assert np.abs(A[-1]).max() == 0 and np.abs(B[-1]).max() == 0 and np.abs(D[-1]).max() == 0
+    for G, R, nm in ((A, Ao, "A"), (B, Bo, "B"), (C, Co, "C"), (D, Do, "D")):
+        err = np.abs(G - R)
+        scale = np.abs(R).max() + 1.0
+        print(name, nm, "max abs err %.2e (scale %.2e), median %.2e" % (err.max(), scale, np.median(err)))
+        assert np.median(err) < 2e-4 * scale
+        if name == "quadruped":
+            # a perturbation can open/close a contact in one arithmetic and not the other: a handful of entries of the
+            # stiff contact block differ at O(1); everything else agrees to round-off / eps
+            assert np.quantile(err, 0.99) < 5e-3 * scale and err.max() < 0.1 * scale
+        else:
+            assert err.max() < 2e-3 * scale
+
+
+@pytest.mark.parametrize("name", ["cartpole", "quadruped", "particle"])
+def test_cost_derivatives(ctx, name):
+    m, e, o = ctx[name]
+    H = 8
+    state, xs, us, ts, res = _nominal(m, o, H)
+    Ao, Bo, Co, Do = o.model_derivatives(xs, us, ts, mocap_of(m), tol=1e-6)
+    g = e.cost_derivatives(res, Co, Do)
+    r = o.cost_derivatives(res, Co, Do)
+    for G, R in zip(g, r):
+        np.testing.assert_allclose(G, R, rtol=2e-4, atol=2e-5 * (np.abs(R).max() + 1e-6))
+
+
+def test_backward_pass_vs_oracle(ctx, oracle_lib):
+    m, e, o = ctx["quadruped"]
+    H = 16
+    state, xs, us, ts, res = _nominal(m, o, H)
+    A, B, C, D = o.model_derivatives(xs, us, ts, mocap_of(m), tol=1e-6)
+    cx, cu, cxx, cuu, cxu = o.cost_derivatives(res, C, D)
+    cr = np.asarray(m.actuator_ctrlrange).reshape(-1, 2)
+    for reg_type, mu, limits in ((0, 1.0, 1), (1, 0.5, 1), (2, 0.1, 0), (0, 10.0, 0)):
+        g = e.backward_pass(A, B, cx, cu, cxx, cxu, cuu, us, mu=mu, reg_type=reg_type, limits=limits)
+        r = oracle_lib.backward_pass(A, B, cx, cu, cxx, cxu, cuu, us, cr, mu=mu, reg_type=reg_type, limits=limits)
+        assert g["status"] == r["status"] == 1
+        for k in ("du", "K", "Vx"):
+            scale = np.abs(r[k]).max() + 1e-6
+            assert np.abs(g[k] - r[k]).max() < 5e-3 * scale, (reg_type, k, np.abs(g[k] - r[k]).max(), scale)
+        np.testing.assert_allclose(g["dV"], r["dV"], rtol=5e-3, atol=1e-6)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+def test_feedback_rollouts(ctx, oracle_lib, mode):
+    """FeedbackRollouts (time-indexed, 3 interpolations) and ActionRollouts (step-indexed) vs the oracle."""
+    m, e, o = ctx["quadruped"]
+    H = 24
+    state, xs, us, ts, res = _nominal(m, o, H, seed=3)
+    rng = np.random.default_rng(5)
+    K = rng.normal(size=(H, m.nu, 2 * m.nv)) * 0.05
+    du = rng.normal(size=(H, m.nu)) * 0.05
+    steps = np.array([1.0, 0.3, 0.1, 0.0])
+    ret, fail, order = e.rollout_feedback(state, 0.0, mocap_of(m), us, xs, ts, K, du, steps, mode)
+    r = o.rollout_feedback(state, 0.0, mocap_of(m), us, xs, ts, K, du, steps, mode)
+    assert not fail.any() and not r["failure"].any()
+    np.testing.assert_allclose(ret, r["returns"], rtol=2e-3)
+    tr = e.fetch_all()
+    np.testing.assert_allclose(tr["actions"][:, :4], r["actions"][:, :4], atol=2e-4)
+    # step 0 with zero gains reproduces the nominal rollout itself
+    ret0, _, _ = e.rollout_feedback(state, 0.0, mocap_of(m), us, xs, ts, 0 * K, 0 * du, np.array([0.0]), 3)
+    nominal_return = o.rollout_feedback(state, 0.0, mocap_of(m), us, xs, ts, 0 * K, 0 * du, np.array([0.0]), 3)["returns"][0]
+    np.testing.assert_allclose(ret0[0], nominal_return, rtol=2e-3)
