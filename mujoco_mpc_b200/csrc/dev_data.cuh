@@ -23,8 +23,10 @@ namespace mjpc_dev {
   X(grad, M.nv) X(search, M.nv) X(Mv, M.nv) X(vtmp, M.nv) X(con_dist, M.maxcon) X(con_pos, 3 * M.maxcon)          \
   X(con_frame, 9 * M.maxcon) X(con_friction, 5 * M.maxcon) X(con_solref, 2 * M.maxcon)                            \
   X(con_solimp, 5 * M.maxcon) X(con_mu, M.maxcon) X(con_margin, M.maxcon) X(con_dim, M.maxcon)                    \
-  X(con_g1, M.maxcon) X(con_g2, M.maxcon) X(con_adr, M.maxcon) X(efc_J, M.maxefc * M.nv)                          \
-  X(efc_W, M.maxefc * M.nv) X(efc_pos, M.maxefc) X(efc_margin, M.maxefc) X(efc_diag, M.maxefc)                    \
+  X(con_g1, M.maxcon) X(con_g2, M.maxcon) X(con_adr, M.maxcon) X(efc_J, M.maxefc * 16)                            \
+  X(efc_W, 2 * M.maxcon * 16) X(con_nd, M.maxcon) X(con_dof, M.maxcon * 16) X(con_loc, M.maxcon * M.nv)           \
+  X(con_boff, M.maxcon + 1) X(con_xf, M.maxcon * 16) X(efc_blk, 1024) X(efc_dof, M.maxefc) X(efc_sgn, M.maxefc)     \
+  X(efc_Jd, (M.maxefc + 8) * M.nv) X(efc_Xd, 2 * M.maxcon * M.nv) X(efc_pos, M.maxefc) X(efc_margin, M.maxefc) X(efc_diag, M.maxefc)                    \
   X(efc_R, M.maxefc) X(efc_D, M.maxefc) X(efc_K, M.maxefc) X(efc_B, M.maxefc) X(efc_imp, M.maxefc)                \
   X(efc_aref, M.maxefc) X(efc_hw, M.maxefc) X(efc_force, M.maxefc) X(efc_jar, M.maxefc) X(efc_Jv, M.maxefc) X(efc_floss, M.maxefc)    \
   X(efc_type, M.maxefc) X(efc_id, M.maxefc) X(efc_state, M.maxefc) X(efc_item, M.maxefc) X(efc_hc, 36 * M.maxcon) X(con_mlo, M.maxcon) X(con_mhi, M.maxcon) \
@@ -61,21 +63,29 @@ constexpr float kMinImp = 0.0001f, kMaxImp = 0.9999f, kMinMu = 1e-5f;
 enum { CNSTR_FRICTION_DOF = 0, CNSTR_LIMIT_JOINT, CNSTR_CONTACT_FRICTIONLESS, CNSTR_CONTACT_ELLIPTIC };
 enum { STATE_SATISFIED = 0, STATE_QUADRATIC, STATE_LINEARNEG, STATE_LINEARPOS, STATE_CONE };
 
+// Everything a trajectory touches lives in the CTA's dynamic shared memory:
+//   [model floats nf][model ints ni][DevModel header][DevLayout][warp 0 state][warp 1 state] ...
+// All accessors derive their pointers from the g_smem symbol with 32-bit float indices, so the compiler emits
+// LDS/STS with shared-window addressing (pointers kept in a struct degrade to generic LD + 64-bit address
+// arithmetic: that was ~45 % of the executed instructions in the first profile, profiles/r01_v4_rollout_ncu.txt).
+extern __shared__ __align__(16) float g_smem[];
+
 struct Ctx {
-  const DevModel* M;
-  const DevLayout* L;
-  const float* mf;  // model floats (shared memory)
-  const int* mi;    // model ints (shared memory)
-  float* d;         // this warp's data block (shared memory)
+  int hdr;    // float index of the DevModel header copy
+  int lay;    // float index of the DevLayout copy
+  int ibase;  // float index where the model's int arrays start
+  int dbase;  // float index of this warp's state block
   int lane;
   int ncon, nefc, nitem, niter, nlim;
   int warn;
   float time;
 };
-#define MF(n) (c.mf + c.M->fo[F_##n])
-#define MI(n) (c.mi + c.M->io[I_##n])
-#define DF(n) (c.d + c.L->off[D_##n])
-#define DI(n) (reinterpret_cast<int*>(c.d + c.L->off[D_##n]))
+#define CM(c) (*reinterpret_cast<const DevModel*>(g_smem + (c).hdr))
+#define CL(c) (*reinterpret_cast<const DevLayout*>(g_smem + (c).lay))
+#define MF(n) (g_smem + CM(c).fo[F_##n])
+#define MI(n) (reinterpret_cast<const int*>(g_smem + c.ibase) + CM(c).io[I_##n])
+#define DF(n) (g_smem + c.dbase + CL(c).off[D_##n])
+#define DI(n) (reinterpret_cast<int*>(g_smem + c.dbase) + CL(c).off[D_##n])
 
 // ---------------------------------------------------------------------------------------- small math
 __device__ __forceinline__ float dot3(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }

@@ -40,9 +40,10 @@ namespace mjpc_dev {
 //   hpair_i/hpair_j      : structurally non-zero lower-triangle entries of the Newton Hessian M + J^T D J:
 //                          the M pattern plus (chain(b1) u chain(b2))^2 for every dynamic-dynamic geom pair
 //   floss_row            : constraint row of each dof's friction-loss constraint (-1 if none)
+//   chain_adr/num/dof    : dofs on the chain root -> body, in root-to-leaf order (compact contact Jacobians)
 #define MJPC_I_DERIVED(X)                                                                                        \
   X(level_adr) X(level_body) X(body_subtreeend) X(body_lastdof) X(body_dofmask_lo) X(body_dofmask_hi)            \
-  X(mpair_i) X(mpair_j) X(floss_dof) X(limit_jnt) X(hpair_i) X(hpair_j) X(floss_row)
+  X(mpair_i) X(mpair_j) X(floss_dof) X(limit_jnt) X(hpair_i) X(hpair_j) X(floss_row) X(chain_adr) X(chain_num) X(chain_dof)
 
 enum FloatArrayId {
 #define X(n) F_##n,
@@ -215,6 +216,23 @@ inline ModelPack pack_model(const void* data, size_t nbytes, int maxcon, int max
     for (size_t k = 0; k < fl.size(); k++) frow[fl[k]] = (int)k;
     M.nhpair = (int)hi_.size();
     put(I_hpair_i, hi_); put(I_hpair_j, hj_); put(I_floss_row, frow);
+    // dof chains per body, and the widest chain union any candidate pair can produce (compact Jacobian width)
+    std::vector<int> cadr(nb, 0), cnum(nb, 0), cdofs;
+    for (int bb = 0; bb < nb; bb++) {
+      std::vector<int> ch;
+      for (int d = lastdof[bb]; d >= 0; d = dofpar[d]) ch.push_back(d);
+      cadr[bb] = (int)cdofs.size(); cnum[bb] = (int)ch.size();
+      cdofs.insert(cdofs.end(), ch.rbegin(), ch.rend());
+    }
+    int widest = 0;
+    for (size_t k = 0; k < g1.size(); k++) {
+      const uint64_t mm = chain(gb[g1[k]]) | chain(gb[g2[k]]);
+      int cnt = 0;
+      for (int r = 0; r < nv; r++) cnt += (int)((mm >> r) & 1);
+      widest = std::max(widest, cnt);
+    }
+    if (widest > 16) throw std::runtime_error("a contact pair couples more than 16 dofs (compact Jacobian width)");
+    put(I_chain_adr, cadr); put(I_chain_num, cnum); put(I_chain_dof, cdofs);
   }
   while (P.i.size() % 4) P.i.push_back(0);
   while (P.f.size() % 4) P.f.push_back(0.f);

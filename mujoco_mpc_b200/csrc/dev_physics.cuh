@@ -9,7 +9,7 @@ namespace mjpc_dev {
 
 // ------------------------------------------------------------------------------------------ position stage
 __device__ __noinline__ void k_kinematics(Ctx& c) {
-  const DevModel& M = *c.M;
+  const DevModel& M = CM(c);
   const int lane = c.lane;
   float *xpos = DF(xpos), *xquat = DF(xquat), *xmat = DF(xmat), *xipos = DF(xipos), *ximat = DF(ximat);
   float *xanchor = DF(xanchor), *xaxis = DF(xaxis);
@@ -112,7 +112,7 @@ __device__ __noinline__ void k_kinematics(Ctx& c) {
 }
 
 __device__ __noinline__ void k_com_pos(Ctx& c) {
-  const DevModel& M = *c.M;
+  const DevModel& M = CM(c);
   const int lane = c.lane;
   const int *subend = MI(body_subtreeend), *rootid = MI(body_rootid);
   const float *mass = MF(body_mass), *submass = MF(body_subtreemass), *inertia = MF(body_inertia);
@@ -184,7 +184,7 @@ __device__ __noinline__ void k_com_pos(Ctx& c) {
 
 // composite rigid body inertia -> dense joint-space inertia qM, then its Cholesky factor qLD
 __device__ __noinline__ void k_crb(Ctx& c) {
-  const DevModel& M = *c.M;
+  const DevModel& M = CM(c);
   const int lane = c.lane, nv = M.nv;
   const int* subend = MI(body_subtreeend);
   float *cinert = DF(cinert), *crb = DF(crb), *cdof = DF(cdof), *dofbuf = DF(dofbuf), *qM = DF(qM), *qLD = DF(qLD);
@@ -345,7 +345,7 @@ __device__ __forceinline__ int collide_sphere_box(RawContact* out, const float* 
 }
 
 __device__ __noinline__ void k_collision(Ctx& c) {
-  const DevModel& M = *c.M;
+  const DevModel& M = CM(c);
   const int lane = c.lane;
   c.ncon = 0;
   if (M.disable_contact) return;
@@ -458,11 +458,31 @@ __device__ __forceinline__ float get_impedance(const float* solimp, float pos, f
   return dmin + y * (dmax - dmin);
 }
 
+constexpr int kL = 16;  // width of a compact constraint-Jacobian row (dofs of the chains a contact couples)
+// Small data-dependent trip counts (contact dimension <= 6, chain width <= kL) are written as fixed-bound,
+// fully unrolled, predicated loops: straight-line code with no taken branches, which is what a single
+// resident warp per scheduler needs (every loop back-edge is an exposed fetch bubble).
+#define FOR_DIM(j, start, dim) _Pragma("unroll") for (int j = (start); j < 6; j++) if (j < (dim))
+#define FOR_KL(l, nd) _Pragma("unroll") for (int l = 0; l < kL; l++) if (l < (nd))
+
+// J row (compact) dot a dof-indexed vector: friction-loss / limit rows touch one dof, contact rows their chain
+__device__ __forceinline__ float row_dot(Ctx& c, int row, int nsimple, const float* v) {
+  if (row < nsimple) return DF(efc_sgn)[row] * v[DI(efc_dof)[row]];
+  const int ci = DI(efc_id)[row];
+  const int nd = DI(con_nd)[ci];
+  const int* dofs = DI(con_dof) + ci * kL;
+  const float* Jr = DF(efc_J) + row * kL;
+  float a = 0.f;
+  FOR_KL(l, nd) a += Jr[l] * v[dofs[l]];
+  return a;
+}
+
 __device__ __noinline__ void k_make_constraint(Ctx& c) {
-  const DevModel& M = *c.M;
+  const DevModel& M = CM(c);
   const int lane = c.lane, nv = M.nv;
-  float *J = DF(efc_J), *epos = DF(efc_pos), *emargin = DF(efc_margin), *ediag = DF(efc_diag), *efloss = DF(efc_floss);
-  int *etype = DI(efc_type), *eid = DI(efc_id), *eitem = DI(efc_item);
+  float *J = DF(efc_J), *epos = DF(efc_pos), *emargin = DF(efc_margin), *ediag = DF(efc_diag), *efloss = DF(efc_floss),
+        *esgn = DF(efc_sgn);
+  int *etype = DI(efc_type), *eid = DI(efc_id), *eitem = DI(efc_item), *edof = DI(efc_dof);
   const float *dinvw = MF(dof_invweight0), *qpos = DF(qpos);
   int ne = 0, nitem = 0;
   // --- dof friction loss rows (static list)
@@ -470,11 +490,9 @@ __device__ __noinline__ void k_make_constraint(Ctx& c) {
     const int* fl = MI(floss_dof);
     const float* flv = MF(dof_frictionloss);
     const int nf = M.nfloss;
-    for (int k = lane; k < nf * nv; k += 32) J[k] = 0;
-    __syncwarp();
     for (int k = lane; k < nf; k += 32) {
       const int dof = fl[k];
-      J[k * nv + dof] = 1;
+      edof[k] = dof; esgn[k] = 1.f;
       epos[k] = 0; emargin[k] = 0; ediag[k] = dinvw[dof]; etype[k] = CNSTR_FRICTION_DOF; eid[k] = dof;
       efloss[k] = flv[dof]; eitem[k] = k;
     }
@@ -501,8 +519,7 @@ __device__ __noinline__ void k_make_constraint(Ctx& c) {
       for (int q = 0; q < cnt; q++) {
         const int r = ne + incl - cnt + q;
         if (r >= M.maxefc) break;
-        for (int i = 0; i < nv; i++) J[r * nv + i] = 0;
-        J[r * nv + jdadr[j]] = sgn[q];
+        edof[r] = jdadr[j]; esgn[r] = sgn[q];
         epos[r] = dist[q]; emargin[r] = jmargin[j]; ediag[r] = dinvw[jdadr[j]]; etype[r] = CNSTR_LIMIT_JOINT;
         eid[r] = j; efloss[r] = 0; eitem[nitem + incl - cnt + q] = r;
       }
@@ -513,62 +530,88 @@ __device__ __noinline__ void k_make_constraint(Ctx& c) {
   }
   c.nlim = ne - M.nfloss;
   // --- contacts: row addresses are assigned sequentially (a contact that does not fit is dropped, later
-  //     smaller ones may still fit: same rule as the oracle)
-  int *cadr = DI(con_adr), *cdim = DI(con_dim);
+  //     smaller ones may still fit: same rule as the oracle); dof lists = union of the two bodies' chains
+  int *cadr = DI(con_adr), *cdim = DI(con_dim), *cnd = DI(con_nd), *cdofl = DI(con_dof), *cloc = DI(con_loc),
+      *cboff = DI(con_boff);
+  const int *g1a = DI(con_g1), *g2a = DI(con_g2), *gbody = MI(geom_bodyid);
+  for (int w = lane; w < c.ncon * nv; w += 32) cloc[w] = -1;
+  __syncwarp();
+  {
+    const int *chadr = MI(chain_adr), *chnum = MI(chain_num), *chdof = MI(chain_dof);
+    for (int ci = lane; ci < c.ncon; ci += 32) {
+      int nd = 0;
+      for (int s2 = 0; s2 < 2; s2++) {
+        const int bb = gbody[s2 ? g2a[ci] : g1a[ci]];
+        for (int q = 0; q < chnum[bb]; q++) {
+          const int dof = chdof[chadr[bb] + q];
+          if (cloc[ci * nv + dof] < 0 && nd < kL) { cloc[ci * nv + dof] = nd; cdofl[ci * kL + nd] = dof; nd++; }
+        }
+      }
+      cnd[ci] = nd;
+    }
+  }
+  __syncwarp();
   if (lane == 0) {
-    int r = ne, it = nitem;
+    int r = ne, it = nitem, bo = 0;
     for (int ci = 0; ci < c.ncon; ci++) {
       const int dim = cdim[ci];
+      cboff[ci] = bo;
       if (r + dim > M.maxefc) { cadr[ci] = -1; continue; }
       cadr[ci] = r;
       eitem[it++] = r;  // one work item per contact
       r += dim;
+      bo += cnd[ci] * (cnd[ci] + 1) / 2;
     }
+    cboff[c.ncon] = bo;
     ne = r; nitem = it;
   }
   ne = __shfl_sync(kFull, ne, 0);
   nitem = __shfl_sync(kFull, nitem, 0);
   __syncwarp();
   {
-    const int *g1a = DI(con_g1), *g2a = DI(con_g2), *gbody = MI(geom_bodyid), *rootid = MI(body_rootid),
-              *mlo = MI(body_dofmask_lo), *mhi = MI(body_dofmask_hi);
+    const int *rootid = MI(body_rootid), *mlo = MI(body_dofmask_lo), *mhi = MI(body_dofmask_hi);
     const float *cpos = DF(con_pos), *cframe = DF(con_frame), *scom = DF(subtree_com), *cdof = DF(cdof),
                 *binvw = MF(body_invweight0);
-    // Jacobian entries: one (contact, dof) pair per lane
-    const int nwork = c.ncon * nv;
+    // dense copies of the contact rows feed the register-blocked Hessian assembly (zeros off the chains)
+    float* Jd = DF(efc_Jd);
+    for (int w = lane + (M.nfloss + c.nlim) * nv; w < ne * nv; w += 32) Jd[w] = 0.f;
+    __syncwarp();
+    // compact Jacobian entries: one (contact, local dof) pair per lane
+    const int nwork = c.ncon * kL;
     for (int w = lane; w < nwork; w += 32) {
-      const int ci = w / nv, i = w - ci * nv;
+      const int ci = w / kL, l = w - ci * kL;
       const int adr = cadr[ci];
-      if (adr < 0) continue;
+      if (adr < 0 || l >= cnd[ci]) continue;
+      const int i = cdofl[ci * kL + l];
       const int dim = cdim[ci];
       const int b1 = gbody[g1a[ci]], b2 = gbody[g2a[ci]];
       float jp[3] = {0, 0, 0}, jr[3] = {0, 0, 0};
       const float* cd = cdof + 6 * i;
-      for (int s = 0; s < 2; s++) {
-        const int b = s ? b2 : b1;
-        if (b <= 0) continue;
-        const unsigned lo = (unsigned)mlo[b], hi = (unsigned)mhi[b];
+      for (int s2 = 0; s2 < 2; s2++) {
+        const int bb = s2 ? b2 : b1;
+        if (bb <= 0) continue;
+        const unsigned lo = (unsigned)mlo[bb], hi = (unsigned)mhi[bb];
         const bool on = i < 32 ? ((lo >> i) & 1u) : ((hi >> (i - 32)) & 1u);
         if (!on) continue;
         float off[3], t[3];
-        for (int q = 0; q < 3; q++) off[q] = cpos[3 * ci + q] - scom[3 * rootid[b] + q];
+        for (int q = 0; q < 3; q++) off[q] = cpos[3 * ci + q] - scom[3 * rootid[bb] + q];
         cross3(t, cd, off);
-        const float sg = s ? 1.f : -1.f;
+        const float sg = s2 ? 1.f : -1.f;
         for (int q = 0; q < 3; q++) { jp[q] += sg * (cd[3 + q] + t[q]); jr[q] += sg * cd[q]; }
       }
       const float* fr = cframe + 9 * ci;
       for (int k = 0; k < dim; k++) {
         const float* ax = fr + 3 * (k % 3);
-        J[(adr + k) * nv + i] = k < 3 ? dot3(ax, jp) : dot3(ax, jr);
+        const float v = k < 3 ? dot3(ax, jp) : dot3(ax, jr);
+        J[(adr + k) * kL + l] = v;
+        Jd[(adr + k) * nv + i] = v;
       }
     }
     // per-row scalars: one contact per lane
     for (int ci = lane; ci < c.ncon; ci += 32) {
       const int adr = cadr[ci];
-      const int b1 = gbody[g1a[ci]], b2 = gbody[g2a[ci]];
-      DI(con_mlo)[ci] = mlo[b1] | mlo[b2];   // dofs this contact's Jacobian rows can touch
-      DI(con_mhi)[ci] = mhi[b1] | mhi[b2];
       if (adr < 0) continue;
+      const int b1 = gbody[g1a[ci]], b2 = gbody[g2a[ci]];
       const int dim = cdim[ci];
       const float tran = binvw[2 * b1] + binvw[2 * b2], rot = binvw[2 * b1 + 1] + binvw[2 * b2 + 1];
       for (int k = 0; k < dim; k++) {
@@ -633,7 +676,7 @@ __device__ __noinline__ void k_make_constraint(Ctx& c) {
 
 // ------------------------------------------------------------------------------------------ velocity stage
 __device__ __noinline__ void k_com_vel(Ctx& c) {
-  const DevModel& M = *c.M;
+  const DevModel& M = CM(c);
   const int lane = c.lane;
   float *cvel = DF(cvel), *cdof = DF(cdof), *cdof_dot = DF(cdof_dot), *qvel = DF(qvel);
   if (lane < 6) cvel[lane] = 0;
@@ -689,7 +732,7 @@ __device__ __noinline__ void k_com_vel(Ctx& c) {
 
 // passive forces, RNE bias, actuation, qfrc_smooth, qacc_smooth
 __device__ __noinline__ void k_smooth_forces(Ctx& c) {
-  const DevModel& M = *c.M;
+  const DevModel& M = CM(c);
   const int lane = c.lane, nv = M.nv;
   float *qvel = DF(qvel), *qpos = DF(qpos), *passive = DF(qfrc_passive);
   const float* damping = MF(dof_damping);
@@ -778,13 +821,13 @@ __device__ __noinline__ void k_smooth_forces(Ctx& c) {
 
 // constraint reference acceleration aref = -B*vel - K*imp*(pos - margin)
 __device__ __noinline__ void k_reference(Ctx& c) {
-  const int lane = c.lane, nv = c.M->nv;
-  const float *J = DF(efc_J), *qvel = DF(qvel), *K = DF(efc_K), *B = DF(efc_B), *imp = DF(efc_imp),
-              *pos = DF(efc_pos), *margin = DF(efc_margin);
+  const int lane = c.lane;
+  const float *qvel = DF(qvel), *K = DF(efc_K), *B = DF(efc_B), *imp = DF(efc_imp), *pos = DF(efc_pos),
+              *margin = DF(efc_margin);
   float* aref = DF(efc_aref);
+  const int nsimple = CM(c).nfloss + c.nlim;
   for (int i = lane; i < c.nefc; i += 32) {
-    float v = 0;
-    for (int j = 0; j < nv; j++) v += J[i * nv + j] * qvel[j];
+    const float v = row_dot(c, i, nsimple, qvel);
     aref[i] = -B[i] * v - K[i] * imp[i] * (pos[i] - margin[i]);
   }
   __syncwarp();
@@ -797,7 +840,7 @@ __device__ __noinline__ void k_reference(Ctx& c) {
 //   Dm*S*(v v^T + c1*P + c2*ut ut^T)*S,  v = (1, -mu*u/T), ut = (0, u), c1 = mu^2 - mu*N/T, c2 = mu*N/T^3 - mu^2/T^2
 //   X_v = sum_a S_a v_a J_a (weight Dm),  X_u = sum_{a>=1} S_a u_a J_a (weight Dm*c2),  hw[a>=1] = Dm*c1*S_a^2
 __device__ __noinline__ float k_update_constraint(Ctx& c, bool hess) {
-  const DevModel& M = *c.M;
+  const DevModel& M = CM(c);
   const int lane = c.lane, nv = M.nv;
   const float *jar = DF(efc_jar), *D = DF(efc_D), *R = DF(efc_R), *floss = DF(efc_floss), *J = DF(efc_J);
   float *force = DF(efc_force), *X = DF(efc_W), *hw = DF(efc_hw), *xw = DF(efc_hc);
@@ -826,12 +869,12 @@ __device__ __noinline__ float k_update_constraint(Ctx& c, bool hess) {
       float u[6];
       u[0] = jar[i] * mu;
       float tt = 0;
-      for (int j = 1; j < dim; j++) { u[j] = jar[i + j] * fr[j - 1]; tt += u[j] * u[j]; }
+      FOR_DIM(j, 1, dim) { u[j] = jar[i + j] * fr[j - 1]; tt += u[j] * u[j]; }
       const float N = u[0], Tn = sqrtf(tt);
       if (N >= mu * Tn || (Tn <= 0 && N >= 0)) {
-        for (int j = 0; j < dim; j++) { force[i + j] = 0; state[i + j] = STATE_SATISFIED; hw[i + j] = 0.f; }
+        FOR_DIM(j, 0, dim) { force[i + j] = 0; state[i + j] = STATE_SATISFIED; hw[i + j] = 0.f; }
       } else if (mu * N + Tn <= 0 || (Tn <= 0 && N < 0)) {
-        for (int j = 0; j < dim; j++) {
+        FOR_DIM(j, 0, dim) {
           cost += 0.5f * D[i + j] * jar[i + j] * jar[i + j];
           force[i + j] = -D[i + j] * jar[i + j];
           state[i + j] = STATE_QUADRATIC;
@@ -844,16 +887,16 @@ __device__ __noinline__ float k_update_constraint(Ctx& c, bool hess) {
         const float f0 = -Dm * NmT * mu;
         const float iT = 1.0f / Tn;
         force[i] = f0;
-        for (int j = 1; j < dim; j++) force[i + j] = -f0 * iT * u[j] * fr[j - 1];
-        for (int j = 0; j < dim; j++) state[i + j] = STATE_CONE;
+        FOR_DIM(j, 1, dim) force[i + j] = -f0 * iT * u[j] * fr[j - 1];
+        FOR_DIM(j, 0, dim) state[i + j] = STATE_CONE;
         if (hess) {
           const float c1 = mu * mu - mu * N * iT;
           hw[i] = 0.f;
-          for (int j = 1; j < dim; j++) hw[i + j] = Dm * c1 * fr[j - 1] * fr[j - 1];
+          FOR_DIM(j, 1, dim) hw[i + j] = Dm * c1 * fr[j - 1] * fr[j - 1];
           // coefficients of the two effective rows, stored per contact: [S_a v_a (6), S_a u_a (6), wv, wu]
           float* q = xw + 36 * ci;
           q[0] = mu; q[6] = 0.f;
-          for (int j = 1; j < dim; j++) { q[j] = -fr[j - 1] * mu * u[j] * iT; q[6 + j] = fr[j - 1] * u[j]; }
+          FOR_DIM(j, 1, dim) { q[j] = -fr[j - 1] * mu * u[j] * iT; q[6 + j] = fr[j - 1] * u[j]; }
           q[12] = Dm;
           q[13] = Dm * (mu * N * iT * iT * iT - mu * mu * iT * iT);
         }
@@ -863,35 +906,105 @@ __device__ __noinline__ float k_update_constraint(Ctx& c, bool hess) {
   cost = warp_sum(cost);
   __syncwarp();
   if (hess) {
-    // effective rows of cone contacts: one (contact, dof) pair per lane
-    const int* cadr = DI(con_adr);
-    const int total = c.ncon * nv;
+    // effective rows of cone contacts (compact): one (contact, local dof) pair per lane
+    const int *cadr = DI(con_adr), *cnd = DI(con_nd);
+    const int total = c.ncon * kL;
     for (int w = lane; w < total; w += 32) {
-      const int ci = w / nv, sidx = w - ci * nv;
+      const int ci = w / kL, l = w - ci * kL;
       const int a0 = cadr[ci];
-      if (a0 < 0 || state[a0] != STATE_CONE) continue;
+      if (a0 < 0 || l >= cnd[ci] || state[a0] != STATE_CONE) continue;
       const int dim = cdim[ci];
       const float* q = xw + 36 * ci;
       float xv = 0.f, xu = 0.f;
-      for (int a = 0; a < dim; a++) {
-        const float jv = J[(a0 + a) * nv + sidx];
+      FOR_DIM(a, 0, dim) {
+        const float jv = J[(a0 + a) * kL + l];
         xv += q[a] * jv;
         xu += q[6 + a] * jv;
       }
-      X[(2 * ci) * nv + sidx] = xv;
-      X[(2 * ci + 1) * nv + sidx] = xu;
+      X[(2 * ci) * kL + l] = xv;
+      X[(2 * ci + 1) * kL + l] = xu;
+    }
+    if (nv == 18) {   // dense copies for the register-blocked assembly
+      float* Xd = DF(efc_Xd);
+      const int* cloc = DI(con_loc);
+      __syncwarp();
+      for (int w = lane; w < c.ncon * nv; w += 32) {
+        const int ci = w / nv, i = w - ci * nv;
+        const int a0 = cadr[ci];
+        if (a0 < 0 || state[a0] != STATE_CONE) continue;
+        const int l = cloc[w];
+        Xd[(2 * ci) * nv + i] = l >= 0 ? X[(2 * ci) * kL + l] : 0.f;
+        Xd[(2 * ci + 1) * nv + i] = l >= 0 ? X[(2 * ci + 1) * kL + l] : 0.f;
+      }
     }
     __syncwarp();
   }
   return cost;
 }
 
-// Ma = M*qacc, jar = J*qacc - aref, gauss; returns total cost (uniform). If hess: qH = M + J^T diag(hw) J + cone rows.
+// Register-blocked Newton Hessian for compile-time NV: lane owns lower-triangle entries e = lane + 32 q and keeps
+// them in registers; every active constraint row (weight hw != 0) and every cone effective row is one rank-1
+// update read as a dense NV-wide row from shared memory (broadcast loads, no bank conflicts, no branches inside).
+template <int NV>
+__device__ __forceinline__ void hessian_dense_reg(Ctx& c) {
+  const DevModel& M = CM(c);
+  const int lane = c.lane;
+  constexpr int NE = NV * (NV + 1) / 2, NQ = (NE + 31) / 32;
+  const float *qM = DF(qM), *hw = DF(efc_hw), *Jd = DF(efc_Jd), *Xd = DF(efc_Xd), *xw = DF(efc_hc);
+  float* H = DF(qH);
+  const int *frow = MI(floss_row), *edof = DI(efc_dof), *state = DI(efc_state), *cadr = DI(con_adr);
+  int er[NQ], es[NQ];
+  float acc[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; q++) {
+    int e = lane + 32 * q;
+    if (e >= NE) e = NE - 1;
+    int r = (int)((sqrtf(8.f * e + 1.f) - 1.f) * 0.5f);
+    while ((r + 1) * (r + 2) / 2 <= e) r++;
+    while (r * (r + 1) / 2 > e) r--;
+    er[q] = r; es[q] = e - r * (r + 1) / 2;
+    float a = qM[er[q] * NV + es[q]];
+    if (er[q] == es[q]) {
+      const int fr = frow[r];
+      if (fr >= 0) a += hw[fr];
+      for (int k = M.nfloss; k < M.nfloss + c.nlim; k++)
+        if (edof[k] == r) a += hw[k];
+    }
+    acc[q] = a;
+  }
+  const int r0 = M.nfloss + c.nlim, ne = c.nefc;
+  for (int row = r0; row < ne; row++) {
+    const float w = hw[row];
+    if (w == 0.f) continue;   // warp-uniform
+    const float* j = Jd + row * NV;
+#pragma unroll
+    for (int q = 0; q < NQ; q++) acc[q] += w * j[er[q]] * j[es[q]];
+  }
+  for (int ci = 0; ci < c.ncon; ci++) {
+    const int a0 = cadr[ci];
+    if (a0 < 0 || state[a0] != STATE_CONE) continue;   // warp-uniform
+    const float wv = xw[36 * ci + 12], wu = xw[36 * ci + 13];
+    const float* xv = Xd + (2 * ci) * NV;
+    const float* xu = xv + NV;
+#pragma unroll
+    for (int q = 0; q < NQ; q++) acc[q] += wv * xv[er[q]] * xv[es[q]] + wu * xu[er[q]] * xu[es[q]];
+  }
+#pragma unroll
+  for (int q = 0; q < NQ; q++)
+    if (lane + 32 * q < NE) { H[er[q] * NV + es[q]] = acc[q]; H[es[q] * NV + er[q]] = acc[q]; }
+  __syncwarp();
+}
+
+// Ma = M*qacc, jar = J*qacc - aref, gauss; returns total cost (uniform). If hess: qH = M + J^T diag(hw) J + cone rows,
+// assembled in two balanced stages: (1) every contact's small symmetric block (its chain dofs) into scratch,
+// one (contact, block entry) per lane; (2) every structurally non-zero Hessian entry gathers the blocks that
+// contain it (deterministic order, no atomics).
 __device__ __noinline__ float k_total_cost(Ctx& c, const float* qacc, bool hess, float* gauss_out) {
-  const DevModel& M = *c.M;
+  const DevModel& M = CM(c);
   const int lane = c.lane, nv = M.nv;
   const float *qM = DF(qM), *J = DF(efc_J), *aref = DF(efc_aref), *smooth = DF(qfrc_smooth), *qas = DF(qacc_smooth);
   float *Ma = DF(Ma), *jar = DF(efc_jar);
+  const int nsimple = M.nfloss + c.nlim;
   float g = 0;
   for (int i = lane; i < nv; i += 32) {
     float a = 0;
@@ -899,22 +1012,19 @@ __device__ __noinline__ float k_total_cost(Ctx& c, const float* qacc, bool hess,
     Ma[i] = a;
     g += (a - smooth[i]) * (qacc[i] - qas[i]);
   }
-  for (int i = lane; i < c.nefc; i += 32) {
-    float a = 0;
-    for (int j = 0; j < nv; j++) a += J[i * nv + j] * qacc[j];
-    jar[i] = a - aref[i];
-  }
+  for (int i = lane; i < c.nefc; i += 32) jar[i] = row_dot(c, i, nsimple, qacc) - aref[i];
   g = 0.5f * warp_sum(g);
   __syncwarp();
   const float cc = k_update_constraint(c, hess);
-  if (hess) {
-    // Newton Hessian gathered entry by entry over the structurally non-zero pattern (hpair lists);
-    // friction-loss / limit rows only touch the diagonal.
+  if (hess && nv == 18) {
+    hessian_dense_reg<18>(c);
+  } else if (hess) {
     const float *X = DF(efc_W), *hw = DF(efc_hw), *xw = DF(efc_hc);
-    float* H = DF(qH);
-    const int *hi = MI(hpair_i), *hj = MI(hpair_j), *frow = MI(floss_row), *state = DI(efc_state), *eid = DI(efc_id),
-              *cadr = DI(con_adr), *cdim = DI(con_dim), *cmlo = DI(con_mlo), *cmhi = DI(con_mhi), *jdadr = MI(jnt_dofadr);
+    float *H = DF(qH), *blk = DF(efc_blk);
+    const int *hi = MI(hpair_i), *hj = MI(hpair_j), *frow = MI(floss_row), *state = DI(efc_state), *edof = DI(efc_dof),
+              *cadr = DI(con_adr), *cdim = DI(con_dim), *cnd = DI(con_nd), *cloc = DI(con_loc), *cboff = DI(con_boff);
     const int ncon = c.ncon, nf = M.nfloss, nl = c.nlim;
+    // M + diagonal rows
     for (int w = lane; w < nv * nv; w += 32) H[w] = 0.f;   // entries outside the pattern (the factor fills them)
     __syncwarp();
     for (int e = lane; e < M.nhpair; e += 32) {
@@ -924,27 +1034,62 @@ __device__ __noinline__ float k_total_cost(Ctx& c, const float* qacc, bool hess,
         const int fr = frow[r];
         if (fr >= 0) a += hw[fr];
         for (int q = nf; q < nf + nl; q++)
-          if (jdadr[eid[q]] == r) a += hw[q];
-      }
-      const unsigned rbit = 1u << (r & 31), sbit = 1u << (s2 & 31);
-      for (int ci = 0; ci < ncon; ci++) {
-        const int a0 = cadr[ci];
-        if (a0 < 0) continue;
-        const unsigned mr = r < 32 ? (unsigned)cmlo[ci] : (unsigned)cmhi[ci];
-        const unsigned ms = s2 < 32 ? (unsigned)cmlo[ci] : (unsigned)cmhi[ci];
-        if (!(mr & rbit) || !(ms & sbit)) continue;
-        const int dim = cdim[ci];
-        const float* Jr = J + a0 * nv + r;
-        const float* Js = J + a0 * nv + s2;
-        for (int k = 0; k < dim; k++) a += hw[a0 + k] * Jr[k * nv] * Js[k * nv];
-        if (state[a0] == STATE_CONE) {
-          const float* q = xw + 36 * ci;
-          a += q[12] * X[(2 * ci) * nv + r] * X[(2 * ci) * nv + s2] + q[13] * X[(2 * ci + 1) * nv + r] * X[(2 * ci + 1) * nv + s2];
-        }
+          if (edof[q] == r) a += hw[q];
       }
       H[r * nv + s2] = a;
-      H[s2 * nv + r] = a;
     }
+    __syncwarp();
+    int c0 = 0;
+    while (c0 < ncon) {
+      // chunk of contacts whose blocks fit the scratch buffer
+      int c1 = c0 + 1;
+      while (c1 < ncon && cboff[c1 + 1] - cboff[c0] <= 1024) c1++;
+      const int base = cboff[c0], nblk = cboff[c1] - base;
+      // stage 1
+      int ci = c0;
+      for (int t0 = 0; t0 < nblk; t0 += 32) {
+        const int t = t0 + lane;
+        while (ci + 1 < c1 && cboff[ci + 1] - base <= t0) ci++;   // warp-uniform lower bound
+        int cj = ci;
+        while (cj + 1 < c1 && cboff[cj + 1] - base <= t) cj++;
+        if (t < nblk) {
+          const int a0 = cadr[cj];
+          float acc = 0.f;
+          if (a0 >= 0) {
+            const int tt = t - (cboff[cj] - base);
+            int la = (int)((sqrtf(8.f * tt + 1.f) - 1.f) * 0.5f);
+            while ((la + 1) * (la + 2) / 2 <= tt) la++;
+            while (la * (la + 1) / 2 > tt) la--;
+            const int lb = tt - la * (la + 1) / 2;
+            const int dim = cdim[cj];
+            const float* Ja = J + a0 * kL + la;
+            const float* Jb = J + a0 * kL + lb;
+            for (int k = 0; k < dim; k++) acc += hw[a0 + k] * Ja[k * kL] * Jb[k * kL];
+            if (state[a0] == STATE_CONE) {
+              const float* q = xw + 36 * cj;
+              acc += q[12] * X[(2 * cj) * kL + la] * X[(2 * cj) * kL + lb] + q[13] * X[(2 * cj + 1) * kL + la] * X[(2 * cj + 1) * kL + lb];
+            }
+          }
+          blk[t] = acc;
+        }
+      }
+      __syncwarp();
+      // stage 2
+      for (int e = lane; e < M.nhpair; e += 32) {
+        const int r = hi[e], s2 = hj[e];
+        float a = H[r * nv + s2];
+        for (int cq = c0; cq < c1; cq++) {
+          const int lr = cloc[cq * nv + r], ls = cloc[cq * nv + s2];
+          if ((lr | ls) < 0 || cadr[cq] < 0) continue;
+          const int mx = max(lr, ls), mn = min(lr, ls);
+          a += blk[cboff[cq] - base + mx * (mx + 1) / 2 + mn];
+        }
+        H[r * nv + s2] = a;
+      }
+      __syncwarp();
+      c0 = c1;
+    }
+    for (int e = lane; e < M.nhpair; e += 32) { const int r = hi[e], s2 = hj[e]; H[s2 * nv + r] = H[r * nv + s2]; }
     __syncwarp();
   }
   *gauss_out = g;
@@ -976,7 +1121,7 @@ __device__ __noinline__ LsPoint k_ls_eval(Ctx& c, float g0, float g1, float g2, 
       const float* fr = DF(con_friction) + 5 * ci;
       const float U0 = jar[i] * mu, V0 = Jv[i] * mu;
       float UU = 0, UV = 0, VV = 0;
-      for (int j = 1; j < dim; j++) {
+      FOR_DIM(j, 1, dim) {
         const float uj = jar[i + j] * fr[j - 1], vj = Jv[i + j] * fr[j - 1];
         UU += uj * uj; UV += uj * vj; VV += vj * vj;
       }
@@ -985,7 +1130,7 @@ __device__ __noinline__ LsPoint k_ls_eval(Ctx& c, float g0, float g1, float g2, 
       const float Tn = Tsqr <= 0 ? 0.f : sqrtf(Tsqr);
       if (N >= mu * Tn || (Tn <= 0 && N >= 0)) {
       } else if (mu * N + Tn <= 0 || (Tn <= 0 && N < 0)) {
-        for (int j = 0; j < dim; j++) {
+        FOR_DIM(j, 0, dim) {
           const float Dj = D[i + j], vj = Jv[i + j], xj = jar[i + j] + alpha * vj;
           cost += 0.5f * Dj * xj * xj; d1 += Dj * xj * vj; d2 += Dj * vj * vj;
         }
@@ -1008,13 +1153,92 @@ __device__ __noinline__ LsPoint k_ls_eval(Ctx& c, float g0, float g1, float g2, 
   return p;
 }
 
+// Per-lane cache of one work item's line-search data: everything that does not depend on alpha is folded once
+// per line search so an evaluation is a handful of register operations plus three warp reductions.
+struct LsItem {
+  int kind;                 // 0 none, 1 friction-loss, 2 inequality (limit / frictionless), 3 elliptic contact
+  float D, x0, jv, f, rf;   // kinds 1, 2
+  float mu, U0, V0, UU, UV, VV, Q0, Q1, Q2, Dm;  // kind 3
+};
+
+__device__ __forceinline__ LsItem ls_load_item(Ctx& c) {
+  LsItem it;
+  it.kind = 0;
+  it.D = it.x0 = it.jv = it.f = it.rf = it.mu = it.U0 = it.V0 = it.UU = it.UV = it.VV = it.Q0 = it.Q1 = it.Q2 = it.Dm = 0.f;
+  if (c.lane >= c.nitem) return it;
+  const float *jar = DF(efc_jar), *Jv = DF(efc_Jv), *D = DF(efc_D), *R = DF(efc_R), *floss = DF(efc_floss);
+  const int i = DI(efc_item)[c.lane];
+  const int ty = DI(efc_type)[i];
+  it.D = D[i]; it.x0 = jar[i]; it.jv = Jv[i];
+  if (ty == CNSTR_FRICTION_DOF) { it.kind = 1; it.f = floss[i]; it.rf = R[i] * it.f; }
+  else if (ty == CNSTR_LIMIT_JOINT || ty == CNSTR_CONTACT_FRICTIONLESS) { it.kind = 2; }
+  else {
+    it.kind = 3;
+    const int ci = DI(efc_id)[i];
+    const int dim = DI(con_dim)[ci];
+    const float* fr = DF(con_friction) + 5 * ci;
+    it.mu = DF(con_mu)[ci];
+    it.U0 = jar[i] * it.mu; it.V0 = Jv[i] * it.mu;
+    FOR_DIM(j, 1, dim) {
+      const float uj = jar[i + j] * fr[j - 1], vj = Jv[i + j] * fr[j - 1];
+      it.UU += uj * uj; it.UV += uj * vj; it.VV += vj * vj;
+    }
+    FOR_DIM(j, 0, dim) {
+      const float Dj = D[i + j], xj = jar[i + j], vj = Jv[i + j];
+      it.Q0 += Dj * xj * xj; it.Q1 += Dj * xj * vj; it.Q2 += Dj * vj * vj;
+    }
+    it.Dm = it.D / (it.mu * it.mu * (1 + it.mu * it.mu));
+  }
+  return it;
+}
+
+__device__ __forceinline__ LsPoint ls_eval_cached(const LsItem& it, float g0, float g1, float g2, float alpha) {
+  float cost = 0, d1 = 0, d2 = 0;
+  if (it.kind == 1) {
+    const float x = it.x0 + alpha * it.jv;
+    if (x <= -it.rf) { cost = it.f * (-0.5f * it.rf - x); d1 = -it.f * it.jv; }
+    else if (x >= it.rf) { cost = it.f * (-0.5f * it.rf + x); d1 = it.f * it.jv; }
+    else { cost = 0.5f * it.D * x * x; d1 = it.D * x * it.jv; d2 = it.D * it.jv * it.jv; }
+  } else if (it.kind == 2) {
+    const float x = it.x0 + alpha * it.jv;
+    if (x < 0) { cost = 0.5f * it.D * x * x; d1 = it.D * x * it.jv; d2 = it.D * it.jv * it.jv; }
+  } else if (it.kind == 3) {
+    const float mu = it.mu;
+    const float N = it.U0 + alpha * it.V0;
+    const float Tsqr = it.UU + alpha * (2 * it.UV + alpha * it.VV);
+    const float Tn = Tsqr <= 0 ? 0.f : sqrtf(Tsqr);
+    if (N >= mu * Tn || (Tn <= 0 && N >= 0)) {
+    } else if (mu * N + Tn <= 0 || (Tn <= 0 && N < 0)) {
+      cost = 0.5f * (it.Q0 + alpha * (2 * it.Q1 + alpha * it.Q2));
+      d1 = it.Q1 + alpha * it.Q2;
+      d2 = it.Q2;
+    } else {
+      const float N1 = it.V0, T1 = (it.UV + alpha * it.VV) / Tn;
+      const float T2 = it.VV / Tn - (it.UV + alpha * it.VV) * T1 / (Tn * Tn);
+      const float NmT = N - mu * Tn;
+      cost = 0.5f * it.Dm * NmT * NmT;
+      d1 = it.Dm * NmT * (N1 - mu * T1);
+      d2 = it.Dm * ((N1 - mu * T1) * (N1 - mu * T1) + NmT * (-mu * T2));
+    }
+  }
+  LsPoint p;
+  p.alpha = alpha;
+  p.cost = g0 + alpha * g1 + alpha * alpha * g2 + warp_sum(cost);
+  p.d1 = g1 + 2 * alpha * g2 + warp_sum(d1);
+  p.d2 = 2 * g2 + warp_sum(d2);
+  return p;
+}
+
 __device__ __noinline__ float k_line_search(Ctx& c, float g0, float g1, float g2, float snorm, float scale_inv) {
-  const DevModel& M = *c.M;
+  const DevModel& M = CM(c);
   if (snorm < kMinVal) return 0.f;
-  const LsPoint p0 = k_ls_eval(c, g0, g1, g2, 0.f);
+  const bool cached = c.nitem <= 32;   // one work item per lane: the usual case
+  const LsItem item = ls_load_item(c);
+  auto ev = [&](float alpha) { return cached ? ls_eval_cached(item, g0, g1, g2, alpha) : k_ls_eval(c, g0, g1, g2, alpha); };
+  const LsPoint p0 = ev(0.f);
   const float gtol = fmaxf(fmaxf(M.tolerance, kTolFloor) * M.ls_tolerance * snorm * scale_inv, 64 * 1.1920929e-7f * fabsf(p0.d1));
   if (p0.d2 <= kMinVal) return 0.f;
-  LsPoint p1 = k_ls_eval(c, g0, g1, g2, -p0.d1 / p0.d2);
+  LsPoint p1 = ev(-p0.d1 / p0.d2);
   if (p0.cost < p1.cost) p1 = p0;
   if (fabsf(p1.d1) < gtol) return p1.alpha;
   int iter = 0;
@@ -1024,7 +1248,7 @@ __device__ __noinline__ float k_line_search(Ctx& c, float g0, float g1, float g2
     iter++;
     p2 = p1;
     if (p1.d2 <= kMinVal) break;
-    p1 = k_ls_eval(c, g0, g1, g2, p1.alpha - p1.d1 / p1.d2);
+    p1 = ev(p1.alpha - p1.d1 / p1.d2);
     if (fabsf(p1.d1) < gtol) return p1.cost <= p0.cost ? p1.alpha : 0.f;
     if ((p1.d1 > 0) != (p2.d1 > 0)) { bracket = true; break; }
   }
@@ -1037,7 +1261,7 @@ __device__ __noinline__ float k_line_search(Ctx& c, float g0, float g1, float g2
     const float amin = fminf(lo.alpha, hi.alpha), amax = fmaxf(lo.alpha, hi.alpha);
     if (!(a > amin && a < amax)) a = 0.5f * (lo.alpha + hi.alpha);
     if (a == lo.alpha || a == hi.alpha) break;
-    const LsPoint pm = k_ls_eval(c, g0, g1, g2, a);
+    const LsPoint pm = ev(a);
     if (fabsf(pm.d1) < gtol) return pm.cost <= p0.cost ? pm.alpha : 0.f;
     if (pm.d1 < 0) lo = pm; else hi = pm;
   }
@@ -1045,8 +1269,43 @@ __device__ __noinline__ float k_line_search(Ctx& c, float g0, float g1, float g2
   return best.cost < p0.cost ? best.alpha : 0.f;
 }
 
+// out[dof] = sum over constraint rows of J[row][dof] * force[row], in two balanced stages (per contact, then per dof)
+__device__ __forceinline__ void jt_force(Ctx& c, float* out_or_null) {
+  const DevModel& M = CM(c);
+  const int lane = c.lane, nv = M.nv;
+  const float *J = DF(efc_J), *force = DF(efc_force), *esgn = DF(efc_sgn);
+  float* xf = DF(con_xf);
+  const int *cadr = DI(con_adr), *cdim = DI(con_dim), *cnd = DI(con_nd), *cloc = DI(con_loc), *frow = MI(floss_row),
+            *edof = DI(efc_dof);
+  for (int w = lane; w < c.ncon * kL; w += 32) {
+    const int ci = w / kL, l = w - ci * kL;
+    const int a0 = cadr[ci];
+    float a = 0.f;
+    if (a0 >= 0 && l < cnd[ci]) {
+      const int dim = cdim[ci];
+      FOR_DIM(k, 0, dim) a += J[(a0 + k) * kL + l] * force[a0 + k];
+    }
+    xf[w] = a;
+  }
+  __syncwarp();
+  const int nf = M.nfloss, nl = c.nlim;
+  for (int i = lane; i < nv; i += 32) {
+    float a = 0.f;
+    const int fr = frow[i];
+    if (fr >= 0) a += force[fr];
+    for (int q = nf; q < nf + nl; q++)
+      if (edof[q] == i) a += esgn[q] * force[q];
+    for (int ci = 0; ci < c.ncon; ci++) {
+      const int l = cloc[ci * nv + i];
+      if (l >= 0) a += xf[ci * kL + l];
+    }
+    out_or_null[i] = a;
+  }
+  __syncwarp();
+}
+
 __device__ __noinline__ void k_solve(Ctx& c) {
-  const DevModel& M = *c.M;
+  const DevModel& M = CM(c);
   const int lane = c.lane, nv = M.nv, ne = c.nefc;
   float *qacc = DF(qacc), *qas = DF(qacc_smooth), *qws = DF(qacc_warmstart), *qfc = DF(qfrc_constraint);
   c.niter = 0;
@@ -1065,15 +1324,16 @@ __device__ __noinline__ void k_solve(Ctx& c) {
   }
   __syncwarp();
   const float scale_inv = M.meaninertia * (float)max(1, nv);
-  float *grad = DF(grad), *search = DF(search), *Mv = DF(Mv), *Ma = DF(Ma), *smooth = DF(qfrc_smooth),
-        *J = DF(efc_J), *force = DF(efc_force), *Jv = DF(efc_Jv), *qM = DF(qM);
+  const int nsimple = M.nfloss + c.nlim;
+  float *grad = DF(grad), *search = DF(search), *Mv = DF(Mv), *Ma = DF(Ma), *smooth = DF(qfrc_smooth), *Jv = DF(efc_Jv),
+        *qM = DF(qM);
   float cost = k_total_cost(c, qacc, true, &gauss);
   float gnorm2;
   auto grad_dir = [&]() {
+    jt_force(c, qfc);   // qfc doubles as J^T force scratch; it is final after the last iteration
     float g2 = 0;
     for (int i = lane; i < nv; i += 32) {
-      float a = Ma[i] - smooth[i];
-      for (int r = 0; r < ne; r++) a -= J[r * nv + i] * force[r];
+      const float a = Ma[i] - smooth[i] - qfc[i];
       grad[i] = a;
       g2 += a * a;
     }
@@ -1094,11 +1354,7 @@ __device__ __noinline__ void k_solve(Ctx& c) {
       q2 += 0.5f * search[i] * a;
       sn += search[i] * search[i];
     }
-    for (int i = lane; i < ne; i += 32) {
-      float a = 0;
-      for (int j = 0; j < nv; j++) a += J[i * nv + j] * search[j];
-      Jv[i] = a;
-    }
+    for (int i = lane; i < ne; i += 32) Jv[i] = row_dot(c, i, nsimple, search);
     q1 = warp_sum(q1); q2 = warp_sum(q2); sn = sqrtf(warp_sum(sn));
     __syncwarp();
     const float alpha = k_line_search(c, gauss, q1, q2, sn, scale_inv);
@@ -1113,12 +1369,8 @@ __device__ __noinline__ void k_solve(Ctx& c) {
     const float tol = fmaxf(M.tolerance, kTolFloor);
     if (improvement < tol || gradient < tol) break;
   }
-  for (int i = lane; i < nv; i += 32) {
-    float a = 0;
-    for (int r = 0; r < ne; r++) a += J[r * nv + i] * force[r];
-    qfc[i] = a;
-  }
-  __syncwarp();
+  // qfc holds J^T force of the last evaluated point (forces are updated by every k_total_cost call)
+  jt_force(c, qfc);
 }
 
 // ------------------------------------------------------------------------------------------ pipeline pieces
@@ -1143,7 +1395,7 @@ __device__ __noinline__ void k_forward(Ctx& c) {
 
 // semi-implicit Euler with implicit joint damping
 __device__ __noinline__ void k_euler(Ctx& c) {
-  const DevModel& M = *c.M;
+  const DevModel& M = CM(c);
   const int lane = c.lane, nv = M.nv;
   const float h = M.timestep;
   float *qacc = DF(qacc), *qvel = DF(qvel), *qpos = DF(qpos), *vt = DF(vtmp);

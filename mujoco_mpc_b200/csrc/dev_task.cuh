@@ -69,7 +69,7 @@ __device__ __forceinline__ float norm_value(const float* x, const float* params,
 // CostValue of the residual in shared memory; warp-uniform result. Terms are evaluated one per lane and
 // summed in term order (same association as the scalar reference loop).
 __device__ __noinline__ float k_cost_value(Ctx& c) {
-  const DevModel& M = *c.M;
+  const DevModel& M = CM(c);
   const int lane = c.lane;
   const int *dimr = MI(task_dim_norm_residual), *ntype = MI(task_norm), *npar = MI(task_num_norm_parameter);
   const float *w = MF(task_weight), *prm = MF(task_norm_parameter), *res = DF(residual);
@@ -117,7 +117,7 @@ __device__ __forceinline__ float spline_sample1(const float* times, const float*
 }
 // ctrl <- clamp(spline(time)); one actuator per lane
 __device__ __forceinline__ void k_policy_spline(Ctx& c, int P, int interp) {
-  const DevModel& M = *c.M;
+  const DevModel& M = CM(c);
   const float* range = MF(actuator_ctrlrange);
   for (int i = c.lane; i < M.nu; i += 32) {
     float a = spline_sample1(DF(knot_times), DF(knots), P, M.nu, interp, c.time, i);
@@ -189,7 +189,7 @@ struct FeedbackArgs {
 
 // ctrl <- clamp(u + scale * K * (x (-) x_nom)); global-memory reads are lane-strided (coalesced)
 __device__ __noinline__ void k_policy_feedback(Ctx& c, const FeedbackArgs& fa, float step, int index) {
-  const DevModel& M = *c.M;
+  const DevModel& M = CM(c);
   const int lane = c.lane, nq = M.nq, nv = M.nv, nu = M.nu, ds = nq + nv, n = 2 * nv, H = fa.H;
   float *xn = DF(xnom), *dx = DF(dx), *ctrl = DF(ctrl);
   int rep = 0;
@@ -284,7 +284,7 @@ __device__ __forceinline__ float ray_geom(const float* gpos, const float* gmat, 
   return -1;
 }
 __device__ __forceinline__ float ground_height(Ctx& c, const float* pos, bool* ok) {
-  const DevModel& M = *c.M;
+  const DevModel& M = CM(c);
   const float down[3] = {0, 0, -1};
   const float query[3] = {pos[0], pos[1], pos[2] + 0.5f};
   const int *rg = MI(ray_geoms), *gtype = MI(geom_type);
@@ -380,7 +380,7 @@ struct QuadrupedFn {
 };
 
 __device__ __noinline__ void k_residual_quadruped(Ctx& c) {
-  const DevModel& M = *c.M;
+  const DevModel& M = CM(c);
   const int lane = c.lane;
   QuadrupedFn fn{MF(task_state), MI(task_ids), MF(task_parameters)};
   const int* I = fn.I;
@@ -512,7 +512,7 @@ __device__ __noinline__ void k_residual_quadruped(Ctx& c) {
 }
 
 __device__ __noinline__ void k_residual(Ctx& c) {
-  const DevModel& M = *c.M;
+  const DevModel& M = CM(c);
   const int lane = c.lane;
   float* r = DF(residual);
   switch (M.residual_id) {

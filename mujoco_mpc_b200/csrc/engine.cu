@@ -74,7 +74,7 @@ struct mjpc_b200 {
   bool resident_ok = false;
   size_t smem_bytes(int P, int wpc) const {
     DevLayout L = make_layout(pack.M, P);
-    return ((size_t)pack.M.nf + pack.M.ni + (size_t)wpc * L.total) * 4;
+    return ((size_t)smem_header_words(pack.M) + (size_t)wpc * L.total) * 4;
   }
 };
 

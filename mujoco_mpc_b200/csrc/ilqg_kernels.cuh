@@ -131,7 +131,7 @@ struct FdArgs {
 };
 
 __device__ __forceinline__ void fd_load_state(Ctx& c, const FdArgs& A, int t) {
-  const DevModel& M = *c.M;
+  const DevModel& M = CM(c);
   const int lane = c.lane, nq = M.nq, nv = M.nv, ds = nq + nv;
   if (A.task_state) {
     float* ts = const_cast<float*>(MF(task_state));

@@ -58,18 +58,33 @@ __device__ __forceinline__ void stage_model_pack(float* dst, const float* src, u
   __syncthreads();
 }
 
+// shared-memory words taken by the pack + header copies (must match engine.cu smem_bytes)
+__host__ __device__ inline int smem_header_words(const DevModel& M) {
+  return M.nf + M.ni + (int)((sizeof(DevModel) + 15) / 16) * 4 + (int)((sizeof(DevLayout) + 15) / 16) * 4;
+}
+
+// copy the DevModel / DevLayout kernel parameters behind the pack and set up this warp's context
 __device__ __forceinline__ void init_ctx(Ctx& c, const DevModel* M, const DevLayout* L, float* smem, int warp, int lane) {
-  c.M = M; c.L = L;
-  c.mf = smem;
-  c.mi = reinterpret_cast<const int*>(smem + M->nf);
-  c.d = smem + M->nf + M->ni + (size_t)warp * L->total;
+  const int hdr = M->nf + M->ni;
+  const int lay = hdr + (int)((sizeof(DevModel) + 15) / 16) * 4;
+  const int data0 = lay + (int)((sizeof(DevLayout) + 15) / 16) * 4;
+  {
+    const int* srcM = reinterpret_cast<const int*>(M);
+    const int* srcL = reinterpret_cast<const int*>(L);
+    int* dst = reinterpret_cast<int*>(smem);
+    for (int i = threadIdx.x; i < (int)(sizeof(DevModel) / 4); i += blockDim.x) dst[hdr + i] = srcM[i];
+    for (int i = threadIdx.x; i < (int)(sizeof(DevLayout) / 4); i += blockDim.x) dst[lay + i] = srcL[i];
+  }
+  __syncthreads();
+  c.hdr = hdr; c.lay = lay; c.ibase = M->nf;
+  c.dbase = data0 + warp * L->total;
   c.lane = lane;
   c.ncon = 0; c.nefc = 0; c.nitem = 0; c.niter = 0; c.nlim = 0; c.warn = 0; c.time = 0.f;
 }
 
 // write the trace points (GetTraces, mjpc/utilities.cc:268-285)
 __device__ __forceinline__ void write_traces(Ctx& c, float* out) {
-  const DevModel& M = *c.M;
+  const DevModel& M = CM(c);
   const int *ty = MI(task_trace_objtype), *id = MI(task_trace_objid);
   for (int w = c.lane; w < 3 * M.num_trace; w += 32) {
     const int k = w / 3, q = w - 3 * k;
@@ -84,9 +99,9 @@ extern "C" __global__ void __launch_bounds__(128) rollout_kernel(const __grid_co
   stage_model_pack(smem, A.pack, (unsigned)((M.nf + M.ni) * 4));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cand = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (cand >= A.N) return;
   Ctx c;
   init_ctx(c, &A.M, &A.L, smem, warp, lane);
+  if (cand >= A.N) return;
   const int nq = M.nq, nv = M.nv, nu = M.nu, ds = nq + nv, nr = M.num_residual, ntr = 3 * M.num_trace, H = A.H;
   // per-iteration task state (time-rebased) overrides the packed copy: the pack in shared memory is per CTA,
   // every warp writes the same values
