@@ -26,7 +26,7 @@ namespace mjpc_dev {
   X(con_g1, M.maxcon) X(con_g2, M.maxcon) X(con_adr, M.maxcon) X(efc_J, M.maxefc * 16)                            \
   X(efc_W, 2 * M.maxcon * 16) X(con_nd, M.maxcon) X(con_dof, M.maxcon * 16) X(con_loc, M.maxcon * M.nv)           \
   X(con_boff, M.maxcon + 1) X(con_xf, M.maxcon * 16) X(efc_blk, 1024) X(efc_dof, M.maxefc) X(efc_sgn, M.maxefc)     \
-  X(efc_Jd, (M.maxefc + 8) * M.nv) X(efc_Xd, 2 * M.maxcon * M.nv) X(efc_pos, M.maxefc) X(efc_margin, M.maxefc) X(efc_diag, M.maxefc)                    \
+  X(efc_Jd, (M.maxefc + 8) * ((M.nv + 3) / 4 * 4)) X(efc_Xd, 2 * M.maxcon * ((M.nv + 3) / 4 * 4)) X(efc_pos, M.maxefc) X(efc_margin, M.maxefc) X(efc_diag, M.maxefc)                    \
   X(efc_R, M.maxefc) X(efc_D, M.maxefc) X(efc_K, M.maxefc) X(efc_B, M.maxefc) X(efc_imp, M.maxefc)                \
   X(efc_aref, M.maxefc) X(efc_hw, M.maxefc) X(efc_force, M.maxefc) X(efc_jar, M.maxefc) X(efc_Jv, M.maxefc) X(efc_floss, M.maxefc)    \
   X(efc_type, M.maxefc) X(efc_id, M.maxefc) X(efc_state, M.maxefc) X(efc_item, M.maxefc) X(efc_hc, 36 * M.maxcon) X(con_mlo, M.maxcon) X(con_mhi, M.maxcon) \

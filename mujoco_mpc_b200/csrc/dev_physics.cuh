@@ -574,7 +574,8 @@ __device__ __noinline__ void k_make_constraint(Ctx& c) {
                 *binvw = MF(body_invweight0);
     // dense copies of the contact rows feed the register-blocked Hessian assembly (zeros off the chains)
     float* Jd = DF(efc_Jd);
-    for (int w = lane + (M.nfloss + c.nlim) * nv; w < ne * nv; w += 32) Jd[w] = 0.f;
+    const int nvp = (nv + 3) & ~3;   // dense row stride, 16-byte aligned for vector loads
+    for (int w = lane + (M.nfloss + c.nlim) * nvp; w < ne * nvp; w += 32) Jd[w] = 0.f;
     __syncwarp();
     // compact Jacobian entries: one (contact, local dof) pair per lane
     const int nwork = c.ncon * kL;
@@ -604,7 +605,7 @@ __device__ __noinline__ void k_make_constraint(Ctx& c) {
         const float* ax = fr + 3 * (k % 3);
         const float v = k < 3 ? dot3(ax, jp) : dot3(ax, jr);
         J[(adr + k) * kL + l] = v;
-        Jd[(adr + k) * nv + i] = v;
+        Jd[(adr + k) * nvp + i] = v;
       }
     }
     // per-row scalars: one contact per lane
@@ -933,8 +934,8 @@ __device__ __noinline__ float k_update_constraint(Ctx& c, bool hess) {
         const int a0 = cadr[ci];
         if (a0 < 0 || state[a0] != STATE_CONE) continue;
         const int l = cloc[w];
-        Xd[(2 * ci) * nv + i] = l >= 0 ? X[(2 * ci) * kL + l] : 0.f;
-        Xd[(2 * ci + 1) * nv + i] = l >= 0 ? X[(2 * ci + 1) * kL + l] : 0.f;
+        Xd[(2 * ci) * 20 + i] = l >= 0 ? X[(2 * ci) * kL + l] : 0.f;
+        Xd[(2 * ci + 1) * 20 + i] = l >= 0 ? X[(2 * ci + 1) * kL + l] : 0.f;
       }
     }
     __syncwarp();
@@ -942,27 +943,29 @@ __device__ __noinline__ float k_update_constraint(Ctx& c, bool hess) {
   return cost;
 }
 
-// Register-blocked Newton Hessian for compile-time NV: lane owns lower-triangle entries e = lane + 32 q and keeps
-// them in registers; every active constraint row (weight hw != 0) and every cone effective row is one rank-1
-// update read as a dense NV-wide row from shared memory (broadcast loads, no bank conflicts, no branches inside).
-template <int NV>
+// Register-blocked Newton Hessian for compile-time NV: lane owns structurally non-zero lower-triangle entries
+// e = lane + 32 q (hpair tables, NQ per lane) and keeps them in registers; every active constraint row (weight
+// hw != 0) and every cone effective row is one rank-1 update read as a dense row from shared memory
+// (broadcast loads, no bank conflicts, no branches inside).
+template <int NV, int NQ>
 __device__ __forceinline__ void hessian_dense_reg(Ctx& c) {
   const DevModel& M = CM(c);
   const int lane = c.lane;
-  constexpr int NE = NV * (NV + 1) / 2, NQ = (NE + 31) / 32;
+  constexpr int NVP = (NV + 3) / 4 * 4;
   const float *qM = DF(qM), *hw = DF(efc_hw), *Jd = DF(efc_Jd), *Xd = DF(efc_Xd), *xw = DF(efc_hc);
   float* H = DF(qH);
-  const int *frow = MI(floss_row), *edof = DI(efc_dof), *state = DI(efc_state), *cadr = DI(con_adr);
+  const int *frow = MI(floss_row), *edof = DI(efc_dof), *state = DI(efc_state), *cadr = DI(con_adr),
+            *hi = MI(hpair_i), *hj = MI(hpair_j);
+  const int NE = M.nhpair;
   int er[NQ], es[NQ];
   float acc[NQ];
+  for (int w = lane; w < NV * NV; w += 32) H[w] = 0.f;   // entries outside the pattern (the factor fills them)
 #pragma unroll
   for (int q = 0; q < NQ; q++) {
     int e = lane + 32 * q;
     if (e >= NE) e = NE - 1;
-    int r = (int)((sqrtf(8.f * e + 1.f) - 1.f) * 0.5f);
-    while ((r + 1) * (r + 2) / 2 <= e) r++;
-    while (r * (r + 1) / 2 > e) r--;
-    er[q] = r; es[q] = e - r * (r + 1) / 2;
+    const int r = hi[e];
+    er[q] = r; es[q] = hj[e];
     float a = qM[er[q] * NV + es[q]];
     if (er[q] == es[q]) {
       const int fr = frow[r];
@@ -976,7 +979,7 @@ __device__ __forceinline__ void hessian_dense_reg(Ctx& c) {
   for (int row = r0; row < ne; row++) {
     const float w = hw[row];
     if (w == 0.f) continue;   // warp-uniform
-    const float* j = Jd + row * NV;
+    const float* j = Jd + row * NVP;
 #pragma unroll
     for (int q = 0; q < NQ; q++) acc[q] += w * j[er[q]] * j[es[q]];
   }
@@ -984,14 +987,46 @@ __device__ __forceinline__ void hessian_dense_reg(Ctx& c) {
     const int a0 = cadr[ci];
     if (a0 < 0 || state[a0] != STATE_CONE) continue;   // warp-uniform
     const float wv = xw[36 * ci + 12], wu = xw[36 * ci + 13];
-    const float* xv = Xd + (2 * ci) * NV;
-    const float* xu = xv + NV;
+    const float* xv = Xd + (2 * ci) * NVP;
+    const float* xu = xv + NVP;
 #pragma unroll
     for (int q = 0; q < NQ; q++) acc[q] += wv * xv[er[q]] * xv[es[q]] + wu * xu[er[q]] * xu[es[q]];
   }
+  __syncwarp();
 #pragma unroll
   for (int q = 0; q < NQ; q++)
     if (lane + 32 * q < NE) { H[er[q] * NV + es[q]] = acc[q]; H[es[q] * NV + er[q]] = acc[q]; }
+  __syncwarp();
+}
+
+// dense-row variants of J*v and J^T*force for compile-time NV (vectorised, fully unrolled)
+template <int NV>
+__device__ __forceinline__ float row_dot_dense(Ctx& c, int row, int nsimple, const float* v) {
+  if (row < nsimple) return DF(efc_sgn)[row] * v[DI(efc_dof)[row]];
+  constexpr int NVP = (NV + 3) / 4 * 4;
+  const float* j = DF(efc_Jd) + row * NVP;
+  float a = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; k++) a += j[k] * v[k];
+  return a;
+}
+template <int NV>
+__device__ __forceinline__ void jt_force_dense(Ctx& c, float* out) {
+  const DevModel& M = CM(c);
+  const int lane = c.lane;
+  constexpr int NVP = (NV + 3) / 4 * 4;
+  const float *Jd = DF(efc_Jd), *force = DF(efc_force), *esgn = DF(efc_sgn);
+  const int *frow = MI(floss_row), *edof = DI(efc_dof);
+  const int nf = M.nfloss, nl = c.nlim, ne = c.nefc;
+  if (lane < NV) {
+    float a = 0.f;
+    const int fr = frow[lane];
+    if (fr >= 0) a += force[fr];
+    for (int q = nf; q < nf + nl; q++)
+      if (edof[q] == lane) a += esgn[q] * force[q];
+    for (int row = nf + nl; row < ne; row++) a += Jd[row * NVP + lane] * force[row];
+    out[lane] = a;
+  }
   __syncwarp();
 }
 
@@ -1012,12 +1047,15 @@ __device__ __noinline__ float k_total_cost(Ctx& c, const float* qacc, bool hess,
     Ma[i] = a;
     g += (a - smooth[i]) * (qacc[i] - qas[i]);
   }
-  for (int i = lane; i < c.nefc; i += 32) jar[i] = row_dot(c, i, nsimple, qacc) - aref[i];
+  if (nv == 18) { for (int i = lane; i < c.nefc; i += 32) jar[i] = row_dot_dense<18>(c, i, nsimple, qacc) - aref[i]; }
+  else { for (int i = lane; i < c.nefc; i += 32) jar[i] = row_dot(c, i, nsimple, qacc) - aref[i]; }
   g = 0.5f * warp_sum(g);
   __syncwarp();
   const float cc = k_update_constraint(c, hess);
-  if (hess && nv == 18) {
-    hessian_dense_reg<18>(c);
+  if (hess && nv == 18 && M.nhpair <= 128) {
+    hessian_dense_reg<18, 4>(c);
+  } else if (hess && nv == 18) {
+    hessian_dense_reg<18, 6>(c);
   } else if (hess) {
     const float *X = DF(efc_W), *hw = DF(efc_hw), *xw = DF(efc_hc);
     float *H = DF(qH), *blk = DF(efc_blk);
@@ -1330,7 +1368,7 @@ __device__ __noinline__ void k_solve(Ctx& c) {
   float cost = k_total_cost(c, qacc, true, &gauss);
   float gnorm2;
   auto grad_dir = [&]() {
-    jt_force(c, qfc);   // qfc doubles as J^T force scratch; it is final after the last iteration
+    if (nv == 18) jt_force_dense<18>(c, qfc); else jt_force(c, qfc);   // qfc doubles as J^T force scratch
     float g2 = 0;
     for (int i = lane; i < nv; i += 32) {
       const float a = Ma[i] - smooth[i] - qfc[i];
@@ -1354,7 +1392,8 @@ __device__ __noinline__ void k_solve(Ctx& c) {
       q2 += 0.5f * search[i] * a;
       sn += search[i] * search[i];
     }
-    for (int i = lane; i < ne; i += 32) Jv[i] = row_dot(c, i, nsimple, search);
+    if (nv == 18) { for (int i = lane; i < ne; i += 32) Jv[i] = row_dot_dense<18>(c, i, nsimple, search); }
+    else { for (int i = lane; i < ne; i += 32) Jv[i] = row_dot(c, i, nsimple, search); }
     q1 = warp_sum(q1); q2 = warp_sum(q2); sn = sqrtf(warp_sum(sn));
     __syncwarp();
     const float alpha = k_line_search(c, gauss, q1, q2, sn, scale_inv);
@@ -1370,7 +1409,7 @@ __device__ __noinline__ void k_solve(Ctx& c) {
     if (improvement < tol || gradient < tol) break;
   }
   // qfc holds J^T force of the last evaluated point (forces are updated by every k_total_cost call)
-  jt_force(c, qfc);
+  if (nv == 18) jt_force_dense<18>(c, qfc); else jt_force(c, qfc);
 }
 
 // ------------------------------------------------------------------------------------------ pipeline pieces

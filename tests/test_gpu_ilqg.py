@@ -78,7 +78,7 @@ def test_model_derivatives(ctx, name, eps):
         if name == "quadruped":
             # a perturbation can open/close a contact in one arithmetic and not the other: a handful of entries of the
             # stiff contact block differ at O(1); everything else agrees to round-off / eps
-            assert np.quantile(err, 0.99) < 5e-3 * scale and err.max() < 0.1 * scale
+            assert np.quantile(err, 0.99) < 1e-2 * scale and err.max() < 0.1 * scale
         else:
             assert err.max() < 2e-3 * scale
 
