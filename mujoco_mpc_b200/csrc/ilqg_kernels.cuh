@@ -361,8 +361,10 @@ __device__ inline void chol_solve_serial(float* x, const float* L, const float* 
 // projected-Newton box QP (same algorithm and constants as oracle/ilqg.h box_qp). scratch >= 6n floats + n ints
 __device__ inline int box_qp_serial(float* res, float* R, int* index, const float* Hm, const float* g, int n,
                                     const float* lower, const float* upper, float* scratch) {
+  // fp32 floors on the reference's fp64 constants (mingrad 1e-16, minstep 1e-22): below ~1e-7 relative neither the
+  // free-gradient norm nor a backtracked step is resolvable in fp32, and looping on them only burns serial time
   const int maxiter = 100;
-  const float mingrad = 1e-16f, backtrack = 0.5f, minstep = 1e-22f, armijo = 0.01f;
+  const float mingrad = 1e-6f, backtrack = 0.5f, minstep = 1e-7f, armijo = 0.01f;
   float *grad = scratch, *search = grad + n, *cand = search + n, *tmp = cand + n, *rhs = tmp + n, *sol = rhs + n;
   int* clamped = reinterpret_cast<int*>(sol + n);
   for (int i = 0; i < n; i++) { res[i] = fmaxf(lower[i], fminf(upper[i], res[i])); clamped[i] = 0; }
@@ -391,7 +393,9 @@ __device__ inline int box_qp_serial(float* res, float* R, int* index, const floa
     }
     float norm2 = 0;
     for (int a = 0; a < nfree; a++) norm2 += grad[index[a]] * grad[index[a]];
-    if (norm2 < mingrad * mingrad) break;
+    float gscale = 0;
+    for (int i = 0; i < n; i++) gscale += g[i] * g[i];
+    if (norm2 < mingrad * mingrad * (1.f + gscale)) break;
     for (int i = 0; i < n; i++) tmp[i] = clamped[i] ? res[i] : 0.f;
     for (int a = 0; a < nfree; a++) {
       const int i = index[a];

@@ -52,3 +52,37 @@ def quadruped_inputs(m, N=16, H=64, seed=0, sigma=0.04, iteration=0):
     cr = np.asarray(m.actuator_ctrlrange).reshape(-1, 2)
     knots = candidate_knots(np.zeros((P, m.nu)), sigma, cr, iteration, N, seed=0x5EED + seed)
     return state, mocap_of(m), knots, kt
+
+
+class OracleBackend:
+    """The CPU oracle behind the same five calls Engine exposes (tests + CPU baseline only)."""
+
+    def __init__(self, m, threads=2, precision=64):
+        from mujoco_mpc_b200.blob import to_blob
+        from oracle import pyoracle
+        self.m, self.po, self.threads = m, pyoracle, threads
+        self.o = pyoracle.Oracle(to_blob(m), m, precision)
+        self.last = None
+
+    def rollout_spline(self, state, time, mocap, knots, kt, interp, H):
+        r = self.o.rollout_spline(state, time, mocap, knots, kt, interp, H, nthreads=self.threads, full=True)
+        self.last = r
+        return r["returns"], r["failure"], np.argsort(r["returns"], kind="stable")
+
+    def rollout_feedback(self, state, time, mocap, u_nom, x_nom, t_nom, gains, du, step_sizes, mode):
+        r = self.o.rollout_feedback(state, time, mocap, u_nom, x_nom, t_nom, gains, du, step_sizes, mode, nthreads=self.threads)
+        self.last = r
+        return r["returns"], r["failure"], np.argsort(r["returns"], kind="stable")
+
+    def fetch_trajectory(self, i):
+        return {k: self.last[k][i] for k in ("states", "actions", "times", "residual", "costs", "trace")}
+
+    def model_derivatives(self, x, u, t, mocap, tol):
+        return self.o.model_derivatives(np.asarray(x, float), np.asarray(u, float), np.asarray(t, float), mocap, tol=tol)
+
+    def cost_derivatives(self, residual, C, D):
+        return self.o.cost_derivatives(np.asarray(residual, float), np.asarray(C, float), np.asarray(D, float))
+
+    def backward_pass(self, A, B, cx, cu, cxx, cxu, cuu, actions, mu=0.0, reg_type=0, limits=1):
+        cr = np.asarray(self.m.actuator_ctrlrange, float).reshape(-1, 2)
+        return self.po.backward_pass(A, B, cx, cu, cxx, cxu, cuu, actions, cr, mu=mu, reg_type=reg_type, limits=limits)

@@ -132,3 +132,32 @@ def test_feedback_rollouts(ctx, oracle_lib, mode):
     ret0, _, _ = e.rollout_feedback(state, 0.0, mocap_of(m), us, xs, ts, 0 * K, 0 * du, np.array([0.0]), 3)
     nominal_return = o.rollout_feedback(state, 0.0, mocap_of(m), us, xs, ts, 0 * K, 0 * du, np.array([0.0]), 3)["returns"][0]
     np.testing.assert_allclose(ret0[0], nominal_return, rtol=2e-3)
+
+
+def test_ilqg_planner_on_device(ctx):
+    """ilqg_test.cc:49-126 with every sweep on the device (fp32 finite differences need eps ~ 1e-3)."""
+    from mujoco_mpc_b200.ilqg import ILQGPlanner
+    m, e, _ = ctx["particle"]
+    pl = ILQGPlanner(m, e, horizon=26, fd_tolerance=1e-3)
+    pl.set_state(np.zeros(4), 0.0, mocap_of(m))
+    for _ in range(25):
+        pl.optimize_policy()
+    goal = mocap_of(m)[:2]
+    assert abs(pl.states[-1, 0] - goal[0]) < 1e-2 and abs(pl.states[-1, 1] - goal[1]) < 1e-2
+    assert abs(pl.states[-1, 2]) < 0.1 and abs(pl.states[-1, 3]) < 0.1
+
+
+def test_ilqg_quadruped_iteration_improves(ctx):
+    """BASELINE config 4 shape (Quadruped, iLQG, H=64): a few iterations lower the nominal return."""
+    from mujoco_mpc_b200.ilqg import ILQGPlanner
+    m, e, _ = ctx["quadruped"]
+    pl = ILQGPlanner(m, e, horizon=64, num_rollouts=10, fd_tolerance=1e-3)
+    pl.set_state(np.concatenate([m.key_qpos[0], np.zeros(m.nv)]), 0.0, mocap_of(m))
+    pl.nominal_trajectory()
+    first = pl.total_return
+    ok = 0
+    for _ in range(6):
+        ok += bool(pl.optimize_policy())
+    assert ok >= 3 and np.isfinite(pl.total_return)
+    assert pl.total_return < first
+    assert (np.abs(pl.actions) <= 1.0 + 1e-6).all()
