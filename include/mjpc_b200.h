@@ -155,6 +155,23 @@ int mjpc_b200_read_returns(mjpc_b200_t* h, float* returns, uint8_t* failure, int
 void* mjpc_b200_stream(mjpc_b200_t* h);
 float* mjpc_b200_device_returns(mjpc_b200_t* h);
 
+/* ---- C++ host layer above the ABI (csrc/host/sampling_planner.{h,cc}): SamplingPlanner with the reference's
+ * method names (mjpc/planners/sampling/planner.h:40-160); these C wrappers are what ctypes / a test harness binds.
+ * mjpc_b200_host_spline_sample = TimeSpline::Sample (mjpc/spline/spline.cc:103-156), usable without a GPU. */
+void mjpc_b200_host_spline_sample(const double* times, const double* values, int P, int dim, int interp, double t,
+                                  double* out);
+double mjpc_b200_host_philox_normal(uint32_t seed, uint32_t iteration, uint32_t candidate, uint32_t knot, uint32_t dof);
+int mjpc_b200_planner_create(const mjpc_model_blob* model, int num_trajectory, int num_spline_points, int interpolation,
+                             double exploration, double timestep, const double* ctrlrange, uint32_t seed,
+                             int max_horizon, int device, void** out);
+void mjpc_b200_planner_destroy(void* planner);
+void mjpc_b200_planner_reset(void* planner, int horizon, const double* initial_repeated_action);
+void mjpc_b200_planner_set_state(void* planner, const double* state, double time, const double* mocap);
+int mjpc_b200_planner_optimize_policy(void* planner, int horizon);          /* SamplingPlanner::OptimizePolicy */
+void mjpc_b200_planner_action_from_policy(void* planner, double* action, double time, int use_previous);
+int mjpc_b200_planner_get_result(void* planner, int* winner, double* improvement, float* returns, double* knots,
+                                 double* knot_times);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,7 +12,9 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 
 def sources():
+    host = os.path.join(CSRC, "host")
     return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))] + \
+        [os.path.join(host, f) for f in sorted(os.listdir(host)) if f.endswith((".cc", ".h"))] + \
         [os.path.join(HERE, "..", "include", "mjpc_b200.h")]
 
 
@@ -27,7 +29,7 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO, os.path.join(CSRC, "engine.cu")]
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO, os.path.join(CSRC, "engine.cu"), os.path.join(CSRC, "host", "sampling_planner.cc")]
     subprocess.check_call(cmd, cwd=CSRC)
     return SO
 

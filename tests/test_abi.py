@@ -41,3 +41,36 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cc")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and '"oracle/' not in txt and "../oracle" not in txt, f
+
+
+def test_cpp_host_spline_and_noise_match_python_mirror():
+    """The C++ host layer (TimeSpline::Sample restatement, injected Philox noise) vs the reference's spline known
+    answers (spline_test.cc:115-158) and the Python mirror - no GPU needed."""
+    import numpy as np
+    from mujoco_mpc_b200 import build
+    from mujoco_mpc_b200.planner import philox_normal, sample_spline
+    lib = ctypes.CDLL(build.build())
+    lib.mjpc_b200_host_philox_normal.restype = ctypes.c_double
+    dp = ctypes.POINTER(ctypes.c_double)
+
+    def sample(times, values, interp, t):
+        times = np.ascontiguousarray(times, float); values = np.ascontiguousarray(values, float)
+        out = np.zeros(values.shape[1])
+        lib.mjpc_b200_host_spline_sample(times.ctypes.data_as(dp), values.ctypes.data_as(dp), len(times), values.shape[1],
+                                         interp, ctypes.c_double(t), out.ctypes.data_as(dp))
+        return out
+    np.testing.assert_allclose(sample([1, 2], [[1.0, 2], [3, 4]], 0, 1.5), [1, 2])
+    np.testing.assert_allclose(sample([1, 2], [[1.0, 2], [3, 4]], 1, 1.5), [2, 3])
+    np.testing.assert_allclose(sample([0, 1, 2, 3], [[1.0, 2], [1, 2], [3, 4], [3, 4]], 2, 1.5), [2, 3])
+    for x in np.arange(0.0, 1.0001, 0.125):
+        np.testing.assert_allclose(sample([-1, 0, 1], [[1.0], [0.0], [1.0]], 2, x), [-x ** 3 + 2 * x ** 2], atol=1e-12)
+    rng = np.random.default_rng(2)
+    times = np.cumsum(rng.uniform(0.1, 0.4, 5)); vals = rng.normal(size=(5, 3))
+    for interp in (0, 1, 2):
+        for t in np.linspace(times[0] - 0.2, times[-1] + 0.2, 23):
+            np.testing.assert_allclose(sample(times, vals, interp, t), sample_spline(times, vals, interp, t), atol=1e-12)
+    z = philox_normal(7, 4, 3, 12)
+    for (i, k, d) in ((0, 0, 0), (3, 2, 11), (1, 1, 5)):
+        zc = lib.mjpc_b200_host_philox_normal(ctypes.c_uint32(0x5EED), ctypes.c_uint32(7), ctypes.c_uint32(i),
+                                              ctypes.c_uint32(k), ctypes.c_uint32(d))
+        assert abs(zc - z[i, k, d]) < 1e-12

@@ -177,3 +177,28 @@ def test_edge_cases(engines, quadruped):
         e.rollout_spline(state, 0.0, mocap, np.zeros((100000, 3, 12)), kt, 2, 8)      # above capacity
     with pytest.raises(EngineError):
         e.rollout_spline(state, 0.0, mocap, knots, kt, 7, 8)                           # bad interpolation id
+
+
+def test_cpp_host_planner_matches_python_mirror(engines, quadruped):
+    """The C++ SamplingPlanner (csrc/host) and the Python mirror drive the same C ABI with the same injected noise:
+    identical winners / installed knots over several planning iterations."""
+    from mujoco_mpc_b200.engine import CppSamplingPlanner
+    from mujoco_mpc_b200.planner import SamplingPlanner
+    m = quadruped
+    state = np.concatenate([m.key_qpos[0], np.zeros(m.nv)])
+    mocap = mocap_of(m)
+    N, H = 64, 32
+    cpp = CppSamplingPlanner(m, N, H)
+    py = SamplingPlanner(m, engines("quadruped"), num_trajectory=N, horizon=H)
+    cpp.reset(np.zeros(m.nu)); py.reset(np.zeros(m.nu))
+    cpp.set_state(state, 0.0, mocap); py.set_state(state, 0.0, mocap)
+    for it in range(4):
+        rc = cpp.optimize_policy()
+        ret, fail = py.optimize_policy()
+        np.testing.assert_allclose(rc["knot_times"], py.times, atol=1e-12)
+        assert rc["winner"] == py.winner, it
+        np.testing.assert_allclose(rc["knots"], py.values, atol=1e-6)
+        np.testing.assert_allclose(rc["returns"], ret, rtol=1e-5)
+    a = cpp.action_from_policy(0.1)
+    np.testing.assert_allclose(a, py.action_from_policy(0.1), atol=1e-6)
+    cpp.close()
