@@ -79,31 +79,45 @@ def algorithmic_bytes_per_env_step(m, P):
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.t_mark = [], None, index, None
 
     def start(self):
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
 
+    def mark(self):
+        """Start of the timed region: only samples taken from here on are reported."""
+        self.t_mark = time.time()
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
     def stop(self):
         if self.proc:
             self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        rows = [r for t, r in self.rows if self.t_mark is None or t >= self.t_mark]
+        if not rows and self.rows:
+            rows = [self.rows[-1][1]]
+
+        def num(x):
+            try:
+                return float(x)
+            except ValueError:
+                return None
+        sm = [num(r[0]) for r in rows if r and num(r[0]) is not None]
+        mx = [num(r[1]) for r in rows if len(r) > 1 and num(r[1]) is not None]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        reasons = sorted({names[i] for r in rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
 
@@ -186,12 +200,13 @@ def main():
     eng.upload_spline_inputs(state, 0.0, mocap, knots[0], kt, INTERP, HORIZON)
     eng.sync()
     clocks = ClockSampler(local)
+    clocks.start()          # nvidia-smi needs ~0.5 s to produce its first row: start before the warm-up
     kern_ms, coll_ms = [], []
     launches0 = 0
     for it in range(n_iter):
         if it == args.warmup:
             barrier()
-            clocks.start()
+            clocks.mark()
             launches0 = eng.launch_count
             t_wall0 = time.perf_counter()
         flush.zero_()

@@ -202,3 +202,59 @@ def test_cpp_host_planner_matches_python_mirror(engines, quadruped):
     a = cpp.action_from_policy(0.1)
     np.testing.assert_allclose(a, py.action_from_policy(0.1), atol=1e-6)
     cpp.close()
+
+
+def test_set_task_and_time_rebasing(engines, oracles, quadruped):
+    """mjpc_b200_set_task (the per-iteration residual snapshot, agent.cc:316-319) and the host-side time rebasing."""
+    from mujoco_mpc_b200 import task as T
+    m = quadruped
+    e, o = engines("quadruped"), oracles("quadruped", 64)
+    N, H = 8, 24
+    state, mocap, knots, kt = quadruped_inputs(m, N=N, H=H)
+    base, _, _ = e.rollout_spline(state, 0.0, mocap, knots, kt, 2, H)
+    # (1) new weights / parameters change the returns exactly as in the oracle
+    w = np.asarray(m.task_weight, float).copy(); w[0] = 3.0; w[5] = 0.5
+    prm = np.asarray(m.task_parameters, float).copy(); prm[m.task_parameter_names.index("residual_Amplitude")] = 0.1
+    e.set_task(weight=w, parameters=prm); o.set_task(weight=w, parameters=prm)
+    ret, _, _ = e.rollout_spline(state, 0.0, mocap, knots, kt, 2, H)
+    ref = o.rollout_spline(state, 0.0, mocap, knots, kt, 2, H, full=False)["returns"]
+    assert np.abs(ret - base).max() > 1e-3
+    np.testing.assert_allclose(ret, ref, rtol=5e-4)
+    # (2) a rollout that starts at t0 = 1000 s with the task clock shifted by the same amount is the same rollout
+    ts = np.asarray(m.task_state, float).copy()
+    ts[T.QS_MODE_START_TIME] += 1000.0; ts[T.QS_PHASE_START_TIME] += 1000.0
+    e.set_task(weight=w, parameters=prm, task_state=ts)
+    ret2, _, _ = e.rollout_spline(state, 1000.0, mocap, knots, kt + 1000.0, 2, H)
+    np.testing.assert_allclose(ret2, ret, rtol=1e-5)
+    tr = e.fetch_trajectory(0)
+    np.testing.assert_allclose(tr["times"], 1000.0 + np.arange(H) * 0.01, atol=1e-5)
+    # (3) other modes of the quadruped residual (Biped / Walk / Scramble / Flip) agree with the oracle
+    for mode in (1, 2, 3, 4):
+        ts2 = np.asarray(m.task_state, float).copy()
+        ts2[T.QS_MODE] = mode; ts2[T.QS_HEADING] = 1.0; ts2[T.QS_SPEED] = 0.5; ts2[T.QS_ORIENTATION] = 1.0
+        e.set_task(task_state=ts2); o.set_task(task_state=ts2)
+        r1, f1, _ = e.rollout_spline(state, 0.0, mocap, knots[:4], kt, 2, 12)
+        r2 = o.rollout_spline(state, 0.0, mocap, knots[:4], kt, 2, 12, full=False)
+        assert not f1.any() and not r2["failure"].any()
+        np.testing.assert_allclose(r1, r2["returns"], rtol=1e-3, err_msg="mode %d" % mode)
+    e.set_task(weight=np.asarray(m.task_weight, float), parameters=np.asarray(m.task_parameters, float),
+               task_state=np.asarray(m.task_state, float))
+    o.set_task(weight=np.asarray(m.task_weight, float), parameters=np.asarray(m.task_parameters, float),
+               task_state=np.asarray(m.task_state, float))
+
+
+def test_handles_are_independent(quadruped):
+    """Two handles (different models) alive at once; create/destroy does not leak or disturb the other."""
+    from mujoco_mpc_b200.engine import Engine
+    m = quadruped
+    state, mocap, knots, kt = quadruped_inputs(m, N=4, H=8)
+    e1 = Engine(m, 8, 16)
+    r1, _, _ = e1.rollout_spline(state, 0.0, mocap, knots, kt, 2, 8)
+    for _ in range(5):
+        e2 = Engine(get_model("cartpole"), 8, 16)
+        mc = get_model("cartpole")
+        e2.rollout_spline(np.array([1.0, 0, 0, 0]), 0.0, np.zeros(0), np.zeros((4, 10, 1)), np.arange(10) * 0.03, 2, 8)
+        e2.close()
+    r2, _, _ = e1.rollout_spline(state, 0.0, mocap, knots, kt, 2, 8)
+    assert np.array_equal(r1, r2)
+    e1.close()
