@@ -999,16 +999,28 @@ __device__ __forceinline__ void hessian_dense_reg(Ctx& c) {
   __syncwarp();
 }
 
+// row i of (NV x NV row-major matrix) times vector, compile-time NV, 8-byte vector loads (NV even)
+template <int NV>
+__device__ __forceinline__ float mat_row_dot(const float* Mrow, const float* v) {
+  float a = 0.f;
+  if (NV % 2 == 0) {
+    const float2* m2 = reinterpret_cast<const float2*>(Mrow);
+    const float2* v2 = reinterpret_cast<const float2*>(v);
+#pragma unroll
+    for (int k = 0; k < NV / 2; k++) { const float2 x = m2[k], y = v2[k]; a += x.x * y.x + x.y * y.y; }
+  } else {
+#pragma unroll
+    for (int k = 0; k < NV; k++) a += Mrow[k] * v[k];
+  }
+  return a;
+}
+
 // dense-row variants of J*v and J^T*force for compile-time NV (vectorised, fully unrolled)
 template <int NV>
 __device__ __forceinline__ float row_dot_dense(Ctx& c, int row, int nsimple, const float* v) {
   if (row < nsimple) return DF(efc_sgn)[row] * v[DI(efc_dof)[row]];
   constexpr int NVP = (NV + 3) / 4 * 4;
-  const float* j = DF(efc_Jd) + row * NVP;
-  float a = 0.f;
-#pragma unroll
-  for (int k = 0; k < NV; k++) a += j[k] * v[k];
-  return a;
+  return mat_row_dot<NV>(DF(efc_Jd) + row * NVP, v);   // NVP is a multiple of 4: rows are 16-byte aligned
 }
 template <int NV>
 __device__ __forceinline__ void jt_force_dense(Ctx& c, float* out) {
@@ -1043,7 +1055,8 @@ __device__ __noinline__ float k_total_cost(Ctx& c, const float* qacc, bool hess,
   float g = 0;
   for (int i = lane; i < nv; i += 32) {
     float a = 0;
-    for (int j = 0; j < nv; j++) a += qM[i * nv + j] * qacc[j];
+    if (nv == 18) a = mat_row_dot<18>(qM + i * 18, qacc);
+    else for (int j = 0; j < nv; j++) a += qM[i * nv + j] * qacc[j];
     Ma[i] = a;
     g += (a - smooth[i]) * (qacc[i] - qas[i]);
   }
@@ -1386,7 +1399,8 @@ __device__ __noinline__ void k_solve(Ctx& c) {
     float q1 = 0, q2 = 0, sn = 0;
     for (int i = lane; i < nv; i += 32) {
       float a = 0;
-      for (int j = 0; j < nv; j++) a += qM[i * nv + j] * search[j];
+      if (nv == 18) a = mat_row_dot<18>(qM + i * 18, search);
+      else for (int j = 0; j < nv; j++) a += qM[i * nv + j] * search[j];
       Mv[i] = a;
       q1 += search[i] * (Ma[i] - smooth[i]);
       q2 += 0.5f * search[i] * a;

@@ -243,6 +243,34 @@ int oracle_forward_debug(void* hv, const double* qpos, const double* qvel, const
                        next_qvel);
 }
 
+// ---- exact operation count of one spline rollout batch (instrumented scalar, oracle/counted.h)
+// returns the number of arithmetic operations per simulated env-step averaged over the N x H batch
+double oracle_count_flops(const void* blob, size_t nbytes, const double* state, double time, const double* mocap,
+                          const double* knots, const double* knot_times, int interp, int P, int N, int H,
+                          double* returns_out) {
+  using T = Counted;
+  Model<T> m(blob, nbytes);
+  CostSpec<T> cost(m);
+  Data<T> d(m);
+  const int ds = m.nq + m.nv, nu = m.nu;
+  std::vector<T> st(ds), mc(7 * m.nmocap), ud(m.nuserdata + 1), kt(P);
+  for (int i = 0; i < ds; i++) st[i] = state[i];
+  for (int i = 0; i < 7 * m.nmocap; i++) mc[i] = mocap[i];
+  for (int i = 0; i < P; i++) kt[i] = knot_times[i];
+  Counted::flops = 0;
+  for (int i = 0; i < N; i++) {
+    std::vector<T> kn((size_t)P * nu);
+    for (size_t k = 0; k < kn.size(); k++) kn[k] = knots[(size_t)i * P * nu + k];
+    Trajectory<T> tr;
+    tr.Initialize(ds, nu, m.num_residual, m.num_trace, H);
+    tr.Allocate(H);
+    auto pol = spline_policy<T>(m, kn.data(), kt.data(), P, interp);
+    rollout<T>(tr, pol, m, cost, d, st.data(), T(time), mc.data(), ud.data(), H);
+    if (returns_out) returns_out[i] = (double)tr.total_return;
+  }
+  return (double)Counted::flops / ((double)N * H);
+}
+
 // ---- stand-alone pieces pinned against the reference's known-answer tests
 double oracle_norm(double* g, double* H, const double* x, const double* params, int n, int type) {
   return Norm<double>(g, H, x, params, n, type);

@@ -32,7 +32,7 @@ void find_interval(int* bounds, const T* seq, T value, int length) {
   int lower = upper - 1;
   if (lower < 0) { bounds[0] = bounds[1] = 0; }
   else if (lower > length - 1) { bounds[0] = bounds[1] = length - 1; }
-  else { bounds[0] = std::max(lower, 0); bounds[1] = std::min(upper, length - 1); }
+  else { bounds[0] = mm::max(lower, 0); bounds[1] = mm::min(upper, length - 1); }
 }
 template <class T>
 T fd_slope(T x, const T* xs, const T* ys, int dim, int length, int i) {
@@ -256,8 +256,8 @@ void cost_derivatives(const CostSpec<T>& cs, const T* residual, const T* C, cons
       f += k;
       p += cs.num_norm_parameter[i];
     }
-    if (std::fabs(cs.risk) < (T)kRiskNeutralTolerance) continue;
-    T s = std::exp(cs.risk * c);
+    if (mm::fabs(cs.risk) < (T)kRiskNeutralTolerance) continue;
+    T s = mm::exp(cs.risk * c);
     for (int a = 0; a < n; a++) Cx[a] *= s;
     for (int a = 0; a < m; a++) Cu[a] *= s;
     // note the order: the reference scales cx/cu first and then uses the *scaled* gradients in the outer products
@@ -281,7 +281,7 @@ int box_qp(T* res, T* R, int* index, const T* Hm, const T* g, int n, const T* lo
     for (int i = 0; i < n; i++) { T a = 0; for (int j = 0; j < n; j++) a += Hm[i * n + j] * x[j]; v += x[i] * ((T)0.5 * a + g[i]); }
     return v;
   };
-  for (int i = 0; i < n; i++) res[i] = std::max(lower[i], std::min(upper[i], res[i]));
+  for (int i = 0; i < n; i++) res[i] = mm::max(lower[i], mm::min(upper[i], res[i]));
   T value = value_of(res);
   int nfree = 0;
   for (int iter = 0; iter < maxiter; iter++) {
@@ -320,7 +320,7 @@ int box_qp(T* res, T* R, int* index, const T* Hm, const T* g, int n, const T* lo
     T step = 1, vc = value;
     bool accepted = false;
     while (step > minstep) {
-      for (int i = 0; i < n; i++) cand[i] = std::max(lower[i], std::min(upper[i], res[i] + step * search[i]));
+      for (int i = 0; i < n; i++) cand[i] = mm::max(lower[i], mm::min(upper[i], res[i] + step * search[i]));
       vc = value_of(cand.data());
       if ((vc - value) / (step * sdotg) >= armijo) { accepted = true; break; }
       step *= backtrack;
@@ -344,7 +344,7 @@ int backward_pass(const T* A, const T* B, const T* cx, const T* cu, const T* cxx
   for (int i = 0; i < n; i++) Vx[(size_t)(H - 1) * n + i] = cx[(size_t)(H - 1) * n + i];
   for (int i = 0; i < n * n; i++) Vxx[(size_t)(H - 1) * n * n + i] = cxx[(size_t)(H - 1) * n * n + i];
   std::vector<T> qp_res(m, 0), qp_R(m * m), qp_lower(m), qp_upper(m), Vreg(n * n), Qxu_reg(n * m), Quu_reg(m * m),
-      tmp(n * n), tmp2(std::max(n, m) * std::max(n, m)), L(m * m), sol(m), rhs(m), Qd(m);
+      tmp(n * n), tmp2(mm::max(n, m) * mm::max(n, m)), L(m * m), sol(m), rhs(m), Qd(m);
   std::vector<int> qp_index(m);
   auto AtW = [&](T* out, const T* At, const T* W) {  // out[n][n] = At' * W
     for (int i = 0; i < n; i++)

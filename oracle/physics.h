@@ -13,6 +13,7 @@
 #include <limits>
 #include <vector>
 
+#include "counted.h"
 #include "model.h"
 
 namespace oracle {
@@ -34,7 +35,7 @@ template <class T> inline void cross3(T* r, const T* a, const T* b) {
   T x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
   r[0] = x; r[1] = y; r[2] = z;
 }
-template <class T> inline T norm3(const T* a) { return std::sqrt(dot3(a, a)); }
+template <class T> inline T norm3(const T* a) { return mm::sqrt(dot3(a, a)); }
 template <class T> inline T normalize3(T* a) {
   T n = norm3(a);
   if (n < kMinVal<T>()) { a[0] = 1; a[1] = 0; a[2] = 0; return n; }
@@ -49,7 +50,7 @@ template <class T> inline void quat_mul(T* r, const T* a, const T* b) {
   r[0] = w; r[1] = x; r[2] = y; r[3] = z;
 }
 template <class T> inline void quat_normalize(T* q) {
-  T n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  T n = mm::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
   if (n < kMinVal<T>()) { q[0] = 1; q[1] = q[2] = q[3] = 0; return; }
   q[0] /= n; q[1] /= n; q[2] /= n; q[3] /= n;
 }
@@ -70,8 +71,8 @@ template <class T> inline void rot_vec_T(T* r, const T* m, const T* v) {  // r =
   r[0] = x; r[1] = y; r[2] = z;
 }
 template <class T> inline void axis_angle_quat(T* q, const T* axis, T angle) {
-  T s = std::sin(angle * (T)0.5);
-  q[0] = std::cos(angle * (T)0.5); q[1] = axis[0] * s; q[2] = axis[1] * s; q[3] = axis[2] * s;
+  T s = mm::sin(angle * (T)0.5);
+  q[0] = mm::cos(angle * (T)0.5); q[1] = axis[0] * s; q[2] = axis[1] * s; q[3] = axis[2] * s;
 }
 // q <- q * exp(w*h/2): integrate body-frame angular velocity
 template <class T> inline void quat_integrate(T* q, const T* w, T h) {
@@ -117,13 +118,13 @@ template <class T> inline void make_frame(T* f) {
 }
 // dense in-place Cholesky (lower) of n x n row-major; returns min pivot. A = L L^T
 template <class T> inline T chol_factor(T* A, int n) {
-  T minp = std::numeric_limits<T>::max();
+  T minp = mm::big<T>();
   for (int j = 0; j < n; j++) {
     T s = A[j * n + j];
     for (int k = 0; k < j; k++) s -= A[j * n + k] * A[j * n + k];
-    minp = std::min(minp, s);
+    minp = mm::min(minp, s);
     if (s < kMinVal<T>()) s = kMinVal<T>();
-    T l = std::sqrt(s);
+    T l = mm::sqrt(s);
     A[j * n + j] = l;
     for (int i = j + 1; i < n; i++) {
       T t = A[i * n + j];
@@ -197,7 +198,7 @@ struct Data {
     qfrc_passive.assign(m.nv, 0); qfrc_bias.assign(m.nv, 0); actuator_force.assign(m.nu, 0);
     qfrc_actuator.assign(m.nv, 0); qfrc_smooth.assign(m.nv, 0); qacc_smooth.assign(m.nv, 0);
     qacc.assign(m.nv, 0); qfrc_constraint.assign(m.nv, 0);
-    residual.assign(std::max(m.num_residual, 1), 0);
+    residual.assign(mm::max(m.num_residual, 1), 0);
   }
 };
 
@@ -470,7 +471,7 @@ template <class T>
 int collide_sphere_capsule(RawContact<T>* out, const T* sp, T sr, const T* cp, const T* cm, const T* csize) {
   T axis[3] = {cm[2], cm[5], cm[8]};
   T dv[3] = {sp[0] - cp[0], sp[1] - cp[1], sp[2] - cp[2]};
-  T x = std::max(-csize[1], std::min(csize[1], dot3(dv, axis)));
+  T x = mm::max(-csize[1], mm::min(csize[1], dot3(dv, axis)));
   T q[3] = {cp[0] + axis[0] * x, cp[1] + axis[1] * x, cp[2] + axis[2] * x};
   return collide_sphere_sphere(out, sp, sr, q, csize[0]);
 }
@@ -481,7 +482,7 @@ int collide_sphere_box(RawContact<T>* out, const T* sp, T sr, const T* bp, const
   rot_vec_T(loc, bm, dv);
   bool inside = true;
   for (int c = 0; c < 3; c++) {
-    cl[c] = std::max(-bs[c], std::min(bs[c], loc[c]));
+    cl[c] = mm::max(-bs[c], mm::min(bs[c], loc[c]));
     if (cl[c] != loc[c]) inside = false;
   }
   T nl[3], dist, pl[3];
@@ -493,8 +494,8 @@ int collide_sphere_box(RawContact<T>* out, const T* sp, T sr, const T* bp, const
     for (int c = 0; c < 3; c++) pl[c] = cl[c] - nl[c] * dist * (T)0.5;
   } else {
     // centre inside the box: push out through the nearest face
-    int k = 0; T best = bs[0] - std::fabs(loc[0]);
-    for (int c = 1; c < 3; c++) { T g = bs[c] - std::fabs(loc[c]); if (g < best) { best = g; k = c; } }
+    int k = 0; T best = bs[0] - mm::fabs(loc[0]);
+    for (int c = 1; c < 3; c++) { T g = bs[c] - mm::fabs(loc[c]); if (g < best) { best = g; k = c; } }
     T sgn = loc[k] >= 0 ? (T)1 : (T)-1;
     nl[0] = nl[1] = nl[2] = 0; nl[k] = -sgn;
     dist = -best - sr;
@@ -517,8 +518,8 @@ void collision(const Model<T>& m, Data<T>& d) {
   for (int p = 0; p < m.npair; p++) {
     int g1 = m.pair_geom1[p], g2 = m.pair_geom2[p];
     int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
-    T margin = std::max(m.geom_margin[g1], m.geom_margin[g2]);
-    T gap = std::max(m.geom_gap[g1], m.geom_gap[g2]);
+    T margin = mm::max(m.geom_margin[g1], m.geom_margin[g2]);
+    T gap = mm::max(m.geom_gap[g1], m.geom_gap[g2]);
     const T* p1 = &d.geom_xpos[3 * g1]; const T* p2 = &d.geom_xpos[3 * g2];
     const T* m1 = &d.geom_xmat[9 * g1]; const T* m2 = &d.geom_xmat[9 * g2];
     const T* s1 = &m.geom_size[3 * g1]; const T* s2 = &m.geom_size[3 * g2];
@@ -560,7 +561,7 @@ void collision(const Model<T>& m, Data<T>& d) {
         for (int a = 0; a < 5; a++) c.solimp[a] = m.geom_solimp[5 * gp + a];
         for (int a = 0; a < 3; a++) fr[a] = m.geom_friction[3 * gp + a];
       } else {
-        c.dim = std::max(m.geom_condim[g1], m.geom_condim[g2]);
+        c.dim = mm::max(m.geom_condim[g1], m.geom_condim[g2]);
         T w1 = m.geom_solmix[g1], w2 = m.geom_solmix[g2], mix;
         if (w1 >= kMinVal<T>() && w2 >= kMinVal<T>()) mix = w1 / (w1 + w2);
         else if (w1 < kMinVal<T>() && w2 < kMinVal<T>()) mix = (T)0.5;
@@ -569,12 +570,12 @@ void collision(const Model<T>& m, Data<T>& d) {
         if (r1[0] > 0 && r2[0] > 0) {
           for (int a = 0; a < 2; a++) c.solref[a] = mix * r1[a] + (1 - mix) * r2[a];
         } else {
-          for (int a = 0; a < 2; a++) c.solref[a] = std::min(r1[a], r2[a]);
+          for (int a = 0; a < 2; a++) c.solref[a] = mm::min(r1[a], r2[a]);
         }
         for (int a = 0; a < 5; a++) c.solimp[a] = mix * m.geom_solimp[5 * g1 + a] + (1 - mix) * m.geom_solimp[5 * g2 + a];
-        for (int a = 0; a < 3; a++) fr[a] = std::max(f1[a], f2[a]);
+        for (int a = 0; a < 3; a++) fr[a] = mm::max(f1[a], f2[a]);
       }
-      for (int a = 0; a < 3; a++) fr[a] = std::max(fr[a], (T)kMinMu);
+      for (int a = 0; a < 3; a++) fr[a] = mm::max(fr[a], (T)kMinMu);
       c.friction[0] = c.friction[1] = fr[0]; c.friction[2] = fr[1]; c.friction[3] = c.friction[4] = fr[2];
       c.mu = 0; c.efc_address = -1;
       d.contact.push_back(c);
@@ -606,11 +607,11 @@ void jac_point(const Model<T>& m, const Data<T>& d, int b, const T* point, T* ja
 
 template <class T>
 void get_impedance(const T* solimp_in, T pos, T margin, T* imp, T* impP) {
-  T dmin = std::min((T)kMaxImp, std::max((T)kMinImp, solimp_in[0]));
-  T dmax = std::min((T)kMaxImp, std::max((T)kMinImp, solimp_in[1]));
-  T width = std::max((T)0, solimp_in[2]);
-  T mid = std::min((T)kMaxImp, std::max((T)kMinImp, solimp_in[3]));
-  T power = std::max((T)1, solimp_in[4]);
+  T dmin = mm::min((T)kMaxImp, mm::max((T)kMinImp, solimp_in[0]));
+  T dmax = mm::min((T)kMaxImp, mm::max((T)kMinImp, solimp_in[1]));
+  T width = mm::max((T)0, solimp_in[2]);
+  T mid = mm::min((T)kMaxImp, mm::max((T)kMinImp, solimp_in[3]));
+  T power = mm::max((T)1, solimp_in[4]);
   if (dmin == dmax || width <= kMinVal<T>()) { *imp = (T)0.5 * (dmin + dmax); *impP = 0; return; }
   T x = (pos - margin) / width;
   if (x < 0) x = -x;
@@ -618,8 +619,8 @@ void get_impedance(const T* solimp_in, T pos, T margin, T* imp, T* impP) {
   if (x == 0) { *imp = dmin; *impP = 0; return; }
   T y;
   if (power == 1) y = x;
-  else if (x <= mid) y = std::pow(x, power) / std::pow(mid, power - 1);
-  else y = 1 - std::pow(1 - x, power) / std::pow(1 - mid, power - 1);
+  else if (x <= mid) y = mm::pow(x, power) / mm::pow(mid, power - 1);
+  else y = 1 - mm::pow(1 - x, power) / mm::pow(1 - mid, power - 1);
   *imp = dmin + y * (dmax - dmin);
   *impP = 0;
 }
@@ -703,28 +704,28 @@ void make_constraint(const Model<T>& m, Data<T>& d) {
     }
     T imp, impP;
     get_impedance(solimp, d.efc_pos[i], d.efc_margin[i], &imp, &impP);
-    T dmax = std::min((T)kMaxImp, std::max((T)kMinImp, solimp[1]));
+    T dmax = mm::min((T)kMaxImp, mm::max((T)kMinImp, solimp[1]));
     T K, B;
     if (solref[0] > 0) {
       T tc = solref[0], dr = solref[1];
-      if (!m.disable_refsafe) tc = std::max(tc, 2 * m.timestep);
-      K = 1 / std::max(kMinVal<T>(), dmax * dmax * tc * tc * dr * dr);
-      B = 2 / std::max(kMinVal<T>(), dmax * tc);
+      if (!m.disable_refsafe) tc = mm::max(tc, 2 * m.timestep);
+      K = 1 / mm::max(kMinVal<T>(), dmax * dmax * tc * tc * dr * dr);
+      B = 2 / mm::max(kMinVal<T>(), dmax * tc);
     } else {
-      K = -solref[0] / std::max(kMinVal<T>(), dmax * dmax);
-      B = -solref[1] / std::max(kMinVal<T>(), dmax);
+      K = -solref[0] / mm::max(kMinVal<T>(), dmax * dmax);
+      B = -solref[1] / mm::max(kMinVal<T>(), dmax);
     }
     if (friction_row) K = 0;
     d.efc_KBIP[4 * i] = K; d.efc_KBIP[4 * i + 1] = B; d.efc_KBIP[4 * i + 2] = imp; d.efc_KBIP[4 * i + 3] = impP;
-    d.efc_R[i] = std::max(kMinVal<T>(), (1 - imp) * d.efc_diagApprox[i] / imp);
+    d.efc_R[i] = mm::max(kMinVal<T>(), (1 - imp) * d.efc_diagApprox[i] / imp);
   }
   // friction-cone adjustment of R (elliptic): R[1] = R[0]/impratio, R[j]*mu[j]^2 constant
   for (int ci = 0; ci < d.ncon; ci++) {
     Contact<T>& c = d.contact[ci];
     if (c.efc_address < 0 || c.dim == 1) continue;
     int a = c.efc_address;
-    d.efc_R[a + 1] = d.efc_R[a] / std::max(kMinVal<T>(), m.impratio);
-    c.mu = c.friction[0] * std::sqrt(d.efc_R[a + 1] / d.efc_R[a]);
+    d.efc_R[a + 1] = d.efc_R[a] / mm::max(kMinVal<T>(), m.impratio);
+    c.mu = c.friction[0] * mm::sqrt(d.efc_R[a + 1] / d.efc_R[a]);
     for (int j = 1; j < c.dim - 1; j++)
       d.efc_R[a + j + 1] = d.efc_R[a + 1] * c.friction[0] * c.friction[0] / (c.friction[j] * c.friction[j]);
   }
@@ -768,7 +769,7 @@ void com_vel(const Model<T>& m, Data<T>& d) {
   for (int b = m.nbody - 1; b > 0; b--)
     for (int c = 0; c < 3; c++) d.subtree_linvel[3 * m.body_parentid[b] + c] += d.subtree_linvel[3 * b + c];
   for (int b = 0; b < m.nbody; b++)
-    for (int c = 0; c < 3; c++) d.subtree_linvel[3 * b + c] /= std::max(kMinVal<T>(), m.body_subtreemass[b]);
+    for (int c = 0; c < 3; c++) d.subtree_linvel[3 * b + c] /= mm::max(kMinVal<T>(), m.body_subtreemass[b]);
 }
 
 template <class T>
@@ -817,7 +818,7 @@ void actuation(const Model<T>& m, Data<T>& d) {
   for (int i = 0; i < m.nu; i++) {
     T ctrl = d.ctrl[i];
     if (m.actuator_ctrllimited[i])
-      ctrl = std::max(m.actuator_ctrlrange[2 * i], std::min(m.actuator_ctrlrange[2 * i + 1], ctrl));
+      ctrl = mm::max(m.actuator_ctrlrange[2 * i], mm::min(m.actuator_ctrlrange[2 * i + 1], ctrl));
     int j = m.actuator_trnid[i];
     T gear = m.actuator_gear[i];
     T force = m.actuator_gainprm[3 * i] * ctrl;
@@ -826,7 +827,7 @@ void actuation(const Model<T>& m, Data<T>& d) {
       force += m.actuator_biasprm[3 * i] + m.actuator_biasprm[3 * i + 1] * length + m.actuator_biasprm[3 * i + 2] * vel;
     }
     if (m.actuator_forcelimited[i])
-      force = std::max(m.actuator_forcerange[2 * i], std::min(m.actuator_forcerange[2 * i + 1], force));
+      force = mm::max(m.actuator_forcerange[2 * i], mm::min(m.actuator_forcerange[2 * i + 1], force));
     d.actuator_force[i] = force;
     d.qfrc_actuator[m.jnt_dofadr[j]] += gear * force;
   }
@@ -864,7 +865,7 @@ T update_constraint(const Model<T>& m, Data<T>& d, const std::vector<T>& jar, T*
       u[0] = jar[i] * mu;
       T tt = 0;
       for (int j = 1; j < dim; j++) { u[j] = jar[i + j] * c.friction[j - 1]; tt += u[j] * u[j]; }
-      T N = u[0], Tn = std::sqrt(tt);
+      T N = u[0], Tn = mm::sqrt(tt);
       if (N >= mu * Tn || (Tn <= 0 && N >= 0)) {            // top zone: nothing
         for (int j = 0; j < dim; j++) { d.efc_force[i + j] = 0; d.efc_state[i + j] = STATE_SATISFIED; }
       } else if (mu * N + Tn <= 0 || (Tn <= 0 && N < 0)) {   // bottom zone: quadratic
@@ -950,7 +951,7 @@ LsPoint<T> ls_eval(const Model<T>& m, const Data<T>& d, const SolverCtx<T>& s, c
       }
       T N = U0 + alpha * V0;
       T Tsqr = UU + alpha * (2 * UV + alpha * VV);
-      T Tn = Tsqr <= 0 ? (T)0 : std::sqrt(Tsqr);
+      T Tn = Tsqr <= 0 ? (T)0 : mm::sqrt(Tsqr);
       if (N >= mu * Tn || (Tn <= 0 && N >= 0)) {
         // nothing
       } else if (mu * N + Tn <= 0 || (Tn <= 0 && N < 0)) {
@@ -978,16 +979,16 @@ T line_search(const Model<T>& m, const Data<T>& d, const SolverCtx<T>& s, const 
   int nv = m.nv;
   T snorm = 0;
   for (int i = 0; i < nv; i++) snorm += s.search[i] * s.search[i];
-  snorm = std::sqrt(snorm);
+  snorm = mm::sqrt(snorm);
   if (snorm < kMinVal<T>()) return 0;
   LsPoint<T> p0 = ls_eval(m, d, s, qg, (T)0);
   // derivative tolerance; the relative floor (64 eps) guards reduced precision and is inactive in fp64
-  T gtol = std::max(std::max(m.tolerance, kTolFloor<T>()) * m.ls_tolerance * snorm * scale_inv,
-                    64 * std::numeric_limits<T>::epsilon() * std::fabs(p0.d1));
+  T gtol = mm::max(mm::max(m.tolerance, kTolFloor<T>()) * m.ls_tolerance * snorm * scale_inv,
+                    64 * mm::eps<T>() * mm::fabs(p0.d1));
   if (p0.d2 <= kMinVal<T>()) return 0;
   LsPoint<T> p1 = ls_eval(m, d, s, qg, -p0.d1 / p0.d2);
   if (p0.cost < p1.cost) p1 = p0;
-  if (std::fabs(p1.d1) < gtol) return p1.alpha;
+  if (mm::fabs(p1.d1) < gtol) return p1.alpha;
   // Newton iterations on one side until the derivative changes sign
   int iter = 0;
   LsPoint<T> p2 = p1;
@@ -997,7 +998,7 @@ T line_search(const Model<T>& m, const Data<T>& d, const SolverCtx<T>& s, const 
     p2 = p1;
     if (p1.d2 <= kMinVal<T>()) break;
     p1 = ls_eval(m, d, s, qg, p1.alpha - p1.d1 / p1.d2);
-    if (std::fabs(p1.d1) < gtol) return p1.cost <= p0.cost ? p1.alpha : (T)0;
+    if (mm::fabs(p1.d1) < gtol) return p1.cost <= p0.cost ? p1.alpha : (T)0;
     if ((p1.d1 > 0) != (p2.d1 > 0)) { bracket = true; break; }
   }
   if (!bracket) return p1.cost < p0.cost ? p1.alpha : (T)0;
@@ -1005,13 +1006,13 @@ T line_search(const Model<T>& m, const Data<T>& d, const SolverCtx<T>& s, const 
   LsPoint<T> lo = p1.d1 < 0 ? p1 : p2, hi = p1.d1 < 0 ? p2 : p1;
   while (iter < m.ls_iterations) {
     iter++;
-    const LsPoint<T>& from = std::fabs(lo.d1) < std::fabs(hi.d1) ? lo : hi;
+    const LsPoint<T>& from = mm::fabs(lo.d1) < mm::fabs(hi.d1) ? lo : hi;
     T a = from.d2 > kMinVal<T>() ? from.alpha - from.d1 / from.d2 : (T)0.5 * (lo.alpha + hi.alpha);
-    T amin = std::min(lo.alpha, hi.alpha), amax = std::max(lo.alpha, hi.alpha);
+    T amin = mm::min(lo.alpha, hi.alpha), amax = mm::max(lo.alpha, hi.alpha);
     if (!(a > amin && a < amax)) a = (T)0.5 * (lo.alpha + hi.alpha);
     if (a == lo.alpha || a == hi.alpha) break;
     LsPoint<T> pm = ls_eval(m, d, s, qg, a);
-    if (std::fabs(pm.d1) < gtol) return pm.cost <= p0.cost ? pm.alpha : (T)0;
+    if (mm::fabs(pm.d1) < gtol) return pm.cost <= p0.cost ? pm.alpha : (T)0;
     if (pm.d1 < 0) lo = pm; else hi = pm;
   }
   const LsPoint<T>& best = lo.cost < hi.cost ? lo : hi;
@@ -1056,7 +1057,7 @@ void solve_constraints(const Model<T>& m, Data<T>& d) {
   } else {
     d.qacc = d.qacc_smooth;
   }
-  T scale_inv = m.meaninertia * (T)std::max(1, nv);  // 1/scale
+  T scale_inv = m.meaninertia * (T)mm::max(1, nv);  // 1/scale
   auto gradient_and_direction = [&]() {
     // grad = Ma - qfrc_smooth - J^T force;  search = -H^-1 grad
     for (int i = 0; i < nv; i++) {
@@ -1087,8 +1088,8 @@ void solve_constraints(const Model<T>& m, Data<T>& d) {
     d.solver_niter = iter + 1;
     T gn = 0;
     for (int i = 0; i < nv; i++) gn += s.grad[i] * s.grad[i];
-    T improvement = (old - s.cost) / scale_inv, gradient = std::sqrt(gn) / scale_inv;
-    const T tol = std::max(m.tolerance, kTolFloor<T>());
+    T improvement = (old - s.cost) / scale_inv, gradient = mm::sqrt(gn) / scale_inv;
+    const T tol = mm::max(m.tolerance, kTolFloor<T>());
     if (improvement < tol || gradient < tol) break;
   }
   for (int i = 0; i < nv; i++) {
@@ -1129,7 +1130,7 @@ void forward(const Model<T>& m, Data<T>& d, ResidualCallback<T> cb) {
 template <class T>
 bool bad(const std::vector<T>& v) {
   for (T x : v)
-    if (!(std::fabs(x) < (T)kMaxVal)) return true;  // catches NaN and |x| >= mjMAXVAL
+    if (!(mm::fabs(x) < (T)kMaxVal)) return true;  // catches NaN and |x| >= mjMAXVAL
   return false;
 }
 

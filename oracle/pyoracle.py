@@ -179,3 +179,15 @@ def backward_pass(A, B, cx, cu, cxx, cxu, cuu, actions, ctrlrange, mu=0.0, reg_t
                                         _p(o["Qxx"]), _p(o["Qxu"]), _p(o["Quu"]))
     o["status"] = status
     return o
+
+
+def count_flops(blob: bytes, state, time, mocap, knots, knot_times, interp, H):
+    """Exact arithmetic-operation count per simulated env-step (instrumented scalar, oracle/counted.h)."""
+    knots = _d(knots)
+    N, P, nu = knots.shape
+    st, mc, kt = _d(state), _d(mocap), _d(knot_times)
+    ret = np.zeros(N)
+    lib().oracle_count_flops.restype = C.c_double
+    f = lib().oracle_count_flops(blob, C.c_size_t(len(blob)), _p(st), C.c_double(time), _p(mc), _p(knots), _p(kt),
+                                 int(interp), P, N, int(H), _p(ret))
+    return float(f), ret

@@ -36,14 +36,14 @@ T ray_geom(const T* gpos, const T* gmat, const T* size, int type, const T* pnt, 
     T x = -lp[2] / lv[2];
     if (x < 0) return -1;
     T p0 = lp[0] + x * lv[0], p1 = lp[1] + x * lv[1];
-    if ((size[0] <= 0 || std::fabs(p0) <= size[0]) && (size[1] <= 0 || std::fabs(p1) <= size[1])) return x;
+    if ((size[0] <= 0 || mm::fabs(p0) <= size[0]) && (size[1] <= 0 || mm::fabs(p1) <= size[1])) return x;
     return -1;
   }
   if (type == GEOM_SPHERE) {
     T a = dot3(lv, lv), b = dot3(lv, lp), c = dot3(lp, lp) - size[0] * size[0];
     T det = b * b - a * c;
     if (det < 0 || a < kMinVal<T>()) return -1;
-    T sq = std::sqrt(det);
+    T sq = mm::sqrt(det);
     T x0 = (-b - sq) / a, x1 = (-b + sq) / a;
     if (x0 >= 0) return x0;
     if (x1 >= 0) return x1;
@@ -52,13 +52,13 @@ T ray_geom(const T* gpos, const T* gmat, const T* size, int type, const T* pnt, 
   if (type == GEOM_BOX) {
     T best = -1;
     for (int i = 0; i < 3; i++) {
-      if (std::fabs(lv[i]) <= kMinVal<T>()) continue;
+      if (mm::fabs(lv[i]) <= kMinVal<T>()) continue;
       for (int s = -1; s <= 1; s += 2) {
         T x = ((T)s * size[i] - lp[i]) / lv[i];
         if (x < 0) continue;
         int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
         T q1 = lp[i1] + x * lv[i1], q2 = lp[i2] + x * lv[i2];
-        if (std::fabs(q1) <= size[i1] && std::fabs(q2) <= size[i2] && (best < 0 || x < best)) best = x;
+        if (mm::fabs(q1) <= size[i1] && mm::fabs(q2) <= size[i2] && (best < 0 || x < best)) best = x;
       }
     }
     return best;
@@ -88,7 +88,7 @@ void sub_quat(T* res, const T* qa, const T* qb) {  // qb * quat(res) = qa
   T axis[3] = {qd[1], qd[2], qd[3]};
   T s = norm3(axis);
   if (s < kMinVal<T>()) { axis[0] = 1; axis[1] = axis[2] = 0; } else { axis[0] /= s; axis[1] /= s; axis[2] /= s; }
-  T speed = 2 * std::atan2(s, qd[0]);
+  T speed = 2 * mm::atan2(s, qd[0]);
   if (speed > (T)M_PI) speed -= 2 * (T)M_PI;
   for (int c = 0; c < 3; c++) res[c] = axis[c] * speed;
 }
@@ -107,7 +107,7 @@ void residual_particle_copy(const Model<T>& m, Data<T>& d, T* r) {
 }
 template <class T>
 void residual_cartpole(const Model<T>& m, Data<T>& d, T* r) {
-  r[0] = std::cos(d.qpos[1]) - 1;
+  r[0] = mm::cos(d.qpos[1]) - 1;
   r[1] = d.qpos[0] - m.parameters[0];
   r[2] = d.qvel[1];
   r[3] = d.ctrl[0];
@@ -125,13 +125,13 @@ struct QuadrupedFn {
   int GetGait() const { return mode() == kModeBiped ? 2 : (int)S[QS_GAIT]; }
   T StepHeight(T time, T footphase, T duty_ratio) const {
     const T pi = (T)M_PI;
-    T angle = std::fmod(time + pi - footphase, 2 * pi) - pi;
+    T angle = mm::fmod(time + pi - footphase, 2 * pi) - pi;
     T value = 0;
     if (duty_ratio < 1) {
       angle *= (T)0.5 / (1 - duty_ratio);
-      value = std::cos(std::max(-pi / 2, std::min(pi / 2, angle)));
+      value = mm::cos(mm::max(-pi / 2, mm::min(pi / 2, angle)));
     }
-    return std::fabs(value) < (T)1e-6 ? (T)0 : value;
+    return mm::fabs(value) < (T)1e-6 ? (T)0 : value;
   }
   void FootStep(T* step, T time, int gait) const {
     static const double kGaitPhase[5][4] = {{0, 0, 0, 0}, {0, 0.75, 0.5, 0.25}, {0, 0.5, 0.5, 0},
@@ -142,15 +142,15 @@ struct QuadrupedFn {
   void Walk(T* pos, T time) const {
     const T* heading = S + QS_HEADING;
     const T* position = S + QS_POSITION;
-    if (std::fabs(S[QS_ANGVEL]) < (T)0.01) {
+    if (mm::fabs(S[QS_ANGVEL]) < (T)0.01) {
       T fw[2] = {heading[0], heading[1]};
-      T n = std::sqrt(fw[0] * fw[0] + fw[1] * fw[1]);
+      T n = mm::sqrt(fw[0] * fw[0] + fw[1] * fw[1]);
       if (n < kMinVal<T>()) { fw[0] = 1; fw[1] = 0; } else { fw[0] /= n; fw[1] /= n; }
       pos[0] = position[0] + heading[0] + time * S[QS_SPEED] * fw[0];
       pos[1] = position[1] + heading[1] + time * S[QS_SPEED] * fw[1];
     } else {
       T angle = time * S[QS_ANGVEL];
-      T c = std::cos(angle), s = std::sin(angle);
+      T c = mm::cos(angle), s = mm::sin(angle);
       pos[0] = c * heading[0] - s * heading[1] + position[0];
       pos[1] = s * heading[0] + c * heading[1] + position[1];
     }
@@ -264,12 +264,12 @@ struct QuadrupedFn {
       if (!ok) d.warning = true;  // reference: mju_error("no group 0 geom detected by raycast")
       T height_target = ground_height + kFootRadius + step[f];
       T height_difference = foot_pos[f][2] - height_target;
-      if (cur == kModeScramble) height_difference = std::min((T)0, height_difference);
+      if (cur == kModeScramble) height_difference = mm::min((T)0, height_difference);
       residual[counter++] = step[f] ? height_difference : (T)0;
     }
     // ---------- Balance
     const T* comvel = &d.subtree_linvel[3 * torso];
-    T fall_time = std::sqrt(2 * height_goal / (T)9.81);
+    T fall_time = mm::sqrt(2 * height_goal / (T)9.81);
     residual[counter++] = compos[0] + comvel[0] * fall_time - avg[0];
     residual[counter++] = compos[1] + comvel[1] * fall_time - avg[1];
     // ---------- Effort
@@ -302,11 +302,11 @@ struct QuadrupedFn {
       th[0] = hs * torso_xmat[2];
       th[1] = hs * torso_xmat[5];
     }
-    T n = std::sqrt(th[0] * th[0] + th[1] * th[1]);
+    T n = mm::sqrt(th[0] * th[0] + th[1] * th[1]);
     if (n < kMinVal<T>()) { th[0] = 1; th[1] = 0; } else { th[0] /= n; th[1] /= n; }
     T heading_goal = param(QI_PARAM_HEADING);
-    residual[counter++] = th[0] - std::cos(heading_goal);
-    residual[counter++] = th[1] - std::sin(heading_goal);
+    residual[counter++] = th[0] - mm::cos(heading_goal);
+    residual[counter++] = th[1] - mm::sin(heading_goal);
     // ---------- Angular momentum (sensor "torso_angmom" is declared subtreelinvel: task_flat.xml:144)
     for (int c = 0; c < 3; c++) residual[counter++] = comvel[c];
   }

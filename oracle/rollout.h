@@ -60,7 +60,7 @@ void update_return(Trajectory<T>& tr, const CostSpec<T>& cost) {
     tr.costs[t] = CostValue(cost, &tr.residual[t * tr.dim_residual]);
     tr.total_return += tr.costs[t];
   }
-  tr.total_return /= (T)std::max(tr.horizon, 1);
+  tr.total_return /= (T)mm::max(tr.horizon, 1);
 }
 
 // policy(action, state, time, step_index)

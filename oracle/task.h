@@ -8,6 +8,7 @@
 #include <cmath>
 #include <vector>
 
+#include "counted.h"
 #include "model.h"
 
 namespace oracle {
@@ -37,14 +38,14 @@ T Norm(T* g, T* H, const T* x, const T* params, int n, int type) {
     case kL22: {
       T c = 0;
       for (int i = 0; i < n; i++) c += x[i] * x[i];
-      T a = std::pow(c, q / 2) + std::pow(p, q);
-      T s = std::pow(a, 1 / q);
+      T a = mm::pow(c, q / 2) + mm::pow(p, q);
+      T s = mm::pow(a, 1 / q);
       y = s - p;
-      T dd = std::pow(c, q / 2 - 1);
+      T dd = mm::pow(c, q / 2 - 1);
       T b = s / a * dd;
       if (g) for (int i = 0; i < n; i++) g[i] = b * x[i];
       if (H) {
-        c = (1 - q) * dd / a + (q - 2) / std::max(c, (T)1e-15);
+        c = (1 - q) * dd / a + (q - 2) / mm::max(c, (T)1e-15);
         for (int i = 0; i < n; i++)
           for (int j = 0; j < n; j++) H[i + j * n] = b * ((i == j ? (T)1 : (T)0) + x[i] * x[j] * c);
       }
@@ -53,7 +54,7 @@ T Norm(T* g, T* H, const T* x, const T* params, int n, int type) {
     case kL2: {
       T dsum = 0;
       for (int i = 0; i < n; i++) dsum += x[i] * x[i];
-      T s = std::sqrt(dsum + p * p);
+      T s = mm::sqrt(dsum + p * p);
       y = s - p;
       if (g) for (int i = 0; i < n; i++) g[i] = s ? x[i] / s : (T)0;
       if (H && s)
@@ -63,22 +64,22 @@ T Norm(T* g, T* H, const T* x, const T* params, int n, int type) {
     }
     case kCosh:
       for (int i = 0; i < n; i++) {
-        y += p * p * (std::cosh(x[i] / p) - 1);
-        if (g) g[i] = p * std::sinh(x[i] / p);
-        if (H) H[i * n + i] = std::cosh(x[i] / p);
+        y += p * p * (mm::cosh(x[i] / p) - 1);
+        if (g) g[i] = p * mm::sinh(x[i] / p);
+        if (H) H[i * n + i] = mm::cosh(x[i] / p);
       }
       break;
     case kPowerLoss:
       for (int i = 0; i < n; i++) {
-        T s = std::fabs(x[i]);
-        y += std::pow(s, p);
-        if (g) g[i] = (x[i] > 0 ? 1 : (x[i] < 0 ? -1 : 0)) * p * std::pow(s, p - 1);
-        if (H) H[i * n + i] = (p - 1) * p * std::pow(s, p - 2);
+        T s = mm::fabs(x[i]);
+        y += mm::pow(s, p);
+        if (g) g[i] = (x[i] > 0 ? 1 : (x[i] < 0 ? -1 : 0)) * p * mm::pow(s, p - 1);
+        if (H) H[i * n + i] = (p - 1) * p * mm::pow(s, p - 2);
       }
       break;
     case kSmoothAbsLoss:
       for (int i = 0; i < n; i++) {
-        T s = std::sqrt(x[i] * x[i] + p * p);
+        T s = mm::sqrt(x[i] * x[i] + p * p);
         y += s - p;
         if (g) g[i] = s ? x[i] / s : (T)0;
         if (H) H[n * i + i] = s ? (1 - g[i] * g[i]) / s : (T)0;
@@ -86,12 +87,12 @@ T Norm(T* g, T* H, const T* x, const T* params, int n, int type) {
       break;
     case kSmoothAbs2Loss:
       for (int i = 0; i < n; i++) {
-        T a = std::fabs(x[i]);
-        T dd = std::pow(a, q);
-        T e = dd + std::pow(p, q);
-        T s = std::pow(e, 1 / q);
+        T a = mm::fabs(x[i]);
+        T dd = mm::pow(a, q);
+        T e = dd + mm::pow(p, q);
+        T s = mm::pow(e, 1 / q);
         y += s - p;
-        T c = s * std::pow(a, q - 2) / e;
+        T c = s * mm::pow(a, q - 2) / e;
         if (g) g[i] = c * x[i];
         if (H) H[i * n + i] = c * (q - 1) * (1 - dd / e);
       }
@@ -99,8 +100,8 @@ T Norm(T* g, T* H, const T* x, const T* params, int n, int type) {
     case kRectifyLoss:
       for (int i = 0; i < n; i++) {
         if (p > 0) {
-          T s = std::exp(x[i] / p);
-          y += p * std::log(1 + s);
+          T s = mm::exp(x[i] / p);
+          y += p * mm::log(1 + s);
           if (g) g[i] = s / (1 + s);
           if (H) H[i * n + i] = s / (p * (1 + s) * (1 + s));
         } else {
@@ -139,12 +140,12 @@ void CostTerms(const CostSpec<T>& c, T* terms, const T* residual, bool weighted)
 
 template <class T>
 T CostValue(const CostSpec<T>& c, const T* residual) {
-  std::vector<T> terms(std::max(c.num_term, 1));
+  std::vector<T> terms(mm::max(c.num_term, 1));
   CostTerms(c, terms.data(), residual, true);
   T cost = 0;
   for (int i = 0; i < c.num_term; i++) cost += terms[i];
-  if (std::fabs(c.risk) < (T)kRiskNeutralTolerance) return cost;
-  return (std::exp(c.risk * cost) - 1) / c.risk;
+  if (mm::fabs(c.risk) < (T)kRiskNeutralTolerance) return cost;
+  return (mm::exp(c.risk * cost) - 1) / c.risk;
 }
 
 // ---- time spline (zero / linear / cubic-Hermite with finite-difference slopes)
@@ -186,7 +187,7 @@ void spline_sample(T* out, const T* times, const T* values, int P, int dim, int 
 
 template <class T>
 void clamp_ctrl(T* x, const T* bounds, int n) {
-  for (int i = 0; i < n; i++) x[i] = std::max(bounds[2 * i], std::min(bounds[2 * i + 1], x[i]));
+  for (int i = 0; i < n; i++) x[i] = mm::max(bounds[2 * i], mm::min(bounds[2 * i + 1], x[i]));
 }
 
 }  // namespace oracle
