@@ -135,8 +135,8 @@ int mjpc_b200_step_debug(mjpc_b200_t* h, const float* qpos, const float* qvel, c
                          const float* mocap, double time, const float* warmstart, float* qacc, float* residual,
                          float* next_qpos, float* next_qvel, float* qM, float* efc_force, int* counts);
 
-/* Per-candidate execution statistics of the last rollout, stats [N][4] = {SM cycles, Newton iterations summed over
- * steps, contacts summed over steps, constraint rows summed over steps} (profiling aid). */
+/* Per-candidate execution statistics of the last rollout, stats [N][12] = {SM cycles, Newton iterations, contacts,
+ * constraint rows (summed over steps), 8 per-phase cycle counters (zero unless built with -DMJPC_PHASE_TIMING)}. */
 int mjpc_b200_fetch_stats(mjpc_b200_t* h, int64_t* stats);
 
 /* Number of CUDA kernels this handle has launched so far (bench.py reports it as gpu_launches). */

@@ -79,7 +79,15 @@ struct Ctx {
   int ncon, nefc, nitem, niter, nlim;
   int warn;
   float time;
+#ifdef MJPC_PHASE_TIMING
+  long long tph[8], tlast;   // profiling build only: SM cycles per pipeline phase
+#endif
 };
+#ifdef MJPC_PHASE_TIMING
+#define PHASE(c, i) do { const long long t_ = clock64(); (c).tph[i] += t_ - (c).tlast; (c).tlast = t_; } while (0)
+#else
+#define PHASE(c, i) do { } while (0)
+#endif
 #define CM(c) (*reinterpret_cast<const DevModel*>(g_smem + (c).hdr))
 #define CL(c) (*reinterpret_cast<const DevLayout*>(g_smem + (c).lay))
 #define MF(n) (g_smem + CM(c).fo[F_##n])

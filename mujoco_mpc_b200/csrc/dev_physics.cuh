@@ -1435,15 +1435,21 @@ __device__ __forceinline__ bool k_bad(Ctx& c, const float* v, int n) {
 
 // everything of mj_forward up to (not including) the sensor/residual callback
 __device__ __noinline__ void k_forward(Ctx& c) {
+  PHASE(c, 7);            // everything between two forward passes (policy, residual, cost, Euler, output)
   k_kinematics(c);
   k_com_pos(c);
   k_crb(c);
+  PHASE(c, 0);
   k_collision(c);
+  PHASE(c, 1);
   k_make_constraint(c);
+  PHASE(c, 2);
   k_com_vel(c);
   k_smooth_forces(c);
   k_reference(c);
+  PHASE(c, 3);
   k_solve(c);
+  PHASE(c, 4);
 }
 
 // semi-implicit Euler with implicit joint damping

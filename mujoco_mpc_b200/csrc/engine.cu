@@ -229,7 +229,7 @@ int mjpc_b200_create(const mjpc_model_blob* model, int max_candidates, int max_h
   CUDA_TRY(dalloc(&h->d_states, N * H * ds)); CUDA_TRY(dalloc(&h->d_actions, N * H * nu));
   CUDA_TRY(dalloc(&h->d_times, N * H)); CUDA_TRY(dalloc(&h->d_residual, N * H * nr));
   CUDA_TRY(dalloc(&h->d_costs, N * H)); CUDA_TRY(dalloc(&h->d_trace, N * H * 3 * (size_t)M.num_trace));
-  CUDA_TRY(dalloc(&h->d_returns, N)); CUDA_TRY(dalloc(&h->d_failure, N)); CUDA_TRY(dalloc(&h->d_order, N)); CUDA_TRY(dalloc(&h->d_stats, 4 * N));
+  CUDA_TRY(dalloc(&h->d_returns, N)); CUDA_TRY(dalloc(&h->d_failure, N)); CUDA_TRY(dalloc(&h->d_order, N)); CUDA_TRY(dalloc(&h->d_stats, 12 * N));
   CUDA_TRY(dalloc(&h->d_dbg, 4 * ds + 2 * nu + (size_t)M.nv * M.nv + nr + 256 + 64 + 7 * (size_t)M.nmocap));
   h->h_in_floats = ds + 7 * M.nmocap + M.task_state_size + N * h->maxP * nu + h->maxP + H * (nu + ds + 1 + nu * n + nu) + N + 64;
   CUDA_TRY(cudaMallocHost((void**)&h->h_in, h->h_in_floats * 4));
@@ -458,7 +458,7 @@ int mjpc_b200_fetch_stats(mjpc_b200_t* h, int64_t* stats) {
   if (!h || !stats || h->lastN < 1) return fail(MJPC_B200_ERR_BAD_ARGUMENT, "fetch_stats: nothing to fetch");
   CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
-  CUDA_TRY(cudaMemcpy(stats, h->d_stats, (size_t)h->lastN * 4 * sizeof(long long), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(stats, h->d_stats, (size_t)h->lastN * 12 * sizeof(long long), cudaMemcpyDeviceToHost));
   return 0;
 }
 

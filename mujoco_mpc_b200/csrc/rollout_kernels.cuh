@@ -31,7 +31,7 @@ struct RolloutArgs {
   double time0;
   float* states; float* actions; double* times; float* residual; float* costs; float* trace;
   float* returns; unsigned char* failure;
-  long long* stats;         // [N][4]: cycles, Newton iterations, contacts summed over steps, constraint rows summed
+  long long* stats;         // [N][12]: cycles, Newton iterations, contacts, constraint rows (summed over steps), 8 phase timers
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -80,6 +80,10 @@ __device__ __forceinline__ void init_ctx(Ctx& c, const DevModel* M, const DevLay
   c.dbase = data0 + warp * L->total;
   c.lane = lane;
   c.ncon = 0; c.nefc = 0; c.nitem = 0; c.niter = 0; c.nlim = 0; c.warn = 0; c.time = 0.f;
+#ifdef MJPC_PHASE_TIMING
+  for (int k = 0; k < 8; k++) c.tph[k] = 0;
+  c.tlast = clock64();
+#endif
 }
 
 // write the trace points (GetTraces, mjpc/utilities.cc:268-285)
@@ -170,8 +174,15 @@ extern "C" __global__ void __launch_bounds__(128) rollout_kernel(const __grid_co
     A.returns[cand] = failed ? 1.0e6f : total / (float)max(H, 1);
     A.failure[cand] = failed ? 1 : 0;
     if (A.stats) {
-      A.stats[4 * cand] = clock64() - clk0; A.stats[4 * cand + 1] = n_newton;
-      A.stats[4 * cand + 2] = n_con; A.stats[4 * cand + 3] = n_efc;
+      A.stats[12 * cand] = clock64() - clk0; A.stats[12 * cand + 1] = n_newton;
+      A.stats[12 * cand + 2] = n_con; A.stats[12 * cand + 3] = n_efc;
+      for (int k = 0; k < 8; k++) {
+#ifdef MJPC_PHASE_TIMING
+        A.stats[12 * cand + 4 + k] = c.tph[k];
+#else
+        A.stats[12 * cand + 4 + k] = 0;
+#endif
+      }
     }
   }
 }

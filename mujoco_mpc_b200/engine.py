@@ -240,7 +240,7 @@ class Engine:
         return dict(K=K, du=du, dV=dV, Vx=Vx, Vxx=Vxx, status=status.value)
 
     def fetch_stats(self):
-        st = np.zeros((self.lastN, 4), np.int64)
+        st = np.zeros((self.lastN, 12), np.int64)
         self._check(self.lib.mjpc_b200_fetch_stats(self.h, st.ctypes.data_as(C.POINTER(C.c_int64))))
         return st
 
