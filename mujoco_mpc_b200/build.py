@@ -25,12 +25,21 @@ def needs_build():
     return any(os.path.getmtime(s) > t for s in sources())
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
-        return SO
+def _compile(verbose):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO, os.path.join(CSRC, "engine.cu"), os.path.join(CSRC, "host", "sampling_planner.cc")]
     subprocess.check_call(cmd, cwd=CSRC)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return SO
+    _compile(verbose)
+    # the static kernel tables (csrc/spec_*.h) are a function of the model compiler + the header/layout structs:
+    # regenerate them from the library just built and compile once more if one changed
+    from . import gen_spec
+    if gen_spec.generate(SO):
+        _compile(verbose)
     return SO
 
 

@@ -9,6 +9,7 @@
 
 namespace mjpc_dev {
 
+constexpr int kMaxSplinePoints = 64;  // knot_times has a fixed capacity so that only the LAST array depends on P
 // name, element count (expression over M = DevModel, P = spline points)
 #define MJPC_D_ARRAYS(X)                                                                                          \
   X(qpos, M.nq) X(qvel, M.nv) X(ctrl, M.nu) X(qacc, M.nv) X(qacc_warmstart, M.nv) X(mocap_pos, 3 * M.nmocap)      \
@@ -30,7 +31,7 @@ namespace mjpc_dev {
   X(efc_R, M.maxefc) X(efc_D, M.maxefc) X(efc_K, M.maxefc) X(efc_B, M.maxefc) X(efc_imp, M.maxefc)                \
   X(efc_aref, M.maxefc) X(efc_hw, M.maxefc) X(efc_force, M.maxefc) X(efc_jar, M.maxefc) X(efc_Jv, M.maxefc) X(efc_floss, M.maxefc)    \
   X(efc_type, M.maxefc) X(efc_id, M.maxefc) X(efc_state, M.maxefc) X(efc_item, M.maxefc) X(efc_hc, 36 * M.maxcon) X(con_mlo, M.maxcon) X(con_mhi, M.maxcon) \
-  X(residual, M.num_residual) X(knots, P * M.nu) X(knot_times, P) X(xnom, M.nq + M.nv) X(dx, 2 * M.nv)
+  X(residual, M.num_residual) X(xnom, M.nq + M.nv) X(dx, 2 * M.nv) X(knot_times, kMaxSplinePoints) X(knots, P * M.nu)
 
 enum DataArrayId {
 #define X(n, sz) D_##n,
@@ -88,12 +89,60 @@ struct Ctx {
 #else
 #define PHASE(c, i) do { } while (0)
 #endif
-#define CM(c) (*reinterpret_cast<const DevModel*>(g_smem + (c).hdr))
-#define CL(c) (*reinterpret_cast<const DevLayout*>(g_smem + (c).lay))
-#define MF(n) (g_smem + CM(c).fo[F_##n])
-#define MI(n) (reinterpret_cast<const int*>(g_smem + c.ibase) + CM(c).io[I_##n])
-#define DF(n) (g_smem + c.dbase + CL(c).off[D_##n])
-#define DI(n) (reinterpret_cast<int*>(g_smem + c.dbase) + CL(c).off[D_##n])
+// ---- model / state accessors.  Every device function is a template over a "spec" SP:
+//   DynSpec          sizes and offsets are read from the header copy in shared memory (any model)
+//   StaticSpec<K>    sizes and offsets are compile-time constants taken from a generated table K (spec_*.h):
+//                    every shared-memory address becomes an immediate, size-dependent loops unroll, option
+//                    branches fold.  Requires one warp per CTA (the state block then sits at a fixed address).
+// Float options (timestep, tolerance, risk ...) always come from the live header: CM(c).timestep.
+template <int V> struct IntC { static constexpr int v = V; };
+constexpr int kHdrWords = (int)((sizeof(DevModel) + 15) / 16) * 4;
+constexpr int kLayWords = (int)((sizeof(DevLayout) + 15) / 16) * 4;
+
+struct DynSpec {
+  static constexpr bool kStatic = false;
+  static constexpr int kNV = 0;
+  static __device__ __forceinline__ const DevModel& hdr(const Ctx& c) { return *reinterpret_cast<const DevModel*>(g_smem + c.hdr); }
+  static __device__ __forceinline__ const DevModel& model(const Ctx& c) { return hdr(c); }
+  template <int ID> static __device__ __forceinline__ float* mf(const Ctx& c) { return g_smem + hdr(c).fo[ID]; }
+  template <int ID> static __device__ __forceinline__ int* mi(const Ctx& c) {
+    return reinterpret_cast<int*>(g_smem + c.ibase) + hdr(c).io[ID];
+  }
+  template <int ID> static __device__ __forceinline__ float* df(const Ctx& c) {
+    return g_smem + c.dbase + reinterpret_cast<const DevLayout*>(g_smem + c.lay)->off[ID];
+  }
+};
+
+template <class K>
+struct StaticSpec {
+  static constexpr bool kStatic = true;
+  static __host__ __device__ constexpr int w(size_t byte_off, int i = 0) { return K::kModelWords[byte_off / 4 + i]; }
+  struct View {
+#define X(n) static constexpr int n = w(offsetof(DevModel, n));
+    MJPC_M_INTS(X)
+#undef X
+  };
+  static constexpr int kNV = View::nv;
+  static constexpr int kHdr = View::nf + View::ni;
+  static constexpr int kData0 = kHdr + kHdrWords + kLayWords;
+  static __device__ __forceinline__ const DevModel& hdr(const Ctx&) { return *reinterpret_cast<const DevModel*>(g_smem + kHdr); }
+  static __device__ __forceinline__ View model(const Ctx&) { return View{}; }
+  template <int ID> static __device__ __forceinline__ float* mf(const Ctx&) {
+    return g_smem + IntC<w(offsetof(DevModel, fo), ID)>::v;
+  }
+  template <int ID> static __device__ __forceinline__ int* mi(const Ctx&) {
+    return reinterpret_cast<int*>(g_smem) + IntC<View::nf + w(offsetof(DevModel, io), ID)>::v;
+  }
+  template <int ID> static __device__ __forceinline__ float* df(const Ctx&) {
+    return g_smem + IntC<kData0 + K::kLayoutOff[ID]>::v;
+  }
+};
+
+#define CM(c) (SP::hdr(c))
+#define MF(n) (SP::template mf<F_##n>(c))
+#define MI(n) (SP::template mi<I_##n>(c))
+#define DF(n) (SP::template df<D_##n>(c))
+#define DI(n) (reinterpret_cast<int*>(SP::template df<D_##n>(c)))
 
 // ---------------------------------------------------------------------------------------- small math
 __device__ __forceinline__ float dot3(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
@@ -284,7 +333,10 @@ __device__ __forceinline__ void warp_chol_factor_solve_reg(float* A, float* x, c
 
 // factor A (destroyed, holds L afterwards) and solve A x = b; dispatches to the register variant for the
 // dof counts of the built-in models
+// NS > 0: the size is a compile-time constant of a static spec (register-resident path, no dispatch)
+template <int NS>
 __device__ __noinline__ void warp_chol_factor_solve(float* A, float* inv, float* x, const float* b, int n, int lane) {
+  if constexpr (NS > 0 && NS <= 32) { warp_chol_factor_solve_reg<NS>(A, x, b, lane); return; }
   if (n == 18) { warp_chol_factor_solve_reg<18>(A, x, b, lane); return; }
   if (n == 2) { warp_chol_factor_solve_reg<2>(A, x, b, lane); return; }
   warp_chol(A, inv, n, lane);

@@ -63,16 +63,21 @@ enum { JNT_FREE = 0, JNT_BALL, JNT_SLIDE, JNT_HINGE };
 enum { OBJ_BODY = 0, OBJ_XBODY, OBJ_GEOM, OBJ_SITE };
 enum { RESIDUAL_PARTICLE = 0, RESIDUAL_PARTICLE_COPY = 1, RESIDUAL_CARTPOLE = 2, RESIDUAL_QUADRUPED_FLAT = 3 };
 
+// integer fields of the header (sizes, option flags, task dimensions, pack sizes).  A statically specialised
+// kernel (spec_*.h) turns every one of them, and the offset tables below, into compile-time constants.
+#define MJPC_M_INTS(X)                                                                                           \
+  X(nq) X(nv) X(nu) X(nbody) X(njnt) X(ngeom) X(nsite) X(nmocap) X(nkey) X(npair) X(nray) X(nlevel) X(nmpair)    \
+  X(nfloss) X(nlimit) X(nhpair) X(cone) X(iterations) X(ls_iterations) X(disable_contact) X(disable_eulerdamp)  \
+  X(disable_frictionloss) X(disable_limit) X(disable_refsafe) X(disable_warmstart) X(maxcon) X(maxefc)           \
+  X(residual_id) X(num_residual) X(num_term) X(num_trace) X(num_parameters) X(task_state_size) X(any_damping)    \
+  X(nf) X(ni)
+
 struct DevModel {
-  int nq, nv, nu, nbody, njnt, ngeom, nsite, nmocap, nkey, npair, nray, nlevel, nmpair, nfloss, nlimit, nhpair;
-  int cone, iterations, ls_iterations;
-  int disable_contact, disable_eulerdamp, disable_frictionloss, disable_limit, disable_refsafe, disable_warmstart;
-  int maxcon, maxefc;
-  int residual_id, num_residual, num_term, num_trace, num_parameters, task_state_size;
-  int any_damping;
-  float timestep, impratio, tolerance, ls_tolerance, meaninertia, risk;
+#define X(n) int n;
+  MJPC_M_INTS(X)       // nf, ni: total floats / ints in the pack
+#undef X
+  float timestep, impratio, tolerance, ls_tolerance, meaninertia, risk;   // always read from the live header
   float gravity[3];
-  int nf, ni;          // total floats / ints in the pack
   int fo[F_COUNT];     // offsets (floats)
   int io[I_COUNT];     // offsets (ints)
 };

@@ -8,8 +8,9 @@
 namespace mjpc_dev {
 
 // ------------------------------------------------------------------------------------------ position stage
+template <class SP>
 __device__ __noinline__ void k_kinematics(Ctx& c) {
-  const DevModel& M = CM(c);
+  auto&& M = SP::model(c);
   const int lane = c.lane;
   float *xpos = DF(xpos), *xquat = DF(xquat), *xmat = DF(xmat), *xipos = DF(xipos), *ximat = DF(ximat);
   float *xanchor = DF(xanchor), *xaxis = DF(xaxis);
@@ -111,8 +112,9 @@ __device__ __noinline__ void k_kinematics(Ctx& c) {
   __syncwarp();
 }
 
+template <class SP>
 __device__ __noinline__ void k_com_pos(Ctx& c) {
-  const DevModel& M = CM(c);
+  auto&& M = SP::model(c);
   const int lane = c.lane;
   const int *subend = MI(body_subtreeend), *rootid = MI(body_rootid);
   const float *mass = MF(body_mass), *submass = MF(body_subtreemass), *inertia = MF(body_inertia);
@@ -183,8 +185,9 @@ __device__ __noinline__ void k_com_pos(Ctx& c) {
 }
 
 // composite rigid body inertia -> dense joint-space inertia qM, then its Cholesky factor qLD
+template <class SP>
 __device__ __noinline__ void k_crb(Ctx& c) {
-  const DevModel& M = CM(c);
+  auto&& M = SP::model(c);
   const int lane = c.lane, nv = M.nv;
   const int* subend = MI(body_subtreeend);
   float *cinert = DF(cinert), *crb = DF(crb), *cdof = DF(cdof), *dofbuf = DF(dofbuf), *qM = DF(qM), *qLD = DF(qLD);
@@ -344,8 +347,9 @@ __device__ __forceinline__ int collide_sphere_box(RawContact* out, const float* 
   return 1;
 }
 
+template <class SP>
 __device__ __noinline__ void k_collision(Ctx& c) {
-  const DevModel& M = CM(c);
+  auto&& M = SP::model(c);
   const int lane = c.lane;
   c.ncon = 0;
   if (M.disable_contact) return;
@@ -466,6 +470,7 @@ constexpr int kL = 16;  // width of a compact constraint-Jacobian row (dofs of t
 #define FOR_KL(l, nd) _Pragma("unroll") for (int l = 0; l < kL; l++) if (l < (nd))
 
 // J row (compact) dot a dof-indexed vector: friction-loss / limit rows touch one dof, contact rows their chain
+template <class SP>
 __device__ __forceinline__ float row_dot(Ctx& c, int row, int nsimple, const float* v) {
   if (row < nsimple) return DF(efc_sgn)[row] * v[DI(efc_dof)[row]];
   const int ci = DI(efc_id)[row];
@@ -477,8 +482,9 @@ __device__ __forceinline__ float row_dot(Ctx& c, int row, int nsimple, const flo
   return a;
 }
 
+template <class SP>
 __device__ __noinline__ void k_make_constraint(Ctx& c) {
-  const DevModel& M = CM(c);
+  auto&& M = SP::model(c);
   const int lane = c.lane, nv = M.nv;
   float *J = DF(efc_J), *epos = DF(efc_pos), *emargin = DF(efc_margin), *ediag = DF(efc_diag), *efloss = DF(efc_floss),
         *esgn = DF(efc_sgn);
@@ -646,7 +652,7 @@ __device__ __noinline__ void k_make_constraint(Ctx& c) {
       if (solref[0] > 0) {
         float tc = solref[0];
         const float dr = solref[1];
-        if (!M.disable_refsafe) tc = fmaxf(tc, 2 * M.timestep);
+        if (!M.disable_refsafe) tc = fmaxf(tc, 2 * CM(c).timestep);
         Kk = 1 / fmaxf(kMinVal, dmax * dmax * tc * tc * dr * dr);
         Bb = 2 / fmaxf(kMinVal, dmax * tc);
       } else {
@@ -662,7 +668,7 @@ __device__ __noinline__ void k_make_constraint(Ctx& c) {
       const int a = cadr[ci], dim = cdim[ci];
       if (a < 0 || dim == 1) continue;
       const float* fr = DF(con_friction) + 5 * ci;
-      R[a + 1] = R[a] / fmaxf(kMinVal, M.impratio);
+      R[a + 1] = R[a] / fmaxf(kMinVal, CM(c).impratio);
       DF(con_mu)[ci] = fr[0] * sqrtf(R[a + 1] / R[a]);
       for (int j = 1; j < dim - 1; j++) R[a + j + 1] = R[a + 1] * fr[0] * fr[0] / (fr[j] * fr[j]);
     }
@@ -676,8 +682,9 @@ __device__ __noinline__ void k_make_constraint(Ctx& c) {
 }
 
 // ------------------------------------------------------------------------------------------ velocity stage
+template <class SP>
 __device__ __noinline__ void k_com_vel(Ctx& c) {
-  const DevModel& M = CM(c);
+  auto&& M = SP::model(c);
   const int lane = c.lane;
   float *cvel = DF(cvel), *cdof = DF(cdof), *cdof_dot = DF(cdof_dot), *qvel = DF(qvel);
   if (lane < 6) cvel[lane] = 0;
@@ -732,8 +739,9 @@ __device__ __noinline__ void k_com_vel(Ctx& c) {
 }
 
 // passive forces, RNE bias, actuation, qfrc_smooth, qacc_smooth
+template <class SP>
 __device__ __noinline__ void k_smooth_forces(Ctx& c) {
-  const DevModel& M = CM(c);
+  auto&& M = SP::model(c);
   const int lane = c.lane, nv = M.nv;
   float *qvel = DF(qvel), *qpos = DF(qpos), *passive = DF(qfrc_passive);
   const float* damping = MF(dof_damping);
@@ -751,7 +759,7 @@ __device__ __noinline__ void k_smooth_forces(Ctx& c) {
   // RNE with qacc = 0
   float *cacc = DF(cacc), *cfrc = DF(cfrc), *cfs = DF(cfrc_sub), *cvel = DF(cvel), *cdof_dot = DF(cdof_dot),
         *cinert = DF(cinert), *cdof = DF(cdof);
-  if (lane < 6) cacc[lane] = lane < 3 ? 0.f : -M.gravity[lane - 3];
+  if (lane < 6) cacc[lane] = lane < 3 ? 0.f : -CM(c).gravity[lane - 3];
   __syncwarp();
   const int *level_adr = MI(level_adr), *level_body = MI(level_body), *parentid = MI(body_parentid),
             *dofadr = MI(body_dofadr), *dofnum = MI(body_dofnum), *subend = MI(body_subtreeend);
@@ -817,18 +825,19 @@ __device__ __noinline__ void k_smooth_forces(Ctx& c) {
   float* smooth = DF(qfrc_smooth);
   for (int i = lane; i < nv; i += 32) smooth[i] = passive[i] - bias[i] + qact[i];
   __syncwarp();
-  warp_chol_factor_solve(DF(qLD), DF(ldinv), DF(qacc_smooth), smooth, nv, lane);
+  warp_chol_factor_solve<SP::kNV>(DF(qLD), DF(ldinv), DF(qacc_smooth), smooth, nv, lane);
 }
 
 // constraint reference acceleration aref = -B*vel - K*imp*(pos - margin)
+template <class SP>
 __device__ __noinline__ void k_reference(Ctx& c) {
   const int lane = c.lane;
   const float *qvel = DF(qvel), *K = DF(efc_K), *B = DF(efc_B), *imp = DF(efc_imp), *pos = DF(efc_pos),
               *margin = DF(efc_margin);
   float* aref = DF(efc_aref);
-  const int nsimple = CM(c).nfloss + c.nlim;
+  const int nsimple = SP::model(c).nfloss + c.nlim;
   for (int i = lane; i < c.nefc; i += 32) {
-    const float v = row_dot(c, i, nsimple, qvel);
+    const float v = row_dot<SP>(c, i, nsimple, qvel);
     aref[i] = -B[i] * v - K[i] * imp[i] * (pos[i] - margin[i]);
   }
   __syncwarp();
@@ -840,8 +849,9 @@ __device__ __noinline__ void k_reference(Ctx& c) {
 // "effective rows" per contact (the cone Hessian is rank-1 + weighted identity + rank-1 in scaled coordinates):
 //   Dm*S*(v v^T + c1*P + c2*ut ut^T)*S,  v = (1, -mu*u/T), ut = (0, u), c1 = mu^2 - mu*N/T, c2 = mu*N/T^3 - mu^2/T^2
 //   X_v = sum_a S_a v_a J_a (weight Dm),  X_u = sum_{a>=1} S_a u_a J_a (weight Dm*c2),  hw[a>=1] = Dm*c1*S_a^2
+template <class SP>
 __device__ __noinline__ float k_update_constraint(Ctx& c, bool hess) {
-  const DevModel& M = CM(c);
+  auto&& M = SP::model(c);
   const int lane = c.lane, nv = M.nv;
   const float *jar = DF(efc_jar), *D = DF(efc_D), *R = DF(efc_R), *floss = DF(efc_floss), *J = DF(efc_J);
   float *force = DF(efc_force), *X = DF(efc_W), *hw = DF(efc_hw), *xw = DF(efc_hc);
@@ -947,9 +957,9 @@ __device__ __noinline__ float k_update_constraint(Ctx& c, bool hess) {
 // e = lane + 32 q (hpair tables, NQ per lane) and keeps them in registers; every active constraint row (weight
 // hw != 0) and every cone effective row is one rank-1 update read as a dense row from shared memory
 // (broadcast loads, no bank conflicts, no branches inside).
-template <int NV, int NQ>
+template <class SP, int NV, int NQ>
 __device__ __forceinline__ void hessian_dense_reg(Ctx& c) {
-  const DevModel& M = CM(c);
+  auto&& M = SP::model(c);
   const int lane = c.lane;
   constexpr int NVP = (NV + 3) / 4 * 4;
   const float *qM = DF(qM), *hw = DF(efc_hw), *Jd = DF(efc_Jd), *Xd = DF(efc_Xd), *xw = DF(efc_hc);
@@ -1016,15 +1026,15 @@ __device__ __forceinline__ float mat_row_dot(const float* Mrow, const float* v) 
 }
 
 // dense-row variants of J*v and J^T*force for compile-time NV (vectorised, fully unrolled)
-template <int NV>
+template <class SP, int NV>
 __device__ __forceinline__ float row_dot_dense(Ctx& c, int row, int nsimple, const float* v) {
   if (row < nsimple) return DF(efc_sgn)[row] * v[DI(efc_dof)[row]];
   constexpr int NVP = (NV + 3) / 4 * 4;
   return mat_row_dot<NV>(DF(efc_Jd) + row * NVP, v);   // NVP is a multiple of 4: rows are 16-byte aligned
 }
-template <int NV>
+template <class SP, int NV>
 __device__ __forceinline__ void jt_force_dense(Ctx& c, float* out) {
-  const DevModel& M = CM(c);
+  auto&& M = SP::model(c);
   const int lane = c.lane;
   constexpr int NVP = (NV + 3) / 4 * 4;
   const float *Jd = DF(efc_Jd), *force = DF(efc_force), *esgn = DF(efc_sgn);
@@ -1046,8 +1056,9 @@ __device__ __forceinline__ void jt_force_dense(Ctx& c, float* out) {
 // assembled in two balanced stages: (1) every contact's small symmetric block (its chain dofs) into scratch,
 // one (contact, block entry) per lane; (2) every structurally non-zero Hessian entry gathers the blocks that
 // contain it (deterministic order, no atomics).
+template <class SP>
 __device__ __noinline__ float k_total_cost(Ctx& c, const float* qacc, bool hess, float* gauss_out) {
-  const DevModel& M = CM(c);
+  auto&& M = SP::model(c);
   const int lane = c.lane, nv = M.nv;
   const float *qM = DF(qM), *J = DF(efc_J), *aref = DF(efc_aref), *smooth = DF(qfrc_smooth), *qas = DF(qacc_smooth);
   float *Ma = DF(Ma), *jar = DF(efc_jar);
@@ -1060,15 +1071,15 @@ __device__ __noinline__ float k_total_cost(Ctx& c, const float* qacc, bool hess,
     Ma[i] = a;
     g += (a - smooth[i]) * (qacc[i] - qas[i]);
   }
-  if (nv == 18) { for (int i = lane; i < c.nefc; i += 32) jar[i] = row_dot_dense<18>(c, i, nsimple, qacc) - aref[i]; }
-  else { for (int i = lane; i < c.nefc; i += 32) jar[i] = row_dot(c, i, nsimple, qacc) - aref[i]; }
+  if (nv == 18) { for (int i = lane; i < c.nefc; i += 32) jar[i] = row_dot_dense<SP, 18>(c, i, nsimple, qacc) - aref[i]; }
+  else { for (int i = lane; i < c.nefc; i += 32) jar[i] = row_dot<SP>(c, i, nsimple, qacc) - aref[i]; }
   g = 0.5f * warp_sum(g);
   __syncwarp();
-  const float cc = k_update_constraint(c, hess);
+  const float cc = k_update_constraint<SP>(c, hess);
   if (hess && nv == 18 && M.nhpair <= 128) {
-    hessian_dense_reg<18, 4>(c);
+    hessian_dense_reg<SP, 18, 4>(c);
   } else if (hess && nv == 18) {
-    hessian_dense_reg<18, 6>(c);
+    hessian_dense_reg<SP, 18, 6>(c);
   } else if (hess) {
     const float *X = DF(efc_W), *hw = DF(efc_hw), *xw = DF(efc_hc);
     float *H = DF(qH), *blk = DF(efc_blk);
@@ -1149,6 +1160,7 @@ __device__ __noinline__ float k_total_cost(Ctx& c, const float* qacc, bool hess,
 
 struct LsPoint { float alpha, cost, d1, d2; };
 
+template <class SP>
 __device__ __noinline__ LsPoint k_ls_eval(Ctx& c, float g0, float g1, float g2, float alpha) {
   const int lane = c.lane;
   const float *jar = DF(efc_jar), *Jv = DF(efc_Jv), *D = DF(efc_D), *R = DF(efc_R), *floss = DF(efc_floss);
@@ -1212,6 +1224,7 @@ struct LsItem {
   float mu, U0, V0, UU, UV, VV, Q0, Q1, Q2, Dm;  // kind 3
 };
 
+template <class SP>
 __device__ __forceinline__ LsItem ls_load_item(Ctx& c) {
   LsItem it;
   it.kind = 0;
@@ -1280,14 +1293,15 @@ __device__ __forceinline__ LsPoint ls_eval_cached(const LsItem& it, float g0, fl
   return p;
 }
 
+template <class SP>
 __device__ __noinline__ float k_line_search(Ctx& c, float g0, float g1, float g2, float snorm, float scale_inv) {
-  const DevModel& M = CM(c);
+  auto&& M = SP::model(c);
   if (snorm < kMinVal) return 0.f;
   const bool cached = c.nitem <= 32;   // one work item per lane: the usual case
-  const LsItem item = ls_load_item(c);
-  auto ev = [&](float alpha) { return cached ? ls_eval_cached(item, g0, g1, g2, alpha) : k_ls_eval(c, g0, g1, g2, alpha); };
+  const LsItem item = ls_load_item<SP>(c);
+  auto ev = [&](float alpha) { return cached ? ls_eval_cached(item, g0, g1, g2, alpha) : k_ls_eval<SP>(c, g0, g1, g2, alpha); };
   const LsPoint p0 = ev(0.f);
-  const float gtol = fmaxf(fmaxf(M.tolerance, kTolFloor) * M.ls_tolerance * snorm * scale_inv, 64 * 1.1920929e-7f * fabsf(p0.d1));
+  const float gtol = fmaxf(fmaxf(CM(c).tolerance, kTolFloor) * CM(c).ls_tolerance * snorm * scale_inv, 64 * 1.1920929e-7f * fabsf(p0.d1));
   if (p0.d2 <= kMinVal) return 0.f;
   LsPoint p1 = ev(-p0.d1 / p0.d2);
   if (p0.cost < p1.cost) p1 = p0;
@@ -1321,8 +1335,9 @@ __device__ __noinline__ float k_line_search(Ctx& c, float g0, float g1, float g2
 }
 
 // out[dof] = sum over constraint rows of J[row][dof] * force[row], in two balanced stages (per contact, then per dof)
+template <class SP>
 __device__ __forceinline__ void jt_force(Ctx& c, float* out_or_null) {
-  const DevModel& M = CM(c);
+  auto&& M = SP::model(c);
   const int lane = c.lane, nv = M.nv;
   const float *J = DF(efc_J), *force = DF(efc_force), *esgn = DF(efc_sgn);
   float* xf = DF(con_xf);
@@ -1355,8 +1370,9 @@ __device__ __forceinline__ void jt_force(Ctx& c, float* out_or_null) {
   __syncwarp();
 }
 
+template <class SP>
 __device__ __noinline__ void k_solve(Ctx& c) {
-  const DevModel& M = CM(c);
+  auto&& M = SP::model(c);
   const int lane = c.lane, nv = M.nv, ne = c.nefc;
   float *qacc = DF(qacc), *qas = DF(qacc_smooth), *qws = DF(qacc_warmstart), *qfc = DF(qfrc_constraint);
   c.niter = 0;
@@ -1367,21 +1383,21 @@ __device__ __noinline__ void k_solve(Ctx& c) {
   }
   float gauss;
   if (!M.disable_warmstart) {
-    const float cw = k_total_cost(c, qws, false, &gauss);
-    const float cs = k_total_cost(c, qas, false, &gauss);
+    const float cw = k_total_cost<SP>(c, qws, false, &gauss);
+    const float cs = k_total_cost<SP>(c, qas, false, &gauss);
     for (int i = lane; i < nv; i += 32) qacc[i] = cw < cs ? qws[i] : qas[i];
   } else {
     for (int i = lane; i < nv; i += 32) qacc[i] = qas[i];
   }
   __syncwarp();
-  const float scale_inv = M.meaninertia * (float)max(1, nv);
+  const float scale_inv = CM(c).meaninertia * (float)max(1, nv);
   const int nsimple = M.nfloss + c.nlim;
   float *grad = DF(grad), *search = DF(search), *Mv = DF(Mv), *Ma = DF(Ma), *smooth = DF(qfrc_smooth), *Jv = DF(efc_Jv),
         *qM = DF(qM);
-  float cost = k_total_cost(c, qacc, true, &gauss);
+  float cost = k_total_cost<SP>(c, qacc, true, &gauss);
   float gnorm2;
   auto grad_dir = [&]() {
-    if (nv == 18) jt_force_dense<18>(c, qfc); else jt_force(c, qfc);   // qfc doubles as J^T force scratch
+    if (nv == 18) jt_force_dense<SP, 18>(c, qfc); else jt_force<SP>(c, qfc);   // qfc doubles as J^T force scratch
     float g2 = 0;
     for (int i = lane; i < nv; i += 32) {
       const float a = Ma[i] - smooth[i] - qfc[i];
@@ -1390,7 +1406,7 @@ __device__ __noinline__ void k_solve(Ctx& c) {
     }
     gnorm2 = warp_sum(g2);
     __syncwarp();
-    warp_chol_factor_solve(DF(qH), DF(hinv), search, grad, nv, lane);
+    warp_chol_factor_solve<SP::kNV>(DF(qH), DF(hinv), search, grad, nv, lane);
     for (int i = lane; i < nv; i += 32) search[i] = -search[i];
     __syncwarp();
   };
@@ -1406,24 +1422,24 @@ __device__ __noinline__ void k_solve(Ctx& c) {
       q2 += 0.5f * search[i] * a;
       sn += search[i] * search[i];
     }
-    if (nv == 18) { for (int i = lane; i < ne; i += 32) Jv[i] = row_dot_dense<18>(c, i, nsimple, search); }
-    else { for (int i = lane; i < ne; i += 32) Jv[i] = row_dot(c, i, nsimple, search); }
+    if (nv == 18) { for (int i = lane; i < ne; i += 32) Jv[i] = row_dot_dense<SP, 18>(c, i, nsimple, search); }
+    else { for (int i = lane; i < ne; i += 32) Jv[i] = row_dot<SP>(c, i, nsimple, search); }
     q1 = warp_sum(q1); q2 = warp_sum(q2); sn = sqrtf(warp_sum(sn));
     __syncwarp();
-    const float alpha = k_line_search(c, gauss, q1, q2, sn, scale_inv);
+    const float alpha = k_line_search<SP>(c, gauss, q1, q2, sn, scale_inv);
     if (alpha == 0.f) break;
     for (int i = lane; i < nv; i += 32) qacc[i] += alpha * search[i];
     __syncwarp();
     const float old = cost;
-    cost = k_total_cost(c, qacc, true, &gauss);
+    cost = k_total_cost<SP>(c, qacc, true, &gauss);
     grad_dir();
     c.niter = iter + 1;
     const float improvement = (old - cost) / scale_inv, gradient = sqrtf(gnorm2) / scale_inv;
-    const float tol = fmaxf(M.tolerance, kTolFloor);
+    const float tol = fmaxf(CM(c).tolerance, kTolFloor);
     if (improvement < tol || gradient < tol) break;
   }
   // qfc holds J^T force of the last evaluated point (forces are updated by every k_total_cost call)
-  if (nv == 18) jt_force_dense<18>(c, qfc); else jt_force(c, qfc);
+  if (nv == 18) jt_force_dense<SP, 18>(c, qfc); else jt_force<SP>(c, qfc);
 }
 
 // ------------------------------------------------------------------------------------------ pipeline pieces
@@ -1434,29 +1450,31 @@ __device__ __forceinline__ bool k_bad(Ctx& c, const float* v, int n) {
 }
 
 // everything of mj_forward up to (not including) the sensor/residual callback
+template <class SP>
 __device__ __noinline__ void k_forward(Ctx& c) {
   PHASE(c, 7);            // everything between two forward passes (policy, residual, cost, Euler, output)
-  k_kinematics(c);
-  k_com_pos(c);
-  k_crb(c);
+  k_kinematics<SP>(c);
+  k_com_pos<SP>(c);
+  k_crb<SP>(c);
   PHASE(c, 0);
-  k_collision(c);
+  k_collision<SP>(c);
   PHASE(c, 1);
-  k_make_constraint(c);
+  k_make_constraint<SP>(c);
   PHASE(c, 2);
-  k_com_vel(c);
-  k_smooth_forces(c);
-  k_reference(c);
+  k_com_vel<SP>(c);
+  k_smooth_forces<SP>(c);
+  k_reference<SP>(c);
   PHASE(c, 3);
-  k_solve(c);
+  k_solve<SP>(c);
   PHASE(c, 4);
 }
 
 // semi-implicit Euler with implicit joint damping
+template <class SP>
 __device__ __noinline__ void k_euler(Ctx& c) {
-  const DevModel& M = CM(c);
+  auto&& M = SP::model(c);
   const int lane = c.lane, nv = M.nv;
-  const float h = M.timestep;
+  const float h = CM(c).timestep;
   float *qacc = DF(qacc), *qvel = DF(qvel), *qpos = DF(qpos), *vt = DF(vtmp);
   const float* acc = qacc;
   if (M.any_damping && !M.disable_eulerdamp) {
@@ -1468,7 +1486,7 @@ __device__ __noinline__ void k_euler(Ctx& c) {
     }
     for (int i = lane; i < nv; i += 32) vt[i] = smooth[i] + qfc[i];
     __syncwarp();
-    warp_chol_factor_solve(H, DF(hinv), vt, vt, nv, lane);
+    warp_chol_factor_solve<SP::kNV>(H, DF(hinv), vt, vt, nv, lane);
     acc = vt;
   }
   for (int i = lane; i < nv; i += 32) qvel[i] += h * acc[i];

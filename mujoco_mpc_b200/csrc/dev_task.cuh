@@ -68,8 +68,9 @@ __device__ __forceinline__ float norm_value(const float* x, const float* params,
 
 // CostValue of the residual in shared memory; warp-uniform result. Terms are evaluated one per lane and
 // summed in term order (same association as the scalar reference loop).
+template <class SP>
 __device__ __noinline__ float k_cost_value(Ctx& c) {
-  const DevModel& M = CM(c);
+  auto&& M = SP::model(c);
   const int lane = c.lane;
   const int *dimr = MI(task_dim_norm_residual), *ntype = MI(task_norm), *npar = MI(task_num_norm_parameter);
   const float *w = MF(task_weight), *prm = MF(task_norm_parameter), *res = DF(residual);
@@ -86,8 +87,8 @@ __device__ __noinline__ float k_cost_value(Ctx& c) {
     const int cnt = min(32, M.num_term - base);
     for (int q = 0; q < cnt; q++) cost += __shfl_sync(kFull, term, q);
   }
-  if (fabsf(M.risk) < 1e-6f) return cost;
-  return (expf(M.risk * cost) - 1.0f) / M.risk;
+  if (fabsf(CM(c).risk) < 1e-6f) return cost;
+  return (expf(CM(c).risk * cost) - 1.0f) / CM(c).risk;
 }
 
 // ------------------------------------------------------------------------------------------ spline policy
@@ -116,8 +117,9 @@ __device__ __forceinline__ float spline_sample1(const float* times, const float*
   return c0 * p0 + c1 * m0 + c2 * p1 + c3 * m1;
 }
 // ctrl <- clamp(spline(time)); one actuator per lane
+template <class SP>
 __device__ __forceinline__ void k_policy_spline(Ctx& c, int P, int interp) {
-  const DevModel& M = CM(c);
+  auto&& M = SP::model(c);
   const float* range = MF(actuator_ctrlrange);
   for (int i = c.lane; i < M.nu; i += 32) {
     float a = spline_sample1(DF(knot_times), DF(knots), P, M.nu, interp, c.time, i);
@@ -188,8 +190,9 @@ struct FeedbackArgs {
 };
 
 // ctrl <- clamp(u + scale * K * (x (-) x_nom)); global-memory reads are lane-strided (coalesced)
+template <class SP>
 __device__ __noinline__ void k_policy_feedback(Ctx& c, const FeedbackArgs& fa, float step, int index) {
-  const DevModel& M = CM(c);
+  auto&& M = SP::model(c);
   const int lane = c.lane, nq = M.nq, nv = M.nv, nu = M.nu, ds = nq + nv, n = 2 * nv, H = fa.H;
   float *xn = DF(xnom), *dx = DF(dx), *ctrl = DF(ctrl);
   int rep = 0;
@@ -283,8 +286,9 @@ __device__ __forceinline__ float ray_geom(const float* gpos, const float* gmat, 
   }
   return -1;
 }
+template <class SP>
 __device__ __forceinline__ float ground_height(Ctx& c, const float* pos, bool* ok) {
-  const DevModel& M = CM(c);
+  auto&& M = SP::model(c);
   const float down[3] = {0, 0, -1};
   const float query[3] = {pos[0], pos[1], pos[2] + 0.5f};
   const int *rg = MI(ray_geoms), *gtype = MI(geom_type);
@@ -379,8 +383,9 @@ struct QuadrupedFn {
   }
 };
 
+template <class SP>
 __device__ __noinline__ void k_residual_quadruped(Ctx& c) {
-  const DevModel& M = CM(c);
+  auto&& M = SP::model(c);
   const int lane = c.lane;
   QuadrupedFn fn{MF(task_state), MI(task_ids), MF(task_parameters)};
   const int* I = fn.I;
@@ -476,7 +481,7 @@ __device__ __noinline__ void k_residual_quadruped(Ctx& c) {
         normalize3(tg);
         for (int k = 0; k < 3; k++) query[k] += 0.15f * tg[k];
       }
-      const float gh = ground_height(c, query, &ok);
+      const float gh = ground_height<SP>(c, query, &ok);
       const float height_target = gh + kFootRadius + step;
       float hd = foot_pos[f][2] - height_target;
       if (cur == kModeScramble) hd = fminf(0.f, hd);
@@ -511,8 +516,9 @@ __device__ __noinline__ void k_residual_quadruped(Ctx& c) {
   __syncwarp();
 }
 
+template <class SP>
 __device__ __noinline__ void k_residual(Ctx& c) {
-  const DevModel& M = CM(c);
+  auto&& M = SP::model(c);
   const int lane = c.lane;
   float* r = DF(residual);
   switch (M.residual_id) {
@@ -535,7 +541,7 @@ __device__ __noinline__ void k_residual(Ctx& c) {
       }
       __syncwarp();
       break;
-    case RESIDUAL_QUADRUPED_FLAT: k_residual_quadruped(c); break;
+    case RESIDUAL_QUADRUPED_FLAT: k_residual_quadruped<SP>(c); break;
     default: break;
   }
 }

@@ -43,6 +43,7 @@ struct mjpc_b200 {
   ModelPack pack;
   int maxN = 0, maxH = 0, maxP = 64;
   int warps_per_cta = 1;
+  int static_spec = 0;   // 1: the model equals spec_quadruped.h -> statically specialised rollout kernel
   float* d_pack = nullptr;
   // inputs
   float *d_state = nullptr, *d_mocap = nullptr, *d_task_state = nullptr, *d_knots = nullptr, *d_knot_times = nullptr;
@@ -68,6 +69,7 @@ struct mjpc_b200 {
   std::vector<int> time_idx;
   int lastN = 0, lastH = 0;
   int64_t launches = 0;
+  int last_static = 0;
   float last_ms = 0;
   // resident-input launch description
   RolloutArgs resident;
@@ -126,7 +128,12 @@ int launch_rollout(mjpc_b200* h, const RolloutArgs& A) {
   const size_t smem = h->smem_bytes(A.P, wpc);
   const int grid = (A.N + wpc - 1) / wpc;
   CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-  rollout_kernel<<<grid, 32 * wpc, smem, h->stream>>>(A);
+  // static instance: same arguments, same shared-memory image; MJPC_B200_NO_STATIC=1 forces the generic kernel
+  const char* ns = std::getenv("MJPC_B200_NO_STATIC");
+  const bool use_static = h->static_spec == 1 && wpc == 1 && !(ns && ns[0] == '1');
+  if (use_static) rollout_kernel_quadruped<<<grid, 32, smem, h->stream>>>(A);
+  else rollout_kernel<<<grid, 32 * wpc, smem, h->stream>>>(A);
+  h->last_static = use_static ? 1 : 0;
   rank_kernel<<<(A.N + 255) / 256, 256, 0, h->stream>>>(A.returns, A.N, h->d_order);
   CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
   CUDA_TRY(cudaGetLastError());
@@ -237,6 +244,10 @@ int mjpc_b200_create(const mjpc_model_blob* model, int max_candidates, int max_h
   CUDA_TRY(cudaMallocHost((void**)&h->h_out, h->h_out_bytes));
   if (int rc = set_smem((const void*)rollout_kernel, h->smem_bytes(h->maxP, h->warps_per_cta))) { mjpc_b200_destroy(h); return rc; }
   if (int rc = set_smem((const void*)step_debug_kernel, h->smem_bytes(1, 1))) { mjpc_b200_destroy(h); return rc; }
+  if (spec_matches<SpecQuadruped>(M, make_layout(M, 1))) {
+    h->static_spec = 1;
+    if (int rc = set_smem((const void*)rollout_kernel_quadruped, h->smem_bytes(h->maxP, 1))) { mjpc_b200_destroy(h); return rc; }
+  }
   if (int rc = ilqg_init(h->ilqg, h->pack.M, (int)H, h->smem_bytes(1, 1))) {
     mjpc_b200_destroy(h);
     return fail(rc, "ilqg buffer allocation failed");
@@ -464,6 +475,24 @@ int mjpc_b200_fetch_stats(mjpc_b200_t* h, int64_t* stats) {
 
 int64_t mjpc_b200_launch_count(const mjpc_b200_t* h) { return h ? h->launches : 0; }
 float mjpc_b200_last_kernel_ms(const mjpc_b200_t* h) { return h ? h->last_ms : 0.f; }
+int mjpc_b200_last_kernel_static(const mjpc_b200_t* h) { return h ? h->last_static : 0; }
+
+// Header + state-layout words of a model, as the static kernel tables (spec_*.h) store them.  Host only.
+int mjpc_b200_spec_words(const mjpc_model_blob* model, int* out, int capacity) {
+  if (!model || !model->data || !out) return fail(MJPC_B200_ERR_BAD_ARGUMENT, "spec_words: null");
+  try {
+    ModelPack P = pack_model(model->data, model->nbytes, 32, 96);
+    const DevLayout L = make_layout(P.M, 1);
+    const int nm = (int)(sizeof(DevModel) / 4), nl = (int)D_COUNT;
+    if (capacity < 2 + nm + nl) return fail(MJPC_B200_ERR_CAPACITY, "spec_words: buffer too small");
+    out[0] = nm; out[1] = nl;
+    std::memcpy(out + 2, &P.M, sizeof(DevModel));
+    for (int i = 0; i < nl; i++) out[2 + nm + i] = L.off[i];
+    return 2 + nm + nl;
+  } catch (const std::exception& e) {
+    return fail(MJPC_B200_ERR_BAD_BLOB, std::string("spec_words: ") + e.what());
+  }
+}
 void* mjpc_b200_stream(mjpc_b200_t* h) { return h ? (void*)h->stream : nullptr; }
 float* mjpc_b200_device_returns(mjpc_b200_t* h) { return h ? h->d_returns : nullptr; }
 

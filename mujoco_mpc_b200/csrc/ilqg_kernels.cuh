@@ -130,8 +130,9 @@ struct FdArgs {
   float *A, *B, *C, *D;
 };
 
+template <class SP>
 __device__ __forceinline__ void fd_load_state(Ctx& c, const FdArgs& A, int t) {
-  const DevModel& M = CM(c);
+  auto&& M = SP::model(c);
   const int lane = c.lane, nq = M.nq, nv = M.nv, ds = nq + nv;
   if (A.task_state) {
     float* ts = const_cast<float*>(MF(task_state));
@@ -150,26 +151,28 @@ __device__ __forceinline__ void fd_load_state(Ctx& c, const FdArgs& A, int t) {
 }
 
 extern "C" __global__ void __launch_bounds__(32) fd_center_kernel(const __grid_constant__ FdArgs A) {
+  using SP = DynSpec;
   extern __shared__ __align__(16) float smem[];
   const DevModel& M = A.M;
   stage_model_pack(smem, A.pack, (unsigned)((M.nf + M.ni) * 4));
   Ctx c;
   init_ctx(c, &A.M, &A.L, smem, 0, threadIdx.x);
   const int lane = c.lane, t = blockIdx.x, nq = M.nq, nv = M.nv, ds = nq + nv, nr = M.num_residual;
-  fd_load_state(c, A, t);
+  fd_load_state<SP>(c, A, t);
   for (int i = lane; i < nv; i += 32) DF(qacc_warmstart)[i] = 0;
   __syncwarp();
-  k_forward(c);
-  k_residual(c);
+  k_forward<SP>(c);
+  k_residual<SP>(c);
   for (int i = lane; i < nr; i += 32) A.r0[(size_t)t * nr + i] = DF(residual)[i];
   for (int i = lane; i < nv; i += 32) A.q0[(size_t)t * nv + i] = DF(qacc)[i];
-  k_euler(c);
+  k_euler<SP>(c);
   for (int i = lane; i < nq; i += 32) A.y0[(size_t)t * ds + i] = DF(qpos)[i];
   for (int i = lane; i < nv; i += 32) A.y0[(size_t)t * ds + nq + i] = DF(qvel)[i];
 }
 
 // one warp per (t, column). columns: [0, nu) controls, [nu, nu+nv) velocities, [nu+nv, nu+2nv) positions
 extern "C" __global__ void __launch_bounds__(32) fd_column_kernel(const __grid_constant__ FdArgs A) {
+  using SP = DynSpec;
   extern __shared__ __align__(16) float smem[];
   const DevModel& M = A.M;
   stage_model_pack(smem, A.pack, (unsigned)((M.nf + M.ni) * 4));
@@ -180,7 +183,7 @@ extern "C" __global__ void __launch_bounds__(32) fd_column_kernel(const __grid_c
   const int t = blockIdx.x / ncol, col = blockIdx.x - t * ncol;
   const bool last = t == A.H - 1;
   if (last && col < nu) return;  // only C is computed at the final time step (model_derivatives.cc:89-93)
-  fd_load_state(c, A, t);
+  fd_load_state<SP>(c, A, t);
   for (int i = lane; i < nv; i += 32) DF(qacc_warmstart)[i] = A.q0[(size_t)t * nv + i];
   __syncwarp();
   float h = A.eps;  // signed step actually taken
@@ -218,8 +221,8 @@ extern "C" __global__ void __launch_bounds__(32) fd_column_kernel(const __grid_c
     }
   }
   __syncwarp();
-  k_forward(c);
-  k_residual(c);
+  k_forward<SP>(c);
+  k_residual<SP>(c);
   const float ih = 1.0f / h;
   // residual columns
   float* Cout = col < nu ? A.D : A.C;
@@ -228,7 +231,7 @@ extern "C" __global__ void __launch_bounds__(32) fd_column_kernel(const __grid_c
   for (int k = lane; k < nr; k += 32)
     Cout[((size_t)t * nr + k) * cw + cc] = (DF(residual)[k] - A.r0[(size_t)t * nr + k]) * ih;
   if (last) return;
-  k_euler(c);
+  k_euler<SP>(c);
   // next-state difference in the tangent space (StateDiff / mj_differentiatePos)
   float* Sout = col < nu ? A.B : A.A;
   const float* y0 = A.y0 + (size_t)t * ds;

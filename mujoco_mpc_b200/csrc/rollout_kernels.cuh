@@ -12,6 +12,7 @@
 #pragma once
 #include "dev_physics.cuh"
 #include "dev_task.cuh"
+#include "spec_quadruped.h"
 
 namespace mjpc_dev {
 
@@ -87,8 +88,9 @@ __device__ __forceinline__ void init_ctx(Ctx& c, const DevModel* M, const DevLay
 }
 
 // write the trace points (GetTraces, mjpc/utilities.cc:268-285)
+template <class SP>
 __device__ __forceinline__ void write_traces(Ctx& c, float* out) {
-  const DevModel& M = CM(c);
+  auto&& M = SP::model(c);
   const int *ty = MI(task_trace_objtype), *id = MI(task_trace_objid);
   for (int w = c.lane; w < 3 * M.num_trace; w += 32) {
     const int k = w / 3, q = w - 3 * k;
@@ -97,15 +99,16 @@ __device__ __forceinline__ void write_traces(Ctx& c, float* out) {
   }
 }
 
-extern "C" __global__ void __launch_bounds__(128) rollout_kernel(const __grid_constant__ RolloutArgs A) {
-  extern __shared__ __align__(16) float smem[];
-  const DevModel& M = A.M;
-  stage_model_pack(smem, A.pack, (unsigned)((M.nf + M.ni) * 4));
+template <class SP>
+__device__ __forceinline__ void rollout_body(const RolloutArgs& A) {
+  float* smem = g_smem;
+  stage_model_pack(smem, A.pack, (unsigned)((A.M.nf + A.M.ni) * 4));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cand = blockIdx.x * (blockDim.x >> 5) + warp;
   Ctx c;
   init_ctx(c, &A.M, &A.L, smem, warp, lane);
   if (cand >= A.N) return;
+  auto&& M = SP::model(c);
   const int nq = M.nq, nv = M.nv, nu = M.nu, ds = nq + nv, nr = M.num_residual, ntr = 3 * M.num_trace, H = A.H;
   // per-iteration task state (time-rebased) overrides the packed copy: the pack in shared memory is per CTA,
   // every warp writes the same values
@@ -144,8 +147,8 @@ extern "C" __global__ void __launch_bounds__(128) rollout_kernel(const __grid_co
   for (int t = 0; t < H; t++) {
     const bool last = t == H - 1;
     if (!last) {
-      if (A.policy_kind == 0) k_policy_spline(c, A.P, A.interp);
-      else k_policy_feedback(c, A.fb, step_size, t);
+      if (A.policy_kind == 0) k_policy_spline<SP>(c, A.P, A.interp);
+      else k_policy_feedback<SP>(c, A.fb, step_size, t);
     }
     // action record (the last row repeats the previous action; H == 1 -> zeros; trajectory.cc:190-196)
     for (int i = lane; i < nu; i += 32) {
@@ -153,19 +156,19 @@ extern "C" __global__ void __launch_bounds__(128) rollout_kernel(const __grid_co
       o_actions[(size_t)t * nu + i] = DF(ctrl)[i];
     }
     if (!last && (k_bad(c, DF(qpos), nq) || k_bad(c, DF(qvel), nv))) { failed = true; break; }
-    k_forward(c);
+    k_forward<SP>(c);
     n_newton += c.niter; n_con += c.ncon; n_efc += c.nefc;
-    k_residual(c);
+    k_residual<SP>(c);
     if (!last && k_bad(c, DF(qacc), nv)) c.warn = 1;
     for (int i = lane; i < nr; i += 32) o_res[(size_t)t * nr + i] = DF(residual)[i];
-    write_traces(c, o_trace + (size_t)t * ntr);
+    write_traces<SP>(c, o_trace + (size_t)t * ntr);
     if (c.warn) { failed = true; break; }
-    const float cost = k_cost_value(c);
+    const float cost = k_cost_value<SP>(c);
     if (lane == 0) o_costs[t] = cost;
     total += cost;
     if (last) break;
     for (int i = lane; i < nv; i += 32) DF(qacc_warmstart)[i] = DF(qacc)[i];
-    k_euler(c);
+    k_euler<SP>(c);
     for (int i = lane; i < nq; i += 32) o_states[(size_t)(t + 1) * ds + i] = DF(qpos)[i];
     for (int i = lane; i < nv; i += 32) o_states[(size_t)(t + 1) * ds + nq + i] = DF(qvel)[i];
     if (lane == 0) o_times[t + 1] = A.time0 + (double)c.time;
@@ -185,6 +188,29 @@ extern "C" __global__ void __launch_bounds__(128) rollout_kernel(const __grid_co
       }
     }
   }
+}
+
+extern "C" __global__ void __launch_bounds__(128) rollout_kernel(const __grid_constant__ RolloutArgs A) {
+  rollout_body<DynSpec>(A);
+}
+// statically specialised instance for the Quadruped (flat) task model (spec_quadruped.h); one warp per CTA
+extern "C" __global__ void __launch_bounds__(32) rollout_kernel_quadruped(const __grid_constant__ RolloutArgs A) {
+  rollout_body<StaticSpec<SpecQuadruped>>(A);
+}
+
+// host: does the live model header / state layout equal the table a static kernel was compiled from?
+// (float options are not part of the comparison: static kernels read them from the live header)
+template <class K>
+inline bool spec_matches(const DevModel& M, const DevLayout& L) {
+  if (K::kNumModelWords != (int)(sizeof(DevModel) / 4) || K::kNumLayout != (int)D_COUNT) return false;
+  const int* w = K::kModelWords;
+#define X(n) if (w[offsetof(DevModel, n) / 4] != M.n) return false;
+  MJPC_M_INTS(X)
+#undef X
+  for (int i = 0; i < F_COUNT; i++) if (w[offsetof(DevModel, fo) / 4 + i] != M.fo[i]) return false;
+  for (int i = 0; i < I_COUNT; i++) if (w[offsetof(DevModel, io) / 4 + i] != M.io[i]) return false;
+  for (int i = 0; i < D_COUNT; i++) if (K::kLayoutOff[i] != L.off[i]) return false;
+  return true;
 }
 
 // order[rank] = i, ascending return, ties broken by index
@@ -211,6 +237,7 @@ struct DebugArgs {
 };
 
 extern "C" __global__ void __launch_bounds__(32) step_debug_kernel(const __grid_constant__ DebugArgs A) {
+  using SP = DynSpec;
   extern __shared__ __align__(16) float smem[];
   const DevModel& M = A.M;
   stage_model_pack(smem, A.pack, (unsigned)((M.nf + M.ni) * 4));
@@ -231,15 +258,15 @@ extern "C" __global__ void __launch_bounds__(32) step_debug_kernel(const __grid_
   for (int i = lane; i < nv * nv; i += 32) DF(qM)[i] = 0;
   c.time = A.time;
   __syncwarp();
-  k_forward(c);
-  k_residual(c);
+  k_forward<SP>(c);
+  k_residual<SP>(c);
   if (k_bad(c, DF(qacc), nv)) c.warn = 1;
   for (int i = lane; i < nv; i += 32) A.qacc[i] = DF(qacc)[i];
   for (int i = lane; i < nv * nv; i += 32) A.qM[i] = DF(qM)[i];
   for (int i = lane; i < M.num_residual; i += 32) A.residual[i] = DF(residual)[i];
   for (int i = lane; i < c.nefc; i += 32) A.efc_force[i] = DF(efc_force)[i];
   if (lane == 0) { A.counts[0] = c.ncon; A.counts[1] = c.nefc; A.counts[2] = c.niter; A.counts[3] = c.warn; }
-  k_euler(c);
+  k_euler<SP>(c);
   for (int i = lane; i < nq; i += 32) A.next_qpos[i] = DF(qpos)[i];
   for (int i = lane; i < nv; i += 32) A.next_qvel[i] = DF(qvel)[i];
 }

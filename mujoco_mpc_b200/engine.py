@@ -22,7 +22,8 @@ EXPORTS = ["mjpc_b200_version", "mjpc_b200_last_error", "mjpc_b200_create", "mjp
            "mjpc_b200_get_info", "mjpc_b200_set_task", "mjpc_b200_rollout_spline", "mjpc_b200_rollout_feedback",
            "mjpc_b200_fetch_trajectory", "mjpc_b200_fetch_all", "mjpc_b200_model_derivatives",
            "mjpc_b200_cost_derivatives", "mjpc_b200_backward_pass", "mjpc_b200_step_debug",
-           "mjpc_b200_fetch_stats", "mjpc_b200_launch_count", "mjpc_b200_last_kernel_ms", "mjpc_b200_upload_spline_inputs",
+           "mjpc_b200_fetch_stats", "mjpc_b200_launch_count", "mjpc_b200_last_kernel_ms", "mjpc_b200_last_kernel_static",
+           "mjpc_b200_spec_words", "mjpc_b200_upload_spline_inputs",
            "mjpc_b200_launch_resident", "mjpc_b200_sync", "mjpc_b200_read_returns", "mjpc_b200_stream",
            "mjpc_b200_device_returns", "mjpc_b200_host_spline_sample", "mjpc_b200_host_philox_normal",
            "mjpc_b200_planner_create", "mjpc_b200_planner_destroy", "mjpc_b200_planner_reset",
@@ -251,6 +252,11 @@ class Engine:
     @property
     def last_kernel_ms(self):
         return float(self.lib.mjpc_b200_last_kernel_ms(self.h))
+
+    @property
+    def last_kernel_static(self):
+        """True if the last rollout launch ran a statically specialised kernel instance (csrc/spec_*.h)."""
+        return bool(self.lib.mjpc_b200_last_kernel_static(self.h))
 
 
 class CppSamplingPlanner:

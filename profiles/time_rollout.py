@@ -11,7 +11,7 @@ state, mocap, knots, kt = quadruped_inputs(m, N=256, H=64)
 for i in range(3):
     ret, fail, order = e.rollout_spline(state, 0.0, mocap, knots, kt, 2, 64)
 st = e.fetch_stats()
-print("%s zero-nominal: kernel %.2f ms  newton/step %.2f  checksum %.6f" % (os.environ.get("MJPC_B200_SO", "default")[-24:], e.last_kernel_ms, st[:, 1].mean() / 64, float(ret.sum())))
+print("%s static=%d zero-nominal: kernel %.2f ms  newton/step %.2f  checksum %.6f" % (os.environ.get("MJPC_B200_SO", "default")[-24:], e.last_kernel_static, e.last_kernel_ms, st[:, 1].mean() / 64, float(ret.sum())))
 pl = SamplingPlanner(m, e, num_trajectory=256, horizon=64)
 pl.reset(); pl.set_state(state, 0.0, mocap)
 for _ in range(30):
