@@ -916,40 +916,6 @@ __device__ __noinline__ float k_update_constraint(Ctx& c, bool hess) {
   }
   cost = warp_sum(cost);
   __syncwarp();
-  if (hess) {
-    // effective rows of cone contacts (compact): one (contact, local dof) pair per lane
-    const int *cadr = DI(con_adr), *cnd = DI(con_nd);
-    const int total = c.ncon * kL;
-    for (int w = lane; w < total; w += 32) {
-      const int ci = w / kL, l = w - ci * kL;
-      const int a0 = cadr[ci];
-      if (a0 < 0 || l >= cnd[ci] || state[a0] != STATE_CONE) continue;
-      const int dim = cdim[ci];
-      const float* q = xw + 36 * ci;
-      float xv = 0.f, xu = 0.f;
-      FOR_DIM(a, 0, dim) {
-        const float jv = J[(a0 + a) * kL + l];
-        xv += q[a] * jv;
-        xu += q[6 + a] * jv;
-      }
-      X[(2 * ci) * kL + l] = xv;
-      X[(2 * ci + 1) * kL + l] = xu;
-    }
-    if (nv == 18) {   // dense copies for the register-blocked assembly
-      float* Xd = DF(efc_Xd);
-      const int* cloc = DI(con_loc);
-      __syncwarp();
-      for (int w = lane; w < c.ncon * nv; w += 32) {
-        const int ci = w / nv, i = w - ci * nv;
-        const int a0 = cadr[ci];
-        if (a0 < 0 || state[a0] != STATE_CONE) continue;
-        const int l = cloc[w];
-        Xd[(2 * ci) * 20 + i] = l >= 0 ? X[(2 * ci) * kL + l] : 0.f;
-        Xd[(2 * ci + 1) * 20 + i] = l >= 0 ? X[(2 * ci + 1) * kL + l] : 0.f;
-      }
-    }
-    __syncwarp();
-  }
   return cost;
 }
 
@@ -1076,11 +1042,60 @@ __device__ __noinline__ float k_total_cost(Ctx& c, const float* qacc, bool hess,
   g = 0.5f * warp_sum(g);
   __syncwarp();
   const float cc = k_update_constraint<SP>(c, hess);
-  if (hess && nv == 18 && M.nhpair <= 128) {
+  *gauss_out = g;
+  return cc + g;
+}
+
+// Newton Hessian H = M + J^T diag(hw) J + cone blocks at the point last evaluated by k_total_cost(.., hess=true)
+// (which leaves the row weights hw and the per-cone coefficients in efc_hc).  Kept apart from the cost evaluation
+// so that the solver only assembles and factorises H when another iteration is actually taken.
+template <class SP>
+__device__ __noinline__ void k_hessian(Ctx& c) {
+  auto&& M = SP::model(c);
+  const int lane = c.lane, nv = M.nv;
+  const float *qM = DF(qM), *J = DF(efc_J);
+  float *X = DF(efc_W);
+  const int *state = DI(efc_state), *cdim = DI(con_dim);
+  const float* xw = DF(efc_hc);
+  {
+    // effective rows of cone contacts (compact): one (contact, local dof) pair per lane
+    const int *cadr = DI(con_adr), *cnd = DI(con_nd);
+    const int total = c.ncon * kL;
+    for (int w = lane; w < total; w += 32) {
+      const int ci = w / kL, l = w - ci * kL;
+      const int a0 = cadr[ci];
+      if (a0 < 0 || l >= cnd[ci] || state[a0] != STATE_CONE) continue;
+      const int dim = cdim[ci];
+      const float* q = xw + 36 * ci;
+      float xv = 0.f, xu = 0.f;
+      FOR_DIM(a, 0, dim) {
+        const float jv = J[(a0 + a) * kL + l];
+        xv += q[a] * jv;
+        xu += q[6 + a] * jv;
+      }
+      X[(2 * ci) * kL + l] = xv;
+      X[(2 * ci + 1) * kL + l] = xu;
+    }
+    if (nv == 18) {   // dense copies for the register-blocked assembly
+      float* Xd = DF(efc_Xd);
+      const int* cloc = DI(con_loc);
+      __syncwarp();
+      for (int w = lane; w < c.ncon * nv; w += 32) {
+        const int ci = w / nv, i = w - ci * nv;
+        const int a0 = cadr[ci];
+        if (a0 < 0 || state[a0] != STATE_CONE) continue;
+        const int l = cloc[w];
+        Xd[(2 * ci) * 20 + i] = l >= 0 ? X[(2 * ci) * kL + l] : 0.f;
+        Xd[(2 * ci + 1) * 20 + i] = l >= 0 ? X[(2 * ci + 1) * kL + l] : 0.f;
+      }
+    }
+    __syncwarp();
+  }
+  if (nv == 18 && M.nhpair <= 128) {
     hessian_dense_reg<SP, 18, 4>(c);
-  } else if (hess && nv == 18) {
+  } else if (nv == 18) {
     hessian_dense_reg<SP, 18, 6>(c);
-  } else if (hess) {
+  } else {
     const float *X = DF(efc_W), *hw = DF(efc_hw), *xw = DF(efc_hc);
     float *H = DF(qH), *blk = DF(efc_blk);
     const int *hi = MI(hpair_i), *hj = MI(hpair_j), *frow = MI(floss_row), *state = DI(efc_state), *edof = DI(efc_dof),
@@ -1154,8 +1169,6 @@ __device__ __noinline__ float k_total_cost(Ctx& c, const float* qacc, bool hess,
     for (int e = lane; e < M.nhpair; e += 32) { const int r = hi[e], s2 = hj[e]; H[s2 * nv + r] = H[r * nv + s2]; }
     __syncwarp();
   }
-  *gauss_out = g;
-  return cc + g;
 }
 
 struct LsPoint { float alpha, cost, d1, d2; };
@@ -1381,37 +1394,50 @@ __device__ __noinline__ void k_solve(Ctx& c) {
     __syncwarp();
     return;
   }
-  float gauss;
+  float gauss, cost;
   if (!M.disable_warmstart) {
-    const float cw = k_total_cost<SP>(c, qws, false, &gauss);
+    // warm start (engine_forward: the better of qacc_warmstart and qacc_smooth).  The smooth point is evaluated
+    // first so that, when the warm start wins (the usual case), the constraint state is already the chosen one.
     const float cs = k_total_cost<SP>(c, qas, false, &gauss);
-    for (int i = lane; i < nv; i += 32) qacc[i] = cw < cs ? qws[i] : qas[i];
+    const float cw = k_total_cost<SP>(c, qws, true, &gauss);
+    const bool warm = cw < cs;
+    for (int i = lane; i < nv; i += 32) qacc[i] = warm ? qws[i] : qas[i];
+    __syncwarp();
+    cost = warm ? cw : k_total_cost<SP>(c, qacc, true, &gauss);
   } else {
     for (int i = lane; i < nv; i += 32) qacc[i] = qas[i];
+    __syncwarp();
+    cost = k_total_cost<SP>(c, qacc, true, &gauss);
   }
-  __syncwarp();
   const float scale_inv = CM(c).meaninertia * (float)max(1, nv);
+  const float tol = fmaxf(CM(c).tolerance, kTolFloor);
   const int nsimple = M.nfloss + c.nlim;
   float *grad = DF(grad), *search = DF(search), *Mv = DF(Mv), *Ma = DF(Ma), *smooth = DF(qfrc_smooth), *Jv = DF(efc_Jv),
         *qM = DF(qM);
-  float cost = k_total_cost<SP>(c, qacc, true, &gauss);
-  float gnorm2;
-  auto grad_dir = [&]() {
-    if (nv == 18) jt_force_dense<SP, 18>(c, qfc); else jt_force<SP>(c, qfc);   // qfc doubles as J^T force scratch
+  float old = cost;
+  bool qfc_current = false;
+  for (int iter = 0; iter <= M.iterations; iter++) {
+    // gradient at the current point; qfc doubles as the J^T force scratch and is the output when we stop here
+    if (nv == 18) jt_force_dense<SP, 18>(c, qfc); else jt_force<SP>(c, qfc);
+    qfc_current = true;
     float g2 = 0;
     for (int i = lane; i < nv; i += 32) {
       const float a = Ma[i] - smooth[i] - qfc[i];
       grad[i] = a;
       g2 += a * a;
     }
-    gnorm2 = warp_sum(g2);
+    const float gnorm2 = warp_sum(g2);
     __syncwarp();
+    if (iter > 0) {
+      const float improvement = (old - cost) / scale_inv, gradient = sqrtf(gnorm2) / scale_inv;
+      if (improvement < tol || gradient < tol) break;
+    }
+    if (iter == M.iterations) break;
+    // Newton direction: assemble + factorise the Hessian only now that another iteration is taken
+    k_hessian<SP>(c);
     warp_chol_factor_solve<SP::kNV>(DF(qH), DF(hinv), search, grad, nv, lane);
     for (int i = lane; i < nv; i += 32) search[i] = -search[i];
     __syncwarp();
-  };
-  grad_dir();
-  for (int iter = 0; iter < M.iterations; iter++) {
     float q1 = 0, q2 = 0, sn = 0;
     for (int i = lane; i < nv; i += 32) {
       float a = 0;
@@ -1430,16 +1456,12 @@ __device__ __noinline__ void k_solve(Ctx& c) {
     if (alpha == 0.f) break;
     for (int i = lane; i < nv; i += 32) qacc[i] += alpha * search[i];
     __syncwarp();
-    const float old = cost;
+    old = cost;
     cost = k_total_cost<SP>(c, qacc, true, &gauss);
-    grad_dir();
+    qfc_current = false;
     c.niter = iter + 1;
-    const float improvement = (old - cost) / scale_inv, gradient = sqrtf(gnorm2) / scale_inv;
-    const float tol = fmaxf(CM(c).tolerance, kTolFloor);
-    if (improvement < tol || gradient < tol) break;
   }
-  // qfc holds J^T force of the last evaluated point (forces are updated by every k_total_cost call)
-  if (nv == 18) jt_force_dense<SP, 18>(c, qfc); else jt_force<SP>(c, qfc);
+  if (!qfc_current) { if (nv == 18) jt_force_dense<SP, 18>(c, qfc); else jt_force<SP>(c, qfc); }
 }
 
 // ------------------------------------------------------------------------------------------ pipeline pieces

@@ -50,15 +50,16 @@ for a, i, s in zip(addr, inst, samp):
 # names from the ELF symbol table: device functions are local symbols "$kernel$mangled" whose value is the
 # offset from the kernel's first instruction
 sym = {}
+kname = vals[hdr.index("Kernel Name")].split("(")[0] if "Kernel Name" in hdr else "rollout_kernel"
 for line in run(["cuobjdump", "-elf", so]).splitlines():
-    mm = re.match(r"\s*0x[0-9a-f]+\s+(0x[0-9a-f]+)\s+0x[0-9a-f]+\s+0x\d+\s+\d+\s+0x[0-9a-f]+\s+\$rollout_kernel\$(\S+)", line)
+    mm = re.match(r"\s*0x[0-9a-f]+\s+(0x[0-9a-f]+)\s+0x[0-9a-f]+\s+0x\d+\s+\d+\s+0x[0-9a-f]+\s+\$" + re.escape(kname) + r"\$(\S+)", line)
     if mm:
-        sym[int(mm.group(1), 16)] = re.sub(r"_ZN8mjpc_dev\d+|E(RNS_3CtxE|Pf|RKNS).*", "", mm.group(2))
+        sym[int(mm.group(1), 16)] = re.sub(r"_ZN8mjpc_dev\d+|I(NS_|Li).*|E(RNS_3CtxE|Pf|RKNS).*", "", mm.group(2))
 
 
 def name_of(k):
     off = k - addr[0]
-    return "rollout_kernel (body)" if off == 0 else sym.get(off, hex(off))
+    return kname + " (body)" if off == 0 else sym.get(off, hex(off))
 
 
 tot, ts = sum(inst), sum(samp)
