@@ -178,6 +178,24 @@ void mjpc_b200_planner_action_from_policy(void* planner, double* action, double 
 int mjpc_b200_planner_get_result(void* planner, int* winner, double* improvement, float* returns, double* knots,
                                  double* knot_times);
 
+/* ---- Cross-Entropy planner (csrc/host/cross_entropy_planner.{h,cc}; mjpc/planners/cross_entropy/planner.h:35-146).
+ * One rollout launch covers the N noisy candidates and the un-noised nominal (candidate N); the elite mean and
+ * variance are host arithmetic in double, as in the reference (planner.cc:201-262).  n_elite <= 0 selects the
+ * reference default max(N/10, 2). */
+int mjpc_b200_ce_planner_create(const mjpc_model_blob* model, int num_trajectory, int n_elite, int num_spline_points,
+                                int interpolation, double std_initial, double std_min, double explore_fraction,
+                                double timestep, const double* ctrlrange, uint32_t seed, int max_horizon, int device,
+                                void** out);
+void mjpc_b200_ce_planner_destroy(void* planner);
+void mjpc_b200_ce_planner_reset(void* planner, int horizon, const double* initial_repeated_action);
+void mjpc_b200_ce_planner_set_state(void* planner, const double* state, double time, const double* mocap);
+int mjpc_b200_ce_planner_optimize_policy(void* planner, int horizon);       /* CrossEntropyPlanner::OptimizePolicy */
+void mjpc_b200_ce_planner_action_from_policy(void* planner, double* action, double time, int use_previous);
+/* improvement, returns [N+1] (last = nominal), elite order [N], installed knots [P][nu] / times [P], variance [P][nu];
+ * returns the number of spline points */
+int mjpc_b200_ce_planner_get_result(void* planner, double* improvement, float* returns, int* order, double* knots,
+                                    double* knot_times, double* variance);
+
 #ifdef __cplusplus
 }
 #endif

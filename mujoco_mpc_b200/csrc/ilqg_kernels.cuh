@@ -150,13 +150,13 @@ __device__ __forceinline__ void fd_load_state(Ctx& c, const FdArgs& A, int t) {
   __syncwarp();
 }
 
-extern "C" __global__ void __launch_bounds__(32) fd_center_kernel(const __grid_constant__ FdArgs A) {
-  using SP = DynSpec;
-  extern __shared__ __align__(16) float smem[];
-  const DevModel& M = A.M;
-  stage_model_pack(smem, A.pack, (unsigned)((M.nf + M.ni) * 4));
+template <class SP>
+__device__ __forceinline__ void fd_center_body(const FdArgs& A) {
+  float* smem = g_smem;
+  stage_model_pack(smem, A.pack, (unsigned)((A.M.nf + A.M.ni) * 4));
   Ctx c;
   init_ctx(c, &A.M, &A.L, smem, 0, threadIdx.x);
+  auto&& M = SP::model(c);
   const int lane = c.lane, t = blockIdx.x, nq = M.nq, nv = M.nv, ds = nq + nv, nr = M.num_residual;
   fd_load_state<SP>(c, A, t);
   for (int i = lane; i < nv; i += 32) DF(qacc_warmstart)[i] = 0;
@@ -171,13 +171,13 @@ extern "C" __global__ void __launch_bounds__(32) fd_center_kernel(const __grid_c
 }
 
 // one warp per (t, column). columns: [0, nu) controls, [nu, nu+nv) velocities, [nu+nv, nu+2nv) positions
-extern "C" __global__ void __launch_bounds__(32) fd_column_kernel(const __grid_constant__ FdArgs A) {
-  using SP = DynSpec;
-  extern __shared__ __align__(16) float smem[];
-  const DevModel& M = A.M;
-  stage_model_pack(smem, A.pack, (unsigned)((M.nf + M.ni) * 4));
+template <class SP>
+__device__ __forceinline__ void fd_column_body(const FdArgs& A) {
+  float* smem = g_smem;
+  stage_model_pack(smem, A.pack, (unsigned)((A.M.nf + A.M.ni) * 4));
   Ctx c;
   init_ctx(c, &A.M, &A.L, smem, 0, threadIdx.x);
+  auto&& M = SP::model(c);
   const int lane = c.lane, nq = M.nq, nv = M.nv, nu = M.nu, ds = nq + nv, n = 2 * nv, nr = M.num_residual;
   const int ncol = nu + 2 * nv;
   const int t = blockIdx.x / ncol, col = blockIdx.x - t * ncol;
@@ -253,6 +253,16 @@ extern "C" __global__ void __launch_bounds__(32) fd_column_kernel(const __grid_c
     }
   }
   for (int i = lane; i < nv; i += 32) Sout[((size_t)t * n + nv + i) * cw + cc] = (qvel[i] - y0[nq + i]) * ih;
+}
+
+extern "C" __global__ void __launch_bounds__(32) fd_center_kernel(const __grid_constant__ FdArgs A) { fd_center_body<DynSpec>(A); }
+extern "C" __global__ void __launch_bounds__(32) fd_column_kernel(const __grid_constant__ FdArgs A) { fd_column_body<DynSpec>(A); }
+// statically specialised instances (spec_quadruped.h), selected by the host when the live model matches
+extern "C" __global__ void __launch_bounds__(32) fd_center_kernel_quadruped(const __grid_constant__ FdArgs A) {
+  fd_center_body<StaticSpec<SpecQuadruped>>(A);
+}
+extern "C" __global__ void __launch_bounds__(32) fd_column_kernel_quadruped(const __grid_constant__ FdArgs A) {
+  fd_column_body<StaticSpec<SpecQuadruped>>(A);
 }
 
 // ------------------------------------------------------------------------------------------ cost derivatives
@@ -575,7 +585,7 @@ inline cudaError_t raise_smem_limit(const void* fn, size_t bytes) {
 }
 
 struct IlqgBuffers {
-  int H = 0, ds = 0, n = 0, nu = 0, nr = 0, nv = 0;
+  int H = 0, ds = 0, n = 0, nu = 0, nr = 0, nv = 0, static_spec = 0;
   float *x = nullptr, *u = nullptr, *t = nullptr, *mocap = nullptr, *ts = nullptr, *y0 = nullptr, *r0 = nullptr,
         *q0 = nullptr, *A = nullptr, *B = nullptr, *C = nullptr, *D = nullptr, *res = nullptr, *cx = nullptr,
         *cu = nullptr, *cxx = nullptr, *cuu = nullptr, *cxu = nullptr, *act = nullptr, *K = nullptr, *du = nullptr,
@@ -601,6 +611,11 @@ inline int ilqg_init(IlqgBuffers& b, const DevModel& M, int H, size_t smem_fd) {
   if (cudaMalloc((void**)&b.status, sizeof(int)) != cudaSuccess) return -4;
   if (raise_smem_limit((const void*)fd_center_kernel, smem_fd) != cudaSuccess) return -4;
   if (raise_smem_limit((const void*)fd_column_kernel, smem_fd) != cudaSuccess) return -4;
+  b.static_spec = spec_matches<SpecQuadruped>(M, make_layout(M, 1)) ? 1 : 0;
+  if (b.static_spec) {
+    if (raise_smem_limit((const void*)fd_center_kernel_quadruped, smem_fd) != cudaSuccess) return -4;
+    if (raise_smem_limit((const void*)fd_column_kernel_quadruped, smem_fd) != cudaSuccess) return -4;
+  }
   return 0;
 }
 inline void ilqg_free(IlqgBuffers& b) {
@@ -626,8 +641,14 @@ inline int ilqg_model_derivatives(IlqgBuffers& b, const DevModel& M, const float
   a.M = M; a.L = make_layout(M, 1); a.pack = d_pack; a.x = b.x; a.u = b.u; a.t = b.t; a.mocap = b.mocap;
   a.task_state = M.task_state_size ? b.ts : nullptr; a.H = H; a.eps = eps; a.y0 = b.y0; a.r0 = b.r0; a.q0 = b.q0;
   a.A = b.A; a.B = b.B; a.C = b.C; a.D = b.D;
-  fd_center_kernel<<<H, 32, smem, st>>>(a);
-  fd_column_kernel<<<H * (M.nu + 2 * M.nv), 32, smem, st>>>(a);
+  const char* ns = std::getenv("MJPC_B200_NO_STATIC");
+  if (b.static_spec == 1 && !(ns && ns[0] == '1')) {
+    fd_center_kernel_quadruped<<<H, 32, smem, st>>>(a);
+    fd_column_kernel_quadruped<<<H * (M.nu + 2 * M.nv), 32, smem, st>>>(a);
+  } else {
+    fd_center_kernel<<<H, 32, smem, st>>>(a);
+    fd_column_kernel<<<H * (M.nu + 2 * M.nv), 32, smem, st>>>(a);
+  }
   *launches += 2;
   ILQG_TRY(cudaGetLastError());
   ILQG_TRY(cudaMemcpyAsync(A, b.A, H * n * n * 4, cudaMemcpyDeviceToHost, st));

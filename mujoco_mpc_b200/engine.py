@@ -28,7 +28,10 @@ EXPORTS = ["mjpc_b200_version", "mjpc_b200_last_error", "mjpc_b200_create", "mjp
            "mjpc_b200_device_returns", "mjpc_b200_host_spline_sample", "mjpc_b200_host_philox_normal",
            "mjpc_b200_planner_create", "mjpc_b200_planner_destroy", "mjpc_b200_planner_reset",
            "mjpc_b200_planner_set_state", "mjpc_b200_planner_optimize_policy",
-           "mjpc_b200_planner_action_from_policy", "mjpc_b200_planner_get_result"]
+           "mjpc_b200_planner_action_from_policy", "mjpc_b200_planner_get_result",
+           "mjpc_b200_ce_planner_create", "mjpc_b200_ce_planner_destroy", "mjpc_b200_ce_planner_reset",
+           "mjpc_b200_ce_planner_set_state", "mjpc_b200_ce_planner_optimize_policy",
+           "mjpc_b200_ce_planner_action_from_policy", "mjpc_b200_ce_planner_get_result"]
 
 
 class ModelBlob(C.Structure):
@@ -62,6 +65,7 @@ def load_library():
         lib.mjpc_b200_device_returns.restype = C.c_void_p
         lib.mjpc_b200_host_philox_normal.restype = C.c_double
         lib.mjpc_b200_planner_destroy.argtypes = [C.c_void_p]
+        lib.mjpc_b200_ce_planner_destroy.argtypes = [C.c_void_p]
         for n in ("mjpc_b200_destroy", "mjpc_b200_fetch_stats", "mjpc_b200_launch_count", "mjpc_b200_last_kernel_ms", "mjpc_b200_stream",
                   "mjpc_b200_device_returns", "mjpc_b200_sync", "mjpc_b200_launch_resident"):
             getattr(lib, n).argtypes = [C.c_void_p]
@@ -311,4 +315,62 @@ class CppSamplingPlanner:
     def action_from_policy(self, time, use_previous=False):
         a = np.zeros(self.nu)
         self.lib.mjpc_b200_planner_action_from_policy(self.h, _pd(a), C.c_double(time), int(use_previous))
+        return a
+
+
+class CppCrossEntropyPlanner:
+    """The C++ Cross-Entropy planner (csrc/host/cross_entropy_planner.cc) through its C wrappers."""
+
+    def __init__(self, model, num_trajectory, horizon, n_elite=0, seed=0x5EED, device=0):
+        self.lib = load_library()
+        m = self.m = model
+        self._blob = to_blob(model)
+        self._buf = C.create_string_buffer(self._blob, len(self._blob))
+        mb = ModelBlob(C.cast(self._buf, C.c_void_p), len(self._blob))
+        num = m.numeric
+        self.P = int(num.get("sampling_spline_points", [3])[0])
+        self.horizon, self.N, self.nu = int(horizon), int(num_trajectory), m.nu
+        cr = _d(np.asarray(m.actuator_ctrlrange, float).reshape(-1))
+        h = C.c_void_p()
+        rc = self.lib.mjpc_b200_ce_planner_create(
+            C.byref(mb), self.N, int(n_elite), self.P, int(num.get("sampling_representation", [2])[0]),
+            C.c_double(float(num.get("sampling_exploration", [0.1])[0])), C.c_double(float(num.get("std_min", [0.01])[0])),
+            C.c_double(float(num.get("explore_fraction", [0.0])[0])), C.c_double(float(m.opt_timestep)), _pd(cr),
+            C.c_uint32(seed), self.horizon, int(device), C.byref(h))
+        if rc != 0:
+            raise EngineError(f"mjpc_b200_ce_planner_create failed ({rc}): {self.lib.mjpc_b200_last_error().decode()}")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mjpc_b200_ce_planner_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def reset(self, initial_repeated_action=None):
+        a = _d(initial_repeated_action)
+        self.lib.mjpc_b200_ce_planner_reset(self.h, self.horizon, _pd(a))
+
+    def set_state(self, state, time, mocap):
+        s, mc = _d(state), _d(mocap)
+        self.lib.mjpc_b200_ce_planner_set_state(self.h, _pd(s), C.c_double(time), _pd(mc))
+
+    def optimize_policy(self):
+        rc = self.lib.mjpc_b200_ce_planner_optimize_policy(self.h, self.horizon)
+        if rc != 0:
+            raise EngineError(f"ce_planner_optimize_policy failed: {self.lib.mjpc_b200_last_error().decode()}")
+        return self.result()
+
+    def result(self):
+        imp = C.c_double()
+        ret = np.zeros(self.N + 1, np.float32); order = np.zeros(self.N, np.int32)
+        knots = np.zeros((self.P, self.nu)); kt = np.zeros(self.P); var = np.zeros((self.P, self.nu))
+        self.lib.mjpc_b200_ce_planner_get_result(self.h, C.byref(imp), _pf(ret), order.ctypes.data_as(C.POINTER(C.c_int)),
+                                                 _pd(knots), _pd(kt), _pd(var))
+        return dict(improvement=imp.value, returns=ret, order=order, knots=knots, knot_times=kt, variance=var)
+
+    def action_from_policy(self, time, use_previous=False):
+        a = np.zeros(self.nu)
+        self.lib.mjpc_b200_ce_planner_action_from_policy(self.h, _pd(a), C.c_double(time), int(use_previous))
         return a

@@ -145,3 +145,82 @@ class SamplingPlanner:
 
     def action_from_policy(self, time):
         return clamp(sample_spline(self.times, self.values, self.interp, time), self.ctrlrange)
+
+
+class CrossEntropyPlanner:
+    """Cross-Entropy Method planner (mjpc/planners/cross_entropy/planner.cc) on the same rollout backend.
+
+    Per OptimizePolicy (planner.cc:153-292): resample the nominal to the current time (ResamplePolicy, :343-371),
+    roll out N noisy candidates + the un-noised nominal (Rollouts, :414-459: ONE launch of N+1 candidates here, the
+    nominal is candidate N), rank, then  policy = mean of the n_elite best knot sets, variance = their sample
+    variance (/(n_elite-1)).  Noise (AddNoiseToPolicy, :374-411) is N(0, max(sqrt(variance[k]), std)) per
+    parameter - not scaled by the control range - with std = sampling_exploration for the first
+    explore_fraction*N candidates and std_min for the rest; drawn from the injected Philox stream.
+    BestTrajectory() is the NOMINAL trajectory (:462-464).
+    """
+
+    def __init__(self, model, backend, num_trajectory=None, horizon=None, n_elite=None, seed=0x5EED):
+        m = self.model = model
+        self.backend = backend
+        num = m.numeric
+        self.num_trajectory = int(num_trajectory or num.get("sampling_trajectories", [10])[0])
+        self.P = int(num.get("sampling_spline_points", [3])[0])
+        self.std_initial = float(num.get("sampling_exploration", [0.1])[0])
+        self.std_min = float(num.get("std_min", [0.01])[0])
+        self.explore_fraction = float(num.get("explore_fraction", [0.0])[0])
+        self.n_elite = int(n_elite or num.get("n_elite", [max(self.num_trajectory // 10, 2)])[0])
+        self.interp = int(num.get("sampling_representation", [2])[0])
+        self.timestep = float(m.opt_timestep)
+        self.horizon = int(horizon or max(min(num.get("agent_horizon", [0.5])[0] / self.timestep + 1, 512), 1))
+        self.ctrlrange = np.asarray(m.actuator_ctrlrange, float).reshape(-1, 2)
+        self.seed = seed
+        self.reset()
+
+    def reset(self, initial_repeated_action=None):
+        self.times = np.zeros(1)
+        self.values = np.zeros((1, self.model.nu)) if initial_repeated_action is None else \
+            np.asarray(initial_repeated_action, float)[None]
+        self.variance = np.full((self.P, self.model.nu), self.std_initial ** 2)
+        self.iteration = 0
+        self.improvement = 0.0
+
+    def set_state(self, state, time, mocap):
+        self.state, self.time, self.mocap = np.asarray(state, float), float(time), np.asarray(mocap, float)
+
+    def resample(self):
+        """ResamplePolicy (:343-371): always (horizon-1)*dt/(P-1), also for zero-order splines."""
+        shift = max((self.horizon - 1) * self.timestep / (self.P - 1), 1e-5)
+        new_t = self.time + shift * np.arange(self.P)
+        new_v = np.stack([clamp(sample_spline(self.times, self.values, self.interp, tt), self.ctrlrange) for tt in new_t])
+        return new_t, new_v
+
+    def make_candidates(self, times, nominal):
+        N, P, nu = self.num_trajectory, self.P, self.model.nu
+        z = philox_normal(self.iteration, N, P, nu, self.seed)
+        std = np.where(np.arange(N) < N * self.explore_fraction, self.std_initial, self.std_min)
+        sd = np.maximum(np.sqrt(self.variance)[None], std[:, None, None])
+        k = np.clip(nominal[None] + sd * z, self.ctrlrange[:, 0], self.ctrlrange[:, 1])
+        return np.concatenate([k, nominal[None]], 0)       # candidate N = the nominal trajectory
+
+    def optimize_policy(self):
+        N = self.num_trajectory
+        n_elite = self.n_elite = min(self.n_elite, N)
+        times, nominal = self.resample()
+        knots = self.make_candidates(times, nominal)
+        ret, fail, _ = self.backend.rollout_spline(self.state, self.time, self.mocap, knots, times, self.interp, self.horizon)
+        ret = np.asarray(ret, float)
+        order = np.argsort(ret[:N], kind="stable")
+        elite = knots[order[:n_elite]].astype(float)
+        mean = elite.mean(0)
+        self.variance = ((elite - mean[None]) ** 2).sum(0) / (n_elite - 1)
+        self.times, self.values = times, mean
+        avg_return = float(ret[order[:n_elite]].mean())
+        self.improvement = max(avg_return - float(ret[order[0]]), 0.0)
+        self.nominal_index = N
+        self.order = order
+        self.returns = ret
+        self.iteration += 1
+        return ret, fail
+
+    def action_from_policy(self, time):
+        return clamp(sample_spline(self.times, self.values, self.interp, time), self.ctrlrange)

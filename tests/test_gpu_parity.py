@@ -207,6 +207,51 @@ def test_cpp_host_planner_matches_python_mirror(engines, quadruped):
     cpp.close()
 
 
+def test_cpp_cross_entropy_planner_matches_python_mirror(engines, quadruped):
+    """Cross-Entropy planner (mjpc/planners/cross_entropy/planner.cc): the C++ host class and the Python mirror
+    drive the same rollout ABI with the same injected noise - same elite order, installed mean knots and
+    variance over several iterations; the nominal (candidate N) is the returned best trajectory."""
+    from mujoco_mpc_b200.engine import CppCrossEntropyPlanner
+    from mujoco_mpc_b200.planner import CrossEntropyPlanner
+    m = quadruped
+    state = np.concatenate([m.key_qpos[0], np.zeros(m.nv)])
+    mocap = mocap_of(m)
+    N, H, ne = 48, 32, 6
+    cpp = CppCrossEntropyPlanner(m, N, H, n_elite=ne)
+    py = CrossEntropyPlanner(m, engines("quadruped"), num_trajectory=N, horizon=H, n_elite=ne)
+    cpp.reset(np.zeros(m.nu)); py.reset(np.zeros(m.nu))
+    cpp.set_state(state, 0.0, mocap); py.set_state(state, 0.0, mocap)
+    for it in range(4):
+        rc = cpp.optimize_policy()
+        ret, fail = py.optimize_policy()
+        assert len(rc["returns"]) == N + 1
+        np.testing.assert_allclose(rc["returns"], ret, rtol=1e-5)
+        assert list(rc["order"][:ne]) == list(py.order[:ne]), it
+        np.testing.assert_allclose(rc["knot_times"], py.times, atol=1e-12)
+        np.testing.assert_allclose(rc["knots"], py.values, atol=1e-6)
+        np.testing.assert_allclose(rc["variance"], py.variance, rtol=1e-4, atol=1e-10)
+        assert abs(rc["improvement"] - py.improvement) < 1e-5
+    np.testing.assert_allclose(cpp.action_from_policy(0.1), py.action_from_policy(0.1), atol=1e-6)
+    cpp.close()
+
+
+def test_static_and_generic_kernels_agree(quadruped, monkeypatch):
+    """The statically specialised rollout kernel (csrc/spec_quadruped.h) and the generic one run the same device
+    functions: same returns on the same inputs, and the shipped quadruped model must select the static instance."""
+    from mujoco_mpc_b200.engine import Engine
+    m = quadruped
+    state, mocap, knots, kt = quadruped_inputs(m, N=32, H=64)
+    e = Engine(m, 32, 64)
+    r1, f1, o1 = e.rollout_spline(state, 0.0, mocap, knots, kt, 2, 64)
+    assert e.last_kernel_static, "spec_quadruped.h is stale: run python -m mujoco_mpc_b200.build"
+    monkeypatch.setenv("MJPC_B200_NO_STATIC", "1")
+    r2, f2, o2 = e.rollout_spline(state, 0.0, mocap, knots, kt, 2, 64)
+    assert not e.last_kernel_static
+    np.testing.assert_allclose(r1, r2, rtol=2e-4)
+    assert (f1 == f2).all()
+    e.close()
+
+
 def test_set_task_and_time_rebasing(engines, oracles, quadruped):
     """mjpc_b200_set_task (the per-iteration residual snapshot, agent.cc:316-319) and the host-side time rebasing."""
     from mujoco_mpc_b200 import task as T

@@ -61,3 +61,24 @@ def test_philox_noise_is_reproducible():
     assert np.array_equal(a, b) and not np.array_equal(a, c)
     z = philox_normal(0, 256, 3, 12).ravel()
     assert abs(z.mean()) < 0.05 and abs(z.std() - 1) < 0.05
+
+
+def test_cross_entropy_particle_reaches_goal():
+    """Cross-Entropy planner (mjpc/planners/cross_entropy/planner.cc) on the oracle backend: same behavioural bar as
+    the reference's sampling test, plus the elite statistics (mean/variance of the n_elite best knot sets)."""
+    from mujoco_mpc_b200.planner import CrossEntropyPlanner
+    m = get_model("particle")
+    pl = CrossEntropyPlanner(m, OracleBackend(m, threads=2), num_trajectory=16, horizon=11, n_elite=4)
+    pl.set_state(np.zeros(4), 0.0, mocap_of(m))
+    assert np.allclose(pl.variance, pl.std_initial ** 2)          # Reset: variance = std_initial^2 (planner.cc:141-142)
+    for it in range(60):
+        ret, fail = pl.optimize_policy()
+        assert len(ret) == 17 and not fail.any()                   # N noisy candidates + the nominal
+        # elites: mean of the best n_elite knot sets is the installed policy
+        assert (ret[pl.order[:4]] <= np.sort(ret[:16])[3] + 1e-12).all()
+        assert pl.improvement >= 0
+    tr = pl.backend.fetch_trajectory(pl.nominal_index)            # BestTrajectory() is the nominal (planner.cc:462)
+    assert np.abs(tr["states"][-1, :2] - mocap_of(m)[:2]).max() < 0.1
+    cr = np.asarray(m.actuator_ctrlrange).reshape(-1, 2)
+    assert (np.abs(tr["actions"]) <= cr[:, 1] + 1e-9).all()
+    assert (pl.variance >= 0).all() and pl.variance.shape == (pl.P, m.nu)
