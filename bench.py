@@ -137,6 +137,33 @@ def cpu_baseline_run(steps, warmup, threads):
     return float(np.mean(times)), (state, mocap, knots[-1], kt, ret)
 
 
+def ilqg_probe(m, eng, mocap):
+    """BASELINE config 4 (Quadruped iLQG, H=64, 10 line-search rollouts): wall time of each C-ABI sweep with host
+    buffers (H2D/D2H included), after 3 warm-up planning iterations.  Reported beside the headline, not part of it."""
+    from mujoco_mpc_b200.ilqg import ILQGPlanner
+    pl = ILQGPlanner(m, eng, horizon=HORIZON, num_rollouts=10, fd_tolerance=1e-3)
+    pl.set_state(np.concatenate([m.key_qpos[0], np.zeros(m.nv)]), 0.0, mocap)
+    for _ in range(3):
+        pl.optimize_policy()
+
+    def tm(f, reps=5):
+        f(); t0 = time.perf_counter()
+        for _ in range(reps):
+            out = f()
+        return (time.perf_counter() - t0) / reps * 1e3, out
+    t_fd, (A, B, C, D) = tm(lambda: eng.model_derivatives(pl.states, pl.actions, pl.times, pl.mocap, 1e-3))
+    t_cd, cd = tm(lambda: eng.cost_derivatives(pl.residual, C, D))
+    t_bp, bp = tm(lambda: eng.backward_pass(A, B, cd[0], cd[1], cd[2], cd[4], cd[3], pl.actions, mu=pl.regularization))
+    t_ro, _ = tm(lambda: eng.rollout_feedback(pl.state, 0.0, pl.mocap, pl.actions, pl.states, pl.times, bp["K"], bp["du"],
+                                              pl._steps(), 3))
+    t_it, _ = tm(lambda: pl.optimize_policy())
+    fd_steps = HORIZON * (1 + m.nu + 2 * m.nv)
+    return {"workload": "Quadruped (flat) iLQG, H=64, 10 line-search rollouts, one-sided FD", "fd_sweep_ms": t_fd,
+            "fd_mj_step_equivalents": fd_steps, "fd_steps_per_s": fd_steps / (t_fd * 1e-3), "cost_derivatives_ms": t_cd,
+            "backward_pass_ms": t_bp, "line_search_rollouts_ms": t_ro, "optimize_policy_ms": t_it,
+            "timing": "host wall clock around each C-ABI call, host buffers"}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -270,12 +297,13 @@ def main():
     kernel_ms = float(np.mean(kern_ms))
     achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "kernel": "rollout_kernel", "kernel_ms": kernel_ms, "peak_source": peak_src,
+                "kernel": "rollout_kernel_quadruped" if eng.last_kernel_static else "rollout_kernel", "kernel_ms": kernel_ms, "peak_source": peak_src,
                 "algorithmic_bytes_per_env_step": algorithmic_bytes_per_env_step(m, P),
                 "note": "latency/occupancy-bound by construction: 256 warps, 64 dependent steps each (DESIGN.md)"}
     prof = os.path.join(ROOT, "profiles", "traffic_r01.json")
     if os.path.exists(prof):
         roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+    ilqg = ilqg_probe(m, eng, mocap) if world == 1 else None
     cpu = None
     parity = None
     if not args.no_cpu_baseline:
@@ -304,7 +332,7 @@ def main():
                        "l2": "flushed between timed iterations (256 MB memset)", "sharding": "candidates, %d per GPU" % N_CAND,
                        "e2e_call": "Engine.rollout_spline (mjpc_b200_rollout_spline) + fetch_trajectory(winner), host buffers"},
             "clocks": clk, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(gpu_launches), "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
+            "gpu_launches": int(gpu_launches), "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "ilqg": ilqg,
             "wall_s_timed_region": wall}
     print(json.dumps(line), flush=True)
     if world > 1:
