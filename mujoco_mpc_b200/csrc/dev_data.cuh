@@ -78,6 +78,7 @@ struct Ctx {
   int dbase;  // float index of this warp's state block
   int lane;
   int ncon, nefc, nitem, niter, nlim;
+  int npseudo;  // tendon-limit pseudo-contacts at the tail of the contact list (included in ncon)
   int warn;
   float time;
 #ifdef MJPC_PHASE_TIMING

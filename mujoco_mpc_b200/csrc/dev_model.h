@@ -21,7 +21,8 @@ namespace mjpc_dev {
   X(dof_solimp) X(dof_invweight0) X(geom_size) X(geom_pos) X(geom_quat) X(geom_friction) X(geom_solmix)          \
   X(geom_solref) X(geom_solimp) X(geom_margin) X(geom_gap) X(geom_rbound) X(site_pos) X(site_quat)               \
   X(actuator_gear) X(actuator_gainprm) X(actuator_biasprm) X(actuator_ctrlrange) X(actuator_forcerange)          \
-  X(key_qpos) X(task_weight) X(task_norm_parameter) X(task_parameters) X(task_state)
+  X(key_qpos) X(task_weight) X(task_norm_parameter) X(task_parameters) X(task_state) X(wrap_coef) X(tendon_range)     \
+  X(tendon_margin) X(tendon_solref) X(tendon_solimp) X(tendon_invweight0)
 // ---- int arrays copied verbatim from the blob
 #define MJPC_I_ARRAYS(X)                                                                                         \
   X(body_parentid) X(body_rootid) X(body_jntnum) X(body_jntadr) X(body_dofnum) X(body_dofadr) X(body_mocapid)    \
@@ -29,7 +30,7 @@ namespace mjpc_dev {
   X(dof_parentid) X(geom_type) X(geom_bodyid) X(geom_condim) X(geom_priority) X(site_bodyid) X(actuator_trnid)   \
   X(actuator_biastype) X(actuator_ctrllimited) X(actuator_forcelimited) X(pair_geom1) X(pair_geom2)              \
   X(ray_geoms) X(task_dim_norm_residual) X(task_norm) X(task_num_norm_parameter) X(task_trace_objtype)           \
-  X(task_trace_objid) X(task_ids)
+  X(task_trace_objid) X(task_ids) X(tendon_adr) X(tendon_num) X(tendon_limited) X(wrap_dof) X(wrap_qposadr)
 // ---- int arrays derived on the host for warp-parallel traversal
 //   level_adr/level_body : bodies grouped by tree depth (lanes work on one level at a time)
 //   body_subtreeend      : DFS order => subtree of b is the contiguous range [b, body_subtreeend[b])
@@ -61,12 +62,15 @@ enum IntArrayId {
 enum { GEOM_PLANE = 0, GEOM_HFIELD, GEOM_SPHERE, GEOM_CAPSULE, GEOM_ELLIPSOID, GEOM_CYLINDER, GEOM_BOX };
 enum { JNT_FREE = 0, JNT_BALL, JNT_SLIDE, JNT_HINGE };
 enum { OBJ_BODY = 0, OBJ_XBODY, OBJ_GEOM, OBJ_SITE };
-enum { RESIDUAL_PARTICLE = 0, RESIDUAL_PARTICLE_COPY = 1, RESIDUAL_CARTPOLE = 2, RESIDUAL_QUADRUPED_FLAT = 3 };
+enum { CONE_PYRAMIDAL = 0, CONE_ELLIPTIC = 1 };
+enum { RESIDUAL_PARTICLE = 0, RESIDUAL_PARTICLE_COPY = 1, RESIDUAL_CARTPOLE = 2, RESIDUAL_QUADRUPED_FLAT = 3,
+       RESIDUAL_HUMANOID_STAND = 4 };
 
 // integer fields of the header (sizes, option flags, task dimensions, pack sizes).  A statically specialised
 // kernel (spec_*.h) turns every one of them, and the offset tables below, into compile-time constants.
 #define MJPC_M_INTS(X)                                                                                           \
   X(nq) X(nv) X(nu) X(nbody) X(njnt) X(ngeom) X(nsite) X(nmocap) X(nkey) X(npair) X(nray) X(nlevel) X(nmpair)    \
+  X(ntendon)                                                                                                     \
   X(nfloss) X(nlimit) X(nhpair) X(cone) X(iterations) X(ls_iterations) X(disable_contact) X(disable_eulerdamp)  \
   X(disable_frictionloss) X(disable_limit) X(disable_refsafe) X(disable_warmstart) X(maxcon) X(maxefc)           \
   X(residual_id) X(num_residual) X(num_term) X(num_trace) X(num_parameters) X(task_state_size) X(any_damping)    \
@@ -135,7 +139,7 @@ inline ModelPack pack_model(const void* data, size_t nbytes, int maxcon, int max
   std::memset(&M, 0, sizeof(M));
   M.nq = b.i("nq"); M.nv = b.i("nv"); M.nu = b.i("nu"); M.nbody = b.i("nbody"); M.njnt = b.i("njnt");
   M.ngeom = b.i("ngeom"); M.nsite = b.i("nsite"); M.nmocap = b.i("nmocap"); M.nkey = b.i("nkey");
-  M.npair = b.i("npair");
+  M.npair = b.i("npair"); M.ntendon = b.i("ntendon");
   if (b.i("na") != 0) throw std::runtime_error("actuator activations (na > 0) are not supported");
   M.cone = b.i("opt_cone"); M.iterations = b.i("opt_iterations"); M.ls_iterations = b.i("opt_ls_iterations");
   if (b.i("opt_integrator") != 0) throw std::runtime_error("only the Euler integrator is implemented");
@@ -215,6 +219,18 @@ inline ModelPack pack_model(const void* data, size_t nbytes, int maxcon, int max
       if (!m1 || !m2) continue;
       const uint64_t mm = m1 | m2;
       for (int r = 0; r < nv; r++) if ((mm >> r) & 1) for (int c2 = 0; c2 <= r; c2++) if ((mm >> c2) & 1) pat[(size_t)r * nv + c2] = 1;
+    }
+    {
+      // fixed tendons couple the dofs they wrap (limit rows)
+      auto tadr = b.ints("tendon_adr"), tnum = b.ints("tendon_num"), wdof = b.ints("wrap_dof");
+      for (size_t t = 0; t < tadr.size(); t++) {
+        if (tnum[t] > 16) throw std::runtime_error("a tendon wraps more than 16 dofs (compact Jacobian width)");
+        for (int a = tadr[t]; a < tadr[t] + tnum[t]; a++)
+          for (int c2 = tadr[t]; c2 < tadr[t] + tnum[t]; c2++) {
+            const int r = std::max(wdof[a], wdof[c2]), q = std::min(wdof[a], wdof[c2]);
+            pat[(size_t)r * nv + q] = 1;
+          }
+      }
     }
     std::vector<int> hi_, hj_, frow(nv, -1);
     for (int r = 0; r < nv; r++) for (int c2 = 0; c2 <= r; c2++) if (pat[(size_t)r * nv + c2]) { hi_.push_back(r); hj_.push_back(c2); }

@@ -352,7 +352,7 @@ __device__ __noinline__ void k_collision(Ctx& c) {
   auto&& M = SP::model(c);
   const int lane = c.lane;
   c.ncon = 0;
-  if (M.disable_contact) return;
+  c.npseudo = 0;
   const int *pg1 = MI(pair_geom1), *pg2 = MI(pair_geom2), *gtype = MI(geom_type), *gprio = MI(geom_priority),
             *gcondim = MI(geom_condim);
   const float *gmargin = MF(geom_margin), *ggap = MF(geom_gap), *gsize = MF(geom_size), *grbound = MF(geom_rbound),
@@ -360,12 +360,13 @@ __device__ __noinline__ void k_collision(Ctx& c) {
               *gsolimp = MF(geom_solimp);
   const float *gxpos = DF(geom_xpos), *gxmat = DF(geom_xmat);
   int ncon = 0;
-  for (int base = 0; base < M.npair; base += 32) {
+  const int npair = M.disable_contact ? 0 : M.npair;
+  for (int base = 0; base < npair; base += 32) {
     const int p = base + lane;
     RawContact raw[4];
     int cnt = 0, g1 = 0, g2 = 0;
     float margin = 0, gap = 0;
-    if (p < M.npair) {
+    if (p < npair) {
       g1 = pg1[p]; g2 = pg2[p];
       const int t1 = gtype[g1], t2 = gtype[g2];
       margin = fmaxf(gmargin[g1], gmargin[g2]);
@@ -440,7 +441,40 @@ __device__ __noinline__ void k_collision(Ctx& c) {
     ncon = min(ncon + total, M.maxcon);
     __syncwarp();
   }
-  c.ncon = ncon;
+  // Active limits of fixed tendons ride along as frictionless pseudo-contacts (dim 1) appended after the geometric
+  // contacts: they need exactly what a contact row needs - a short dof list, a compact Jacobian row, dist, margin,
+  // solref/solimp - and every later phase then treats them uniformly.  con_g1 = -(tendon+1) marks them, con_mu
+  // carries the side (+-1).  (Row order therefore differs from the oracle's: tendon limits come after contacts.)
+  int npseudo = 0;
+  if (!M.disable_limit && M.ntendon > 0 && lane == 0) {
+    const int *tadr = MI(tendon_adr), *tnum = MI(tendon_num), *tlim = MI(tendon_limited), *wq = MI(wrap_qposadr);
+    const float *wc = MF(wrap_coef), *trange = MF(tendon_range), *tmargin = MF(tendon_margin);
+    const float* qpos = DF(qpos);
+    for (int t = 0; t < M.ntendon; t++) {
+      if (!tlim[t]) continue;
+      float len = 0.f;
+      for (int w = tadr[t]; w < tadr[t] + tnum[t]; w++) len += wc[w] * qpos[wq[w]];
+      for (int side = -1; side <= 1; side += 2) {
+        const float dd = side * (trange[2 * t + (side + 1) / 2] - len);
+        if (dd < tmargin[t] && ncon + npseudo < M.maxcon) {
+          const int idx = ncon + npseudo;
+          DF(con_dist)[idx] = dd; DF(con_margin)[idx] = tmargin[t];
+          DI(con_g1)[idx] = -(t + 1); DI(con_g2)[idx] = -(t + 1);
+          for (int q = 0; q < 2; q++) DF(con_solref)[2 * idx + q] = MF(tendon_solref)[2 * t + q];
+          for (int q = 0; q < 5; q++) DF(con_solimp)[5 * idx + q] = MF(tendon_solimp)[5 * t + q];
+          for (int q = 0; q < 5; q++) DF(con_friction)[5 * idx + q] = 0.f;
+          DI(con_dim)[idx] = 1;
+          DF(con_mu)[idx] = (float)side;
+          DI(con_adr)[idx] = -1;
+          npseudo++;
+        }
+      }
+    }
+  }
+  npseudo = __shfl_sync(kFull, npseudo, 0);
+  __syncwarp();
+  c.npseudo = npseudo;
+  c.ncon = ncon + npseudo;
 }
 
 // ------------------------------------------------------------------------------------------ constraints
@@ -540,12 +574,23 @@ __device__ __noinline__ void k_make_constraint(Ctx& c) {
   int *cadr = DI(con_adr), *cdim = DI(con_dim), *cnd = DI(con_nd), *cdofl = DI(con_dof), *cloc = DI(con_loc),
       *cboff = DI(con_boff);
   const int *g1a = DI(con_g1), *g2a = DI(con_g2), *gbody = MI(geom_bodyid);
+  const bool pyramidal = M.cone == CONE_PYRAMIDAL;
   for (int w = lane; w < c.ncon * nv; w += 32) cloc[w] = -1;
   __syncwarp();
   {
     const int *chadr = MI(chain_adr), *chnum = MI(chain_num), *chdof = MI(chain_dof);
+    const int *tadr = MI(tendon_adr), *tnum = MI(tendon_num), *wdof = MI(wrap_dof);
     for (int ci = lane; ci < c.ncon; ci += 32) {
       int nd = 0;
+      if (g1a[ci] < 0) {   // tendon-limit pseudo-contact: the wrapped dofs
+        const int t = -g1a[ci] - 1;
+        for (int w = tadr[t]; w < tadr[t] + tnum[t]; w++) {
+          const int dof = wdof[w];
+          if (cloc[ci * nv + dof] < 0 && nd < kL) { cloc[ci * nv + dof] = nd; cdofl[ci * kL + nd] = dof; nd++; }
+        }
+        cnd[ci] = nd;
+        continue;
+      }
       for (int s2 = 0; s2 < 2; s2++) {
         const int bb = gbody[s2 ? g2a[ci] : g1a[ci]];
         for (int q = 0; q < chnum[bb]; q++) {
@@ -560,12 +605,15 @@ __device__ __noinline__ void k_make_constraint(Ctx& c) {
   if (lane == 0) {
     int r = ne, it = nitem, bo = 0;
     for (int ci = 0; ci < c.ncon; ci++) {
-      const int dim = cdim[ci];
+      const int condim = cdim[ci];
+      const bool pyr = pyramidal && condim > 1;
+      const int nrow = pyr ? 2 * (condim - 1) : condim;   // pyramidal cone: two opposing edges per friction direction
       cboff[ci] = bo;
-      if (r + dim > M.maxefc) { cadr[ci] = -1; continue; }
+      if (r + nrow > M.maxefc) { cadr[ci] = -1; continue; }
       cadr[ci] = r;
-      eitem[it++] = r;  // one work item per contact
-      r += dim;
+      if (pyr) { for (int k = 0; k < nrow; k++) eitem[it++] = r + k; }   // independent one-sided rows
+      else eitem[it++] = r;                                               // one work item per contact
+      r += nrow;
       bo += cnd[ci] * (cnd[ci] + 1) / 2;
     }
     cboff[c.ncon] = bo;
@@ -584,6 +632,8 @@ __device__ __noinline__ void k_make_constraint(Ctx& c) {
     for (int w = lane + (M.nfloss + c.nlim) * nvp; w < ne * nvp; w += 32) Jd[w] = 0.f;
     __syncwarp();
     // compact Jacobian entries: one (contact, local dof) pair per lane
+    const int *tadr2 = MI(tendon_adr), *tnum2 = MI(tendon_num), *wdof2 = MI(wrap_dof);
+    const float* wcoef = MF(wrap_coef);
     const int nwork = c.ncon * kL;
     for (int w = lane; w < nwork; w += 32) {
       const int ci = w / kL, l = w - ci * kL;
@@ -591,6 +641,14 @@ __device__ __noinline__ void k_make_constraint(Ctx& c) {
       if (adr < 0 || l >= cnd[ci]) continue;
       const int i = cdofl[ci * kL + l];
       const int dim = cdim[ci];
+      if (g1a[ci] < 0) {   // tendon limit: J = -side * coef on the wrapped dofs
+        const int t = -g1a[ci] - 1;
+        float v = 0.f;
+        for (int w2 = tadr2[t]; w2 < tadr2[t] + tnum2[t]; w2++) if (wdof2[w2] == i) v += -DF(con_mu)[ci] * wcoef[w2];
+        J[adr * kL + l] = v;
+        Jd[adr * nvp + i] = v;
+        continue;
+      }
       const int b1 = gbody[g1a[ci]], b2 = gbody[g2a[ci]];
       float jp[3] = {0, 0, 0}, jr[3] = {0, 0, 0};
       const float* cd = cdof + 6 * i;
@@ -607,6 +665,18 @@ __device__ __noinline__ void k_make_constraint(Ctx& c) {
         for (int q = 0; q < 3; q++) { jp[q] += sg * (cd[3 + q] + t[q]); jr[q] += sg * cd[q]; }
       }
       const float* fr = cframe + 9 * ci;
+      if (pyramidal && dim > 1) {
+        const float* mu = DF(con_friction) + 5 * ci;
+        const float vn = dot3(fr, jp);
+        for (int k = 1; k < dim; k++) {
+          const float* ax = fr + 3 * (k % 3);
+          const float vt = mu[k - 1] * (k < 3 ? dot3(ax, jp) : dot3(ax, jr));
+          const int r0 = adr + 2 * (k - 1);
+          J[r0 * kL + l] = vn + vt; Jd[r0 * nvp + i] = vn + vt;
+          J[(r0 + 1) * kL + l] = vn - vt; Jd[(r0 + 1) * nvp + i] = vn - vt;
+        }
+        continue;
+      }
       for (int k = 0; k < dim; k++) {
         const float* ax = fr + 3 * (k % 3);
         const float v = k < 3 ? dot3(ax, jp) : dot3(ax, jr);
@@ -618,9 +688,27 @@ __device__ __noinline__ void k_make_constraint(Ctx& c) {
     for (int ci = lane; ci < c.ncon; ci += 32) {
       const int adr = cadr[ci];
       if (adr < 0) continue;
+      if (g1a[ci] < 0) {
+        epos[adr] = DF(con_dist)[ci]; emargin[adr] = DF(con_margin)[ci];
+        ediag[adr] = MF(tendon_invweight0)[-g1a[ci] - 1];
+        etype[adr] = CNSTR_CONTACT_FRICTIONLESS; eid[adr] = ci; efloss[adr] = 0;
+        continue;
+      }
       const int b1 = gbody[g1a[ci]], b2 = gbody[g2a[ci]];
       const int dim = cdim[ci];
       const float tran = binvw[2 * b1] + binvw[2 * b2], rot = binvw[2 * b1 + 1] + binvw[2 * b2 + 1];
+      if (pyramidal && dim > 1) {
+        const float* mu = DF(con_friction) + 5 * ci;
+        for (int k = 1; k < dim; k++)
+          for (int e = 0; e < 2; e++) {
+            const int r = adr + 2 * (k - 1) + e;
+            epos[r] = DF(con_dist)[ci]; emargin[r] = DF(con_margin)[ci];
+            ediag[r] = tran + mu[k - 1] * mu[k - 1] * (k < 3 ? tran : rot);
+            etype[r] = CNSTR_CONTACT_FRICTIONLESS;   // a pyramid edge is a one-sided quadratic row
+            eid[r] = ci; efloss[r] = 0;
+          }
+        continue;
+      }
       for (int k = 0; k < dim; k++) {
         const int r = adr + k;
         epos[r] = k == 0 ? DF(con_dist)[ci] : 0.f;
@@ -668,6 +756,15 @@ __device__ __noinline__ void k_make_constraint(Ctx& c) {
       const int a = cadr[ci], dim = cdim[ci];
       if (a < 0 || dim == 1) continue;
       const float* fr = DF(con_friction) + 5 * ci;
+      if (pyramidal) {
+        // all edges share R = 2 mu^2 R_first; from here on con_dim is the contact's ROW count
+        const float mu = fr[0] * sqrtf(1.f / fmaxf(kMinVal, CM(c).impratio));
+        const float Rpy = 2.f * mu * mu * R[a];
+        for (int j = 0; j < 2 * (dim - 1); j++) R[a + j] = Rpy;
+        DF(con_mu)[ci] = mu;
+        cdim[ci] = 2 * (dim - 1);
+        continue;
+      }
       R[a + 1] = R[a] / fmaxf(kMinVal, CM(c).impratio);
       DF(con_mu)[ci] = fr[0] * sqrtf(R[a + 1] / R[a]);
       for (int j = 1; j < dim - 1; j++) R[a + j + 1] = R[a + 1] * fr[0] * fr[0] / (fr[j] * fr[j]);

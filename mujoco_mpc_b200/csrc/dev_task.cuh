@@ -542,6 +542,25 @@ __device__ __noinline__ void k_residual(Ctx& c) {
       __syncwarp();
       break;
     case RESIDUAL_QUADRUPED_FLAT: k_residual_quadruped<SP>(c); break;
+    case RESIDUAL_HUMANOID_STAND: {
+      // mjpc/tasks/humanoid/stand/stand.cc:30-97; task_ids = {torso body, head body, sites sp0..sp3}
+      const int* I = MI(task_ids);
+      const float *sx = DF(site_xpos), *head = DF(xipos) + 3 * I[1], *com = DF(subtree_com) + 3 * I[0],
+                  *vel = DF(subtree_linvel) + 3 * I[0];
+      if (lane == 0) {
+        float favg[3] = {0, 0, 0};
+        for (int k = 0; k < 4; k++)
+          for (int q = 0; q < 3; q++) favg[q] += 0.25f * sx[3 * I[2 + k] + q];
+        r[0] = head[2] - favg[2] - MF(task_parameters)[0];
+        const float dx = favg[0] - (com[0] + vel[0] * 0.2f), dy = favg[1] - (com[1] + vel[1] * 0.2f);
+        r[1] = sqrtf(dx * dx + dy * dy);
+        r[2] = vel[0]; r[3] = vel[1];
+      }
+      for (int i = lane; i < M.nv - 6; i += 32) r[4 + i] = DF(qvel)[6 + i];
+      for (int i = lane; i < M.nu; i += 32) r[4 + M.nv - 6 + i] = DF(ctrl)[i];
+      __syncwarp();
+      break;
+    }
     default: break;
   }
 }

@@ -437,6 +437,113 @@ __device__ inline int box_qp_serial(float* res, float* R, int* index, const floa
   return nfree;
 }
 
+// ---- warp-parallel versions (warp 0 of the CTA; n <= 32; lane i owns element / row i).  Same algorithm and
+// constants as the serial code above; the left-looking Cholesky and the forward substitution subtract in the
+// same order as the serial loops, reductions are butterfly sums (identical in every lane, so control flow stays
+// warp-uniform).  The serial box-QP was 59 % of the backward pass (profiles/README.md, prof_r01_bp).
+__device__ inline float chol_warp(float* A, int n, int lane) {
+  float minp = 3.4e38f;
+  for (int j = 0; j < n; j++) {
+    float s = 0.f;
+    if (lane >= j && lane < n) {
+      s = A[lane * n + j];
+      for (int k = 0; k < j; k++) s -= A[lane * n + k] * A[j * n + k];
+    }
+    float piv = __shfl_sync(kFull, s, j);
+    minp = fminf(minp, piv);
+    if (piv < 1e-15f) piv = 1e-15f;
+    const float l = sqrtf(piv);
+    if (lane == j) A[j * n + j] = l;
+    else if (lane > j && lane < n) A[lane * n + j] = s / l;
+    __syncwarp();
+  }
+  return minp;
+}
+// x = (L L^T)^-1 b for lane < n (value returned per lane; b passed per lane)
+__device__ inline float chol_solve_warp(const float* L, float b, int n, int lane) {
+  float y = b;
+  for (int i = 0; i < n; i++) {
+    const float xi = __shfl_sync(kFull, y, i) / L[i * n + i];
+    if (lane == i) y = xi;
+    else if (lane > i && lane < n) y -= L[lane * n + i] * xi;
+  }
+  for (int i = n - 1; i >= 0; i--) {
+    const float xi = __shfl_sync(kFull, y, i) / L[i * n + i];
+    if (lane == i) y = xi;
+    else if (lane < i) y -= L[i * n + lane] * xi;
+  }
+  return y;
+}
+// scratch >= 2n floats.  res/R/index as in box_qp_serial; returns nfree or -1 (not positive definite)
+__device__ inline int box_qp_warp(float* res, float* R, int* index, const float* Hm, const float* g, int n,
+                                  const float* lower, const float* upper, float* scratch, int lane) {
+  const int maxiter = 100;
+  const float mingrad = 1e-6f, backtrack = 0.5f, minstep = 1e-7f, armijo = 0.01f;
+  float *xs = scratch, *ts = scratch + n;        // shared copies of the current iterate / a temporary vector
+  const bool act = lane < n;
+  const float lo = act ? lower[lane] : 0.f, hi = act ? upper[lane] : 0.f, gi = act ? g[lane] : 0.f;
+  float x = act ? fmaxf(lo, fminf(hi, res[lane])) : 0.f;
+  auto hrow = [&](const float* v) { float a = 0.f; if (act) for (int j = 0; j < n; j++) a += Hm[lane * n + j] * v[j]; return a; };
+  auto value_of = [&](float xv) {   // xv: this lane's element; the vector is published through ts
+    if (act) ts[lane] = xv;
+    __syncwarp();
+    const float a = hrow(ts);
+    const float v = warp_sum(act ? xv * (0.5f * a + gi) : 0.f);
+    __syncwarp();
+    return v;
+  };
+  float value = value_of(x);
+  const float gscale = warp_sum(gi * gi);
+  int nfree = 0, clamped = 0;
+  for (int iter = 0; iter < maxiter; iter++) {
+    if (act) xs[lane] = x;
+    __syncwarp();
+    const float grad = gi + hrow(xs);
+    const int cl = act && ((x == lo && grad > 0) || (x == hi && grad < 0));
+    bool changed = iter == 0 || __any_sync(kFull, cl != clamped);
+    clamped = cl;
+    const unsigned fmask = __ballot_sync(kFull, act && !cl);
+    nfree = __popc(fmask);
+    const int pos = __popc(fmask & ((1u << lane) - 1u));
+    if (act && !cl) index[pos] = lane;
+    __syncwarp();
+    if (nfree == 0) break;
+    if (changed) {
+      for (int e = lane; e < nfree * nfree; e += 32) { const int a = e / nfree, b = e - a * nfree; R[e] = Hm[index[a] * n + index[b]]; }
+      __syncwarp();
+      if (!(chol_warp(R, nfree, lane) > 1e-15f)) return -1;
+    }
+    const float norm2 = warp_sum((act && !cl) ? grad * grad : 0.f);
+    if (norm2 < mingrad * mingrad * (1.f + gscale)) break;
+    if (act) ts[lane] = cl ? x : 0.f;
+    __syncwarp();
+    float rhs = 0.f;
+    if (lane < nfree) { const int i = index[lane]; rhs = g[i]; for (int j = 0; j < n; j++) rhs += Hm[i * n + j] * ts[j]; }
+    __syncwarp();
+    const float sol = chol_solve_warp(R, rhs, nfree, lane);
+    if (lane < nfree) ts[index[lane]] = sol;     // scatter the free solution back to full indexing
+    __syncwarp();
+    const float search = (act && !cl) ? -ts[lane] - x : 0.f;
+    __syncwarp();
+    const float sdotg = warp_sum(search * grad);
+    if (sdotg >= 0) break;
+    float step = 1, vc = value, cand = x;
+    bool accepted = false;
+    while (step > minstep) {
+      cand = act ? fmaxf(lo, fminf(hi, x + step * search)) : 0.f;
+      vc = value_of(cand);
+      if ((vc - value) / (step * sdotg) >= armijo) { accepted = true; break; }
+      step *= backtrack;
+    }
+    if (!accepted) break;
+    x = cand;
+    value = vc;
+  }
+  if (act) res[lane] = x;
+  __syncwarp();
+  return nfree;
+}
+
 // dynamic smem layout (floats): At[n*n] Bt[n*m] W[n*n] T1[n*n] Qxx[n*n] Qxu[n*m] Quu[m*m] QxuR[n*m] QuuR[m*m]
 //   K[m*n] Wx[n] Qx[n] Qu[m] du[m] Qd[m] qp_res[m] qp_R[m*m] qp_lo[m] qp_hi[m] scratch[8m] + index[m] ints
 extern "C" __global__ void __launch_bounds__(256) backward_pass_kernel(const __grid_constant__ BackwardArgs P) {
@@ -498,27 +605,28 @@ extern "C" __global__ void __launch_bounds__(256) backward_pass_kernel(const __g
     }
     for (int e = tid; e < m * n; e += nt) K[e] = 0;
     __syncthreads();
-    // control step: box QP (or plain solve) on one thread, gains on all threads
-    if (tid == 0) {
+    // control step: box QP (or plain solve) on warp 0, gains on all threads
+    if (tid < 32) {
       int mf;
       if (P.limits == 1) {
-        for (int i = 0; i < m; i++) {
-          qp_lo[i] = P.ctrlrange[2 * i] - P.actions[(size_t)t * m + i];
-          qp_hi[i] = P.ctrlrange[2 * i + 1] - P.actions[(size_t)t * m + i];
+        if (tid < m) {
+          qp_lo[tid] = P.ctrlrange[2 * tid] - P.actions[(size_t)t * m + tid];
+          qp_hi[tid] = P.ctrlrange[2 * tid + 1] - P.actions[(size_t)t * m + tid];
         }
-        mf = box_qp_serial(qp_res, qp_R, qp_index, QuuR, Qu, m, qp_lo, qp_hi, scratch);
-        if (mf >= 0) for (int i = 0; i < m; i++) du[i] = qp_res[i];
+        __syncwarp();
+        mf = box_qp_warp(qp_res, qp_R, qp_index, QuuR, Qu, m, qp_lo, qp_hi, scratch, tid);
+        if (mf >= 0 && tid < m) du[tid] = qp_res[tid];
       } else {
-        for (int i = 0; i < m * m; i++) qp_R[i] = QuuR[i];
-        mf = (chol_serial(qp_R, m) > 1e-15f) ? m : -1;
+        for (int i = tid; i < m * m; i += 32) qp_R[i] = QuuR[i];
+        __syncwarp();
+        mf = (chol_warp(qp_R, m, tid) > 1e-15f) ? m : -1;
         if (mf >= 0) {
-          for (int i = 0; i < m; i++) qp_index[i] = i;
-          chol_solve_serial(du, qp_R, Qu, m);
-          for (int i = 0; i < m; i++) du[i] = -du[i];
+          if (tid < m) qp_index[tid] = tid;
+          const float sol = chol_solve_warp(qp_R, tid < m ? Qu[tid] : 0.f, m, tid);
+          if (tid < m) du[tid] = -sol;
         }
       }
-      s_mf = mf;
-      if (mf < 0) s_ok = 0;
+      if (tid == 0) { s_mf = mf; if (mf < 0) s_ok = 0; }
     }
     __syncthreads();
     if (!s_ok) break;

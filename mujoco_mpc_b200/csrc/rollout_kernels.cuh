@@ -80,7 +80,7 @@ __device__ __forceinline__ void init_ctx(Ctx& c, const DevModel* M, const DevLay
   c.hdr = hdr; c.lay = lay; c.ibase = M->nf;
   c.dbase = data0 + warp * L->total;
   c.lane = lane;
-  c.ncon = 0; c.nefc = 0; c.nitem = 0; c.niter = 0; c.nlim = 0; c.warn = 0; c.time = 0.f;
+  c.ncon = 0; c.npseudo = 0; c.nefc = 0; c.nitem = 0; c.niter = 0; c.nlim = 0; c.warn = 0; c.time = 0.f;
 #ifdef MJPC_PHASE_TIMING
   for (int k = 0; k < 8; k++) c.tph[k] = 0;
   c.tlast = clock64();
@@ -157,7 +157,7 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& A) {
     }
     if (!last && (k_bad(c, DF(qpos), nq) || k_bad(c, DF(qvel), nv))) { failed = true; break; }
     k_forward<SP>(c);
-    n_newton += c.niter; n_con += c.ncon; n_efc += c.nefc;
+    n_newton += c.niter; n_con += c.ncon - c.npseudo; n_efc += c.nefc;
     k_residual<SP>(c);
     if (!last && k_bad(c, DF(qacc), nv)) c.warn = 1;
     for (int i = lane; i < nr; i += 32) o_res[(size_t)t * nr + i] = DF(residual)[i];
@@ -265,7 +265,7 @@ extern "C" __global__ void __launch_bounds__(32) step_debug_kernel(const __grid_
   for (int i = lane; i < nv * nv; i += 32) A.qM[i] = DF(qM)[i];
   for (int i = lane; i < M.num_residual; i += 32) A.residual[i] = DF(residual)[i];
   for (int i = lane; i < c.nefc; i += 32) A.efc_force[i] = DF(efc_force)[i];
-  if (lane == 0) { A.counts[0] = c.ncon; A.counts[1] = c.nefc; A.counts[2] = c.niter; A.counts[3] = c.warn; }
+  if (lane == 0) { A.counts[0] = c.ncon - c.npseudo; A.counts[1] = c.nefc; A.counts[2] = c.niter; A.counts[3] = c.warn; }
   k_euler<SP>(c);
   for (int i = lane; i < nq; i += 32) A.next_qpos[i] = DF(qpos)[i];
   for (int i = lane; i < nv; i += 32) A.next_qvel[i] = DF(qvel)[i];

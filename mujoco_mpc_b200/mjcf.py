@@ -597,6 +597,40 @@ class Compiler:
             for ch in sec.findall("exclude"):
                 excl.append((m.body_names.index(ch.get("body1")), m.body_names.index(ch.get("body2"))))
         m.exclude = excl
+        # fixed tendons (length = sum coef * qpos of scalar joints); spatial tendons are not supported
+        t_adr, t_num, w_dof, w_qadr, w_coef = [], [], [], [], []
+        t_lim, t_range, t_margin, t_solref, t_solimp, names = [], [], [], [], [], []
+        for sec in self.root.findall("tendon"):
+            for ch in sec:
+                if ch.tag != "fixed":
+                    raise NotImplementedError("only <fixed> tendons are supported")
+                a = self.defaults.get("tendon", ch.get("class", "main"))
+                a.update(ch.attrib)
+                if float(a.get("stiffness", 0)) != 0 or float(a.get("damping", 0)) != 0 or float(a.get("frictionloss", 0)) != 0:
+                    raise NotImplementedError("tendon stiffness / damping / frictionloss are not supported")
+                t_adr.append(len(w_dof)); names.append(ch.get("name", ""))
+                for w in ch.findall("joint"):
+                    j = m.jnt_names.index(w.get("joint"))
+                    if m.jnt_type[j] not in (JNT_SLIDE, JNT_HINGE):
+                        raise NotImplementedError("fixed tendons over free/ball joints")
+                    w_dof.append(int(m.jnt_dofadr[j])); w_qadr.append(int(m.jnt_qposadr[j])); w_coef.append(float(w.get("coef")))
+                t_num.append(len(w_dof) - t_adr[-1])
+                rng = _f(a.get("range"), 2, [0, 0])
+                lim = a.get("limited", "auto")
+                t_lim.append(1 if lim == "true" or (lim == "auto" and "range" in a and self.autolimits) else 0)
+                t_range.append(rng); t_margin.append(float(a.get("margin", 0)))
+                t_solref.append(_f(a.get("solreflimit"), 2, [0.02, 1]))
+                t_solimp.append(_f(a.get("solimplimit"), 5, [0.9, 0.95, 0.001, 0.5, 2]))
+        nt = len(t_adr)
+        m.ntendon = nt
+        m.tendon_names = names
+        m.tendon_adr, m.tendon_num = np.array(t_adr, np.int32), np.array(t_num, np.int32)
+        m.wrap_dof, m.wrap_qposadr, m.wrap_coef = np.array(w_dof, np.int32), np.array(w_qadr, np.int32), np.array(w_coef, float)
+        m.tendon_limited = np.array(t_lim, np.int32)
+        m.tendon_range = np.array(t_range, float).reshape(nt, 2)
+        m.tendon_margin = np.array(t_margin, float)
+        m.tendon_solref = np.array(t_solref, float).reshape(nt, 2)
+        m.tendon_solimp = np.array(t_solimp, float).reshape(nt, 5)
 
     def _parse_sensors(self, m):
         sens = []
@@ -700,8 +734,17 @@ class Compiler:
                 biw[b, 1] = max(MINVAL, (A[3, 3] + A[4, 4] + A[5, 5]) / 3)
             m.body_invweight0 = biw
             m.stat_meaninertia = float(np.mean(np.diag(M)))
+            # tendon_invweight0 = J M^-1 J^T at qpos0 (set0 in MuJoCo's compiler)
+            tiw = np.zeros(m.ntendon)
+            for t in range(m.ntendon):
+                J = np.zeros(nv)
+                for w in range(m.tendon_adr[t], m.tendon_adr[t] + m.tendon_num[t]):
+                    J[m.wrap_dof[w]] += m.wrap_coef[w]
+                tiw[t] = max(MINVAL, float(J @ Minv @ J))
+            m.tendon_invweight0 = tiw
         else:
             m.dof_invweight0 = np.zeros(0); m.body_invweight0 = np.zeros((m.nbody, 2)); m.stat_meaninertia = 1.0
+            m.tendon_invweight0 = np.zeros(m.ntendon)
         m.M0 = M
 
     # -------------------------------------------------------- static candidate pair list

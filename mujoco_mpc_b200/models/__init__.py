@@ -285,6 +285,186 @@ def quadruped_flat_xml(horizon=0.63, trajectories=256) -> str:
 """
 
 
+def _humanoid_leg(side: str, sy: int) -> str:
+    """One leg of the MJPC humanoid (mjpc/tasks/humanoid/humanoid.xml.patch:147-201); sy = -1 right, +1 left."""
+    s = "right" if side == "r" else "left"
+    ax_x = "1 0 0" if sy < 0 else "-1 0 0"
+    ax_z = "0 0 1" if sy < 0 else "0 0 -1"
+    ankle_x = "1 0 .5" if sy < 0 else "-1 0 -.5"
+    sp_a, sp_b = ("sp2", "sp3") if sy < 0 else ("sp0", "sp1")
+    return f"""
+          <body name="thigh_{s}" pos="0 {0.1 * sy} -.04">
+            <site name="tracking[{side}hip]" class="tracking_site" pos="0 {-0.025 * sy} 0.025"/>
+            <joint name="hip_x_{s}" axis="{ax_x}" class="hip_x"/>
+            <joint name="hip_z_{s}" axis="{ax_z}" class="hip_z"/>
+            <joint name="hip_y_{s}" class="hip_y"/>
+            <geom name="thigh_{s}" fromto="0 0 0 0 {-0.01 * sy} -.34" class="thigh"/>
+            <body name="shin_{s}" pos="0 {-0.01 * sy} -.4">
+              <joint name="knee_{s}" class="knee"/>
+              <site name="tracking[{side}knee]" class="tracking_site" pos="0 0 0.05"/>
+              <geom name="shin_{s}" class="shin"/>
+              <body name="foot_{s}" pos="0 0 -.39">
+                <joint name="ankle_y_{s}" class="ankle_y"/>
+                <joint name="ankle_x_{s}" class="ankle_x" axis="{ankle_x}"/>
+                <geom name="foot1_{s}" class="foot1"/>
+                <geom name="foot2_{s}" class="foot2"/>
+                <site name="foot_{s}" pos=".05 {-0.03 * sy} 0" type="sphere" size=".027"/>
+                <site name="{sp_a}" pos="-.07 0 0" type="sphere" size=".027"/>
+                <site name="{sp_b}" pos=".14 0 0" type="sphere" size=".027"/>
+                <body name="heel_{s}" pos="-0.05 0 0.04">
+                  <site name="tracking[{side}heel]" class="tracking_site"/>
+                </body>
+                <body name="toe_{s}" pos="0.07 0 -0.01">
+                  <site name="tracking[{side}toe]" class="tracking_site"/>
+                </body>
+              </body>
+            </body>
+          </body>"""
+
+
+def _humanoid_arm(side: str, sy: int) -> str:
+    """One arm (humanoid.xml.patch:258-287); sy = -1 right, +1 left."""
+    s = "right" if side == "r" else "left"
+    sh1 = "2 1 1" if sy < 0 else "-2 1 -1"
+    sh2 = "0 -1 1" if sy < 0 else "0 -1 -1"
+    elb = "0 -1 1" if sy < 0 else "0 -1 -1"
+    y = -sy   # right arm extends towards -y
+    return f"""
+      <body name="upper_arm_{s}" pos="0 {0.17 * sy} .06">
+        <site name="tracking[{side}shoulder]" class="tracking_site"/>
+        <joint name="shoulder1_{s}" axis="{sh1}" class="shoulder"/>
+        <joint name="shoulder2_{s}" axis="{sh2}" class="shoulder"/>
+        <geom name="upper_arm_{s}" fromto="0 0 0 .16 {0.16 * sy} -.16" class="arm_upper"/>
+        <body name="lower_arm_{s}" pos=".18 {0.18 * sy} -.18">
+          <joint name="elbow_{s}" axis="{elb}" class="elbow"/>
+          <site name="tracking[{side}elbow]" class="tracking_site"/>
+          <site name="tracking[{side}hand]" class="tracking_site" pos="0.13 {0.13 * y} 0.13"/>
+          <geom name="lower_arm_{s}" fromto=".01 {0.01 * y} .01 .17 {0.17 * y} .17" class="arm_lower"/>
+          <body name="hand_{s}" pos=".18 {0.18 * y} .18">
+            <geom name="hand_{s}" class="hand"/>
+          </body>
+        </body>
+      </body>"""
+
+
+_HUMANOID_ACTUATORS = (("abdomen_y", 40), ("abdomen_z", 40), ("abdomen_x", 40),
+                       ("hip_x_right", 40), ("hip_z_right", 40), ("hip_y_right", 120), ("knee_right", 100),
+                       ("ankle_x_right", 20), ("ankle_y_right", 20),
+                       ("hip_x_left", 40), ("hip_z_left", 40), ("hip_y_left", 120), ("knee_left", 100),
+                       ("ankle_x_left", 20), ("ankle_y_left", 20),
+                       ("shoulder1_right", 20), ("shoulder2_right", 20), ("elbow_right", 40),
+                       ("shoulder1_left", 20), ("shoulder2_left", 20), ("elbow_left", 40))
+
+
+def humanoid_stand_xml(horizon=0.35, trajectories=10) -> str:
+    """MJPC "Humanoid Stand": the modified dm_control humanoid (every body, joint, geom, tendon and actuator is
+    spelled out by mjpc/tasks/humanoid/humanoid.xml.patch) + mjpc/tasks/humanoid/stand/task.xml.
+    Physics features beyond the A1: pyramidal friction cones (MuJoCo's default cone), joint springs, several
+    hinges per body, two fixed tendons with limits, motors with gears 20-120."""
+    acts = "".join(f'<motor name="{n}" gear="{g}" joint="{n}"/>' for n, g in _HUMANOID_ACTUATORS)
+    return f"""
+<mujoco model="Humanoid">
+  <custom>
+    <numeric name="agent_planner" data="0"/>
+    <numeric name="agent_horizon" data="{horizon}"/>
+    <numeric name="agent_timestep" data="0.015"/>
+    <numeric name="sampling_spline_points" data="3"/>
+    <numeric name="sampling_exploration" data="0.05"/>
+    <numeric name="sampling_trajectories" data="{trajectories}"/>
+    <numeric name="gradient_spline_points" data="5"/>
+    <numeric name="residual_Height Goal" data="1.4 0.0 1.5"/>
+  </custom>
+  <default>
+    <motor ctrlrange="-1 1" ctrllimited="true"/>
+    <site size=".04" group="3"/>
+    <default class="body">
+      <geom type="capsule" condim="1" friction=".7" solimp=".9 .99 .003" solref=".015 1"/>
+      <default class="thigh"><geom size=".06"/></default>
+      <default class="shin"><geom fromto="0 0 0 0 0 -.3" size=".049"/></default>
+      <default class="foot">
+        <geom size=".027"/>
+        <default class="foot1"><geom fromto="-.07 -.01 0 .14 -.03 0"/></default>
+        <default class="foot2"><geom fromto="-.07 .01 0 .14 .03 0"/></default>
+      </default>
+      <default class="arm_upper"><geom size=".04"/></default>
+      <default class="arm_lower"><geom size=".031"/></default>
+      <default class="hand"><geom type="sphere" size=".04"/></default>
+      <joint type="hinge" damping=".2" stiffness="1" armature=".01" limited="true" solimplimit="0 .99 .01"/>
+      <default class="joint_big">
+        <joint damping="5" stiffness="10"/>
+        <default class="hip_x"><joint range="-30 10"/></default>
+        <default class="hip_z"><joint range="-60 35"/></default>
+        <default class="hip_y"><joint axis="0 1 0" range="-150 20"/></default>
+        <default class="joint_big_stiff"><joint stiffness="20"/></default>
+      </default>
+      <default class="knee"><joint pos="0 0 .02" axis="0 -1 0" range="-160 2"/></default>
+      <default class="ankle">
+        <joint range="-50 50"/>
+        <default class="ankle_y"><joint pos="0 0 .08" axis="0 1 0" stiffness="6"/></default>
+        <default class="ankle_x"><joint pos="0 0 .04" stiffness="3"/></default>
+      </default>
+      <default class="shoulder"><joint range="-85 60"/></default>
+      <default class="elbow"><joint range="-100 50" stiffness="0"/></default>
+      <default class="tracking_site"><site type="sphere" size="0.027" group="3"/></default>
+    </default>
+  </default>
+  <worldbody>
+    <geom name="floor" type="plane" conaffinity="1" size="50 50 .05"/>
+    <body name="torso" pos="0 0 1.282" childclass="body">
+      <freejoint name="root"/>
+      <geom name="torso" fromto="0 -.07 0 0 .07 0" size=".07"/>
+      <geom name="waist_upper" fromto="-.01 -.06 -.12 -.01 .06 -.12" size=".06"/>
+      <body name="head" pos="0 0 .19">
+        <geom name="head" type="sphere" size=".09"/>
+        <site name="tracking[head]" class="tracking_site" pos="0.09 0 0"/>
+      </body>
+      <body name="waist_lower" pos="-.01 0 -.26">
+        <geom name="waist_lower" fromto="0 -.06 0 0 .06 0" size=".06"/>
+        <joint name="abdomen_z" pos="0 0 .065" axis="0 0 1" range="-45 45" class="joint_big_stiff"/>
+        <joint name="abdomen_y" pos="0 0 .065" axis="0 1 0" range="-75 30" class="joint_big"/>
+        <body name="pelvis" pos="0 0 -.165">
+          <site name="tracking[pelvis]" class="tracking_site" pos="0 0 0.075" size=".05"/>
+          <joint name="abdomen_x" pos="0 0 .1" axis="1 0 0" range="-35 35" class="joint_big"/>
+          <geom name="butt" fromto="-.02 -.07 0 -.02 .07 0" size=".09"/>{_humanoid_leg("r", -1)}{_humanoid_leg("l", 1)}
+        </body>
+      </body>{_humanoid_arm("r", -1)}{_humanoid_arm("l", 1)}
+    </body>
+  </worldbody>
+  <contact>
+    <exclude body1="waist_lower" body2="thigh_right"/>
+    <exclude body1="waist_lower" body2="thigh_left"/>
+  </contact>
+  <tendon>
+    <fixed name="hamstring_right" limited="true" range="-0.3 2">
+      <joint joint="hip_y_right" coef=".5"/>
+      <joint joint="knee_right" coef="-.5"/>
+    </fixed>
+    <fixed name="hamstring_left" limited="true" range="-0.3 2">
+      <joint joint="hip_y_left" coef=".5"/>
+      <joint joint="knee_left" coef="-.5"/>
+    </fixed>
+  </tendon>
+  <actuator>{acts}</actuator>
+  <sensor>
+    <user name="Height" dim="1" user="6 100.0 0.0 100.0 0.1"/>
+    <user name="Balance" dim="1" user="6 50.0 0.0 100.0 0.1"/>
+    <user name="CoM Vel." dim="2" user="0 10.0 0.0 100.0"/>
+    <user name="Joint Vel." dim="21" user="0 0.01 0.0 0.1"/>
+    <user name="Control" dim="21" user="3 0.025 0.0 0.1 0.3"/>
+    <framepos name="trace0" objtype="body" objname="torso"/>
+    <framepos name="torso_position" objtype="body" objname="torso"/>
+    <framepos name="head_position" objtype="body" objname="head"/>
+    <subtreelinvel name="torso_subtreelinvel" body="torso"/>
+    <subtreecom name="torso_subtreecom" body="torso"/>
+    <framepos name="sp0" objtype="site" objname="sp0"/>
+    <framepos name="sp1" objtype="site" objname="sp1"/>
+    <framepos name="sp2" objtype="site" objname="sp2"/>
+    <framepos name="sp3" objtype="site" objname="sp3"/>
+  </sensor>
+</mujoco>
+"""
+
+
 def _robot_vs_world_only(m, g1, g2):
     """Keep only pairs with exactly one static (world-welded) geom: robot self-collision pairs are
     dropped (DESIGN.md 'Out of scope': most need capsule/cylinder/box convex tests)."""
@@ -336,6 +516,16 @@ def load(name: str, agent_timestep: bool = True, **kw):
         m.task_ids = ids
         m.task_state = T.quadruped_state_block(float(np.linalg.norm(m.opt_gravity)),
                                                float(m.task_parameters[pn.index("Cadence")]))
+    elif name == "humanoid":
+        m = compile_xml(humanoid_stand_xml(**kw), pair_filter=_robot_vs_world_only)
+        m.task_residual_id = T.RESIDUAL_HUMANOID_STAND
+        ids = np.zeros(T.HI_SIZE, np.int32)
+        ids[T.HI_TORSO_BODY] = m.body_names.index("torso")
+        ids[T.HI_HEAD_BODY] = m.body_names.index("head")
+        for k in range(4):
+            ids[T.HI_SITE_SP0 + k] = m.site_names.index("sp%d" % k)
+        m.task_ids = ids
+        m.task_state = np.zeros(1)
     else:
         raise KeyError(name)
     m.task_name = name

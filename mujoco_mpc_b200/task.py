@@ -19,6 +19,9 @@ RESIDUAL_PARTICLE = 0        # mjpc/test/testdata/particle_residual.h:22-52
 RESIDUAL_PARTICLE_COPY = 1   # mjpc/test/agent/rollout_test.cc:25-50
 RESIDUAL_CARTPOLE = 2        # mjpc/tasks/cartpole/cartpole.cc:36-49
 RESIDUAL_QUADRUPED_FLAT = 3  # mjpc/tasks/quadruped/quadruped.cc:33-226
+RESIDUAL_HUMANOID_STAND = 4  # mjpc/tasks/humanoid/stand/stand.cc:30-97
+# task_ids layout of the humanoid stand residual
+HI_TORSO_BODY, HI_HEAD_BODY, HI_SITE_SP0, HI_SIZE = 0, 1, 2, 6
 
 # quadruped task-state block layout (doubles); ResidualFn members, quadruped.h:160-225
 QS_MODE, QS_MODE_START_TIME, QS_POSITION, QS_HEADING, QS_SPEED, QS_ANGVEL, QS_GROUND = 0, 1, 2, 5, 7, 8, 9

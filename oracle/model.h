@@ -63,7 +63,7 @@ struct BlobReader {
 template <class T>
 struct Model {
   // sizes
-  int nq, nv, nu, na, nbody, njnt, ngeom, nsite, nmocap, nkey, nuserdata, nsensordata, npair;
+  int nq, nv, nu, na, nbody, njnt, ngeom, nsite, nmocap, nkey, nuserdata, nsensordata, npair, ntendon;
   // options
   T timestep, impratio, tolerance, ls_tolerance, meaninertia;
   T gravity[3];
@@ -88,6 +88,9 @@ struct Model {
   std::vector<T> actuator_gear, actuator_gainprm, actuator_biasprm, actuator_ctrlrange, actuator_forcerange;
   // collision candidates, ray-cast set
   std::vector<int> pair_geom1, pair_geom2, ray_geoms;
+  // fixed tendons (length = sum coef * qpos)
+  std::vector<int> tendon_adr, tendon_num, tendon_limited, wrap_dof, wrap_qposadr;
+  std::vector<T> wrap_coef, tendon_range, tendon_margin, tendon_solref, tendon_solimp, tendon_invweight0;
   // keyframes
   std::vector<T> key_qpos, key_qvel, key_ctrl, key_mpos, key_mquat;
   // task (mjpc/task.cc:147-248 parse result + residual registry id + per-task state block)
@@ -102,7 +105,7 @@ struct Model {
     BlobReader b(blob, nbytes);
     nq = b.i("nq"); nv = b.i("nv"); nu = b.i("nu"); na = b.i("na"); nbody = b.i("nbody"); njnt = b.i("njnt");
     ngeom = b.i("ngeom"); nsite = b.i("nsite"); nmocap = b.i("nmocap"); nkey = b.i("nkey");
-    nuserdata = b.i("nuserdata"); nsensordata = b.i("nsensordata"); npair = b.i("npair");
+    nuserdata = b.i("nuserdata"); nsensordata = b.i("nsensordata"); npair = b.i("npair"); ntendon = b.i("ntendon");
     timestep = (T)b.r("opt_timestep"); impratio = (T)b.r("opt_impratio"); tolerance = (T)b.r("opt_tolerance");
     ls_tolerance = (T)b.r("opt_ls_tolerance"); meaninertia = (T)b.r("stat_meaninertia");
     auto g = b.reals("opt_gravity");
@@ -130,6 +133,8 @@ struct Model {
     LR(actuator_gear); LR(actuator_gainprm); LR(actuator_biasprm); LR(actuator_ctrlrange); LR(actuator_forcerange);
     LI(pair_geom1); LI(pair_geom2); LI(ray_geoms);
     LR(key_qpos); LR(key_qvel); LR(key_ctrl); LR(key_mpos); LR(key_mquat);
+    LI(tendon_adr); LI(tendon_num); LI(tendon_limited); LI(wrap_dof); LI(wrap_qposadr);
+    LR(wrap_coef); LR(tendon_range); LR(tendon_margin); LR(tendon_solref); LR(tendon_solimp); LR(tendon_invweight0);
 #undef LI
 #undef LR
     num_term = b.i("task_num_term"); num_residual = b.i("task_num_residual"); num_trace = b.i("task_num_trace");

@@ -26,7 +26,13 @@ constexpr double kMaxVal = 1e10;      // mjMAXVAL
 constexpr double kMinImp = 0.0001, kMaxImp = 0.9999, kMinMu = 1e-5;
 constexpr int kMaxConDim = 6;
 
-enum { CNSTR_FRICTION_DOF = 0, CNSTR_LIMIT_JOINT, CNSTR_CONTACT_FRICTIONLESS, CNSTR_CONTACT_ELLIPTIC };
+enum { CNSTR_FRICTION_DOF = 0, CNSTR_LIMIT_JOINT, CNSTR_CONTACT_FRICTIONLESS, CNSTR_CONTACT_ELLIPTIC, CNSTR_LIMIT_TENDON,
+       CNSTR_CONTACT_PYRAMIDAL };
+// one-sided quadratic rows: cost 0.5 D jar^2 when jar < 0 (limits, frictionless contacts, pyramid edges)
+inline bool cnstr_inequality(int type) {
+  return type == CNSTR_LIMIT_JOINT || type == CNSTR_CONTACT_FRICTIONLESS || type == CNSTR_LIMIT_TENDON ||
+         type == CNSTR_CONTACT_PYRAMIDAL;
+}
 enum { STATE_SATISFIED = 0, STATE_QUADRATIC, STATE_LINEARNEG, STATE_LINEARPOS, STATE_CONE };
 
 // ------------------------------------------------------------------------------------------ small math
@@ -660,17 +666,60 @@ void make_constraint(const Model<T>& m, Data<T>& d) {
         }
       }
     }
+  // tendon limits (fixed tendons: length = sum coef * qpos, Jacobian = coef on the wrapped dofs)
+  if (!m.disable_limit)
+    for (int t = 0; t < m.ntendon; t++) {
+      if (!m.tendon_limited[t]) continue;
+      T len = 0;
+      for (int w = m.tendon_adr[t]; w < m.tendon_adr[t] + m.tendon_num[t]; w++) len += m.wrap_coef[w] * d.qpos[m.wrap_qposadr[w]];
+      for (int side = -1; side <= 1; side += 2) {
+        T dist = side * (m.tendon_range[2 * t + (side + 1) / 2] - len);
+        if (dist < m.tendon_margin[t]) {
+          std::fill(row.begin(), row.end(), (T)0);
+          for (int w = m.tendon_adr[t]; w < m.tendon_adr[t] + m.tendon_num[t]; w++) row[m.wrap_dof[w]] += (T)-side * m.wrap_coef[w];
+          add_row(row.data(), dist, m.tendon_margin[t], m.tendon_invweight0[t], CNSTR_LIMIT_TENDON, t, 0);
+        }
+      }
+    }
   // contacts
+  const bool pyramidal = m.cone == 0;
   for (int ci = 0; ci < d.ncon; ci++) {
     Contact<T>& c = d.contact[ci];
     int dim = c.dim;
-    if ((int)d.efc_pos.size() + dim > d.maxefc) { c.efc_address = -1; continue; }  // capacity: dropped
+    const int nrow = (pyramidal && dim > 1) ? 2 * (dim - 1) : dim;
+    if ((int)d.efc_pos.size() + nrow > d.maxefc) { c.efc_address = -1; continue; }  // capacity: dropped
     int b1 = m.geom_bodyid[c.geom1], b2 = m.geom_bodyid[c.geom2];
     jac_point(m, d, b1, c.pos, jp1.data(), jr1.data());
     jac_point(m, d, b2, c.pos, jp2.data(), jr2.data());
     T tran = m.body_invweight0[2 * b1] + m.body_invweight0[2 * b2];
     T rot = m.body_invweight0[2 * b1 + 1] + m.body_invweight0[2 * b2 + 1];
     c.efc_address = (int)d.efc_pos.size();
+    if (pyramidal && dim > 1) {
+      // pyramidal cone: rows Jn +- mu_k Jt_k for every friction direction, all with pos = dist;
+      // diagApprox = tran + mu_k^2 * (tran | rot)
+      std::vector<T> jn(nv), jt(nv);
+      auto frame_row = [&](int k, T* out) {
+        const T* ax = &c.frame[3 * (k % 3)];
+        const bool is_rot = k >= 3;
+        for (int i = 0; i < nv; i++) {
+          T s2 = 0;
+          for (int a = 0; a < 3; a++)
+            s2 += ax[a] * (is_rot ? (jr2[a * nv + i] - jr1[a * nv + i]) : (jp2[a * nv + i] - jp1[a * nv + i]));
+          out[i] = s2;
+        }
+      };
+      frame_row(0, jn.data());
+      for (int k = 1; k < dim; k++) {
+        frame_row(k, jt.data());
+        const T mu = c.friction[k - 1];
+        const T diag = tran + mu * mu * (k < 3 ? tran : rot);
+        for (int sgn = 1; sgn >= -1; sgn -= 2) {
+          for (int i = 0; i < nv; i++) row[i] = jn[i] + sgn * mu * jt[i];
+          add_row(row.data(), c.dist, c.includemargin, diag, CNSTR_CONTACT_PYRAMIDAL, ci, 0);
+        }
+      }
+      continue;
+    }
     for (int k = 0; k < dim; k++) {
       const T* ax = &c.frame[3 * (k % 3)];
       bool is_rot = k >= 3;
@@ -698,6 +747,7 @@ void make_constraint(const Model<T>& m, Data<T>& d) {
     switch (d.efc_type[i]) {
       case CNSTR_FRICTION_DOF: solref = &m.dof_solref[2 * id]; solimp = &m.dof_solimp[5 * id]; friction_row = true; break;
       case CNSTR_LIMIT_JOINT: solref = &m.jnt_solref[2 * id]; solimp = &m.jnt_solimp[5 * id]; break;
+      case CNSTR_LIMIT_TENDON: solref = &m.tendon_solref[2 * id]; solimp = &m.tendon_solimp[5 * id]; break;
       default:
         solref = d.contact[id].solref; solimp = d.contact[id].solimp;
         friction_row = (d.efc_type[i] == CNSTR_CONTACT_ELLIPTIC && i > d.contact[id].efc_address);
@@ -724,6 +774,13 @@ void make_constraint(const Model<T>& m, Data<T>& d) {
     Contact<T>& c = d.contact[ci];
     if (c.efc_address < 0 || c.dim == 1) continue;
     int a = c.efc_address;
+    if (pyramidal) {
+      // pyramidal: all edges share R = 2 mu^2 R_first with mu = friction[0] (impratio acts through mu)
+      c.mu = c.friction[0] * mm::sqrt(1 / mm::max(kMinVal<T>(), m.impratio));
+      const T Rpy = 2 * c.mu * c.mu * d.efc_R[a];
+      for (int j = 0; j < 2 * (c.dim - 1); j++) d.efc_R[a + j] = Rpy;
+      continue;
+    }
     d.efc_R[a + 1] = d.efc_R[a] / mm::max(kMinVal<T>(), m.impratio);
     c.mu = c.friction[0] * mm::sqrt(d.efc_R[a + 1] / d.efc_R[a]);
     for (int j = 1; j < c.dim - 1; j++)
@@ -854,7 +911,7 @@ T update_constraint(const Model<T>& m, Data<T>& d, const std::vector<T>& jar, T*
       if (x <= -rf) { cost += f * (-(T)0.5 * rf - x); d.efc_force[i] = f; d.efc_state[i] = STATE_LINEARNEG; }
       else if (x >= rf) { cost += f * (-(T)0.5 * rf + x); d.efc_force[i] = -f; d.efc_state[i] = STATE_LINEARPOS; }
       else { cost += (T)0.5 * D * x * x; d.efc_force[i] = -D * x; d.efc_state[i] = STATE_QUADRATIC; }
-    } else if (type == CNSTR_LIMIT_JOINT || type == CNSTR_CONTACT_FRICTIONLESS) {
+    } else if (cnstr_inequality(type)) {
       if (x < 0) { cost += (T)0.5 * D * x * x; d.efc_force[i] = -D * x; d.efc_state[i] = STATE_QUADRATIC; }
       else { d.efc_force[i] = 0; d.efc_state[i] = STATE_SATISFIED; }
     } else {  // elliptic cone, first row of the contact
@@ -938,7 +995,7 @@ LsPoint<T> ls_eval(const Model<T>& m, const Data<T>& d, const SolverCtx<T>& s, c
       if (x <= -rf) { cost += f * (-(T)0.5 * rf - x); d1 += -f * jv; }
       else if (x >= rf) { cost += f * (-(T)0.5 * rf + x); d1 += f * jv; }
       else { cost += (T)0.5 * D * x * x; d1 += D * x * jv; d2 += D * jv * jv; }
-    } else if (type == CNSTR_LIMIT_JOINT || type == CNSTR_CONTACT_FRICTIONLESS) {
+    } else if (cnstr_inequality(type)) {
       if (x < 0) { cost += (T)0.5 * D * x * x; d1 += D * x * jv; d2 += D * jv * jv; }
     } else {
       const Contact<T>& c = d.contact[d.efc_id[i]];

@@ -12,7 +12,8 @@
 
 namespace oracle {
 
-enum { RESIDUAL_PARTICLE = 0, RESIDUAL_PARTICLE_COPY = 1, RESIDUAL_CARTPOLE = 2, RESIDUAL_QUADRUPED_FLAT = 3 };
+enum { RESIDUAL_PARTICLE = 0, RESIDUAL_PARTICLE_COPY = 1, RESIDUAL_CARTPOLE = 2, RESIDUAL_QUADRUPED_FLAT = 3,
+       RESIDUAL_HUMANOID_STAND = 4 };
 enum { QS_MODE = 0, QS_MODE_START_TIME = 1, QS_POSITION = 2, QS_HEADING = 5, QS_SPEED = 7, QS_ANGVEL = 8, QS_GROUND = 9,
        QS_ORIENTATION = 10, QS_GAIT = 14, QS_PHASE_START = 15, QS_PHASE_START_TIME = 16, QS_PHASE_VELOCITY = 17,
        QS_JUMP_VEL = 18, QS_FLIGHT_TIME = 19, QS_JUMP_ACC = 20, QS_CROUCH_TIME = 21, QS_LEAP_TIME = 22,
@@ -111,6 +112,30 @@ void residual_cartpole(const Model<T>& m, Data<T>& d, T* r) {
   r[1] = d.qpos[0] - m.parameters[0];
   r[2] = d.qvel[1];
   r[3] = d.ctrl[0];
+}
+
+// Humanoid Stand <- mjpc/tasks/humanoid/stand/stand.cc:30-97.  task_ids = {torso body, head body, site sp0..sp3};
+// sensors restated: framepos(objtype=body) = xipos, framepos(site) = site_xpos, subtreecom / subtreelinvel of torso.
+enum { HI_TORSO_BODY = 0, HI_HEAD_BODY, HI_SITE_SP0, HI_SIZE = 6 };
+template <class T>
+void residual_humanoid_stand(const Model<T>& m, Data<T>& d, T* r) {
+  const int* I = m.task_ids.data();
+  const T* f[4];
+  for (int k = 0; k < 4; k++) f[k] = &d.site_xpos[3 * I[HI_SITE_SP0 + k]];
+  const T* head = &d.xipos[3 * I[HI_HEAD_BODY]];
+  int counter = 0;
+  r[counter++] = head[2] - (T)0.25 * (f[0][2] + f[1][2] + f[2][2] + f[3][2]) - m.parameters[0];
+  const T* com = &d.subtree_com[3 * I[HI_TORSO_BODY]];
+  const T* vel = &d.subtree_linvel[3 * I[HI_TORSO_BODY]];
+  const T kFallTime = (T)0.2;
+  T dx[2];
+  for (int c = 0; c < 2; c++)
+    dx[c] = (T)0.25 * (f[0][c] + f[1][c] + f[2][c] + f[3][c]) - (com[c] + vel[c] * kFallTime);
+  r[counter++] = mm::sqrt(dx[0] * dx[0] + dx[1] * dx[1]);
+  r[counter++] = vel[0];
+  r[counter++] = vel[1];
+  for (int i = 6; i < m.nv; i++) r[counter++] = d.qvel[i];
+  for (int i = 0; i < m.nu; i++) r[counter++] = d.ctrl[i];
 }
 
 template <class T>
@@ -324,6 +349,7 @@ ResidualCallback<T> residual_by_id(int id) {
     case RESIDUAL_PARTICLE_COPY: return residual_particle_copy<T>;
     case RESIDUAL_CARTPOLE: return residual_cartpole<T>;
     case RESIDUAL_QUADRUPED_FLAT: return residual_quadruped<T>;
+    case RESIDUAL_HUMANOID_STAND: return residual_humanoid_stand<T>;
   }
   return nullptr;
 }

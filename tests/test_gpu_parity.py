@@ -306,3 +306,55 @@ def test_handles_are_independent(quadruped):
     r2, _, _ = e1.rollout_spline(state, 0.0, mocap, knots, kt, 2, 8)
     assert np.array_equal(r1, r2)
     e1.close()
+
+
+def _humanoid_poses(m):
+    """(qpos, qvel, ctrl) cases: standing contact, random airborne, tendon lower limit, deep crouch with contacts."""
+    rng = np.random.default_rng(3)
+    jn = m.jnt_names
+    hip, knee = m.jnt_qposadr[jn.index("hip_y_right")], m.jnt_qposadr[jn.index("knee_right")]
+    cases = []
+    q = m.qpos0.copy(); cases.append((q, np.zeros(m.nv), np.zeros(m.nu)))
+    q = m.qpos0.copy(); q[7:] += 0.3 * rng.standard_normal(m.nq - 7); q[2] = 2.0
+    cases.append((q, 0.5 * rng.standard_normal(m.nv), rng.uniform(-1, 1, m.nu)))
+    q = m.qpos0.copy(); q[2] = 3.0; q[hip] = -1.0; q[knee] = 0.0
+    cases.append((q, 0.2 * rng.standard_normal(m.nv), np.zeros(m.nu)))
+    q = m.qpos0.copy(); q[2] -= 0.02; q[7:] += 0.05 * rng.standard_normal(m.nq - 7)
+    cases.append((q, 0.3 * rng.standard_normal(m.nv), rng.uniform(-0.3, 0.3, m.nu)))
+    return cases
+
+
+def test_humanoid_single_step(engines, oracles):
+    """Humanoid (nv = 27, generic kernel path): pyramidal cones, tendon-limit rows, joint springs, 3 hinges per body."""
+    m = get_model("humanoid")
+    e, o = engines("humanoid", N=64, H=32), oracles("humanoid", 64)
+    for k, (q, v, u) in enumerate(_humanoid_poses(m)):
+        g = e.step_debug(q, v, u, np.zeros(0))
+        r = o.forward_debug(q, v, u, np.zeros(0))
+        assert g["ncon"] == r["ncon"] and g["nefc"] == r["nefc"], (k, g["ncon"], r["ncon"], g["nefc"], r["nefc"])
+        assert np.abs(g["qM"] - r["qM"]).max() < 2e-5 * np.abs(r["qM"]).max()
+        scale = np.abs(r["qacc"]).max() + 1.0
+        assert np.abs(g["qacc"] - r["qacc"]).max() < 2e-3 * scale, (k, np.abs(g["qacc"] - r["qacc"]).max(), scale)
+        assert np.abs(g["next_qpos"] - r["next_qpos"]).max() < 1e-4
+        assert np.abs(g["residual"] - r["residual"][: m.task_num_residual]).max() < 2e-4
+
+
+def test_humanoid_rollout_returns(engines, oracles):
+    m = get_model("humanoid")
+    e = engines("humanoid", N=64, H=32)
+    N, H = 32, 24
+    rng = np.random.default_rng(5)
+    state = np.concatenate([m.qpos0, np.zeros(m.nv)])
+    knots = np.clip(0.05 * rng.standard_normal((N, 3, m.nu)), -1, 1); knots[0] = 0
+    kt = np.array([0.0, 0.1725, 0.345])
+    ret, fail, order = e.rollout_spline(state, 0.0, np.zeros(0), knots, kt, 2, H)
+    r64 = oracles("humanoid", 64).rollout_spline(state, 0.0, np.zeros(0), knots, kt, 2, H, nthreads=8, full=True)
+    r32 = oracles("humanoid", 32).rollout_spline(state, 0.0, np.zeros(0), knots, kt, 2, H, nthreads=8, full=False)
+    assert not fail.any() and not r64["failure"].any()
+    rel64 = np.abs(ret - r64["returns"]) / np.abs(r64["returns"])
+    rel32 = np.abs(ret - r32["returns"]) / np.abs(r32["returns"])
+    print("humanoid: max rel return error vs fp32 oracle %.2e, vs fp64 oracle %.2e" % (rel32.max(), rel64.max()))
+    assert np.minimum(rel32, rel64).max() < 5e-4 and np.median(rel64) < 5e-5
+    tr = e.fetch_all()
+    np.testing.assert_allclose(tr["states"][:N, :6, : m.nq], r64["states"][:, :6, : m.nq], atol=5e-4)
+    np.testing.assert_allclose(tr["actions"][:N, :H], r64["actions"], atol=2e-5)

@@ -1,0 +1,86 @@
+"""CPU: the humanoid model (mjpc/tasks/humanoid/humanoid.xml.patch + stand/task.xml) through the MJCF compiler and
+the oracle - the physics features the A1 does not exercise: pyramidal cones, fixed-tendon limits, joint springs,
+several hinges per body."""
+import numpy as np
+
+from conftest import get_model
+
+
+def _oracle(m, precision=64):
+    from mujoco_mpc_b200.blob import to_blob
+    from oracle import pyoracle
+    return pyoracle.Oracle(to_blob(m), m, precision)
+
+
+def test_humanoid_model_dimensions():
+    m = get_model("humanoid")
+    # nq/nv/nu = 28/27/21, 1 + 20 bodies; stand task: 46 residuals in 5 terms, dt 0.015
+    assert (m.nq, m.nv, m.nu, m.nbody) == (28, 27, 21, 21)
+    assert m.task_num_residual == 46 and m.task_num_term == 5 and abs(m.opt_timestep - 0.015) < 1e-12
+    assert m.opt_cone == 0 and m.ntendon == 2
+    assert list(m.tendon_num) == [2, 2] and np.allclose(m.wrap_coef, [0.5, -0.5, 0.5, -0.5])
+    assert np.allclose(m.tendon_range, [[-0.3, 2], [-0.3, 2]]) and (m.tendon_invweight0 > 0).all()
+    # gears and class inheritance from the patch: hip_y 120, knee 100; hip_y stiffness 10 (joint_big), knee 1, elbow 0
+    names = m.actuator_names
+    assert np.ravel(m.actuator_gear[names.index("hip_y_right")])[0] == 120 and np.ravel(m.actuator_gear[names.index("knee_left")])[0] == 100
+    jn = m.jnt_names
+    assert m.jnt_stiffness[jn.index("hip_y_left")] == 10 and m.jnt_stiffness[jn.index("knee_right")] == 1
+    assert m.jnt_stiffness[jn.index("elbow_left")] == 0 and m.jnt_stiffness[jn.index("abdomen_z")] == 20
+    assert np.allclose(np.degrees(m.jnt_range[jn.index("knee_left")]), [-160, 2])
+
+
+def test_humanoid_mass_matrix_matches_independent_numpy():
+    from mujoco_mpc_b200.refmath import mass_matrix_and_jacobians
+    m = get_model("humanoid")
+    o = _oracle(m)
+    rng = np.random.default_rng(1)
+    for _ in range(3):
+        q = m.qpos0.copy()
+        q[7:] += 0.4 * rng.standard_normal(m.nq - 7)
+        q[3:7] = rng.standard_normal(4); q[3:7] /= np.linalg.norm(q[3:7]); q[2] = 3.0
+        r = o.forward_debug(q, 0.3 * rng.standard_normal(m.nv), np.zeros(m.nu), np.zeros(0))
+        M, _ = mass_matrix_and_jacobians(m, q)
+        assert np.abs(r["qM"] - M).max() < 1e-10 * np.abs(M).max()
+
+
+def test_humanoid_pyramidal_contacts_and_tendon_limits():
+    m = get_model("humanoid")
+    o = _oracle(m)
+    q, v, u = m.qpos0.copy(), np.zeros(m.nv), np.zeros(m.nu)
+    r = o.forward_debug(q, v, u, np.zeros(0))
+    # standing pose: both ends of the four foot capsules touch; condim max(1, 3) = 3 -> 4 pyramid edges per contact
+    assert r["ncon"] == 8 and r["nefc"] == 4 * r["ncon"] and not r["warning"]
+    assert (r["efc_force"] >= -1e-12).all() and r["efc_force"].sum() > 0          # one-sided rows push only
+    # in the air no rows; bending the right hip back with a straight knee shortens the hamstring tendon below its
+    # lower limit (length = 0.5 hip_y - 0.5 knee, range [-0.3, 2]) -> exactly one extra (tendon) row beside the
+    # hip_y joint-limit rows that this pose may also activate
+    q2 = q.copy(); q2[2] = 3.0
+    base = o.forward_debug(q2, v, u, np.zeros(0))
+    assert base["ncon"] == 0 and base["nefc"] == 0
+    jn = m.jnt_names
+    hip, knee = m.jnt_qposadr[jn.index("hip_y_right")], m.jnt_qposadr[jn.index("knee_right")]
+    q3 = q2.copy(); q3[hip] = -1.0; q3[knee] = 0.0         # length -0.5 < -0.3, hip_y still inside [-150, 20] deg
+    r3 = o.forward_debug(q3, v, u, np.zeros(0))
+    assert r3["ncon"] == 0 and r3["nefc"] == 1
+    dof_hip, dof_knee = m.jnt_dofadr[jn.index("hip_y_right")], m.jnt_dofadr[jn.index("knee_right")]
+    fc = r3["qfrc_constraint"]
+    # J = -side * coef with side = -1 (lower limit): force on hip_y positive, on the knee negative, same magnitude
+    assert fc[dof_hip] > 0 and abs(fc[dof_hip] + fc[dof_knee]) < 1e-9 * abs(fc[dof_hip])
+    assert np.abs(np.delete(fc, [dof_hip, dof_knee])).max() < 1e-12
+
+
+def test_humanoid_stand_residual_and_rollout():
+    m = get_model("humanoid")
+    o = _oracle(m)
+    q, v = m.qpos0.copy(), np.zeros(m.nv)
+    u = np.linspace(-0.5, 0.5, m.nu)
+    r = o.forward_debug(q, v, u, np.zeros(0))
+    res = r["residual"][:46]
+    assert np.allclose(res[4:25], 0) and np.allclose(res[25:46], u)              # joint velocities, controls
+    assert abs(res[0] - (1.282 + 0.19 - 0.0 - 1.4 - (1.282 - 0.04 - 0.4 - 0.39 - 0.4 + 0.0))) < 0.5  # head-feet height - goal
+    H = int(0.35 / 0.015 + 1)
+    knots = np.zeros((4, 3, m.nu)); knots[1:] = 0.1 * np.random.default_rng(0).standard_normal((3, 3, m.nu))
+    out = o.rollout_spline(np.concatenate([q, v]), 0.0, np.zeros(0), knots, np.array([0.0, 0.17, 0.34]), 2, H, nthreads=2)
+    assert not out["failure"].any() and np.isfinite(out["returns"]).all() and (out["returns"] > 0).all()
+    assert abs(out["states"][0, -1, 2] - 1.282) < 0.05        # zero control: the springs hold the pose for 0.35 s
+    assert (out["states"][:, -1, 2] > 0.5).all()
