@@ -78,6 +78,7 @@ struct Ctx {
   int dbase;  // float index of this warp's state block
   int lane;
   int ncon, nefc, nitem, niter, nlim;
+  const float* gkey;  // HBM: keyframe mocap positions [nkey][3*nmocap] (too large for the shared-memory pack)
   int npseudo;  // tendon-limit pseudo-contacts at the tail of the contact list (included in ncon)
   int warn;
   float time;

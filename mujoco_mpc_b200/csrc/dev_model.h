@@ -64,7 +64,7 @@ enum { JNT_FREE = 0, JNT_BALL, JNT_SLIDE, JNT_HINGE };
 enum { OBJ_BODY = 0, OBJ_XBODY, OBJ_GEOM, OBJ_SITE };
 enum { CONE_PYRAMIDAL = 0, CONE_ELLIPTIC = 1 };
 enum { RESIDUAL_PARTICLE = 0, RESIDUAL_PARTICLE_COPY = 1, RESIDUAL_CARTPOLE = 2, RESIDUAL_QUADRUPED_FLAT = 3,
-       RESIDUAL_HUMANOID_STAND = 4 };
+       RESIDUAL_HUMANOID_STAND = 4, RESIDUAL_HUMANOID_TRACK = 5 };
 
 // integer fields of the header (sizes, option flags, task dimensions, pack sizes).  A statically specialised
 // kernel (spec_*.h) turns every one of them, and the offset tables below, into compile-time constants.
@@ -155,7 +155,10 @@ inline ModelPack pack_model(const void* data, size_t nbytes, int maxcon, int max
   auto g = b.reals("opt_gravity");
   for (int k = 0; k < 3; k++) M.gravity[k] = (float)g[k];
   // verbatim arrays
-#define X(n) { auto v = b.reals(#n); M.fo[F_##n] = (int)P.f.size(); for (double x : v) P.f.push_back((float)x); \
+  // keyframe tables of mocap tasks (thousands of frames) do not fit the shared-memory pack: they stay in HBM
+  // (engine.cu appends key_mpos behind the staged pack); residuals that index key_qpos need nkey small
+#define X(n) { auto v = b.reals(#n); if (std::string(#n) == "key_qpos" && v.size() > 1024) v.clear();               \
+               M.fo[F_##n] = (int)P.f.size(); for (double x : v) P.f.push_back((float)x);                          \
                while (P.f.size() % 4) P.f.push_back(0.f); }
   MJPC_F_ARRAYS(X)
 #undef X

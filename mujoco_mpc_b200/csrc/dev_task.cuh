@@ -561,6 +561,49 @@ __device__ __noinline__ void k_residual(Ctx& c) {
       __syncwarp();
       break;
     }
+    case RESIDUAL_HUMANOID_TRACK: {
+      // mjpc/tasks/humanoid/tracking/tracking.cc:94-216; task_ids = 16 tracking sites then 16 mocap ids,
+      // task_state = [mode, reference_time (rebased)], keyframes in HBM (c.gkey).  One tracked body per lane.
+      const int lengths[10] = {121, 154, 115, 78, 145, 188, 260, 279, 39, 510};
+      const int* I = MI(task_ids);
+      const float* S = MF(task_state);
+      const int mode = (int)S[0];
+      int start = 0;
+      for (int i = 0; i < mode; i++) start += lengths[i];
+      const int last = start + lengths[mode] - 1;
+      const float idx = fminf((float)last, fmaxf(0.f, (c.time - S[1]) * 30.0f + (float)start));
+      const int k0 = (int)floorf(idx), k1 = min(k0 + 1, last);
+      const float w1 = idx - (float)k0, w0 = 1.f - w1;
+      const int nm3 = 3 * M.nmocap, nj = M.nv - 6, nu = M.nu;
+      for (int i = lane; i < nj; i += 32) r[i] = DF(qvel)[6 + i];
+      for (int i = lane; i < nu; i += 32) r[nj + i] = DF(ctrl)[i];
+      float mp[3] = {0, 0, 0}, sp[3] = {0, 0, 0}, vel[3] = {0, 0, 0};
+      if (lane < 16) {
+        const float *p0 = c.gkey + (size_t)nm3 * k0 + 3 * I[16 + lane], *p1 = c.gkey + (size_t)nm3 * k1 + 3 * I[16 + lane];
+        const int site = I[lane], body = MI(site_bodyid)[site];
+        const float *sx = DF(site_xpos) + 3 * site, *cv = DF(cvel) + 6 * body,
+                    *com = DF(subtree_com) + 3 * MI(body_rootid)[body];
+        float off[3], wx[3];
+        for (int q = 0; q < 3; q++) {
+          const float a = __ldg(p0 + q), b = __ldg(p1 + q);
+          mp[q] = a * w0 + b * w1; sp[q] = sx[q]; off[q] = sx[q] - com[q];
+          vel[q] = (b - a) * 30.0f;
+        }
+        cross3(wx, cv, off);
+        for (int q = 0; q < 3; q++) vel[q] -= cv[3 + q] + wx[q];
+      }
+      float am[3], as[3];
+      for (int q = 0; q < 3; q++) { am[q] = warp_sum(mp[q]) * (1.f / 16.f); as[q] = warp_sum(sp[q]) * (1.f / 16.f); }
+      const int o = nj + nu;
+      if (lane < 3) r[o + lane] = am[lane] - as[lane];
+      if (lane < 16)
+        for (int q = 0; q < 3; q++) {
+          r[o + 3 + 3 * lane + q] = (mp[q] - am[q]) - (sp[q] - as[q]);
+          r[o + 51 + 3 * lane + q] = vel[q];
+        }
+      __syncwarp();
+      break;
+    }
     default: break;
   }
 }

@@ -32,6 +32,7 @@ int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
 // indices of task_state entries that hold absolute times (rebased to the rollout start before upload)
 std::vector<int> time_like_state(int residual_id) {
   if (residual_id == RESIDUAL_QUADRUPED_FLAT) return {QS_MODE_START_TIME, QS_PHASE_START_TIME};
+  if (residual_id == RESIDUAL_HUMANOID_TRACK) return {1};   // reference_time
   return {};
 }
 }  // namespace
@@ -93,7 +94,7 @@ int upload_task(mjpc_b200* h) {
   for (size_t i = 0; i < h->parameters.size(); i++) f[M.fo[F_task_parameters] + i] = (float)h->parameters[i];
   for (size_t i = 0; i < h->task_state.size(); i++) f[M.fo[F_task_state] + i] = (float)h->task_state[i];
   h->pack.M.risk = (float)h->risk;
-  CUDA_TRY(cudaMemcpyAsync(h->d_pack, f.data(), f.size() * 4, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->d_pack, f.data(), (size_t)(M.nf + M.ni) * 4, cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));  // f is pageable
   return 0;
 }
@@ -224,6 +225,8 @@ int mjpc_b200_create(const mjpc_model_blob* model, int max_candidates, int max_h
     const size_t nf = f.size();
     f.resize(nf + h->pack.i.size());
     std::memcpy(f.data() + nf, h->pack.i.data(), h->pack.i.size() * 4);
+    // not staged to shared memory: keyframe mocap positions, read from HBM by the tracking residual (Ctx::gkey)
+    for (double x : h->pack.key_mpos) f.push_back((float)x);
     CUDA_TRY(dalloc(&h->d_pack, f.size()));
     CUDA_TRY(cudaMemcpy(h->d_pack, f.data(), f.size() * 4, cudaMemcpyHostToDevice));
   }

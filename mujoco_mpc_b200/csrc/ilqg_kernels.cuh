@@ -155,7 +155,7 @@ __device__ __forceinline__ void fd_center_body(const FdArgs& A) {
   float* smem = g_smem;
   stage_model_pack(smem, A.pack, (unsigned)((A.M.nf + A.M.ni) * 4));
   Ctx c;
-  init_ctx(c, &A.M, &A.L, smem, 0, threadIdx.x);
+  init_ctx(c, &A.M, &A.L, smem, 0, threadIdx.x, A.pack);
   auto&& M = SP::model(c);
   const int lane = c.lane, t = blockIdx.x, nq = M.nq, nv = M.nv, ds = nq + nv, nr = M.num_residual;
   fd_load_state<SP>(c, A, t);
@@ -176,7 +176,7 @@ __device__ __forceinline__ void fd_column_body(const FdArgs& A) {
   float* smem = g_smem;
   stage_model_pack(smem, A.pack, (unsigned)((A.M.nf + A.M.ni) * 4));
   Ctx c;
-  init_ctx(c, &A.M, &A.L, smem, 0, threadIdx.x);
+  init_ctx(c, &A.M, &A.L, smem, 0, threadIdx.x, A.pack);
   auto&& M = SP::model(c);
   const int lane = c.lane, nq = M.nq, nv = M.nv, nu = M.nu, ds = nq + nv, n = 2 * nv, nr = M.num_residual;
   const int ncol = nu + 2 * nv;

@@ -65,7 +65,8 @@ __host__ __device__ inline int smem_header_words(const DevModel& M) {
 }
 
 // copy the DevModel / DevLayout kernel parameters behind the pack and set up this warp's context
-__device__ __forceinline__ void init_ctx(Ctx& c, const DevModel* M, const DevLayout* L, float* smem, int warp, int lane) {
+__device__ __forceinline__ void init_ctx(Ctx& c, const DevModel* M, const DevLayout* L, float* smem, int warp, int lane,
+                                         const float* pack) {
   const int hdr = M->nf + M->ni;
   const int lay = hdr + (int)((sizeof(DevModel) + 15) / 16) * 4;
   const int data0 = lay + (int)((sizeof(DevLayout) + 15) / 16) * 4;
@@ -80,6 +81,7 @@ __device__ __forceinline__ void init_ctx(Ctx& c, const DevModel* M, const DevLay
   c.hdr = hdr; c.lay = lay; c.ibase = M->nf;
   c.dbase = data0 + warp * L->total;
   c.lane = lane;
+  c.gkey = pack + M->nf + M->ni;   // the keyframe table follows the staged part of the pack in HBM
   c.ncon = 0; c.npseudo = 0; c.nefc = 0; c.nitem = 0; c.niter = 0; c.nlim = 0; c.warn = 0; c.time = 0.f;
 #ifdef MJPC_PHASE_TIMING
   for (int k = 0; k < 8; k++) c.tph[k] = 0;
@@ -106,7 +108,7 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& A) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cand = blockIdx.x * (blockDim.x >> 5) + warp;
   Ctx c;
-  init_ctx(c, &A.M, &A.L, smem, warp, lane);
+  init_ctx(c, &A.M, &A.L, smem, warp, lane, A.pack);
   if (cand >= A.N) return;
   auto&& M = SP::model(c);
   const int nq = M.nq, nv = M.nv, nu = M.nu, ds = nq + nv, nr = M.num_residual, ntr = 3 * M.num_trace, H = A.H;
@@ -242,7 +244,7 @@ extern "C" __global__ void __launch_bounds__(32) step_debug_kernel(const __grid_
   const DevModel& M = A.M;
   stage_model_pack(smem, A.pack, (unsigned)((M.nf + M.ni) * 4));
   Ctx c;
-  init_ctx(c, &A.M, &A.L, smem, 0, threadIdx.x);
+  init_ctx(c, &A.M, &A.L, smem, 0, threadIdx.x, A.pack);
   const int lane = c.lane, nq = M.nq, nv = M.nv;
   if (A.task_state) {
     float* ts = const_cast<float*>(MF(task_state));

@@ -465,6 +465,85 @@ def humanoid_stand_xml(horizon=0.35, trajectories=10) -> str:
 """
 
 
+def humanoid_track_xml(horizon=0.5, trajectories=32) -> str:
+    """MJPC "Humanoid Track" (mjpc/tasks/humanoid/tracking/task.xml): the same humanoid, dt 0.005, 16 mocap bodies,
+    21 cost terms over 141 residuals.  The 1889 CMU keyframes the reference vendors are replaced by synthetic clips
+    of the same lengths (synth_mocap below): they are data of the reference, not part of the path."""
+    base = humanoid_stand_xml()
+    custom = f"""
+  <custom>
+    <numeric name="sampling_representation" data="2"/>
+    <numeric name="agent_planner" data="2"/>
+    <numeric name="agent_horizon" data="{horizon}"/>
+    <numeric name="agent_timestep" data="0.005"/>
+    <numeric name="sampling_spline_points" data="16"/>
+    <numeric name="sampling_exploration" data="0.15"/>
+    <numeric name="sampling_trajectories" data="{trajectories}"/>
+    <numeric name="gradient_spline_points" data="5"/>
+    <numeric name="ilqg_num_rollouts" data="16"/>
+    <numeric name="ilqg_regularization_type" data="1"/>
+    <numeric name="ilqg_representation" data="2"/>
+  </custom>
+  <option timestep="0.005"/>"""
+    mocap = "".join(f'<body name="mocap[{b}]" mocap="true"><site name="mocap[{b}]" type="sphere" size="0.027" group="3"/></body>'
+                    for b in T.TRACK_BODIES)
+    terms = [("Joint Vel.", 21, "0 0.001 0.0 0.01"), ("Control", 21, "3 0.1 0 1.0 0.3"),
+             ("Pos[avg]", 3, "6 100.0 0.0 100.0 0.1"), ("Pos[pelvis]", 3, "6 30.0 0.0 100.0 0.1"),
+             ("Pos[head]", 3, "6 0.0 0.0 100.0 0.1"), ("Pos[toe]", 6, "7 30.0 0.0 100.0 0.2 4"),
+             ("Pos[heel]", 6, "7 30.0 0.0 100.0 0.2 4"), ("Pos[knee]", 6, "6 30.0 0.0 100.0 0.1"),
+             ("Pos[hand]", 6, "6 30.0 0.0 100.0 0.1"), ("Pos[elbow]", 6, "7 30.0 0.0 100.0 0.2 4"),
+             ("Pos[shoulder]", 6, "6 30.0 0.0 100.0 0.1"), ("Pos[hip]", 6, "6 30.0 0.0 100.0 0.1"),
+             ("Vel[root]", 3, "6 0.1 0 1.0 0.3"), ("Vel[head]", 3, "6 0.0 0 1.0 0.3"), ("Vel[toe]", 6, "6 0.1 0 1.0 0.3"),
+             ("Vel[heel]", 6, "6 0.1 0 1.0 0.3"), ("Vel[knee]", 6, "6 0.1 0 1.0 0.3"), ("Vel[hand]", 6, "6 0.1 0 1.0 0.3"),
+             ("Vel[elbow]", 6, "6 0.1 0 1.0 0.3"), ("Vel[shoulder]", 6, "6 0.1 0 1.0 0.3"), ("Vel[hip]", 6, "6 0.1 0 1.0 0.3")]
+    sensors = "".join(f'<user name="{n}" dim="{d}" user="{u}"/>' for n, d, u in terms)
+    sensors += '<framepos name="trace0" objtype="body" objname="torso"/>'
+    a = base.index("<custom>"); b = base.index("</custom>") + len("</custom>")
+    base = base[:a] + custom.strip() + base[b:]
+    base = base.replace("  </worldbody>", mocap + "\n  </worldbody>")
+    a = base.index("<sensor>"); b = base.index("</sensor>")
+    base = base[:a] + "<sensor>" + sensors + base[b:]
+    return base.replace('<mujoco model="Humanoid">', '<mujoco model="Humanoid Track">')
+
+
+def synth_mocap(m, seed=0):
+    """Synthetic stand-in for the reference's CMU keyframes: 10 clips with the reference's lengths (tracking.cc:43-54),
+    30 fps.  Each clip is a smooth band-limited joint-angle motion inside 35 % of the joint ranges around the standing
+    pose (different frequencies / phases per clip and joint) with the root lowered so the lowest foot marker stays at
+    its standing height; the 16 tracked site positions of that pose are the frame's mocap positions.
+    Returns key_qpos [K][nq], key_mpos [K][16*3]."""
+    from ..refmath import kinematics
+    from ..mjcf import quat2mat
+    rng = np.random.default_rng(seed)
+    sites = [m.site_names.index("tracking[%s]" % b) for b in T.TRACK_BODIES]
+    foot = [T.TRACK_BODIES.index(b) for b in ("ltoe", "rtoe", "lheel", "rheel")]
+    hinge = [j for j in range(m.njnt) if m.jnt_type[j] == 3]
+    lo = np.array([m.jnt_range[j][0] for j in hinge]); hi = np.array([m.jnt_range[j][1] for j in hinge])
+    qadr = np.array([m.jnt_qposadr[j] for j in hinge])
+
+    def markers(q):
+        kin = kinematics(m, q)
+        return np.array([kin["xpos"][m.site_bodyid[s]] + kin["xmat"][m.site_bodyid[s]] @ m.site_pos[s] for s in sites])
+    stand = markers(m.qpos0)
+    z_foot = stand[foot, 2].min()
+    kq, km = [], []
+    for clip, length in enumerate(T.TRACK_MOTION_LENGTHS):
+        f = rng.uniform(0.3, 1.2, len(hinge)); ph = rng.uniform(0, 2 * np.pi, len(hinge))
+        amp = 0.35 * rng.uniform(0.2, 1.0, len(hinge))
+        for k in range(length):
+            t = k / T.TRACK_FPS
+            env = min(1.0, t / 0.5)                       # every clip starts from the standing pose
+            q = m.qpos0.copy()
+            s = np.sin(2 * np.pi * f * t + ph) - np.sin(ph)
+            q[qadr] = np.clip(env * amp * s * 0.5 * (hi - lo), 0.9 * lo, 0.9 * hi)
+            q[0] = 0.15 * env * np.sin(2 * np.pi * 0.2 * t + clip)          # slow drift of the root in x
+            mk = markers(q)
+            dz = z_foot - mk[foot, 2].min()
+            q[2] += dz; mk[:, 2] += dz
+            kq.append(q); km.append(mk.reshape(-1))
+    return np.array(kq), np.array(km)
+
+
 def _robot_vs_world_only(m, g1, g2):
     """Keep only pairs with exactly one static (world-welded) geom: robot self-collision pairs are
     dropped (DESIGN.md 'Out of scope': most need capsule/cylinder/box convex tests)."""
@@ -526,6 +605,20 @@ def load(name: str, agent_timestep: bool = True, **kw):
             ids[T.HI_SITE_SP0 + k] = m.site_names.index("sp%d" % k)
         m.task_ids = ids
         m.task_state = np.zeros(1)
+    elif name == "humanoid_track":
+        m = compile_xml(humanoid_track_xml(**kw), pair_filter=_robot_vs_world_only)
+        m.task_residual_id = T.RESIDUAL_HUMANOID_TRACK
+        ids = [m.site_names.index("tracking[%s]" % b) for b in T.TRACK_BODIES]
+        ids += [int(m.body_mocapid[m.body_names.index("mocap[%s]" % b)]) for b in T.TRACK_BODIES]
+        m.task_ids = np.array(ids, np.int32)
+        m.task_state = np.zeros(T.TS_SIZE)               # mode 0 (first clip), reference_time 0
+        kq, km = synth_mocap(m)
+        m.nkey = len(kq)
+        m.key_qpos, m.key_mpos = kq, km
+        m.key_qvel = np.zeros((m.nkey, m.nv)); m.key_ctrl = np.zeros((m.nkey, m.nu))
+        m.key_mquat = np.tile(np.array([1.0, 0, 0, 0]), (m.nkey, m.nmocap))
+        m.key_names = ["frame%d" % i for i in range(m.nkey)]
+        m.mocap_pos0 = km[0].reshape(-1, 3).copy()
     else:
         raise KeyError(name)
     m.task_name = name

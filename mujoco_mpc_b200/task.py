@@ -22,6 +22,14 @@ RESIDUAL_QUADRUPED_FLAT = 3  # mjpc/tasks/quadruped/quadruped.cc:33-226
 RESIDUAL_HUMANOID_STAND = 4  # mjpc/tasks/humanoid/stand/stand.cc:30-97
 # task_ids layout of the humanoid stand residual
 HI_TORSO_BODY, HI_HEAD_BODY, HI_SITE_SP0, HI_SIZE = 0, 1, 2, 6
+RESIDUAL_HUMANOID_TRACK = 5  # mjpc/tasks/humanoid/tracking/tracking.cc:94-216
+# tracking: task_ids = 16 tracking-site ids then the 16 mocap ids, both in tracking.cc:71-75 body order;
+# task_state = [current_mode, reference_time] (reference_time is time-like: rebased per rollout)
+TRACK_BODIES = ("pelvis", "head", "ltoe", "rtoe", "lheel", "rheel", "lknee", "rknee", "lhand", "rhand", "lelbow",
+                "relbow", "lshoulder", "rshoulder", "lhip", "rhip")
+TRACK_MOTION_LENGTHS = (121, 154, 115, 78, 145, 188, 260, 279, 39, 510)   # tracking.cc:43-54
+TRACK_FPS = 30.0
+TS_MODE, TS_REFERENCE_TIME, TS_SIZE = 0, 1, 2
 
 # quadruped task-state block layout (doubles); ResidualFn members, quadruped.h:160-225
 QS_MODE, QS_MODE_START_TIME, QS_POSITION, QS_HEADING, QS_SPEED, QS_ANGVEL, QS_GROUND = 0, 1, 2, 5, 7, 8, 9

@@ -13,7 +13,7 @@
 namespace oracle {
 
 enum { RESIDUAL_PARTICLE = 0, RESIDUAL_PARTICLE_COPY = 1, RESIDUAL_CARTPOLE = 2, RESIDUAL_QUADRUPED_FLAT = 3,
-       RESIDUAL_HUMANOID_STAND = 4 };
+       RESIDUAL_HUMANOID_STAND = 4, RESIDUAL_HUMANOID_TRACK = 5 };
 enum { QS_MODE = 0, QS_MODE_START_TIME = 1, QS_POSITION = 2, QS_HEADING = 5, QS_SPEED = 7, QS_ANGVEL = 8, QS_GROUND = 9,
        QS_ORIENTATION = 10, QS_GAIT = 14, QS_PHASE_START = 15, QS_PHASE_START_TIME = 16, QS_PHASE_VELOCITY = 17,
        QS_JUMP_VEL = 18, QS_FLIGHT_TIME = 19, QS_JUMP_ACC = 20, QS_CROUCH_TIME = 21, QS_LEAP_TIME = 22,
@@ -136,6 +136,56 @@ void residual_humanoid_stand(const Model<T>& m, Data<T>& d, T* r) {
   r[counter++] = vel[1];
   for (int i = 6; i < m.nv; i++) r[counter++] = d.qvel[i];
   for (int i = 0; i < m.nu; i++) r[counter++] = d.ctrl[i];
+}
+
+// Humanoid Track <- mjpc/tasks/humanoid/tracking/tracking.cc:29-216.  task_ids = 16 tracking-site ids then 16 mocap
+// ids (body order of tracking.cc:71-75); task_state = [current_mode, reference_time].  Sensors restated:
+// tracking_pos[x] = site_xpos, tracking_linvel[x] = world-frame linear velocity of the site (mj_objectVelocity).
+constexpr int kTrackMotionLengths[10] = {121, 154, 115, 78, 145, 188, 260, 279, 39, 510};
+constexpr double kTrackFps = 30.0;
+template <class T>
+void residual_humanoid_track(const Model<T>& m, Data<T>& d, T* r) {
+  const int* I = m.task_ids.data();
+  const int mode = (int)m.task_state[0];
+  const T reference_time = m.task_state[1];
+  int start = 0;
+  for (int i = 0; i < mode; i++) start += kTrackMotionLengths[i];
+  const int length = kTrackMotionLengths[mode];
+  const T current_index = (d.time - reference_time) * (T)kTrackFps + start;
+  const int last_key_index = start + length - 1;
+  // ComputeInterpolationValues (tracking.cc:29-39)
+  const T clamped = mm::max((T)0, mm::min((T)last_key_index, current_index));
+  const int k0 = (int)std::floor(mm::dbl(clamped));
+  const int k1 = k0 + 1 < last_key_index ? k0 + 1 : last_key_index;
+  const T w1 = clamped - (T)k0, w0 = (T)1 - w1;
+  const int nm = m.nmocap;
+  int counter = 0;
+  for (int i = 6; i < m.nv; i++) r[counter++] = d.qvel[i];
+  for (int i = 0; i < m.nu; i++) r[counter++] = d.ctrl[i];
+  T mpos[16][3], spos[16][3], avg_m[3] = {0, 0, 0}, avg_s[3] = {0, 0, 0};
+  for (int b = 0; b < 16; b++) {
+    const T* p0 = &m.key_mpos[(size_t)nm * 3 * k0 + 3 * I[16 + b]];
+    const T* p1 = &m.key_mpos[(size_t)nm * 3 * k1 + 3 * I[16 + b]];
+    for (int c = 0; c < 3; c++) {
+      mpos[b][c] = p0[c] * w0 + p1[c] * w1;
+      spos[b][c] = d.site_xpos[3 * I[b] + c];
+      avg_m[c] += mpos[b][c]; avg_s[c] += spos[b][c];
+    }
+  }
+  for (int c = 0; c < 3; c++) { avg_m[c] /= 16; avg_s[c] /= 16; }
+  for (int c = 0; c < 3; c++) r[counter++] = avg_m[c] - avg_s[c];
+  for (int b = 0; b < 16; b++)
+    for (int c = 0; c < 3; c++) r[counter++] = (mpos[b][c] - avg_m[c]) - (spos[b][c] - avg_s[c]);
+  for (int b = 0; b < 16; b++) {
+    const T* p0 = &m.key_mpos[(size_t)nm * 3 * k0 + 3 * I[16 + b]];
+    const T* p1 = &m.key_mpos[(size_t)nm * 3 * k1 + 3 * I[16 + b]];
+    const int body = m.site_bodyid[I[b]];
+    const T* cv = &d.cvel[6 * body];
+    T off[3], wx[3];
+    for (int c = 0; c < 3; c++) off[c] = d.site_xpos[3 * I[b] + c] - d.subtree_com[3 * m.body_rootid[body] + c];
+    cross3(wx, cv, off);
+    for (int c = 0; c < 3; c++) r[counter++] = (p1[c] - p0[c]) * (T)kTrackFps - (cv[3 + c] + wx[c]);
+  }
 }
 
 template <class T>
@@ -350,6 +400,7 @@ ResidualCallback<T> residual_by_id(int id) {
     case RESIDUAL_CARTPOLE: return residual_cartpole<T>;
     case RESIDUAL_QUADRUPED_FLAT: return residual_quadruped<T>;
     case RESIDUAL_HUMANOID_STAND: return residual_humanoid_stand<T>;
+    case RESIDUAL_HUMANOID_TRACK: return residual_humanoid_track<T>;
   }
   return nullptr;
 }

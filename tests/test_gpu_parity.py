@@ -358,3 +358,55 @@ def test_humanoid_rollout_returns(engines, oracles):
     tr = e.fetch_all()
     np.testing.assert_allclose(tr["states"][:N, :6, : m.nq], r64["states"][:, :6, : m.nq], atol=5e-4)
     np.testing.assert_allclose(tr["actions"][:N, :H], r64["actions"], atol=2e-5)
+
+
+def _track_mocap(m):
+    return np.concatenate([m.key_mpos[0].reshape(-1, 3), np.tile([1.0, 0, 0, 0], (m.nmocap, 1))], 1).reshape(-1)
+
+
+def test_humanoid_track_single_step(engines, oracles):
+    """BASELINE config 3 task: 141-dim tracking residual reading the keyframe table from HBM, at several clip
+    times / clips (task_state = [mode, reference_time], the clock is rebased on the device)."""
+    from mujoco_mpc_b200 import task as T
+    m = get_model("humanoid_track")
+    e, o = engines("humanoid_track", N=64, H=128), oracles("humanoid_track", 64)
+    mocap = _track_mocap(m)
+    rng = np.random.default_rng(7)
+    for mode, t in ((0, 0.0), (0, 1.2345), (4, 2.01), (9, 100.0), (2, 1003.7)):
+        ts = np.array([float(mode), 1000.0 if t > 1000 else 0.25])
+        e.set_task(task_state=ts); o.set_task(task_state=ts)
+        q = m.key_qpos[sum(T.TRACK_MOTION_LENGTHS[:mode]) + 7].copy()
+        q[7:] += 0.03 * rng.standard_normal(m.nq - 7)
+        v = 0.3 * rng.standard_normal(m.nv); u = rng.uniform(-0.5, 0.5, m.nu)
+        g = e.step_debug(q, v, u, mocap, time=t)
+        r = o.forward_debug(q, v, u, mocap, time=t)
+        assert g["ncon"] == r["ncon"] and g["nefc"] == r["nefc"]
+        scale = np.abs(r["qacc"]).max() + 1.0
+        assert np.abs(g["qacc"] - r["qacc"]).max() < 2e-3 * scale
+        # marker velocities scale with |qvel| * lever arms; positions with metres: 2e-4 absolute covers both in fp32
+        assert np.abs(g["residual"] - r["residual"][:141]).max() < 3e-4, (mode, t, np.abs(g["residual"] - r["residual"][:141]).max())
+    ts = np.asarray(m.task_state, float)
+    e.set_task(task_state=ts); o.set_task(task_state=ts)
+
+
+def test_humanoid_track_rollout_returns(engines, oracles):
+    """Config-3 shaped rollouts (16 cubic knots, dt 0.005) at a size the oracle finishes in seconds."""
+    m = get_model("humanoid_track")
+    e = engines("humanoid_track", N=64, H=128)
+    N, H, P = 24, 101, 16
+    rng = np.random.default_rng(11)
+    state = np.concatenate([m.key_qpos[0], np.zeros(m.nv)])
+    knots = np.clip(0.15 * 0.3 * rng.standard_normal((N, P, m.nu)), -1, 1); knots[0] = 0
+    kt = np.arange(P) * (H - 1) * 0.005 / (P - 1)
+    mocap = _track_mocap(m)
+    ret, fail, order = e.rollout_spline(state, 0.0, mocap, knots, kt, 2, H)
+    r64 = oracles("humanoid_track", 64).rollout_spline(state, 0.0, mocap, knots, kt, 2, H, nthreads=8, full=True)
+    r32 = oracles("humanoid_track", 32).rollout_spline(state, 0.0, mocap, knots, kt, 2, H, nthreads=8, full=False)
+    assert not fail.any() and not r64["failure"].any()
+    rel64 = np.abs(ret - r64["returns"]) / np.abs(r64["returns"])
+    rel32 = np.abs(ret - r32["returns"]) / np.abs(r32["returns"])
+    print("humanoid track: max rel return error vs fp32 oracle %.2e, vs fp64 oracle %.2e" % (rel32.max(), rel64.max()))
+    assert np.minimum(rel32, rel64).max() < 1e-3 and np.median(rel64) < 1e-4
+    tr = e.fetch_all()
+    np.testing.assert_allclose(tr["residual"][:N, 0], r64["residual"][:, 0], atol=3e-4)
+    np.testing.assert_allclose(tr["actions"][:N, :H], r64["actions"], atol=2e-5)

@@ -84,3 +84,36 @@ def test_humanoid_stand_residual_and_rollout():
     assert not out["failure"].any() and np.isfinite(out["returns"]).all() and (out["returns"] > 0).all()
     assert abs(out["states"][0, -1, 2] - 1.282) < 0.05        # zero control: the springs hold the pose for 0.35 s
     assert (out["states"][:, -1, 2] > 0.5).all()
+
+
+def test_humanoid_track_residual_against_independent_numpy():
+    """Tracking residual (tracking.cc:94-216) of the oracle vs a numpy restatement built on refmath (independent
+    kinematics + Jacobians): joint velocities, controls, mean-centred marker errors, marker velocity errors."""
+    from mujoco_mpc_b200 import task as T
+    from mujoco_mpc_b200.refmath import body_jacobian, kinematics
+    m = get_model("humanoid_track")
+    assert (m.nbody, m.nmocap, m.nkey, m.task_num_residual, m.task_num_term) == (37, 16, 1889, 141, 21)
+    assert sum(T.TRACK_MOTION_LENGTHS) == m.nkey and abs(m.opt_timestep - 0.005) < 1e-12
+    o = _oracle(m)
+    rng = np.random.default_rng(2)
+    mocap = np.concatenate([np.concatenate([m.key_mpos[0].reshape(-1, 3), np.tile([1.0, 0, 0, 0], (16, 1))], 1).reshape(-1)])
+    for mode, t in ((0, 0.0), (0, 1.2345), (3, 0.51), (9, 100.0)):      # last: clamps to the clip's final frame
+        o.set_task(task_state=np.array([float(mode), 0.25]))
+        q = m.key_qpos[sum(T.TRACK_MOTION_LENGTHS[:mode]) + 5].copy()
+        q[7:] += 0.05 * rng.standard_normal(m.nq - 7); q[2] += 1.0      # airborne: no contact forces needed here
+        v = 0.5 * rng.standard_normal(m.nv)
+        u = rng.uniform(-1, 1, m.nu)
+        r = o.forward_debug(q, v, u, mocap, time=t)["residual"][:141]
+        start = sum(T.TRACK_MOTION_LENGTHS[:mode]); last = start + T.TRACK_MOTION_LENGTHS[mode] - 1
+        idx = min(max((t - 0.25) * 30.0 + start, 0.0), float(last))
+        k0 = int(np.floor(idx)); k1 = min(k0 + 1, last); w1 = idx - k0
+        kin = kinematics(m, q)
+        mp = (m.key_mpos[k0] * (1 - w1) + m.key_mpos[k1] * w1).reshape(16, 3)
+        sp, sv = np.zeros((16, 3)), np.zeros((16, 3))
+        for b, name in enumerate(T.TRACK_BODIES):
+            s = m.site_names.index("tracking[%s]" % name); body = m.site_bodyid[s]
+            sp[b] = kin["xpos"][body] + kin["xmat"][body] @ m.site_pos[s]
+            sv[b] = body_jacobian(m, kin, body, sp[b])[:3] @ v
+        expect = np.concatenate([v[6:], u, mp.mean(0) - sp.mean(0), ((mp - mp.mean(0)) - (sp - sp.mean(0))).reshape(-1),
+                                 ((m.key_mpos[k1] - m.key_mpos[k0]).reshape(16, 3) * 30.0 - sv).reshape(-1)])
+        assert np.abs(r - expect).max() < 1e-9, (mode, t, np.abs(r - expect).argmax())
