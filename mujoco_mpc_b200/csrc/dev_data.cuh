@@ -103,7 +103,7 @@ constexpr int kLayWords = (int)((sizeof(DevLayout) + 15) / 16) * 4;
 
 struct DynSpec {
   static constexpr bool kStatic = false;
-  static constexpr int kNV = 0;
+  static constexpr int kNV = 0, kNHPair = 0;
   static __device__ __forceinline__ const DevModel& hdr(const Ctx& c) { return *reinterpret_cast<const DevModel*>(g_smem + c.hdr); }
   static __device__ __forceinline__ const DevModel& model(const Ctx& c) { return hdr(c); }
   template <int ID> static __device__ __forceinline__ float* mf(const Ctx& c) { return g_smem + hdr(c).fo[ID]; }
@@ -124,7 +124,7 @@ struct StaticSpec {
     MJPC_M_INTS(X)
 #undef X
   };
-  static constexpr int kNV = View::nv;
+  static constexpr int kNV = View::nv, kNHPair = View::nhpair;
   static constexpr int kHdr = View::nf + View::ni;
   static constexpr int kData0 = kHdr + kHdrWords + kLayWords;
   static __device__ __forceinline__ const DevModel& hdr(const Ctx&) { return *reinterpret_cast<const DevModel*>(g_smem + kHdr); }

@@ -1115,6 +1115,23 @@ __device__ __forceinline__ void jt_force_dense(Ctx& c, float* out) {
   __syncwarp();
 }
 
+// size dispatch: a static spec knows nv at compile time (dense, fully unrolled rows); the generic spec keeps the
+// runtime fast path for nv == 18 and otherwise the compact rows
+template <class SP>
+__device__ __forceinline__ float m_row_dot(const float* qM, int i, const float* v, int nv) {
+  if constexpr (SP::kNV > 0) return mat_row_dot<SP::kNV>(qM + i * SP::kNV, v);
+  else {
+    if (nv == 18) return mat_row_dot<18>(qM + i * 18, v);
+    float a = 0;
+    for (int j = 0; j < nv; j++) a += qM[i * nv + j] * v[j];
+    return a;
+  }
+}
+template <class SP>
+__device__ __forceinline__ float j_row_dot(Ctx& c, int row, int nsimple, const float* v, int nv) {
+  if constexpr (SP::kNV > 0) return row_dot_dense<SP, SP::kNV>(c, row, nsimple, v);
+  else return nv == 18 ? row_dot_dense<SP, 18>(c, row, nsimple, v) : row_dot<SP>(c, row, nsimple, v);
+}
 // Ma = M*qacc, jar = J*qacc - aref, gauss; returns total cost (uniform). If hess: qH = M + J^T diag(hw) J + cone rows,
 // assembled in two balanced stages: (1) every contact's small symmetric block (its chain dofs) into scratch,
 // one (contact, block entry) per lane; (2) every structurally non-zero Hessian entry gathers the blocks that
@@ -1129,13 +1146,11 @@ __device__ __noinline__ float k_total_cost(Ctx& c, const float* qacc, bool hess,
   float g = 0;
   for (int i = lane; i < nv; i += 32) {
     float a = 0;
-    if (nv == 18) a = mat_row_dot<18>(qM + i * 18, qacc);
-    else for (int j = 0; j < nv; j++) a += qM[i * nv + j] * qacc[j];
+    a = m_row_dot<SP>(qM, i, qacc, nv);
     Ma[i] = a;
     g += (a - smooth[i]) * (qacc[i] - qas[i]);
   }
-  if (nv == 18) { for (int i = lane; i < c.nefc; i += 32) jar[i] = row_dot_dense<SP, 18>(c, i, nsimple, qacc) - aref[i]; }
-  else { for (int i = lane; i < c.nefc; i += 32) jar[i] = row_dot<SP>(c, i, nsimple, qacc) - aref[i]; }
+  for (int i = lane; i < c.nefc; i += 32) jar[i] = j_row_dot<SP>(c, i, nsimple, qacc, nv) - aref[i];
   g = 0.5f * warp_sum(g);
   __syncwarp();
   const float cc = k_update_constraint<SP>(c, hess);
@@ -1173,7 +1188,8 @@ __device__ __noinline__ void k_hessian(Ctx& c) {
       X[(2 * ci) * kL + l] = xv;
       X[(2 * ci + 1) * kL + l] = xu;
     }
-    if (nv == 18) {   // dense copies for the register-blocked assembly
+    if (SP::kNV > 0 || nv == 18) {   // dense copies for the register-blocked assembly
+      const int nvp = (nv + 3) & ~3;
       float* Xd = DF(efc_Xd);
       const int* cloc = DI(con_loc);
       __syncwarp();
@@ -1182,11 +1198,15 @@ __device__ __noinline__ void k_hessian(Ctx& c) {
         const int a0 = cadr[ci];
         if (a0 < 0 || state[a0] != STATE_CONE) continue;
         const int l = cloc[w];
-        Xd[(2 * ci) * 20 + i] = l >= 0 ? X[(2 * ci) * kL + l] : 0.f;
-        Xd[(2 * ci + 1) * 20 + i] = l >= 0 ? X[(2 * ci + 1) * kL + l] : 0.f;
+        Xd[(2 * ci) * nvp + i] = l >= 0 ? X[(2 * ci) * kL + l] : 0.f;
+        Xd[(2 * ci + 1) * nvp + i] = l >= 0 ? X[(2 * ci + 1) * kL + l] : 0.f;
       }
     }
     __syncwarp();
+  }
+  if constexpr (SP::kNV > 0) {
+    hessian_dense_reg<SP, SP::kNV, (SP::kNHPair + 31) / 32>(c);
+    return;
   }
   if (nv == 18 && M.nhpair <= 128) {
     hessian_dense_reg<SP, 18, 4>(c);
@@ -1481,6 +1501,12 @@ __device__ __forceinline__ void jt_force(Ctx& c, float* out_or_null) {
 }
 
 template <class SP>
+__device__ __forceinline__ void jt_force_any(Ctx& c, float* out, int nv) {
+  if constexpr (SP::kNV > 0) jt_force_dense<SP, SP::kNV>(c, out);
+  else { if (nv == 18) jt_force_dense<SP, 18>(c, out); else jt_force<SP>(c, out); }
+}
+
+template <class SP>
 __device__ __noinline__ void k_solve(Ctx& c) {
   auto&& M = SP::model(c);
   const int lane = c.lane, nv = M.nv, ne = c.nefc;
@@ -1515,7 +1541,7 @@ __device__ __noinline__ void k_solve(Ctx& c) {
   bool qfc_current = false;
   for (int iter = 0; iter <= M.iterations; iter++) {
     // gradient at the current point; qfc doubles as the J^T force scratch and is the output when we stop here
-    if (nv == 18) jt_force_dense<SP, 18>(c, qfc); else jt_force<SP>(c, qfc);
+    jt_force_any<SP>(c, qfc, nv);
     qfc_current = true;
     float g2 = 0;
     for (int i = lane; i < nv; i += 32) {
@@ -1538,15 +1564,13 @@ __device__ __noinline__ void k_solve(Ctx& c) {
     float q1 = 0, q2 = 0, sn = 0;
     for (int i = lane; i < nv; i += 32) {
       float a = 0;
-      if (nv == 18) a = mat_row_dot<18>(qM + i * 18, search);
-      else for (int j = 0; j < nv; j++) a += qM[i * nv + j] * search[j];
+      a = m_row_dot<SP>(qM, i, search, nv);
       Mv[i] = a;
       q1 += search[i] * (Ma[i] - smooth[i]);
       q2 += 0.5f * search[i] * a;
       sn += search[i] * search[i];
     }
-    if (nv == 18) { for (int i = lane; i < ne; i += 32) Jv[i] = row_dot_dense<SP, 18>(c, i, nsimple, search); }
-    else { for (int i = lane; i < ne; i += 32) Jv[i] = row_dot<SP>(c, i, nsimple, search); }
+    for (int i = lane; i < ne; i += 32) Jv[i] = j_row_dot<SP>(c, i, nsimple, search, nv);
     q1 = warp_sum(q1); q2 = warp_sum(q2); sn = sqrtf(warp_sum(sn));
     __syncwarp();
     const float alpha = k_line_search<SP>(c, gauss, q1, q2, sn, scale_inv);
@@ -1558,7 +1582,7 @@ __device__ __noinline__ void k_solve(Ctx& c) {
     qfc_current = false;
     c.niter = iter + 1;
   }
-  if (!qfc_current) { if (nv == 18) jt_force_dense<SP, 18>(c, qfc); else jt_force<SP>(c, qfc); }
+  if (!qfc_current) jt_force_any<SP>(c, qfc, nv);
 }
 
 // ------------------------------------------------------------------------------------------ pipeline pieces

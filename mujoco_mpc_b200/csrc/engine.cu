@@ -44,7 +44,7 @@ struct mjpc_b200 {
   ModelPack pack;
   int maxN = 0, maxH = 0, maxP = 64;
   int warps_per_cta = 1;
-  int static_spec = 0;   // 1: the model equals spec_quadruped.h -> statically specialised rollout kernel
+  int static_spec = 0;   // 1 / 2: the model equals spec_quadruped.h / spec_humanoid_track.h -> static rollout kernel
   float* d_pack = nullptr;
   // inputs
   float *d_state = nullptr, *d_mocap = nullptr, *d_task_state = nullptr, *d_knots = nullptr, *d_knot_times = nullptr;
@@ -131,8 +131,9 @@ int launch_rollout(mjpc_b200* h, const RolloutArgs& A) {
   CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
   // static instance: same arguments, same shared-memory image; MJPC_B200_NO_STATIC=1 forces the generic kernel
   const char* ns = std::getenv("MJPC_B200_NO_STATIC");
-  const bool use_static = h->static_spec == 1 && wpc == 1 && !(ns && ns[0] == '1');
-  if (use_static) rollout_kernel_quadruped<<<grid, 32, smem, h->stream>>>(A);
+  const bool use_static = h->static_spec != 0 && wpc == 1 && !(ns && ns[0] == '1');
+  if (use_static && h->static_spec == 1) rollout_kernel_quadruped<<<grid, 32, smem, h->stream>>>(A);
+  else if (use_static && h->static_spec == 2) rollout_kernel_humanoid_track<<<grid, 32, smem, h->stream>>>(A);
   else rollout_kernel<<<grid, 32 * wpc, smem, h->stream>>>(A);
   h->last_static = use_static ? 1 : 0;
   rank_kernel<<<(A.N + 255) / 256, 256, 0, h->stream>>>(A.returns, A.N, h->d_order);
@@ -250,6 +251,9 @@ int mjpc_b200_create(const mjpc_model_blob* model, int max_candidates, int max_h
   if (spec_matches<SpecQuadruped>(M, make_layout(M, 1))) {
     h->static_spec = 1;
     if (int rc = set_smem((const void*)rollout_kernel_quadruped, h->smem_bytes(h->maxP, 1))) { mjpc_b200_destroy(h); return rc; }
+  } else if (spec_matches<SpecHumanoidTrack>(M, make_layout(M, 1))) {
+    h->static_spec = 2;
+    if (int rc = set_smem((const void*)rollout_kernel_humanoid_track, h->smem_bytes(h->maxP, 1))) { mjpc_b200_destroy(h); return rc; }
   }
   if (int rc = ilqg_init(h->ilqg, h->pack.M, (int)H, h->smem_bytes(1, 1))) {
     mjpc_b200_destroy(h);

@@ -13,6 +13,7 @@
 #include "dev_physics.cuh"
 #include "dev_task.cuh"
 #include "spec_quadruped.h"
+#include "spec_humanoid_track.h"
 
 namespace mjpc_dev {
 
@@ -198,6 +199,10 @@ extern "C" __global__ void __launch_bounds__(128) rollout_kernel(const __grid_co
 // statically specialised instance for the Quadruped (flat) task model (spec_quadruped.h); one warp per CTA
 extern "C" __global__ void __launch_bounds__(32) rollout_kernel_quadruped(const __grid_constant__ RolloutArgs A) {
   rollout_body<StaticSpec<SpecQuadruped>>(A);
+}
+// ... and for the Humanoid Track task model (spec_humanoid_track.h)
+extern "C" __global__ void __launch_bounds__(32) rollout_kernel_humanoid_track(const __grid_constant__ RolloutArgs A) {
+  rollout_body<StaticSpec<SpecHumanoidTrack>>(A);
 }
 
 // host: does the live model header / state layout equal the table a static kernel was compiled from?

@@ -235,17 +235,27 @@ def test_cpp_cross_entropy_planner_matches_python_mirror(engines, quadruped):
     cpp.close()
 
 
-def test_static_and_generic_kernels_agree(quadruped, monkeypatch):
-    """The statically specialised rollout kernel (csrc/spec_quadruped.h) and the generic one run the same device
-    functions: same returns on the same inputs, and the shipped quadruped model must select the static instance."""
+@pytest.mark.parametrize("name", ["quadruped", "humanoid_track"])
+def test_static_and_generic_kernels_agree(name, monkeypatch):
+    """The statically specialised rollout kernels (csrc/spec_*.h) and the generic one run the same device
+    functions: same returns on the same inputs, and the shipped task models must select their static instance."""
     from mujoco_mpc_b200.engine import Engine
-    m = quadruped
-    state, mocap, knots, kt = quadruped_inputs(m, N=32, H=64)
-    e = Engine(m, 32, 64)
-    r1, f1, o1 = e.rollout_spline(state, 0.0, mocap, knots, kt, 2, 64)
-    assert e.last_kernel_static, "spec_quadruped.h is stale: run python -m mujoco_mpc_b200.build"
+    m = get_model(name)
+    if name == "quadruped":
+        state, mocap, knots, kt = quadruped_inputs(m, N=32, H=64)
+        H = 64
+    else:
+        rng = np.random.default_rng(1)
+        H, P = 48, 16
+        state = np.concatenate([m.key_qpos[0], np.zeros(m.nv)])
+        mocap = _track_mocap(m)
+        knots = np.clip(0.05 * rng.standard_normal((32, P, m.nu)), -1, 1)
+        kt = np.arange(P) * (H - 1) * 0.005 / (P - 1)
+    e = Engine(m, 32, H)
+    r1, f1, o1 = e.rollout_spline(state, 0.0, mocap, knots, kt, 2, H)
+    assert e.last_kernel_static, "csrc/spec_%s.h is stale: run python -m mujoco_mpc_b200.build" % name
     monkeypatch.setenv("MJPC_B200_NO_STATIC", "1")
-    r2, f2, o2 = e.rollout_spline(state, 0.0, mocap, knots, kt, 2, 64)
+    r2, f2, o2 = e.rollout_spline(state, 0.0, mocap, knots, kt, 2, H)
     assert not e.last_kernel_static
     np.testing.assert_allclose(r1, r2, rtol=2e-4)
     assert (f1 == f2).all()
