@@ -19,7 +19,7 @@ def ctx(oracle_lib):
     from mujoco_mpc_b200.engine import Engine
     build.build()
     out = {}
-    for name in ("cartpole", "quadruped", "particle"):
+    for name in ("cartpole", "quadruped", "particle", "humanoid"):
         m = get_model(name)
         out[name] = (m, Engine(m, 64, 64), oracle_lib.Oracle(to_blob(m), m, 64))
     yield out
@@ -61,7 +61,7 @@ def test_backward_pass_golden_on_device(ctx, oracle_lib):
     assert np.abs(o["K"][:, :, 2:]).max() == 0 and np.abs(o["Vxx"][:, 2:, :]).max() == 0
 
 
-@pytest.mark.parametrize("name,eps", [("cartpole", 1e-3), ("quadruped", 1e-3)])
+@pytest.mark.parametrize("name,eps", [("cartpole", 1e-3), ("quadruped", 1e-3), ("humanoid", 1e-3)])
 def test_model_derivatives(ctx, name, eps):
     m, e, o = ctx[name]
     H = 8
@@ -75,7 +75,7 @@ def test_model_derivatives(ctx, name, eps):
         scale = np.abs(R).max() + 1.0
         print(name, nm, "max abs err %.2e (scale %.2e), median %.2e" % (err.max(), scale, np.median(err)))
         assert np.median(err) < 2e-4 * scale
-        if name == "quadruped":
+        if name in ("quadruped", "humanoid"):
             # a perturbation can open/close a contact in one arithmetic and not the other: a handful of entries of the
             # stiff contact block differ at O(1); everything else agrees to round-off / eps
             assert np.quantile(err, 0.99) < 1e-2 * scale and err.max() < 0.1 * scale
@@ -83,7 +83,7 @@ def test_model_derivatives(ctx, name, eps):
             assert err.max() < 2e-3 * scale
 
 
-@pytest.mark.parametrize("name", ["cartpole", "quadruped", "particle"])
+@pytest.mark.parametrize("name", ["cartpole", "quadruped", "particle", "humanoid"])
 def test_cost_derivatives(ctx, name):
     m, e, o = ctx[name]
     H = 8
@@ -160,4 +160,19 @@ def test_ilqg_quadruped_iteration_improves(ctx):
         ok += bool(pl.optimize_policy())
     assert ok >= 3 and np.isfinite(pl.total_return)
     assert pl.total_return < first
+    assert (np.abs(pl.actions) <= 1.0 + 1e-6).all()
+
+
+def test_ilqg_humanoid_iteration_improves(ctx):
+    """iLQG on the humanoid (Stand task, nv = 27, pyramidal cones, tendon limits) through the generic FD kernels."""
+    from mujoco_mpc_b200.ilqg import ILQGPlanner
+    m, e, _ = ctx["humanoid"]
+    pl = ILQGPlanner(m, e, horizon=24, num_rollouts=10, fd_tolerance=1e-3)
+    pl.set_state(np.concatenate([m.qpos0, np.zeros(m.nv)]), 0.0, mocap_of(m))
+    pl.nominal_trajectory()
+    first = pl.total_return
+    ok = 0
+    for _ in range(5):
+        ok += bool(pl.optimize_policy())
+    assert ok >= 2 and np.isfinite(pl.total_return) and pl.total_return <= first
     assert (np.abs(pl.actions) <= 1.0 + 1e-6).all()
