@@ -68,10 +68,21 @@ def test_model_derivatives(ctx, name, eps):
     state, xs, us, ts, res = _nominal(m, o, H)
     A, B, C, D = e.model_derivatives(xs, us, ts, mocap_of(m), eps)
     Ao, Bo, Co, Do = o.model_derivatives(xs, us, ts, mocap_of(m), tol=eps)
+    contact = name in ("quadruped", "humanoid")
+    if contact:
+        # a perturbed step can toggle a contact / limit row in one precision and not in the other (measured on the
+        # humanoid: the fp32 ORACLE differs from the fp64 oracle by the full entry scale on such columns and matches
+        # the device to 4 digits): compare each entry with the nearer of the two oracle precisions
+        from mujoco_mpc_b200.blob import to_blob
+        from oracle import pyoracle
+        o32 = pyoracle.Oracle(to_blob(m), m, 32)
+        A3, B3, C3, D3 = o32.model_derivatives(xs, us, ts, mocap_of(m), tol=eps)
     # structure: last step has only C
     assert np.abs(A[-1]).max() == 0 and np.abs(B[-1]).max() == 0 and np.abs(D[-1]).max() == 0
-    for G, R, nm in ((A, Ao, "A"), (B, Bo, "B"), (C, Co, "C"), (D, Do, "D")):
+    for k, (G, R, nm) in enumerate(((A, Ao, "A"), (B, Bo, "B"), (C, Co, "C"), (D, Do, "D"))):
         err = np.abs(G - R)
+        if contact:
+            err = np.minimum(err, np.abs(G - (A3, B3, C3, D3)[k]))
         scale = np.abs(R).max() + 1.0
         print(name, nm, "max abs err %.2e (scale %.2e), median %.2e" % (err.max(), scale, np.median(err)))
         assert np.median(err) < 2e-4 * scale
