@@ -196,6 +196,22 @@ void mjpc_b200_ce_planner_action_from_policy(void* planner, double* action, doub
 int mjpc_b200_ce_planner_get_result(void* planner, double* improvement, float* returns, int* order, double* knots,
                                     double* knot_times, double* variance);
 
+/* ---- iLQG planner (csrc/host/ilqg_planner.{h,cc}; mjpc/planners/ilqg/planner.h, planner.cc:156-740).
+ * OptimizePolicy = NominalTrajectory (feedback-scaling line search) + Iteration (model derivatives, cost derivatives,
+ * backward pass with the regularisation retry loop, K action rollouts, winner, regularisation update); each sweep is
+ * one call of the ABI above.  Returns 1 when the policy was updated, 0 when the iteration was rejected, <0 on error. */
+int mjpc_b200_ilqg_planner_create(const mjpc_model_blob* model, int num_rollouts, int representation, double fd_tolerance,
+                                  int max_horizon, int device, void** out);
+void mjpc_b200_ilqg_planner_destroy(void* planner);
+void mjpc_b200_ilqg_planner_reset(void* planner, int horizon, const double* initial_repeated_action);
+void mjpc_b200_ilqg_planner_set_state(void* planner, const double* state, double time, const double* mocap);
+int mjpc_b200_ilqg_planner_nominal_trajectory(void* planner, int horizon);
+int mjpc_b200_ilqg_planner_optimize_policy(void* planner, int horizon);
+void mjpc_b200_ilqg_planner_action_from_policy(void* planner, double* action, double time);
+/* scalars[6] = {total_return, regularization, improvement, expected, surprise, winner}; nominal states [H][dim_state],
+ * actions [H][nu], times [H] (any pointer may be NULL); returns H */
+int mjpc_b200_ilqg_planner_get_result(void* planner, double* scalars, float* states, float* actions, double* times);
+
 #ifdef __cplusplus
 }
 #endif

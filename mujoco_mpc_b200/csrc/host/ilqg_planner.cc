@@ -1,0 +1,216 @@
+// ilqg_planner.cc - see ilqg_planner.h.  Reference: mjpc/planners/ilqg/planner.cc.
+#include "ilqg_planner.h"
+
+#include <algorithm>
+#include <cmath>
+
+namespace mjpc_b200_host {
+
+iLQGPlanner::~iLQGPlanner() {
+  if (gpu_) mjpc_b200_destroy(gpu_);
+}
+
+int iLQGPlanner::Initialize(const mjpc_model_blob* model, int num_rollouts, int representation, int max_horizon, int device) {
+  K_ = std::max(num_rollouts, 1);
+  int rc = mjpc_b200_create(model, std::max(K_, 1), max_horizon, device, &gpu_);
+  if (rc) return rc;
+  mjpc_b200_get_info(gpu_, &info_);
+  nu_ = info_.nu; ds_ = info_.dim_state; n_ = info_.dim_dstate; nr_ = info_.num_residual;
+  representation_ = representation;
+  state_.assign(ds_, 0.0); mocap_.assign(7 * info_.nmocap, 0.0);
+  Reset(max_horizon, nullptr);
+  return 0;
+}
+
+void iLQGPlanner::Reset(int horizon, const double* a) {
+  H_ = horizon;
+  const size_t H = horizon;
+  states.assign(H * ds_, 0.f); times.assign(H, 0.0); residual.assign(H * nr_, 0.f);
+  actions.assign(H * nu_, 0.f);
+  if (a) for (size_t t = 0; t < H; t++) for (int i = 0; i < nu_; i++) actions[t * nu_ + i] = (float)a[i];
+  gains.assign(H * nu_ * n_, 0.f); du.assign(H * nu_, 0.f);
+  total_return = 0; regularization = 1.0; regularization_rate = 1.0; regularization_factor = 2.0;
+  feedback_scaling = 1.0; winner = 0; improvement = expected = surprise = 0;
+  ret_.assign(K_, 0.f); fail_.assign(K_, 0); order_.assign(K_, 0);
+}
+
+void iLQGPlanner::SetState(const double* state, double time, const double* mocap) {
+  std::copy(state, state + ds_, state_.begin());
+  if (!mocap_.empty()) std::copy(mocap, mocap + mocap_.size(), mocap_.begin());
+  time_ = time;
+}
+
+std::vector<float> iLQGPlanner::StepSizes() const {
+  std::vector<float> s(K_, 0.f);
+  const int steps = K_ - 1;
+  if (steps > 0) {
+    const double lo = std::log(settings.min_linesearch_step), hi = std::log(1.0);
+    const double step = (hi - lo) / std::max(steps - 1, 1);
+    for (int i = 0; i < steps; i++) s[i] = (float)std::exp(lo + i * step);
+  }
+  s[K_ - 1] = 0.f;
+  return s;
+}
+
+int iLQGPlanner::BestRollout(const std::vector<float>& ret, const std::vector<uint8_t>& fail, int K) {
+  int best = -1;
+  float best_ret = 0;
+  for (int j = K - 1; j >= 0; j--) {
+    if (fail[j]) continue;
+    if (best == -1 || ret[j] < best_ret) { best_ret = ret[j]; best = j; }
+  }
+  return best;
+}
+
+int iLQGPlanner::Install(int candidate, double ret) {
+  const size_t H = H_;
+  best_.horizon = H_; best_.dim_state = ds_; best_.dim_action = nu_; best_.dim_residual = nr_;
+  best_.dim_trace = 3 * info_.num_trace;
+  best_.states.resize(H * ds_); best_.actions.resize(H * nu_); best_.times.resize(H); best_.residual.resize(H * nr_);
+  best_.costs.resize(H); best_.trace.resize(H * best_.dim_trace);
+  if (mjpc_b200_fetch_trajectory(gpu_, candidate, best_.states.data(), best_.actions.data(), best_.times.data(),
+                                 best_.residual.data(), best_.costs.data(), best_.trace.data()))
+    return -1;
+  states = best_.states; actions = best_.actions; times = best_.times; residual = best_.residual;
+  total_return = ret;
+  best_.total_return = ret; best_.failure = false;
+  return 0;
+}
+
+int iLQGPlanner::NominalTrajectory(int horizon) {
+  H_ = horizon;
+  const std::vector<float> steps = StepSizes();
+  std::vector<float> st(state_.begin(), state_.end()), mc(mocap_.begin(), mocap_.end());
+  if (mjpc_b200_rollout_feedback(gpu_, st.data(), time_, mc.empty() ? nullptr : mc.data(), nullptr, actions.data(),
+                                 states.data(), times.data(), gains.data(), nullptr, steps.data(), representation_, K_,
+                                 horizon, ret_.data(), fail_.data(), order_.data()))
+    return -1;
+  const int best = BestRollout(ret_, fail_, K_);
+  if (best == -1) { feedback_scaling = 0.0; return 0; }
+  if (Install(best, ret_[best])) return -1;
+  feedback_scaling = steps[best];
+  return 1;
+}
+
+void iLQGPlanner::ScaleRegularization(double factor) {
+  if (factor > 1) regularization_rate = std::max(regularization_rate * factor, factor);
+  else regularization_rate = std::min(regularization_rate * factor, factor);
+  regularization = std::min(std::max(regularization * regularization_rate, settings.min_regularization),
+                            settings.max_regularization);
+}
+
+void iLQGPlanner::UpdateRegularization(double z, double s) {
+  const double f = regularization_factor;
+  if (!(std::isfinite(z) && std::isfinite(s))) ScaleRegularization(f * f);
+  else if (z > 0.5 || s > 0.3) ScaleRegularization(1.0 / f);
+  else if (z < 0.1 || s < 0.06) ScaleRegularization(f);
+}
+
+int iLQGPlanner::Iteration(int horizon) {
+  const size_t H = horizon, n = n_, m = nu_, nr = nr_;
+  const double previous_return = total_return;
+  const std::vector<float> steps = StepSizes();
+  A_.resize(H * n * n); B_.resize(H * n * m); C_.resize(H * nr * n); D_.resize(H * nr * m);
+  cx_.resize(H * n); cu_.resize(H * m); cxx_.resize(H * n * n); cuu_.resize(H * m * m); cxu_.resize(H * n * m);
+  Kbuf_.resize(H * m * n); dubuf_.resize(H * m);
+  std::vector<float> mc(mocap_.begin(), mocap_.end()), st(state_.begin(), state_.end());
+  if (mjpc_b200_model_derivatives(gpu_, states.data(), actions.data(), times.data(), mc.empty() ? nullptr : mc.data(),
+                                  horizon, (float)settings.fd_tolerance, A_.data(), B_.data(), C_.data(), D_.data()))
+    return -1;
+  if (mjpc_b200_cost_derivatives(gpu_, residual.data(), C_.data(), D_.data(), horizon, cx_.data(), cu_.data(),
+                                 cxx_.data(), cuu_.data(), cxu_.data()))
+    return -1;
+  int status = 0, reg_iter = 0;
+  float dV[2] = {0, 0};
+  while (reg_iter < settings.max_regularization_iterations && status == 0) {
+    if (mjpc_b200_backward_pass(gpu_, A_.data(), B_.data(), cx_.data(), cu_.data(), cxx_.data(), cxu_.data(),
+                                cuu_.data(), actions.data(), horizon, (float)regularization, settings.regularization_type,
+                                settings.action_limits, Kbuf_.data(), dubuf_.data(), dV, nullptr, nullptr, &status))
+      return -1;
+    if (status == 0 && regularization <= settings.max_regularization) {
+      ScaleRegularization(regularization_factor);
+      reg_iter++;
+    }
+  }
+  if (status == 0) return 0;
+  gains = Kbuf_; du = dubuf_;
+  if (mjpc_b200_rollout_feedback(gpu_, st.data(), time_, mc.empty() ? nullptr : mc.data(), nullptr, actions.data(),
+                                 states.data(), times.data(), gains.data(), du.data(), steps.data(), 3, K_, horizon,
+                                 ret_.data(), fail_.data(), order_.data()))
+    return -1;
+  const int best = BestRollout(ret_, fail_, K_);
+  if (best == -1) return 0;
+  winner = best;
+  if (Install(best, ret_[best])) return -1;
+  const double action_step = steps[best];
+  expected = -1.0 * action_step * ((double)dV[0] + action_step * (double)dV[1]) + 1.0e-16;
+  improvement = previous_return - total_return;
+  surprise = std::min(std::max(0.0, improvement / expected), 2.0);
+  UpdateRegularization(surprise, action_step);
+  feedback_scaling = 1.0;
+  return 1;
+}
+
+int iLQGPlanner::OptimizePolicy(int horizon) {
+  if (NominalTrajectory(horizon) < 0) return -1;
+  return Iteration(horizon);
+}
+
+// iLQGPolicy::Action with linear interpolation of the nominal (policy.cc:82-161): u = u_t + K_t (x (-) x_t), clamped.
+// The tangent-space difference of the free-joint quaternion needs the model's joint table, which stays behind the
+// ABI: this host copy serves the open-loop part (state == nullptr) that the physics thread needs between plans.
+void iLQGPlanner::ActionFromPolicy(double* action, const double*, double time) const {
+  const int H = H_;
+  int lo = 0;
+  while (lo + 1 < H && times[lo + 1] <= time) lo++;
+  const int hi = std::min(lo + 1, H - 1);
+  const double dt = times[hi] - times[lo];
+  const double w = dt > 0 ? std::min(std::max((time - times[lo]) / dt, 0.0), 1.0) : 0.0;
+  for (int i = 0; i < nu_; i++)
+    action[i] = (1 - w) * actions[(size_t)lo * nu_ + i] + w * actions[(size_t)hi * nu_ + i];
+}
+
+}  // namespace mjpc_b200_host
+
+// ------------------------------------------------------------------------------------------ C entry points
+using mjpc_b200_host::iLQGPlanner;
+
+extern "C" {
+
+int mjpc_b200_ilqg_planner_create(const mjpc_model_blob* model, int num_rollouts, int representation, double fd_tolerance,
+                                  int max_horizon, int device, void** out) {
+  if (!model || !out || num_rollouts < 1 || max_horizon < 2) return MJPC_B200_ERR_BAD_ARGUMENT;
+  auto* p = new iLQGPlanner;
+  int rc = p->Initialize(model, num_rollouts, representation, max_horizon, device);
+  if (rc) { delete p; *out = nullptr; return rc; }
+  if (fd_tolerance > 0) p->settings.fd_tolerance = fd_tolerance;
+  *out = p;
+  return 0;
+}
+void mjpc_b200_ilqg_planner_destroy(void* p) { delete (iLQGPlanner*)p; }
+void mjpc_b200_ilqg_planner_reset(void* p, int horizon, const double* initial_repeated_action) {
+  ((iLQGPlanner*)p)->Reset(horizon, initial_repeated_action);
+}
+void mjpc_b200_ilqg_planner_set_state(void* p, const double* state, double time, const double* mocap) {
+  ((iLQGPlanner*)p)->SetState(state, time, mocap);
+}
+int mjpc_b200_ilqg_planner_nominal_trajectory(void* p, int horizon) { return ((iLQGPlanner*)p)->NominalTrajectory(horizon); }
+int mjpc_b200_ilqg_planner_optimize_policy(void* p, int horizon) { return ((iLQGPlanner*)p)->OptimizePolicy(horizon); }
+void mjpc_b200_ilqg_planner_action_from_policy(void* p, double* action, double time) {
+  ((iLQGPlanner*)p)->ActionFromPolicy(action, nullptr, time);
+}
+// scalars[6] = {total_return, regularization, improvement, expected, surprise, winner}; nominal states [H][dim_state],
+// actions [H][nu], times [H]; any pointer may be NULL
+int mjpc_b200_ilqg_planner_get_result(void* pv, double* scalars, float* states, float* actions, double* times) {
+  auto* p = (iLQGPlanner*)pv;
+  if (scalars) {
+    scalars[0] = p->total_return; scalars[1] = p->regularization; scalars[2] = p->improvement;
+    scalars[3] = p->expected; scalars[4] = p->surprise; scalars[5] = p->winner;
+  }
+  if (states) std::copy(p->states.begin(), p->states.end(), states);
+  if (actions) std::copy(p->actions.begin(), p->actions.end(), actions);
+  if (times) std::copy(p->times.begin(), p->times.end(), times);
+  return (int)p->times.size();
+}
+
+}  // extern "C"

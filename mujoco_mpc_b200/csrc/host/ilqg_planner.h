@@ -1,0 +1,65 @@
+// ilqg_planner.h - C++ host side of the iLQG planner with the reference's method names
+// (mjpc/planners/ilqg/planner.h, planner.cc:40-740; settings.h:21-36; backward_pass.cc:327-356 regularisation).
+// Every sweep is one call of the C ABI: NominalTrajectory / ActionRollouts -> mjpc_b200_rollout_feedback,
+// ModelDerivatives::Compute -> mjpc_b200_model_derivatives, CostDerivatives::Compute -> mjpc_b200_cost_derivatives,
+// the Riccati loop -> mjpc_b200_backward_pass (the regularisation retry loop, planner.cc:429-520, stays here).
+#pragma once
+#include <cstdint>
+#include <shared_mutex>
+#include <vector>
+
+#include "../../../include/mjpc_b200.h"
+#include "sampling_planner.h"
+
+namespace mjpc_b200_host {
+
+struct iLQGSettings {                    // mjpc/planners/ilqg/settings.h:21-36
+  double min_linesearch_step = 1.0e-3;
+  double fd_tolerance = 1.0e-6;          // fp32 finite differences want ~1e-3 (tests/test_gpu_ilqg.py header)
+  double min_regularization = 1.0e-6;
+  double max_regularization = 1.0e6;
+  int regularization_type = 0;           // 0 control, 1 feedback, 2 value, 3 none
+  int max_regularization_iterations = 5;
+  int action_limits = 1;
+  int nominal_feedback_scaling = 1;
+};
+
+class iLQGPlanner {
+ public:
+  ~iLQGPlanner();
+  int Initialize(const mjpc_model_blob* model, int num_rollouts, int representation, int max_horizon, int device);
+  void Reset(int horizon, const double* initial_repeated_action);
+  void SetState(const double* state, double time, const double* mocap);
+  int OptimizePolicy(int horizon);       // planner.cc:156-165: NominalTrajectory + Iteration; 1 = policy updated
+  int NominalTrajectory(int horizon);    // :167-223
+  int Iteration(int horizon);            // :377-627
+  void ActionFromPolicy(double* action, const double* state, double time) const;   // ilqg/policy.cc:82-161 (mode 1: linear)
+  const Trajectory* BestTrajectory() const { return &best_; }
+
+  iLQGSettings settings;
+  // policy: nominal trajectory, feedback gains, open-loop improvement (iLQGPolicy)
+  std::vector<float> states, actions, residual, gains, du;
+  std::vector<double> times;
+  double total_return = 0, regularization = 1.0, regularization_rate = 1.0, regularization_factor = 2.0;
+  double feedback_scaling = 1.0, improvement = 0, expected = 0, surprise = 0;
+  int winner = 0;
+  mjpc_b200_t* gpu() { return gpu_; }
+
+ private:
+  std::vector<float> StepSizes() const;                                   // LogScale (utilities.cc:819-825) + trailing 0
+  static int BestRollout(const std::vector<float>& ret, const std::vector<uint8_t>& fail, int K);   // :727-740
+  int Install(int candidate, double ret);
+  void ScaleRegularization(double factor);                                // backward_pass.cc:327-343
+  void UpdateRegularization(double z, double s);                          // :345-356
+  mjpc_b200_t* gpu_ = nullptr;
+  mjpc_b200_info info_{};
+  int K_ = 10, representation_ = 1, H_ = 0, nu_ = 0, ds_ = 0, n_ = 0, nr_ = 0;
+  std::vector<double> state_, mocap_;
+  double time_ = 0;
+  std::vector<float> A_, B_, C_, D_, cx_, cu_, cxx_, cuu_, cxu_, Kbuf_, dubuf_, ret_;
+  std::vector<uint8_t> fail_;
+  std::vector<int> order_;
+  Trajectory best_;
+};
+
+}  // namespace mjpc_b200_host

@@ -31,7 +31,11 @@ EXPORTS = ["mjpc_b200_version", "mjpc_b200_last_error", "mjpc_b200_create", "mjp
            "mjpc_b200_planner_action_from_policy", "mjpc_b200_planner_get_result",
            "mjpc_b200_ce_planner_create", "mjpc_b200_ce_planner_destroy", "mjpc_b200_ce_planner_reset",
            "mjpc_b200_ce_planner_set_state", "mjpc_b200_ce_planner_optimize_policy",
-           "mjpc_b200_ce_planner_action_from_policy", "mjpc_b200_ce_planner_get_result"]
+           "mjpc_b200_ce_planner_action_from_policy", "mjpc_b200_ce_planner_get_result",
+           "mjpc_b200_ilqg_planner_create", "mjpc_b200_ilqg_planner_destroy", "mjpc_b200_ilqg_planner_reset",
+           "mjpc_b200_ilqg_planner_set_state", "mjpc_b200_ilqg_planner_nominal_trajectory",
+           "mjpc_b200_ilqg_planner_optimize_policy", "mjpc_b200_ilqg_planner_action_from_policy",
+           "mjpc_b200_ilqg_planner_get_result"]
 
 
 class ModelBlob(C.Structure):
@@ -66,6 +70,7 @@ def load_library():
         lib.mjpc_b200_host_philox_normal.restype = C.c_double
         lib.mjpc_b200_planner_destroy.argtypes = [C.c_void_p]
         lib.mjpc_b200_ce_planner_destroy.argtypes = [C.c_void_p]
+        lib.mjpc_b200_ilqg_planner_destroy.argtypes = [C.c_void_p]
         for n in ("mjpc_b200_destroy", "mjpc_b200_fetch_stats", "mjpc_b200_launch_count", "mjpc_b200_last_kernel_ms", "mjpc_b200_stream",
                   "mjpc_b200_device_returns", "mjpc_b200_sync", "mjpc_b200_launch_resident"):
             getattr(lib, n).argtypes = [C.c_void_p]
@@ -373,4 +378,58 @@ class CppCrossEntropyPlanner:
     def action_from_policy(self, time, use_previous=False):
         a = np.zeros(self.nu)
         self.lib.mjpc_b200_ce_planner_action_from_policy(self.h, _pd(a), C.c_double(time), int(use_previous))
+        return a
+
+
+class CppILQGPlanner:
+    """The C++ iLQG planner (csrc/host/ilqg_planner.cc) through its C wrappers."""
+
+    def __init__(self, model, horizon, num_rollouts=10, representation=1, fd_tolerance=1e-3, device=0):
+        self.lib = load_library()
+        m = self.m = model
+        self._blob = to_blob(model)
+        self._buf = C.create_string_buffer(self._blob, len(self._blob))
+        mb = ModelBlob(C.cast(self._buf, C.c_void_p), len(self._blob))
+        self.H, self.nu, self.ds = int(horizon), m.nu, m.nq + m.nv
+        h = C.c_void_p()
+        rc = self.lib.mjpc_b200_ilqg_planner_create(C.byref(mb), int(num_rollouts), int(representation),
+                                                    C.c_double(fd_tolerance), self.H, int(device), C.byref(h))
+        if rc != 0:
+            raise EngineError(f"mjpc_b200_ilqg_planner_create failed ({rc}): {self.lib.mjpc_b200_last_error().decode()}")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mjpc_b200_ilqg_planner_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def reset(self, initial_repeated_action=None):
+        a = _d(initial_repeated_action)
+        self.lib.mjpc_b200_ilqg_planner_reset(self.h, self.H, _pd(a))
+
+    def set_state(self, state, time, mocap):
+        s, mc = _d(state), _d(mocap)
+        self.lib.mjpc_b200_ilqg_planner_set_state(self.h, _pd(s), C.c_double(time), _pd(mc))
+
+    def nominal_trajectory(self):
+        return self.lib.mjpc_b200_ilqg_planner_nominal_trajectory(self.h, self.H)
+
+    def optimize_policy(self):
+        rc = self.lib.mjpc_b200_ilqg_planner_optimize_policy(self.h, self.H)
+        if rc < 0:
+            raise EngineError(f"ilqg_planner_optimize_policy failed: {self.lib.mjpc_b200_last_error().decode()}")
+        return rc
+
+    def result(self):
+        sc = np.zeros(6); st = np.zeros((self.H, self.ds), np.float32); ac = np.zeros((self.H, self.nu), np.float32)
+        tm = np.zeros(self.H)
+        self.lib.mjpc_b200_ilqg_planner_get_result(self.h, _pd(sc), _pf(st), _pf(ac), _pd(tm))
+        return dict(total_return=sc[0], regularization=sc[1], improvement=sc[2], expected=sc[3], surprise=sc[4],
+                    winner=int(sc[5]), states=st, actions=ac, times=tm)
+
+    def action_from_policy(self, time):
+        a = np.zeros(self.nu)
+        self.lib.mjpc_b200_ilqg_planner_action_from_policy(self.h, _pd(a), C.c_double(time))
         return a

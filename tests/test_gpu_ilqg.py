@@ -187,3 +187,32 @@ def test_ilqg_humanoid_iteration_improves(ctx):
         ok += bool(pl.optimize_policy())
     assert ok >= 2 and np.isfinite(pl.total_return) and pl.total_return <= first
     assert (np.abs(pl.actions) <= 1.0 + 1e-6).all()
+
+
+def test_cpp_ilqg_planner_matches_python_mirror(ctx):
+    """The C++ iLQGPlanner (csrc/host/ilqg_planner.cc) and the Python mirror drive the same sweeps through the same
+    ABI: identical nominal trajectories, returns and regularisation schedule over several planning iterations."""
+    from mujoco_mpc_b200.engine import CppILQGPlanner, Engine
+    from mujoco_mpc_b200.ilqg import ILQGPlanner
+    m = get_model("quadruped")
+    H = 32
+    state = np.concatenate([m.key_qpos[0], np.zeros(m.nv)])
+    cpp = CppILQGPlanner(m, H, num_rollouts=10, representation=1, fd_tolerance=1e-3)
+    e = Engine(m, 16, H)
+    py = ILQGPlanner(m, e, horizon=H, num_rollouts=10, fd_tolerance=1e-3, representation=1)
+    cpp.reset(); cpp.set_state(state, 0.0, mocap_of(m)); py.set_state(state, 0.0, mocap_of(m))
+    for it in range(4):
+        ok_c = cpp.optimize_policy()
+        ok_p = py.optimize_policy()
+        r = cpp.result()
+        assert bool(ok_c) == bool(ok_p), it
+        np.testing.assert_allclose(r["total_return"], py.total_return, rtol=1e-6)
+        np.testing.assert_allclose(r["regularization"], py.regularization, rtol=1e-12)
+        np.testing.assert_allclose(r["actions"], py.actions, atol=1e-6)
+        np.testing.assert_allclose(r["states"], py.states, atol=1e-5)
+        if ok_c:
+            assert r["winner"] == py.winner
+            np.testing.assert_allclose(r["surprise"], py.surprise, rtol=1e-4, atol=1e-6)
+    a = cpp.action_from_policy(0.055)
+    assert a.shape == (m.nu,) and np.isfinite(a).all() and (np.abs(a) <= 1 + 1e-6).all()
+    cpp.close(); e.close()
