@@ -94,6 +94,12 @@ int mjpc_b200_rollout_spline(mjpc_b200_t* h, const float* state, double time, co
                              const float* userdata, const float* knots, const double* knot_times, int interp,
                              int P, int N, int H, float* returns, uint8_t* failure, int* order);
 
+/* NoisyRollout (mjpc/trajectory.cc:100-210, used by the Robust planner): the following rollouts of this handle add
+ * Ornstein-Uhlenbeck noise to xfrc_applied of every body (stationary std xfrc_std, correlation time xfrc_rate
+ * seconds), drawn from Philox4x32-10 with key (seed, 1) and counter (step, candidate, element, 'XFRC') - the
+ * reference's absl::BitGen cannot be seeded.  xfrc_std = 0 switches the noise off (the default). */
+int mjpc_b200_set_xfrc_noise(mjpc_b200_t* h, double xfrc_std, double xfrc_rate, uint32_t seed);
+
 /* K line-search rollouts of the iLQG policy. u_nom [H][nu], x_nom [H][dim_state], t_nom [H] (absolute),
  * gains [H][nu][dim_dstate], du [H][nu] (may be NULL), step_sizes [K]. */
 int mjpc_b200_rollout_feedback(mjpc_b200_t* h, const float* state, double time, const float* mocap,
@@ -195,6 +201,23 @@ void mjpc_b200_ce_planner_action_from_policy(void* planner, double* action, doub
  * returns the number of spline points */
 int mjpc_b200_ce_planner_get_result(void* planner, double* improvement, float* returns, int* order, double* knots,
                                     double* knot_times, double* variance);
+
+/* ---- Robust planner (csrc/host/robust_planner.{h,cc}; mjpc/planners/robust/robust_planner.cc:40-160) over the
+ * sampling planner: the best `ncandidates` of the clean launch are re-rolled `nrepetitions` times each with
+ * NoisyRollout force perturbations (one launch on a second handle) and the best mean score is installed.
+ * ncandidates = -1 -> num_trajectory / nrepetitions, nrepetitions <= 0 -> 5 (the reference's defaults). */
+int mjpc_b200_robust_planner_create(const mjpc_model_blob* model, int num_trajectory, int num_spline_points,
+                                    int interpolation, double exploration, double timestep, const double* ctrlrange,
+                                    uint32_t seed, int ncandidates, int nrepetitions, double xfrc_std, double xfrc_rate,
+                                    int max_horizon, int device, void** out);
+void mjpc_b200_robust_planner_destroy(void* planner);
+void mjpc_b200_robust_planner_reset(void* planner, int horizon, const double* initial_repeated_action);
+void mjpc_b200_robust_planner_set_state(void* planner, const double* state, double time, const double* mocap);
+int mjpc_b200_robust_planner_optimize_policy(void* planner, int horizon);
+void mjpc_b200_robust_planner_action_from_policy(void* planner, double* action, double time, int use_previous);
+/* winner, robust scores [ncandidates], clean returns [num_trajectory], installed knots/times; returns #scores */
+int mjpc_b200_robust_planner_get_result(void* planner, int* winner, double* scores, float* returns, double* knots,
+                                        double* knot_times);
 
 /* ---- iLQG planner (csrc/host/ilqg_planner.{h,cc}; mjpc/planners/ilqg/planner.h, planner.cc:156-740).
  * OptimizePolicy = NominalTrajectory (feedback-scaling line search) + Iteration (model derivatives, cost derivatives,

@@ -921,6 +921,25 @@ __device__ __noinline__ void k_smooth_forces(Ctx& c) {
   __syncwarp();
   float* smooth = DF(qfrc_smooth);
   for (int i = lane; i < nv; i += 32) smooth[i] = passive[i] - bias[i] + qact[i];
+  if (c.xfrc_on) {
+    // mj_xfrcAccumulate: force / torque at the centre of mass of every body in the subtree of the dof's body
+    // (DFS order: a contiguous body range), mapped through the com-based motion axis of the dof
+    const float *xf = DF(xfrc), *cdof = DF(cdof), *xipos = DF(xipos), *scom = DF(subtree_com);
+    const int *dbody = MI(dof_bodyid), *subend = MI(body_subtreeend), *rootid = MI(body_rootid);
+    for (int i = lane; i < nv; i += 32) {
+      const int b0 = dbody[i];
+      const float* cd = cdof + 6 * i;
+      float a = 0.f;
+      for (int b = b0; b < subend[b0]; b++) {
+        float off[3], t[3];
+        for (int q = 0; q < 3; q++) off[q] = xipos[3 * b + q] - scom[3 * rootid[b] + q];
+        cross3(t, cd, off);
+        const float* f = xf + 6 * b;
+        for (int q = 0; q < 3; q++) a += (cd[3 + q] + t[q]) * f[q] + cd[q] * f[3 + q];
+      }
+      smooth[i] += a;
+    }
+  }
   __syncwarp();
   warp_chol_factor_solve<SP::kNV>(DF(qLD), DF(ldinv), DF(qacc_smooth), smooth, nv, lane);
 }

@@ -70,6 +70,8 @@ struct mjpc_b200 {
   std::vector<int> time_idx;
   int lastN = 0, lastH = 0;
   int64_t launches = 0;
+  float xfrc_std = 0.f, xfrc_rate = 1.f;   // NoisyRollout settings for the following rollouts (0 = off)
+  unsigned noise_seed = 0;
   int last_static = 0;
   float last_ms = 0;
   // resident-input launch description
@@ -154,6 +156,7 @@ RolloutArgs base_args(mjpc_b200* h, double time, int N, int H) {
   A.states = h->d_states; A.actions = h->d_actions; A.times = h->d_times; A.residual = h->d_residual;
   A.costs = h->d_costs; A.trace = h->d_trace; A.returns = h->d_returns; A.failure = h->d_failure;
   A.stats = h->d_stats;
+  A.xfrc_std = h->xfrc_std; A.xfrc_rate = h->xfrc_rate; A.noise_seed = h->noise_seed;
   return A;
 }
 
@@ -478,6 +481,15 @@ int mjpc_b200_fetch_stats(mjpc_b200_t* h, int64_t* stats) {
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   CUDA_TRY(cudaMemcpy(stats, h->d_stats, (size_t)h->lastN * 12 * sizeof(long long), cudaMemcpyDeviceToHost));
   return 0;
+}
+
+// NoisyRollout (mjpc/trajectory.cc:100-210) for the following rollouts of this handle: Ornstein-Uhlenbeck
+// xfrc_applied noise with stationary std `xfrc_std` [N, N m] and correlation time `xfrc_rate` [s]; 0 switches it off.
+int mjpc_b200_set_xfrc_noise(mjpc_b200_t* h, double xfrc_std, double xfrc_rate, uint32_t seed) {
+  if (!h || xfrc_std < 0 || !(xfrc_rate > 0)) return fail(MJPC_B200_ERR_BAD_ARGUMENT, "set_xfrc_noise: bad argument");
+  h->xfrc_std = (float)xfrc_std; h->xfrc_rate = (float)xfrc_rate; h->noise_seed = seed;
+  h->resident_ok = false;
+  return MJPC_B200_OK;
 }
 
 int64_t mjpc_b200_launch_count(const mjpc_b200_t* h) { return h ? h->launches : 0; }

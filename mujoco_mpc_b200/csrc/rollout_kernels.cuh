@@ -29,6 +29,8 @@ struct RolloutArgs {
   FeedbackArgs fb;
   const float* step_sizes;  // [N] for the feedback policy
   int policy_kind;          // 0 spline, 1 feedback
+  float xfrc_std, xfrc_rate;   // NoisyRollout (trajectory.cc:100-210): OU force noise, std 0 = off
+  unsigned noise_seed;
   int P, interp, N, H;
   double time0;
   float* states; float* actions; double* times; float* residual; float* costs; float* trace;
@@ -83,7 +85,7 @@ __device__ __forceinline__ void init_ctx(Ctx& c, const DevModel* M, const DevLay
   c.dbase = data0 + warp * L->total;
   c.lane = lane;
   c.gkey = pack + M->nf + M->ni;   // the keyframe table follows the staged part of the pack in HBM
-  c.ncon = 0; c.npseudo = 0; c.nefc = 0; c.nitem = 0; c.niter = 0; c.nlim = 0; c.warn = 0; c.time = 0.f;
+  c.ncon = 0; c.npseudo = 0; c.xfrc_on = 0; c.nefc = 0; c.nitem = 0; c.niter = 0; c.nlim = 0; c.warn = 0; c.time = 0.f;
 #ifdef MJPC_PHASE_TIMING
   for (int k = 0; k < 8; k++) c.tph[k] = 0;
   c.tlast = clock64();
@@ -100,6 +102,22 @@ __device__ __forceinline__ void write_traces(Ctx& c, float* out) {
     const float* src = ty[k] == OBJ_SITE ? DF(site_xpos) : ty[k] == OBJ_GEOM ? DF(geom_xpos) : ty[k] == OBJ_XBODY ? DF(xpos) : DF(xipos);
     out[w] = src[3 * id[k] + q];
   }
+}
+
+// Injected noise of NoisyRollout: Philox4x32-10, key (seed, 1), counter (step, stream, element, 'XFRC'), Box-Muller on
+// the first two words - the definition of oracle/rollout.h (xfrc_normal), evaluated in fp32 here.
+__device__ __forceinline__ float xfrc_normal(unsigned seed, unsigned step, unsigned stream, unsigned element) {
+  unsigned c0 = step, c1 = stream, c2 = element, c3 = 0x58465243u, k0 = seed, k1 = 1u;
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const unsigned n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  const float u1 = ((float)c0 + 0.5f) * 2.3283064365386963e-10f, u2 = ((float)c1 + 0.5f) * 2.3283064365386963e-10f;
+  return sqrtf(-2.0f * logf(fmaxf(u1, 1e-12f))) * cospif(2.0f * u2);
 }
 
 template <class SP>
@@ -127,6 +145,11 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& A) {
     if (q < 3) DF(mocap_pos)[3 * k + q] = A.mocap[i]; else DF(mocap_quat)[4 * k + q - 3] = A.mocap[i];
   }
   for (int i = lane; i < nv * nv; i += 32) DF(qM)[i] = 0;
+  const bool noisy = A.xfrc_std > 0.f;
+  const float ou_rate = noisy ? expf(-CM(c).timestep / A.xfrc_rate) : 0.f;
+  const float ou_scale = noisy ? A.xfrc_std * sqrtf(1.f - ou_rate * ou_rate) : 0.f;
+  for (int i = lane; i < 6 * M.nbody; i += 32) DF(xfrc)[i] = 0;
+  c.xfrc_on = noisy ? 1 : 0;
   float step_size = 0.f;
   if (A.policy_kind == 0) {
     for (int i = lane; i < A.P * nu; i += 32) DF(knots)[i] = A.knots[(size_t)cand * A.P * nu + i];
@@ -159,6 +182,12 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& A) {
       o_actions[(size_t)t * nu + i] = DF(ctrl)[i];
     }
     if (!last && (k_bad(c, DF(qpos), nq) || k_bad(c, DF(qvel), nv))) { failed = true; break; }
+    if (noisy && !last) {   // Ornstein-Uhlenbeck perturbation in discrete time (trajectory.cc:147-155)
+      float* xf = DF(xfrc);
+      for (int i = lane; i < 6 * M.nbody; i += 32)
+        xf[i] = ou_rate * xf[i] + ou_scale * xfrc_normal(A.noise_seed, (unsigned)t, (unsigned)cand, (unsigned)i);
+      __syncwarp();
+    }
     k_forward<SP>(c);
     n_newton += c.niter; n_con += c.ncon - c.npseudo; n_efc += c.nefc;
     k_residual<SP>(c);

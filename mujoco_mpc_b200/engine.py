@@ -19,7 +19,7 @@ _ip = C.POINTER(C.c_int)
 _bp = C.POINTER(C.c_uint8)
 
 EXPORTS = ["mjpc_b200_version", "mjpc_b200_last_error", "mjpc_b200_create", "mjpc_b200_destroy",
-           "mjpc_b200_get_info", "mjpc_b200_set_task", "mjpc_b200_rollout_spline", "mjpc_b200_rollout_feedback",
+           "mjpc_b200_get_info", "mjpc_b200_set_task", "mjpc_b200_set_xfrc_noise", "mjpc_b200_rollout_spline", "mjpc_b200_rollout_feedback",
            "mjpc_b200_fetch_trajectory", "mjpc_b200_fetch_all", "mjpc_b200_model_derivatives",
            "mjpc_b200_cost_derivatives", "mjpc_b200_backward_pass", "mjpc_b200_step_debug",
            "mjpc_b200_fetch_stats", "mjpc_b200_launch_count", "mjpc_b200_last_kernel_ms", "mjpc_b200_last_kernel_static",
@@ -35,7 +35,10 @@ EXPORTS = ["mjpc_b200_version", "mjpc_b200_last_error", "mjpc_b200_create", "mjp
            "mjpc_b200_ilqg_planner_create", "mjpc_b200_ilqg_planner_destroy", "mjpc_b200_ilqg_planner_reset",
            "mjpc_b200_ilqg_planner_set_state", "mjpc_b200_ilqg_planner_nominal_trajectory",
            "mjpc_b200_ilqg_planner_optimize_policy", "mjpc_b200_ilqg_planner_action_from_policy",
-           "mjpc_b200_ilqg_planner_get_result"]
+           "mjpc_b200_ilqg_planner_get_result",
+           "mjpc_b200_robust_planner_create", "mjpc_b200_robust_planner_destroy", "mjpc_b200_robust_planner_reset",
+           "mjpc_b200_robust_planner_set_state", "mjpc_b200_robust_planner_optimize_policy",
+           "mjpc_b200_robust_planner_action_from_policy", "mjpc_b200_robust_planner_get_result"]
 
 
 class ModelBlob(C.Structure):
@@ -71,6 +74,7 @@ def load_library():
         lib.mjpc_b200_planner_destroy.argtypes = [C.c_void_p]
         lib.mjpc_b200_ce_planner_destroy.argtypes = [C.c_void_p]
         lib.mjpc_b200_ilqg_planner_destroy.argtypes = [C.c_void_p]
+        lib.mjpc_b200_robust_planner_destroy.argtypes = [C.c_void_p]
         for n in ("mjpc_b200_destroy", "mjpc_b200_fetch_stats", "mjpc_b200_launch_count", "mjpc_b200_last_kernel_ms", "mjpc_b200_stream",
                   "mjpc_b200_device_returns", "mjpc_b200_sync", "mjpc_b200_launch_resident"):
             getattr(lib, n).argtypes = [C.c_void_p]
@@ -258,6 +262,10 @@ class Engine:
     def launch_count(self):
         return int(self.lib.mjpc_b200_launch_count(self.h))
 
+    def set_xfrc_noise(self, std, rate=1.0, seed=0):
+        """NoisyRollout perturbation for the following rollouts (mjpc_b200_set_xfrc_noise); std 0 = off."""
+        self._check(self.lib.mjpc_b200_set_xfrc_noise(self.h, C.c_double(std), C.c_double(rate), C.c_uint32(seed)))
+
     @property
     def last_kernel_ms(self):
         return float(self.lib.mjpc_b200_last_kernel_ms(self.h))
@@ -432,4 +440,63 @@ class CppILQGPlanner:
     def action_from_policy(self, time):
         a = np.zeros(self.nu)
         self.lib.mjpc_b200_ilqg_planner_action_from_policy(self.h, _pd(a), C.c_double(time))
+        return a
+
+
+class CppRobustPlanner:
+    """The C++ Robust planner (csrc/host/robust_planner.cc) through its C wrappers."""
+
+    def __init__(self, model, num_trajectory, horizon, ncandidates=-1, nrepetitions=5, xfrc_std=0.1, xfrc_rate=0.1,
+                 seed=0x5EED, device=0):
+        self.lib = load_library()
+        m = self.m = model
+        self._blob = to_blob(model)
+        self._buf = C.create_string_buffer(self._blob, len(self._blob))
+        mb = ModelBlob(C.cast(self._buf, C.c_void_p), len(self._blob))
+        num = m.numeric
+        self.P = int(num.get("sampling_spline_points", [3])[0])
+        self.horizon, self.N, self.nu = int(horizon), int(num_trajectory), m.nu
+        self.nc = int(ncandidates if ncandidates != -1 else num_trajectory // nrepetitions)
+        cr = _d(np.asarray(m.actuator_ctrlrange, float).reshape(-1))
+        h = C.c_void_p()
+        rc = self.lib.mjpc_b200_robust_planner_create(
+            C.byref(mb), self.N, self.P, int(num.get("sampling_representation", [2])[0]),
+            C.c_double(float(num.get("sampling_exploration", [0.1])[0])), C.c_double(float(m.opt_timestep)), _pd(cr),
+            C.c_uint32(seed), int(ncandidates), int(nrepetitions), C.c_double(xfrc_std), C.c_double(xfrc_rate),
+            self.horizon, int(device), C.byref(h))
+        if rc != 0:
+            raise EngineError(f"mjpc_b200_robust_planner_create failed ({rc}): {self.lib.mjpc_b200_last_error().decode()}")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mjpc_b200_robust_planner_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def reset(self, initial_repeated_action=None):
+        a = _d(initial_repeated_action)
+        self.lib.mjpc_b200_robust_planner_reset(self.h, self.horizon, _pd(a))
+
+    def set_state(self, state, time, mocap):
+        s, mc = _d(state), _d(mocap)
+        self.lib.mjpc_b200_robust_planner_set_state(self.h, _pd(s), C.c_double(time), _pd(mc))
+
+    def optimize_policy(self):
+        rc = self.lib.mjpc_b200_robust_planner_optimize_policy(self.h, self.horizon)
+        if rc != 0:
+            raise EngineError(f"robust_planner_optimize_policy failed: {self.lib.mjpc_b200_last_error().decode()}")
+        return self.result()
+
+    def result(self):
+        winner = C.c_int()
+        scores = np.zeros(max(self.nc, 1)); ret = np.zeros(self.N, np.float32)
+        knots = np.zeros((self.P, self.nu)); kt = np.zeros(self.P)
+        n = self.lib.mjpc_b200_robust_planner_get_result(self.h, C.byref(winner), _pd(scores), _pf(ret), _pd(knots), _pd(kt))
+        return dict(winner=winner.value, scores=scores[:n], returns=ret, knots=knots, knot_times=kt)
+
+    def action_from_policy(self, time, use_previous=False):
+        a = np.zeros(self.nu)
+        self.lib.mjpc_b200_robust_planner_action_from_policy(self.h, _pd(a), C.c_double(time), int(use_previous))
         return a

@@ -224,3 +224,70 @@ class CrossEntropyPlanner:
 
     def action_from_policy(self, time):
         return clamp(sample_spline(self.times, self.values, self.interp, time), self.ctrlrange)
+
+
+class RobustPlanner:
+    """Robust planner (mjpc/planners/robust/robust_planner.cc:91-157) over a SamplingPlanner delegate.
+
+    OptimizePolicy: the delegate's candidate rollouts -> the best `ncandidates`; each is rolled out `nrepetitions`
+    times with NoisyRollout force perturbations (ONE launch of ncandidates*nrepetitions candidates, noise stream =
+    launch index, seed + iteration); a candidate's score is the mean of its non-failed noisy returns (its clean
+    score only if all failed); the best score is installed.  Defaults: robust_repetitions 5, robust_candidates =
+    sampling_trajectories / repetitions, robust_xfrc 0.1, robust_xfrc_rate 0.1 (robust_planner.cc:44-57)."""
+
+    def __init__(self, model, backend, num_trajectory=None, horizon=None, ncandidates=None, nrepetitions=None,
+                 xfrc_std=None, xfrc_rate=None, seed=0x5EED):
+        num = model.numeric
+        self.delegate = SamplingPlanner(model, backend, num_trajectory, horizon, seed)
+        self.backend = backend
+        self.nrepetitions = int(nrepetitions or num.get("robust_repetitions", [5])[0])
+        nc = ncandidates if ncandidates is not None else int(num.get("robust_candidates", [-1])[0])
+        self.ncandidates = int(nc if nc != -1 else self.delegate.num_trajectory // self.nrepetitions)
+        self.xfrc_std = float(xfrc_std if xfrc_std is not None else num.get("robust_xfrc", [0.1])[0])
+        self.xfrc_rate = float(xfrc_rate if xfrc_rate is not None else num.get("robust_xfrc_rate", [0.1])[0])
+        self.seed = seed
+
+    def reset(self, initial_repeated_action=None):
+        self.delegate.reset(initial_repeated_action)
+
+    def set_state(self, state, time, mocap):
+        self.delegate.set_state(state, time, mocap)
+
+    def optimize_policy(self):
+        d = self.delegate
+        knots = d.make_candidates()                                  # OptimizePolicyCandidates (planner.cc:155-194)
+        ret, fail, order = self.backend.rollout_spline(d.state, d.time, d.mocap, knots, d.times, d.interp, d.horizon)
+        order = np.asarray(order if order is not None else np.argsort(ret, kind="stable"))
+        nc = min(self.ncandidates, d.num_trajectory)
+        self.scores = None
+        if nc <= 1:
+            best = 0
+        else:
+            top = order[:nc]
+            rep = self.nrepetitions
+            knots2 = np.repeat(knots[top], rep, axis=0)
+            self.backend.set_xfrc_noise(self.xfrc_std, self.xfrc_rate, (self.seed + d.iteration) & 0xFFFFFFFF)
+            ret2, fail2, _ = self.backend.rollout_spline(d.state, d.time, d.mocap, knots2, d.times, d.interp, d.horizon)
+            self.backend.set_xfrc_noise(0.0, self.xfrc_rate, 0)
+            best, best_score, scores = -1, 0.0, []
+            for c in range(nc):
+                mean, valid = float(ret[top[c]]), 0
+                for j in range(rep):
+                    if fail2[rep * c + j]:
+                        continue
+                    mean = (valid * mean + float(ret2[rep * c + j])) / (valid + 1)
+                    valid += 1
+                scores.append(mean)
+                if best == -1 or mean < best_score:
+                    best, best_score = c, mean
+            self.scores = np.array(scores)
+        d.winner = int(order[best])                                   # CopyCandidateToPolicy(best)
+        d.improvement = max(float(ret[0]) - float(ret[d.winner]), 0.0)
+        d.values = knots[d.winner].astype(float)
+        d.returns = ret
+        d.iteration += 1
+        self.winner = d.winner
+        return ret, fail
+
+    def action_from_policy(self, time):
+        return self.delegate.action_from_policy(time)

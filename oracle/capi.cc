@@ -21,6 +21,7 @@ struct Engine {
   CostSpec<T> cost;
   std::vector<std::unique_ptr<Data<T>>> data;  // one per worker (Planner::ResizeMjData, planners/planner.cc:23-33)
   std::unique_ptr<ThreadPool> pool;
+  XfrcNoise noise;                              // applied by rollout_spline / rollout_feedback when std > 0
   Engine(const void* blob, size_t n) : model(blob, n), cost(model) {}
   void resize(int nthreads) {
     if (!pool || pool->NumThreads() != nthreads) pool.reset(new ThreadPool(nthreads));
@@ -82,7 +83,8 @@ int rollout_spline(Engine<T>& e, const double* state, double time, const double*
       tr.Allocate(H);
       Data<T>& d = *e.data[ThreadPool::WorkerId()];
       auto pol = spline_policy<T>(m, kn.data() + (size_t)i * P * nu, kt.data(), P, interp);
-      rollout<T>(tr, pol, m, e.cost, d, st.data(), (T)time, mc.data(), ud.data(), H);
+      XfrcNoise nz = e.noise; nz.stream = (uint32_t)i;
+      rollout<T>(tr, pol, m, e.cost, d, st.data(), (T)time, mc.data(), ud.data(), H, nz);
     });
   }
   e.pool->WaitCount(before + N);
@@ -213,6 +215,13 @@ int oracle_rollout_spline(void* hv, const double* state, double time, const doub
                           failure, states, actions, times, residual, costs, trace);
   return rollout_spline(*h->e32, state, time, mocap, userdata, knots, knot_times, interp, P, N, H, nthreads, returns,
                         failure, states, actions, times, residual, costs, trace);
+}
+
+// NoisyRollout settings for the following rollout_spline calls (std 0 switches the noise off)
+void oracle_set_xfrc_noise(void* hv, double std, double rate, uint32_t seed) {
+  auto* h = (Handle*)hv;
+  if (h->e64) { h->e64->noise.std = std; h->e64->noise.rate = rate; h->e64->noise.seed = seed; }
+  if (h->e32) { h->e32->noise.std = std; h->e32->noise.rate = rate; h->e32->noise.seed = seed; }
 }
 
 int oracle_rollout_feedback(void* hv, const double* state, double time, const double* mocap, const double* userdata,

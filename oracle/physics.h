@@ -172,6 +172,8 @@ struct Data {
   std::vector<T> cvel, cdof_dot, subtree_linvel, qfrc_passive, qfrc_bias;
   // forces / accelerations
   std::vector<T> actuator_force, qfrc_actuator, qfrc_smooth, qacc_smooth, qacc, qfrc_constraint;
+  std::vector<T> xfrc_applied;   // [nbody][force 3, torque 3] world frame, applied at the body's centre of mass
+  bool xfrc_active = false;      // NoisyRollout (trajectory.cc:147-155); false -> the array is ignored
   // constraints
   std::vector<Contact<T>> contact;
   int ncon = 0, nefc = 0, solver_niter = 0;
@@ -203,7 +205,7 @@ struct Data {
     cvel.assign(6 * m.nbody, 0); cdof_dot.assign(6 * m.nv, 0); subtree_linvel.assign(3 * m.nbody, 0);
     qfrc_passive.assign(m.nv, 0); qfrc_bias.assign(m.nv, 0); actuator_force.assign(m.nu, 0);
     qfrc_actuator.assign(m.nv, 0); qfrc_smooth.assign(m.nv, 0); qacc_smooth.assign(m.nv, 0);
-    qacc.assign(m.nv, 0); qfrc_constraint.assign(m.nv, 0);
+    qacc.assign(m.nv, 0); qfrc_constraint.assign(m.nv, 0); xfrc_applied.assign(6 * m.nbody, 0);
     residual.assign(mm::max(m.num_residual, 1), 0);
   }
 };
@@ -1179,6 +1181,15 @@ void forward(const Model<T>& m, Data<T>& d, ResidualCallback<T> cb) {
   }
   actuation(m, d);
   for (int i = 0; i < nv; i++) d.qfrc_smooth[i] = d.qfrc_passive[i] - d.qfrc_bias[i] + d.qfrc_actuator[i];
+  if (d.xfrc_active) {   // mj_xfrcAccumulate: Cartesian force / torque at each body's centre of mass -> joint space
+    std::vector<T> jp(3 * nv), jr(3 * nv);
+    for (int b = 1; b < m.nbody; b++) {
+      const T* f = &d.xfrc_applied[6 * b];
+      jac_point(m, d, b, &d.xipos[3 * b], jp.data(), jr.data());
+      for (int i = 0; i < nv; i++)
+        for (int c = 0; c < 3; c++) d.qfrc_smooth[i] += jp[c * nv + i] * f[c] + jr[c * nv + i] * f[3 + c];
+    }
+  }
   chol_solve(d.qacc_smooth.data(), d.qLD.data(), d.qfrc_smooth.data(), nv);
   solve_constraints(m, d);
   if (cb) cb(m, d, d.residual.data());  // mjcb_sensor at mjSTAGE_ACC (mjpc/app.cc:110-126)

@@ -76,6 +76,10 @@ class Oracle:
                        trace=np.zeros((N, H, 3 * m.task_num_trace)))
         return out
 
+    def set_xfrc_noise(self, std, rate=1.0, seed=0):
+        """NoisyRollout perturbation (trajectory.cc:147-155) for the following rollout_spline calls; std 0 = off."""
+        lib().oracle_set_xfrc_noise(self.h, C.c_double(std), C.c_double(rate), C.c_uint32(seed))
+
     def rollout_spline(self, state, time, mocap, knots, knot_times, interp, H, nthreads=1, full=True, userdata=None):
         knots = _d(knots)
         N, P, nu = knots.shape

@@ -6,6 +6,8 @@
 //   UpdateReturn                   <- mjpc/trajectory.cc:312-326
 //   GetTraces                      <- mjpc/utilities.cc:268-285
 #pragma once
+#include <cmath>
+#include <cstdint>
 #include <functional>
 #include <vector>
 
@@ -66,9 +68,30 @@ void update_return(Trajectory<T>& tr, const CostSpec<T>& cost) {
 // policy(action, state, time, step_index)
 template <class T> using Policy = std::function<void(T*, const T*, T, int)>;
 
+// Injected noise source of NoisyRollout (the reference's absl::BitGen is unseedable): Philox4x32-10, key (seed, 1),
+// counter (step, stream, element, 'XFRC'), Box-Muller on the first two words.  Same definition on the device.
+inline void philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]}, k0 = key[0], k1 = key[1];
+  for (int r = 0; r < 10; r++) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+    const uint32_t n[4] = {(uint32_t)(p1 >> 32) ^ c[1] ^ k0, (uint32_t)p1, (uint32_t)(p0 >> 32) ^ c[3] ^ k1, (uint32_t)p0};
+    for (int i = 0; i < 4; i++) c[i] = n[i];
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  for (int i = 0; i < 4; i++) out[i] = c[i];
+}
+inline double xfrc_normal(uint32_t seed, uint32_t step, uint32_t stream, uint32_t element) {
+  const uint32_t ctr[4] = {step, stream, element, 0x58465243u}, key[2] = {seed, 1u};
+  uint32_t r[4];
+  philox4x32(ctr, key, r);
+  const double u1 = ((double)r[0] + 0.5) / 4294967296.0, u2 = ((double)r[1] + 0.5) / 4294967296.0;
+  return std::sqrt(-2.0 * std::log(u1)) * std::cos(2.0 * M_PI * u2);
+}
+struct XfrcNoise { double std = 0, rate = 1; uint32_t seed = 0, stream = 0; };
+
 template <class T>
 void rollout(Trajectory<T>& tr, const Policy<T>& policy, const Model<T>& m, const CostSpec<T>& cost, Data<T>& d,
-             const T* state, T time, const T* mocap, const T* userdata, int steps) {
+             const T* state, T time, const T* mocap, const T* userdata, int steps, const XfrcNoise& noise = XfrcNoise()) {
   ResidualCallback<T> cb = residual_by_id<T>(m.residual_id);
   int nq = m.nq, nv = m.nv, nu = m.nu, ds = tr.dim_state, nr = tr.dim_residual;
   tr.failure = false;
@@ -86,9 +109,18 @@ void rollout(Trajectory<T>& tr, const Policy<T>& policy, const Model<T>& m, cons
   d.time = time;
   // the reference leaves mjData::qacc_warmstart as the worker thread last left it; we define it as zero
   std::fill(d.qacc_warmstart.begin(), d.qacc_warmstart.end(), (T)0);
+  // ... and mjData::xfrc_applied likewise: defined as zero at the start of a noisy rollout
+  std::fill(d.xfrc_applied.begin(), d.xfrc_applied.end(), (T)0);
+  d.xfrc_active = noise.std > 0;
   for (int t = 0; t < steps - 1; t++) {
     policy(&tr.actions[t * nu], &tr.states[t * ds], d.time, t);
     for (int i = 0; i < nu; i++) d.ctrl[i] = tr.actions[t * nu + i];
+    if (noise.std > 0) {   // Ornstein-Uhlenbeck perturbation in discrete time (trajectory.cc:147-155)
+      const T rate = mm::exp(-m.timestep / (T)noise.rate);
+      const T scale = (T)noise.std * mm::sqrt(1 - rate * rate);
+      for (int i = 0; i < 6 * m.nbody; i++)
+        d.xfrc_applied[i] = rate * d.xfrc_applied[i] + scale * (T)xfrc_normal(noise.seed, (uint32_t)t, noise.stream, (uint32_t)i);
+    }
     step(m, d, cb);
     for (int i = 0; i < nr; i++) tr.residual[t * nr + i] = d.residual[i];
     get_traces(&tr.trace[t * tr.dim_trace], m, d);

@@ -69,6 +69,9 @@ class OracleBackend:
         self.last = r
         return r["returns"], r["failure"], np.argsort(r["returns"], kind="stable")
 
+    def set_xfrc_noise(self, std, rate=1.0, seed=0):
+        self.o.set_xfrc_noise(std, rate, seed)
+
     def rollout_feedback(self, state, time, mocap, u_nom, x_nom, t_nom, gains, du, step_sizes, mode):
         r = self.o.rollout_feedback(state, time, mocap, u_nom, x_nom, t_nom, gains, du, step_sizes, mode, nthreads=self.threads)
         self.last = r

@@ -420,3 +420,79 @@ def test_humanoid_track_rollout_returns(engines, oracles):
     tr = e.fetch_all()
     np.testing.assert_allclose(tr["residual"][:N, 0], r64["residual"][:, 0], atol=3e-4)
     np.testing.assert_allclose(tr["actions"][:N, :H], r64["actions"], atol=2e-5)
+
+
+def test_noisy_rollout_matches_oracle(engines, oracles, quadruped):
+    """NoisyRollout (trajectory.cc:100-210): in-kernel Ornstein-Uhlenbeck xfrc noise from the injected Philox stream
+    (fp32 Box-Muller on the device, fp64 in the oracle) -> same perturbed trajectories as the oracle."""
+    m = quadruped
+    e, o = engines("quadruped"), oracles("quadruped", 64)
+    N, H = 16, 32
+    state, mocap, knots, kt = quadruped_inputs(m, N=N, H=H)
+    clean, _, _ = e.rollout_spline(state, 0.0, mocap, knots, kt, 2, H)
+    e.set_xfrc_noise(2.0, 0.1, 77); o.set_xfrc_noise(2.0, 0.1, 77)
+    try:
+        ret, fail, _ = e.rollout_spline(state, 0.0, mocap, knots, kt, 2, H)
+        tr = e.fetch_all()
+        ref = o.rollout_spline(state, 0.0, mocap, knots, kt, 2, H, nthreads=8, full=True)
+    finally:
+        e.set_xfrc_noise(0.0); o.set_xfrc_noise(0.0)
+    assert not fail.any()
+    assert np.abs(ret - clean).max() > 1e-4                       # the perturbation is visible in the returns
+    np.testing.assert_allclose(tr["states"][:N, :6], ref["states"][:, :6], atol=2e-4)   # first steps: free flight + noise
+    rel = np.abs(ret - ref["returns"]) / np.abs(ref["returns"])
+    print("noisy rollouts: max rel return error vs fp64 oracle %.2e" % rel.max())
+    assert rel.max() < 2e-3 and np.median(rel) < 2e-4
+    again, _, _ = e.rollout_spline(state, 0.0, mocap, knots, kt, 2, H)
+    np.testing.assert_allclose(again, clean, rtol=1e-6)           # switched off again
+
+
+def test_noisy_rollout_equals_equivalent_controls_on_device(engines):
+    """Same construction as tests/test_planners_cpu.py: on the particle a Cartesian force is exactly a control."""
+    from mujoco_mpc_b200.planner import philox4x32
+    m = get_model("particle")
+    e = engines("particle", N=8, H=16)
+    H, std, rate_s, seed = 12, 0.05, 0.2, 1234
+    body = int(m.jnt_bodyid[0])
+    state = np.array([0.05, -0.02, 0.1, 0.0])
+    kt = np.arange(H) * m.opt_timestep - 1e-6
+    e.set_xfrc_noise(std, rate_s, seed)
+    try:
+        e.rollout_spline(state, 0.0, mocap_of(m), np.zeros((2, H, m.nu)), kt, 0, H)
+        noisy = e.fetch_trajectory(1)
+    finally:
+        e.set_xfrc_noise(0.0)
+    rate = np.exp(-m.opt_timestep / rate_s); scale = std * np.sqrt(1 - rate * rate)
+    x = np.zeros(6 * m.nbody); forces = np.zeros((H, 2))
+    for t in range(H - 1):
+        ctr = np.array([[t, 1, el, 0x58465243] for el in range(6 * m.nbody)], np.uint32)
+        r = philox4x32(ctr, (seed, 1))
+        u1 = (r[:, 0].astype(np.float64) + 0.5) / 4294967296.0; u2 = (r[:, 1].astype(np.float64) + 0.5) / 4294967296.0
+        x = rate * x + scale * np.sqrt(-2 * np.log(u1)) * np.cos(2 * np.pi * u2)
+        forces[t] = x[6 * body: 6 * body + 2]
+    e.rollout_spline(state, 0.0, mocap_of(m), forces[None], kt, 0, H)
+    clean = e.fetch_trajectory(0)
+    np.testing.assert_allclose(noisy["states"], clean["states"], atol=2e-6)
+
+
+def test_cpp_robust_planner_matches_python_mirror(engines, quadruped):
+    """Robust planner (robust_planner.cc:91-157): C++ host class vs the Python mirror on the same engine ABI."""
+    from mujoco_mpc_b200.engine import CppRobustPlanner
+    from mujoco_mpc_b200.planner import RobustPlanner
+    m = quadruped
+    state = np.concatenate([m.key_qpos[0], np.zeros(m.nv)])
+    mocap = mocap_of(m)
+    N, H = 40, 32
+    cpp = CppRobustPlanner(m, N, H, ncandidates=5, nrepetitions=4, xfrc_std=1.0, xfrc_rate=0.1)
+    py = RobustPlanner(m, engines("quadruped"), num_trajectory=N, horizon=H, ncandidates=5, nrepetitions=4,
+                       xfrc_std=1.0, xfrc_rate=0.1)
+    cpp.reset(np.zeros(m.nu)); py.reset(np.zeros(m.nu))
+    cpp.set_state(state, 0.0, mocap); py.set_state(state, 0.0, mocap)
+    for it in range(3):
+        rc = cpp.optimize_policy()
+        ret, fail = py.optimize_policy()
+        np.testing.assert_allclose(rc["returns"], ret, rtol=1e-5)
+        np.testing.assert_allclose(rc["scores"], py.scores, rtol=1e-5)
+        assert rc["winner"] == py.winner, it
+        np.testing.assert_allclose(rc["knots"], py.delegate.values, atol=1e-6)
+    cpp.close()

@@ -82,3 +82,64 @@ def test_cross_entropy_particle_reaches_goal():
     cr = np.asarray(m.actuator_ctrlrange).reshape(-1, 2)
     assert (np.abs(tr["actions"]) <= cr[:, 1] + 1e-9).all()
     assert (pl.variance >= 0).all() and pl.variance.shape == (pl.P, m.nu)
+
+
+def test_noisy_rollout_force_perturbation_equals_equivalent_controls():
+    """NoisyRollout (mjpc/trajectory.cc:100-210): Ornstein-Uhlenbeck xfrc_applied noise from the injected Philox
+    stream.  On the particle (two slide joints on one body, unit-gear motors on the same joints) a Cartesian force on
+    the body is exactly a control: the noisy rollout with zero controls must reproduce the clean rollout driven by the
+    recomputed noise sequence - this pins the noise definition, the OU recursion and the force -> joint-space map."""
+    from mujoco_mpc_b200.blob import to_blob
+    from mujoco_mpc_b200.planner import philox4x32
+    from oracle import pyoracle
+    m = get_model("particle")
+    o = pyoracle.Oracle(to_blob(m), m, 64)
+    H, std, rate_s, seed = 12, 0.05, 0.2, 1234
+    body = m.body_names.index("pointmass") if "pointmass" in m.body_names else int(m.jnt_bodyid[0])
+    assert int(m.jnt_bodyid[0]) == int(m.jnt_bodyid[1]) == body
+    state = np.array([0.05, -0.02, 0.1, 0.0])
+    kt = np.arange(H) * m.opt_timestep - 1e-9     # knots are reached robustly despite the accumulated rollout clock
+    o.set_xfrc_noise(std, rate_s, seed)
+    noisy = o.rollout_spline(state, 0.0, mocap_of(m), np.zeros((2, H, m.nu)), kt, 0, H)
+    o.set_xfrc_noise(0.0)
+    # recompute the perturbation of candidate (stream) 1: counter (step, stream, element, 'XFRC'), key (seed, 1)
+    rate = np.exp(-m.opt_timestep / rate_s); scale = std * np.sqrt(1 - rate * rate)
+    x = np.zeros(6 * m.nbody); forces = np.zeros((H, 2))
+    for t in range(H - 1):
+        ctr = np.array([[t, 1, e, 0x58465243] for e in range(6 * m.nbody)], np.uint32)
+        r = philox4x32(ctr, (seed, 1))
+        u1 = (r[:, 0].astype(np.float64) + 0.5) / 4294967296.0; u2 = (r[:, 1].astype(np.float64) + 0.5) / 4294967296.0
+        x = rate * x + scale * np.sqrt(-2 * np.log(u1)) * np.cos(2 * np.pi * u2)
+        forces[t] = x[6 * body: 6 * body + 2]
+    assert np.abs(forces).max() < 1.0                      # inside the control range, so the clamp is inactive
+    clean = o.rollout_spline(state, 0.0, mocap_of(m), forces[None], kt, 0, H)
+    np.testing.assert_allclose(noisy["states"][1], clean["states"][0], atol=1e-12)
+    assert np.abs(noisy["states"][1] - noisy["states"][0]).max() > 1e-5      # streams differ per candidate
+
+
+def test_robust_planner_cpu():
+    """Robust planner (robust_planner.cc:91-157) on the oracle backend: the installed candidate minimises the mean of
+    its noisy-rollout returns among the top candidates; with zero force noise it reduces to the sampling planner."""
+    from mujoco_mpc_b200.planner import RobustPlanner, SamplingPlanner
+    m = get_model("particle")
+    st, mc = np.array([0.1, -0.1, 0.0, 0.0]), mocap_of(m)
+    rp = RobustPlanner(m, OracleBackend(m, threads=2), num_trajectory=20, horizon=11, ncandidates=4, nrepetitions=3,
+                       xfrc_std=0.2, xfrc_rate=0.1)
+    assert rp.ncandidates == 4 and rp.nrepetitions == 3
+    rp.reset(); rp.set_state(st, 0.0, mc)
+    for _ in range(5):
+        ret, fail = rp.optimize_policy()
+        assert rp.scores.shape == (4,) and rp.winner in list(np.argsort(ret, kind="stable")[:4])
+        assert rp.scores.min() == rp.scores[list(np.argsort(ret, kind="stable")[:4]).index(rp.winner)]
+    # defaults from the reference: 5 repetitions, candidates = trajectories / repetitions, std 0.1, rate 0.1
+    d = RobustPlanner(m, OracleBackend(m, threads=1), num_trajectory=20, horizon=11)
+    assert (d.nrepetitions, d.ncandidates, d.xfrc_std, d.xfrc_rate) == (5, 4, 0.1, 0.1)
+    # no force noise: every repetition reproduces the clean return -> same winner as Predictive Sampling
+    r0 = RobustPlanner(m, OracleBackend(m, threads=2), num_trajectory=20, horizon=11, ncandidates=4, nrepetitions=2, xfrc_std=0.0)
+    sp = SamplingPlanner(m, OracleBackend(m, threads=2), num_trajectory=20, horizon=11)
+    for p in (r0, sp):
+        p.reset(); p.set_state(st, 0.0, mc)
+    for _ in range(3):
+        r0.optimize_policy(); sp.optimize_policy()
+        assert r0.winner == sp.winner
+        np.testing.assert_allclose(r0.delegate.values, sp.values, atol=1e-12)
