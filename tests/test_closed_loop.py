@@ -59,3 +59,50 @@ def test_quadruped_closed_loop_cost_matches_cpu_planner(oracle_lib):
         cz.append(plant.cost_value(r["residual"][: m.task_num_residual])); warm = r["qacc"]
         q, v = r["next_qpos"], r["next_qvel"]
     assert c_gpu.mean() < np.mean(cz)
+
+
+def test_humanoid_track_closed_loop(oracle_lib):
+    """BASELINE config 3 loop at a small size: Tracking::TransitionLocked (host) moves the mocap markers and owns
+    (mode, reference_time); every plan iteration snapshots that task state into the engine (mjpc_b200_set_task), the
+    device plans, the oracle plant steps.  The tracked markers must stay close to the clip, and better than with
+    zero control."""
+    from mujoco_mpc_b200.blob import to_blob
+    from mujoco_mpc_b200.engine import Engine
+    from mujoco_mpc_b200.planner import SamplingPlanner
+    from mujoco_mpc_b200.transition import HumanoidTrackTransition
+    m = get_model("humanoid_track")
+    plant = oracle_lib.Oracle(to_blob(m), m, 64)
+    N, H, steps = 64, 41, 80
+
+    def run(plan):
+        e = Engine(m, N, H) if plan else None
+        pl = SamplingPlanner(m, e, num_trajectory=N, horizon=H) if plan else None
+        if plan:
+            pl.reset(np.zeros(m.nu))
+        tr = HumanoidTrackTransition(m)
+        q, v, t, warm, errs, costs = m.qpos0.copy(), np.zeros(m.nv), 0.0, None, [], []
+        for k in range(steps):
+            q, v, mocap = tr.transition(t, q, v)
+            plant.set_task(task_state=tr.task_state())
+            u = np.zeros(m.nu)
+            if plan:
+                e.set_task(task_state=tr.task_state())
+                pl.set_state(np.concatenate([q, v]), t, mocap)
+                pl.optimize_policy()
+                u = pl.action_from_policy(t)
+            r = plant.forward_debug(q, v, u, mocap, time=t, warmstart=warm)
+            res = r["residual"][:141]
+            errs.append(np.abs(res[45:93]).max())          # mean-centred marker position errors [m]
+            costs.append(plant.cost_value(res)); warm = r["qacc"]
+            q, v = r["next_qpos"], r["next_qvel"]
+            t += m.opt_timestep
+        if plan:
+            e.close()
+        return np.array(errs), np.array(costs), q
+    e_mpc, c_mpc, q_mpc = run(True)
+    e_zero, c_zero, q_zero = run(False)
+    print("humanoid track closed loop (0.4 s): mean cost MPC %.3f vs zero control %.3f; max marker error %.3f / %.3f m" % (
+        c_mpc.mean(), c_zero.mean(), e_mpc.max(), e_zero.max()))
+    assert np.isfinite(c_mpc).all() and q_mpc[2] > 0.8          # upright
+    assert c_mpc.mean() < c_zero.mean()
+    plant.set_task(task_state=np.asarray(m.task_state, float))

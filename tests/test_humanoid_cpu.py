@@ -117,3 +117,26 @@ def test_humanoid_track_residual_against_independent_numpy():
         expect = np.concatenate([v[6:], u, mp.mean(0) - sp.mean(0), ((mp - mp.mean(0)) - (sp - sp.mean(0))).reshape(-1),
                                  ((m.key_mpos[k1] - m.key_mpos[k0]).reshape(16, 3) * 30.0 - sv).reshape(-1)])
         assert np.abs(r - expect).max() < 1e-9, (mode, t, np.abs(r - expect).argmax())
+
+
+def test_humanoid_track_transition():
+    """Tracking::TransitionLocked (tracking.cc:218-267): clip switch restarts the clock and resets the plant to the
+    clip's first keyframe; markers follow the linearly interpolated keyframes and clamp at the clip end."""
+    from mujoco_mpc_b200 import task as T
+    from mujoco_mpc_b200.transition import HumanoidTrackTransition
+    m = get_model("humanoid_track")
+    tr = HumanoidTrackTransition(m)
+    q, v, mocap = tr.transition(0.0, m.qpos0.copy(), np.ones(m.nv))
+    assert tr.current_mode == 0 and tr.reference_time == 0.0
+    np.testing.assert_allclose(q, m.key_qpos[0]); assert np.allclose(v, 0)
+    np.testing.assert_allclose(mocap.reshape(16, 7)[:, :3].reshape(-1), m.key_mpos[0])
+    q2, v2, mocap = tr.transition(0.05, q + 0.01, v)                 # 1.5 frames into the clip: state untouched
+    np.testing.assert_allclose(q2, q + 0.01)
+    np.testing.assert_allclose(mocap.reshape(16, 7)[:, :3].reshape(-1), 0.5 * (m.key_mpos[1] + m.key_mpos[2]), atol=1e-12)
+    tr.mode = 3                                                        # GUI switches the clip at t = 1.0
+    q3, v3, mocap = tr.transition(1.0, q2, v2)
+    start = sum(T.TRACK_MOTION_LENGTHS[:3])
+    assert tr.current_mode == 3 and tr.reference_time == 1.0
+    np.testing.assert_allclose(q3, m.key_qpos[start]); np.testing.assert_allclose(tr.task_state(), [3.0, 1.0])
+    _, _, mocap = tr.transition(1000.0, q3, v3)                        # far past the end: last frame of clip 3
+    np.testing.assert_allclose(mocap.reshape(16, 7)[:, :3].reshape(-1), m.key_mpos[start + T.TRACK_MOTION_LENGTHS[3] - 1])
