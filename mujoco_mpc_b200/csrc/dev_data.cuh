@@ -299,6 +299,7 @@ __device__ __forceinline__ void warp_chol_factor_solve_reg(float* A, float* x, c
 #pragma unroll
   for (int k = 0; k < N; k++) row[k] = A[li * N + k];
   float y = b[li];
+  __syncwarp();   // lanes >= N read row N-1 / b[N-1], which lane N-1 (and x == b callers) overwrite below
 #pragma unroll
   for (int j = 0; j < N; j++) {
     float p = __shfl_sync(kFull, row[j], j);
