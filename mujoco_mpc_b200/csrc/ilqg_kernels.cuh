@@ -200,6 +200,7 @@ __device__ __forceinline__ void fd_column_body(const FdArgs& A) {
       return;
     }
     h = fwd ? A.eps : -A.eps;
+    __syncwarp();   // every lane has read u0 before lane 0 overwrites it
     if (lane == 0) DF(ctrl)[i] = u0 + h;
   } else if (col < nu + nv) {
     if (lane == 0) DF(qvel)[col - nu] += A.eps;
