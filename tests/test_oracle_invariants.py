@@ -115,3 +115,45 @@ def test_resting_sphere_penetration_closed_form(oracle_lib):
         x = g * (1 - imp(x)) / (kk * imp(x) ** 2)
     assert abs(depth - x) < 1e-9 * max(1.0, 1 / x) and 1e-5 < x < 1e-3, (depth, x)
     assert abs(r["efc_force"][0] - 1.5 * g) < 1e-8          # the contact carries exactly the weight
+
+
+@pytest.mark.parametrize("cone", ["elliptic", "pyramidal"])
+def test_sliding_box_coulomb_friction(oracle_lib, cone):
+    """A box sliding on the plane decelerates at mu*g while it slides and then sticks (velocity exactly killed by the
+    friction rows, no creep): exercises the cone zones of the Newton solver - sliding = on the cone boundary ("middle
+    zone" for the elliptic cone, one active edge pair for the pyramid), stuck = inside the cone (quadratic zone)."""
+    mu = 0.4
+    xml = f"""
+<mujoco model="box">
+  <option timestep="0.002" cone="{cone}" impratio="1"/>
+  <custom><numeric name="agent_planner" data="0"/><numeric name="agent_horizon" data="0.1"/></custom>
+  <worldbody>
+    <geom name="floor" type="plane" size="5 5 .1" friction="{mu} 0.005 0.0001"/>
+    <body name="box" pos="0 0 0.05"><freejoint/><geom name="box" type="box" size="0.1 0.1 0.05" mass="2" friction="{mu} 0.005 0.0001"/></body>
+  </worldbody>
+  <sensor><user name="Dummy" dim="13" user="0 1 0 1"/></sensor>
+</mujoco>"""
+    m = compile_xml(xml)
+    m.task_residual_id = T.RESIDUAL_PARTICLE_COPY
+    m.task_ids, m.task_state, m.ray_geoms = np.zeros(1, np.int32), np.zeros(1), np.zeros(0, np.int32)
+    o = oracle_lib.Oracle(to_blob(m), m, 64)
+    q, v, warm = m.qpos0.copy(), np.zeros(m.nv), None
+    for k in range(500):                                    # settle on the floor
+        r = o.forward_debug(q, v, np.zeros(0), np.zeros(0), warmstart=warm)
+        q, v, warm = r["next_qpos"], r["next_qvel"], r["qacc"]
+    assert r["ncon"] == 4 and np.abs(v).max() < 1e-6
+    v[0] = 1.0                                              # shove it along x
+    vx = []
+    for k in range(200):
+        r = o.forward_debug(q, v, np.zeros(0), np.zeros(0), warmstart=warm)
+        q, v, warm = r["next_qpos"], r["next_qvel"], r["qacc"]
+        vx.append(v[0])
+    vx = np.array(vx)
+    t = 0.002 * (np.arange(200) + 1)
+    sliding = vx > 0.2
+    decel = -np.polyfit(t[sliding], vx[sliding], 1)[0]
+    assert abs(decel - mu * 9.81) < 0.03 * mu * 9.81, (cone, decel, mu * 9.81)
+    assert abs(vx[-1]) < 1e-4 and abs(v[1]) < 1e-6 and abs(q[2] - 0.05) < 1e-3     # stopped, stuck, still on the floor
+    # the last few cm/s decay smoothly (soft constraint): compare the time to shed 95 % of the speed
+    t95 = 0.95 / (mu * 9.81)
+    assert abs(t[np.argmax(vx < 0.05)] - t95) < 0.05 * t95, (cone, t[np.argmax(vx < 0.05)], t95)
