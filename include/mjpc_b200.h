@@ -219,6 +219,26 @@ void mjpc_b200_robust_planner_action_from_policy(void* planner, double* action, 
 int mjpc_b200_robust_planner_get_result(void* planner, int* winner, double* scores, float* returns, double* knots,
                                         double* knot_times);
 
+/* ---- Task::Transition of the config tasks on the host (csrc/host/task_transition.{h,cc}): the state machines that
+ * produce the task-state block the kernels consume (QuadrupedFlat::TransitionLocked quadruped.cc:228-395,
+ * Tracking::TransitionLocked tracking.cc:218-267).  Host only - no device, no handle.
+ * quadruped ids[14] = {p_gait, p_gait_switch, p_cadence, p_amplitude, p_duty, p_walk_speed, p_walk_turn,
+ *                      w_upright, w_height, w_position, w_gait, w_balance, w_effort, w_posture};
+ * view[24] = {time, torso_subtreelinvel[3], torso_xmat[9], torso_xpos[3], torso_xquat[4], head_site_xpos[3],
+ *             ground height under the torso subtree com (read when the Flip mode starts)}. */
+void* mjpc_b200_quadruped_transition_create(const int* ids, const double* parameters, int nparam, const double* weight,
+                                            int nweight, const double* task_state, int nstate, const double* goal_pos);
+void mjpc_b200_quadruped_transition_destroy(void* transition);
+/* caller / GUI edits of Task::parameters and Task::weight between transitions (either may be NULL) */
+void mjpc_b200_quadruped_transition_set(void* transition, const double* parameters, const double* weight);
+void mjpc_b200_quadruped_transition_step(void* transition, int* mode_inout, const double* view, double* parameters,
+                                         double* weight, double* task_state, double* goal_pos);
+void* mjpc_b200_track_transition_create(int nq, int nv, int nmocap, int nkey, const double* key_qpos,
+                                        const double* key_qvel, const double* key_mpos);
+void mjpc_b200_track_transition_destroy(void* transition);
+void mjpc_b200_track_transition_step(void* transition, int mode, double time, double* qpos, double* qvel,
+                                     double* mocap_pos, double* task_state);
+
 /* ---- iLQG planner (csrc/host/ilqg_planner.{h,cc}; mjpc/planners/ilqg/planner.h, planner.cc:156-740).
  * OptimizePolicy = NominalTrajectory (feedback-scaling line search) + Iteration (model derivatives, cost derivatives,
  * backward pass with the regularisation retry loop, K action rollouts, winner, regularisation update); each sweep is

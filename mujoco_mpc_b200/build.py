@@ -30,7 +30,8 @@ def _compile(verbose):
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO, os.path.join(CSRC, "engine.cu"), os.path.join(CSRC, "host", "sampling_planner.cc"),
                                                                            os.path.join(CSRC, "host", "cross_entropy_planner.cc"),
                                                                            os.path.join(CSRC, "host", "ilqg_planner.cc"),
-                                                                           os.path.join(CSRC, "host", "robust_planner.cc")]
+                                                                           os.path.join(CSRC, "host", "robust_planner.cc"),
+                                                                           os.path.join(CSRC, "host", "task_transition.cc")]
     subprocess.check_call(cmd, cwd=CSRC)
 
 

@@ -38,7 +38,10 @@ EXPORTS = ["mjpc_b200_version", "mjpc_b200_last_error", "mjpc_b200_create", "mjp
            "mjpc_b200_ilqg_planner_get_result",
            "mjpc_b200_robust_planner_create", "mjpc_b200_robust_planner_destroy", "mjpc_b200_robust_planner_reset",
            "mjpc_b200_robust_planner_set_state", "mjpc_b200_robust_planner_optimize_policy",
-           "mjpc_b200_robust_planner_action_from_policy", "mjpc_b200_robust_planner_get_result"]
+           "mjpc_b200_robust_planner_action_from_policy", "mjpc_b200_robust_planner_get_result",
+           "mjpc_b200_quadruped_transition_create", "mjpc_b200_quadruped_transition_destroy",
+           "mjpc_b200_quadruped_transition_step", "mjpc_b200_quadruped_transition_set", "mjpc_b200_track_transition_create",
+           "mjpc_b200_track_transition_destroy", "mjpc_b200_track_transition_step"]
 
 
 class ModelBlob(C.Structure):
@@ -75,6 +78,10 @@ def load_library():
         lib.mjpc_b200_ce_planner_destroy.argtypes = [C.c_void_p]
         lib.mjpc_b200_ilqg_planner_destroy.argtypes = [C.c_void_p]
         lib.mjpc_b200_robust_planner_destroy.argtypes = [C.c_void_p]
+        for n in ("mjpc_b200_quadruped_transition_create", "mjpc_b200_track_transition_create"):
+            getattr(lib, n).restype = C.c_void_p
+        lib.mjpc_b200_quadruped_transition_destroy.argtypes = [C.c_void_p]
+        lib.mjpc_b200_track_transition_destroy.argtypes = [C.c_void_p]
         for n in ("mjpc_b200_destroy", "mjpc_b200_fetch_stats", "mjpc_b200_launch_count", "mjpc_b200_last_kernel_ms", "mjpc_b200_stream",
                   "mjpc_b200_device_returns", "mjpc_b200_sync", "mjpc_b200_launch_resident"):
             getattr(lib, n).argtypes = [C.c_void_p]

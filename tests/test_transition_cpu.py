@@ -100,3 +100,71 @@ def test_flip_saves_and_restores_weights():
     assert tr.current_mode == K_MODE_QUADRUPED
     np.testing.assert_allclose(tr.weight, w0)
     np.testing.assert_allclose(tr.goal_pos[:2], [1.3, 2.0]) and tr.parameters[tr.p["select_Gait switch"]] == 1
+
+
+def test_cpp_transitions_match_python(tmp_path):
+    """csrc/host/task_transition.cc (C++) vs transition.py on the same random plant-view sequence, including mode
+    switches (Walk, Flip, forbidden ones), auto gait switching and clip changes of the tracking task."""
+    import ctypes as C
+
+    from mujoco_mpc_b200 import task as T
+    from mujoco_mpc_b200.engine import load_library
+    from mujoco_mpc_b200.transition import HumanoidTrackTransition, QuadrupedFlatTransition
+    lib = load_library()
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    m = get_model("quadruped")
+    py = QuadrupedFlatTransition(m)
+    ids = np.array([py.p[n] for n in ("select_Gait", "select_Gait switch", "Cadence", "Amplitude", "Duty ratio", "Walk speed",
+                                      "Walk turn")] +
+                   [py.w[n] for n in ("Upright", "Height", "Position", "Gait", "Balance", "Effort", "Posture")], np.int32)
+    P0, W0, S0, G0 = py.parameters.copy(), py.weight.copy(), py.state.copy(), py.goal_pos.copy()
+    h = C.c_void_p(lib.mjpc_b200_quadruped_transition_create(ids.ctypes.data_as(C.POINTER(C.c_int)), dp(P0), len(P0), dp(W0),
+                                                             len(W0), dp(S0), len(S0), dp(G0)))
+    assert h.value
+    rng = np.random.default_rng(0)
+    t, mode = 0.0, 0
+    P, W, S, G = np.zeros_like(P0), np.zeros_like(W0), np.zeros(T.QS_SIZE), np.zeros(3)
+    requests = {100: 2, 400: 0, 700: 1, 705: 4, 900: 0, 905: 4, 1300: 3}   # Walk, Quadruped, Biped, Flip (forbidden), Quadruped, Flip, Scramble
+    seen = set()
+    for k in range(1500):
+        t += 0.01
+        if k in requests:
+            mode = requests[k]
+        if k == 100:                                              # a GUI edit of two parameters, mirrored on both sides
+            py.parameters[py.p["Walk speed"]] = 0.4; py.parameters[py.p["Walk turn"]] = 0.5
+            lib.mjpc_b200_quadruped_transition_set(h, dp(py.parameters), None)
+        view = _view(t, vel=(1.5 * abs(np.sin(0.004 * k)), 0.1 * rng.standard_normal(), 0), yaw=0.3 * np.sin(0.01 * k),
+                     pos=(0.01 * k, 0.2 * np.sin(0.01 * k), 0.26))
+        flat = np.concatenate([[view["time"]], view["torso_subtreelinvel"], view["torso_xmat"], view["torso_xpos"],
+                               view["torso_xquat"], view["head_site_xpos"], [0.0]])
+        py.mode = mode
+        py.transition(view)
+        cm = C.c_int(mode)
+        lib.mjpc_b200_quadruped_transition_step(h, C.byref(cm), dp(flat), dp(P), dp(W), dp(S), dp(G))
+        np.testing.assert_allclose(P, py.parameters, atol=1e-12, err_msg="parameters at step %d" % k)
+        np.testing.assert_allclose(W, py.weight, atol=1e-12, err_msg="weights at step %d" % k)
+        np.testing.assert_allclose(S, py.task_state(), atol=1e-9, err_msg="task state at step %d" % k)
+        np.testing.assert_allclose(G, py.goal_pos, atol=1e-9, err_msg="goal at step %d" % k)
+        assert cm.value == py.mode
+        mode = py.mode                                            # Transition may rewrite Task::mode
+        seen.add((py.current_mode, int(py.current_gait)))
+    assert {mm for mm, _ in seen} == {0, 1, 2, 3, 4} and len({g for _, g in seen}) >= 3     # all modes, several gaits
+    lib.mjpc_b200_quadruped_transition_destroy(h)
+    # ---- tracking
+    mt = get_model("humanoid_track")
+    tp = HumanoidTrackTransition(mt)
+    kq, kv, km = (np.ascontiguousarray(x, np.float64) for x in (mt.key_qpos, mt.key_qvel, mt.key_mpos))
+    th = C.c_void_p(lib.mjpc_b200_track_transition_create(mt.nq, mt.nv, mt.nmocap, mt.nkey, dp(kq), dp(kv), dp(km)))
+    assert th.value
+    q, v = mt.qpos0.copy(), np.ones(mt.nv)
+    qc, vc = q.copy(), v.copy()
+    mp, ts = np.zeros(3 * mt.nmocap), np.zeros(2)
+    for k, (mode, time) in enumerate([(0, 0.0), (0, 0.033), (0, 0.5), (3, 0.7), (3, 0.71), (3, 9.0), (9, 9.5), (9, 30.0)]):
+        tp.mode = mode
+        q, v, mocap = tp.transition(time, q, v)
+        lib.mjpc_b200_track_transition_step(th, mode, C.c_double(time), dp(qc), dp(vc), dp(mp), dp(ts))
+        np.testing.assert_allclose(qc, q, atol=1e-12); np.testing.assert_allclose(vc, v, atol=1e-12)
+        np.testing.assert_allclose(mp, mocap.reshape(-1, 7)[:, :3].reshape(-1), atol=1e-12)
+        np.testing.assert_allclose(ts, tp.task_state(), atol=1e-12)
+        q = q + 0.01; v = v * 0.9; qc = qc + 0.01; vc = vc * 0.9
+    lib.mjpc_b200_track_transition_destroy(th)
