@@ -19,6 +19,8 @@
 #include <utility>
 #include <vector>
 
+#include <mutex>
+
 #include "rollout_kernels.cuh"
 
 namespace mjpc_dev {
@@ -681,8 +683,12 @@ extern "C" __global__ void __launch_bounds__(256) backward_pass_kernel(const __g
 }
 
 // ------------------------------------------------------------------------------------------ host launchers
+// (the dynamic shared-memory opt-in is a per-kernel, process-wide attribute: only ever raised; handles may be created
+// from several threads, hence the lock)
 inline cudaError_t raise_smem_limit(const void* fn, size_t bytes) {
   static std::vector<std::pair<const void*, size_t>> seen;
+  static std::mutex mtx;
+  const std::lock_guard<std::mutex> lock(mtx);
   for (auto& e : seen)
     if (e.first == fn) {
       if (e.second >= bytes) return cudaSuccess;
