@@ -332,7 +332,7 @@ def main():
     config3 = humanoid_probe() if world == 1 else None
     cpu = None
     parity = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:     # the CPU arm is reported at N = 1 only
         threads = os.cpu_count() or 1
         cpu_s, (c_state, c_mocap, c_knots, c_kt, cpu_ret) = cpu_baseline_run(3, 1, threads)
         cpu = {"value": N_CAND * HORIZON / cpu_s, "unit": UNIT, "cores": threads, "kind": "port",
