@@ -217,6 +217,14 @@ int oracle_rollout_spline(void* hv, const double* state, double time, const doub
                         failure, states, actions, times, residual, costs, trace);
 }
 
+// interpolation helpers of the iLQG policy (mjpc/utilities.cc:303-422), exported for the golden tests
+void oracle_find_interval(const double* seq, double value, int length, int* bounds) {
+  find_interval<double>(bounds, seq, value, length);
+}
+void oracle_interpolate(double* out, double x, const double* xs, const double* ys, int dim, int length, int rep) {
+  interpolate<double>(out, x, xs, ys, dim, length, rep);
+}
+
 // NoisyRollout settings for the following rollout_spline calls (std 0 switches the noise off)
 void oracle_set_xfrc_noise(void* hv, double std, double rate, uint32_t seed) {
   auto* h = (Handle*)hv;

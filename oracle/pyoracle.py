@@ -195,3 +195,18 @@ def count_flops(blob: bytes, state, time, mocap, knots, knot_times, interp, H):
     f = lib().oracle_count_flops(blob, C.c_size_t(len(blob)), _p(st), C.c_double(time), _p(mc), _p(knots), _p(kt),
                                  int(interp), P, N, int(H), _p(ret))
     return float(f), ret
+
+
+def find_interval(seq, value):
+    seq = _d(seq)
+    b = (C.c_int * 2)()
+    lib().oracle_find_interval(_p(seq), C.c_double(value), len(seq), b)
+    return int(b[0]), int(b[1])
+
+
+def interpolate(x, xs, ys, rep):
+    xs, ys = _d(xs), _d(np.atleast_2d(np.asarray(ys, float).T).T if np.ndim(ys) == 1 else ys)
+    dim = ys.shape[1]
+    out = np.zeros(dim)
+    lib().oracle_interpolate(_p(out), C.c_double(x), _p(xs), _p(ys), dim, len(xs), int(rep))
+    return out

@@ -160,3 +160,24 @@ def test_fp32_oracle_tracks_fp64(oracle_lib, quadruped):
     r64 = o64.rollout_spline(state, 0.0, mocap, knots, kt, 2, 16, full=False)
     r32 = o32.rollout_spline(state, 0.0, mocap, knots, kt, 2, 16, full=False)
     np.testing.assert_allclose(r32["returns"], r64["returns"], rtol=2e-4)
+
+
+def test_interpolation_helpers_golden(oracle_lib):
+    """mjpc/test/agent/agent_utilities_test.cc:237-283 (FindInterval, LinearInterpolation) + the zero-order and cubic
+    variants used by iLQGPolicy::Action (utilities.cc:303-422): endpoints clamp, interior is the usual formula."""
+    seq = [-1.0, 0.0, 1.0, 2.0]
+    assert oracle_lib.find_interval(seq, 0.5) == (1, 2)
+    assert oracle_lib.find_interval(seq, -2.0) == (0, 0)
+    assert oracle_lib.find_interval(seq, 2.1) == (3, 3)
+    x, y = [1.0, 2.0], np.array([[1.0], [2.0]])
+    assert abs(oracle_lib.interpolate(1.5, x, y, 1)[0] - 1.5) < 1e-12
+    assert abs(oracle_lib.interpolate(0.5, x, y, 1)[0] - 1.0) < 1e-12      # lower extrapolation clamps
+    assert abs(oracle_lib.interpolate(2.5, x, y, 1)[0] - 2.0) < 1e-12      # upper extrapolation clamps
+    assert abs(oracle_lib.interpolate(1.5, x, y, 0)[0] - 1.0) < 1e-12      # zero-order hold
+    # cubic Hermite with finite-difference slopes reproduces a straight line exactly, and the nodes
+    xs = np.array([0.0, 0.3, 0.7, 1.0, 1.6]); ys = (2.0 * xs - 1.0)[:, None]
+    for q in (0.1, 0.5, 0.9, 1.3):
+        assert abs(oracle_lib.interpolate(q, xs, ys, 2)[0] - (2 * q - 1)) < 1e-12
+    ys2 = np.sin(xs)[:, None]
+    for k, q in enumerate(xs[:-1]):
+        assert abs(oracle_lib.interpolate(q, xs, ys2, 2)[0] - ys2[k, 0]) < 1e-12
