@@ -250,7 +250,13 @@ void mjpc_b200_ilqg_planner_reset(void* planner, int horizon, const double* init
 void mjpc_b200_ilqg_planner_set_state(void* planner, const double* state, double time, const double* mocap);
 int mjpc_b200_ilqg_planner_nominal_trajectory(void* planner, int horizon);
 int mjpc_b200_ilqg_planner_optimize_policy(void* planner, int horizon);
-void mjpc_b200_ilqg_planner_action_from_policy(void* planner, double* action, double time);
+/* iLQGPolicy::Action (ilqg/policy.cc:82-161): state may be NULL (open loop), otherwise the time-varying feedback
+ * feedback_scaling * K (state (-) x_nominal) is added before clamping */
+void mjpc_b200_ilqg_planner_action_from_policy(void* planner, double* action, const double* state, double time);
+/* the same, stateless and host only: u_nom [H][nu], x_nom [H][dim_state], t_nom [H], gains [H][nu][2 nv] */
+int mjpc_b200_host_ilqg_policy_action(const mjpc_model_blob* model, const float* u_nom, const float* x_nom,
+                                      const double* t_nom, const float* gains, int horizon, int representation,
+                                      double feedback_scaling, const double* state, double time, double* action);
 /* scalars[6] = {total_return, regularization, improvement, expected, surprise, winner}; nominal states [H][dim_state],
  * actions [H][nu], times [H] (any pointer may be NULL); returns H */
 int mjpc_b200_ilqg_planner_get_result(void* planner, double* scalars, float* states, float* actions, double* times);

@@ -3,8 +3,117 @@
 
 #include <algorithm>
 #include <cmath>
+#include <mutex>
+
+#include "../dev_model.h"   // Blob reader (plain C++)
 
 namespace mjpc_b200_host {
+
+// ------------------------------------------------------------------------------------------ iLQGPolicy::Action
+namespace {
+void FindInterval(int* b, const double* seq, double value, int length) {   // utilities.cc:303-330
+  int upper = 0;
+  while (upper < length && !(value < seq[upper])) upper++;
+  const int lower = upper - 1;
+  if (lower < 0) b[0] = b[1] = 0;
+  else if (lower > length - 1) b[0] = b[1] = length - 1;
+  else { b[0] = std::max(lower, 0); b[1] = std::min(upper, length - 1); }
+}
+double FdSlope(double x, const double* xs, const float* ys, int dim, int length, int i) {   // utilities.cc:333-365
+  int b[2];
+  FindInterval(b, xs, x, length);
+  auto Y = [&](int k) { return (double)ys[(size_t)dim * k + i]; };
+  if (b[0] == 0 && b[1] == 0) return length > 2 ? (Y(b[1] + 1) - Y(b[1])) / (xs[b[1] + 1] - xs[b[1]]) : 0.0;
+  if (b[0] == length - 1 && b[1] == length - 1) return length > 2 ? (Y(b[0]) - Y(b[0] - 1)) / (xs[b[0]] - xs[b[0] - 1]) : 0.0;
+  if (b[0] == 0) return (Y(b[1]) - Y(b[0])) / (xs[b[1]] - xs[b[0]]);
+  return 0.5 * (Y(b[1]) - Y(b[0])) / (xs[b[1]] - xs[b[0]]) + 0.5 * (Y(b[0]) - Y(b[0] - 1)) / (xs[b[0]] - xs[b[0] - 1]);
+}
+void Interpolate(double* out, double x, const double* xs, const float* ys, int dim, int length, int rep) {
+  int b[2];
+  FindInterval(b, xs, x, length);
+  if (rep == 0 || b[0] == b[1]) { for (int i = 0; i < dim; i++) out[i] = ys[(size_t)dim * b[0] + i]; return; }
+  const double t = (x - xs[b[0]]) / (xs[b[1]] - xs[b[0]]);
+  if (rep == 1) {
+    for (int i = 0; i < dim; i++) out[i] = ys[(size_t)dim * b[0] + i] * (1 - t) + ys[(size_t)dim * b[1] + i] * t;
+    return;
+  }
+  const double dt = xs[b[1]] - xs[b[0]];
+  const double c0 = 2 * t * t * t - 3 * t * t + 1, c1 = (t * t * t - 2 * t * t + t) * dt, c2 = -2 * t * t * t + 3 * t * t,
+               c3 = (t * t * t - t * t) * dt;
+  for (int i = 0; i < dim; i++)
+    out[i] = c0 * ys[(size_t)b[0] * dim + i] + c1 * FdSlope(xs[b[0]], xs, ys, dim, length, i) +
+             c2 * ys[(size_t)b[1] * dim + i] + c3 * FdSlope(xs[b[1]], xs, ys, dim, length, i);
+}
+void NormalizeQuat(double* q) {
+  const double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  if (n < 1e-15) { q[0] = 1; q[1] = q[2] = q[3] = 0; return; }
+  for (int k = 0; k < 4; k++) q[k] /= n;
+}
+void SubQuat(double* res, const double* qa, const double* qb) {   // qb * quat(res) = qa  (mju_subQuat)
+  const double n[4] = {qb[0], -qb[1], -qb[2], -qb[3]};
+  const double d[4] = {n[0] * qa[0] - n[1] * qa[1] - n[2] * qa[2] - n[3] * qa[3],
+                       n[0] * qa[1] + n[1] * qa[0] + n[2] * qa[3] - n[3] * qa[2],
+                       n[0] * qa[2] - n[1] * qa[3] + n[2] * qa[0] + n[3] * qa[1],
+                       n[0] * qa[3] + n[1] * qa[2] - n[2] * qa[1] + n[3] * qa[0]};
+  double axis[3] = {d[1], d[2], d[3]};
+  const double s = std::sqrt(axis[0] * axis[0] + axis[1] * axis[1] + axis[2] * axis[2]);
+  if (s < 1e-15) { axis[0] = 1; axis[1] = axis[2] = 0; } else { for (double& a : axis) a /= s; }
+  double speed = 2 * std::atan2(s, d[0]);
+  if (speed > M_PI) speed -= 2 * M_PI;
+  for (int c = 0; c < 3; c++) res[c] = axis[c] * speed;
+}
+}  // namespace
+
+int iLQGPolicyModel::Load(const mjpc_model_blob* blob) {
+  try {
+    mjpc_dev::Blob b(blob->data, blob->nbytes);
+    nq = b.i("nq"); nv = b.i("nv"); nu = b.i("nu");
+    jnt_type = b.ints("jnt_type"); jnt_qposadr = b.ints("jnt_qposadr"); jnt_dofadr = b.ints("jnt_dofadr");
+    ctrlrange = b.reals("actuator_ctrlrange");
+  } catch (const std::exception&) {
+    return MJPC_B200_ERR_BAD_BLOB;
+  }
+  return 0;
+}
+
+void iLQGPolicyAction(const iLQGPolicyModel& m, const float* u_nom, const float* x_nom, const double* t_nom,
+                      const float* gains, int H, int representation, double feedback_scaling, const double* state,
+                      double time, double* action) {
+  const int ds = m.nq + m.nv, n = 2 * m.nv, nu = m.nu;
+  int b[2];
+  FindInterval(b, t_nom, time, H);
+  const int rep = (b[0] == b[1]) ? 0 : representation;
+  Interpolate(action, time, t_nom, u_nom, nu, H - 1, rep);
+  if (state) {
+    std::vector<double> xi(ds), K((size_t)nu * n), dx(n);
+    Interpolate(xi.data(), time, t_nom, x_nom, ds, H, rep);
+    if (rep != 0)
+      for (size_t j = 0; j < m.jnt_type.size(); j++) {
+        if (m.jnt_type[j] == 0) NormalizeQuat(&xi[m.jnt_qposadr[j] + 3]);
+        else if (m.jnt_type[j] == 1) NormalizeQuat(&xi[m.jnt_qposadr[j]]);
+      }
+    Interpolate(K.data(), time, t_nom, gains, nu * n, H - 1, rep);
+    // StateDiff(model, dx, x_interp, state, 1): tangent-space difference state (-) x_interp
+    for (size_t j = 0; j < m.jnt_type.size(); j++) {
+      const int qa = m.jnt_qposadr[j], da = m.jnt_dofadr[j];
+      if (m.jnt_type[j] == 0) {
+        for (int c = 0; c < 3; c++) dx[da + c] = state[qa + c] - xi[qa + c];
+        SubQuat(&dx[da + 3], state + qa + 3, &xi[qa + 3]);
+      } else if (m.jnt_type[j] == 1) {
+        SubQuat(&dx[da], state + qa, &xi[qa]);
+      } else {
+        dx[da] = state[qa] - xi[qa];
+      }
+    }
+    for (int i = 0; i < m.nv; i++) dx[m.nv + i] = state[m.nq + i] - xi[m.nq + i];
+    for (int i = 0; i < nu; i++) {
+      double a = 0;
+      for (int j = 0; j < n; j++) a += K[(size_t)i * n + j] * dx[j];
+      action[i] += feedback_scaling * a;
+    }
+  }
+  for (int i = 0; i < nu; i++) action[i] = std::max(m.ctrlrange[2 * i], std::min(m.ctrlrange[2 * i + 1], action[i]));
+}
 
 iLQGPlanner::~iLQGPlanner() {
   if (gpu_) mjpc_b200_destroy(gpu_);
@@ -17,6 +126,7 @@ int iLQGPlanner::Initialize(const mjpc_model_blob* model, int num_rollouts, int 
   mjpc_b200_get_info(gpu_, &info_);
   nu_ = info_.nu; ds_ = info_.dim_state; n_ = info_.dim_dstate; nr_ = info_.num_residual;
   representation_ = representation;
+  if (int prc = pm_.Load(model)) return prc;
   state_.assign(ds_, 0.0); mocap_.assign(7 * info_.nmocap, 0.0);
   Reset(max_horizon, nullptr);
   return 0;
@@ -71,7 +181,10 @@ int iLQGPlanner::Install(int candidate, double ret) {
   if (mjpc_b200_fetch_trajectory(gpu_, candidate, best_.states.data(), best_.actions.data(), best_.times.data(),
                                  best_.residual.data(), best_.costs.data(), best_.trace.data()))
     return -1;
-  states = best_.states; actions = best_.actions; times = best_.times; residual = best_.residual;
+  {
+    const std::unique_lock<std::shared_mutex> lock(mtx_);
+    states = best_.states; actions = best_.actions; times = best_.times; residual = best_.residual;
+  }
   total_return = ret;
   best_.total_return = ret; best_.failure = false;
   return 0;
@@ -133,7 +246,10 @@ int iLQGPlanner::Iteration(int horizon) {
     }
   }
   if (status == 0) return 0;
-  gains = Kbuf_; du = dubuf_;
+  {
+    const std::unique_lock<std::shared_mutex> lock(mtx_);
+    gains = Kbuf_; du = dubuf_;
+  }
   if (mjpc_b200_rollout_feedback(gpu_, st.data(), time_, mc.empty() ? nullptr : mc.data(), nullptr, actions.data(),
                                  states.data(), times.data(), gains.data(), du.data(), steps.data(), 3, K_, horizon,
                                  ret_.data(), fail_.data(), order_.data()))
@@ -156,18 +272,10 @@ int iLQGPlanner::OptimizePolicy(int horizon) {
   return Iteration(horizon);
 }
 
-// iLQGPolicy::Action with linear interpolation of the nominal (policy.cc:82-161): u = u_t + K_t (x (-) x_t), clamped.
-// The tangent-space difference of the free-joint quaternion needs the model's joint table, which stays behind the
-// ABI: this host copy serves the open-loop part (state == nullptr) that the physics thread needs between plans.
-void iLQGPlanner::ActionFromPolicy(double* action, const double*, double time) const {
-  const int H = H_;
-  int lo = 0;
-  while (lo + 1 < H && times[lo + 1] <= time) lo++;
-  const int hi = std::min(lo + 1, H - 1);
-  const double dt = times[hi] - times[lo];
-  const double w = dt > 0 ? std::min(std::max((time - times[lo]) / dt, 0.0), 1.0) : 0.0;
-  for (int i = 0; i < nu_; i++)
-    action[i] = (1 - w) * actions[(size_t)lo * nu_ + i] + w * actions[(size_t)hi * nu_ + i];
+void iLQGPlanner::ActionFromPolicy(double* action, const double* state, double time) const {
+  const std::shared_lock<std::shared_mutex> lock(mtx_);
+  iLQGPolicyAction(pm_, actions.data(), states.data(), times.data(), gains.data(), H_, representation_, feedback_scaling,
+                   state, time, action);
 }
 
 }  // namespace mjpc_b200_host
@@ -196,8 +304,20 @@ void mjpc_b200_ilqg_planner_set_state(void* p, const double* state, double time,
 }
 int mjpc_b200_ilqg_planner_nominal_trajectory(void* p, int horizon) { return ((iLQGPlanner*)p)->NominalTrajectory(horizon); }
 int mjpc_b200_ilqg_planner_optimize_policy(void* p, int horizon) { return ((iLQGPlanner*)p)->OptimizePolicy(horizon); }
-void mjpc_b200_ilqg_planner_action_from_policy(void* p, double* action, double time) {
-  ((iLQGPlanner*)p)->ActionFromPolicy(action, nullptr, time);
+void mjpc_b200_ilqg_planner_action_from_policy(void* p, double* action, const double* state, double time) {
+  ((iLQGPlanner*)p)->ActionFromPolicy(action, state, time);
+}
+// stateless form of iLQGPolicy::Action (host only, no device): u_nom [H][nu], x_nom [H][dim_state], t_nom [H],
+// gains [H][nu][2nv]; state may be NULL (open loop)
+int mjpc_b200_host_ilqg_policy_action(const mjpc_model_blob* model, const float* u_nom, const float* x_nom,
+                                      const double* t_nom, const float* gains, int horizon, int representation,
+                                      double feedback_scaling, const double* state, double time, double* action) {
+  if (!model || !u_nom || !x_nom || !t_nom || !gains || !action || horizon < 2) return MJPC_B200_ERR_BAD_ARGUMENT;
+  mjpc_b200_host::iLQGPolicyModel pm;
+  if (int rc = pm.Load(model)) return rc;
+  mjpc_b200_host::iLQGPolicyAction(pm, u_nom, x_nom, t_nom, gains, horizon, representation, feedback_scaling, state, time,
+                                   action);
+  return 0;
 }
 // scalars[6] = {total_return, regularization, improvement, expected, surprise, winner}; nominal states [H][dim_state],
 // actions [H][nu], times [H]; any pointer may be NULL

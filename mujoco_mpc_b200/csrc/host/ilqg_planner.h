@@ -24,6 +24,20 @@ struct iLQGSettings {                    // mjpc/planners/ilqg/settings.h:21-36
   int nominal_feedback_scaling = 1;
 };
 
+// iLQGPolicy::Action (mjpc/planners/ilqg/policy.cc:82-161) on the host: what the physics thread evaluates between plans.
+// Interpolates the nominal actions / states / gains at `time` (representation 0 zero-order, 1 linear, 2 cubic with
+// finite-difference slopes; mjpc/utilities.cc:303-422), adds feedback_scaling * K (x (-) x_nominal) with the
+// tangent-space state difference (StateDiff, utilities.cc:543-553) when a state is given, clamps to ctrlrange.
+struct iLQGPolicyModel {       // the few mjModel fields the policy needs, read from the blob
+  int nq = 0, nv = 0, nu = 0;
+  std::vector<int> jnt_type, jnt_qposadr, jnt_dofadr;
+  std::vector<double> ctrlrange;
+  int Load(const mjpc_model_blob* blob);
+};
+void iLQGPolicyAction(const iLQGPolicyModel& m, const float* u_nom, const float* x_nom, const double* t_nom,
+                      const float* gains, int horizon, int representation, double feedback_scaling, const double* state,
+                      double time, double* action);
+
 class iLQGPlanner {
  public:
   ~iLQGPlanner();
@@ -33,7 +47,7 @@ class iLQGPlanner {
   int OptimizePolicy(int horizon);       // planner.cc:156-165: NominalTrajectory + Iteration; 1 = policy updated
   int NominalTrajectory(int horizon);    // :167-223
   int Iteration(int horizon);            // :377-627
-  void ActionFromPolicy(double* action, const double* state, double time) const;   // ilqg/policy.cc:82-161 (mode 1: linear)
+  void ActionFromPolicy(double* action, const double* state, double time) const;   // ilqg/policy.cc:82-161
   const Trajectory* BestTrajectory() const { return &best_; }
 
   iLQGSettings settings;
@@ -53,6 +67,8 @@ class iLQGPlanner {
   void UpdateRegularization(double z, double s);                          // :345-356
   mjpc_b200_t* gpu_ = nullptr;
   mjpc_b200_info info_{};
+  iLQGPolicyModel pm_;
+  mutable std::shared_mutex mtx_;   // the policy is read by the physics thread while a plan installs a new one
   int K_ = 10, representation_ = 1, H_ = 0, nu_ = 0, ds_ = 0, n_ = 0, nr_ = 0;
   std::vector<double> state_, mocap_;
   double time_ = 0;

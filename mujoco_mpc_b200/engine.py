@@ -35,7 +35,7 @@ EXPORTS = ["mjpc_b200_version", "mjpc_b200_last_error", "mjpc_b200_create", "mjp
            "mjpc_b200_ilqg_planner_create", "mjpc_b200_ilqg_planner_destroy", "mjpc_b200_ilqg_planner_reset",
            "mjpc_b200_ilqg_planner_set_state", "mjpc_b200_ilqg_planner_nominal_trajectory",
            "mjpc_b200_ilqg_planner_optimize_policy", "mjpc_b200_ilqg_planner_action_from_policy",
-           "mjpc_b200_ilqg_planner_get_result",
+           "mjpc_b200_ilqg_planner_get_result", "mjpc_b200_host_ilqg_policy_action",
            "mjpc_b200_robust_planner_create", "mjpc_b200_robust_planner_destroy", "mjpc_b200_robust_planner_reset",
            "mjpc_b200_robust_planner_set_state", "mjpc_b200_robust_planner_optimize_policy",
            "mjpc_b200_robust_planner_action_from_policy", "mjpc_b200_robust_planner_get_result",
@@ -444,9 +444,10 @@ class CppILQGPlanner:
         return dict(total_return=sc[0], regularization=sc[1], improvement=sc[2], expected=sc[3], surprise=sc[4],
                     winner=int(sc[5]), states=st, actions=ac, times=tm)
 
-    def action_from_policy(self, time):
+    def action_from_policy(self, time, state=None):
         a = np.zeros(self.nu)
-        self.lib.mjpc_b200_ilqg_planner_action_from_policy(self.h, _pd(a), C.c_double(time))
+        s = _d(state)
+        self.lib.mjpc_b200_ilqg_planner_action_from_policy(self.h, _pd(a), _pd(s), C.c_double(time))
         return a
 
 

@@ -217,6 +217,21 @@ int oracle_rollout_spline(void* hv, const double* state, double time, const doub
                         failure, states, actions, times, residual, costs, trace);
 }
 
+// iLQGPolicy::Action of the oracle (mode 0/1/2 time-indexed, feedback scaled by `step`), exported for the host-policy test
+int oracle_ilqg_policy_action(void* hv, const double* u_nom, const double* x_nom, const double* t_nom, const double* gains,
+                              int H, int mode, double step, const double* state, double time, double* action) {
+  auto* h = (Handle*)hv;
+  const Model<double>& m = h->e64->model;
+  const int ds = m.nq + m.nv + m.na, nu = m.nu, n = 2 * m.nv + m.na;
+  ILQGPolicyData<double> pd;
+  pd.H = H;
+  pd.u.assign(u_nom, u_nom + (size_t)H * nu); pd.x.assign(x_nom, x_nom + (size_t)H * ds); pd.t.assign(t_nom, t_nom + H);
+  pd.K.assign(gains, gains + (size_t)H * nu * n); pd.du.assign((size_t)H * nu, 0.0);
+  auto pol = ilqg_policy<double>(m, pd, step, mode);
+  pol(action, state, time, 0);
+  return 0;
+}
+
 // interpolation helpers of the iLQG policy (mjpc/utilities.cc:303-422), exported for the golden tests
 void oracle_find_interval(const double* seq, double value, int length, int* bounds) {
   find_interval<double>(bounds, seq, value, length);

@@ -126,6 +126,15 @@ class Oracle:
         o["contact"] = o["contact"][: ncon.value]
         return o
 
+    def ilqg_policy_action(self, u_nom, x_nom, t_nom, gains, mode, step, state, time):
+        """iLQGPolicy::Action of the oracle (fp64 handle only)."""
+        assert self.precision == 64
+        u, x, t, K, s = _d(u_nom), _d(x_nom), _d(t_nom), _d(gains), _d(state)
+        out = np.zeros(self.m.nu)
+        lib().oracle_ilqg_policy_action(self.h, _p(u), _p(x), _p(t), _p(K), len(t), int(mode), C.c_double(step), _p(s),
+                                        C.c_double(time), _p(out))
+        return out
+
     def cost_value(self, residual, terms=False):
         r = _d(residual)
         t = np.zeros(max(self.m.task_num_term, 1))

@@ -143,3 +143,47 @@ def test_robust_planner_cpu():
         r0.optimize_policy(); sp.optimize_policy()
         assert r0.winner == sp.winner
         np.testing.assert_allclose(r0.delegate.values, sp.values, atol=1e-12)
+
+
+def test_host_ilqg_policy_action_matches_oracle():
+    """iLQGPolicy::Action on the host (csrc/host/ilqg_planner.cc, what the physics thread calls between plans) vs the
+    oracle's policy: zero / linear / cubic interpolation of nominal actions, states (free-joint quaternion
+    renormalised) and gains, tangent-space state difference, feedback scaling, clamp; before / inside / after the plan."""
+    import ctypes as C
+
+    from mujoco_mpc_b200.blob import to_blob
+    from mujoco_mpc_b200.engine import ModelBlob, load_library
+    from oracle import pyoracle
+    lib = load_library()
+    m = get_model("quadruped")
+    blob = to_blob(m)
+    buf = C.create_string_buffer(blob, len(blob))
+    mb = ModelBlob(C.cast(buf, C.c_void_p), len(blob))
+    o = pyoracle.Oracle(blob, m, 64)
+    rng = np.random.default_rng(4)
+    H, nu, ds, n = 12, m.nu, m.nq + m.nv, 2 * m.nv
+    t = 0.5 + np.cumsum(rng.uniform(0.005, 0.02, H))
+    u = rng.uniform(-0.6, 0.6, (H, nu)).astype(np.float32)
+    x = np.tile(np.concatenate([m.key_qpos[0], np.zeros(m.nv)]), (H, 1)) + 0.05 * rng.standard_normal((H, ds))
+    for k in range(H):
+        x[k, 3:7] /= np.linalg.norm(x[k, 3:7])
+    x = x.astype(np.float32)
+    K = (0.3 * rng.standard_normal((H, nu, n))).astype(np.float32)
+    fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    for mode in (0, 1, 2):
+        for time in (t[0] - 0.1, t[0], 0.5 * (t[3] + t[4]), t[7] + 1e-4, t[-2] + 0.001, t[-1] + 1.0):
+            for scale in (1.0, 0.37):
+                state = x[5].astype(np.float64) + 0.02 * rng.standard_normal(ds)
+                state[3:7] /= np.linalg.norm(state[3:7])
+                for st in (state, None):
+                    out = np.zeros(nu)
+                    rc = lib.mjpc_b200_host_ilqg_policy_action(C.byref(mb), fp(u), fp(x), dp(t), fp(K), H, mode, C.c_double(scale),
+                                                               dp(st) if st is not None else None, C.c_double(time), dp(out))
+                    assert rc == 0
+                    if st is not None:
+                        ref = o.ilqg_policy_action(u, x, t, K, mode, scale, st, time)
+                    else:   # open loop: the oracle's policy with the nominal state itself (zero feedback) at zero scale
+                        ref = o.ilqg_policy_action(u, x, t, K, mode, 0.0, state, time)
+                    np.testing.assert_allclose(out, ref, atol=1e-9, err_msg="mode %d time %.4f" % (mode, time))
+                    assert (np.abs(out) <= 1 + 1e-12).all()
