@@ -327,7 +327,12 @@ def main():
                 "note": "latency/occupancy-bound by construction: 256 warps, 64 dependent steps each (DESIGN.md)"}
     prof = os.path.join(ROOT, "profiles", "traffic_r01.json")
     if os.path.exists(prof):
-        roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+        pj = json.load(open(prof))
+        roofline["traffic"] = pj.get("dram_bytes_per_launch")
+        # what actually bounds the kernel (from the committed ncu capture of the same launch): issue-slot use and stalls
+        roofline["latency_bound_evidence"] = {k: pj[k] for k in ("smsp__issue_active_pct", "sm__warps_active_pct_of_peak",
+                                                                 "warp_instructions_per_env_step", "stall_mix_pct",
+                                                                 "counters_from") if k in pj}
     ilqg = ilqg_probe(m, eng, mocap) if world == 1 else None
     config3 = humanoid_probe() if world == 1 else None
     cpu = None
