@@ -141,6 +141,15 @@ int mjpc_b200_step_debug(mjpc_b200_t* h, const float* qpos, const float* qvel, c
                          const float* mocap, double time, const float* warmstart, float* qacc, float* residual,
                          float* next_qpos, float* next_qvel, float* qM, float* efc_force, int* counts);
 
+/* Batched variant for teacher-forced per-step parity at full planner sizes: B independent (qpos, qvel, ctrl, warm start,
+ * absolute time) tuples are each advanced by one mj_step (mjpc/trajectory.cc:158) through the same kernel instance the
+ * rollout uses.  The task state is rebased to time0 as for a rollout starting there.  warmstart may be NULL (zeros).
+ * Outputs (any may be NULL): qacc [B][nv], next_qpos [B][nq], next_qvel [B][nv], residual [B][nr], cost [B],
+ * counts [B][4] = {ncon, nefc, solver iterations, warning}. */
+int mjpc_b200_step_batch(mjpc_b200_t* h, int B, const float* qpos, const float* qvel, const float* ctrl,
+                         const float* warmstart, const float* mocap, double time0, const double* times, float* qacc,
+                         float* next_qpos, float* next_qvel, float* residual, float* cost, int* counts);
+
 /* Per-candidate execution statistics of the last rollout, stats [N][12] = {SM cycles, Newton iterations, contacts,
  * constraint rows (summed over steps), 8 per-phase cycle counters (zero unless built with -DMJPC_PHASE_TIMING)}. */
 int mjpc_b200_fetch_stats(mjpc_b200_t* h, int64_t* stats);

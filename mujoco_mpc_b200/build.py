@@ -7,8 +7,11 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.environ.get("MJPC_B200_SO") or os.path.join(CSRC, "libmjpc_b200.so")  # override: perf experiments only
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-use_fast_math",
-              "-Xcompiler", "-fPIC", "-shared"]
+# -use_fast_math (approximate division / sqrt / sincos, flush-to-zero): the parity ablation with and without it is
+# profiles/parity_ablation.py -> profiles/r02_fast_math_ablation.txt; MJPC_B200_NO_FAST_MATH=1 builds the IEEE variant
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17"] + \
+             ([] if os.environ.get("MJPC_B200_NO_FAST_MATH") == "1" else ["-use_fast_math"]) + \
+             os.environ.get("MJPC_B200_NVCC_EXTRA", "").split() + ["-Xcompiler", "-fPIC", "-shared"]
 
 
 def sources():

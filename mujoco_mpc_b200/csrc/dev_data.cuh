@@ -31,6 +31,7 @@ constexpr int kMaxSplinePoints = 64;  // knot_times has a fixed capacity so that
   X(efc_R, M.maxefc) X(efc_D, M.maxefc) X(efc_K, M.maxefc) X(efc_B, M.maxefc) X(efc_imp, M.maxefc)                \
   X(efc_aref, M.maxefc) X(efc_hw, M.maxefc) X(efc_force, M.maxefc) X(efc_jar, M.maxefc) X(efc_Jv, M.maxefc) X(efc_floss, M.maxefc)    \
   X(efc_type, M.maxefc) X(efc_id, M.maxefc) X(efc_state, M.maxefc) X(efc_item, M.maxefc) X(efc_hc, 36 * M.maxcon) X(con_mlo, M.maxcon) X(con_mhi, M.maxcon) \
+  X(efc_w, 6 * M.maxefc) X(wsub, 36 * M.nbody) X(con_side, M.maxcon) X(con_mbody, M.maxcon) X(efc_drow, M.maxefc) \
   X(residual, M.num_residual) X(xnom, M.nq + M.nv) X(dx, 2 * M.nv) X(xfrc, 6 * M.nbody) X(knot_times, kMaxSplinePoints) X(knots, P * M.nu)
 
 enum DataArrayId {
@@ -59,7 +60,8 @@ inline DevLayout make_layout(const DevModel& M, int P) {
 constexpr unsigned kFull = 0xffffffffu;
 constexpr float kMinVal = 1e-15f;
 constexpr float kMaxVal = 1e10f;
-constexpr float kTolFloor = 1e-6f;  // fp32 floor on opt.tolerance (same rule as the oracle's fp32 instantiation)
+constexpr float kTolFloor = 1e-6f;
+constexpr float kGradFloor = 16.f;   // the fp32 gradient cannot be driven below kGradFloor * eps * |its terms| (k_solve)  // fp32 floor on opt.tolerance (same rule as the oracle's fp32 instantiation)
 constexpr float kMinImp = 0.0001f, kMaxImp = 0.9999f, kMinMu = 1e-5f;
 enum { CNSTR_FRICTION_DOF = 0, CNSTR_LIMIT_JOINT, CNSTR_CONTACT_FRICTIONLESS, CNSTR_CONTACT_ELLIPTIC };
 enum { STATE_SATISFIED = 0, STATE_QUADRATIC, STATE_LINEARNEG, STATE_LINEARPOS, STATE_CONE };
@@ -78,6 +80,7 @@ struct Ctx {
   int dbase;  // float index of this warp's state block
   int lane;
   int ncon, nefc, nitem, niter, nlim;
+  int ndrow;   // constraint rows whose Hessian contribution is assembled row by row (efc_drow): contacts between two moving bodies, tendon limits
   const float* gkey;  // HBM: keyframe mocap positions [nkey][3*nmocap] (too large for the shared-memory pack)
   int xfrc_on;  // NoisyRollout: DF(xfrc) holds Cartesian force/torque per body, added to the smooth forces
   int npseudo;  // tendon-limit pseudo-contacts at the tail of the contact list (included in ncon)

@@ -773,6 +773,66 @@ __device__ __noinline__ void k_make_constraint(Ctx& c) {
     float* D = DF(efc_D);
     for (int i = lane; i < ne; i += 32) D[i] = 1 / R[i];
   }
+  // --- wrench-space form of the rows of ONE-SIDED contacts (one geom on a body without dofs): J[row][i] = w_row . cdof_i
+  //     for every dof i in the moving body's chain, w_row = side * (off x axis ; axis) for a translational direction and
+  //     side * (axis ; 0) for a rotational one, off = contact point - com-frame origin.  The Newton Hessian of these
+  //     rows is then assembled as a composite "contact inertia" over the kinematic tree (k_hessian) instead of one rank-1
+  //     update per row.  Rows of contacts between two moving bodies and of tendon limits keep the row-by-row path
+  //     (efc_drow).
+  {
+    int *cside = DI(con_side), *cmb = DI(con_mbody), *drow = DI(efc_drow);
+    const int* chnum = MI(chain_num);
+    const int* rootid = MI(body_rootid);
+    const float *cpos = DF(con_pos), *cframe = DF(con_frame), *scom = DF(subtree_com);
+    float* W6 = DF(efc_w);
+    for (int ci = lane; ci < c.ncon; ci += 32) {
+      int side = 0, mb = 0;
+      if (g1a[ci] >= 0) {
+        const int b1 = gbody[g1a[ci]], b2 = gbody[g2a[ci]];
+        if (chnum[b1] == 0 && chnum[b2] > 0) { side = 1; mb = b2; }
+        else if (chnum[b2] == 0 && chnum[b1] > 0) { side = -1; mb = b1; }
+      }
+      cside[ci] = side; cmb[ci] = mb;
+    }
+    __syncwarp();
+    const int r0 = M.nfloss + c.nlim;
+    int nd = 0;
+    for (int base = r0; base < ne; base += 32) {
+      const int i = base + lane;
+      bool dense = false;
+      if (i < ne) {
+        const int ci = eid[i];
+        const int side = cside[ci];
+        if (side == 0) dense = true;
+        else {
+          const int k = i - cadr[ci], nrows = cdim[ci], mb = cmb[ci];
+          const float* fr = cframe + 9 * ci;
+          float off[3];
+          for (int q = 0; q < 3; q++) off[q] = cpos[3 * ci + q] - scom[3 * rootid[mb] + q];
+          float w[6];
+          auto axis_w = [&](int a, float* o) {   // direction a of the contact frame: 0..2 translational, 3..5 rotational
+            const float* ax = fr + 3 * (a % 3);
+            if (a < 3) { cross3(o, off, ax); o[3] = ax[0]; o[4] = ax[1]; o[5] = ax[2]; }
+            else { o[0] = ax[0]; o[1] = ax[1]; o[2] = ax[2]; o[3] = o[4] = o[5] = 0.f; }
+          };
+          if (pyramidal && nrows > 1) {   // pyramid edge: normal +- mu_k * tangent_k
+            float wt[6];
+            const int kk = k / 2 + 1;
+            axis_w(0, w); axis_w(kk, wt);
+            const float sm = ((k & 1) ? -1.f : 1.f) * DF(con_friction)[5 * ci + kk - 1];
+            for (int q = 0; q < 6; q++) w[q] += sm * wt[q];
+          } else {
+            axis_w(k, w);
+          }
+          for (int q = 0; q < 6; q++) W6[6 * i + q] = (float)side * w[q];
+        }
+      }
+      const unsigned mask = __ballot_sync(kFull, dense);
+      if (dense) drow[nd + __popc(mask & ((1u << lane) - 1u))] = i;
+      nd += __popc(mask);
+    }
+    c.ndrow = nd;
+  }
   c.nefc = ne;
   c.nitem = nitem;
   __syncwarp();
@@ -1047,42 +1107,118 @@ __device__ __forceinline__ void hessian_dense_reg(Ctx& c) {
   const float *qM = DF(qM), *hw = DF(efc_hw), *Jd = DF(efc_Jd), *Xd = DF(efc_Xd), *xw = DF(efc_hc);
   float* H = DF(qH);
   const int *frow = MI(floss_row), *edof = DI(efc_dof), *state = DI(efc_state), *cadr = DI(con_adr),
-            *hi = MI(hpair_i), *hj = MI(hpair_j);
-  const int NE = M.nhpair;
+            *hi = MI(hpair_i), *hj = MI(hpair_j), *cside = DI(con_side), *cdim = DI(con_dim);
+  const int NE = M.nhpair, ncon = c.ncon;
+  // ---- one-sided contacts: composite contact "inertia".  With J[row][i] = w_row . cdof_i on the moving body's chain,
+  //      sum_rows (weights) J^T J = cdof_r^T ( sum over contacts below body(r) of W_c ) cdof_s,  W_c (6x6) = sum_a hw_a
+  //      w_a w_a^T + cone terms - the same subtree-composite structure as the joint-space inertia itself (k_crb).
+  float* Wc = DF(efc_blk);        // [ncon][21] lower triangles (the generic path's block scratch, unused here)
+  float* wsub = DF(wsub);         // [nbody][36]
+  float* g = DF(dofbuf);          // [nv][6]   (k_crb's scratch, free after qM was formed)
+  const float* W6 = DF(efc_w);
+  {
+    // cone effective rows in wrench space: V = sum_a q_a w_a, U = sum_a q_{6+a} w_a  -> efc_hc[36 ci + 14 ..]
+    float* xwm = DF(efc_hc);
+    for (int w = lane; w < ncon * 6; w += 32) {
+      const int ci = w / 6, p = w - 6 * ci;
+      const int a0 = cadr[ci];
+      if (a0 < 0 || cside[ci] == 0 || state[a0] != STATE_CONE) continue;
+      const int dim = cdim[ci];
+      const float* q = xw + 36 * ci;
+      float v = 0.f, u = 0.f;
+      FOR_DIM(a, 0, dim) { const float wa = W6[6 * (a0 + a) + p]; v += q[a] * wa; u += q[6 + a] * wa; }
+      xwm[36 * ci + 14 + p] = v; xwm[36 * ci + 20 + p] = u;
+    }
+    __syncwarp();
+    for (int w = lane; w < ncon * 21; w += 32) {
+      const int ci = w / 21, e = w - 21 * ci;
+      int p = e < 1 ? 0 : e < 3 ? 1 : e < 6 ? 2 : e < 10 ? 3 : e < 15 ? 4 : 5;
+      const int q2 = e - p * (p + 1) / 2;
+      const int a0 = cadr[ci];
+      float acc = 0.f;
+      if (a0 >= 0 && cside[ci] != 0) {
+        const int nrows = cdim[ci];
+        for (int a = 0; a < nrows; a++) acc += hw[a0 + a] * W6[6 * (a0 + a) + p] * W6[6 * (a0 + a) + q2];
+        if (state[a0] == STATE_CONE) {
+          const float* q = xw + 36 * ci;
+          acc += q[12] * q[14 + p] * q[14 + q2] + q[13] * q[20 + p] * q[20 + q2];
+        }
+      }
+      Wc[w] = acc;
+    }
+    __syncwarp();
+    const int *subend = MI(body_subtreeend), *cmb = DI(con_mbody);
+    const int nb = M.nbody;
+    for (int w = lane; w < nb * 21; w += 32) {
+      const int b = w / 21, e = w - 21 * b;
+      int p = e < 1 ? 0 : e < 3 ? 1 : e < 6 ? 2 : e < 10 ? 3 : e < 15 ? 4 : 5;
+      const int q2 = e - p * (p + 1) / 2;
+      const int se = subend[b];
+      float acc = 0.f;
+      for (int ci = 0; ci < ncon; ci++) {
+        const int mb = cmb[ci];
+        if (cside[ci] != 0 && cadr[ci] >= 0 && mb >= b && mb < se) acc += Wc[21 * ci + e];
+      }
+      wsub[36 * b + 6 * p + q2] = acc; wsub[36 * b + 6 * q2 + p] = acc;
+    }
+    __syncwarp();
+    const int* dbody = MI(dof_bodyid);
+    const float* cdof = DF(cdof);
+    for (int w = lane; w < NV * 6; w += 32) {
+      const int i = w / 6, k = w - 6 * i;
+      const float* Wb = wsub + 36 * dbody[i] + 6 * k;
+      const float* cd = cdof + 6 * i;
+      float a = 0.f;
+#pragma unroll
+      for (int l = 0; l < 6; l++) a += Wb[l] * cd[l];
+      g[w] = a;
+    }
+    __syncwarp();
+  }
   int er[NQ], es[NQ];
   float acc[NQ];
   for (int w = lane; w < NV * NV; w += 32) H[w] = 0.f;   // entries outside the pattern (the factor fills them)
+  {
+    const float* cdof = DF(cdof);
 #pragma unroll
-  for (int q = 0; q < NQ; q++) {
-    int e = lane + 32 * q;
-    if (e >= NE) e = NE - 1;
-    const int r = hi[e];
-    er[q] = r; es[q] = hj[e];
-    float a = qM[er[q] * NV + es[q]];
-    if (er[q] == es[q]) {
-      const int fr = frow[r];
-      if (fr >= 0) a += hw[fr];
-      for (int k = M.nfloss; k < M.nfloss + c.nlim; k++)
-        if (edof[k] == r) a += hw[k];
+    for (int q = 0; q < NQ; q++) {
+      int e = lane + 32 * q;
+      if (e >= NE) e = NE - 1;
+      const int r = hi[e];
+      er[q] = r; es[q] = hj[e];
+      float a = qM[er[q] * NV + es[q]];
+      const float *gr = g + 6 * r, *cs = cdof + 6 * es[q];
+#pragma unroll
+      for (int l = 0; l < 6; l++) a += gr[l] * cs[l];
+      if (er[q] == es[q]) {
+        const int fr = frow[r];
+        if (fr >= 0) a += hw[fr];
+        for (int k = M.nfloss; k < M.nfloss + c.nlim; k++)
+          if (edof[k] == r) a += hw[k];
+      }
+      acc[q] = a;
     }
-    acc[q] = a;
   }
-  const int r0 = M.nfloss + c.nlim, ne = c.nefc;
-  for (int row = r0; row < ne; row++) {
+  // ---- rows of two-sided contacts and tendon limits: one rank-1 update per active row / cone effective row
+  const int* drow = DI(efc_drow);
+  for (int k = 0; k < c.ndrow; k++) {
+    const int row = drow[k];
     const float w = hw[row];
     if (w == 0.f) continue;   // warp-uniform
     const float* j = Jd + row * NVP;
 #pragma unroll
     for (int q = 0; q < NQ; q++) acc[q] += w * j[er[q]] * j[es[q]];
   }
-  for (int ci = 0; ci < c.ncon; ci++) {
-    const int a0 = cadr[ci];
-    if (a0 < 0 || state[a0] != STATE_CONE) continue;   // warp-uniform
-    const float wv = xw[36 * ci + 12], wu = xw[36 * ci + 13];
-    const float* xv = Xd + (2 * ci) * NVP;
-    const float* xu = xv + NVP;
+  if (c.ndrow > 0) {
+    for (int ci = 0; ci < ncon; ci++) {
+      const int a0 = cadr[ci];
+      if (a0 < 0 || cside[ci] != 0 || state[a0] != STATE_CONE) continue;   // warp-uniform
+      const float wv = xw[36 * ci + 12], wu = xw[36 * ci + 13];
+      const float* xv = Xd + (2 * ci) * NVP;
+      const float* xu = xv + NVP;
 #pragma unroll
-    for (int q = 0; q < NQ; q++) acc[q] += wv * xv[er[q]] * xv[es[q]] + wu * xu[er[q]] * xu[es[q]];
+      for (int q = 0; q < NQ; q++) acc[q] += wv * xv[er[q]] * xv[es[q]] + wu * xu[er[q]] * xu[es[q]];
+    }
   }
   __syncwarp();
 #pragma unroll
@@ -1156,20 +1292,30 @@ __device__ __forceinline__ float j_row_dot(Ctx& c, int row, int nsimple, const f
 // one (contact, block entry) per lane; (2) every structurally non-zero Hessian entry gathers the blocks that
 // contain it (deterministic order, no atomics).
 template <class SP>
-__device__ __noinline__ float k_total_cost(Ctx& c, const float* qacc, bool hess, float* gauss_out) {
+__device__ __noinline__ float k_total_cost(Ctx& c, const float* qacc, bool hess, float* gauss_out, float step = 0.f) {
   auto&& M = SP::model(c);
   const int lane = c.lane, nv = M.nv;
   const float *qM = DF(qM), *J = DF(efc_J), *aref = DF(efc_aref), *smooth = DF(qfrc_smooth), *qas = DF(qacc_smooth);
   float *Ma = DF(Ma), *jar = DF(efc_jar);
   const int nsimple = M.nfloss + c.nlim;
   float g = 0;
-  for (int i = lane; i < nv; i += 32) {
-    float a = 0;
-    a = m_row_dot<SP>(qM, i, qacc, nv);
-    Ma[i] = a;
-    g += (a - smooth[i]) * (qacc[i] - qas[i]);
+  if (step != 0.f) {
+    // qacc moved by step * search: M qacc and J qacc - aref follow from the products the line search already formed
+    const float *Mv = DF(Mv), *Jv = DF(efc_Jv);
+    for (int i = lane; i < nv; i += 32) {
+      const float a = Ma[i] + step * Mv[i];
+      Ma[i] = a;
+      g += (a - smooth[i]) * (qacc[i] - qas[i]);
+    }
+    for (int i = lane; i < c.nefc; i += 32) jar[i] += step * Jv[i];
+  } else {
+    for (int i = lane; i < nv; i += 32) {
+      const float a = m_row_dot<SP>(qM, i, qacc, nv);
+      Ma[i] = a;
+      g += (a - smooth[i]) * (qacc[i] - qas[i]);
+    }
+    for (int i = lane; i < c.nefc; i += 32) jar[i] = j_row_dot<SP>(c, i, nsimple, qacc, nv) - aref[i];
   }
-  for (int i = lane; i < c.nefc; i += 32) jar[i] = j_row_dot<SP>(c, i, nsimple, qacc, nv) - aref[i];
   g = 0.5f * warp_sum(g);
   __syncwarp();
   const float cc = k_update_constraint<SP>(c, hess);
@@ -1188,14 +1334,15 @@ __device__ __noinline__ void k_hessian(Ctx& c) {
   float *X = DF(efc_W);
   const int *state = DI(efc_state), *cdim = DI(con_dim);
   const float* xw = DF(efc_hc);
-  {
+  const bool tree_path = SP::kNV > 0 || nv == 18;   // hessian_dense_reg: one-sided contacts go through the composite form
+  if (!tree_path || c.ndrow > 0) {
     // effective rows of cone contacts (compact): one (contact, local dof) pair per lane
-    const int *cadr = DI(con_adr), *cnd = DI(con_nd);
+    const int *cadr = DI(con_adr), *cnd = DI(con_nd), *cside = DI(con_side);
     const int total = c.ncon * kL;
     for (int w = lane; w < total; w += 32) {
       const int ci = w / kL, l = w - ci * kL;
       const int a0 = cadr[ci];
-      if (a0 < 0 || l >= cnd[ci] || state[a0] != STATE_CONE) continue;
+      if (a0 < 0 || l >= cnd[ci] || state[a0] != STATE_CONE || (tree_path && cside[ci] != 0)) continue;
       const int dim = cdim[ci];
       const float* q = xw + 36 * ci;
       float xv = 0.f, xu = 0.f;
@@ -1215,7 +1362,7 @@ __device__ __noinline__ void k_hessian(Ctx& c) {
       for (int w = lane; w < c.ncon * nv; w += 32) {
         const int ci = w / nv, i = w - ci * nv;
         const int a0 = cadr[ci];
-        if (a0 < 0 || state[a0] != STATE_CONE) continue;
+        if (a0 < 0 || state[a0] != STATE_CONE || cside[ci] != 0) continue;
         const int l = cloc[w];
         Xd[(2 * ci) * nvp + i] = l >= 0 ? X[(2 * ci) * kL + l] : 0.f;
         Xd[(2 * ci + 1) * nvp + i] = l >= 0 ? X[(2 * ci + 1) * kL + l] : 0.f;
@@ -1452,8 +1599,12 @@ __device__ __noinline__ float k_line_search(Ctx& c, float g0, float g1, float g2
   const LsPoint p0 = ev(0.f);
   const float gtol = fmaxf(fmaxf(CM(c).tolerance, kTolFloor) * CM(c).ls_tolerance * snorm * scale_inv, 64 * 1.1920929e-7f * fabsf(p0.d1));
   if (p0.d2 <= kMinVal) return 0.f;
+  // fp32 cannot resolve cost differences below ~eps * cost, which is where the last Newton iterations live.  The
+  // 1-D cost is convex and p0.d1 < 0, so acceptance is decided on the derivative: |d1| < gtol is the minimiser, and a
+  // point still on the descending side (d1 <= 0, alpha > 0) cannot be worse than alpha = 0 (same rule as the fp32
+  // instantiation of the oracle, oracle/physics.h line_search).
   LsPoint p1 = ev(-p0.d1 / p0.d2);
-  if (p0.cost < p1.cost) p1 = p0;
+  if (p0.cost < p1.cost && !(p1.d1 <= 0.f)) p1 = p0;
   if (fabsf(p1.d1) < gtol) return p1.alpha;
   int iter = 0;
   LsPoint p2 = p1;
@@ -1463,10 +1614,10 @@ __device__ __noinline__ float k_line_search(Ctx& c, float g0, float g1, float g2
     p2 = p1;
     if (p1.d2 <= kMinVal) break;
     p1 = ev(p1.alpha - p1.d1 / p1.d2);
-    if (fabsf(p1.d1) < gtol) return p1.cost <= p0.cost ? p1.alpha : 0.f;
+    if (fabsf(p1.d1) < gtol) return p1.alpha;
     if ((p1.d1 > 0) != (p2.d1 > 0)) { bracket = true; break; }
   }
-  if (!bracket) return p1.cost < p0.cost ? p1.alpha : 0.f;
+  if (!bracket) return ((p1.d1 <= 0.f && p1.alpha > 0.f) || p1.cost < p0.cost) ? p1.alpha : 0.f;
   LsPoint lo = p1.d1 < 0 ? p1 : p2, hi = p1.d1 < 0 ? p2 : p1;
   while (iter < M.ls_iterations) {
     iter++;
@@ -1476,11 +1627,11 @@ __device__ __noinline__ float k_line_search(Ctx& c, float g0, float g1, float g2
     if (!(a > amin && a < amax)) a = 0.5f * (lo.alpha + hi.alpha);
     if (a == lo.alpha || a == hi.alpha) break;
     const LsPoint pm = ev(a);
-    if (fabsf(pm.d1) < gtol) return pm.cost <= p0.cost ? pm.alpha : 0.f;
+    if (fabsf(pm.d1) < gtol) return pm.alpha;
     if (pm.d1 < 0) lo = pm; else hi = pm;
   }
-  const LsPoint best = lo.cost < hi.cost ? lo : hi;
-  return best.cost < p0.cost ? best.alpha : 0.f;
+  if (lo.alpha > 0.f) return lo.alpha;   // bracket closed to adjacent values: the descending end is an improvement
+  return hi.cost < p0.cost ? hi.alpha : 0.f;
 }
 
 // out[dof] = sum over constraint rows of J[row][dof] * force[row], in two balanced stages (per contact, then per dof)
@@ -1556,23 +1707,34 @@ __device__ __noinline__ void k_solve(Ctx& c) {
   const int nsimple = M.nfloss + c.nlim;
   float *grad = DF(grad), *search = DF(search), *Mv = DF(Mv), *Ma = DF(Ma), *smooth = DF(qfrc_smooth), *Jv = DF(efc_Jv),
         *qM = DF(qM);
-  float old = cost;
+  float old = cost, prev_gradient = 3.0e38f, alpha = 0.f;
+  int stalls = 0;
   bool qfc_current = false;
   for (int iter = 0; iter <= M.iterations; iter++) {
     // gradient at the current point; qfc doubles as the J^T force scratch and is the output when we stop here
     jt_force_any<SP>(c, qfc, nv);
     qfc_current = true;
-    float g2 = 0;
+    float g2 = 0, ga = 0;
     for (int i = lane; i < nv; i += 32) {
       const float a = Ma[i] - smooth[i] - qfc[i];
       grad[i] = a;
       g2 += a * a;
+      const float m = fabsf(Ma[i]) + fabsf(smooth[i]) + fabsf(qfc[i]);
+      ga += m * m;
     }
-    const float gnorm2 = warp_sum(g2);
+    const float gnorm2 = warp_sum(g2), gabs2 = warp_sum(ga);
     __syncwarp();
     if (iter > 0) {
+      // fp32 termination (same rule as the fp32 oracle, oracle/physics.h solve_constraints): the gradient test has a
+      // rounding floor; a cost decrease below the rounding of the cost itself is not evidence of convergence and only
+      // stops the solver when a (near) full Newton step no longer shrinks the gradient
       const float improvement = (old - cost) / scale_inv, gradient = sqrtf(gnorm2) / scale_inv;
-      if (improvement < tol || gradient < tol) break;
+      const float gfloor = kGradFloor * 1.1920929e-7f * sqrtf(gabs2) / scale_inv;
+      if (gradient < fmaxf(tol, gfloor)) break;
+      const bool resolvable = fabsf(old - cost) > 16.f * 1.1920929e-7f * fabsf(cost);
+      if (resolvable) { if (improvement < tol) break; stalls = 0; }
+      else if (gradient > 0.5f * prev_gradient && (alpha > 0.5f || ++stalls >= 3)) break;
+      prev_gradient = gradient;
     }
     if (iter == M.iterations) break;
     // Newton direction: assemble + factorise the Hessian only now that another iteration is taken
@@ -1592,12 +1754,12 @@ __device__ __noinline__ void k_solve(Ctx& c) {
     for (int i = lane; i < ne; i += 32) Jv[i] = j_row_dot<SP>(c, i, nsimple, search, nv);
     q1 = warp_sum(q1); q2 = warp_sum(q2); sn = sqrtf(warp_sum(sn));
     __syncwarp();
-    const float alpha = k_line_search<SP>(c, gauss, q1, q2, sn, scale_inv);
+    alpha = k_line_search<SP>(c, gauss, q1, q2, sn, scale_inv);
     if (alpha == 0.f) break;
     for (int i = lane; i < nv; i += 32) qacc[i] += alpha * search[i];
     __syncwarp();
     old = cost;
-    cost = k_total_cost<SP>(c, qacc, true, &gauss);
+    cost = k_total_cost<SP>(c, qacc, true, &gauss, alpha);
     qfc_current = false;
     c.niter = iter + 1;
   }

@@ -475,6 +475,70 @@ int mjpc_b200_step_debug(mjpc_b200_t* h, const float* qpos, const float* qvel, c
   return 0;
 }
 
+// Batched single-step parity hook (see step_batch_kernel): B tuples -> one mj_step each.  times are absolute; the task
+// state is rebased to `time0` exactly as a rollout starting at time0 would (device time = times[b] - time0).
+int mjpc_b200_step_batch(mjpc_b200_t* h, int B, const float* qpos, const float* qvel, const float* ctrl,
+                         const float* warmstart, const float* mocap, double time0, const double* times, float* qacc,
+                         float* next_qpos, float* next_qvel, float* residual, float* cost, int* counts) {
+  if (!h || B < 1 || !qpos || !qvel || !ctrl || !times) return fail(MJPC_B200_ERR_BAD_ARGUMENT, "step_batch: bad argument");
+  const DevModel& M = h->pack.M;
+  if (M.nmocap && !mocap) return fail(MJPC_B200_ERR_BAD_ARGUMENT, "step_batch: mocap required");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const size_t nq = M.nq, nv = M.nv, nu = M.nu, nr = std::max(M.num_residual, 1), nm = 7 * (size_t)M.nmocap,
+               nts = (size_t)M.task_state_size;
+  const size_t per = nq + nv + nu + nv + 1 + nv + nq + nv + nr + 1 + 4;
+  const size_t words = per * (size_t)B + nm + nts + 16;
+  float* d = nullptr;
+  CUDA_TRY(dalloc(&d, words));
+  struct Guard { float* p; ~Guard() { cudaFree(p); } } guard{d};
+  float *d_qpos = d, *d_qvel = d_qpos + B * nq, *d_ctrl = d_qvel + B * nv, *d_warm = d_ctrl + B * nu, *d_time = d_warm + B * nv,
+        *d_qacc = d_time + B, *d_nq = d_qacc + B * nv, *d_nv = d_nq + B * nq, *d_res = d_nv + B * nv, *d_cost = d_res + B * nr,
+        *d_counts = d_cost + B, *d_mocap = d_counts + 4 * (size_t)B, *d_ts = d_mocap + nm;
+  std::vector<float> trel(B), ts(nts);
+  for (int i = 0; i < B; i++) trel[i] = (float)(times[i] - time0);
+  for (size_t i = 0; i < nts; i++) {
+    double v = h->task_state[i];
+    if (std::find(h->time_idx.begin(), h->time_idx.end(), (int)i) != h->time_idx.end()) v -= time0;
+    ts[i] = (float)v;
+  }
+  CUDA_TRY(cudaMemcpy(d_qpos, qpos, B * nq * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(d_qvel, qvel, B * nv * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(d_ctrl, ctrl, B * nu * 4, cudaMemcpyHostToDevice));
+  if (warmstart) CUDA_TRY(cudaMemcpy(d_warm, warmstart, B * nv * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(d_time, trel.data(), (size_t)B * 4, cudaMemcpyHostToDevice));
+  if (nm) CUDA_TRY(cudaMemcpy(d_mocap, mocap, nm * 4, cudaMemcpyHostToDevice));
+  if (nts) CUDA_TRY(cudaMemcpy(d_ts, ts.data(), nts * 4, cudaMemcpyHostToDevice));
+  StepBatchArgs A;
+  std::memset(&A, 0, sizeof(A));
+  A.M = h->pack.M; A.L = make_layout(h->pack.M, 1); A.pack = h->d_pack;
+  A.qpos = d_qpos; A.qvel = d_qvel; A.ctrl = d_ctrl; A.warmstart = warmstart ? d_warm : nullptr; A.mocap = d_mocap;
+  A.task_state = nts ? d_ts : nullptr; A.time = d_time; A.B = B;
+  A.qacc = d_qacc; A.next_qpos = d_nq; A.next_qvel = d_nv; A.residual = d_res; A.cost = d_cost; A.counts = (int*)d_counts;
+  const size_t smem = h->smem_bytes(1, 1);
+  const char* ns = std::getenv("MJPC_B200_NO_STATIC");
+  const bool use_static = h->static_spec != 0 && !(ns && ns[0] == '1');
+  const void* fn = use_static ? (h->static_spec == 1 ? (const void*)step_batch_kernel_quadruped : (const void*)step_batch_kernel_humanoid_track)
+                              : (const void*)step_batch_kernel;
+  if (int rc = set_smem(fn, smem)) return rc;
+  CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+  if (use_static && h->static_spec == 1) step_batch_kernel_quadruped<<<B, 32, smem, h->stream>>>(A);
+  else if (use_static) step_batch_kernel_humanoid_track<<<B, 32, smem, h->stream>>>(A);
+  else step_batch_kernel<<<B, 32, smem, h->stream>>>(A);
+  CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  h->last_static = use_static ? 1 : 0;
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1) != cudaSuccess) cudaGetLastError();
+  if (qacc) CUDA_TRY(cudaMemcpy(qacc, d_qacc, B * nv * 4, cudaMemcpyDeviceToHost));
+  if (next_qpos) CUDA_TRY(cudaMemcpy(next_qpos, d_nq, B * nq * 4, cudaMemcpyDeviceToHost));
+  if (next_qvel) CUDA_TRY(cudaMemcpy(next_qvel, d_nv, B * nv * 4, cudaMemcpyDeviceToHost));
+  if (residual) CUDA_TRY(cudaMemcpy(residual, d_res, B * (size_t)M.num_residual * 4, cudaMemcpyDeviceToHost));
+  if (cost) CUDA_TRY(cudaMemcpy(cost, d_cost, (size_t)B * 4, cudaMemcpyDeviceToHost));
+  if (counts) CUDA_TRY(cudaMemcpy(counts, d_counts, (size_t)B * 16, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 int mjpc_b200_fetch_stats(mjpc_b200_t* h, int64_t* stats) {
   if (!h || !stats || h->lastN < 1) return fail(MJPC_B200_ERR_BAD_ARGUMENT, "fetch_stats: nothing to fetch");
   CUDA_TRY(cudaSetDevice(h->device));

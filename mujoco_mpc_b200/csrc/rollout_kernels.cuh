@@ -85,7 +85,7 @@ __device__ __forceinline__ void init_ctx(Ctx& c, const DevModel* M, const DevLay
   c.dbase = data0 + warp * L->total;
   c.lane = lane;
   c.gkey = pack + M->nf + M->ni;   // the keyframe table follows the staged part of the pack in HBM
-  c.ncon = 0; c.npseudo = 0; c.xfrc_on = 0; c.nefc = 0; c.nitem = 0; c.niter = 0; c.nlim = 0; c.warn = 0; c.time = 0.f;
+  c.ncon = 0; c.npseudo = 0; c.xfrc_on = 0; c.nefc = 0; c.ndrow = 0; c.nitem = 0; c.niter = 0; c.nlim = 0; c.warn = 0; c.time = 0.f;
 #ifdef MJPC_PHASE_TIMING
   for (int k = 0; k < 8; k++) c.tph[k] = 0;
   c.tlast = clock64();
@@ -305,6 +305,74 @@ extern "C" __global__ void __launch_bounds__(32) step_debug_kernel(const __grid_
   k_euler<SP>(c);
   for (int i = lane; i < nq; i += 32) A.next_qpos[i] = DF(qpos)[i];
   for (int i = lane; i < nv; i += 32) A.next_qvel[i] = DF(qvel)[i];
+}
+
+
+// Batched parity hook: B independent (qpos, qvel, ctrl, warm start, time) tuples, each advanced by ONE mj_step through
+// the same device functions - and the same static / generic instances - the rollout kernel runs.  Teacher-forced
+// per-step parity tests feed it the oracle's own states, so a mismatch cannot be blamed on trajectory divergence.
+struct StepBatchArgs {
+  DevModel M;
+  DevLayout L;
+  const float* pack;
+  const float* qpos; const float* qvel; const float* ctrl; const float* warmstart;   // [B][nq|nv|nu|nv]
+  const float* mocap; const float* task_state;
+  const float* time;    // [B], relative to the rollout start the task state was rebased to
+  int B;
+  float* qacc; float* next_qpos; float* next_qvel; float* residual; float* cost; int* counts;   // counts [B][4]
+};
+
+template <class SP>
+__device__ __forceinline__ void step_batch_body(const StepBatchArgs& A) {
+  float* smem = g_smem;
+  stage_model_pack(smem, A.pack, (unsigned)((A.M.nf + A.M.ni) * 4));
+  Ctx c;
+  init_ctx(c, &A.M, &A.L, smem, 0, threadIdx.x, A.pack);
+  auto&& M = SP::model(c);
+  const int lane = c.lane, nq = M.nq, nv = M.nv, nu = M.nu, nr = M.num_residual;
+  const int b = blockIdx.x;
+  if (b >= A.B) return;
+  if (A.task_state) {
+    float* ts = const_cast<float*>(MF(task_state));
+    for (int i = lane; i < M.task_state_size; i += 32) ts[i] = A.task_state[i];
+  }
+  for (int i = lane; i < nq; i += 32) DF(qpos)[i] = A.qpos[(size_t)b * nq + i];
+  for (int i = lane; i < nv; i += 32) {
+    DF(qvel)[i] = A.qvel[(size_t)b * nv + i];
+    DF(qacc_warmstart)[i] = A.warmstart ? A.warmstart[(size_t)b * nv + i] : 0.f;
+  }
+  for (int i = lane; i < nu; i += 32) DF(ctrl)[i] = A.ctrl[(size_t)b * nu + i];
+  for (int i = lane; i < 7 * M.nmocap; i += 32) {
+    const int k = i / 7, q = i - 7 * k;
+    if (q < 3) DF(mocap_pos)[3 * k + q] = A.mocap[i]; else DF(mocap_quat)[4 * k + q - 3] = A.mocap[i];
+  }
+  for (int i = lane; i < nv * nv; i += 32) DF(qM)[i] = 0;
+  for (int i = lane; i < 6 * M.nbody; i += 32) DF(xfrc)[i] = 0;
+  c.time = A.time[b];
+  __syncwarp();
+  k_forward<SP>(c);
+  k_residual<SP>(c);
+  if (k_bad(c, DF(qacc), nv)) c.warn = 1;
+  const float cost = k_cost_value<SP>(c);
+  for (int i = lane; i < nv; i += 32) A.qacc[(size_t)b * nv + i] = DF(qacc)[i];
+  for (int i = lane; i < nr; i += 32) A.residual[(size_t)b * nr + i] = DF(residual)[i];
+  if (lane == 0) {
+    A.cost[b] = cost;
+    A.counts[4 * b] = c.ncon - c.npseudo; A.counts[4 * b + 1] = c.nefc; A.counts[4 * b + 2] = c.niter; A.counts[4 * b + 3] = c.warn;
+  }
+  for (int i = lane; i < nv; i += 32) DF(qacc_warmstart)[i] = DF(qacc)[i];
+  k_euler<SP>(c);
+  for (int i = lane; i < nq; i += 32) A.next_qpos[(size_t)b * nq + i] = DF(qpos)[i];
+  for (int i = lane; i < nv; i += 32) A.next_qvel[(size_t)b * nv + i] = DF(qvel)[i];
+}
+extern "C" __global__ void __launch_bounds__(32) step_batch_kernel(const __grid_constant__ StepBatchArgs A) {
+  step_batch_body<DynSpec>(A);
+}
+extern "C" __global__ void __launch_bounds__(32) step_batch_kernel_quadruped(const __grid_constant__ StepBatchArgs A) {
+  step_batch_body<StaticSpec<SpecQuadruped>>(A);
+}
+extern "C" __global__ void __launch_bounds__(32) step_batch_kernel_humanoid_track(const __grid_constant__ StepBatchArgs A) {
+  step_batch_body<StaticSpec<SpecHumanoidTrack>>(A);
 }
 
 }  // namespace mjpc_dev

@@ -21,7 +21,7 @@ _bp = C.POINTER(C.c_uint8)
 EXPORTS = ["mjpc_b200_version", "mjpc_b200_last_error", "mjpc_b200_create", "mjpc_b200_destroy",
            "mjpc_b200_get_info", "mjpc_b200_set_task", "mjpc_b200_set_xfrc_noise", "mjpc_b200_rollout_spline", "mjpc_b200_rollout_feedback",
            "mjpc_b200_fetch_trajectory", "mjpc_b200_fetch_all", "mjpc_b200_model_derivatives",
-           "mjpc_b200_cost_derivatives", "mjpc_b200_backward_pass", "mjpc_b200_step_debug",
+           "mjpc_b200_cost_derivatives", "mjpc_b200_backward_pass", "mjpc_b200_step_debug", "mjpc_b200_step_batch",
            "mjpc_b200_fetch_stats", "mjpc_b200_launch_count", "mjpc_b200_last_kernel_ms", "mjpc_b200_last_kernel_static",
            "mjpc_b200_spec_words", "mjpc_b200_upload_spline_inputs",
            "mjpc_b200_launch_resident", "mjpc_b200_sync", "mjpc_b200_read_returns", "mjpc_b200_stream",
@@ -225,6 +225,20 @@ class Engine:
                                                   counts.ctypes.data_as(_ip)))
         o.update(ncon=int(counts[0]), nefc=int(counts[1]), niter=int(counts[2]), warning=int(counts[3]))
         o["efc_force"] = o["efc_force"][: o["nefc"]]
+        return o
+
+    def step_batch(self, qpos, qvel, ctrl, mocap, times, time0=0.0, warmstart=None):
+        """B independent single steps (mjpc_b200_step_batch): teacher-forced per-step parity at planner sizes."""
+        q, v, u, mc, ws, t = _f(qpos), _f(qvel), _f(ctrl), _f(mocap), _f(warmstart), _d(times)
+        B, nv, nq = q.shape[0], self.info.nv, self.info.nq
+        o = dict(qacc=np.zeros((B, nv), np.float32), next_qpos=np.zeros((B, nq), np.float32),
+                 next_qvel=np.zeros((B, nv), np.float32), residual=np.zeros((B, max(self.nr, 1)), np.float32),
+                 cost=np.zeros(B, np.float32))
+        counts = np.zeros((B, 4), np.int32)
+        self._check(self.lib.mjpc_b200_step_batch(self.h, B, _pf(q), _pf(v), _pf(u), _pf(ws), _pf(mc), C.c_double(time0),
+                                                  _pd(t), _pf(o["qacc"]), _pf(o["next_qpos"]), _pf(o["next_qvel"]),
+                                                  _pf(o["residual"]), _pf(o["cost"]), counts.ctypes.data_as(_ip)))
+        o.update(ncon=counts[:, 0], nefc=counts[:, 1], niter=counts[:, 2], warning=counts[:, 3])
         return o
 
     # ---- iLQG sweeps

@@ -179,6 +179,50 @@ int forward_debug(Engine<T>& e, const double* qpos, const double* qvel, const do
   return d.warning ? 1 : 0;
 }
 
+// B independent single steps (mj_step, trajectory.cc:158) from given (qpos, qvel, ctrl, warm start, time): the CPU
+// side of the teacher-forced per-step parity tests.  counts [B][4] = {ncon, nefc, Newton iterations, warning}.
+template <class T>
+int step_batch(Engine<T>& e, int B, const double* qpos, const double* qvel, const double* ctrl, const double* warmstart,
+               const double* mocap, const double* times, int nthreads, double* qacc, double* next_qpos,
+               double* next_qvel, double* residual, double* cost, int* counts) {
+  const Model<T>& m = e.model;
+  e.resize(nthreads);
+  const int nq = m.nq, nv = m.nv, nu = m.nu, nr = m.num_residual;
+  const int before = e.pool->GetCount();
+  for (int w = 0; w < nthreads; w++) {
+    e.pool->Schedule([&, w]() {
+      Data<T>& d = *e.data[w];
+      for (int b = w; b < B; b += nthreads) {
+        for (int i = 0; i < nq; i++) d.qpos[i] = (T)qpos[(size_t)b * nq + i];
+        for (int i = 0; i < nv; i++) d.qvel[i] = (T)qvel[(size_t)b * nv + i];
+        for (int i = 0; i < nu; i++) d.ctrl[i] = (T)ctrl[(size_t)b * nu + i];
+        for (int i = 0; i < m.nmocap; i++) {
+          for (int c = 0; c < 3; c++) d.mocap_pos[3 * i + c] = (T)mocap[7 * i + c];
+          for (int c = 0; c < 4; c++) d.mocap_quat[4 * i + c] = (T)mocap[7 * i + 3 + c];
+        }
+        for (int i = 0; i < nv; i++) d.qacc_warmstart[i] = warmstart ? (T)warmstart[(size_t)b * nv + i] : (T)0;
+        std::fill(d.xfrc_applied.begin(), d.xfrc_applied.end(), (T)0);
+        d.xfrc_active = false;
+        d.time = (T)times[b];
+        d.warning = false;
+        forward<T>(m, d, residual_by_id<T>(m.residual_id));
+        if (bad(d.qacc)) d.warning = true;
+        if (qacc) for (int i = 0; i < nv; i++) qacc[(size_t)b * nv + i] = d.qacc[i];
+        if (residual) for (int i = 0; i < nr; i++) residual[(size_t)b * nr + i] = d.residual[i];
+        if (cost) cost[b] = CostValue(e.cost, d.residual.data());
+        if (counts) { counts[4 * b] = d.ncon; counts[4 * b + 1] = d.nefc; counts[4 * b + 2] = d.solver_niter; counts[4 * b + 3] = d.warning; }
+        d.qacc_warmstart = d.qacc;
+        euler<T>(m, d);
+        if (next_qpos) for (int i = 0; i < nq; i++) next_qpos[(size_t)b * nq + i] = d.qpos[i];
+        if (next_qvel) for (int i = 0; i < nv; i++) next_qvel[(size_t)b * nv + i] = d.qvel[i];
+      }
+    });
+  }
+  e.pool->WaitCount(before + nthreads);
+  e.pool->ResetCount();
+  return 0;
+}
+
 }  // namespace
 
 #define DISPATCH(h, call) ((h)->precision == 64 ? call(*(h)->e64) : call(*(h)->e32))
@@ -197,6 +241,18 @@ void* oracle_create(const void* blob, size_t nbytes, int precision) {
   }
 }
 void oracle_destroy(void* hv) { delete (Handle*)hv; }
+int oracle_step_batch(void* hv, int B, const double* qpos, const double* qvel, const double* ctrl, const double* warmstart,
+                      const double* mocap, const double* times, int nthreads, double* qacc, double* next_qpos,
+                      double* next_qvel, double* residual, double* cost, int* counts) {
+  Handle* h = (Handle*)hv;
+#define CALL(e) step_batch(e, B, qpos, qvel, ctrl, warmstart, mocap, times, nthreads, qacc, next_qpos, next_qvel, residual, cost, counts)
+  return DISPATCH(h, CALL);
+#undef CALL
+}
+// diagnostics: Newton iterations per solve since the last reset (64 bins)
+void oracle_solver_hist(long* out, int reset) {
+  for (int i = 0; i < 64; i++) { out[i] = solver_hist()[i].load(); if (reset) solver_hist()[i] = 0; }
+}
 
 int oracle_set_task(void* hv, const double* weight, const double* parameters, const double* task_state, double risk) {
   auto* h = (Handle*)hv;

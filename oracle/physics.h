@@ -13,10 +13,15 @@
 #include <limits>
 #include <vector>
 
+#include <atomic>
+
 #include "counted.h"
 #include "model.h"
 
 namespace oracle {
+
+// diagnostics: histogram of Newton iterations per solve (all threads), read through oracle_solver_hist()
+inline std::atomic<long>* solver_hist() { static std::atomic<long> h[64]; return h; }
 
 template <class T> constexpr T kMinVal() { return (T)1e-15; }
 // Solver tolerance floor: opt.tolerance (1e-8) is below what fp32 cost differences can resolve, so reduced
@@ -25,6 +30,8 @@ template <class T> constexpr T kTolFloor() { return sizeof(T) == 4 ? (T)1e-6 : (
 constexpr double kMaxVal = 1e10;      // mjMAXVAL
 constexpr double kMinImp = 0.0001, kMaxImp = 0.9999, kMinMu = 1e-5;
 constexpr int kMaxConDim = 6;
+// reduced-precision solver: the gradient cannot be driven below kGradFloor * eps * |terms| (see solve_constraints)
+constexpr double kGradFloor = 16;
 
 enum { CNSTR_FRICTION_DOF = 0, CNSTR_LIMIT_JOINT, CNSTR_CONTACT_FRICTIONLESS, CNSTR_CONTACT_ELLIPTIC, CNSTR_LIMIT_TENDON,
        CNSTR_CONTACT_PYRAMIDAL };
@@ -1045,8 +1052,13 @@ T line_search(const Model<T>& m, const Data<T>& d, const SolverCtx<T>& s, const 
   T gtol = mm::max(mm::max(m.tolerance, kTolFloor<T>()) * m.ls_tolerance * snorm * scale_inv,
                     64 * mm::eps<T>() * mm::fabs(p0.d1));
   if (p0.d2 <= kMinVal<T>()) return 0;
+  // Reduced precision cannot resolve cost differences below ~eps * cost, which is where the last one or two Newton
+  // iterations live.  The 1-D cost is convex and p0.d1 < 0, so acceptance there is decided on the derivative: a
+  // point with |d1| < gtol is the minimiser, and a point still on the descending side (d1 <= 0, alpha > 0) cannot be
+  // worse than alpha = 0.  fp64 keeps the published cost comparisons (identical in exact arithmetic).
+  constexpr bool robust = sizeof(T) == 4;
   LsPoint<T> p1 = ls_eval(m, d, s, qg, -p0.d1 / p0.d2);
-  if (p0.cost < p1.cost) p1 = p0;
+  if (p0.cost < p1.cost && !(robust && p1.d1 <= 0)) p1 = p0;
   if (mm::fabs(p1.d1) < gtol) return p1.alpha;
   // Newton iterations on one side until the derivative changes sign
   int iter = 0;
@@ -1057,10 +1069,10 @@ T line_search(const Model<T>& m, const Data<T>& d, const SolverCtx<T>& s, const 
     p2 = p1;
     if (p1.d2 <= kMinVal<T>()) break;
     p1 = ls_eval(m, d, s, qg, p1.alpha - p1.d1 / p1.d2);
-    if (mm::fabs(p1.d1) < gtol) return p1.cost <= p0.cost ? p1.alpha : (T)0;
+    if (mm::fabs(p1.d1) < gtol) return (robust || p1.cost <= p0.cost) ? p1.alpha : (T)0;
     if ((p1.d1 > 0) != (p2.d1 > 0)) { bracket = true; break; }
   }
-  if (!bracket) return p1.cost < p0.cost ? p1.alpha : (T)0;
+  if (!bracket) return ((robust && p1.d1 <= 0 && p1.alpha > 0) || p1.cost < p0.cost) ? p1.alpha : (T)0;
   // bracketed refinement: safeguarded Newton
   LsPoint<T> lo = p1.d1 < 0 ? p1 : p2, hi = p1.d1 < 0 ? p2 : p1;
   while (iter < m.ls_iterations) {
@@ -1071,8 +1083,12 @@ T line_search(const Model<T>& m, const Data<T>& d, const SolverCtx<T>& s, const 
     if (!(a > amin && a < amax)) a = (T)0.5 * (lo.alpha + hi.alpha);
     if (a == lo.alpha || a == hi.alpha) break;
     LsPoint<T> pm = ls_eval(m, d, s, qg, a);
-    if (mm::fabs(pm.d1) < gtol) return pm.cost <= p0.cost ? pm.alpha : (T)0;
+    if (mm::fabs(pm.d1) < gtol) return (robust || pm.cost <= p0.cost) ? pm.alpha : (T)0;
     if (pm.d1 < 0) lo = pm; else hi = pm;
+  }
+  if (robust) {   // bracket closed to adjacent values: the descending end is a guaranteed improvement
+    if (lo.alpha > 0) return lo.alpha;
+    return hi.cost < p0.cost ? hi.alpha : (T)0;
   }
   const LsPoint<T>& best = lo.cost < hi.cost ? lo : hi;
   return best.cost < p0.cost ? best.alpha : (T)0;
@@ -1130,6 +1146,8 @@ void solve_constraints(const Model<T>& m, Data<T>& d) {
   };
   s.cost = total_cost(d.qacc, true);
   gradient_and_direction();
+  T prev_gradient = std::numeric_limits<T>::max();
+  int stalls = 0;
   for (int iter = 0; iter < m.iterations; iter++) {
     mulM(s.Mv, s.search);
     mulJ(s.Jv, s.search);
@@ -1149,8 +1167,24 @@ void solve_constraints(const Model<T>& m, Data<T>& d) {
     for (int i = 0; i < nv; i++) gn += s.grad[i] * s.grad[i];
     T improvement = (old - s.cost) / scale_inv, gradient = mm::sqrt(gn) / scale_inv;
     const T tol = mm::max(m.tolerance, kTolFloor<T>());
-    if (improvement < tol || gradient < tol) break;
+    if (sizeof(T) == 4) {
+      // reduced precision: a cost decrease below the rounding of the cost itself is not evidence of convergence
+      // (the gradient can still be 1e4 x tol there); such an iteration only stops the solver when the gradient no
+      // longer shrinks.  Resolvable improvements follow the published rule.
+      const bool resolvable = mm::fabs(old - s.cost) > 16 * mm::eps<T>() * mm::fabs(s.cost);
+      // rounding floor of the gradient itself: eps x the magnitude of the terms it is the difference of
+      T gabs = 0;
+      for (int i = 0; i < nv; i++) { T a = mm::fabs(s.Ma[i]) + mm::fabs(d.qfrc_smooth[i]) + mm::fabs(s.Ma[i] - d.qfrc_smooth[i] - s.grad[i]); gabs += a * a; }
+      const T gfloor = (T)kGradFloor * mm::eps<T>() * mm::sqrt(gabs) / scale_inv;
+      if (gradient < mm::max(tol, gfloor)) break;
+      // a (near) full Newton step that fails to shrink the gradient is the rounding floor; a short step is a kink
+      // crossing (cone / friction-loss zone change) and the next step is a full one - allow a few of those
+      if (resolvable) { if (improvement < tol) break; stalls = 0; }
+      else if (gradient > (T)0.5 * prev_gradient && (alpha > (T)0.5 || ++stalls >= 3)) break;
+      prev_gradient = gradient;
+    } else if (improvement < tol || gradient < tol) break;
   }
+  solver_hist()[std::min(d.solver_niter, 63)]++;
   for (int i = 0; i < nv; i++) {
     T a = 0;
     for (int r = 0; r < ne; r++) a += d.efc_J[r * nv + i] * d.efc_force[r];

@@ -108,6 +108,25 @@ class Oracle:
                                       g("states"), g("actions"), g("times"), g("residual"), g("costs"), g("trace"))
         return o
 
+    def step_batch(self, qpos, qvel, ctrl, mocap, times, warmstart=None, nthreads=1):
+        """B independent mj_steps from given states (teacher-forced per-step parity)."""
+        m = self.m
+        q, v, u, mc, t, ws = _d(qpos), _d(qvel), _d(ctrl), _d(mocap), _d(times), _d(warmstart)
+        B = q.shape[0]
+        o = dict(qacc=np.zeros((B, m.nv)), next_qpos=np.zeros((B, m.nq)), next_qvel=np.zeros((B, m.nv)),
+                 residual=np.zeros((B, max(m.task_num_residual, 1))), cost=np.zeros(B))
+        counts = np.zeros((B, 4), np.int32)
+        lib().oracle_step_batch(self.h, B, _p(q), _p(v), _p(u), _p(ws), _p(mc), _p(t), int(nthreads), _p(o["qacc"]),
+                                _p(o["next_qpos"]), _p(o["next_qvel"]), _p(o["residual"]), _p(o["cost"]),
+                                counts.ctypes.data_as(C.POINTER(C.c_int)))
+        o.update(ncon=counts[:, 0], nefc=counts[:, 1], niter=counts[:, 2], warning=counts[:, 3])
+        return o
+
+    def solver_hist(self, reset=True):
+        h = (C.c_long * 64)()
+        lib().oracle_solver_hist(h, int(reset))
+        return np.array(h[:])
+
     def forward_debug(self, qpos, qvel, ctrl, mocap, time=0.0, warmstart=None):
         m = self.m
         o = dict(qacc=np.zeros(m.nv), qM=np.zeros((m.nv, m.nv)), qfrc_bias=np.zeros(m.nv), qfrc_smooth=np.zeros(m.nv),

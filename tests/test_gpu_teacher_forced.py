@@ -1,0 +1,157 @@
+"""GPU: parity at BASELINE sizes without the chaos excuse.
+
+Teacher-forced per-step check (config 2, Quadruped PS 256 x 64, and config 3's per-GPU share of Humanoid Track): every
+(state, action, time) of the fp64 oracle's own trajectories is advanced by ONE device mj_step through
+mjpc_b200_step_batch - the same kernel instance the rollout runs - and compared with the oracle's next state, residual
+and cost.  A single step from an identical state cannot diverge through contact make/break history, so every miss
+beyond the fp32 bounds below is a bug.  The same steps through the oracle's fp32 instantiation give the yardstick: two
+implementations of the same fp32 arithmetic.
+
+Stated fp32 bounds for one step (qvel error in rad/s or m/s; |qacc| reaches 500 in these states, dt = 0.01):
+    median <= 2e-5, 99th percentile <= 6e-4, maximum <= 5e-3, and device percentiles within 3x the fp32 oracle's;
+    identical contact / constraint-row counts; residual 2e-4 absolute; per-step cost 2e-5 relative.
+
+Return parity at full size: <= 1e-4 relative vs the fp64 oracle for EVERY candidate on which the fp32 and fp64
+oracles agree to 1e-4 themselves, and the same argmin (trajectory.cc:141-202 is the loop being matched).
+"""
+import numpy as np
+import pytest
+
+from conftest import get_model, mocap_of
+
+pytestmark = pytest.mark.gpu
+
+
+def _steady_state_inputs(m, N, H, burn=12):
+    """bench.py's input recipe: nominal = the sampling planner's policy after `burn` iterations on the fp64 oracle."""
+    import bench
+    from mujoco_mpc_b200.planner import SamplingPlanner, candidate_knots
+    be = bench.OracleBackend(m, 8)
+    state = np.concatenate([m.key_qpos[0], np.zeros(m.nv)])
+    pl = SamplingPlanner(m, be, num_trajectory=64, horizon=H, seed=0x5EED)
+    pl.reset(); pl.set_state(state, 0.0, mocap_of(m))
+    for _ in range(burn):
+        pl.optimize_policy()
+    pl.make_candidates()
+    knots = candidate_knots(pl.values, pl.sigma, pl.ctrlrange, burn, N, seed=pl.seed).astype(np.float32)
+    return state, mocap_of(m), knots, pl.times.copy()
+
+
+def _pct(e):
+    return float(np.median(e)), float(np.percentile(e, 99)), float(e.max())
+
+
+@pytest.fixture(scope="module")
+def quad_case():
+    from mujoco_mpc_b200 import build
+    from mujoco_mpc_b200.blob import to_blob
+    from mujoco_mpc_b200.engine import Engine
+    from oracle import pyoracle
+    build.build(); pyoracle.build()
+    m = get_model("quadruped")
+    N, H = 256, 64
+    state, mocap, knots, kt = _steady_state_inputs(m, N, H)
+    o64, o32 = pyoracle.Oracle(to_blob(m), m, 64), pyoracle.Oracle(to_blob(m), m, 32)
+    r64 = o64.rollout_spline(state, 0.0, mocap, knots, kt, 2, H, nthreads=8, full=True)
+    e = Engine(m, N, H)
+    yield dict(m=m, N=N, H=H, state=state, mocap=mocap, knots=knots, kt=kt, o64=o64, o32=o32, r64=r64, e=e)
+    e.close()
+
+
+def test_teacher_forced_steps_quadruped_256x64(quad_case):
+    c = quad_case
+    m, N, H, r = c["m"], c["N"], c["H"], c["r64"]
+    nq = m.nq
+    S = r["states"][:, : H - 1].reshape(-1, nq + m.nv); U = r["actions"][:, : H - 1].reshape(-1, m.nu)
+    T = r["times"][:, : H - 1].reshape(-1)
+    ref = c["o64"].step_batch(S[:, :nq], S[:, nq:], U, c["mocap"], T, nthreads=8)
+    f32 = c["o32"].step_batch(S[:, :nq], S[:, nq:], U, c["mocap"], T, nthreads=8)
+    dev = c["e"].step_batch(S[:, :nq], S[:, nq:], U, c["mocap"], T)
+    assert c["e"].last_kernel_static, "the static instance (the one the bench runs) must be the one under test"
+    # the oracle's batched step reproduces its own rollout (warm start differs: solver tolerance only)
+    assert np.abs(ref["next_qvel"] - r["states"][:, 1:, nq:].reshape(-1, m.nv)).max() < 1e-5
+    assert (dev["ncon"] == ref["ncon"]).all() and (dev["nefc"] == ref["nefc"]).all() and not dev["warning"].any()
+    ev = np.abs(dev["next_qvel"] - ref["next_qvel"]).max(1); ev32 = np.abs(f32["next_qvel"] - ref["next_qvel"]).max(1)
+    eq = np.abs(dev["next_qpos"] - ref["next_qpos"]).max(1)
+    print("teacher-forced %d steps: device qvel err median %.2e p99 %.2e max %.2e | fp32 oracle %.2e %.2e %.2e | "
+          "Newton iterations device %.2f fp32 oracle %.2f fp64 oracle %.2f" %
+          ((len(ev),) + _pct(ev) + _pct(ev32) + (dev["niter"].mean(), f32["niter"].mean(), ref["niter"].mean())))
+    p50, p99, mx = _pct(ev)
+    q50, q99, qmx = _pct(ev32)
+    assert p50 <= 2e-5 and p99 <= 6e-4 and mx <= 5e-3
+    assert p50 <= 3 * q50 and p99 <= 3 * q99 and mx <= 3 * max(qmx, 1e-3)
+    assert eq.max() <= 1e-5 + 0.01 * mx * 1.01 + 2e-6       # positions integrate the velocity error over one dt
+    er = np.abs(dev["residual"] - ref["residual"]).max(1)
+    assert er.max() <= 2e-4, er.max()
+    ec = np.abs(dev["cost"] - ref["cost"]) / np.maximum(np.abs(ref["cost"]), 1e-9)
+    assert ec.max() <= 2e-5, ec.max()
+
+
+def test_full_size_returns_quadruped_256x64(quad_case):
+    c = quad_case
+    m, N, H = c["m"], c["N"], c["H"]
+    ret, fail, order = c["e"].rollout_spline(c["state"], 0.0, c["mocap"], c["knots"], c["kt"], 2, H)
+    assert c["e"].last_kernel_static and not fail.any()
+    r64 = c["r64"]["returns"]
+    r32 = c["o32"].rollout_spline(c["state"], 0.0, c["mocap"], c["knots"], c["kt"], 2, H, nthreads=8, full=False)["returns"]
+    rel = np.abs(ret - r64) / np.abs(r64)
+    floor = np.abs(r32 - r64) / np.abs(r64)
+    agree = floor <= 1e-4
+    print("256x64 returns vs fp64 oracle: max %.2e median %.2e, >1e-4: %d; fp32-vs-fp64 oracle max %.2e, >1e-4: %d" %
+          (rel.max(), np.median(rel), (rel > 1e-4).sum(), floor.max(), (~agree).sum()))
+    assert agree.sum() >= 0.95 * N            # the oracle precisions themselves must agree almost everywhere
+    assert (rel[agree] <= 1e-4).all(), np.sort(rel[agree])[-5:]
+    assert (rel > 1e-4).sum() <= (~agree).sum()
+    assert int(order[0]) == int(np.argmin(r64))
+    tr = c["e"].fetch_all()
+    np.testing.assert_allclose(tr["actions"], c["r64"]["actions"], atol=2e-5)
+    # the whole 64-step state trajectories stay together, not only the returns
+    es = np.abs(tr["states"][agree] - c["r64"]["states"][agree]).max()
+    assert es < 2e-2, es
+
+
+def test_teacher_forced_steps_humanoid_track_128x128():
+    """config 3's per-GPU share (128 of 1024 candidates x 128 steps) on the reference's own keyframes."""
+    from mujoco_mpc_b200.blob import to_blob
+    from mujoco_mpc_b200.engine import Engine
+    from oracle import pyoracle
+    m = get_model("humanoid_track")
+    N, H, P = 128, 128, 16
+    mocap = np.concatenate([m.key_mpos[0].reshape(-1, 3), np.tile([1.0, 0, 0, 0], (m.nmocap, 1))], 1).reshape(-1)
+    state = np.concatenate([m.key_qpos[0], np.zeros(m.nv)])
+    kt = np.arange(P) * (H - 1) * m.opt_timestep / (P - 1)
+    knots = np.clip(0.15 * np.random.default_rng(0).standard_normal((N, P, m.nu)), -1, 1); knots[0] = 0
+    o64, o32 = pyoracle.Oracle(to_blob(m), m, 64), pyoracle.Oracle(to_blob(m), m, 32)
+    r = o64.rollout_spline(state, 0.0, mocap, knots, kt, 2, H, nthreads=8, full=True)
+    nq = m.nq
+    ok = ~r["failure"].astype(bool)
+    S = r["states"][ok, : H - 1].reshape(-1, nq + m.nv); U = r["actions"][ok, : H - 1].reshape(-1, m.nu)
+    T = r["times"][ok, : H - 1].reshape(-1)
+    ref = o64.step_batch(S[:, :nq], S[:, nq:], U, mocap, T, nthreads=8)
+    f32 = o32.step_batch(S[:, :nq], S[:, nq:], U, mocap, T, nthreads=8)
+    e = Engine(m, N, H)
+    try:
+        dev = e.step_batch(S[:, :nq], S[:, nq:], U, mocap, T)
+        assert e.last_kernel_static
+        same = (dev["ncon"] == ref["ncon"]) & (dev["nefc"] == ref["nefc"])
+        # a contact exactly at its margin may be detected on one side only (fp32 distance): allow a handful
+        assert (~same).sum() <= 1e-3 * len(same) + 2, (~same).sum()
+        ev = np.abs(dev["next_qvel"] - ref["next_qvel"]).max(1)[same]
+        ev32 = np.abs(f32["next_qvel"] - ref["next_qvel"]).max(1)[same]
+        print("humanoid-track teacher-forced %d steps: device qvel err median %.2e p99 %.2e max %.2e | fp32 oracle %.2e %.2e %.2e"
+              % ((len(ev),) + _pct(ev) + _pct(ev32)))
+        p50, p99, mx = _pct(ev); q50, q99, qmx = _pct(ev32)
+        assert p50 <= 5e-5 and p99 <= 2e-3 and mx <= 2e-2
+        assert p50 <= 3 * q50 + 1e-6 and p99 <= 3 * q99 + 1e-5
+        er = np.abs(dev["residual"] - ref["residual"]).max(1)[same]
+        assert er.max() <= 5e-4, er.max()
+        ret, fail, order = e.rollout_spline(state, 0.0, mocap, knots, kt, 2, H)
+        r32 = o32.rollout_spline(state, 0.0, mocap, knots, kt, 2, H, nthreads=8, full=False)["returns"]
+        rel = np.abs(ret - r["returns"]) / np.abs(r["returns"]); floor = np.abs(r32 - r["returns"]) / np.abs(r["returns"])
+        agree = (floor <= 1e-4) & ok
+        print("humanoid-track 128x128 returns: max rel %.2e, >1e-4: %d; oracle fp32-vs-fp64 >1e-4: %d" %
+              (rel[ok].max(), (rel[ok] > 1e-4).sum(), (floor[ok] > 1e-4).sum()))
+        assert (rel[agree] <= 1e-4).all(), np.sort(rel[agree])[-5:]
+        assert (fail.astype(bool) == r["failure"].astype(bool)).all()
+    finally:
+        e.close()
