@@ -87,6 +87,12 @@ int mjpc_b200_get_info(const mjpc_b200_t* h, mjpc_b200_info* info);
 
 int mjpc_b200_set_task(mjpc_b200_t* h, const mjpc_task_desc* task);
 
+/* MakeDifferentiable (mjpc/utilities.cc:60-75) for the following calls of this handle: on != 0 zeroes solimp[0] of every
+ * joint and geom in the model the kernels read, 0 restores the model's values - what Agent::PlanIteration does around
+ * OptimizePolicy for gradient-based planners (agent.cc:296-309,346-356; default on for iLQG / iLQS / Gradient,
+ * agent.cc:158-164).  The C++ iLQG planner switches it on unless iLQGSettings::differentiable is cleared. */
+int mjpc_b200_set_differentiable(mjpc_b200_t* h, int on);
+
 /* N candidate splines -> N rollouts of H steps. knots [N][P][nu]; knot_times [P] (absolute seconds).
  * candidate_offset: global index of this handle's first candidate (multi-GPU sharding; only used for bookkeeping).
  * returns [N], failure [N]; order [N] = candidate indices sorted by return (ties: lower index first), may be NULL. */
@@ -115,11 +121,17 @@ int mjpc_b200_fetch_trajectory(mjpc_b200_t* h, int candidate, float* states, flo
 int mjpc_b200_fetch_all(mjpc_b200_t* h, float* states, float* actions, double* times, float* residual,
                         float* costs, float* trace);
 
-/* Finite-difference transition / residual Jacobians along a trajectory (one-sided, step `tol`).
- * x [H][dim_state], u [H][nu], t [H]; A [H][n][n], B [H][n][nu], C [H][nr][n], D [H][nr][nu], n = dim_dstate,
- * nr = num_residual (the rows CostDerivatives reads).  Row H-1 of A, B, D is left zero (model_derivatives.cc:89-93). */
+/* Finite-difference transition / residual Jacobians along a trajectory (ModelDerivatives::Compute,
+ * model_derivatives.cc:45-165).  x [H][dim_state], u [H][nu], t [H]; A [H][n][n], B [H][n][nu], C [H][nr][n],
+ * D [H][nr][nu], n = dim_dstate, nr = num_residual (the rows CostDerivatives reads).
+ *   skip  derivative_skip: only every (skip+1)-th step plus H-2 and H-1 is differentiated, the rest is linearly
+ *         interpolated between its evaluated neighbours (model_derivatives.cc:56-72,109-164); 0 = every step
+ *   tol   finite-difference step (ilqg/settings.h:23, reference default 1e-6 in double; fp32 wants ~1e-3)
+ *   mode  0 one-sided, 1 centred (ilqg/settings.h:24 fd_mode -> mjd_transitionFD flg_centered)
+ * Row H-1 of A, B, D is left zero (model_derivatives.cc:89-93). */
 int mjpc_b200_model_derivatives(mjpc_b200_t* h, const float* x, const float* u, const double* t,
-                                const float* mocap, int H, float tol, float* A, float* B, float* C, float* D);
+                                const float* mocap, int H, int skip, float tol, int mode, float* A, float* B,
+                                float* C, float* D);
 
 /* Gauss-Newton cost derivatives. residual [H][nr], C, D as above -> cx [H][n], cu [H][nu], cxx [H][n][n],
  * cuu [H][nu][nu], cxu [H][n][nu]. */
@@ -172,6 +184,27 @@ int mjpc_b200_upload_spline_inputs(mjpc_b200_t* h, const float* state, double ti
 int mjpc_b200_launch_resident(mjpc_b200_t* h);          /* async on the engine stream */
 int mjpc_b200_sync(mjpc_b200_t* h);
 int mjpc_b200_read_returns(mjpc_b200_t* h, float* returns, uint8_t* failure, int* order);
+/* ---- Multi-GPU: ONE planning problem, its candidates sharded over the ranks of an NCCL communicator owned by the
+ * handle (one process per GPU).  Rank g owns the contiguous candidate range [g*N/G, (g+1)*N/G) (the first N % G ranks
+ * one more); candidate 0, the un-noised nominal (sampling/planner.cc:374), lives on rank 0.  The single exchange per
+ * planning iteration - per-candidate returns + failure flags - is one ncclAllGather enqueued on the engine stream
+ * behind the rollout kernel; ranking runs on the device on the gathered vector, so every rank sees the same
+ * returns / failure / order for all N candidates (north_star: "a single NCCL all-reduce of per-candidate returns").
+ * NCCL is bound with dlopen("libnccl.so.2") at the first call; without it these return MJPC_B200_ERR_UNSUPPORTED.
+ *   comm_unique_id: rank 0 generates the 128-byte ncclUniqueId, the caller distributes it (MPI / torch.distributed / file)
+ *   comm_init:      collective over all ranks (ncclCommInitRank)                                                     */
+int mjpc_b200_comm_unique_id(void* out, size_t nbytes);
+int mjpc_b200_comm_init(mjpc_b200_t* h, int nranks, int rank, const void* unique_id, size_t nbytes);
+int mjpc_b200_comm_info(const mjpc_b200_t* h, int* nranks, int* rank);
+/* Same arguments on every rank (knots [N][P][nu] for ALL candidates; inputs are replicated, a few KB).  N may be up to
+ * nranks * max_candidates.  returns [N], failure [N], order [N] are global and identical on every rank. */
+int mjpc_b200_rollout_spline_sharded(mjpc_b200_t* h, const float* state, double time, const float* mocap,
+                                     const float* userdata, const float* knots, const double* knot_times, int interp,
+                                     int P, int N, int H, float* returns, uint8_t* failure, int* order);
+/* Trajectory of GLOBAL candidate index on every rank (ncclBroadcast from its owner); collective. */
+int mjpc_b200_fetch_trajectory_sharded(mjpc_b200_t* h, int candidate, float* states, float* actions, double* times,
+                                       float* residual, float* costs, float* trace);
+
 /* Raw stream / device pointers for multi-GPU plumbing (NCCL all-gather of returns runs on this stream). */
 void* mjpc_b200_stream(mjpc_b200_t* h);
 float* mjpc_b200_device_returns(mjpc_b200_t* h);

@@ -792,7 +792,7 @@ __device__ __noinline__ void k_make_constraint(Ctx& c) {
         if (chnum[b1] == 0 && chnum[b2] > 0) { side = 1; mb = b2; }
         else if (chnum[b2] == 0 && chnum[b1] > 0) { side = -1; mb = b1; }
       }
-      cside[ci] = side; cmb[ci] = mb;
+      cside[ci] = side; cmb[ci] = (side != 0 && cadr[ci] >= 0) ? mb : -1;   // -1: not part of the composite form
     }
     __syncwarp();
     const int r0 = M.nfloss + c.nlim;
@@ -805,7 +805,7 @@ __device__ __noinline__ void k_make_constraint(Ctx& c) {
         const int side = cside[ci];
         if (side == 0) dense = true;
         else {
-          const int k = i - cadr[ci], nrows = cdim[ci], mb = cmb[ci];
+          const int k = i - cadr[ci], nrows = cdim[ci], mb = cmb[ci];   // rows exist only for contacts with cadr >= 0
           const float* fr = cframe + 9 * ci;
           float off[3];
           for (int q = 0; q < 3; q++) off[q] = cpos[3 * ci + q] - scom[3 * rootid[mb] + q];
@@ -1113,7 +1113,6 @@ __device__ __forceinline__ void hessian_dense_reg(Ctx& c) {
   //      sum_rows (weights) J^T J = cdof_r^T ( sum over contacts below body(r) of W_c ) cdof_s,  W_c (6x6) = sum_a hw_a
   //      w_a w_a^T + cone terms - the same subtree-composite structure as the joint-space inertia itself (k_crb).
   float* Wc = DF(efc_blk);        // [ncon][21] lower triangles (the generic path's block scratch, unused here)
-  float* wsub = DF(wsub);         // [nbody][36]
   float* g = DF(dofbuf);          // [nv][6]   (k_crb's scratch, free after qM was formed)
   const float* W6 = DF(efc_w);
   {
@@ -1122,55 +1121,62 @@ __device__ __forceinline__ void hessian_dense_reg(Ctx& c) {
     for (int w = lane; w < ncon * 6; w += 32) {
       const int ci = w / 6, p = w - 6 * ci;
       const int a0 = cadr[ci];
-      if (a0 < 0 || cside[ci] == 0 || state[a0] != STATE_CONE) continue;
-      const int dim = cdim[ci];
-      const float* q = xw + 36 * ci;
       float v = 0.f, u = 0.f;
-      FOR_DIM(a, 0, dim) { const float wa = W6[6 * (a0 + a) + p]; v += q[a] * wa; u += q[6 + a] * wa; }
-      xwm[36 * ci + 14 + p] = v; xwm[36 * ci + 20 + p] = u;
+      if (a0 >= 0 && cside[ci] != 0 && state[a0] == STATE_CONE) {
+        const int dim = cdim[ci];
+        const float* q = xw + 36 * ci;
+        FOR_DIM(a, 0, dim) { const float wa = W6[6 * (a0 + a) + p]; v += q[a] * wa; u += q[6 + a] * wa; }
+      }
+      xwm[36 * ci + 14 + p] = v; xwm[36 * ci + 20 + p] = u;   // zeros for non-cone contacts: read (times 0) below
     }
     __syncwarp();
-    for (int w = lane; w < ncon * 21; w += 32) {
+    // (straight-line: clamped indices, weights selected to zero instead of branches - every taken branch costs a
+    // reconvergence (BSSY/BSYNC ~30 cycles) with a single resident warp)
+    constexpr int kMaxRows = 10;   // pyramidal condim 6; elliptic contacts have <= 6 rows
+    const bool pyr = M.cone == CONE_PYRAMIDAL;
+    const int nwork = ncon * 21;
+    for (int base = 0; base < nwork; base += 32) {
+      const int w = min(base + lane, nwork - 1);
       const int ci = w / 21, e = w - 21 * ci;
-      int p = e < 1 ? 0 : e < 3 ? 1 : e < 6 ? 2 : e < 10 ? 3 : e < 15 ? 4 : 5;
+      const int p = (e >= 1) + (e >= 3) + (e >= 6) + (e >= 10) + (e >= 15);
       const int q2 = e - p * (p + 1) / 2;
-      const int a0 = cadr[ci];
+      const int a0r = cadr[ci];
+      const bool on = a0r >= 0 && cside[ci] != 0;
+      const int a0 = max(a0r, 0);
+      const int nrows = on ? cdim[ci] : 0;
       float acc = 0.f;
-      if (a0 >= 0 && cside[ci] != 0) {
-        const int nrows = cdim[ci];
-        for (int a = 0; a < nrows; a++) acc += hw[a0 + a] * W6[6 * (a0 + a) + p] * W6[6 * (a0 + a) + q2];
-        if (state[a0] == STATE_CONE) {
-          const float* q = xw + 36 * ci;
-          acc += q[12] * q[14 + p] * q[14 + q2] + q[13] * q[20 + p] * q[20 + q2];
-        }
+#pragma unroll
+      for (int a = 0; a < kMaxRows; a++) {
+        if (a >= 6 && !pyr) break;                       // compile-time for a static spec
+        const int r = min(a0 + a, M.maxefc - 1);
+        const float t = hw[r] * W6[6 * r + p] * W6[6 * r + q2];   // may read rows of other constraints: selected away
+        acc += a < nrows ? t : 0.f;                                // (a select, never a multiply by zero: NaN-safe)
       }
-      Wc[w] = acc;
+      const float* q = xw + 36 * ci;
+      const float tc = q[12] * q[14 + p] * q[14 + q2] + q[13] * q[20 + p] * q[20 + q2];
+      acc += (on && state[a0] == STATE_CONE) ? tc : 0.f;
+      if (base + lane < nwork) Wc[w] = acc;
     }
     __syncwarp();
-    const int *subend = MI(body_subtreeend), *cmb = DI(con_mbody);
-    const int nb = M.nbody;
-    for (int w = lane; w < nb * 21; w += 32) {
-      const int b = w / 21, e = w - 21 * b;
-      int p = e < 1 ? 0 : e < 3 ? 1 : e < 6 ? 2 : e < 10 ? 3 : e < 15 ? 4 : 5;
-      const int q2 = e - p * (p + 1) / 2;
-      const int se = subend[b];
-      float acc = 0.f;
-      for (int ci = 0; ci < ncon; ci++) {
-        const int mb = cmb[ci];
-        if (cside[ci] != 0 && cadr[ci] >= 0 && mb >= b && mb < se) acc += Wc[21 * ci + e];
-      }
-      wsub[36 * b + 6 * p + q2] = acc; wsub[36 * b + 6 * q2 + p] = acc;
-    }
-    __syncwarp();
-    const int* dbody = MI(dof_bodyid);
+    // g_i = (sum of W_c over the contacts on bodies in the subtree of dof i's body) cdof_i, one (dof, component) per lane
+    const int *subend = MI(body_subtreeend), *cmb = DI(con_mbody), *dbody = MI(dof_bodyid);
     const float* cdof = DF(cdof);
     for (int w = lane; w < NV * 6; w += 32) {
       const int i = w / 6, k = w - 6 * i;
-      const float* Wb = wsub + 36 * dbody[i] + 6 * k;
-      const float* cd = cdof + 6 * i;
-      float a = 0.f;
+      const int b = dbody[i], se = subend[b];
+      int idx[6];
+      float cd[6];
 #pragma unroll
-      for (int l = 0; l < 6; l++) a += Wb[l] * cd[l];
+      for (int l = 0; l < 6; l++) { idx[l] = k >= l ? k * (k + 1) / 2 + l : l * (l + 1) / 2 + k; cd[l] = cdof[6 * i + l]; }
+      float a = 0.f;
+      for (int ci = 0; ci < ncon; ci++) {
+        const int mb = cmb[ci];                       // -1 for two-sided / dropped contacts
+        const float* Wk = Wc + 21 * ci;
+        float d = 0.f;
+#pragma unroll
+        for (int l = 0; l < 6; l++) d += Wk[idx[l]] * cd[l];
+        a += (mb >= b && mb < se) ? d : 0.f;
+      }
       g[w] = a;
     }
     __syncwarp();
@@ -1193,8 +1199,7 @@ __device__ __forceinline__ void hessian_dense_reg(Ctx& c) {
       if (er[q] == es[q]) {
         const int fr = frow[r];
         if (fr >= 0) a += hw[fr];
-        for (int k = M.nfloss; k < M.nfloss + c.nlim; k++)
-          if (edof[k] == r) a += hw[k];
+        for (int k = M.nfloss; k < M.nfloss + c.nlim; k++) { const float hk = hw[k]; a += edof[k] == r ? hk : 0.f; }
       }
       acc[q] = a;
     }
@@ -1246,9 +1251,12 @@ __device__ __forceinline__ float mat_row_dot(const float* Mrow, const float* v) 
 // dense-row variants of J*v and J^T*force for compile-time NV (vectorised, fully unrolled)
 template <class SP, int NV>
 __device__ __forceinline__ float row_dot_dense(Ctx& c, int row, int nsimple, const float* v) {
-  if (row < nsimple) return DF(efc_sgn)[row] * v[DI(efc_dof)[row]];
   constexpr int NVP = (NV + 3) / 4 * 4;
-  return mat_row_dot<NV>(DF(efc_Jd) + row * NVP, v);   // NVP is a multiple of 4: rows are 16-byte aligned
+  // both forms are evaluated and one is selected (no divergent region): simple rows touch one dof, contact rows are
+  // dense; the dense rows of simple constraints are never written, hence the select and not a sum
+  const float simple = DF(efc_sgn)[row] * v[row < nsimple ? DI(efc_dof)[row] : 0];   // efc_dof is only written for simple rows
+  const float dense = mat_row_dot<NV>(DF(efc_Jd) + row * NVP, v);   // NVP is a multiple of 4: rows are 16-byte aligned
+  return row < nsimple ? simple : dense;
 }
 template <class SP, int NV>
 __device__ __forceinline__ void jt_force_dense(Ctx& c, float* out) {
@@ -1258,14 +1266,15 @@ __device__ __forceinline__ void jt_force_dense(Ctx& c, float* out) {
   const float *Jd = DF(efc_Jd), *force = DF(efc_force), *esgn = DF(efc_sgn);
   const int *frow = MI(floss_row), *edof = DI(efc_dof);
   const int nf = M.nfloss, nl = c.nlim, ne = c.nefc;
-  if (lane < NV) {
+  {
+    const int li = lane < NV ? lane : NV - 1;   // all lanes run, clamped; the store is predicated
     float a = 0.f;
-    const int fr = frow[lane];
-    if (fr >= 0) a += force[fr];
-    for (int q = nf; q < nf + nl; q++)
-      if (edof[q] == lane) a += esgn[q] * force[q];
-    for (int row = nf + nl; row < ne; row++) a += Jd[row * NVP + lane] * force[row];
-    out[lane] = a;
+    const int fr = frow[li];
+    const float ff = force[max(fr, 0)];
+    a += fr >= 0 ? ff : 0.f;
+    for (int q = nf; q < nf + nl; q++) { const float t = esgn[q] * force[q]; a += edof[q] == li ? t : 0.f; }
+    for (int row = nf + nl; row < ne; row++) a += Jd[row * NVP + li] * force[row];
+    if (lane < NV) out[lane] = a;
   }
   __syncwarp();
 }
@@ -1302,19 +1311,35 @@ __device__ __noinline__ float k_total_cost(Ctx& c, const float* qacc, bool hess,
   if (step != 0.f) {
     // qacc moved by step * search: M qacc and J qacc - aref follow from the products the line search already formed
     const float *Mv = DF(Mv), *Jv = DF(efc_Jv);
-    for (int i = lane; i < nv; i += 32) {
+    for (int b0 = 0; b0 < nv; b0 += 32) {
+      const int i = min(b0 + lane, nv - 1);
+      const bool on = b0 + lane < nv;
       const float a = Ma[i] + step * Mv[i];
-      Ma[i] = a;
-      g += (a - smooth[i]) * (qacc[i] - qas[i]);
+      __syncwarp();
+      if (on) Ma[i] = a;
+      g += on ? (a - smooth[i]) * (qacc[i] - qas[i]) : 0.f;
     }
-    for (int i = lane; i < c.nefc; i += 32) jar[i] += step * Jv[i];
+    const int ne = c.nefc;
+    for (int b0 = 0; b0 < ne; b0 += 32) {
+      const int i = min(b0 + lane, ne - 1);
+      const float v = jar[i] + step * Jv[i];
+      __syncwarp();
+      if (b0 + lane < ne) jar[i] = v;
+    }
   } else {
-    for (int i = lane; i < nv; i += 32) {
+    for (int b0 = 0; b0 < nv; b0 += 32) {
+      const int i = min(b0 + lane, nv - 1);
+      const bool on = b0 + lane < nv;
       const float a = m_row_dot<SP>(qM, i, qacc, nv);
-      Ma[i] = a;
-      g += (a - smooth[i]) * (qacc[i] - qas[i]);
+      if (on) Ma[i] = a;
+      g += on ? (a - smooth[i]) * (qacc[i] - qas[i]) : 0.f;
     }
-    for (int i = lane; i < c.nefc; i += 32) jar[i] = j_row_dot<SP>(c, i, nsimple, qacc, nv) - aref[i];
+    const int ne = c.nefc;
+    for (int b0 = 0; b0 < ne; b0 += 32) {
+      const int i = min(b0 + lane, ne - 1);
+      const float v = j_row_dot<SP>(c, i, nsimple, qacc, nv) - aref[i];
+      if (b0 + lane < ne) jar[i] = v;
+    }
   }
   g = 0.5f * warp_sum(g);
   __syncwarp();
@@ -1552,35 +1577,36 @@ __device__ __forceinline__ LsItem ls_load_item(Ctx& c) {
   return it;
 }
 
+// Straight-line evaluation (selects, no branches): the three constraint kinds sit on different lanes, so a branchy
+// version executes every path anyway and pays a reconvergence per path on top.  Divisions by Tn = 0 produce inf / NaN
+// in lanes whose result is then selected away (never multiplied by zero).
 __device__ __forceinline__ LsPoint ls_eval_cached(const LsItem& it, float g0, float g1, float g2, float alpha) {
-  float cost = 0, d1 = 0, d2 = 0;
-  if (it.kind == 1) {
-    const float x = it.x0 + alpha * it.jv;
-    if (x <= -it.rf) { cost = it.f * (-0.5f * it.rf - x); d1 = -it.f * it.jv; }
-    else if (x >= it.rf) { cost = it.f * (-0.5f * it.rf + x); d1 = it.f * it.jv; }
-    else { cost = 0.5f * it.D * x * x; d1 = it.D * x * it.jv; d2 = it.D * it.jv * it.jv; }
-  } else if (it.kind == 2) {
-    const float x = it.x0 + alpha * it.jv;
-    if (x < 0) { cost = 0.5f * it.D * x * x; d1 = it.D * x * it.jv; d2 = it.D * it.jv * it.jv; }
-  } else if (it.kind == 3) {
-    const float mu = it.mu;
-    const float N = it.U0 + alpha * it.V0;
-    const float Tsqr = it.UU + alpha * (2 * it.UV + alpha * it.VV);
-    const float Tn = Tsqr <= 0 ? 0.f : sqrtf(Tsqr);
-    if (N >= mu * Tn || (Tn <= 0 && N >= 0)) {
-    } else if (mu * N + Tn <= 0 || (Tn <= 0 && N < 0)) {
-      cost = 0.5f * (it.Q0 + alpha * (2 * it.Q1 + alpha * it.Q2));
-      d1 = it.Q1 + alpha * it.Q2;
-      d2 = it.Q2;
-    } else {
-      const float N1 = it.V0, T1 = (it.UV + alpha * it.VV) / Tn;
-      const float T2 = it.VV / Tn - (it.UV + alpha * it.VV) * T1 / (Tn * Tn);
-      const float NmT = N - mu * Tn;
-      cost = 0.5f * it.Dm * NmT * NmT;
-      d1 = it.Dm * NmT * (N1 - mu * T1);
-      d2 = it.Dm * ((N1 - mu * T1) * (N1 - mu * T1) + NmT * (-mu * T2));
-    }
-  }
+  // kinds 1, 2: scalar row
+  const float x = it.x0 + alpha * it.jv;
+  const float qc = 0.5f * it.D * x * x, qd1 = it.D * x * it.jv, qd2 = it.D * it.jv * it.jv;
+  const bool neg = x <= -it.rf, pos = x >= it.rf;
+  const float c1 = neg ? it.f * (-0.5f * it.rf - x) : pos ? it.f * (-0.5f * it.rf + x) : qc;
+  const float d11 = neg ? -it.f * it.jv : pos ? it.f * it.jv : qd1;
+  const float d21 = (neg || pos) ? 0.f : qd2;
+  const bool act2 = x < 0.f;
+  // kind 3: elliptic cone
+  const float mu = it.mu;
+  const float N = it.U0 + alpha * it.V0;
+  const float Tsqr = it.UU + alpha * (2 * it.UV + alpha * it.VV);
+  const float Tn = Tsqr <= 0 ? 0.f : sqrtf(Tsqr);
+  const bool top = N >= mu * Tn || (Tn <= 0 && N >= 0);
+  const bool bottom = !top && (mu * N + Tn <= 0 || (Tn <= 0 && N < 0));
+  const float iT = 1.0f / Tn;
+  const float N1 = it.V0, T1 = (it.UV + alpha * it.VV) * iT;
+  const float T2 = it.VV * iT - (it.UV + alpha * it.VV) * T1 * iT * iT;
+  const float NmT = N - mu * Tn, s1 = N1 - mu * T1;
+  const float c3 = top ? 0.f : bottom ? 0.5f * (it.Q0 + alpha * (2 * it.Q1 + alpha * it.Q2)) : 0.5f * it.Dm * NmT * NmT;
+  const float d13 = top ? 0.f : bottom ? it.Q1 + alpha * it.Q2 : it.Dm * NmT * s1;
+  const float d23 = top ? 0.f : bottom ? it.Q2 : it.Dm * (s1 * s1 + NmT * (-mu * T2));
+  const int k = it.kind;
+  const float cost = k == 1 ? c1 : k == 2 ? (act2 ? qc : 0.f) : k == 3 ? c3 : 0.f;
+  const float d1 = k == 1 ? d11 : k == 2 ? (act2 ? qd1 : 0.f) : k == 3 ? d13 : 0.f;
+  const float d2 = k == 1 ? d21 : k == 2 ? (act2 ? qd2 : 0.f) : k == 3 ? d23 : 0.f;
   LsPoint p;
   p.alpha = alpha;
   p.cost = g0 + alpha * g1 + alpha * alpha * g2 + warp_sum(cost);
@@ -1682,6 +1708,7 @@ __device__ __noinline__ void k_solve(Ctx& c) {
   const int lane = c.lane, nv = M.nv, ne = c.nefc;
   float *qacc = DF(qacc), *qas = DF(qacc_smooth), *qws = DF(qacc_warmstart), *qfc = DF(qfrc_constraint);
   c.niter = 0;
+  // (lane loops below run on ALL lanes with a clamped index and predicated stores: no divergent regions)
   if (ne == 0) {
     for (int i = lane; i < nv; i += 32) { qacc[i] = qas[i]; qfc[i] = 0; }
     __syncwarp();
@@ -1694,7 +1721,7 @@ __device__ __noinline__ void k_solve(Ctx& c) {
     const float cs = k_total_cost<SP>(c, qas, false, &gauss);
     const float cw = k_total_cost<SP>(c, qws, true, &gauss);
     const bool warm = cw < cs;
-    for (int i = lane; i < nv; i += 32) qacc[i] = warm ? qws[i] : qas[i];
+    for (int b0 = 0; b0 < nv; b0 += 32) { const int i = min(b0 + lane, nv - 1); const float v = warm ? qws[i] : qas[i]; if (b0 + lane < nv) qacc[i] = v; }
     __syncwarp();
     cost = warm ? cw : k_total_cost<SP>(c, qacc, true, &gauss);
   } else {
@@ -1715,12 +1742,14 @@ __device__ __noinline__ void k_solve(Ctx& c) {
     jt_force_any<SP>(c, qfc, nv);
     qfc_current = true;
     float g2 = 0, ga = 0;
-    for (int i = lane; i < nv; i += 32) {
+    for (int b0 = 0; b0 < nv; b0 += 32) {
+      const int i = min(b0 + lane, nv - 1);
+      const bool on = b0 + lane < nv;
       const float a = Ma[i] - smooth[i] - qfc[i];
-      grad[i] = a;
-      g2 += a * a;
+      if (on) grad[i] = a;
+      g2 += on ? a * a : 0.f;
       const float m = fabsf(Ma[i]) + fabsf(smooth[i]) + fabsf(qfc[i]);
-      ga += m * m;
+      ga += on ? m * m : 0.f;
     }
     const float gnorm2 = warp_sum(g2), gabs2 = warp_sum(ga);
     __syncwarp();
@@ -1740,23 +1769,29 @@ __device__ __noinline__ void k_solve(Ctx& c) {
     // Newton direction: assemble + factorise the Hessian only now that another iteration is taken
     k_hessian<SP>(c);
     warp_chol_factor_solve<SP::kNV>(DF(qH), DF(hinv), search, grad, nv, lane);
-    for (int i = lane; i < nv; i += 32) search[i] = -search[i];
+    for (int b0 = 0; b0 < nv; b0 += 32) { const int i = min(b0 + lane, nv - 1); const float v = -search[i]; __syncwarp(); if (b0 + lane < nv) search[i] = v; }
     __syncwarp();
     float q1 = 0, q2 = 0, sn = 0;
-    for (int i = lane; i < nv; i += 32) {
-      float a = 0;
-      a = m_row_dot<SP>(qM, i, search, nv);
-      Mv[i] = a;
-      q1 += search[i] * (Ma[i] - smooth[i]);
-      q2 += 0.5f * search[i] * a;
-      sn += search[i] * search[i];
+    for (int b0 = 0; b0 < nv; b0 += 32) {
+      const int i = min(b0 + lane, nv - 1);
+      const bool on = b0 + lane < nv;
+      const float a = m_row_dot<SP>(qM, i, search, nv);
+      if (on) Mv[i] = a;
+      const float si = on ? search[i] : 0.f;
+      q1 += si * (Ma[i] - smooth[i]);
+      q2 += 0.5f * si * a;
+      sn += si * si;
     }
-    for (int i = lane; i < ne; i += 32) Jv[i] = j_row_dot<SP>(c, i, nsimple, search, nv);
+    for (int b0 = 0; b0 < ne; b0 += 32) {
+      const int i = min(b0 + lane, ne - 1);
+      const float v = j_row_dot<SP>(c, i, nsimple, search, nv);
+      if (b0 + lane < ne) Jv[i] = v;
+    }
     q1 = warp_sum(q1); q2 = warp_sum(q2); sn = sqrtf(warp_sum(sn));
     __syncwarp();
     alpha = k_line_search<SP>(c, gauss, q1, q2, sn, scale_inv);
     if (alpha == 0.f) break;
-    for (int i = lane; i < nv; i += 32) qacc[i] += alpha * search[i];
+    for (int b0 = 0; b0 < nv; b0 += 32) { const int i = min(b0 + lane, nv - 1); const float v = qacc[i] + alpha * search[i]; __syncwarp(); if (b0 + lane < nv) qacc[i] = v; }
     __syncwarp();
     old = cost;
     cost = k_total_cost<SP>(c, qacc, true, &gauss, alpha);

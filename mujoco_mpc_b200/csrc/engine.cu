@@ -3,6 +3,8 @@
 // kernels in rollout_kernels.cuh / ilqg_kernels.cuh.  There is deliberately NO CPU fallback: without a
 // usable CUDA device every entry point returns MJPC_B200_ERR_CUDA.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the NCCL entry points are bound with dlopen at comm_init (no link-time dependency)
 
 #include <algorithm>
 #include <cmath>
@@ -74,6 +76,20 @@ struct mjpc_b200 {
   unsigned noise_seed = 0;
   int last_static = 0;
   float last_ms = 0;
+  // multi-GPU: one NCCL communicator per handle; the per-iteration exchange (all-gather of returns + failure flags)
+  // is enqueued on the engine stream right behind the rollout kernel
+  ncclComm_t comm = nullptr;
+  int nranks = 1, rank = 0;
+  int totalN = 0, shard_lo = 0, shard_hi = 0;   // of the last sharded rollout
+  float *d_slot = nullptr, *d_gather = nullptr, *d_returns_all = nullptr;
+  unsigned char* d_failure_all = nullptr;
+  int* d_order_all = nullptr;
+  float* d_bcast = nullptr;
+  size_t bcast_floats = 0;
+  int maxTotal = 0;
+  // MakeDifferentiable (utilities.cc:60-75): the model's own solimp[0] values, and whether the pack currently holds 0
+  std::vector<float> jnt_solimp0, geom_solimp0;
+  int differentiable = 0;
   // resident-input launch description
   RolloutArgs resident;
   bool resident_ok = false;
@@ -175,6 +191,65 @@ int read_back(mjpc_b200* h, int N, float* returns, uint8_t* failure, int* order)
   return 0;
 }
 
+// ---- NCCL, bound at run time (dlopen): a process that already loaded an NCCL (PyTorch's) shares it by SONAME
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+NcclApi& nccl_api() {
+  static NcclApi api;
+  if (api.lib) return api;
+  api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!api.lib) api.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!api.lib) return api;
+#define BIND(field, name) api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.lib, name))
+  BIND(GetUniqueId, "ncclGetUniqueId"); BIND(CommInitRank, "ncclCommInitRank"); BIND(CommDestroy, "ncclCommDestroy");
+  BIND(AllGather, "ncclAllGather"); BIND(Broadcast, "ncclBroadcast"); BIND(GetErrorString, "ncclGetErrorString");
+#undef BIND
+  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.Broadcast && api.GetErrorString;
+  return api;
+}
+#define NCCL_TRY(expr)                                                                                     \
+  do {                                                                                                     \
+    ncclResult_t r_ = (expr);                                                                              \
+    if (r_ != ncclSuccess)                                                                                 \
+      return fail(MJPC_B200_ERR_CUDA, std::string(#expr) + ": " + nccl_api().GetErrorString(r_));          \
+  } while (0)
+
+// contiguous balanced candidate ranges: the first N % G ranks own one candidate more
+inline void shard_range(int N, int G, int r, int* lo, int* hi) {
+  const int base = N / G, rem = N % G;
+  *lo = r * base + std::min(r, rem);
+  *hi = *lo + base + (r < rem ? 1 : 0);
+}
+
+// gathered [G][width][2] (return, failure flag) -> compact returns[N], failure[N] in global candidate order
+__global__ void compact_gather_kernel(const float* __restrict__ gathered, int N, int G, int width, float* __restrict__ ret,
+                                      unsigned char* __restrict__ failure) {
+  const int base = N / G, rem = N % G;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    // owner of global candidate i under shard_range
+    int r = i < rem * (base + 1) ? i / (base + 1) : rem + (base ? (i - rem * (base + 1)) / base : 0);
+    const int lo = r * base + min(r, rem);
+    const float* src = gathered + ((size_t)r * width + (i - lo)) * 2;
+    ret[i] = src[0];
+    failure[i] = src[1] != 0.f ? 1 : 0;
+  }
+}
+__global__ void pack_slot_kernel(const float* __restrict__ ret, const unsigned char* __restrict__ failure, int n, int width,
+                                 float* __restrict__ slot) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < width; i += gridDim.x * blockDim.x) {
+    slot[2 * i] = i < n ? ret[i] : 3.0e38f;
+    slot[2 * i + 1] = i < n ? (float)failure[i] : 1.f;
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -212,6 +287,8 @@ int mjpc_b200_create(const mjpc_model_blob* model, int max_candidates, int max_h
     h->task_state = b.reals("task_state"); h->risk = b.r("task_risk");
   }
   h->time_idx = time_like_state(M.residual_id);
+  for (int i = 0; i < M.njnt; i++) h->jnt_solimp0.push_back(h->pack.f[M.fo[F_jnt_solimp] + 5 * i]);
+  for (int i = 0; i < M.ngeom; i++) h->geom_solimp0.push_back(h->pack.f[M.fo[F_geom_solimp] + 5 * i]);
   CUDA_TRY(cudaSetDevice(device));
   CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreate(&h->ev0));
@@ -270,6 +347,9 @@ void mjpc_b200_destroy(mjpc_b200_t* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->comm && nccl_api().ok) nccl_api().CommDestroy(h->comm);
+  void* mbufs[] = {h->d_slot, h->d_gather, h->d_returns_all, h->d_failure_all, h->d_order_all, h->d_bcast};
+  for (void* p : mbufs) if (p) cudaFree(p);
   void* bufs[] = {h->d_pack, h->d_state, h->d_mocap, h->d_task_state, h->d_knots, h->d_knot_times, h->d_unom, h->d_xnom,
                   h->d_tnom, h->d_gains, h->d_du, h->d_steps, h->d_states, h->d_actions, h->d_times, h->d_residual,
                   h->d_costs, h->d_trace, h->d_returns, h->d_failure, h->d_order, h->d_dbg, h->d_stats};
@@ -302,6 +382,22 @@ int mjpc_b200_set_task(mjpc_b200_t* h, const mjpc_task_desc* task) {
   if (task->parameters) h->parameters.assign(task->parameters, task->parameters + h->parameters.size());
   if (task->task_state) h->task_state.assign(task->task_state, task->task_state + h->task_state.size());
   h->risk = task->risk;
+  return upload_task(h);
+}
+
+// Agent::PlanIteration's MakeDifferentiable (agent.cc:296-309, utilities.cc:60-75): while on, every joint's and geom's
+// solimp[0] is 0 in the model the kernels read (contact pairs take their solimp from the geoms here); off restores the
+// model's own values (agent.cc:346-356).  Gradient-based planners (iLQG, iLQS, Gradient) plan with it on by default.
+int mjpc_b200_set_differentiable(mjpc_b200_t* h, int on) {
+  if (!h) return fail(MJPC_B200_ERR_BAD_ARGUMENT, "set_differentiable: null");
+  on = on ? 1 : 0;
+  if (on == h->differentiable) return 0;
+  const DevModel& M = h->pack.M;
+  std::vector<float>& f = h->pack.f;
+  for (int i = 0; i < M.njnt; i++) f[M.fo[F_jnt_solimp] + 5 * i] = on ? 0.f : h->jnt_solimp0[i];
+  for (int i = 0; i < M.ngeom; i++) f[M.fo[F_geom_solimp] + 5 * i] = on ? 0.f : h->geom_solimp0[i];
+  h->differentiable = on;
+  CUDA_TRY(cudaSetDevice(h->device));
   return upload_task(h);
 }
 
@@ -475,6 +571,123 @@ int mjpc_b200_step_debug(mjpc_b200_t* h, const float* qpos, const float* qvel, c
   return 0;
 }
 
+// ---- multi-GPU: one planning problem, candidates sharded over the ranks of an NCCL communicator
+int mjpc_b200_comm_unique_id(void* out, size_t nbytes) {
+  if (!out || nbytes < sizeof(ncclUniqueId)) return fail(MJPC_B200_ERR_BAD_ARGUMENT, "comm_unique_id: need 128 bytes");
+  NcclApi& api = nccl_api();
+  if (!api.ok) return fail(MJPC_B200_ERR_UNSUPPORTED, "libnccl.so.2 not found");
+  ncclUniqueId id;
+  NCCL_TRY(api.GetUniqueId(&id));
+  std::memcpy(out, &id, sizeof(id));
+  return 0;
+}
+
+int mjpc_b200_comm_init(mjpc_b200_t* h, int nranks, int rank, const void* unique_id, size_t nbytes) {
+  if (!h || nranks < 1 || rank < 0 || rank >= nranks || !unique_id || nbytes < sizeof(ncclUniqueId))
+    return fail(MJPC_B200_ERR_BAD_ARGUMENT, "comm_init: bad argument");
+  if (h->comm) return fail(MJPC_B200_ERR_BAD_ARGUMENT, "comm_init: communicator already initialised");
+  NcclApi& api = nccl_api();
+  if (!api.ok) return fail(MJPC_B200_ERR_UNSUPPORTED, "libnccl.so.2 not found");
+  CUDA_TRY(cudaSetDevice(h->device));
+  ncclUniqueId id;
+  std::memcpy(&id, unique_id, sizeof(id));
+  NCCL_TRY(api.CommInitRank(&h->comm, nranks, id, rank));
+  h->nranks = nranks; h->rank = rank;
+  h->maxTotal = nranks * h->maxN;
+  const DevModel& M = h->pack.M;
+  const size_t width = h->maxN;
+  CUDA_TRY(dalloc(&h->d_slot, 2 * width)); CUDA_TRY(dalloc(&h->d_gather, 2 * width * nranks));
+  CUDA_TRY(dalloc(&h->d_returns_all, (size_t)h->maxTotal)); CUDA_TRY(dalloc(&h->d_failure_all, (size_t)h->maxTotal));
+  CUDA_TRY(dalloc(&h->d_order_all, (size_t)h->maxTotal));
+  h->bcast_floats = (size_t)h->maxH * (M.nq + M.nv + M.nu + M.num_residual + 1 + 3 * M.num_trace + 2) + 16;
+  CUDA_TRY(dalloc(&h->d_bcast, h->bcast_floats));
+  return 0;
+}
+
+int mjpc_b200_comm_info(const mjpc_b200_t* h, int* nranks, int* rank) {
+  if (!h) return fail(MJPC_B200_ERR_BAD_ARGUMENT, "comm_info: null");
+  if (nranks) *nranks = h->nranks;
+  if (rank) *rank = h->rank;
+  return 0;
+}
+
+// SamplingPlanner::Rollouts for ONE planning problem on all ranks: every rank passes the same N candidates (inputs are
+// replicated: a few KB), rolls out its contiguous shard, then the per-candidate returns and failure flags are exchanged
+// with ONE ncclAllGather enqueued on the engine stream behind the rollout kernel (no host hop), compacted to global
+// candidate order and ranked on the device.  returns / failure / order describe all N candidates, identical on every rank.
+int mjpc_b200_rollout_spline_sharded(mjpc_b200_t* h, const float* state, double time, const float* mocap,
+                                     const float* userdata, const float* knots, const double* knot_times, int interp,
+                                     int P, int N, int H, float* returns, uint8_t* failure, int* order) {
+  if (!h || !knots) return fail(MJPC_B200_ERR_BAD_ARGUMENT, "rollout_spline_sharded: null");
+  if (h->nranks > 1 && !h->comm) return fail(MJPC_B200_ERR_BAD_ARGUMENT, "rollout_spline_sharded: comm_init first");
+  if (h->nranks == 1) {
+    int rc = mjpc_b200_rollout_spline(h, state, time, mocap, userdata, knots, knot_times, interp, P, N, H, returns, failure, order);
+    if (rc == 0) { h->totalN = N; h->shard_lo = 0; h->shard_hi = N; }
+    return rc;
+  }
+  if (N < h->nranks || N > h->maxTotal) return fail(MJPC_B200_ERR_CAPACITY, "rollout_spline_sharded: N outside [nranks, nranks * max_candidates]");
+  const DevModel& M = h->pack.M;
+  int lo, hi;
+  shard_range(N, h->nranks, h->rank, &lo, &hi);
+  const int n = hi - lo, width = N / h->nranks + (N % h->nranks ? 1 : 0);
+  if (n > h->maxN) return fail(MJPC_B200_ERR_CAPACITY, "rollout_spline_sharded: shard above max_candidates");
+  int rc = mjpc_b200_upload_spline_inputs(h, state, time, mocap, userdata, knots + (size_t)lo * P * M.nu, knot_times, interp, P, n, H);
+  if (rc) return rc;
+  h->resident.cand0 = lo;
+  rc = launch_rollout(h, h->resident);
+  if (rc) return rc;
+  NcclApi& api = nccl_api();
+  pack_slot_kernel<<<(width + 255) / 256, 256, 0, h->stream>>>(h->d_returns, h->d_failure, n, width, h->d_slot);
+  NCCL_TRY(api.AllGather(h->d_slot, h->d_gather, 2 * (size_t)width, ncclFloat, h->comm, h->stream));
+  compact_gather_kernel<<<(N + 255) / 256, 256, 0, h->stream>>>(h->d_gather, N, h->nranks, width, h->d_returns_all, h->d_failure_all);
+  rank_kernel<<<(N + 255) / 256, 256, 0, h->stream>>>(h->d_returns_all, N, h->d_order_all);
+  CUDA_TRY(cudaEventRecord(h->ev1, h->stream));   // the timed span now covers rollout + exchange + ranking
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 3;
+  h->totalN = N; h->shard_lo = lo; h->shard_hi = hi;
+  float* hr = (float*)h->h_out;   // h_out holds maxN * 16 bytes: read back in chunks through pageable copies instead
+  (void)hr;
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1) != cudaSuccess) cudaGetLastError();
+  if (returns) CUDA_TRY(cudaMemcpy(returns, h->d_returns_all, (size_t)N * 4, cudaMemcpyDeviceToHost));
+  if (failure) CUDA_TRY(cudaMemcpy(failure, h->d_failure_all, (size_t)N, cudaMemcpyDeviceToHost));
+  if (order) CUDA_TRY(cudaMemcpy(order, h->d_order_all, (size_t)N * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// Trajectory of GLOBAL candidate `candidate` of the last sharded rollout on every rank: the owner packs it into one
+// buffer, ncclBroadcast on the engine stream, every rank unpacks (BestTrajectory must be available wherever the policy
+// is installed).  Any output pointer may be NULL.
+int mjpc_b200_fetch_trajectory_sharded(mjpc_b200_t* h, int candidate, float* states, float* actions, double* times,
+                                       float* residual, float* costs, float* trace) {
+  if (!h || h->totalN < 1 || candidate < 0 || candidate >= h->totalN)
+    return fail(MJPC_B200_ERR_BAD_ARGUMENT, "fetch_trajectory_sharded: bad candidate");
+  if (h->nranks == 1) return mjpc_b200_fetch_trajectory(h, candidate, states, actions, times, residual, costs, trace);
+  const DevModel& M = h->pack.M;
+  const size_t H = h->lastH, ds = M.nq + M.nv, nu = M.nu, nr = M.num_residual, ntr = 3 * M.num_trace;
+  CUDA_TRY(cudaSetDevice(h->device));
+  int owner = 0, lo = 0, hi = 0;
+  for (owner = 0; owner < h->nranks; owner++) { shard_range(h->totalN, h->nranks, owner, &lo, &hi); if (candidate < hi) break; }
+  float* b = h->d_bcast;
+  const size_t o_s = 0, o_a = o_s + H * ds, o_r = o_a + H * nu, o_c = o_r + H * nr, o_tr = o_c + H, o_t = (o_tr + H * ntr + 1) & ~(size_t)1,
+               total = o_t + 2 * H;
+  if (total > h->bcast_floats) return fail(MJPC_B200_ERR_CAPACITY, "fetch_trajectory_sharded: horizon above capacity");
+  if (owner == h->rank) {
+    const size_t i = candidate - lo;
+    auto cp = [&](size_t off, const void* src, size_t bytes) { return cudaMemcpyAsync(b + off, src, bytes, cudaMemcpyDeviceToDevice, h->stream); };
+    CUDA_TRY(cp(o_s, h->d_states + i * H * ds, H * ds * 4)); CUDA_TRY(cp(o_a, h->d_actions + i * H * nu, H * nu * 4));
+    CUDA_TRY(cp(o_r, h->d_residual + i * H * nr, H * nr * 4)); CUDA_TRY(cp(o_c, h->d_costs + i * H, H * 4));
+    if (ntr) CUDA_TRY(cp(o_tr, h->d_trace + i * H * ntr, H * ntr * 4));
+    CUDA_TRY(cp(o_t, h->d_times + i * H, H * 8));
+  }
+  NCCL_TRY(nccl_api().Broadcast(b, b, total, ncclFloat, owner, h->comm, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  auto get = [&](void* dst, size_t off, size_t bytes) { return dst ? cudaMemcpy(dst, b + off, bytes, cudaMemcpyDeviceToHost) : cudaSuccess; };
+  CUDA_TRY(get(states, o_s, H * ds * 4)); CUDA_TRY(get(actions, o_a, H * nu * 4)); CUDA_TRY(get(residual, o_r, H * nr * 4));
+  CUDA_TRY(get(costs, o_c, H * 4)); CUDA_TRY(get(trace, o_tr, H * ntr * 4)); CUDA_TRY(get(times, o_t, H * 8));
+  return 0;
+}
+
 // Batched single-step parity hook (see step_batch_kernel): B tuples -> one mj_step each.  times are absolute; the task
 // state is rebased to `time0` exactly as a rollout starting at time0 would (device time = times[b] - time0).
 int mjpc_b200_step_batch(mjpc_b200_t* h, int B, const float* qpos, const float* qvel, const float* ctrl,
@@ -581,9 +794,10 @@ float* mjpc_b200_device_returns(mjpc_b200_t* h) { return h ? h->d_returns : null
 
 // ---- iLQG entry points (kernels in ilqg_kernels.cuh)
 int mjpc_b200_model_derivatives(mjpc_b200_t* h, const float* x, const float* u, const double* t, const float* mocap,
-                                int H, float tol, float* A, float* B, float* C, float* D) {
+                                int H, int skip, float tol, int mode, float* A, float* B, float* C, float* D) {
   if (!h || !x || !u || !t || !A || !B || !C || !D) return fail(MJPC_B200_ERR_BAD_ARGUMENT, "model_derivatives: null");
   if (H < 1 || H > h->maxH || !(tol > 0)) return fail(MJPC_B200_ERR_BAD_ARGUMENT, "model_derivatives: bad H or tol");
+  if (skip < 0 || mode < 0 || mode > 1) return fail(MJPC_B200_ERR_BAD_ARGUMENT, "model_derivatives: bad skip or mode");
   if (h->pack.M.nmocap && !mocap) return fail(MJPC_B200_ERR_BAD_ARGUMENT, "model_derivatives: mocap required");
   CUDA_TRY(cudaSetDevice(h->device));
   std::vector<float> ts(h->pack.M.task_state_size), trel(H);
@@ -596,8 +810,9 @@ int mjpc_b200_model_derivatives(mjpc_b200_t* h, const float* x, const float* u, 
   for (int i = 0; i < H; i++) trel[i] = (float)(t[i] - t[0]);
   int launches = 0;
   int rc = ilqg_model_derivatives(h->ilqg, h->pack.M, h->d_pack, h->stream, x, u, trel.data(), mocap, ts.data(), H, tol,
-                                  A, B, C, D, h->smem_bytes(1, 1), &launches);
+                                  A, B, C, D, h->smem_bytes(1, 1), &launches, h->ev0, h->ev1, skip, mode);
   h->launches += launches;
+  if (rc == 0 && cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1) != cudaSuccess) cudaGetLastError();
   if (rc) return fail(rc, "model_derivatives: CUDA failure");
   return 0;
 }
@@ -609,8 +824,9 @@ int mjpc_b200_cost_derivatives(mjpc_b200_t* h, const float* residual, const floa
   if (H < 1 || H > h->maxH) return fail(MJPC_B200_ERR_BAD_ARGUMENT, "cost_derivatives: bad H");
   CUDA_TRY(cudaSetDevice(h->device));
   int launches = 0;
-  int rc = ilqg_cost_derivatives(h->ilqg, h->pack.M, h->d_pack, h->stream, residual, C, D, H, cx, cu, cxx, cuu, cxu, &launches);
+  int rc = ilqg_cost_derivatives(h->ilqg, h->pack.M, h->d_pack, h->stream, residual, C, D, H, cx, cu, cxx, cuu, cxu, &launches, h->ev0, h->ev1);
   h->launches += launches;
+  if (rc == 0 && cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1) != cudaSuccess) cudaGetLastError();
   if (rc) return fail(rc, "cost_derivatives: CUDA failure");
   return 0;
 }
@@ -625,8 +841,9 @@ int mjpc_b200_backward_pass(mjpc_b200_t* h, const float* A, const float* B, cons
   CUDA_TRY(cudaSetDevice(h->device));
   int launches = 0;
   int rc = ilqg_backward_pass(h->ilqg, h->pack.M, h->d_pack, h->stream, A, B, cx, cu, cxx, cxu, cuu, actions, H, mu,
-                              reg_type, limits, K, du, dV, Vx, Vxx, status_out, &launches);
+                              reg_type, limits, K, du, dV, Vx, Vxx, status_out, &launches, h->ev0, h->ev1);
   h->launches += launches;
+  if (rc == 0 && cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1) != cudaSuccess) cudaGetLastError();
   if (rc) return fail(rc, "backward_pass: CUDA failure");
   return 0;
 }

@@ -125,6 +125,7 @@ int iLQGPlanner::Initialize(const mjpc_model_blob* model, int num_rollouts, int 
   if (rc) return rc;
   mjpc_b200_get_info(gpu_, &info_);
   nu_ = info_.nu; ds_ = info_.dim_state; n_ = info_.dim_dstate; nr_ = info_.num_residual;
+  Hmax_ = info_.max_horizon;
   representation_ = representation;
   if (int prc = pm_.Load(model)) return prc;
   state_.assign(ds_, 0.0); mocap_.assign(7 * info_.nmocap, 0.0);
@@ -132,14 +133,18 @@ int iLQGPlanner::Initialize(const mjpc_model_blob* model, int num_rollouts, int 
   return 0;
 }
 
+// all trajectory-shaped buffers are allocated at max_horizon once (the reference allocates kMaxTrajectoryHorizon):
+// a later call with a larger horizon <= max_horizon never reads past the end
 void iLQGPlanner::Reset(int horizon, const double* a) {
-  H_ = horizon;
-  const size_t H = horizon;
+  H_ = live_H_ = std::min(std::max(horizon, 1), Hmax_);
+  const size_t H = Hmax_;
+  const std::unique_lock<std::shared_mutex> lock(mtx_);
   states.assign(H * ds_, 0.f); times.assign(H, 0.0); residual.assign(H * nr_, 0.f);
   actions.assign(H * nu_, 0.f);
   if (a) for (size_t t = 0; t < H; t++) for (int i = 0; i < nu_; i++) actions[t * nu_ + i] = (float)a[i];
   gains.assign(H * nu_ * n_, 0.f); du.assign(H * nu_, 0.f);
-  total_return = 0; regularization = 1.0; regularization_rate = 1.0; regularization_factor = 2.0;
+  c_states_ = states; c_actions_ = actions; c_times_ = times; c_residual_ = residual; c_gains_ = gains; c_du_ = du;
+  total_return = c_return_ = 0; regularization = 1.0; regularization_rate = 1.0; regularization_factor = 2.0;
   feedback_scaling = 1.0; winner = 0; improvement = expected = surprise = 0;
   ret_.assign(K_, 0.f); fail_.assign(K_, 0); order_.assign(K_, 0);
 }
@@ -172,7 +177,8 @@ int iLQGPlanner::BestRollout(const std::vector<float>& ret, const std::vector<ui
   return best;
 }
 
-int iLQGPlanner::Install(int candidate, double ret) {
+// candidate_policy[0].trajectory = trajectory[candidate] (planner.cc:214,560): the first H rows of the working copy
+int iLQGPlanner::FetchCandidate(int candidate, double ret) {
   const size_t H = H_;
   best_.horizon = H_; best_.dim_state = ds_; best_.dim_action = nu_; best_.dim_residual = nr_;
   best_.dim_trace = 3 * info_.num_trace;
@@ -181,26 +187,36 @@ int iLQGPlanner::Install(int candidate, double ret) {
   if (mjpc_b200_fetch_trajectory(gpu_, candidate, best_.states.data(), best_.actions.data(), best_.times.data(),
                                  best_.residual.data(), best_.costs.data(), best_.trace.data()))
     return -1;
-  {
-    const std::unique_lock<std::shared_mutex> lock(mtx_);
-    states = best_.states; actions = best_.actions; times = best_.times; residual = best_.residual;
-  }
-  total_return = ret;
+  std::copy(best_.states.begin(), best_.states.end(), c_states_.begin());
+  std::copy(best_.actions.begin(), best_.actions.end(), c_actions_.begin());
+  std::copy(best_.times.begin(), best_.times.end(), c_times_.begin());
+  std::copy(best_.residual.begin(), best_.residual.end(), c_residual_.begin());
+  c_return_ = ret;
   best_.total_return = ret; best_.failure = false;
   return 0;
 }
 
+// planner.cc:167-223.  Works on candidate_policy[0] (a copy of the live policy); the live policy - what
+// ActionFromPolicy evaluates concurrently - is not touched.  `feedback_scaling` is the winning line-search scale
+// (a planner diagnostic, planner.cc:217); the live policy keeps its own feedback_scaling of 1.
 int iLQGPlanner::NominalTrajectory(int horizon) {
+  if (horizon < 1 || horizon > Hmax_) return -1;
   H_ = horizon;
   const std::vector<float> steps = StepSizes();
   std::vector<float> st(state_.begin(), state_.end()), mc(mocap_.begin(), mocap_.end());
-  if (mjpc_b200_rollout_feedback(gpu_, st.data(), time_, mc.empty() ? nullptr : mc.data(), nullptr, actions.data(),
-                                 states.data(), times.data(), gains.data(), nullptr, steps.data(), representation_, K_,
-                                 horizon, ret_.data(), fail_.data(), order_.data()))
-    return -1;
+  {
+    const std::shared_lock<std::shared_mutex> lock(mtx_);
+    c_states_ = states; c_actions_ = actions; c_times_ = times; c_residual_ = residual; c_gains_ = gains; c_du_ = du;
+    c_return_ = total_return;
+  }
+  if (settings.differentiable) mjpc_b200_set_differentiable(gpu_, 1);
+  const int rc = mjpc_b200_rollout_feedback(gpu_, st.data(), time_, mc.empty() ? nullptr : mc.data(), nullptr, c_actions_.data(),
+                                            c_states_.data(), c_times_.data(), c_gains_.data(), nullptr, steps.data(),
+                                            representation_, K_, horizon, ret_.data(), fail_.data(), order_.data());
+  if (rc) return -1;
   const int best = BestRollout(ret_, fail_, K_);
-  if (best == -1) { feedback_scaling = 0.0; return 0; }
-  if (Install(best, ret_[best])) return -1;
+  if (best == -1) { feedback_scaling = 0.0; return 0; }   // candidate_policy[0] keeps the live trajectory (:203-211)
+  if (FetchCandidate(best, ret_[best])) return -1;
   feedback_scaling = steps[best];
   return 1;
 }
@@ -220,24 +236,27 @@ void iLQGPlanner::UpdateRegularization(double z, double s) {
 }
 
 int iLQGPlanner::Iteration(int horizon) {
+  if (horizon < 2 || horizon > Hmax_) return -1;
   const size_t H = horizon, n = n_, m = nu_, nr = nr_;
-  const double previous_return = total_return;
+  const double previous_return = c_return_;
   const std::vector<float> steps = StepSizes();
   A_.resize(H * n * n); B_.resize(H * n * m); C_.resize(H * nr * n); D_.resize(H * nr * m);
   cx_.resize(H * n); cu_.resize(H * m); cxx_.resize(H * n * n); cuu_.resize(H * m * m); cxu_.resize(H * n * m);
   Kbuf_.resize(H * m * n); dubuf_.resize(H * m);
   std::vector<float> mc(mocap_.begin(), mocap_.end()), st(state_.begin(), state_.end());
-  if (mjpc_b200_model_derivatives(gpu_, states.data(), actions.data(), times.data(), mc.empty() ? nullptr : mc.data(),
-                                  horizon, (float)settings.fd_tolerance, A_.data(), B_.data(), C_.data(), D_.data()))
+  if (settings.differentiable) mjpc_b200_set_differentiable(gpu_, 1);
+  if (mjpc_b200_model_derivatives(gpu_, c_states_.data(), c_actions_.data(), c_times_.data(), mc.empty() ? nullptr : mc.data(),
+                                  horizon, settings.derivative_skip, (float)settings.fd_tolerance, settings.fd_mode,
+                                  A_.data(), B_.data(), C_.data(), D_.data()))
     return -1;
-  if (mjpc_b200_cost_derivatives(gpu_, residual.data(), C_.data(), D_.data(), horizon, cx_.data(), cu_.data(),
+  if (mjpc_b200_cost_derivatives(gpu_, c_residual_.data(), C_.data(), D_.data(), horizon, cx_.data(), cu_.data(),
                                  cxx_.data(), cuu_.data(), cxu_.data()))
     return -1;
   int status = 0, reg_iter = 0;
   float dV[2] = {0, 0};
   while (reg_iter < settings.max_regularization_iterations && status == 0) {
     if (mjpc_b200_backward_pass(gpu_, A_.data(), B_.data(), cx_.data(), cu_.data(), cxx_.data(), cxu_.data(),
-                                cuu_.data(), actions.data(), horizon, (float)regularization, settings.regularization_type,
+                                cuu_.data(), c_actions_.data(), horizon, (float)regularization, settings.regularization_type,
                                 settings.action_limits, Kbuf_.data(), dubuf_.data(), dV, nullptr, nullptr, &status))
       return -1;
     if (status == 0 && regularization <= settings.max_regularization) {
@@ -245,25 +264,47 @@ int iLQGPlanner::Iteration(int horizon) {
       reg_iter++;
     }
   }
-  if (status == 0) return 0;
-  {
-    const std::unique_lock<std::shared_mutex> lock(mtx_);
-    gains = Kbuf_; du = dubuf_;
-  }
-  if (mjpc_b200_rollout_feedback(gpu_, st.data(), time_, mc.empty() ? nullptr : mc.data(), nullptr, actions.data(),
-                                 states.data(), times.data(), gains.data(), du.data(), steps.data(), 3, K_, horizon,
+  if (status == 0) return 0;   // backward-pass failure: the live policy is untouched (planner.cc:523-531)
+  // candidate_policy[j] = candidate_policy[0] with the new gains / improvement (:536-540): staged, not published
+  std::copy(Kbuf_.begin(), Kbuf_.end(), c_gains_.begin());
+  std::copy(dubuf_.begin(), dubuf_.end(), c_du_.begin());
+  if (mjpc_b200_rollout_feedback(gpu_, st.data(), time_, mc.empty() ? nullptr : mc.data(), nullptr, c_actions_.data(),
+                                 c_states_.data(), c_times_.data(), c_gains_.data(), c_du_.data(), steps.data(), 3, K_, horizon,
                                  ret_.data(), fail_.data(), order_.data()))
     return -1;
   const int best = BestRollout(ret_, fail_, K_);
-  if (best == -1) return 0;
+  if (best == -1) return 0;    // every rollout failed: nothing is published (:548-550)
   winner = best;
-  if (Install(best, ret_[best])) return -1;
   const double action_step = steps[best];
+  // policy.CopyFrom(candidate_policy[winner]) (:597-605).  ActionRollouts left candidate j's nominal ACTIONS at
+  // old + step_j * du with the OLD nominal states (:639-643); only candidate 0's trajectory was then replaced by the
+  // winning rollout (:560) - restated literally: the closed-loop trajectory is published only when the winner is 0.
+  std::vector<float> old_actions(c_actions_.begin(), c_actions_.begin() + H * m);
+  std::vector<float> old_states(c_states_.begin(), c_states_.begin() + H * ds_), old_residual(c_residual_.begin(), c_residual_.begin() + H * nr);
+  std::vector<double> old_times(c_times_.begin(), c_times_.begin() + H);
+  if (FetchCandidate(best, ret_[best])) return -1;      // candidate_policy[0].trajectory = trajectory[winner]
   expected = -1.0 * action_step * ((double)dV[0] + action_step * (double)dV[1]) + 1.0e-16;
-  improvement = previous_return - total_return;
+  improvement = previous_return - c_return_;
   surprise = std::min(std::max(0.0, improvement / expected), 2.0);
   UpdateRegularization(surprise, action_step);
-  feedback_scaling = 1.0;
+  {
+    const std::unique_lock<std::shared_mutex> lock(mtx_);
+    if (best == 0) {
+      std::copy(c_states_.begin(), c_states_.begin() + H * ds_, states.begin());
+      std::copy(c_actions_.begin(), c_actions_.begin() + H * m, actions.begin());
+      std::copy(c_times_.begin(), c_times_.begin() + H, times.begin());
+      std::copy(c_residual_.begin(), c_residual_.begin() + H * nr, residual.begin());
+    } else {
+      std::copy(old_states.begin(), old_states.end(), states.begin());
+      for (size_t k = 0; k < H * m; k++) actions[k] = old_actions[k] + (float)action_step * c_du_[k];
+      std::copy(old_times.begin(), old_times.end(), times.begin());
+      std::copy(old_residual.begin(), old_residual.end(), residual.begin());
+    }
+    std::copy(c_gains_.begin(), c_gains_.begin() + H * m * n, gains.begin());
+    std::copy(c_du_.begin(), c_du_.begin() + H * m, du.begin());
+    total_return = c_return_;
+    live_H_ = horizon;
+  }
   return 1;
 }
 
@@ -274,7 +315,8 @@ int iLQGPlanner::OptimizePolicy(int horizon) {
 
 void iLQGPlanner::ActionFromPolicy(double* action, const double* state, double time) const {
   const std::shared_lock<std::shared_mutex> lock(mtx_);
-  iLQGPolicyAction(pm_, actions.data(), states.data(), times.data(), gains.data(), H_, representation_, feedback_scaling,
+  // the live policy's own feedback_scaling is always 1 (planner.cc:603)
+  iLQGPolicyAction(pm_, actions.data(), states.data(), times.data(), gains.data(), live_H_, representation_, 1.0,
                    state, time, action);
 }
 
@@ -327,10 +369,11 @@ int mjpc_b200_ilqg_planner_get_result(void* pv, double* scalars, float* states, 
     scalars[0] = p->total_return; scalars[1] = p->regularization; scalars[2] = p->improvement;
     scalars[3] = p->expected; scalars[4] = p->surprise; scalars[5] = p->winner;
   }
-  if (states) std::copy(p->states.begin(), p->states.end(), states);
-  if (actions) std::copy(p->actions.begin(), p->actions.end(), actions);
-  if (times) std::copy(p->times.begin(), p->times.end(), times);
-  return (int)p->times.size();
+  const int H = p->horizon();
+  if (states) std::copy(p->states.begin(), p->states.begin() + (size_t)H * p->dim_state(), states);
+  if (actions) std::copy(p->actions.begin(), p->actions.begin() + (size_t)H * p->dim_action(), actions);
+  if (times) std::copy(p->times.begin(), p->times.begin() + H, times);
+  return H;
 }
 
 }  // extern "C"

@@ -22,6 +22,11 @@ struct iLQGSettings {                    // mjpc/planners/ilqg/settings.h:21-36
   int max_regularization_iterations = 5;
   int action_limits = 1;
   int nominal_feedback_scaling = 1;
+  int fd_mode = 0;                       // ilqg/settings.h:24: 0 one-sided, 1 centred finite differences
+  int derivative_skip = 0;               // planner.h derivative_skip_ (GUI "Deriv. Skip"): interpolate skipped steps
+  // Agent::PlanIteration plans gradient-based planners on a "differentiable" model: solimp[0] = 0 for every joint,
+  // geom and pair while planning (agent.cc:296-309,346-356; utilities.cc:60-75; default on, agent.cc:158-164)
+  int differentiable = 1;
 };
 
 // iLQGPolicy::Action (mjpc/planners/ilqg/policy.cc:82-161) on the host: what the physics thread evaluates between plans.
@@ -51,25 +56,34 @@ class iLQGPlanner {
   const Trajectory* BestTrajectory() const { return &best_; }
 
   iLQGSettings settings;
-  // policy: nominal trajectory, feedback gains, open-loop improvement (iLQGPolicy)
+  // the LIVE policy (iLQGPolicy policy): nominal trajectory, feedback gains, open-loop improvement.  Only written
+  // under the unique lock at the end of a successful Iteration (planner.cc:597-605); buffers keep max_horizon rows.
   std::vector<float> states, actions, residual, gains, du;
   std::vector<double> times;
   double total_return = 0, regularization = 1.0, regularization_rate = 1.0, regularization_factor = 2.0;
   double feedback_scaling = 1.0, improvement = 0, expected = 0, surprise = 0;
   int winner = 0;
   mjpc_b200_t* gpu() { return gpu_; }
+  int horizon() const { return live_H_; }
+  int dim_state() const { return ds_; }
+  int dim_action() const { return nu_; }
 
  private:
   std::vector<float> StepSizes() const;                                   // LogScale (utilities.cc:819-825) + trailing 0
   static int BestRollout(const std::vector<float>& ret, const std::vector<uint8_t>& fail, int K);   // :727-740
-  int Install(int candidate, double ret);
+  int FetchCandidate(int candidate, double ret);                          // candidate_policy[0].trajectory = trajectory[i]
   void ScaleRegularization(double factor);                                // backward_pass.cc:327-343
   void UpdateRegularization(double z, double s);                          // :345-356
   mjpc_b200_t* gpu_ = nullptr;
   mjpc_b200_info info_{};
   iLQGPolicyModel pm_;
   mutable std::shared_mutex mtx_;   // the policy is read by the physics thread while a plan installs a new one
-  int K_ = 10, representation_ = 1, H_ = 0, nu_ = 0, ds_ = 0, n_ = 0, nr_ = 0;
+  int K_ = 10, representation_ = 1, H_ = 0, Hmax_ = 0, nu_ = 0, ds_ = 0, n_ = 0, nr_ = 0;
+  // candidate_policy[0]: the working copy NominalTrajectory / Iteration operate on (planner.cc:190-222,392-560)
+  std::vector<float> c_states_, c_actions_, c_residual_, c_gains_, c_du_;
+  std::vector<double> c_times_;
+  double c_return_ = 0;
+  int live_H_ = 0;
   std::vector<double> state_, mocap_;
   double time_ = 0;
   std::vector<float> A_, B_, C_, D_, cx_, cu_, cxx_, cuu_, cxu_, Kbuf_, dubuf_, ret_;

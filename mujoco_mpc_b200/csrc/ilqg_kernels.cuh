@@ -126,6 +126,10 @@ struct FdArgs {
   const float* task_state;
   int H;
   float eps;
+  const int* eval_t;  // [neval] evaluated time steps (derivative_skip, model_derivatives.cc:56-72)
+  int neval, mode;    // mode 0 one-sided, 1 centred
+  float* yp;          // [neval*ncol][ds]  centred mode: next state of the +eps evaluation
+  float* rp;          // [neval*ncol][nr]  ... and its residual
   float* y0;  // [H][ds]   centre next state
   float* r0;  // [H][nr]   centre residual
   float* q0;  // [H][nv]   centre qacc (warm start of the perturbed solves)
@@ -159,7 +163,7 @@ __device__ __forceinline__ void fd_center_body(const FdArgs& A) {
   Ctx c;
   init_ctx(c, &A.M, &A.L, smem, 0, threadIdx.x, A.pack);
   auto&& M = SP::model(c);
-  const int lane = c.lane, t = blockIdx.x, nq = M.nq, nv = M.nv, ds = nq + nv, nr = M.num_residual;
+  const int lane = c.lane, t = A.eval_t[blockIdx.x], nq = M.nq, nv = M.nv, ds = nq + nv, nr = M.num_residual;
   fd_load_state<SP>(c, A, t);
   for (int i = lane; i < nv; i += 32) DF(qacc_warmstart)[i] = 0;
   __syncwarp();
@@ -172,7 +176,37 @@ __device__ __forceinline__ void fd_center_body(const FdArgs& A) {
   for (int i = lane; i < nv; i += 32) A.y0[(size_t)t * ds + nq + i] = DF(qvel)[i];
 }
 
-// one warp per (t, column). columns: [0, nu) controls, [nu, nu+nv) velocities, [nu+nv, nu+2nv) positions
+// one warp per (evaluated t, column). columns: [0, nu) controls, [nu, nu+nv) velocities, [nu+nv, nu+2nv) positions.
+// Centred mode runs the +eps evaluation, parks its next state / residual in HBM scratch, reloads the state, runs the
+// -eps evaluation and differences the two ([EXT] mjd_transitionFD flg_centered); a control that can only be nudged one
+// way inside ctrlrange falls back to the one-sided difference.
+template <class SP>
+__device__ __forceinline__ void fd_perturb(Ctx& c, int col, int nu, int nv, float h) {
+  const int lane = c.lane;
+  if (col < nu) {
+    if (lane == 0) DF(ctrl)[col] += h;
+  } else if (col < nu + nv) {
+    if (lane == 0) DF(qvel)[col - nu] += h;
+  } else {
+    // tangent-space position perturbation ([EXT] mj_integratePos with a unit vector)
+    const int dof = col - nu - nv;
+    if (lane == 0) {
+      const int j = MI(dof_jntid)[dof];
+      const int qa = MI(jnt_qposadr)[j], da = MI(jnt_dofadr)[j], k = dof - da, ty = MI(jnt_type)[j];
+      float* qpos = DF(qpos);
+      if (ty == JNT_FREE) {
+        if (k < 3) qpos[qa + k] += h;
+        else { float w[3] = {0, 0, 0}; w[k - 3] = 1; quat_integrate(qpos + qa + 3, w, h); }
+      } else if (ty == JNT_BALL) {
+        float w[3] = {0, 0, 0}; w[k] = 1; quat_integrate(qpos + qa, w, h);
+      } else {
+        qpos[qa] += h;
+      }
+    }
+  }
+  __syncwarp();
+}
+
 template <class SP>
 __device__ __forceinline__ void fd_column_body(const FdArgs& A) {
   float* smem = g_smem;
@@ -182,62 +216,66 @@ __device__ __forceinline__ void fd_column_body(const FdArgs& A) {
   auto&& M = SP::model(c);
   const int lane = c.lane, nq = M.nq, nv = M.nv, nu = M.nu, ds = nq + nv, n = 2 * nv, nr = M.num_residual;
   const int ncol = nu + 2 * nv;
-  const int t = blockIdx.x / ncol, col = blockIdx.x - t * ncol;
+  const int te = blockIdx.x / ncol, col = blockIdx.x - te * ncol;
+  const int t = A.eval_t[te];
   const bool last = t == A.H - 1;
   if (last && col < nu) return;  // only C is computed at the final time step (model_derivatives.cc:89-93)
   fd_load_state<SP>(c, A, t);
   for (int i = lane; i < nv; i += 32) DF(qacc_warmstart)[i] = A.q0[(size_t)t * nv + i];
   __syncwarp();
-  float h = A.eps;  // signed step actually taken
+  float h = A.eps;  // signed step of a one-sided difference
+  bool centred = A.mode == 1;
   if (col < nu) {
     const int i = col;
     const bool limited = MI(actuator_ctrllimited)[i] != 0;
     const float lo = MF(actuator_ctrlrange)[2 * i], hi = MF(actuator_ctrlrange)[2 * i + 1];
     const float u0 = DF(ctrl)[i];
-    const bool fwd = !limited || (u0 >= lo && u0 <= hi && u0 + A.eps >= lo && u0 + A.eps <= hi);
-    const bool back = !fwd && (!limited || (u0 - A.eps >= lo && u0 - A.eps <= hi && u0 >= lo && u0 <= hi));
+    const bool inside = u0 >= lo && u0 <= hi;
+    const bool fwd = !limited || (inside && u0 + A.eps >= lo && u0 + A.eps <= hi);
+    const bool back = !limited || (inside && u0 - A.eps >= lo && u0 - A.eps <= hi);
     if (!fwd && !back) {
       for (int k = lane; k < n; k += 32) A.B[((size_t)t * n + k) * nu + i] = 0;
       for (int k = lane; k < nr; k += 32) A.D[((size_t)t * nr + k) * nu + i] = 0;
       return;
     }
-    h = fwd ? A.eps : -A.eps;
+    centred = centred && fwd && back;
+    if (!centred) h = fwd ? A.eps : -A.eps;
     __syncwarp();   // every lane has read u0 before lane 0 overwrites it
-    if (lane == 0) DF(ctrl)[i] = u0 + h;
-  } else if (col < nu + nv) {
-    if (lane == 0) DF(qvel)[col - nu] += A.eps;
-  } else {
-    // tangent-space position perturbation ([EXT] mj_integratePos with a unit vector)
-    const int dof = col - nu - nv;
-    if (lane == 0) {
-      const int j = MI(dof_jntid)[dof];
-      const int qa = MI(jnt_qposadr)[j], da = MI(jnt_dofadr)[j], k = dof - da, ty = MI(jnt_type)[j];
-      float* qpos = DF(qpos);
-      if (ty == JNT_FREE) {
-        if (k < 3) qpos[qa + k] += A.eps;
-        else { float w[3] = {0, 0, 0}; w[k - 3] = 1; quat_integrate(qpos + qa + 3, w, A.eps); }
-      } else if (ty == JNT_BALL) {
-        float w[3] = {0, 0, 0}; w[k] = 1; quat_integrate(qpos + qa, w, A.eps);
-      } else {
-        qpos[qa] += A.eps;
-      }
-    }
   }
-  __syncwarp();
+  float* yp = A.yp + (size_t)blockIdx.x * ds;
+  float* rp = A.rp + (size_t)blockIdx.x * nr;
+  fd_perturb<SP>(c, col, nu, nv, centred ? A.eps : h);
   k_forward<SP>(c);
   k_residual<SP>(c);
-  const float ih = 1.0f / h;
+  if (centred) {
+    for (int k = lane; k < nr; k += 32) rp[k] = DF(residual)[k];
+    if (!last) {
+      k_euler<SP>(c);
+      for (int i = lane; i < nq; i += 32) yp[i] = DF(qpos)[i];
+      for (int i = lane; i < nv; i += 32) yp[nq + i] = DF(qvel)[i];
+    }
+    __syncwarp();
+    fd_load_state<SP>(c, A, t);
+    for (int i = lane; i < nv; i += 32) DF(qacc_warmstart)[i] = A.q0[(size_t)t * nv + i];
+    __syncwarp();
+    fd_perturb<SP>(c, col, nu, nv, -A.eps);
+    k_forward<SP>(c);
+    k_residual<SP>(c);
+  }
+  // centred: (plus - minus) / 2 eps with the current evaluation as "minus"; one-sided: (this - centre) / h
+  const float ih = centred ? -0.5f / A.eps : 1.0f / h;
+  const float* rref = centred ? rp : A.r0 + (size_t)t * nr;
   // residual columns
   float* Cout = col < nu ? A.D : A.C;
   const int cw = col < nu ? nu : n;
   const int cc = col < nu ? col : (col < nu + nv ? nv + (col - nu) : col - nu - nv);
   for (int k = lane; k < nr; k += 32)
-    Cout[((size_t)t * nr + k) * cw + cc] = (DF(residual)[k] - A.r0[(size_t)t * nr + k]) * ih;
+    Cout[((size_t)t * nr + k) * cw + cc] = (DF(residual)[k] - rref[k]) * ih;
   if (last) return;
   k_euler<SP>(c);
   // next-state difference in the tangent space (StateDiff / mj_differentiatePos)
   float* Sout = col < nu ? A.B : A.A;
-  const float* y0 = A.y0 + (size_t)t * ds;
+  const float* y0 = centred ? yp : A.y0 + (size_t)t * ds;
   const int *jtype = MI(jnt_type), *jqadr = MI(jnt_qposadr), *jdadr = MI(jnt_dofadr);
   const float *qpos = DF(qpos), *qvel = DF(qvel);
   for (int j = lane; j < M.njnt; j += 32) {
@@ -256,6 +294,23 @@ __device__ __forceinline__ void fd_column_body(const FdArgs& A) {
     }
   }
   for (int i = lane; i < nv; i += 32) Sout[((size_t)t * n + nv + i) * cw + cc] = (qvel[i] - y0[nq + i]) * ih;
+}
+
+// linear interpolation of the skipped time steps (model_derivatives.cc:109-164): one CTA per interpolated t
+struct FdInterpArgs {
+  const int *t, *e0, *e1;   // [ninterp]
+  const float* w;           // [ninterp] weight of e1
+  float *A, *B, *C, *D;
+  int nA, nB, nC, nD;
+};
+extern "C" __global__ void __launch_bounds__(256) fd_interp_kernel(const __grid_constant__ FdInterpArgs P) {
+  const int k = blockIdx.x, t = P.t[k], e0 = P.e0[k], e1 = P.e1[k];
+  const float w = P.w[k];
+  auto lerp = [&](float* X, int sz) {
+    for (int i = threadIdx.x; i < sz; i += blockDim.x)
+      X[(size_t)t * sz + i] = (1.f - w) * X[(size_t)e0 * sz + i] + w * X[(size_t)e1 * sz + i];
+  };
+  lerp(P.A, P.nA); lerp(P.B, P.nB); lerp(P.C, P.nC); lerp(P.D, P.nD);
 }
 
 extern "C" __global__ void __launch_bounds__(32) fd_center_kernel(const __grid_constant__ FdArgs A) { fd_center_body<DynSpec>(A); }
@@ -704,11 +759,12 @@ struct IlqgBuffers {
   float *x = nullptr, *u = nullptr, *t = nullptr, *mocap = nullptr, *ts = nullptr, *y0 = nullptr, *r0 = nullptr,
         *q0 = nullptr, *A = nullptr, *B = nullptr, *C = nullptr, *D = nullptr, *res = nullptr, *cx = nullptr,
         *cu = nullptr, *cxx = nullptr, *cuu = nullptr, *cxu = nullptr, *act = nullptr, *K = nullptr, *du = nullptr,
-        *dV = nullptr, *Vx = nullptr, *Vxx = nullptr, *range = nullptr;
+        *dV = nullptr, *Vx = nullptr, *Vxx = nullptr, *range = nullptr, *yp = nullptr, *rp = nullptr, *iw = nullptr;
   int* status = nullptr;
+  int* idx = nullptr;   // [4 H]: evaluate list, then interpolate t / e0 / e1
   std::vector<float**> all() {
     return {&x, &u, &t, &mocap, &ts, &y0, &r0, &q0, &A, &B, &C, &D, &res, &cx, &cu, &cxx, &cuu, &cxu, &act, &K, &du,
-            &dV, &Vx, &Vxx, &range};
+            &dV, &Vx, &Vxx, &range, &yp, &rp, &iw};
   }
 };
 
@@ -720,10 +776,12 @@ inline int ilqg_init(IlqgBuffers& b, const DevModel& M, int H, size_t smem_fd) {
       {&b.y0, Hs * ds}, {&b.r0, Hs * nr}, {&b.q0, Hs * M.nv}, {&b.A, Hs * n * n}, {&b.B, Hs * n * m}, {&b.C, Hs * nr * n},
       {&b.D, Hs * nr * m}, {&b.res, Hs * nr}, {&b.cx, Hs * n}, {&b.cu, Hs * m}, {&b.cxx, Hs * n * n}, {&b.cuu, Hs * m * m},
       {&b.cxu, Hs * n * m}, {&b.act, Hs * m}, {&b.K, Hs * m * n}, {&b.du, Hs * m}, {&b.dV, 2}, {&b.Vx, Hs * n},
-      {&b.Vxx, Hs * n * n}, {&b.range, 2 * m + 1}};
+      {&b.Vxx, Hs * n * n}, {&b.range, 2 * m + 1},
+      {&b.yp, (Hs + 2) * (m + n) * ds}, {&b.rp, (Hs + 2) * (m + n) * nr + 1}, {&b.iw, Hs + 1}};
   for (auto& e : plan)
     if (cudaMalloc((void**)e.p, (e.cnt ? e.cnt : 1) * sizeof(float)) != cudaSuccess) return -4;
   if (cudaMalloc((void**)&b.status, sizeof(int)) != cudaSuccess) return -4;
+  if (cudaMalloc((void**)&b.idx, (4 * Hs + 8) * sizeof(int)) != cudaSuccess) return -4;
   if (raise_smem_limit((const void*)fd_center_kernel, smem_fd) != cudaSuccess) return -4;
   if (raise_smem_limit((const void*)fd_column_kernel, smem_fd) != cudaSuccess) return -4;
   b.static_spec = spec_matches<SpecQuadruped>(M, make_layout(M, 1)) ? 1 : 0;
@@ -736,13 +794,15 @@ inline int ilqg_init(IlqgBuffers& b, const DevModel& M, int H, size_t smem_fd) {
 inline void ilqg_free(IlqgBuffers& b) {
   for (float** p : b.all()) if (*p) { cudaFree(*p); *p = nullptr; }
   if (b.status) { cudaFree(b.status); b.status = nullptr; }
+  if (b.idx) { cudaFree(b.idx); b.idx = nullptr; }
 }
 
 #define ILQG_TRY(e) do { if ((e) != cudaSuccess) { cudaGetLastError(); return -4; } } while (0)
 
 inline int ilqg_model_derivatives(IlqgBuffers& b, const DevModel& M, const float* d_pack, cudaStream_t st, const float* x,
                                   const float* u, const float* trel, const float* mocap, const float* ts, int H, float eps,
-                                  float* A, float* B, float* C, float* D, size_t smem, int* launches) {
+                                  float* A, float* B, float* C, float* D, size_t smem, int* launches, cudaEvent_t e0 = nullptr, cudaEvent_t e1 = nullptr,
+                                  int skip = 0, int mode = 0) {
   const size_t n = b.n, m = b.nu, nr = b.nr, ds = b.ds;
   ILQG_TRY(cudaMemcpyAsync(b.x, x, H * ds * 4, cudaMemcpyHostToDevice, st));
   ILQG_TRY(cudaMemcpyAsync(b.u, u, H * m * 4, cudaMemcpyHostToDevice, st));
@@ -751,20 +811,66 @@ inline int ilqg_model_derivatives(IlqgBuffers& b, const DevModel& M, const float
   if (M.task_state_size) ILQG_TRY(cudaMemcpyAsync(b.ts, ts, M.task_state_size * 4, cudaMemcpyHostToDevice, st));
   ILQG_TRY(cudaMemsetAsync(b.A, 0, H * n * n * 4, st)); ILQG_TRY(cudaMemsetAsync(b.B, 0, H * n * m * 4, st));
   ILQG_TRY(cudaMemsetAsync(b.C, 0, H * nr * n * 4, st)); ILQG_TRY(cudaMemsetAsync(b.D, 0, H * nr * m * 4, st));
+  // evaluate / interpolate lists exactly as ModelDerivatives::Compute builds them (model_derivatives.cc:56-72)
+  std::vector<int> ev, it_t, it_e0, it_e1;
+  std::vector<float> it_w;
+  if (H >= 2) {
+    const int s2 = skip + 1;
+    ev.push_back(0);
+    for (int t = s2; t < H - s2; t += s2) ev.push_back(t);
+    ev.push_back(H - 2); ev.push_back(H - 1);
+    for (int t = 0, e = 0; t < H; t++) {
+      if (e == (int)ev.size() || ev[e] > t) {
+        int upper = 0;                                  // FindInterval (utilities.h:125-144)
+        while (upper < (int)ev.size() && !(t < ev[upper])) upper++;
+        const int lower = upper - 1;
+        int b0, b1;
+        if (lower < 0) b0 = b1 = 0;
+        else if (lower > (int)ev.size() - 1) b0 = b1 = (int)ev.size() - 1;
+        else { b0 = std::max(lower, 0); b1 = std::min(upper, (int)ev.size() - 1); }
+        it_t.push_back(t); it_e0.push_back(ev[b0]); it_e1.push_back(ev[b1]);
+        it_w.push_back(b0 == b1 ? 0.f : (float)(double(t - ev[b0]) / double(ev[b1] - ev[b0])));
+      } else e++;
+    }
+    // drop duplicate evaluations (T-2 appears twice when skip = 0): same result, half the work
+    std::vector<int> uniq;
+    for (int t : ev) if (std::find(uniq.begin(), uniq.end(), t) == uniq.end()) uniq.push_back(t);
+    ev = uniq;
+  } else ev.push_back(0);
+  const int neval = (int)ev.size(), ninterp = (int)it_t.size();
+  ILQG_TRY(cudaMemcpyAsync(b.idx, ev.data(), neval * 4, cudaMemcpyHostToDevice, st));
+  if (ninterp) {
+    ILQG_TRY(cudaMemcpyAsync(b.idx + H + 2, it_t.data(), ninterp * 4, cudaMemcpyHostToDevice, st));
+    ILQG_TRY(cudaMemcpyAsync(b.idx + 2 * H + 4, it_e0.data(), ninterp * 4, cudaMemcpyHostToDevice, st));
+    ILQG_TRY(cudaMemcpyAsync(b.idx + 3 * H + 6, it_e1.data(), ninterp * 4, cudaMemcpyHostToDevice, st));
+    ILQG_TRY(cudaMemcpyAsync(b.iw, it_w.data(), ninterp * 4, cudaMemcpyHostToDevice, st));
+  }
+  ILQG_TRY(cudaStreamSynchronize(st));   // the index vectors are pageable host memory
   FdArgs a;
   std::memset(&a, 0, sizeof(a));
+  a.eval_t = b.idx; a.neval = neval; a.mode = mode; a.yp = b.yp; a.rp = b.rp;
   a.M = M; a.L = make_layout(M, 1); a.pack = d_pack; a.x = b.x; a.u = b.u; a.t = b.t; a.mocap = b.mocap;
   a.task_state = M.task_state_size ? b.ts : nullptr; a.H = H; a.eps = eps; a.y0 = b.y0; a.r0 = b.r0; a.q0 = b.q0;
   a.A = b.A; a.B = b.B; a.C = b.C; a.D = b.D;
   const char* ns = std::getenv("MJPC_B200_NO_STATIC");
+  if (e0) ILQG_TRY(cudaEventRecord(e0, st));   // kernel-only span (copies and memsets stay outside)
   if (b.static_spec == 1 && !(ns && ns[0] == '1')) {
-    fd_center_kernel_quadruped<<<H, 32, smem, st>>>(a);
-    fd_column_kernel_quadruped<<<H * (M.nu + 2 * M.nv), 32, smem, st>>>(a);
+    fd_center_kernel_quadruped<<<neval, 32, smem, st>>>(a);
+    fd_column_kernel_quadruped<<<neval * (M.nu + 2 * M.nv), 32, smem, st>>>(a);
   } else {
-    fd_center_kernel<<<H, 32, smem, st>>>(a);
-    fd_column_kernel<<<H * (M.nu + 2 * M.nv), 32, smem, st>>>(a);
+    fd_center_kernel<<<neval, 32, smem, st>>>(a);
+    fd_column_kernel<<<neval * (M.nu + 2 * M.nv), 32, smem, st>>>(a);
   }
   *launches += 2;
+  if (ninterp) {
+    FdInterpArgs ia;
+    ia.t = b.idx + H + 2; ia.e0 = b.idx + 2 * H + 4; ia.e1 = b.idx + 3 * H + 6; ia.w = b.iw;
+    ia.A = b.A; ia.B = b.B; ia.C = b.C; ia.D = b.D;
+    ia.nA = (int)(n * n); ia.nB = (int)(n * m); ia.nC = (int)(nr * n); ia.nD = (int)(nr * m);
+    fd_interp_kernel<<<ninterp, 256, 0, st>>>(ia);
+    *launches += 1;
+  }
+  if (e1) ILQG_TRY(cudaEventRecord(e1, st));
   ILQG_TRY(cudaGetLastError());
   ILQG_TRY(cudaMemcpyAsync(A, b.A, H * n * n * 4, cudaMemcpyDeviceToHost, st));
   ILQG_TRY(cudaMemcpyAsync(B, b.B, H * n * m * 4, cudaMemcpyDeviceToHost, st));
@@ -776,7 +882,7 @@ inline int ilqg_model_derivatives(IlqgBuffers& b, const DevModel& M, const float
 
 inline int ilqg_cost_derivatives(IlqgBuffers& b, const DevModel& M, const float* d_pack, cudaStream_t st,
                                  const float* residual, const float* C, const float* D, int H, float* cx, float* cu,
-                                 float* cxx, float* cuu, float* cxu, int* launches) {
+                                 float* cxx, float* cuu, float* cxu, int* launches, cudaEvent_t e0 = nullptr, cudaEvent_t e1 = nullptr) {
   const size_t n = b.n, m = b.nu, nr = b.nr;
   ILQG_TRY(cudaMemcpyAsync(b.res, residual, H * nr * 4, cudaMemcpyHostToDevice, st));
   ILQG_TRY(cudaMemcpyAsync(b.C, C, H * nr * n * 4, cudaMemcpyHostToDevice, st));
@@ -788,7 +894,9 @@ inline int ilqg_cost_derivatives(IlqgBuffers& b, const DevModel& M, const float*
   const size_t kmax = 32;
   const size_t smem = (nr + kmax * kmax + kmax * n + kmax * m + n + m + n * n + m * m + n * m + 8) * 4;
   ILQG_TRY(raise_smem_limit((const void*)cost_derivatives_kernel, smem));
+  if (e0) ILQG_TRY(cudaEventRecord(e0, st));
   cost_derivatives_kernel<<<H, 256, smem, st>>>(a);
+  if (e1) ILQG_TRY(cudaEventRecord(e1, st));
   *launches += 1;
   ILQG_TRY(cudaGetLastError());
   ILQG_TRY(cudaMemcpyAsync(cx, b.cx, H * n * 4, cudaMemcpyDeviceToHost, st));
@@ -803,7 +911,7 @@ inline int ilqg_cost_derivatives(IlqgBuffers& b, const DevModel& M, const float*
 inline int ilqg_backward_pass(IlqgBuffers& b, const DevModel& M, const float* d_pack, cudaStream_t st, const float* A,
                               const float* B, const float* cx, const float* cu, const float* cxx, const float* cxu,
                               const float* cuu, const float* actions, int H, float mu, int reg_type, int limits, float* K,
-                              float* du, float* dV, float* Vx, float* Vxx, int* status_out, int* launches) {
+                              float* du, float* dV, float* Vx, float* Vxx, int* status_out, int* launches, cudaEvent_t e0 = nullptr, cudaEvent_t e1 = nullptr) {
   (void)d_pack;
   const size_t n = b.n, m = b.nu;
   if (m > 32) return -5;
@@ -823,7 +931,9 @@ inline int ilqg_backward_pass(IlqgBuffers& b, const DevModel& M, const float* d_
   a.K = b.K; a.du = b.du; a.dV = b.dV; a.Vx = b.Vx; a.Vxx = b.Vxx; a.status = b.status;
   const size_t smem = (4 * n * n + 3 * n * m + 3 * m * m + m * n + 2 * n + 12 * m + 9 * m + 16) * 4;
   ILQG_TRY(raise_smem_limit((const void*)backward_pass_kernel, smem));
+  if (e0) ILQG_TRY(cudaEventRecord(e0, st));
   backward_pass_kernel<<<1, 256, smem, st>>>(a);
+  if (e1) ILQG_TRY(cudaEventRecord(e1, st));
   *launches += 1;
   ILQG_TRY(cudaGetLastError());
   ILQG_TRY(cudaMemcpyAsync(K, b.K, H * m * n * 4, cudaMemcpyDeviceToHost, st));

@@ -31,6 +31,7 @@ struct RolloutArgs {
   int policy_kind;          // 0 spline, 1 feedback
   float xfrc_std, xfrc_rate;   // NoisyRollout (trajectory.cc:100-210): OU force noise, std 0 = off
   unsigned noise_seed;
+  int cand0;                // global index of this launch's first candidate (multi-GPU shards): noise stream = cand0 + local index
   int P, interp, N, H;
   double time0;
   float* states; float* actions; double* times; float* residual; float* costs; float* trace;
@@ -185,7 +186,7 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& A) {
     if (noisy && !last) {   // Ornstein-Uhlenbeck perturbation in discrete time (trajectory.cc:147-155)
       float* xf = DF(xfrc);
       for (int i = lane; i < 6 * M.nbody; i += 32)
-        xf[i] = ou_rate * xf[i] + ou_scale * xfrc_normal(A.noise_seed, (unsigned)t, (unsigned)cand, (unsigned)i);
+        xf[i] = ou_rate * xf[i] + ou_scale * xfrc_normal(A.noise_seed, (unsigned)t, (unsigned)(A.cand0 + cand), (unsigned)i);
       __syncwarp();
     }
     k_forward<SP>(c);

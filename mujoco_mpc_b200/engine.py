@@ -19,9 +19,10 @@ _ip = C.POINTER(C.c_int)
 _bp = C.POINTER(C.c_uint8)
 
 EXPORTS = ["mjpc_b200_version", "mjpc_b200_last_error", "mjpc_b200_create", "mjpc_b200_destroy",
-           "mjpc_b200_get_info", "mjpc_b200_set_task", "mjpc_b200_set_xfrc_noise", "mjpc_b200_rollout_spline", "mjpc_b200_rollout_feedback",
+           "mjpc_b200_get_info", "mjpc_b200_set_task", "mjpc_b200_set_differentiable", "mjpc_b200_set_xfrc_noise", "mjpc_b200_rollout_spline", "mjpc_b200_rollout_feedback",
            "mjpc_b200_fetch_trajectory", "mjpc_b200_fetch_all", "mjpc_b200_model_derivatives",
-           "mjpc_b200_cost_derivatives", "mjpc_b200_backward_pass", "mjpc_b200_step_debug", "mjpc_b200_step_batch",
+           "mjpc_b200_cost_derivatives", "mjpc_b200_backward_pass", "mjpc_b200_step_debug", "mjpc_b200_step_batch", "mjpc_b200_comm_unique_id", "mjpc_b200_comm_init",
+           "mjpc_b200_comm_info", "mjpc_b200_rollout_spline_sharded", "mjpc_b200_fetch_trajectory_sharded",
            "mjpc_b200_fetch_stats", "mjpc_b200_launch_count", "mjpc_b200_last_kernel_ms", "mjpc_b200_last_kernel_static",
            "mjpc_b200_spec_words", "mjpc_b200_upload_spline_inputs",
            "mjpc_b200_launch_resident", "mjpc_b200_sync", "mjpc_b200_read_returns", "mjpc_b200_stream",
@@ -147,6 +148,10 @@ class Engine:
         td = TaskDesc(_pd(w), _pd(p), _pd(s), float(self.m.task_risk if risk is None else risk))
         self._check(self.lib.mjpc_b200_set_task(self.h, C.byref(td)))
 
+    def set_differentiable(self, on=True):
+        """MakeDifferentiable (utilities.cc:60-75): solimp[0] = 0 for joints and geoms while planning with gradients."""
+        self._check(self.lib.mjpc_b200_set_differentiable(self.h, int(bool(on))))
+
     # ---- SamplingPlanner::Rollouts
     def rollout_spline(self, state, time, mocap, knots, knot_times, interp, H, want_order=True):
         knots = _f(knots)
@@ -158,6 +163,55 @@ class Engine:
                                                       fail.ctypes.data_as(_bp), order.ctypes.data_as(_ip)))
         self.lastN, self.lastH = N, H
         return ret, fail, order
+
+    # ---- multi-GPU: one planning problem sharded over an NCCL communicator owned by the handle
+    @staticmethod
+    def comm_unique_id():
+        buf = (C.c_uint8 * 128)()
+        lib = load_library()
+        rc = lib.mjpc_b200_comm_unique_id(buf, C.c_size_t(128))
+        if rc != 0:
+            raise EngineError(f"comm_unique_id failed ({rc}): {lib.mjpc_b200_last_error().decode()}")
+        return bytes(buf)
+
+    def comm_init(self, nranks, rank, unique_id: bytes):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._check(self.lib.mjpc_b200_comm_init(self.h, int(nranks), int(rank), buf, C.c_size_t(128)))
+        self.nranks, self.rank = int(nranks), int(rank)
+
+    def comm_init_torch(self, dist):
+        """Distribute rank 0's ncclUniqueId over an existing torch.distributed group, then ncclCommInitRank."""
+        import torch
+        world, rank = dist.get_world_size(), dist.get_rank()
+        t = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            t = torch.tensor(list(self.comm_unique_id()), dtype=torch.uint8)
+        if dist.get_backend() == "nccl":
+            t = t.cuda()
+        dist.broadcast(t, 0)
+        self.comm_init(world, rank, bytes(t.cpu().numpy().tobytes()))
+
+    def rollout_spline_sharded(self, state, time, mocap, knots, knot_times, interp, H):
+        knots = _f(knots)
+        N, P, nu = knots.shape
+        st, mc, kt = _f(state), _f(mocap), _d(knot_times)
+        ret = np.zeros(N, np.float32); fail = np.zeros(N, np.uint8); order = np.zeros(N, np.int32)
+        self._check(self.lib.mjpc_b200_rollout_spline_sharded(self.h, _pf(st), C.c_double(time), _pf(mc), None, _pf(knots),
+                                                              _pd(kt), int(interp), P, N, int(H), _pf(ret),
+                                                              fail.ctypes.data_as(_bp), order.ctypes.data_as(_ip)))
+        nr, rk = getattr(self, "nranks", 1), getattr(self, "rank", 0)
+        self.lastN, self.lastH = N // nr + (1 if rk < N % nr else 0), H     # fetch_all / fetch_stats are per shard
+        return ret, fail, order
+
+    def fetch_trajectory_sharded(self, i):
+        H = self.lastH
+        o = dict(states=np.zeros((H, self.ds), np.float32), actions=np.zeros((H, self.nu), np.float32),
+                 times=np.zeros(H), residual=np.zeros((H, self.nr), np.float32), costs=np.zeros(H, np.float32),
+                 trace=np.zeros((H, self.ntr), np.float32))
+        self._check(self.lib.mjpc_b200_fetch_trajectory_sharded(self.h, int(i), _pf(o["states"]), _pf(o["actions"]),
+                                                                _pd(o["times"]), _pf(o["residual"]), _pf(o["costs"]),
+                                                                _pf(o["trace"])))
+        return o
 
     def upload_spline_inputs(self, state, time, mocap, knots, knot_times, interp, H):
         knots = _f(knots)
@@ -242,13 +296,13 @@ class Engine:
         return o
 
     # ---- iLQG sweeps
-    def model_derivatives(self, x, u, t, mocap, tol):
+    def model_derivatives(self, x, u, t, mocap, tol, skip=0, mode=0):
         x, u, t, mc = _f(x), _f(u), _d(t), _f(mocap)
         H = x.shape[0]
         n, nu, nr = self.n, self.nu, self.nr
         A = np.zeros((H, n, n), np.float32); B = np.zeros((H, n, nu), np.float32)
         Cm = np.zeros((H, nr, n), np.float32); D = np.zeros((H, nr, nu), np.float32)
-        self._check(self.lib.mjpc_b200_model_derivatives(self.h, _pf(x), _pf(u), _pd(t), _pf(mc), H, C.c_float(tol),
+        self._check(self.lib.mjpc_b200_model_derivatives(self.h, _pf(x), _pf(u), _pd(t), _pf(mc), H, int(skip), C.c_float(tol), int(mode),
                                                          _pf(A), _pf(B), _pf(Cm), _pf(D)))
         return A, B, Cm, D
 

@@ -32,6 +32,9 @@ class ILQGSettings:                      # mjpc/planners/ilqg/settings.h:21-36
     max_regularization_iterations = 5
     action_limits = 1
     nominal_feedback_scaling = 1
+    fd_mode = 0                          # 0 one-sided, 1 centred (settings.h:24)
+    derivative_skip = 0                  # iLQGPlanner::derivative_skip_
+    differentiable = 1                   # Agent::PlanIteration MakeDifferentiable default for gradient planners (agent.cc:158-164)
 
 
 class ILQGPlanner:
@@ -78,22 +81,33 @@ class ILQGPlanner:
                 best_ret, best = returns[j], j
         return best
 
-    def _install(self, tr, ret):
-        self.states = np.asarray(tr["states"], float); self.actions = np.asarray(tr["actions"], float)
-        self.times = np.asarray(tr["times"], float); self.residual = np.asarray(tr["residual"], float)
-        self.total_return = float(ret)
+    def _fetch_candidate(self, tr, ret):
+        """candidate_policy[0].trajectory = trajectory[i] (planner.cc:214,560): the working copy, not the live policy"""
+        c = self.cand
+        c["states"] = np.asarray(tr["states"], float); c["actions"] = np.asarray(tr["actions"], float)
+        c["times"] = np.asarray(tr["times"], float); c["residual"] = np.asarray(tr["residual"], float)
+        c["total_return"] = float(ret)
 
-    # -- iLQGPlanner::NominalTrajectory
+    def _differentiable(self):
+        if self.settings.differentiable and hasattr(self.backend, "set_differentiable"):
+            self.backend.set_differentiable(True)
+
+    # -- iLQGPlanner::NominalTrajectory (planner.cc:167-223): works on a copy; the live policy is not touched
     def nominal_trajectory(self):
         steps = self._steps()
-        ret, fail, _ = self.backend.rollout_feedback(self.state, self.time, self.mocap, self.actions, self.states,
-                                                     self.times, self.gains, None, steps, self.representation)
+        self.cand = dict(states=self.states.copy(), actions=self.actions.copy(), times=self.times.copy(),
+                         residual=None if self.residual is None else self.residual.copy(), gains=self.gains.copy(),
+                         du=self.du.copy(), total_return=self.total_return)
+        c = self.cand
+        self._differentiable()
+        ret, fail, _ = self.backend.rollout_feedback(self.state, self.time, self.mocap, c["actions"], c["states"],
+                                                     c["times"], c["gains"], None, steps, self.representation)
         best = self._best(ret, fail)
         if best == -1:
             self.feedback_scaling = 0.0
             return False
-        self._install(self.backend.fetch_trajectory(best), ret[best])
-        self.feedback_scaling = float(steps[best])
+        self._fetch_candidate(self.backend.fetch_trajectory(best), ret[best])
+        self.feedback_scaling = float(steps[best])       # planner diagnostic (planner.cc:217); the live policy keeps 1
         return True
 
     def _scale_regularization(self, factor):
@@ -113,37 +127,49 @@ class ILQGPlanner:
         elif z < 0.1 or s_ < 0.06:
             self._scale_regularization(f)
 
-    # -- iLQGPlanner::Iteration
+    # -- iLQGPlanner::Iteration (planner.cc:377-627)
     def iteration(self):
         s = self.settings
-        previous_return = self.total_return
+        c = self.cand
+        previous_return = c["total_return"]
         steps = self._steps()
-        A, B, C, D = self.backend.model_derivatives(self.states, self.actions, self.times, self.mocap, s.fd_tolerance)
-        cx, cu, cxx, cuu, cxu = self.backend.cost_derivatives(self.residual, C, D)
+        self._differentiable()
+        A, B, C, D = self.backend.model_derivatives(c["states"], c["actions"], c["times"], self.mocap, s.fd_tolerance,
+                                                    skip=s.derivative_skip, mode=s.fd_mode)
+        cx, cu, cxx, cuu, cxu = self.backend.cost_derivatives(c["residual"], C, D)
         status, reg_iter, bp = 0, 0, None
         while reg_iter < s.max_regularization_iterations and status == 0:
-            bp = self.backend.backward_pass(A, B, cx, cu, cxx, cxu, cuu, self.actions, mu=self.regularization,
+            bp = self.backend.backward_pass(A, B, cx, cu, cxx, cxu, cuu, c["actions"], mu=self.regularization,
                                             reg_type=s.regularization_type, limits=s.action_limits)
             status = int(bp["status"])
             if status == 0 and self.regularization <= s.max_regularization:
                 self._scale_regularization(self.regularization_factor)
                 reg_iter += 1
         if status == 0:
-            return False
-        self.gains, self.du, self.dV = np.asarray(bp["K"], float), np.asarray(bp["du"], float), np.asarray(bp["dV"], float)
-        ret, fail, _ = self.backend.rollout_feedback(self.state, self.time, self.mocap, self.actions, self.states,
-                                                     self.times, self.gains, self.du, steps, 3)
+            return False                 # backward-pass failure: the live policy is untouched (:523-531)
+        c["gains"], c["du"], self.dV = np.asarray(bp["K"], float), np.asarray(bp["du"], float), np.asarray(bp["dV"], float)
+        ret, fail, _ = self.backend.rollout_feedback(self.state, self.time, self.mocap, c["actions"], c["states"],
+                                                     c["times"], c["gains"], c["du"], steps, 3)
         best = self._best(ret, fail)
         if best == -1:
-            return False
+            return False                 # nothing is published (:548-550)
         self.winner = best
-        self._install(self.backend.fetch_trajectory(best), ret[best])
         action_step = float(steps[best])
+        old = dict(states=c["states"].copy(), actions=c["actions"].copy(), times=c["times"].copy(), residual=c["residual"].copy())
+        self._fetch_candidate(self.backend.fetch_trajectory(best), ret[best])
         self.expected = -1.0 * action_step * (self.dV[0] + action_step * self.dV[1]) + 1.0e-16
-        self.improvement = previous_return - self.total_return
+        self.improvement = previous_return - c["total_return"]
         self.surprise = min(max(0.0, self.improvement / self.expected), 2.0)
         self._update_regularization(self.surprise, action_step)
-        self.feedback_scaling = 1.0
+        # policy.CopyFrom(candidate_policy[winner]) (:597-605): candidate j keeps the OLD nominal states with actions
+        # old + step_j * du (:639-643); only candidate 0 received the winning rollout (:560)
+        if best == 0:
+            self.states, self.actions, self.times, self.residual = c["states"], c["actions"], c["times"], c["residual"]
+        else:
+            self.states, self.times, self.residual = old["states"], old["times"], old["residual"]
+            self.actions = np.asarray(np.asarray(old["actions"], np.float32) + np.float32(action_step) * np.asarray(c["du"], np.float32), float)
+        self.gains, self.du = c["gains"], c["du"]
+        self.total_return = c["total_return"]
         return True
 
     # -- iLQGPlanner::OptimizePolicy

@@ -22,6 +22,7 @@ struct Engine {
   std::vector<std::unique_ptr<Data<T>>> data;  // one per worker (Planner::ResizeMjData, planners/planner.cc:23-33)
   std::unique_ptr<ThreadPool> pool;
   XfrcNoise noise;                              // applied by rollout_spline / rollout_feedback when std > 0
+  std::vector<double> solimp0;                  // the blob's solimp[0] values (oracle_set_differentiable)
   Engine(const void* blob, size_t n) : model(blob, n), cost(model) {}
   void resize(int nthreads) {
     if (!pool || pool->NumThreads() != nthreads) pool.reset(new ThreadPool(nthreads));
@@ -241,6 +242,21 @@ void* oracle_create(const void* blob, size_t nbytes, int precision) {
   }
 }
 void oracle_destroy(void* hv) { delete (Handle*)hv; }
+// MakeDifferentiable (mjpc/utilities.cc:60-75): solimp[0] = 0 for joints and geoms; on = 0 restores the blob's values
+int oracle_set_differentiable(void* hv, int on) {
+  Handle* h = (Handle*)hv;
+  auto apply = [&](auto& e) {
+    auto& m = e.model;
+    if (e.solimp0.empty()) {
+      for (int i = 0; i < m.njnt; i++) e.solimp0.push_back((double)m.jnt_solimp[5 * i]);
+      for (int i = 0; i < m.ngeom; i++) e.solimp0.push_back((double)m.geom_solimp[5 * i]);
+    }
+    for (int i = 0; i < m.njnt; i++) m.jnt_solimp[5 * i] = on ? 0 : e.solimp0[i];
+    for (int i = 0; i < m.ngeom; i++) m.geom_solimp[5 * i] = on ? 0 : e.solimp0[m.njnt + i];
+  };
+  if (h->precision == 64) apply(*h->e64); else apply(*h->e32);
+  return 0;
+}
 int oracle_step_batch(void* hv, int B, const double* qpos, const double* qvel, const double* ctrl, const double* warmstart,
                       const double* mocap, const double* times, int nthreads, double* qacc, double* next_qpos,
                       double* next_qvel, double* residual, double* cost, int* counts) {
@@ -376,10 +392,11 @@ double oracle_cost_value(void* hv, const double* residual, double* terms) {
 
 // ---- iLQG pieces (oracle/ilqg.h)
 int oracle_model_derivatives(void* hv, const double* states, const double* actions, const double* times,
-                             const double* mocap, int H, double tol, double* A, double* B, double* C, double* D) {
+                             const double* mocap, int H, double tol, double* A, double* B, double* C, double* D, int skip,
+                             int mode, int nthreads) {
   auto* h = (Handle*)hv;
-  if (h->precision == 64) return model_derivatives(h->e64->model, states, actions, times, mocap, H, tol, A, B, C, D);
-  return model_derivatives(h->e32->model, states, actions, times, mocap, H, tol, A, B, C, D);
+  if (h->precision == 64) return model_derivatives(h->e64->model, states, actions, times, mocap, H, tol, A, B, C, D, skip, mode, nthreads);
+  return model_derivatives(h->e32->model, states, actions, times, mocap, H, tol, A, B, C, D, skip, mode, nthreads);
 }
 int oracle_cost_derivatives(void* hv, const double* residual, const double* C, const double* D, int H, int n, int m,
                             double* cx, double* cu, double* cxx, double* cuu, double* cxu) {

@@ -12,6 +12,7 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <thread>
 #include <vector>
 
 #include "rollout.h"
@@ -131,90 +132,147 @@ void perturb_pos(const Model<T>& m, T* qpos, int dof, T eps) {
   }
 }
 
+// Evaluate / interpolate time indices of ModelDerivatives::Compute (model_derivatives.cc:56-72): every (skip+1)-th step,
+// plus T-2 and T-1; everything else is linearly interpolated between its evaluated neighbours (:109-164).
+inline void derivative_indices(int T, int skip, std::vector<int>& evaluate, std::vector<int>& interpolate) {
+  evaluate.clear(); interpolate.clear();
+  const int s = skip + 1;
+  evaluate.push_back(0);
+  for (int t = s; t < T - s; t += s) evaluate.push_back(t);
+  evaluate.push_back(T - 2);
+  evaluate.push_back(T - 1);
+  for (int t = 0, e = 0; t < T; t++) {
+    if (e == (int)evaluate.size() || evaluate[e] > t) interpolate.push_back(t);
+    else e++;
+  }
+}
+
 // A[H][n][n], B[H][n][nu], C[H][nr][n], D[H][nr][nu]; rows of C/D are the task residual rows only
-// (the reference differentiates all nsensordata rows but CostDerivatives reads only the first num_residual)
+// (the reference differentiates all nsensordata rows but CostDerivatives reads only the first num_residual).
+// mode 0: one-sided differences; mode 1: centred ([EXT] mjd_transitionFD flg_centered; a control whose forward or
+// backward nudge would leave ctrlrange falls back to the one-sided difference that stays inside).
+// skip: ModelDerivatives::Compute's derivative_skip (evaluate list + linear interpolation).  nthreads: the reference
+// schedules one task per evaluated time step on its ThreadPool (model_derivatives.cc:76-104).
 template <class T>
 int model_derivatives(const Model<T>& m, const double* states, const double* actions, const double* times,
-                      const double* mocap, int H, double tol, double* A, double* B, double* C, double* D) {
+                      const double* mocap, int H, double tol, double* A, double* B, double* C, double* D, int skip = 0,
+                      int mode = 0, int nthreads = 1) {
   int nq = m.nq, nv = m.nv, nu = m.nu, ds = nq + nv, n = 2 * nv, nr = m.num_residual;
   ResidualCallback<T> cb = residual_by_id<T>(m.residual_id);
-  Data<T> d(m);
-  T eps = (T)tol;
-  for (int i = 0; i < m.nmocap; i++) {
-    for (int c = 0; c < 3; c++) d.mocap_pos[3 * i + c] = (T)mocap[7 * i + c];
-    for (int c = 0; c < 4; c++) d.mocap_quat[4 * i + c] = (T)mocap[7 * i + 3 + c];
-  }
-  std::vector<T> x0(ds), u0(nu), y0(ds), r0(nr), y(ds), dy(n), warm(nv);
-  auto run = [&](const std::vector<T>& x, const std::vector<T>& u, T time, std::vector<T>& ynext, std::vector<T>& r,
-                 bool do_step) {
-    for (int i = 0; i < nq; i++) d.qpos[i] = x[i];
-    for (int i = 0; i < nv; i++) d.qvel[i] = x[nq + i];
-    for (int i = 0; i < nu; i++) d.ctrl[i] = u[i];
-    d.qacc_warmstart = warm;
-    d.time = time;
-    d.warning = false;
-    forward(m, d, cb);
-    for (int i = 0; i < nr; i++) r[i] = d.residual[i];
-    if (do_step) {
-      euler(m, d);
-      for (int i = 0; i < nq; i++) ynext[i] = d.qpos[i];
-      for (int i = 0; i < nv; i++) ynext[nq + i] = d.qvel[i];
+  const T eps = (T)tol;
+  std::vector<int> evaluate, interpolate_t;
+  if (H >= 2) derivative_indices(H, skip, evaluate, interpolate_t);
+  else evaluate.push_back(0);
+  std::fill(A, A + (size_t)H * n * n, 0.0); std::fill(B, B + (size_t)H * n * nu, 0.0);
+  std::fill(C, C + (size_t)H * nr * n, 0.0); std::fill(D, D + (size_t)H * nr * nu, 0.0);
+  auto worker = [&](int w) {
+    Data<T> d(m);
+    for (int i = 0; i < m.nmocap; i++) {
+      for (int c = 0; c < 3; c++) d.mocap_pos[3 * i + c] = (T)mocap[7 * i + c];
+      for (int c = 0; c < 4; c++) d.mocap_quat[4 * i + c] = (T)mocap[7 * i + 3 + c];
+    }
+    std::vector<T> x0(ds), u0(nu), y0(ds), r0(nr), y(ds), ym(ds), dy(n), warm(nv), r(nr), rm(nr);
+    auto run = [&](const std::vector<T>& x, const std::vector<T>& u, T time, std::vector<T>& ynext, std::vector<T>& rr,
+                   bool do_step) {
+      for (int i = 0; i < nq; i++) d.qpos[i] = x[i];
+      for (int i = 0; i < nv; i++) d.qvel[i] = x[nq + i];
+      for (int i = 0; i < nu; i++) d.ctrl[i] = u[i];
+      d.qacc_warmstart = warm;
+      d.time = time;
+      d.warning = false;
+      forward(m, d, cb);
+      for (int i = 0; i < nr; i++) rr[i] = d.residual[i];
+      if (do_step) {
+        euler(m, d);
+        for (int i = 0; i < nq; i++) ynext[i] = d.qpos[i];
+        for (int i = 0; i < nv; i++) ynext[nq + i] = d.qvel[i];
+      }
+    };
+    for (size_t ei = w; ei < evaluate.size(); ei += nthreads) {
+      const int t = evaluate[ei];
+      const bool last = t == H - 1;
+      for (int i = 0; i < ds; i++) x0[i] = (T)states[(size_t)t * ds + i];
+      for (int i = 0; i < nu; i++) u0[i] = (T)actions[(size_t)t * nu + i];
+      const T time = (T)times[t];
+      std::fill(warm.begin(), warm.end(), (T)0);
+      run(x0, u0, time, y0, r0, !last);
+      warm = d.qacc;  // every perturbed evaluation restarts the solver from the centre solution
+      double* At = A + (size_t)t * n * n; double* Bt = B + (size_t)t * n * nu;
+      double* Ct = C + (size_t)t * nr * n; double* Dt = D + (size_t)t * nr * nu;
+      // one column: plus (and, centred, minus) evaluation -> state / residual differences
+      auto column = [&](const std::vector<T>& xp, const std::vector<T>& up, const std::vector<T>* xm,
+                        const std::vector<T>* um, T hp, double* Scol, int sw, double* Rcol, int rw, int cc, bool want_state) {
+        run(xp, up, time, y, r, want_state);
+        if (xm) {
+          run(*xm, *um, time, ym, rm, want_state);
+          if (want_state) {
+            state_diff(m, dy.data(), ym.data(), y.data(), 2 * eps);
+            for (int k = 0; k < n; k++) Scol[k * sw + cc] = dy[k];
+          }
+          for (int k = 0; k < nr; k++) Rcol[k * rw + cc] = (r[k] - rm[k]) / (2 * eps);
+        } else {
+          if (want_state) {
+            state_diff(m, dy.data(), y0.data(), y.data(), hp);
+            for (int k = 0; k < n; k++) Scol[k * sw + cc] = dy[k];
+          }
+          for (int k = 0; k < nr; k++) Rcol[k * rw + cc] = (r[k] - r0[k]) / hp;
+        }
+      };
+      // controls (nudge only where the result stays inside ctrlrange)
+      if (!last)
+        for (int i = 0; i < nu; i++) {
+          const bool limited = m.actuator_ctrllimited[i];
+          const T lo = m.actuator_ctrlrange[2 * i], hi = m.actuator_ctrlrange[2 * i + 1];
+          auto in_range = [&](T a, T b) { return a >= lo && a <= hi && b >= lo && b <= hi; };
+          const bool fwd = !limited || in_range(u0[i], u0[i] + eps);
+          const bool back = !limited || in_range(u0[i] - eps, u0[i]);
+          if (!fwd && !back) continue;   // column stays zero
+          std::vector<T> up = u0, um = u0;
+          if (mode == 1 && fwd && back) {
+            up[i] += eps; um[i] -= eps;
+            column(x0, up, &x0, &um, eps, Bt, nu, Dt, nu, i, true);
+          } else {
+            const T h = fwd ? eps : -eps;
+            up[i] += h;
+            column(x0, up, nullptr, nullptr, h, Bt, nu, Dt, nu, i, true);
+          }
+        }
+      // velocities, then positions (tangent space)
+      for (int pass = 0; pass < 2; pass++)
+        for (int i = 0; i < nv; i++) {
+          std::vector<T> xp = x0, xm = x0;
+          if (pass == 0) { xp[nq + i] += eps; xm[nq + i] -= eps; }
+          else { perturb_pos(m, xp.data(), i, eps); perturb_pos(m, xm.data(), i, -eps); }
+          const int cc = pass == 0 ? nv + i : i;
+          if (mode == 1) column(xp, u0, &xm, &u0, eps, At, n, Ct, n, cc, !last);
+          else column(xp, u0, nullptr, nullptr, eps, At, n, Ct, n, cc, !last);
+        }
     }
   };
-  for (int t = 0; t < H; t++) {
-    bool last = t == H - 1;
-    for (int i = 0; i < ds; i++) x0[i] = (T)states[(size_t)t * ds + i];
-    for (int i = 0; i < nu; i++) u0[i] = (T)actions[(size_t)t * nu + i];
-    T time = (T)times[t];
-    std::fill(warm.begin(), warm.end(), (T)0);
-    run(x0, u0, time, y0, r0, !last);
-    warm = d.qacc;  // every perturbed evaluation restarts the solver from the centre solution
-    std::vector<T> r(nr);
-    double* At = A + (size_t)t * n * n; double* Bt = B + (size_t)t * n * nu;
-    double* Ct = C + (size_t)t * nr * n; double* Dt = D + (size_t)t * nr * nu;
-    // controls (one-sided; nudge backward when the forward nudge would leave ctrlrange)
-    if (!last)
-      for (int i = 0; i < nu; i++) {
-        bool limited = m.actuator_ctrllimited[i];
-        T lo = m.actuator_ctrlrange[2 * i], hi = m.actuator_ctrlrange[2 * i + 1];
-        auto in_range = [&](T a, T b) { return a >= lo && a <= hi && b >= lo && b <= hi; };
-        bool fwd = !limited || in_range(u0[i], u0[i] + eps);
-        bool back = !fwd && (!limited || in_range(u0[i] - eps, u0[i]));
-        std::vector<T> u = u0;
-        if (fwd || back) {
-          u[i] += fwd ? eps : -eps;
-          run(x0, u, time, y, r, true);
-          T sgn = fwd ? (T)1 : (T)-1;
-          state_diff(m, dy.data(), y0.data(), y.data(), sgn * eps);
-          for (int k = 0; k < n; k++) Bt[k * nu + i] = dy[k];
-          for (int k = 0; k < nr; k++) Dt[k * nu + i] = (r[k] - r0[k]) / (sgn * eps);
-        } else {
-          for (int k = 0; k < n; k++) Bt[k * nu + i] = 0;
-          for (int k = 0; k < nr; k++) Dt[k * nu + i] = 0;
-        }
-      }
-    // velocities
-    for (int i = 0; i < nv; i++) {
-      std::vector<T> x = x0;
-      x[nq + i] += eps;
-      run(x, u0, time, y, r, !last);
-      if (!last) {
-        state_diff(m, dy.data(), y0.data(), y.data(), eps);
-        for (int k = 0; k < n; k++) At[k * n + nv + i] = dy[k];
-      }
-      for (int k = 0; k < nr; k++) Ct[k * n + nv + i] = (r[k] - r0[k]) / eps;
+  if (nthreads <= 1) worker(0);
+  else {
+    std::vector<std::thread> th;
+    for (int w = 0; w < nthreads; w++) th.emplace_back(worker, w);
+    for (auto& x : th) x.join();
+  }
+  // linear interpolation of the skipped steps (model_derivatives.cc:109-164)
+  for (int t : interpolate_t) {
+    int b[2];
+    { // FindInterval over the evaluate list (utilities.h:125-144)
+      int upper = 0;
+      const int len = (int)evaluate.size();
+      while (upper < len && !(t < evaluate[upper])) upper++;
+      const int lower = upper - 1;
+      if (lower < 0) b[0] = b[1] = 0;
+      else if (lower > len - 1) b[0] = b[1] = len - 1;
+      else { b[0] = std::max(lower, 0); b[1] = std::min(upper, len - 1); }
     }
-    // positions (tangent space)
-    for (int i = 0; i < nv; i++) {
-      std::vector<T> x = x0;
-      perturb_pos(m, x.data(), i, eps);
-      run(x, u0, time, y, r, !last);
-      if (!last) {
-        state_diff(m, dy.data(), y0.data(), y.data(), eps);
-        for (int k = 0; k < n; k++) At[k * n + i] = dy[k];
-      }
-      for (int k = 0; k < nr; k++) Ct[k * n + i] = (r[k] - r0[k]) / eps;
-    }
+    const int e0 = evaluate[b[0]], e1 = evaluate[b[1]];
+    const double tt = b[0] == b[1] ? 0.0 : double(t - e0) / double(e1 - e0);
+    auto lerp = [&](double* X, size_t sz) {
+      for (size_t k = 0; k < sz; k++) X[(size_t)t * sz + k] = (1.0 - tt) * X[(size_t)e0 * sz + k] + tt * X[(size_t)e1 * sz + k];
+    };
+    lerp(A, (size_t)n * n); lerp(B, (size_t)n * nu); lerp(C, (size_t)nr * n); lerp(D, (size_t)nr * nu);
   }
   return 0;
 }

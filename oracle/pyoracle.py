@@ -76,6 +76,10 @@ class Oracle:
                        trace=np.zeros((N, H, 3 * m.task_num_trace)))
         return out
 
+    def set_differentiable(self, on=True):
+        """MakeDifferentiable (utilities.cc:60-75) on the oracle's model copy."""
+        lib().oracle_set_differentiable(self.h, int(bool(on)))
+
     def set_xfrc_noise(self, std, rate=1.0, seed=0):
         """NoisyRollout perturbation (trajectory.cc:147-155) for the following rollout_spline calls; std 0 = off."""
         lib().oracle_set_xfrc_noise(self.h, C.c_double(std), C.c_double(rate), C.c_uint32(seed))
@@ -160,14 +164,15 @@ class Oracle:
         v = lib().oracle_cost_value(self.h, _p(r), _p(t))
         return (v, t[: self.m.task_num_term]) if terms else v
 
-    def model_derivatives(self, states, actions, times, mocap, tol=1e-6):
+    def model_derivatives(self, states, actions, times, mocap, tol=1e-6, skip=0, mode=0, nthreads=1):
         m = self.m
         H = states.shape[0]
         n, nu, nr = self.n, m.nu, m.task_num_residual
         A, B = np.zeros((H, n, n)), np.zeros((H, n, nu))
         Cm, D = np.zeros((H, nr, n)), np.zeros((H, nr, nu))
         s, a, t, mc = _d(states), _d(actions), _d(times), _d(mocap)
-        lib().oracle_model_derivatives(self.h, _p(s), _p(a), _p(t), _p(mc), H, C.c_double(tol), _p(A), _p(B), _p(Cm), _p(D))
+        lib().oracle_model_derivatives(self.h, _p(s), _p(a), _p(t), _p(mc), H, C.c_double(tol), _p(A), _p(B), _p(Cm), _p(D),
+                                       int(skip), int(mode), int(nthreads))
         return A, B, Cm, D
 
     def cost_derivatives(self, residual, Cm, D):

@@ -72,6 +72,9 @@ class OracleBackend:
     def set_xfrc_noise(self, std, rate=1.0, seed=0):
         self.o.set_xfrc_noise(std, rate, seed)
 
+    def set_differentiable(self, on=True):
+        self.o.set_differentiable(on)
+
     def rollout_feedback(self, state, time, mocap, u_nom, x_nom, t_nom, gains, du, step_sizes, mode):
         r = self.o.rollout_feedback(state, time, mocap, u_nom, x_nom, t_nom, gains, du, step_sizes, mode, nthreads=self.threads)
         self.last = r
@@ -80,8 +83,9 @@ class OracleBackend:
     def fetch_trajectory(self, i):
         return {k: self.last[k][i] for k in ("states", "actions", "times", "residual", "costs", "trace")}
 
-    def model_derivatives(self, x, u, t, mocap, tol):
-        return self.o.model_derivatives(np.asarray(x, float), np.asarray(u, float), np.asarray(t, float), mocap, tol=tol)
+    def model_derivatives(self, x, u, t, mocap, tol, skip=0, mode=0):
+        return self.o.model_derivatives(np.asarray(x, float), np.asarray(u, float), np.asarray(t, float), mocap, tol=tol,
+                                        skip=skip, mode=mode, nthreads=self.threads)
 
     def cost_derivatives(self, residual, C, D):
         return self.o.cost_derivatives(np.asarray(residual, float), np.asarray(C, float), np.asarray(D, float))
