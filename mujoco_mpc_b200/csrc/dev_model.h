@@ -81,6 +81,7 @@ struct DevModel {
   MJPC_M_INTS(X)       // nf, ni: total floats / ints in the pack
 #undef X
   float timestep, impratio, tolerance, ls_tolerance, meaninertia, risk;   // always read from the live header
+  float differentiable;   // != 0: MakeDifferentiable (utilities.cc:60-75) - solimp[0] of joints and geoms reads as 0
   float gravity[3];
   int fo[F_COUNT];     // offsets (floats)
   int io[I_COUNT];     // offsets (ints)

@@ -478,8 +478,8 @@ __device__ __noinline__ void k_collision(Ctx& c) {
 }
 
 // ------------------------------------------------------------------------------------------ constraints
-__device__ __forceinline__ float get_impedance(const float* solimp, float pos, float margin) {
-  const float dmin = fminf(kMaxImp, fmaxf(kMinImp, solimp[0]));
+__device__ __forceinline__ float get_impedance(const float* solimp, float pos, float margin, bool zero_dmin = false) {
+  const float dmin = fminf(kMaxImp, fmaxf(kMinImp, zero_dmin ? 0.f : solimp[0]));
   const float dmax = fminf(kMaxImp, fmaxf(kMinImp, solimp[1]));
   const float width = fmaxf(0.f, solimp[2]);
   const float mid = fminf(kMaxImp, fmaxf(kMinImp, solimp[3]));
@@ -728,13 +728,15 @@ __device__ __noinline__ void k_make_constraint(Ctx& c) {
       const int id = eid[i];
       bool friction_row = false;
       const int ty = etype[i];
+      bool zero_dmin = false;   // MakeDifferentiable zeroes solimp[0] of joints and geoms (not of dofs / tendons)
       if (ty == CNSTR_FRICTION_DOF) { solref = MF(dof_solref) + 2 * id; solimp = MF(dof_solimp) + 5 * id; friction_row = true; }
-      else if (ty == CNSTR_LIMIT_JOINT) { solref = MF(jnt_solref) + 2 * id; solimp = MF(jnt_solimp) + 5 * id; }
+      else if (ty == CNSTR_LIMIT_JOINT) { solref = MF(jnt_solref) + 2 * id; solimp = MF(jnt_solimp) + 5 * id; zero_dmin = CM(c).differentiable != 0.f; }
       else {
         solref = DF(con_solref) + 2 * id; solimp = DF(con_solimp) + 5 * id;
         friction_row = (ty == CNSTR_CONTACT_ELLIPTIC && i > cadr[id]);
+        zero_dmin = CM(c).differentiable != 0.f && g1a[id] >= 0;   // geometric contacts only (tendon limits keep theirs)
       }
-      const float imp = get_impedance(solimp, epos[i], emargin[i]);
+      const float imp = get_impedance(solimp, epos[i], emargin[i], zero_dmin);
       const float dmax = fminf(kMaxImp, fmaxf(kMinImp, solimp[1]));
       float Kk, Bb;
       if (solref[0] > 0) {

@@ -87,9 +87,7 @@ struct mjpc_b200 {
   float* d_bcast = nullptr;
   size_t bcast_floats = 0;
   int maxTotal = 0;
-  // MakeDifferentiable (utilities.cc:60-75): the model's own solimp[0] values, and whether the pack currently holds 0
-  std::vector<float> jnt_solimp0, geom_solimp0;
-  int differentiable = 0;
+  int differentiable = 0;   // MakeDifferentiable (utilities.cc:60-75) for the following launches (DevModel::differentiable)
   // resident-input launch description
   RolloutArgs resident;
   bool resident_ok = false;
@@ -287,8 +285,6 @@ int mjpc_b200_create(const mjpc_model_blob* model, int max_candidates, int max_h
     h->task_state = b.reals("task_state"); h->risk = b.r("task_risk");
   }
   h->time_idx = time_like_state(M.residual_id);
-  for (int i = 0; i < M.njnt; i++) h->jnt_solimp0.push_back(h->pack.f[M.fo[F_jnt_solimp] + 5 * i]);
-  for (int i = 0; i < M.ngeom; i++) h->geom_solimp0.push_back(h->pack.f[M.fo[F_geom_solimp] + 5 * i]);
   CUDA_TRY(cudaSetDevice(device));
   CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreate(&h->ev0));
@@ -386,19 +382,13 @@ int mjpc_b200_set_task(mjpc_b200_t* h, const mjpc_task_desc* task) {
 }
 
 // Agent::PlanIteration's MakeDifferentiable (agent.cc:296-309, utilities.cc:60-75): while on, every joint's and geom's
-// solimp[0] is 0 in the model the kernels read (contact pairs take their solimp from the geoms here); off restores the
-// model's own values (agent.cc:346-356).  Gradient-based planners (iLQG, iLQS, Gradient) plan with it on by default.
+// solimp[0] reads as 0 in the kernels (contact pairs take their solimp from the geoms here); off restores the model's own
+// values (agent.cc:346-356).  Gradient-based planners (iLQG, iLQS, Gradient) plan with it on by default.
 int mjpc_b200_set_differentiable(mjpc_b200_t* h, int on) {
   if (!h) return fail(MJPC_B200_ERR_BAD_ARGUMENT, "set_differentiable: null");
-  on = on ? 1 : 0;
-  if (on == h->differentiable) return 0;
-  const DevModel& M = h->pack.M;
-  std::vector<float>& f = h->pack.f;
-  for (int i = 0; i < M.njnt; i++) f[M.fo[F_jnt_solimp] + 5 * i] = on ? 0.f : h->jnt_solimp0[i];
-  for (int i = 0; i < M.ngeom; i++) f[M.fo[F_geom_solimp] + 5 * i] = on ? 0.f : h->geom_solimp0[i];
-  h->differentiable = on;
-  CUDA_TRY(cudaSetDevice(h->device));
-  return upload_task(h);
+  h->differentiable = on ? 1 : 0;
+  h->pack.M.differentiable = on ? 1.f : 0.f;   // a header option: every launch copies the live header, no re-upload
+  return 0;
 }
 
 int mjpc_b200_upload_spline_inputs(mjpc_b200_t* h, const float* state, double time, const float* mocap,

@@ -177,6 +177,15 @@ int iLQGPlanner::BestRollout(const std::vector<float>& ret, const std::vector<ui
   return best;
 }
 
+// MakeDifferentiable while planning, restored afterwards (agent.cc:296-309,346-356)
+namespace {
+struct DifferentiableScope {
+  mjpc_b200_t* g; bool on;
+  DifferentiableScope(mjpc_b200_t* g_, bool on_) : g(g_), on(on_) { if (on) mjpc_b200_set_differentiable(g, 1); }
+  ~DifferentiableScope() { if (on) mjpc_b200_set_differentiable(g, 0); }
+};
+}  // namespace
+
 // candidate_policy[0].trajectory = trajectory[candidate] (planner.cc:214,560): the first H rows of the working copy
 int iLQGPlanner::FetchCandidate(int candidate, double ret) {
   const size_t H = H_;
@@ -209,7 +218,7 @@ int iLQGPlanner::NominalTrajectory(int horizon) {
     c_states_ = states; c_actions_ = actions; c_times_ = times; c_residual_ = residual; c_gains_ = gains; c_du_ = du;
     c_return_ = total_return;
   }
-  if (settings.differentiable) mjpc_b200_set_differentiable(gpu_, 1);
+  const DifferentiableScope diff(gpu_, settings.differentiable != 0);
   const int rc = mjpc_b200_rollout_feedback(gpu_, st.data(), time_, mc.empty() ? nullptr : mc.data(), nullptr, c_actions_.data(),
                                             c_states_.data(), c_times_.data(), c_gains_.data(), nullptr, steps.data(),
                                             representation_, K_, horizon, ret_.data(), fail_.data(), order_.data());
@@ -244,7 +253,7 @@ int iLQGPlanner::Iteration(int horizon) {
   cx_.resize(H * n); cu_.resize(H * m); cxx_.resize(H * n * n); cuu_.resize(H * m * m); cxu_.resize(H * n * m);
   Kbuf_.resize(H * m * n); dubuf_.resize(H * m);
   std::vector<float> mc(mocap_.begin(), mocap_.end()), st(state_.begin(), state_.end());
-  if (settings.differentiable) mjpc_b200_set_differentiable(gpu_, 1);
+  const DifferentiableScope diff(gpu_, settings.differentiable != 0);
   if (mjpc_b200_model_derivatives(gpu_, c_states_.data(), c_actions_.data(), c_times_.data(), mc.empty() ? nullptr : mc.data(),
                                   horizon, settings.derivative_skip, (float)settings.fd_tolerance, settings.fd_mode,
                                   A_.data(), B_.data(), C_.data(), D_.data()))

@@ -88,9 +88,10 @@ class ILQGPlanner:
         c["times"] = np.asarray(tr["times"], float); c["residual"] = np.asarray(tr["residual"], float)
         c["total_return"] = float(ret)
 
-    def _differentiable(self):
+    def _differentiable(self, on=True):
+        """MakeDifferentiable while planning, restored afterwards (agent.cc:296-309,346-356)"""
         if self.settings.differentiable and hasattr(self.backend, "set_differentiable"):
-            self.backend.set_differentiable(True)
+            self.backend.set_differentiable(on)
 
     # -- iLQGPlanner::NominalTrajectory (planner.cc:167-223): works on a copy; the live policy is not touched
     def nominal_trajectory(self):
@@ -99,9 +100,12 @@ class ILQGPlanner:
                          residual=None if self.residual is None else self.residual.copy(), gains=self.gains.copy(),
                          du=self.du.copy(), total_return=self.total_return)
         c = self.cand
-        self._differentiable()
-        ret, fail, _ = self.backend.rollout_feedback(self.state, self.time, self.mocap, c["actions"], c["states"],
-                                                     c["times"], c["gains"], None, steps, self.representation)
+        self._differentiable(True)
+        try:
+            ret, fail, _ = self.backend.rollout_feedback(self.state, self.time, self.mocap, c["actions"], c["states"],
+                                                         c["times"], c["gains"], None, steps, self.representation)
+        finally:
+            self._differentiable(False)
         best = self._best(ret, fail)
         if best == -1:
             self.feedback_scaling = 0.0
@@ -129,11 +133,17 @@ class ILQGPlanner:
 
     # -- iLQGPlanner::Iteration (planner.cc:377-627)
     def iteration(self):
+        self._differentiable(True)
+        try:
+            return self._iteration()
+        finally:
+            self._differentiable(False)
+
+    def _iteration(self):
         s = self.settings
         c = self.cand
         previous_return = c["total_return"]
         steps = self._steps()
-        self._differentiable()
         A, B, C, D = self.backend.model_derivatives(c["states"], c["actions"], c["times"], self.mocap, s.fd_tolerance,
                                                     skip=s.derivative_skip, mode=s.fd_mode)
         cx, cu, cxx, cuu, cxu = self.backend.cost_derivatives(c["residual"], C, D)

@@ -544,6 +544,27 @@ def synth_mocap(m, seed=0):
     return np.array(kq), np.array(km)
 
 
+def track_keyframes(keyframes_dir=None, synthetic=False):
+    """The Humanoid Track mocap clips (mjpc/tasks/humanoid/tracking/keyframes/*.xml, tracking.cc:43-54).  Order of
+    preference: an explicit directory (or $MJPC_B200_TRACK_KEYFRAMES) holding the reference's XML files, parsed here;
+    the committed fixture models/data/humanoid_track_keyframes.npz (the same data parsed by make_track_keyframes.py -
+    /root/reference does not exist on the GPU box); None -> the caller falls back to synth_mocap.
+    Returns (dict(mpos, qpos, qvel) | None, source string)."""
+    import os
+    if synthetic:
+        return None, "synthetic clips (synth_mocap)"
+    d = keyframes_dir or os.environ.get("MJPC_B200_TRACK_KEYFRAMES")
+    if d:
+        from .make_track_keyframes import parse_keyframes
+        return parse_keyframes(d), "reference keyframes parsed from " + d
+    fx = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "humanoid_track_keyframes.npz")
+    if os.path.exists(fx):
+        z = np.load(fx)
+        return dict(mpos=z["mpos"].astype(float), qpos=z["qpos"].astype(float), qvel=z["qvel"].astype(float)), \
+            "reference keyframes (1889 CMU frames, fixture models/data/humanoid_track_keyframes.npz)"
+    return None, "synthetic clips (synth_mocap): fixture missing"
+
+
 def _robot_vs_world_only(m, g1, g2):
     """Keep only pairs with exactly one static (world-welded) geom: robot self-collision pairs are
     dropped (DESIGN.md 'Out of scope': most need capsule/cylinder/box convex tests)."""
@@ -606,16 +627,27 @@ def load(name: str, agent_timestep: bool = True, **kw):
         m.task_ids = ids
         m.task_state = np.zeros(1)
     elif name == "humanoid_track":
+        keyframes_dir, synthetic = kw.pop("keyframes_dir", None), kw.pop("synthetic_keyframes", False)
         m = compile_xml(humanoid_track_xml(**kw), pair_filter=_robot_vs_world_only)
         m.task_residual_id = T.RESIDUAL_HUMANOID_TRACK
         ids = [m.site_names.index("tracking[%s]" % b) for b in T.TRACK_BODIES]
         ids += [int(m.body_mocapid[m.body_names.index("mocap[%s]" % b)]) for b in T.TRACK_BODIES]
         m.task_ids = np.array(ids, np.int32)
         m.task_state = np.zeros(T.TS_SIZE)               # mode 0 (first clip), reference_time 0
-        kq, km = synth_mocap(m)
+        kf, m.key_source = track_keyframes(keyframes_dir, synthetic)
+        if kf is not None:
+            # the reference's 1889 CMU frames (tracking.cc:43-54); a <key> without qpos / qvel takes the model defaults
+            km = np.asarray(kf["mpos"], float)
+            kq = np.where(np.isnan(kf["qpos"]), m.qpos0[None, :], kf["qpos"]).astype(float)
+            kv = np.asarray(kf["qvel"], float)
+            if kq.shape[1] != m.nq or km.shape[1] != 3 * m.nmocap:
+                raise ValueError("keyframes do not match the humanoid model (nq %d, nmocap %d)" % (m.nq, m.nmocap))
+        else:
+            kq, km = synth_mocap(m)
+            kv = np.zeros((len(kq), m.nv))
         m.nkey = len(kq)
         m.key_qpos, m.key_mpos = kq, km
-        m.key_qvel = np.zeros((m.nkey, m.nv)); m.key_ctrl = np.zeros((m.nkey, m.nu))
+        m.key_qvel = kv; m.key_ctrl = np.zeros((m.nkey, m.nu))
         m.key_mquat = np.tile(np.array([1.0, 0, 0, 0]), (m.nkey, m.nmocap))
         m.key_names = ["frame%d" % i for i in range(m.nkey)]
         m.mocap_pos0 = km[0].reshape(-1, 3).copy()

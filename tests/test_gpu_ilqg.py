@@ -61,37 +61,125 @@ def test_backward_pass_golden_on_device(ctx, oracle_lib):
     assert np.abs(o["K"][:, :, 2:]).max() == 0 and np.abs(o["Vxx"][:, 2:, :]).max() == 0
 
 
+def _column_stats(G, R, R_half):
+    """Per (time step, perturbed coordinate) column: error relative to the column's own scale, and whether the fp64
+    secant itself is stable when the step is halved (a column that moves by > 2 % sits on a contact / limit toggle:
+    there the finite difference is not a derivative in ANY arithmetic and is excluded explicitly)."""
+    colscale = np.abs(R).max(1) + 1.0
+    return np.abs(G - R).max(1) / colscale, np.abs(R - R_half).max(1) / colscale < 0.02
+
+
 @pytest.mark.parametrize("name,eps", [("cartpole", 1e-3), ("quadruped", 1e-3), ("humanoid", 1e-3)])
 def test_model_derivatives(ctx, name, eps):
+    """mjpc_b200_model_derivatives vs the fp64 oracle at the SAME step (same secant), column by column
+    (model_derivatives.cc:76-104).  fp32 bounds: the state Jacobians A, B difference two constraint solves whose per-step
+    error (teacher-forced bound: median 5e-6, p99 6e-4 in qvel) is divided by eps = 1e-3, so their smooth columns are
+    held to median 2e-2 / p99 0.15 / max 0.3 of the column scale AND to 3x the error of the oracle's own fp32
+    instantiation; the residual Jacobians C, D involve no solve: 1e-3.  Toggle columns are classified with the fp64
+    oracle alone (step halving) and must stay below 20 % of the columns."""
+    from mujoco_mpc_b200.blob import to_blob
+    from oracle import pyoracle
     m, e, o = ctx[name]
     H = 8
     state, xs, us, ts, res = _nominal(m, o, H)
-    A, B, C, D = e.model_derivatives(xs, us, ts, mocap_of(m), eps)
-    Ao, Bo, Co, Do = o.model_derivatives(xs, us, ts, mocap_of(m), tol=eps)
+    G = e.model_derivatives(xs, us, ts, mocap_of(m), eps)
+    R = o.model_derivatives(xs, us, ts, mocap_of(m), tol=eps, nthreads=8)
+    Rh = o.model_derivatives(xs, us, ts, mocap_of(m), tol=eps / 2, nthreads=8)
+    F = pyoracle.Oracle(to_blob(m), m, 32).model_derivatives(xs, us, ts, mocap_of(m), tol=eps, nthreads=8)
+    A, B, C, D = G
+    assert np.abs(A[-1]).max() == 0 and np.abs(B[-1]).max() == 0 and np.abs(D[-1]).max() == 0   # last step: only C
     contact = name in ("quadruped", "humanoid")
-    if contact:
-        # a perturbed step can toggle a contact / limit row in one precision and not in the other (measured on the
-        # humanoid: the fp32 ORACLE differs from the fp64 oracle by the full entry scale on such columns and matches
-        # the device to 4 digits): compare each entry with the nearer of the two oracle precisions
-        from mujoco_mpc_b200.blob import to_blob
-        from oracle import pyoracle
-        o32 = pyoracle.Oracle(to_blob(m), m, 32)
-        A3, B3, C3, D3 = o32.model_derivatives(xs, us, ts, mocap_of(m), tol=eps)
-    # structure: last step has only C
-    assert np.abs(A[-1]).max() == 0 and np.abs(B[-1]).max() == 0 and np.abs(D[-1]).max() == 0
-    for k, (G, R, nm) in enumerate(((A, Ao, "A"), (B, Bo, "B"), (C, Co, "C"), (D, Do, "D"))):
-        err = np.abs(G - R)
-        if contact:
-            err = np.minimum(err, np.abs(G - (A3, B3, C3, D3)[k]))
-        scale = np.abs(R).max() + 1.0
-        print(name, nm, "max abs err %.2e (scale %.2e), median %.2e" % (err.max(), scale, np.median(err)))
-        assert np.median(err) < 2e-4 * scale
-        if name in ("quadruped", "humanoid"):
-            # a perturbation can open/close a contact in one arithmetic and not the other: a handful of entries of the
-            # stiff contact block differ at O(1); everything else agrees to round-off / eps
-            assert np.quantile(err, 0.99) < 1e-2 * scale and err.max() < 0.1 * scale
+    for k, nm in enumerate("ABCD"):
+        err, smooth = _column_stats(G[k], R[k], Rh[k])
+        err32, _ = _column_stats(F[k], R[k], Rh[k])
+        assert np.isfinite(G[k]).all()
+        assert smooth.mean() >= (0.8 if contact else 1.0), (nm, smooth.mean())
+        es, es32 = err[smooth], err32[smooth]
+        print(name, nm, "columns %d, smooth %.1f %%; device err / column scale: median %.2e p99 %.2e max %.2e | fp32 oracle %.2e %.2e %.2e"
+              % (smooth.size, 100 * smooth.mean(), np.median(es), np.percentile(es, 99), es.max(), np.median(es32), np.percentile(es32, 99), es32.max()))
+        if nm in "CD" or not contact:
+            assert es.max() < 2e-3, (nm, es.max())
         else:
-            assert err.max() < 2e-3 * scale
+            assert np.median(es) < 2e-2 and np.percentile(es, 99) < 0.15 and es.max() < 0.3
+            assert np.median(es) < 3 * np.median(es32) + 1e-3 and np.percentile(es, 99) < 3 * np.percentile(es32, 99) + 1e-3
+        # toggle columns: bounded by the column scale (no blow-up), nothing tighter is defined there
+        if (~smooth).any():
+            assert err[~smooth].max() < 2.0
+
+
+@pytest.mark.parametrize("name", ["cartpole", "particle"])
+def test_model_derivatives_skip_and_centred(ctx, name):
+    """derivative_skip + linear interpolation (model_derivatives.cc:56-72,109-164) and fd_mode centred
+    (ilqg/settings.h:24) against the oracle on the smooth models, plus the structure of the skip path on the device:
+    evaluated steps equal the skip = 0 result bit for bit, skipped steps are the exact linear blend of their neighbours."""
+    m, e, o = ctx[name]
+    H, eps = 24, 1e-3
+    state, xs, us, ts, res = _nominal(m, o, H)
+    full = e.model_derivatives(xs, us, ts, mocap_of(m), eps)
+    for skip in (1, 3, 5):
+        G = e.model_derivatives(xs, us, ts, mocap_of(m), eps, skip=skip)
+        R = o.model_derivatives(xs, us, ts, mocap_of(m), tol=eps, skip=skip)
+        s = skip + 1
+        ev = sorted(set([0] + list(range(s, H - s, s)) + [H - 2, H - 1]))
+        for k in range(4):
+            np.testing.assert_array_equal(G[k][ev], full[k][ev])
+            scale = np.abs(R[k]).max() + 1.0
+            assert np.abs(G[k] - R[k]).max() < 2e-3 * scale, (skip, "ABCD"[k])
+        for t in range(H):
+            if t in ev:
+                continue
+            e0 = max(x for x in ev if x < t); e1 = min(x for x in ev if x > t)
+            w = np.float32((t - e0) / (e1 - e0))
+            np.testing.assert_allclose(G[0][t], (1 - w) * full[0][e0] + w * full[0][e1], rtol=0, atol=1e-6 * (np.abs(full[0]).max() + 1))
+    Gc = e.model_derivatives(xs, us, ts, mocap_of(m), eps, mode=1)
+    Rc = o.model_derivatives(xs, us, ts, mocap_of(m), tol=eps, mode=1)
+    R1 = o.model_derivatives(xs, us, ts, mocap_of(m), tol=1e-6, mode=1)          # (nearly) the exact derivative
+    for k in range(4):
+        scale = np.abs(Rc[k]).max() + 1.0
+        assert np.abs(Gc[k] - Rc[k]).max() < 2e-3 * scale, "ABCD"[k]
+    # centred differences cancel the O(eps) truncation error of the one-sided secant (cartpole is nonlinear)
+    if name == "cartpole":
+        assert np.abs(Rc[0] - R1[0]).max() < 0.2 * np.abs(o.model_derivatives(xs, us, ts, mocap_of(m), tol=eps)[0] - R1[0]).max() + 1e-9
+
+
+def test_model_derivatives_centred_contact(ctx):
+    """Centred mode on the quadruped (contacts): same column-wise bar as the one-sided test."""
+    m, e, o = ctx["quadruped"]
+    H, eps = 6, 1e-3
+    state, xs, us, ts, res = _nominal(m, o, H)
+    G = e.model_derivatives(xs, us, ts, mocap_of(m), eps, mode=1)
+    R = o.model_derivatives(xs, us, ts, mocap_of(m), tol=eps, mode=1, nthreads=8)
+    Rh = o.model_derivatives(xs, us, ts, mocap_of(m), tol=eps / 2, mode=1, nthreads=8)
+    for k, nm in enumerate("ABCD"):
+        err, smooth = _column_stats(G[k], R[k], Rh[k])
+        assert smooth.mean() >= 0.8
+        es = err[smooth]
+        if nm in "CD":
+            assert es.max() < 2e-3
+        else:
+            assert np.median(es) < 2e-2 and np.percentile(es, 99) < 0.15 and es.max() < 0.3
+
+
+def test_differentiable_model_matches_oracle(ctx):
+    """MakeDifferentiable (utilities.cc:60-75; agent.cc:296-309): solimp[0] = 0 for joints and geoms on both sides -
+    teacher-forced single steps agree to the fp32 per-step bound, and the switch really changes the dynamics."""
+    m, e, o = ctx["quadruped"]
+    state, xs, us, ts, res = _nominal(m, o, 24)
+    q, v = xs[:-1, : m.nq], xs[:-1, m.nq:]
+    plain = e.step_batch(q, v, us[:-1], mocap_of(m), ts[:-1])
+    try:
+        e.set_differentiable(True); o.set_differentiable(True)
+        g = e.step_batch(q, v, us[:-1], mocap_of(m), ts[:-1])
+        r = o.step_batch(q, v, us[:-1], mocap_of(m), ts[:-1], nthreads=4)
+    finally:
+        e.set_differentiable(False); o.set_differentiable(False)
+    assert (g["nefc"] == r["nefc"]).all()
+    err = np.abs(g["next_qvel"] - r["next_qvel"]).max(1)
+    assert np.median(err) < 2e-5 and err.max() < 5e-3
+    incontact = r["ncon"] > 0
+    assert incontact.any() and np.abs(g["next_qvel"] - plain["next_qvel"])[incontact].max() > 1e-4
+    back = e.step_batch(q, v, us[:-1], mocap_of(m), ts[:-1])          # restored: bit-identical to before the switch
+    np.testing.assert_array_equal(back["next_qvel"], plain["next_qvel"])
 
 
 @pytest.mark.parametrize("name", ["cartpole", "quadruped", "particle", "humanoid"])
@@ -165,7 +253,7 @@ def test_ilqg_quadruped_iteration_improves(ctx):
     pl = ILQGPlanner(m, e, horizon=64, num_rollouts=10, fd_tolerance=1e-3)
     pl.set_state(np.concatenate([m.key_qpos[0], np.zeros(m.nv)]), 0.0, mocap_of(m))
     pl.nominal_trajectory()
-    first = pl.total_return
+    first = pl.cand["total_return"]          # candidate_policy[0]: the live policy is only published by an Iteration
     ok = 0
     for _ in range(6):
         ok += bool(pl.optimize_policy())
@@ -181,7 +269,7 @@ def test_ilqg_humanoid_iteration_improves(ctx):
     pl = ILQGPlanner(m, e, horizon=24, num_rollouts=10, fd_tolerance=1e-3)
     pl.set_state(np.concatenate([m.qpos0, np.zeros(m.nv)]), 0.0, mocap_of(m))
     pl.nominal_trajectory()
-    first = pl.total_return
+    first = pl.cand["total_return"]
     ok = 0
     for _ in range(5):
         ok += bool(pl.optimize_policy())

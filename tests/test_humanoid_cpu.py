@@ -128,7 +128,7 @@ def test_humanoid_track_transition():
     tr = HumanoidTrackTransition(m)
     q, v, mocap = tr.transition(0.0, m.qpos0.copy(), np.ones(m.nv))
     assert tr.current_mode == 0 and tr.reference_time == 0.0
-    np.testing.assert_allclose(q, m.key_qpos[0]); assert np.allclose(v, 0)
+    np.testing.assert_allclose(q, m.key_qpos[0]); np.testing.assert_allclose(v, m.key_qvel[0])   # tracking.cc:236-238
     np.testing.assert_allclose(mocap.reshape(16, 7)[:, :3].reshape(-1), m.key_mpos[0])
     q2, v2, mocap = tr.transition(0.05, q + 0.01, v)                 # 1.5 frames into the clip: state untouched
     np.testing.assert_allclose(q2, q + 0.01)
