@@ -317,6 +317,8 @@ def main():
     n_iter = args.steps + args.warmup
     from conftest import get_model
     n_total = world * N_CAND                                   # one problem: N x 256 candidates
+    clocks = ClockSampler(local)
+    clocks.start()          # nvidia-smi needs ~0.5 s to produce its first row: started before the set-up / burn-in
     eng = Engine(get_model("quadruped"), N_CAND, HORIZON, device=local)
     if world > 1:
         eng.comm_init_torch(dist)                              # ncclCommInitRank inside libmjpc_b200.so
@@ -341,8 +343,6 @@ def main():
     if world == 1:
         eng.upload_spline_inputs(state, 0.0, mocap, knots[0], kt, INTERP, HORIZON)
         eng.sync()
-    clocks = ClockSampler(local)
-    clocks.start()          # nvidia-smi needs ~0.5 s to produce its first row: start before the warm-up
     kern_ms = []
     launches0 = 0
     for it in range(n_iter):
@@ -362,7 +362,6 @@ def main():
             kern_ms.append(eng.last_kernel_ms)
     barrier()
     wall = time.perf_counter() - t_wall0
-    clk = clocks.stop()
     gpu_launches = eng.launch_count - launches0
     ms_per_step = max_over_ranks(float(np.sum(kern_ms))) / args.steps
     value = n_total * HORIZON / (ms_per_step * 1e-3)
@@ -388,6 +387,7 @@ def main():
         ret, order, best = e2e_step(args.warmup + it)
     barrier()
     e2e_value = n_total * HORIZON / max_over_ranks((time.perf_counter() - t0) / args.steps)
+    clk = clocks.stop()      # samples cover both timed regions (device-timed and end-to-end), 50 ms apart
 
     # ---------------- N > 1: one-problem evidence + strong scaling of the 256-candidate problem
     multi = None
@@ -474,24 +474,32 @@ def main():
         o32 = pyoracle.Oracle(to_blob(m), m, 32)
         r32 = o32.rollout_spline(state, 0.0, mocap, c_knots, kt, INTERP, HORIZON, nthreads=cores, full=False)["returns"]
         floor = np.abs(r32 - cpu_ret) / np.maximum(np.abs(cpu_ret), 1e-12)
-        # stability of each candidate's fp64 return under one fp32 rounding of the INPUTS (what the device receives)
+        # conditioning of each candidate's return, from the fp64 oracle alone: inputs rounded to fp32 and 5 random
+        # perturbations of the initial velocity of size 1e-5 (= one teacher-forced fp32 step error); a return that moves
+        # by > 2e-5 under ONE of them cannot be pinned to 1e-4 through 64 such steps (tests/test_gpu_teacher_forced.py)
         o64 = pyoracle.Oracle(to_blob(m), m, 64)
-        s32 = np.asarray(state, np.float32)
-        stable = np.ones(len(cpu_ret), bool)
-        for sv in (s32.astype(float), np.nextafter(s32, np.float32(np.inf)).astype(float), np.nextafter(s32, np.float32(-np.inf)).astype(float)):
+        rng = np.random.default_rng(12345)
+        variants = [np.asarray(state, np.float32).astype(float)]
+        for _ in range(5):
+            sv = np.asarray(state, float).copy(); sv[m.nq:] += 1e-5 * rng.standard_normal(m.nv)
+            variants.append(sv)
+        worst = np.zeros(len(cpu_ret))
+        for sv in variants:
             rp = o64.rollout_spline(sv, 0.0, mocap, c_knots.astype(float), kt, INTERP, HORIZON, nthreads=cores, full=False)["returns"]
-            stable &= np.abs(rp - cpu_ret) <= 2e-5 * np.abs(cpu_ret)
+            worst = np.maximum(worst, np.abs(rp - cpu_ret) / np.abs(cpu_ret))
+        stable = worst <= 2e-5
         parity = {"max_rel_return_err_vs_fp64_oracle": float(rel.max()), "mean_rel": float(rel.mean()),
                   "median_rel_vs_fp64_oracle": float(np.median(rel)),
                   "candidates_above_1e-4_vs_fp64": int((rel > 1e-4).sum()),
-                  "input_stable_candidates": int(stable.sum()),
-                  "max_rel_on_input_stable_candidates": float(rel[stable].max()) if stable.any() else None,
-                  "input_stable_candidates_above_1e-4": int((rel[stable] > 1e-4).sum()),
+                  "well_conditioned_candidates": int(stable.sum()),
+                  "max_rel_on_well_conditioned_candidates": float(rel[stable].max()) if stable.any() else None,
+                  "well_conditioned_candidates_above_1e-4": int((rel[stable] > 1e-4).sum()),
                   "fp32_oracle_vs_fp64_oracle": {"max_rel": float(floor.max()), "median_rel": float(np.median(floor)),
                                                  "candidates_above_1e-4": int((floor > 1e-4).sum())},
                   "argmin_agrees": bool(int(gorder[0]) == int(np.argmin(cpu_ret))),
-                  "note": "input-stable = the fp64 oracle's own return moves < 2e-5 when the state is rounded to fp32 / nudged one "
-                          "fp32 ulp (the device receives fp32 inputs); teacher-forced per-step parity at 256x64 is in tests/"}
+                  "note": "well-conditioned = the fp64 oracle's own return moves < 2e-5 when the inputs are rounded to fp32 or the "
+                          "initial velocity is perturbed by 1e-5 (one teacher-forced fp32 step error); teacher-forced per-step "
+                          "parity at 256x64 is asserted in tests/test_gpu_teacher_forced.py"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",

@@ -219,6 +219,8 @@ int mjpc_b200_planner_create(const mjpc_model_blob* model, int num_trajectory, i
                              double exploration, double timestep, const double* ctrlrange, uint32_t seed,
                              int max_horizon, int device, void** out);
 void mjpc_b200_planner_destroy(void* planner);
+/* noise_exploration[0..1] (sampling/planner.cc:85-88, 334-338): exploration2 > 0 replaces the std with probability 0.2 */
+void mjpc_b200_planner_set_exploration(void* planner, double exploration, double exploration2);
 void mjpc_b200_planner_reset(void* planner, int horizon, const double* initial_repeated_action);
 void mjpc_b200_planner_set_state(void* planner, const double* state, double time, const double* mocap);
 int mjpc_b200_planner_optimize_policy(void* planner, int horizon);          /* SamplingPlanner::OptimizePolicy */

@@ -400,7 +400,7 @@ __device__ __noinline__ void k_collision(Ctx& c) {
     const int excl = incl - cnt;
     for (int k = 0; k < cnt; k++) {
       const int idx = ncon + excl + k;
-      if (idx >= M.maxcon) break;  // capacity: later contacts are dropped (same rule as the oracle)
+      if (idx >= M.maxcon) break;  // capacity (warning raised below)
       DF(con_dist)[idx] = raw[k].dist;
       float fr[9];
       for (int q = 0; q < 3; q++) { DF(con_pos)[3 * idx + q] = raw[k].pos[q]; fr[q] = raw[k].normal[q]; }
@@ -438,6 +438,9 @@ __device__ __noinline__ void k_collision(Ctx& c) {
       DF(con_mu)[idx] = 0;
       DI(con_adr)[idx] = -1;
     }
+    // contact buffer full: MuJoCo raises mjWARN_CONTACTFULL and Trajectory::Rollout turns any warning into failure
+    // (trajectory.cc:169-173, utilities.cc:804-816) - never a silently truncated contact set in the ranking
+    if (ncon + total > M.maxcon) c.warn = 1;
     ncon = min(ncon + total, M.maxcon);
     __syncwarp();
   }
@@ -445,7 +448,7 @@ __device__ __noinline__ void k_collision(Ctx& c) {
   // contacts: they need exactly what a contact row needs - a short dof list, a compact Jacobian row, dist, margin,
   // solref/solimp - and every later phase then treats them uniformly.  con_g1 = -(tendon+1) marks them, con_mu
   // carries the side (+-1).  (Row order therefore differs from the oracle's: tendon limits come after contacts.)
-  int npseudo = 0;
+  int npseudo = 0, npseudo_ovf = 0;
   if (!M.disable_limit && M.ntendon > 0 && lane == 0) {
     const int *tadr = MI(tendon_adr), *tnum = MI(tendon_num), *tlim = MI(tendon_limited), *wq = MI(wrap_qposadr);
     const float *wc = MF(wrap_coef), *trange = MF(tendon_range), *tmargin = MF(tendon_margin);
@@ -456,6 +459,7 @@ __device__ __noinline__ void k_collision(Ctx& c) {
       for (int w = tadr[t]; w < tadr[t] + tnum[t]; w++) len += wc[w] * qpos[wq[w]];
       for (int side = -1; side <= 1; side += 2) {
         const float dd = side * (trange[2 * t + (side + 1) / 2] - len);
+        if (dd < tmargin[t] && ncon + npseudo >= M.maxcon) npseudo_ovf = 1;
         if (dd < tmargin[t] && ncon + npseudo < M.maxcon) {
           const int idx = ncon + npseudo;
           DF(con_dist)[idx] = dd; DF(con_margin)[idx] = tmargin[t];
@@ -472,6 +476,7 @@ __device__ __noinline__ void k_collision(Ctx& c) {
     }
   }
   npseudo = __shfl_sync(kFull, npseudo, 0);
+  if (__shfl_sync(kFull, npseudo_ovf, 0)) c.warn = 1;
   __syncwarp();
   c.npseudo = npseudo;
   c.ncon = ncon + npseudo;
@@ -563,6 +568,7 @@ __device__ __noinline__ void k_make_constraint(Ctx& c) {
         epos[r] = dist[q]; emargin[r] = jmargin[j]; ediag[r] = dinvw[jdadr[j]]; etype[r] = CNSTR_LIMIT_JOINT;
         eid[r] = j; efloss[r] = 0; eitem[nitem + incl - cnt + q] = r;
       }
+      if (total > M.maxefc - ne) c.warn = 1;   // constraint buffer full (mjWARN_CNSTRFULL) -> rollout failure
       const int added = min(total, M.maxefc - ne);
       ne += added; nitem += added;
       __syncwarp();
@@ -602,6 +608,7 @@ __device__ __noinline__ void k_make_constraint(Ctx& c) {
     }
   }
   __syncwarp();
+  int efc_ovf = 0;
   if (lane == 0) {
     int r = ne, it = nitem, bo = 0;
     for (int ci = 0; ci < c.ncon; ci++) {
@@ -609,7 +616,7 @@ __device__ __noinline__ void k_make_constraint(Ctx& c) {
       const bool pyr = pyramidal && condim > 1;
       const int nrow = pyr ? 2 * (condim - 1) : condim;   // pyramidal cone: two opposing edges per friction direction
       cboff[ci] = bo;
-      if (r + nrow > M.maxefc) { cadr[ci] = -1; continue; }
+      if (r + nrow > M.maxefc) { cadr[ci] = -1; efc_ovf = 1; continue; }
       cadr[ci] = r;
       if (pyr) { for (int k = 0; k < nrow; k++) eitem[it++] = r + k; }   // independent one-sided rows
       else eitem[it++] = r;                                               // one work item per contact
@@ -621,6 +628,7 @@ __device__ __noinline__ void k_make_constraint(Ctx& c) {
   }
   ne = __shfl_sync(kFull, ne, 0);
   nitem = __shfl_sync(kFull, nitem, 0);
+  if (__shfl_sync(kFull, efc_ovf, 0)) c.warn = 1;   // mjWARN_CNSTRFULL
   __syncwarp();
   {
     const int *rootid = MI(body_rootid), *mlo = MI(body_dofmask_lo), *mhi = MI(body_dofmask_hi);

@@ -87,6 +87,7 @@ struct mjpc_b200 {
   float* d_bcast = nullptr;
   size_t bcast_floats = 0;
   int maxTotal = 0;
+  int nuserdata = 0;
   int differentiable = 0;   // MakeDifferentiable (utilities.cc:60-75) for the following launches (DevModel::differentiable)
   // resident-input launch description
   RolloutArgs resident;
@@ -255,6 +256,16 @@ extern "C" {
 const char* mjpc_b200_version(void) { return "mjpc_b200 0.1.0 (sm_100a)"; }
 const char* mjpc_b200_last_error(void) { return g_last_error.c_str(); }
 
+// inside create(): a failing CUDA call must not leak the half-built handle
+#define CREATE_TRY(expr)                                                                                   \
+  do {                                                                                                     \
+    cudaError_t e_ = (expr);                                                                               \
+    if (e_ != cudaSuccess) {                                                                               \
+      mjpc_b200_destroy(h);                                                                                \
+      return fail(MJPC_B200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));                 \
+    }                                                                                                      \
+  } while (0)
+
 int mjpc_b200_create(const mjpc_model_blob* model, int max_candidates, int max_horizon, int device,
                      mjpc_b200_t** out) {
   if (!model || !model->data || !out || max_candidates < 1 || max_horizon < 1)
@@ -281,16 +292,18 @@ int mjpc_b200_create(const mjpc_model_blob* model, int max_candidates, int max_h
   const DevModel& M = h->pack.M;
   {
     Blob b(model->data, model->nbytes);
+    h->nuserdata = b.i("nuserdata");
+    if (h->nuserdata != 0) { delete h; return fail(MJPC_B200_ERR_UNSUPPORTED, "create: mjData::userdata (nuserdata > 0) is not supported"); }
     h->weight = b.reals("task_weight"); h->parameters = b.reals("task_parameters");
     h->task_state = b.reals("task_state"); h->risk = b.r("task_risk");
   }
   h->time_idx = time_like_state(M.residual_id);
-  CUDA_TRY(cudaSetDevice(device));
-  CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  CUDA_TRY(cudaEventCreate(&h->ev0));
-  CUDA_TRY(cudaEventCreate(&h->ev1));
+  CREATE_TRY(cudaSetDevice(device));
+  CREATE_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CREATE_TRY(cudaEventCreate(&h->ev0));
+  CREATE_TRY(cudaEventCreate(&h->ev1));
   cudaDeviceProp prop;
-  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  CREATE_TRY(cudaGetDeviceProperties(&prop, device));
   const size_t smem_need = h->smem_bytes(h->maxP, 1);
   if (smem_need > (size_t)prop.sharedMemPerBlockOptin) {
     mjpc_b200_destroy(h);
@@ -304,24 +317,24 @@ int mjpc_b200_create(const mjpc_model_blob* model, int max_candidates, int max_h
     std::memcpy(f.data() + nf, h->pack.i.data(), h->pack.i.size() * 4);
     // not staged to shared memory: keyframe mocap positions, read from HBM by the tracking residual (Ctx::gkey)
     for (double x : h->pack.key_mpos) f.push_back((float)x);
-    CUDA_TRY(dalloc(&h->d_pack, f.size()));
-    CUDA_TRY(cudaMemcpy(h->d_pack, f.data(), f.size() * 4, cudaMemcpyHostToDevice));
+    CREATE_TRY(dalloc(&h->d_pack, f.size()));
+    CREATE_TRY(cudaMemcpy(h->d_pack, f.data(), f.size() * 4, cudaMemcpyHostToDevice));
   }
   const size_t N = max_candidates, H = max_horizon, ds = M.nq + M.nv, n = 2 * M.nv, nu = M.nu, nr = M.num_residual;
-  CUDA_TRY(dalloc(&h->d_state, ds)); CUDA_TRY(dalloc(&h->d_mocap, 7 * (size_t)M.nmocap));
-  CUDA_TRY(dalloc(&h->d_task_state, (size_t)M.task_state_size));
-  CUDA_TRY(dalloc(&h->d_knots, N * h->maxP * nu)); CUDA_TRY(dalloc(&h->d_knot_times, (size_t)h->maxP));
-  CUDA_TRY(dalloc(&h->d_unom, H * nu)); CUDA_TRY(dalloc(&h->d_xnom, H * ds)); CUDA_TRY(dalloc(&h->d_tnom, H));
-  CUDA_TRY(dalloc(&h->d_gains, H * nu * n)); CUDA_TRY(dalloc(&h->d_du, H * nu)); CUDA_TRY(dalloc(&h->d_steps, N));
-  CUDA_TRY(dalloc(&h->d_states, N * H * ds)); CUDA_TRY(dalloc(&h->d_actions, N * H * nu));
-  CUDA_TRY(dalloc(&h->d_times, N * H)); CUDA_TRY(dalloc(&h->d_residual, N * H * nr));
-  CUDA_TRY(dalloc(&h->d_costs, N * H)); CUDA_TRY(dalloc(&h->d_trace, N * H * 3 * (size_t)M.num_trace));
-  CUDA_TRY(dalloc(&h->d_returns, N)); CUDA_TRY(dalloc(&h->d_failure, N)); CUDA_TRY(dalloc(&h->d_order, N)); CUDA_TRY(dalloc(&h->d_stats, 12 * N));
-  CUDA_TRY(dalloc(&h->d_dbg, 4 * ds + 2 * nu + (size_t)M.nv * M.nv + nr + 256 + 64 + 7 * (size_t)M.nmocap));
+  CREATE_TRY(dalloc(&h->d_state, ds)); CREATE_TRY(dalloc(&h->d_mocap, 7 * (size_t)M.nmocap));
+  CREATE_TRY(dalloc(&h->d_task_state, (size_t)M.task_state_size));
+  CREATE_TRY(dalloc(&h->d_knots, N * h->maxP * nu)); CREATE_TRY(dalloc(&h->d_knot_times, (size_t)h->maxP));
+  CREATE_TRY(dalloc(&h->d_unom, H * nu)); CREATE_TRY(dalloc(&h->d_xnom, H * ds)); CREATE_TRY(dalloc(&h->d_tnom, H));
+  CREATE_TRY(dalloc(&h->d_gains, H * nu * n)); CREATE_TRY(dalloc(&h->d_du, H * nu)); CREATE_TRY(dalloc(&h->d_steps, N));
+  CREATE_TRY(dalloc(&h->d_states, N * H * ds)); CREATE_TRY(dalloc(&h->d_actions, N * H * nu));
+  CREATE_TRY(dalloc(&h->d_times, N * H)); CREATE_TRY(dalloc(&h->d_residual, N * H * nr));
+  CREATE_TRY(dalloc(&h->d_costs, N * H)); CREATE_TRY(dalloc(&h->d_trace, N * H * 3 * (size_t)M.num_trace));
+  CREATE_TRY(dalloc(&h->d_returns, N)); CREATE_TRY(dalloc(&h->d_failure, N)); CREATE_TRY(dalloc(&h->d_order, N)); CREATE_TRY(dalloc(&h->d_stats, 12 * N));
+  CREATE_TRY(dalloc(&h->d_dbg, 4 * ds + 2 * nu + (size_t)M.nv * M.nv + nr + 256 + 64 + 7 * (size_t)M.nmocap));
   h->h_in_floats = ds + 7 * M.nmocap + M.task_state_size + N * h->maxP * nu + h->maxP + H * (nu + ds + 1 + nu * n + nu) + N + 64;
-  CUDA_TRY(cudaMallocHost((void**)&h->h_in, h->h_in_floats * 4));
+  CREATE_TRY(cudaMallocHost((void**)&h->h_in, h->h_in_floats * 4));
   h->h_out_bytes = N * 16 + 64;
-  CUDA_TRY(cudaMallocHost((void**)&h->h_out, h->h_out_bytes));
+  CREATE_TRY(cudaMallocHost((void**)&h->h_out, h->h_out_bytes));
   if (int rc = set_smem((const void*)rollout_kernel, h->smem_bytes(h->maxP, h->warps_per_cta))) { mjpc_b200_destroy(h); return rc; }
   if (int rc = set_smem((const void*)step_debug_kernel, h->smem_bytes(1, 1))) { mjpc_b200_destroy(h); return rc; }
   if (spec_matches<SpecQuadruped>(M, make_layout(M, 1))) {
@@ -362,7 +375,7 @@ void mjpc_b200_destroy(mjpc_b200_t* h) {
 int mjpc_b200_get_info(const mjpc_b200_t* h, mjpc_b200_info* info) {
   if (!h || !info) return fail(MJPC_B200_ERR_BAD_ARGUMENT, "get_info: null");
   const DevModel& M = h->pack.M;
-  info->nq = M.nq; info->nv = M.nv; info->nu = M.nu; info->na = 0; info->nmocap = M.nmocap; info->nuserdata = 0;
+  info->nq = M.nq; info->nv = M.nv; info->nu = M.nu; info->na = 0 /* na > 0 is rejected by create() */; info->nmocap = M.nmocap; info->nuserdata = h->nuserdata;
   info->dim_state = M.nq + M.nv; info->dim_dstate = 2 * M.nv;
   info->num_residual = M.num_residual; info->num_term = M.num_term; info->num_trace = M.num_trace;
   info->num_parameters = M.num_parameters; info->task_state_size = M.task_state_size;
@@ -394,9 +407,11 @@ int mjpc_b200_set_differentiable(mjpc_b200_t* h, int on) {
 int mjpc_b200_upload_spline_inputs(mjpc_b200_t* h, const float* state, double time, const float* mocap,
                                    const float* userdata, const float* knots, const double* knot_times, int interp,
                                    int P, int N, int H) {
-  (void)userdata;
   if (!h || !state || !knots || !knot_times) return fail(MJPC_B200_ERR_BAD_ARGUMENT, "rollout_spline: null pointer");
   const DevModel& M = h->pack.M;
+  // mjData::userdata: none of the implemented residuals reads it; a model that declares nuserdata > 0 is rejected at
+  // create(), so a non-NULL pointer here can only be a caller error - refuse rather than silently ignore it
+  if (userdata && h->nuserdata == 0) return fail(MJPC_B200_ERR_UNSUPPORTED, "rollout_spline: the model has nuserdata = 0, userdata must be NULL");
   if (M.nmocap && !mocap) return fail(MJPC_B200_ERR_BAD_ARGUMENT, "rollout_spline: mocap required");
   if (N < 1 || H < 1 || P < 1 || interp < 0 || interp > 2) return fail(MJPC_B200_ERR_BAD_ARGUMENT, "rollout_spline: bad sizes");
   if (N > h->maxN || H > h->maxH || P > h->maxP) return fail(MJPC_B200_ERR_CAPACITY, "rollout_spline: N/H/P above capacity");
@@ -454,9 +469,9 @@ int mjpc_b200_rollout_feedback(mjpc_b200_t* h, const float* state, double time, 
                                const float* userdata, const float* u_nom, const float* x_nom, const double* t_nom,
                                const float* gains, const float* du, const float* step_sizes, int mode, int K, int H,
                                float* returns, uint8_t* failure, int* order) {
-  (void)userdata;
   if (!h || !state || !u_nom || !x_nom || !t_nom || !gains || !step_sizes)
     return fail(MJPC_B200_ERR_BAD_ARGUMENT, "rollout_feedback: null pointer");
+  if (userdata && h->nuserdata == 0) return fail(MJPC_B200_ERR_UNSUPPORTED, "rollout_feedback: the model has nuserdata = 0, userdata must be NULL");
   const DevModel& M = h->pack.M;
   if (M.nmocap && !mocap) return fail(MJPC_B200_ERR_BAD_ARGUMENT, "rollout_feedback: mocap required");
   if (K < 1 || H < 1 || mode < 0 || mode > 3) return fail(MJPC_B200_ERR_BAD_ARGUMENT, "rollout_feedback: bad sizes");

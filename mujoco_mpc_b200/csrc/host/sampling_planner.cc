@@ -254,6 +254,10 @@ int mjpc_b200_planner_create(const mjpc_model_blob* model, int num_trajectory, i
   return 0;
 }
 void mjpc_b200_planner_destroy(void* p) { delete (SamplingPlanner*)p; }
+// noise_exploration[0..1] (sampling/planner.cc:85-88): the second std, when > 0, replaces the first with probability 0.2
+void mjpc_b200_planner_set_exploration(void* p, double exploration, double exploration2) {
+  ((SamplingPlanner*)p)->SetExploration(exploration, exploration2);
+}
 void mjpc_b200_planner_reset(void* p, int horizon, const double* initial_repeated_action) {
   ((SamplingPlanner*)p)->Reset(horizon, initial_repeated_action);
 }

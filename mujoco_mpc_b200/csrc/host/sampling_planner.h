@@ -84,6 +84,8 @@ class SamplingPlanner {
   int iteration = 0;
   mjpc_b200_t* gpu() { return gpu_; }
   const std::vector<float>& returns() const { return returns_; }
+  // noise_exploration[0..1] (sampling/planner.cc:85-88)
+  void SetExploration(double e0, double e1) { noise_exploration_[0] = e0; noise_exploration_[1] = e1; }
 
  private:
   mjpc_b200_t* gpu_ = nullptr;

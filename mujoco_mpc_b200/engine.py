@@ -27,7 +27,7 @@ EXPORTS = ["mjpc_b200_version", "mjpc_b200_last_error", "mjpc_b200_create", "mjp
            "mjpc_b200_spec_words", "mjpc_b200_upload_spline_inputs",
            "mjpc_b200_launch_resident", "mjpc_b200_sync", "mjpc_b200_read_returns", "mjpc_b200_stream",
            "mjpc_b200_device_returns", "mjpc_b200_host_spline_sample", "mjpc_b200_host_philox_normal",
-           "mjpc_b200_planner_create", "mjpc_b200_planner_destroy", "mjpc_b200_planner_reset",
+           "mjpc_b200_planner_create", "mjpc_b200_planner_destroy", "mjpc_b200_planner_set_exploration", "mjpc_b200_planner_reset",
            "mjpc_b200_planner_set_state", "mjpc_b200_planner_optimize_policy",
            "mjpc_b200_planner_action_from_policy", "mjpc_b200_planner_get_result",
            "mjpc_b200_ce_planner_create", "mjpc_b200_ce_planner_destroy", "mjpc_b200_ce_planner_reset",
@@ -76,6 +76,7 @@ def load_library():
         lib.mjpc_b200_device_returns.restype = C.c_void_p
         lib.mjpc_b200_host_philox_normal.restype = C.c_double
         lib.mjpc_b200_planner_destroy.argtypes = [C.c_void_p]
+        lib.mjpc_b200_planner_set_exploration.argtypes = [C.c_void_p, C.c_double, C.c_double]
         lib.mjpc_b200_ce_planner_destroy.argtypes = [C.c_void_p]
         lib.mjpc_b200_ilqg_planner_destroy.argtypes = [C.c_void_p]
         lib.mjpc_b200_robust_planner_destroy.argtypes = [C.c_void_p]
@@ -379,6 +380,9 @@ class CppSamplingPlanner:
             self.h = None
 
     __del__ = close
+
+    def set_exploration(self, exploration, exploration2=0.0):
+        self.lib.mjpc_b200_planner_set_exploration(self.h, C.c_double(exploration), C.c_double(exploration2))
 
     def reset(self, initial_repeated_action=None):
         a = _d(initial_repeated_action)

@@ -86,11 +86,17 @@ def resample_nominal(times, values, interp, time, horizon, timestep, P, ctrlrang
     return new_t, new_v
 
 
-def candidate_knots(nominal, sigma, ctrlrange, iteration, N, seed=0x5EED):
-    """Candidate 0 = nominal; candidate i>0 = clamp(nominal + sigma * 0.5*(hi-lo) * z)."""
+def candidate_knots(nominal, sigma, ctrlrange, iteration, N, seed=0x5EED, sigma2=0.0):
+    """Candidate 0 = nominal; candidate i>0 = clamp(nominal + std_i * 0.5*(hi-lo) * z), std_i = sigma, or - when
+    sigma2 > 0 - sigma2 with probability 0.2 (planner.cc:334-338; the Bernoulli draw is word 2 of the Philox block with
+    counter (iteration, candidate, 0xffffffff, 0), as in csrc/host/sampling_planner.cc AddNoiseToPolicy)."""
     P, nu = nominal.shape
     z = philox_normal(iteration, N, P, nu, seed)
     scale = 0.5 * (ctrlrange[:, 1] - ctrlrange[:, 0])
+    if sigma2 > 0:
+        ctr = np.stack([np.full(N, iteration), np.arange(N), np.full(N, 0xFFFFFFFF), np.zeros(N, np.int64)], -1).astype(np.uint32)
+        u = (philox4x32(ctr, (seed, 0))[:, 2].astype(np.float64) + 0.5) / 4294967296.0
+        sigma = np.where(u < 0.2, sigma2, sigma)[:, None, None]
     k = nominal[None] + sigma * scale[None, None, :] * z
     k[0] = nominal
     return np.clip(k, ctrlrange[:, 0], ctrlrange[:, 1])
@@ -106,6 +112,7 @@ class SamplingPlanner:
         self.num_trajectory = int(num_trajectory or num.get("sampling_trajectories", [10])[0])
         self.P = int(num.get("sampling_spline_points", [3])[0])
         self.sigma = float(num.get("sampling_exploration", [0.1])[0])
+        self.sigma2 = 0.0                       # noise_exploration[1] (planner.cc:86): second std, used with p = 0.2
         self.interp = int(num.get("sampling_representation", [2])[0])
         self.timestep = float(m.opt_timestep)
         # steps_ = clamp(horizon/timestep + 1, 1, 512), float truncation (agent.cc:107)
@@ -130,7 +137,8 @@ class SamplingPlanner:
     def make_candidates(self):
         self.times, self.values = resample_nominal(self.times, self.values, self.interp, self.time, self.horizon,
                                                    self.timestep, self.P, self.ctrlrange)
-        return candidate_knots(self.values, self.sigma, self.ctrlrange, self.iteration, self.num_trajectory, self.seed)
+        return candidate_knots(self.values, self.sigma, self.ctrlrange, self.iteration, self.num_trajectory, self.seed,
+                               sigma2=self.sigma2)
 
     def optimize_policy(self):
         knots = self.make_candidates()

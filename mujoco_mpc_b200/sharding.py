@@ -3,9 +3,11 @@
 Candidates are independent units given (state, time, mocap, task snapshot, nominal knots), so the path shards
 with NO data-path collective: rank g owns the contiguous candidate range [g*N/G, (g+1)*N/G) (candidate 0, the
 un-noised nominal, lives on rank 0; mjpc/planners/sampling/planner.cc:374).  The single exchange step per planning
-iteration is an all-gather of the per-candidate returns (N floats: pure latency over NVLink/NVSwitch with NCCL,
-gloo on CPU in the tests); every rank then computes the identical ranking locally, and the owner of the winner
-broadcasts its spline knots (P*nu floats) so all ranks install the same policy.
+iteration is an all-gather of the per-candidate returns (N floats: pure latency over NVLink/NVSwitch).  With an Engine
+that owns an NCCL communicator (Engine.comm_init) all of it - sharding, ncclAllGather on the engine stream, ranking -
+runs inside libmjpc_b200.so (mjpc_b200_rollout_spline_sharded) and this class only forwards; the torch.distributed
+path below is the host-logic twin used by the CPU tests (gloo, oracle backend).  Every rank computes the identical
+ranking and installs the same policy.
 """
 from __future__ import annotations
 
@@ -36,6 +38,12 @@ class ShardedRollouts:
         self.last_local = None
 
     def rollout_spline(self, state, time, mocap, knots, knot_times, interp, H):
+        # product path: the engine owns an NCCL communicator (Engine.comm_init) - sharding, the all-gather of returns on
+        # the engine stream and the ranking all happen inside libmjpc_b200.so (mjpc_b200_rollout_spline_sharded)
+        if getattr(self.backend, "nranks", 1) > 1 and hasattr(self.backend, "rollout_spline_sharded"):
+            N = knots.shape[0]
+            self.last_local = shard_bounds(N, self.world)[self.rank]
+            return self.backend.rollout_spline_sharded(state, time, mocap, knots, knot_times, interp, H)
         import torch
         N = knots.shape[0]
         bounds = shard_bounds(N, self.world)

@@ -559,7 +559,8 @@ void collision(const Model<T>& m, Data<T>& d) {
     else if (t1 == GEOM_SPHERE && t2 == GEOM_BOX) n = collide_sphere_box(raw, p1, s1[0], p2, m2, s2);
     for (int k = 0; k < n; k++) {
       if (!(raw[k].dist < margin)) continue;
-      if ((int)d.contact.size() >= d.maxcon) continue;  // capacity: later contacts are dropped
+      // capacity: MuJoCo raises mjWARN_CONTACTFULL, which the rollout turns into failure (trajectory.cc:169-173)
+      if ((int)d.contact.size() >= d.maxcon) { d.warning = true; continue; }
       Contact<T> c;
       c.dist = raw[k].dist;
       for (int a = 0; a < 3; a++) { c.pos[a] = raw[k].pos[a]; c.frame[a] = raw[k].normal[a]; }
@@ -696,7 +697,7 @@ void make_constraint(const Model<T>& m, Data<T>& d) {
     Contact<T>& c = d.contact[ci];
     int dim = c.dim;
     const int nrow = (pyramidal && dim > 1) ? 2 * (dim - 1) : dim;
-    if ((int)d.efc_pos.size() + nrow > d.maxefc) { c.efc_address = -1; continue; }  // capacity: dropped
+    if ((int)d.efc_pos.size() + nrow > d.maxefc) { c.efc_address = -1; d.warning = true; continue; }  // mjWARN_CNSTRFULL -> failure
     int b1 = m.geom_bodyid[c.geom1], b2 = m.geom_bodyid[c.geom2];
     jac_point(m, d, b1, c.pos, jp1.data(), jr1.data());
     jac_point(m, d, b2, c.pos, jp2.data(), jr2.data());
