@@ -87,6 +87,11 @@ int mjpc_b200_get_info(const mjpc_b200_t* h, mjpc_b200_info* info);
 
 int mjpc_b200_set_task(mjpc_b200_t* h, const mjpc_task_desc* task);
 
+/* Planning-model overrides of Agent::PlanIteration (agent.cc:288-289): opt.timestep = agent_timestep, opt.integrator =
+ * agent_integrator, for the following calls of this handle.  Only the Euler integrator (0) is implemented: any other value
+ * returns MJPC_B200_ERR_UNSUPPORTED. */
+int mjpc_b200_set_options(mjpc_b200_t* h, double timestep, int integrator);
+
 /* MakeDifferentiable (mjpc/utilities.cc:60-75) for the following calls of this handle: on != 0 zeroes solimp[0] of every
  * joint and geom in the model the kernels read, 0 restores the model's values - what Agent::PlanIteration does around
  * OptimizePolicy for gradient-based planners (agent.cc:296-309,346-356; default on for iLQG / iLQS / Gradient,
@@ -304,6 +309,60 @@ int mjpc_b200_host_ilqg_policy_action(const mjpc_model_blob* model, const float*
 /* scalars[6] = {total_return, regularization, improvement, expected, surprise, winner}; nominal states [H][dim_state],
  * actions [H][nu], times [H] (any pointer may be NULL); returns H */
 int mjpc_b200_ilqg_planner_get_result(void* planner, double* scalars, float* states, float* actions, double* times);
+
+/* ---- Gradient planner (csrc/host/gradient_planner.{h,cc}; mjpc/planners/gradient/planner.cc:159-383, gradient.cc:44-107,
+ * spline_mapping.cc): ResamplePolicy, nominal rollout, {model derivatives, cost derivatives, gradient sweep, total derivative
+ * through the spline mapping, K line-search rollouts (ONE mjpc_b200_rollout_spline launch)} x max_rollout.
+ * optimize_policy returns 1 when the return improved, 0 when the nominal was kept, <0 on error. */
+int mjpc_b200_gradient_planner_create(const mjpc_model_blob* model, int num_trajectory, int num_spline_points, int representation,
+                                      double fd_tolerance, double timestep, const double* ctrlrange, int max_horizon, int device,
+                                      void** out);
+void mjpc_b200_gradient_planner_destroy(void* planner);
+void mjpc_b200_gradient_planner_reset(void* planner, int horizon, const double* initial_repeated_action);
+void mjpc_b200_gradient_planner_set_state(void* planner, const double* state, double time, const double* mocap);
+int mjpc_b200_gradient_planner_optimize_policy(void* planner, int horizon);
+void mjpc_b200_gradient_planner_action_from_policy(void* planner, double* action, double time, int use_previous);
+/* scalars[6] = {total_return, winner, action_step, expected, improvement, surprise}; parameters [P][nu], times [P] */
+int mjpc_b200_gradient_planner_get_result(void* planner, double* scalars, double* parameters, double* times);
+/* SplineMapping::Compute (gradient/spline_mapping.cc) as scalar weights W [num_output][num_input]; host only */
+void mjpc_b200_host_spline_mapping(int representation, const double* input_times, int num_input, const double* output_times,
+                                   int num_output, double* W);
+
+/* ---- iLQS planner (csrc/host/gradient_planner.{h,cc}; mjpc/planners/ilqs/planner.cc:87-215): Predictive Sampling first;
+ * when it does not improve, one iLQG iteration seeded with the sampling nominal; when sampling follows iLQG the trajectory
+ * policy is converted to spline parameters through the least-squares inverse of the spline mapping. */
+int mjpc_b200_ilqs_planner_create(const mjpc_model_blob* model, int num_trajectory, int num_spline_points, int interpolation,
+                                  double exploration, double timestep, const double* ctrlrange, uint32_t seed,
+                                  int ilqg_num_rollouts, int ilqg_representation, double fd_tolerance, int max_horizon, int device,
+                                  void** out);
+void mjpc_b200_ilqs_planner_destroy(void* planner);
+void mjpc_b200_ilqs_planner_reset(void* planner, int horizon, const double* initial_repeated_action);
+void mjpc_b200_ilqs_planner_set_state(void* planner, const double* state, double time, const double* mocap);
+void mjpc_b200_ilqs_planner_set_exploration(void* planner, double exploration);
+int mjpc_b200_ilqs_planner_optimize_policy(void* planner, int horizon);
+void mjpc_b200_ilqs_planner_action_from_policy(void* planner, double* action, const double* state, double time, int use_previous);
+/* scalars[4] = {active_policy (0 sampling, 1 iLQG), sampling winner return, iLQG total_return, sampling winner}; returns active_policy */
+int mjpc_b200_ilqs_planner_get_result(void* planner, double* scalars);
+
+/* ---- Agent::PlanIteration glue (csrc/host/agent.{h,cc}; mjpc/agent.cc:85-107,150-164,283-357): owns the planner selected
+ * by agent_planner (0 Sampling, 1 Gradient, 2 iLQG, 3 iLQS, 4 Robust, 5 Cross-Entropy; mjpc/planners/include.h:26-34) and does
+ * per iteration what the reference does around OptimizePolicy: steps_ = int(max(min(horizon / timestep + 1, 512), 1)),
+ * timestep / integrator override, MakeDifferentiable for gradient-based planners (restored afterwards), SetState, the
+ * residual snapshot (set_task on every engine handle of the planner), OptimizePolicy(steps_) - or NominalTrajectory when
+ * planning is disabled.
+ * settings[20] = {planner, horizon, timestep, integrator, differentiable (-1 = the reference default), num_trajectory,
+ *   num_spline_points, representation, exploration, ilqg_num_rollouts, ilqg_representation, fd_tolerance, n_elite, std_min,
+ *   explore_fraction, robust_candidates, robust_repetitions, robust_xfrc, robust_xfrc_rate, seed} */
+int mjpc_b200_agent_steps(double horizon, double timestep);
+int mjpc_b200_agent_create(const mjpc_model_blob* model, const double* settings, const double* ctrlrange, int device, void** out);
+void mjpc_b200_agent_destroy(void* agent);
+void mjpc_b200_agent_reset(void* agent, const double* initial_repeated_action);
+void mjpc_b200_agent_set_state(void* agent, const double* state, double time, const double* mocap);
+void mjpc_b200_agent_set_task(void* agent, const mjpc_task_desc* task);
+void mjpc_b200_agent_set_plan_enabled(void* agent, int on);
+int mjpc_b200_agent_plan_iteration(void* agent);
+int mjpc_b200_agent_get_steps(void* agent);
+void mjpc_b200_agent_action_from_policy(void* agent, double* action, const double* state, double time, int use_previous);
 
 #ifdef __cplusplus
 }

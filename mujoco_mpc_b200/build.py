@@ -34,6 +34,8 @@ def _compile(verbose):
                                                                            os.path.join(CSRC, "host", "cross_entropy_planner.cc"),
                                                                            os.path.join(CSRC, "host", "ilqg_planner.cc"),
                                                                            os.path.join(CSRC, "host", "robust_planner.cc"),
+                                                                           os.path.join(CSRC, "host", "gradient_planner.cc"),
+                                                                           os.path.join(CSRC, "host", "agent.cc"),
                                                                            os.path.join(CSRC, "host", "task_transition.cc")]
     subprocess.check_call(cmd, cwd=CSRC)
 

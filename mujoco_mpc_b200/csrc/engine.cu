@@ -394,6 +394,16 @@ int mjpc_b200_set_task(mjpc_b200_t* h, const mjpc_task_desc* task) {
   return upload_task(h);
 }
 
+// Agent::PlanIteration's planning-model overrides (agent.cc:288-289): model_->opt.timestep = agent_timestep,
+// model_->opt.integrator = agent_integrator.  The timestep is a live header option (no re-upload); only the Euler
+// integrator (mjINT_EULER = 0) is implemented on the device - anything else is refused, never silently replaced.
+int mjpc_b200_set_options(mjpc_b200_t* h, double timestep, int integrator) {
+  if (!h || !(timestep > 0)) return fail(MJPC_B200_ERR_BAD_ARGUMENT, "set_options: bad argument");
+  if (integrator != 0) return fail(MJPC_B200_ERR_UNSUPPORTED, "set_options: only the Euler integrator (0) is implemented");
+  h->pack.M.timestep = (float)timestep;
+  return 0;
+}
+
 // Agent::PlanIteration's MakeDifferentiable (agent.cc:296-309, utilities.cc:60-75): while on, every joint's and geom's
 // solimp[0] reads as 0 in the kernels (contact pairs take their solimp from the geoms here); off restores the model's own
 // values (agent.cc:346-356).  Gradient-based planners (iLQG, iLQS, Gradient) plan with it on by default.

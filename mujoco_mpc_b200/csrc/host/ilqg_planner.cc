@@ -317,6 +317,16 @@ int iLQGPlanner::Iteration(int horizon) {
   return 1;
 }
 
+void iLQGPlanner::SetCandidateTrajectory(const Trajectory& tr) {
+  const size_t H = std::min<size_t>(tr.horizon, Hmax_);
+  H_ = (int)H;
+  std::copy(tr.states.begin(), tr.states.begin() + H * ds_, c_states_.begin());
+  std::copy(tr.actions.begin(), tr.actions.begin() + H * nu_, c_actions_.begin());
+  std::copy(tr.times.begin(), tr.times.begin() + H, c_times_.begin());
+  std::copy(tr.residual.begin(), tr.residual.begin() + H * nr_, c_residual_.begin());
+  c_return_ = tr.total_return;
+}
+
 int iLQGPlanner::OptimizePolicy(int horizon) {
   if (NominalTrajectory(horizon) < 0) return -1;
   return Iteration(horizon);

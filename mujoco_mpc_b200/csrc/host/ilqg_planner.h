@@ -65,6 +65,12 @@ class iLQGPlanner {
   int winner = 0;
   mjpc_b200_t* gpu() { return gpu_; }
   int horizon() const { return live_H_; }
+  // candidate_policy[0] / the last K rollouts, as iLQSPlanner needs them (ilqs/planner.cc:98-215)
+  const std::vector<double>& candidate_times() const { return c_times_; }
+  const std::vector<float>& candidate_actions() const { return c_actions_; }
+  double candidate_return() const { return c_return_; }
+  void SetCandidateTrajectory(const Trajectory& tr);      // candidate_policy[0].trajectory = tr
+  float rollout_return(int j) const { return ret_[j]; }   // trajectory[j].total_return of the last K rollouts
   int dim_state() const { return ds_; }
   int dim_action() const { return nu_; }
 

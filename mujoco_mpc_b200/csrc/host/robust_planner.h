@@ -26,6 +26,7 @@ class RobustPlanner {
   }
   const Trajectory* BestTrajectory() { return delegate_->BestTrajectory(); }
   SamplingPlanner* delegate() { return delegate_.get(); }
+  mjpc_b200_t* noisy() { return noisy_; }
   const std::vector<double>& scores() const { return scores_; }
 
  private:

@@ -208,6 +208,27 @@ void SamplingPlanner::ActionFromPolicy(double* action, double time, bool use_pre
   (use_previous ? previous_policy : policy).Action(action, time);
 }
 
+int SamplingPlanner::FetchTrajectory(int candidate, int horizon, Trajectory* t) {
+  const mjpc_b200_info& in = info_;
+  const size_t H = horizon;
+  t->horizon = horizon; t->dim_state = in.dim_state; t->dim_action = in.nu; t->dim_residual = in.num_residual;
+  t->dim_trace = 3 * in.num_trace;
+  t->states.resize(H * in.dim_state); t->actions.resize(H * in.nu); t->times.resize(H);
+  t->residual.resize(H * in.num_residual); t->costs.resize(H); t->trace.resize(H * t->dim_trace);
+  if (mjpc_b200_fetch_trajectory(gpu_, candidate, t->states.data(), t->actions.data(), t->times.data(), t->residual.data(),
+                                 t->costs.data(), t->trace.data()))
+    return -1;
+  t->total_return = returns_[candidate];
+  t->failure = failure_[candidate];
+  return 0;
+}
+
+void SamplingPlanner::SetPolicy(const double* times, const double* parameters, int num_nodes) {
+  const std::unique_lock<std::shared_mutex> lock(mtx_);
+  policy.plan.Clear();
+  for (int t = 0; t < num_nodes; t++) policy.plan.AddNode(times[t], parameters + (size_t)t * nu_);
+}
+
 const Trajectory* SamplingPlanner::BestTrajectory() {
   mjpc_b200_info& in = info_;
   const int H = in.max_horizon;

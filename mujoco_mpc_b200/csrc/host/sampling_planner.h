@@ -73,6 +73,11 @@ class SamplingPlanner {
   void ActionFromPolicy(double* action, double time, bool use_previous = false);   // :229-237
   void CopyCandidateToPolicy(int candidate);          // :534-543
   const Trajectory* BestTrajectory();
+  int FetchTrajectory(int candidate, int horizon, Trajectory* out);   // trajectory[candidate] of the last Rollouts
+  void SetPolicy(const double* times, const double* parameters, int num_nodes);   // policy.plan = nodes (ilqs/planner.cc:160-172)
+  double time() const { return time_; }
+  double timestep() const { return timestep_; }
+  SplineInterpolation interpolation() const { return interpolation_; }
   double CandidateScore(int candidate) const { return returns_[trajectory_order[candidate]]; }
   int NumParameters() const { return nu_ * policy.num_spline_points; }
 

@@ -40,6 +40,16 @@ EXPORTS = ["mjpc_b200_version", "mjpc_b200_last_error", "mjpc_b200_create", "mjp
            "mjpc_b200_robust_planner_create", "mjpc_b200_robust_planner_destroy", "mjpc_b200_robust_planner_reset",
            "mjpc_b200_robust_planner_set_state", "mjpc_b200_robust_planner_optimize_policy",
            "mjpc_b200_robust_planner_action_from_policy", "mjpc_b200_robust_planner_get_result",
+           "mjpc_b200_gradient_planner_create", "mjpc_b200_gradient_planner_destroy", "mjpc_b200_gradient_planner_reset",
+           "mjpc_b200_gradient_planner_set_state", "mjpc_b200_gradient_planner_optimize_policy",
+           "mjpc_b200_gradient_planner_action_from_policy", "mjpc_b200_gradient_planner_get_result",
+           "mjpc_b200_host_spline_mapping", "mjpc_b200_ilqs_planner_create", "mjpc_b200_ilqs_planner_destroy",
+           "mjpc_b200_ilqs_planner_reset", "mjpc_b200_ilqs_planner_set_state", "mjpc_b200_ilqs_planner_set_exploration",
+           "mjpc_b200_ilqs_planner_optimize_policy", "mjpc_b200_ilqs_planner_action_from_policy",
+           "mjpc_b200_ilqs_planner_get_result",
+           "mjpc_b200_set_options", "mjpc_b200_agent_steps", "mjpc_b200_agent_create", "mjpc_b200_agent_destroy",
+           "mjpc_b200_agent_reset", "mjpc_b200_agent_set_state", "mjpc_b200_agent_set_task", "mjpc_b200_agent_set_plan_enabled",
+           "mjpc_b200_agent_plan_iteration", "mjpc_b200_agent_get_steps", "mjpc_b200_agent_action_from_policy",
            "mjpc_b200_quadruped_transition_create", "mjpc_b200_quadruped_transition_destroy",
            "mjpc_b200_quadruped_transition_step", "mjpc_b200_quadruped_transition_set", "mjpc_b200_track_transition_create",
            "mjpc_b200_track_transition_destroy", "mjpc_b200_track_transition_step"]
@@ -80,6 +90,12 @@ def load_library():
         lib.mjpc_b200_ce_planner_destroy.argtypes = [C.c_void_p]
         lib.mjpc_b200_ilqg_planner_destroy.argtypes = [C.c_void_p]
         lib.mjpc_b200_robust_planner_destroy.argtypes = [C.c_void_p]
+        lib.mjpc_b200_gradient_planner_destroy.argtypes = [C.c_void_p]
+        lib.mjpc_b200_agent_destroy.argtypes = [C.c_void_p]
+        lib.mjpc_b200_agent_steps.argtypes = [C.c_double, C.c_double]
+        lib.mjpc_b200_set_options.argtypes = [C.c_void_p, C.c_double, C.c_int]
+        lib.mjpc_b200_ilqs_planner_destroy.argtypes = [C.c_void_p]
+        lib.mjpc_b200_ilqs_planner_set_exploration.argtypes = [C.c_void_p, C.c_double]
         for n in ("mjpc_b200_quadruped_transition_create", "mjpc_b200_track_transition_create"):
             getattr(lib, n).restype = C.c_void_p
         lib.mjpc_b200_quadruped_transition_destroy.argtypes = [C.c_void_p]
@@ -93,6 +109,22 @@ def load_library():
 
 class EngineError(RuntimeError):
     pass
+
+
+def host_ilqg_policy_action(model, u_nom, x_nom, t_nom, gains, representation, feedback_scaling, state, time):
+    """iLQGPolicy::Action (ilqg/policy.cc:82-161) on the host through mjpc_b200_host_ilqg_policy_action (no device)."""
+    lib = load_library()
+    blob = to_blob(model)
+    buf = C.create_string_buffer(blob, len(blob))
+    mb = ModelBlob(C.cast(buf, C.c_void_p), len(blob))
+    u, x, t, g = _f(u_nom), _f(x_nom), _d(t_nom), _f(gains)
+    st = _d(state)
+    out = np.zeros(model.nu)
+    rc = lib.mjpc_b200_host_ilqg_policy_action(C.byref(mb), _pf(u), _pf(x), _pd(t), _pf(g), int(u.shape[0]), int(representation),
+                                               C.c_double(feedback_scaling), _pd(st), C.c_double(time), _pd(out))
+    if rc != 0:
+        raise EngineError(f"host_ilqg_policy_action failed ({rc})")
+    return out
 
 
 def _f(a):
@@ -148,6 +180,10 @@ class Engine:
         w, p, s = _d(weight), _d(parameters), _d(task_state)
         td = TaskDesc(_pd(w), _pd(p), _pd(s), float(self.m.task_risk if risk is None else risk))
         self._check(self.lib.mjpc_b200_set_task(self.h, C.byref(td)))
+
+    def set_options(self, timestep, integrator=0):
+        """Agent::PlanIteration's planning-model overrides (agent.cc:288-289)."""
+        self._check(self.lib.mjpc_b200_set_options(self.h, C.c_double(timestep), int(integrator)))
 
     def set_differentiable(self, on=True):
         """MakeDifferentiable (utilities.cc:60-75): solimp[0] = 0 for joints and geoms while planning with gradients."""
@@ -579,4 +615,193 @@ class CppRobustPlanner:
     def action_from_policy(self, time, use_previous=False):
         a = np.zeros(self.nu)
         self.lib.mjpc_b200_robust_planner_action_from_policy(self.h, _pd(a), C.c_double(time), int(use_previous))
+        return a
+
+
+def host_spline_mapping(representation, input_times, output_times):
+    """SplineMapping::Compute (gradient/spline_mapping.cc) as scalar weights W [num_output][num_input]."""
+    lib = load_library()
+    ti, to = _d(input_times), _d(output_times)
+    W = np.zeros((len(to), len(ti)))
+    lib.mjpc_b200_host_spline_mapping(int(representation), _pd(ti), len(ti), _pd(to), len(to), _pd(W))
+    return W
+
+
+class CppGradientPlanner:
+    """The C++ GradientPlanner (csrc/host/gradient_planner.cc) through its C wrappers."""
+
+    def __init__(self, model, horizon, num_trajectory=8, num_spline_points=5, representation=1, fd_tolerance=1e-3, device=0):
+        self.lib = load_library()
+        self.m = model
+        self._blob = to_blob(model)
+        self._buf = C.create_string_buffer(self._blob, len(self._blob))
+        mb = ModelBlob(C.cast(self._buf, C.c_void_p), len(self._blob))
+        cr = _d(np.asarray(model.actuator_ctrlrange, float).reshape(-1))
+        self.horizon, self.P, self.nu = int(horizon), int(num_spline_points), model.nu
+        h = C.c_void_p()
+        rc = self.lib.mjpc_b200_gradient_planner_create(C.byref(mb), int(num_trajectory), self.P, int(representation),
+                                                        C.c_double(fd_tolerance), C.c_double(float(model.opt_timestep)), _pd(cr),
+                                                        self.horizon, int(device), C.byref(h))
+        if rc != 0:
+            raise EngineError(f"gradient_planner_create failed ({rc}): {self.lib.mjpc_b200_last_error().decode()}")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mjpc_b200_gradient_planner_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def reset(self, initial_repeated_action=None):
+        a = _d(initial_repeated_action)
+        self.lib.mjpc_b200_gradient_planner_reset(self.h, self.horizon, _pd(a))
+
+    def set_state(self, state, time, mocap):
+        s, mc = _d(state), _d(mocap)
+        self.lib.mjpc_b200_gradient_planner_set_state(self.h, _pd(s), C.c_double(time), _pd(mc))
+
+    def optimize_policy(self):
+        rc = self.lib.mjpc_b200_gradient_planner_optimize_policy(self.h, self.horizon)
+        if rc < 0:
+            raise EngineError(f"gradient_planner_optimize_policy failed: {self.lib.mjpc_b200_last_error().decode()}")
+        return rc
+
+    def result(self):
+        sc = np.zeros(6); p = np.zeros((self.P, self.nu)); t = np.zeros(self.P)
+        self.lib.mjpc_b200_gradient_planner_get_result(self.h, _pd(sc), _pd(p), _pd(t))
+        return dict(total_return=sc[0], winner=int(sc[1]), action_step=sc[2], expected=sc[3], improvement=sc[4],
+                    surprise=sc[5], parameters=p, times=t)
+
+    def action_from_policy(self, time, use_previous=False):
+        a = np.zeros(self.nu)
+        self.lib.mjpc_b200_gradient_planner_action_from_policy(self.h, _pd(a), C.c_double(time), int(use_previous))
+        return a
+
+
+class CppILQSPlanner:
+    """The C++ iLQSPlanner (csrc/host/gradient_planner.cc) through its C wrappers."""
+
+    def __init__(self, model, horizon, num_trajectory=8, num_rollouts=6, fd_tolerance=1e-3, seed=0x5EED, device=0):
+        self.lib = load_library()
+        m = self.m = model
+        self._blob = to_blob(model)
+        self._buf = C.create_string_buffer(self._blob, len(self._blob))
+        mb = ModelBlob(C.cast(self._buf, C.c_void_p), len(self._blob))
+        num = m.numeric
+        cr = _d(np.asarray(m.actuator_ctrlrange, float).reshape(-1))
+        self.horizon, self.nu = int(horizon), m.nu
+        h = C.c_void_p()
+        rc = self.lib.mjpc_b200_ilqs_planner_create(C.byref(mb), int(num_trajectory), int(num.get("sampling_spline_points", [3])[0]),
+                                                    int(num.get("sampling_representation", [2])[0]),
+                                                    C.c_double(float(num.get("sampling_exploration", [0.1])[0])),
+                                                    C.c_double(float(m.opt_timestep)), _pd(cr), C.c_uint32(seed), int(num_rollouts),
+                                                    int(num.get("ilqg_representation", [1])[0]), C.c_double(fd_tolerance),
+                                                    self.horizon, int(device), C.byref(h))
+        if rc != 0:
+            raise EngineError(f"ilqs_planner_create failed ({rc}): {self.lib.mjpc_b200_last_error().decode()}")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mjpc_b200_ilqs_planner_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def reset(self, initial_repeated_action=None):
+        a = _d(initial_repeated_action)
+        self.lib.mjpc_b200_ilqs_planner_reset(self.h, self.horizon, _pd(a))
+
+    def set_state(self, state, time, mocap):
+        s, mc = _d(state), _d(mocap)
+        self.lib.mjpc_b200_ilqs_planner_set_state(self.h, _pd(s), C.c_double(time), _pd(mc))
+
+    def set_exploration(self, sigma):
+        self.lib.mjpc_b200_ilqs_planner_set_exploration(self.h, C.c_double(sigma))
+
+    def optimize_policy(self):
+        rc = self.lib.mjpc_b200_ilqs_planner_optimize_policy(self.h, self.horizon)
+        if rc < 0:
+            raise EngineError(f"ilqs_planner_optimize_policy failed: {self.lib.mjpc_b200_last_error().decode()}")
+        return rc
+
+    def result(self):
+        sc = np.zeros(4)
+        self.lib.mjpc_b200_ilqs_planner_get_result(self.h, _pd(sc))
+        return dict(active_policy=int(sc[0]), sampling_return=sc[1], ilqg_return=sc[2], sampling_winner=int(sc[3]))
+
+    def action_from_policy(self, time, state=None, use_previous=False):
+        a = np.zeros(self.nu); st = _d(state)
+        self.lib.mjpc_b200_ilqs_planner_action_from_policy(self.h, _pd(a), _pd(st), C.c_double(time), int(use_previous))
+        return a
+
+
+class CppAgent:
+    """Agent::PlanIteration glue (csrc/host/agent.cc) through its C wrappers; settings mirror the task XML numerics."""
+    PLANNERS = {"sampling": 0, "gradient": 1, "ilqg": 2, "ilqs": 3, "robust": 4, "cross_entropy": 5}
+
+    def __init__(self, model, planner="sampling", horizon=None, timestep=None, integrator=0, differentiable=-1, num_trajectory=None,
+                 num_spline_points=None, representation=None, exploration=None, ilqg_num_rollouts=10, ilqg_representation=1,
+                 fd_tolerance=1e-3, seed=0x5EED, device=0):
+        self.lib = load_library()
+        m = self.m = model
+        num = m.numeric
+        self._blob = to_blob(model)
+        self._buf = C.create_string_buffer(self._blob, len(self._blob))
+        mb = ModelBlob(C.cast(self._buf, C.c_void_p), len(self._blob))
+        g = lambda k, d: float(num.get(k, [d])[0])
+        st = np.array([self.PLANNERS[planner] if isinstance(planner, str) else planner,
+                       g("agent_horizon", 0.5) if horizon is None else horizon,
+                       g("agent_timestep", 0.01) if timestep is None else timestep, integrator, differentiable,
+                       g("sampling_trajectories", 10) if num_trajectory is None else num_trajectory,
+                       g("sampling_spline_points", 3) if num_spline_points is None else num_spline_points,
+                       g("sampling_representation", 2) if representation is None else representation,
+                       g("sampling_exploration", 0.1) if exploration is None else exploration,
+                       ilqg_num_rollouts, ilqg_representation, fd_tolerance, 0, g("std_min", 0.01), g("explore_fraction", 0.0),
+                       g("robust_candidates", -1), g("robust_repetitions", 5), g("robust_xfrc", 0.1), g("robust_xfrc_rate", 0.1),
+                       seed], float)
+        cr = _d(np.asarray(m.actuator_ctrlrange, float).reshape(-1))
+        h = C.c_void_p()
+        rc = self.lib.mjpc_b200_agent_create(C.byref(mb), _pd(st), _pd(cr), int(device), C.byref(h))
+        if rc != 0:
+            raise EngineError(f"agent_create failed ({rc}): {self.lib.mjpc_b200_last_error().decode()}")
+        self.h, self.nu = h, m.nu
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mjpc_b200_agent_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    @property
+    def steps(self):
+        return int(self.lib.mjpc_b200_agent_get_steps(self.h))
+
+    def reset(self, initial_repeated_action=None):
+        a = _d(initial_repeated_action)
+        self.lib.mjpc_b200_agent_reset(self.h, _pd(a))
+
+    def set_state(self, state, time, mocap):
+        s, mc = _d(state), _d(mocap)
+        self.lib.mjpc_b200_agent_set_state(self.h, _pd(s), C.c_double(time), _pd(mc))
+
+    def set_task(self, weight=None, parameters=None, task_state=None, risk=None):
+        w, p, s = _d(weight), _d(parameters), _d(task_state)
+        td = TaskDesc(_pd(w), _pd(p), _pd(s), float(self.m.task_risk if risk is None else risk))
+        self.lib.mjpc_b200_agent_set_task(self.h, C.byref(td))
+
+    def set_plan_enabled(self, on):
+        self.lib.mjpc_b200_agent_set_plan_enabled(self.h, int(bool(on)))
+
+    def plan_iteration(self):
+        rc = self.lib.mjpc_b200_agent_plan_iteration(self.h)
+        if rc < 0:
+            raise EngineError(f"agent_plan_iteration failed ({rc}): {self.lib.mjpc_b200_last_error().decode()}")
+        return rc
+
+    def action_from_policy(self, time, state=None, use_previous=False):
+        a = np.zeros(self.nu); st = _d(state)
+        self.lib.mjpc_b200_agent_action_from_policy(self.h, _pd(a), _pd(st), C.c_double(time), int(use_previous))
         return a

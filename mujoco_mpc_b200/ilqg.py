@@ -160,6 +160,7 @@ class ILQGPlanner:
         c["gains"], c["du"], self.dV = np.asarray(bp["K"], float), np.asarray(bp["du"], float), np.asarray(bp["dV"], float)
         ret, fail, _ = self.backend.rollout_feedback(self.state, self.time, self.mocap, c["actions"], c["states"],
                                                      c["times"], c["gains"], c["du"], steps, 3)
+        self.last_returns = np.asarray(ret, float)      # trajectory[j].total_return of the K action rollouts
         best = self._best(ret, fail)
         if best == -1:
             return False                 # nothing is published (:548-550)
@@ -181,6 +182,12 @@ class ILQGPlanner:
         self.gains, self.du = c["gains"], c["du"]
         self.total_return = c["total_return"]
         return True
+
+    # -- iLQGPolicy::Action on the live policy (ilqg/policy.cc:82-161) through the host library
+    def action_from_policy(self, time, state=None):
+        from .engine import host_ilqg_policy_action
+        return host_ilqg_policy_action(self.model, self.actions, self.states, self.times, self.gains, self.representation,
+                                       1.0, state, time)
 
     # -- iLQGPlanner::OptimizePolicy
     def optimize_policy(self):

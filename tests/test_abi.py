@@ -74,3 +74,14 @@ def test_cpp_host_spline_and_noise_match_python_mirror():
         zc = lib.mjpc_b200_host_philox_normal(ctypes.c_uint32(0x5EED), ctypes.c_uint32(7), ctypes.c_uint32(i),
                                               ctypes.c_uint32(k), ctypes.c_uint32(d))
         assert abs(zc - z[i, k, d]) < 1e-12
+
+
+def test_agent_steps_rule():
+    """agent.cc:107,292-293: steps_ = max(min(horizon / timestep + 1, 512), 1) truncated to int."""
+    from mujoco_mpc_b200.engine import load_library
+    lib = load_library()
+    st = lib.mjpc_b200_agent_steps
+    assert st(0.47, 0.01) == 47          # 0.47 / 0.01 + 1 = 47.99999999999999 -> 47
+    assert st(0.4701, 0.01) == 48        # the Shadow-Hand workaround of SURVEY.md 8d
+    assert st(0.63, 0.01) == 64 and st(0.31, 0.01) == 32 and st(0.635, 0.005) == 128
+    assert st(100.0, 0.01) == 512 and st(0.0, 0.01) == 1

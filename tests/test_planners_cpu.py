@@ -187,3 +187,45 @@ def test_host_ilqg_policy_action_matches_oracle():
                         ref = o.ilqg_policy_action(u, x, t, K, mode, 0.0, state, time)
                     np.testing.assert_allclose(out, ref, atol=1e-9, err_msg="mode %d time %.4f" % (mode, time))
                     assert (np.abs(out) <= 1 + 1e-12).all()
+
+
+def test_gradient_and_ilqs_mirrors_on_oracle():
+    """The Gradient / iLQS host logic (mujoco_mpc_b200/gradient.py) on the CPU oracle backend: the spline mapping is the
+    exact linear operator of the spline sampler, the gradient planner descends monotonically, iLQS switches to iLQG when
+    sampling cannot improve and converts back (ilqs/planner.cc:98-172)."""
+    from conftest import OracleBackend
+    from mujoco_mpc_b200.gradient import GradientPlanner, ILQSPlanner, gradient_sweep, spline_mapping
+    from mujoco_mpc_b200.planner import sample_spline
+    rng = np.random.default_rng(0)
+    for rep in (0, 1, 2):
+        ti = np.linspace(0.2, 0.7, 6); to = np.linspace(0.2, 0.69, 30); p = rng.standard_normal((6, 2))
+        W = spline_mapping(ti, to, rep)
+        np.testing.assert_allclose(W @ p, np.stack([sample_spline(ti, p, rep, t) for t in to]), atol=1e-12)
+    # gradient sweep against brute-force differentiation of a random linear-quadratic chain
+    T, n, mm = 5, 3, 2
+    A = rng.standard_normal((T, n, n)) * 0.3; B = rng.standard_normal((T, n, mm)); cx = rng.standard_normal((T, n)); cu = rng.standard_normal((T, mm))
+    k, dV0 = gradient_sweep(A, B, cx, cu)
+    def total(du):          # first-order cost change of action perturbations du [T-1][m] through the linear dynamics
+        dx = np.zeros(n); c = 0.0
+        for t in range(T - 1):
+            c += cx[t] @ dx + cu[t] @ du[t]; dx = A[t] @ dx + B[t] @ du[t]
+        return c + cx[T - 1] @ dx
+    for t in range(T - 1):
+        for j in range(mm):
+            du = np.zeros((T - 1, mm)); du[t, j] = 1.0
+            assert abs(total(du) + k[t, j]) < 1e-12          # k = -dJ/du
+    m = get_model("particle")
+    pl = GradientPlanner(m, OracleBackend(m, threads=2), horizon=26, num_trajectory=8, num_spline_points=5, representation=1, fd_tolerance=1e-5)
+    pl.set_state(np.zeros(4), 0.0, mocap_of(m))
+    rets = []
+    for _ in range(12):
+        pl.optimize_policy(); rets.append(pl.total_return)
+    assert rets[-1] < rets[0] and all(b <= a + 1e-12 for a, b in zip(rets, rets[1:]))
+    il = ILQSPlanner(m, OracleBackend(m, threads=2), OracleBackend(m, threads=2), horizon=26, num_trajectory=8, num_rollouts=6, fd_tolerance=1e-5)
+    il.set_state(np.zeros(4), 0.0, mocap_of(m))
+    seq = []
+    for it in range(8):
+        il.sampling.sigma = 0.0 if 2 <= it < 6 else 0.1
+        il.optimize_policy(); seq.append(il.active_policy)
+    assert seq[:2] == [0, 0] and 1 in seq
+    assert il.ilqg.total_return < float(il.sampling.returns[0]) * 1.5
