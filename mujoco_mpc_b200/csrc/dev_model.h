@@ -251,7 +251,8 @@ inline ModelPack pack_model(const void* data, size_t nbytes, int maxcon, int max
     }
     int widest = 0;
     for (size_t k = 0; k < g1.size(); k++) {
-      const uint64_t mm = chain(gb[g1[k]]) | chain(gb[g2[k]]);
+      const uint64_t c1 = chain(gb[g1[k]]), c2m = chain(gb[g2[k]]);
+      const uint64_t mm = (c1 && c2m) ? (c1 ^ c2m) : (c1 | c2m);   // two moving bodies: common ancestor dofs cancel
       int cnt = 0;
       for (int r = 0; r < nv; r++) cnt += (int)((mm >> r) & 1);
       widest = std::max(widest, cnt);

@@ -347,6 +347,38 @@ __device__ __forceinline__ int collide_sphere_box(RawContact* out, const float* 
   return 1;
 }
 
+// [EXT] mjc_CapsuleCapsule restated (same algorithm as oracle/physics.h collide_capsule_capsule): nearest points of the
+// two axis segments, then a sphere test there; (nearly) parallel axes test the segment ends and may return two contacts
+__device__ __forceinline__ int collide_capsule_capsule(RawContact* out, const float* p1, const float* m1, const float* s1,
+                                                        const float* p2, const float* m2, const float* s2, float margin) {
+  const float a1[3] = {m1[2], m1[5], m1[8]}, a2[3] = {m2[2], m2[5], m2[8]};
+  const float dif[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]};
+  const float ma = dot3(a1, a1), mb = -dot3(a1, a2), mc = dot3(a2, a2), u = -dot3(a1, dif), v = dot3(a2, dif);
+  const float det = ma * mc - mb * mb;
+  const float r1 = s1[0], l1 = s1[1], r2 = s2[0], l2 = s2[1];
+  auto sphere = [&](RawContact* o, float x1, float x2) {
+    float v1[3], v2[3];
+    for (int k = 0; k < 3; k++) { v1[k] = p1[k] + a1[k] * x1; v2[k] = p2[k] + a2[k] * x2; }
+    collide_sphere_sphere(o, v1, r1, v2, r2);
+    return o->dist <= margin ? 1 : 0;
+  };
+  if (fabsf(det) >= kMinVal) {
+    float x1 = (mc * u - mb * v) / det, x2 = (ma * v - mb * u) / det;
+    if (x1 > l1) { x1 = l1; x2 = (v - mb * l1) / mc; }
+    else if (x1 < -l1) { x1 = -l1; x2 = (v + mb * l1) / mc; }
+    if (x2 > l2) { x2 = l2; x1 = fmaxf(-l1, fminf(l1, (u - mb * l2) / ma)); }
+    else if (x2 < -l2) { x2 = -l2; x1 = fmaxf(-l1, fminf(l1, (u + mb * l2) / ma)); }
+    return sphere(out, x1, x2);
+  }
+  int n = sphere(out, l1, fmaxf(-l2, fminf(l2, (v - mb * l1) / mc)));
+  n += sphere(out + n, -l1, fmaxf(-l2, fminf(l2, (v + mb * l1) / mc)));
+  if (n >= 2) return n;
+  n += sphere(out + n, fmaxf(-l1, fminf(l1, (u - mb * l2) / ma)), l2);
+  if (n >= 2) return n;
+  n += sphere(out + n, fmaxf(-l1, fminf(l1, (u + mb * l2) / ma)), -l2);
+  return n;
+}
+
 template <class SP>
 __device__ __noinline__ void k_collision(Ctx& c) {
   auto&& M = SP::model(c);
@@ -391,6 +423,7 @@ __device__ __noinline__ void k_collision(Ctx& c) {
         else if (t1 == GEOM_SPHERE && t2 == GEOM_SPHERE) n = collide_sphere_sphere(raw, p1, s1[0], p2, s2[0]);
         else if (t1 == GEOM_SPHERE && t2 == GEOM_CAPSULE) n = collide_sphere_capsule(raw, p1, s1[0], p2, m2, s2);
         else if (t1 == GEOM_SPHERE && t2 == GEOM_BOX) n = collide_sphere_box(raw, p1, s1[0], p2, m2, s2);
+        else if (t1 == GEOM_CAPSULE && t2 == GEOM_CAPSULE) n = collide_capsule_capsule(raw, p1, m1, s1, p2, m2, s2, margin);
       }
       for (int k = 0; k < n; k++)
         if (raw[k].dist < margin) { if (cnt != k) raw[cnt] = raw[k]; cnt++; }
@@ -597,10 +630,17 @@ __device__ __noinline__ void k_make_constraint(Ctx& c) {
         cnd[ci] = nd;
         continue;
       }
+      // contact between two moving bodies: the relative Jacobian vanishes identically on their COMMON ancestor dofs
+      // (same point, same motion axis, opposite signs), so the dof list is the symmetric difference of the two chains
+      const int ba = gbody[g1a[ci]], bbb = gbody[g2a[ci]];
+      const unsigned clo = (unsigned)MI(body_dofmask_lo)[ba] & (unsigned)MI(body_dofmask_lo)[bbb];
+      const unsigned chi = (unsigned)MI(body_dofmask_hi)[ba] & (unsigned)MI(body_dofmask_hi)[bbb];
       for (int s2 = 0; s2 < 2; s2++) {
-        const int bb = gbody[s2 ? g2a[ci] : g1a[ci]];
+        const int bb = s2 ? bbb : ba;
         for (int q = 0; q < chnum[bb]; q++) {
           const int dof = chdof[chadr[bb] + q];
+          const bool common = dof < 32 ? ((clo >> dof) & 1u) : ((chi >> (dof - 32)) & 1u);
+          if (common) continue;
           if (cloc[ci * nv + dof] < 0 && nd < kL) { cloc[ci * nv + dof] = nd; cdofl[ci * kL + nd] = dof; nd++; }
         }
       }

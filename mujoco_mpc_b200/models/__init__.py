@@ -566,8 +566,10 @@ def track_keyframes(keyframes_dir=None, synthetic=False):
 
 
 def _robot_vs_world_only(m, g1, g2):
-    """Keep only pairs with exactly one static (world-welded) geom: robot self-collision pairs are
-    dropped (DESIGN.md 'Out of scope': most need capsule/cylinder/box convex tests)."""
+    """Pair filter of `self_collision=False`: keep only pairs with exactly one static (world-welded) geom.  The default
+    (self_collision=True) keeps every pair MuJoCo's filters keep and the narrow phase implements (capsule-capsule,
+    sphere-capsule, sphere-sphere, sphere-box between robot bodies); pairs that need MuJoCo's general convex collider
+    (cylinder / box against capsule, box-box) are listed in Model.pairs_dropped."""
     s1 = m.body_weldid[m.geom_bodyid[g1]] == 0
     s2 = m.body_weldid[m.geom_bodyid[g2]] == 0
     return bool(s1) != bool(s2)
@@ -578,7 +580,7 @@ def _ray_geoms(m):
     return np.array([g for g in range(m.ngeom) if m.geom_group[g] == 0], np.int32)
 
 
-def load(name: str, agent_timestep: bool = True, **kw):
+def load(name: str, agent_timestep: bool = True, self_collision: bool = True, **kw):
     """Compile one of the built-in tasks. Returns the Model with task ids / state filled in.
 
     agent_timestep=True applies Agent's override of opt.timestep by the ``agent_timestep`` numeric
@@ -594,7 +596,7 @@ def load(name: str, agent_timestep: bool = True, **kw):
         m.task_ids = np.zeros(1, np.int32)
         m.task_state = np.zeros(1)
     elif name == "quadruped":
-        m = compile_xml(quadruped_flat_xml(**kw), pair_filter=_robot_vs_world_only)
+        m = compile_xml(quadruped_flat_xml(**kw), pair_filter=None if self_collision else _robot_vs_world_only)
         m.task_residual_id = T.RESIDUAL_QUADRUPED_FLAT
         ids = np.zeros(T.QI_SIZE, np.int32)
         ids[T.QI_TORSO_BODY] = m.body_names.index("trunk")
@@ -617,7 +619,7 @@ def load(name: str, agent_timestep: bool = True, **kw):
         m.task_state = T.quadruped_state_block(float(np.linalg.norm(m.opt_gravity)),
                                                float(m.task_parameters[pn.index("Cadence")]))
     elif name == "humanoid":
-        m = compile_xml(humanoid_stand_xml(**kw), pair_filter=_robot_vs_world_only)
+        m = compile_xml(humanoid_stand_xml(**kw), pair_filter=None if self_collision else _robot_vs_world_only)
         m.task_residual_id = T.RESIDUAL_HUMANOID_STAND
         ids = np.zeros(T.HI_SIZE, np.int32)
         ids[T.HI_TORSO_BODY] = m.body_names.index("torso")
@@ -628,7 +630,7 @@ def load(name: str, agent_timestep: bool = True, **kw):
         m.task_state = np.zeros(1)
     elif name == "humanoid_track":
         keyframes_dir, synthetic = kw.pop("keyframes_dir", None), kw.pop("synthetic_keyframes", False)
-        m = compile_xml(humanoid_track_xml(**kw), pair_filter=_robot_vs_world_only)
+        m = compile_xml(humanoid_track_xml(**kw), pair_filter=None if self_collision else _robot_vs_world_only)
         m.task_residual_id = T.RESIDUAL_HUMANOID_TRACK
         ids = [m.site_names.index("tracking[%s]" % b) for b in T.TRACK_BODIES]
         ids += [int(m.body_mocapid[m.body_names.index("mocap[%s]" % b)]) for b in T.TRACK_BODIES]

@@ -490,6 +490,40 @@ int collide_sphere_capsule(RawContact<T>* out, const T* sp, T sr, const T* cp, c
   T q[3] = {cp[0] + axis[0] * x, cp[1] + axis[1] * x, cp[2] + axis[2] * x};
   return collide_sphere_sphere(out, sp, sr, q, csize[0]);
 }
+// [EXT] mjc_CapsuleCapsule restated: nearest points of the two axis segments (2x2 system, clamped), then a sphere test
+// there; (nearly) parallel axes test the segment ends instead and may return two contacts.  Only contacts with
+// dist <= margin are returned (as mjraw_SphereSphere does).
+template <class T>
+int collide_capsule_capsule(RawContact<T>* out, const T* p1, const T* m1, const T* s1, const T* p2, const T* m2, const T* s2,
+                            T margin) {
+  const T a1[3] = {m1[2], m1[5], m1[8]}, a2[3] = {m2[2], m2[5], m2[8]};
+  const T dif[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]};
+  const T ma = dot3(a1, a1), mb = -dot3(a1, a2), mc = dot3(a2, a2), u = -dot3(a1, dif), v = dot3(a2, dif);
+  const T det = ma * mc - mb * mb;
+  const T r1 = s1[0], l1 = s1[1], r2 = s2[0], l2 = s2[1];
+  auto clampT = [](T x, T lim) { return mm::max(-lim, mm::min(lim, x)); };
+  auto sphere = [&](RawContact<T>* o, T x1, T x2) {
+    T v1[3], v2[3];
+    for (int c = 0; c < 3; c++) { v1[c] = p1[c] + a1[c] * x1; v2[c] = p2[c] + a2[c] * x2; }
+    collide_sphere_sphere(o, v1, r1, v2, r2);
+    return o->dist <= margin ? 1 : 0;
+  };
+  if (mm::fabs(det) >= kMinVal<T>()) {
+    T x1 = (mc * u - mb * v) / det, x2 = (ma * v - mb * u) / det;
+    if (x1 > l1) { x1 = l1; x2 = (v - mb * l1) / mc; }
+    else if (x1 < -l1) { x1 = -l1; x2 = (v + mb * l1) / mc; }
+    if (x2 > l2) { x2 = l2; x1 = clampT((u - mb * l2) / ma, l1); }
+    else if (x2 < -l2) { x2 = -l2; x1 = clampT((u + mb * l2) / ma, l1); }
+    return sphere(out, x1, x2);
+  }
+  int n = sphere(out, l1, clampT((v - mb * l1) / mc, l2));
+  n += sphere(out + n, -l1, clampT((v + mb * l1) / mc, l2));
+  if (n >= 2) return n;
+  n += sphere(out + n, clampT((u - mb * l2) / ma, l1), l2);
+  if (n >= 2) return n;
+  n += sphere(out + n, clampT((u + mb * l2) / ma, l1), -l2);
+  return n;
+}
 template <class T>
 int collide_sphere_box(RawContact<T>* out, const T* sp, T sr, const T* bp, const T* bm, const T* bs) {
   T dv[3] = {sp[0] - bp[0], sp[1] - bp[1], sp[2] - bp[2]};
@@ -557,6 +591,7 @@ void collision(const Model<T>& m, Data<T>& d) {
     else if (t1 == GEOM_SPHERE && t2 == GEOM_SPHERE) n = collide_sphere_sphere(raw, p1, s1[0], p2, s2[0]);
     else if (t1 == GEOM_SPHERE && t2 == GEOM_CAPSULE) n = collide_sphere_capsule(raw, p1, s1[0], p2, m2, s2);
     else if (t1 == GEOM_SPHERE && t2 == GEOM_BOX) n = collide_sphere_box(raw, p1, s1[0], p2, m2, s2);
+    else if (t1 == GEOM_CAPSULE && t2 == GEOM_CAPSULE) n = collide_capsule_capsule(raw, p1, m1, s1, p2, m2, s2, margin);
     for (int k = 0; k < n; k++) {
       if (!(raw[k].dist < margin)) continue;
       // capacity: MuJoCo raises mjWARN_CONTACTFULL, which the rollout turns into failure (trajectory.cc:169-173)

@@ -157,3 +157,51 @@ def test_sliding_box_coulomb_friction(oracle_lib, cone):
     # the last few cm/s decay smoothly (soft constraint): compare the time to shed 95 % of the speed
     t95 = 0.95 / (mu * 9.81)
     assert abs(t[np.argmax(vx < 0.05)] - t95) < 0.05 * t95, (cone, t[np.argmax(vx < 0.05)], t95)
+
+
+def test_capsule_capsule_closed_form(oracle_lib):
+    """[EXT] mjc_CapsuleCapsule restated (oracle/physics.h collide_capsule_capsule): crossed capsules touch at one point
+    midway between the axes; parallel overlapping capsules produce two contacts at the ends of the overlap; contacts
+    between two MOVING bodies push them apart with equal and opposite forces (momentum conserved)."""
+    from mujoco_mpc_b200.blob import to_blob
+    from mujoco_mpc_b200.mjcf import compile_xml
+    xml = """
+    <mujoco>
+      <option timestep="0.002" gravity="0 0 0"/>
+      <custom><numeric name="agent_planner" data="0"/><numeric name="agent_horizon" data="0.1"/></custom>
+      <worldbody>
+        <body name="a" pos="0 0 0"><freejoint/><geom name="ga" type="capsule" size="0.05 0.3" quat="0.7071068 0 0.7071068 0" mass="1" condim="1"/></body>
+        <body name="b" pos="0 0 0"><freejoint/><geom name="gb" type="capsule" size="0.04 0.2" quat="0.7071068 0.7071068 0 0" mass="2" condim="1"/></body>
+      </worldbody>
+      <sensor><user name="Dummy" dim="26" user="0 1 0 1"/></sensor>
+    </mujoco>"""
+    m = compile_xml(xml)
+    m.task_residual_id = T.RESIDUAL_PARTICLE_COPY           # any residual: only the state is inspected
+    m.task_ids, m.task_state, m.ray_geoms = np.zeros(1, np.int32), np.zeros(1), np.zeros(0, np.int32)
+    o = oracle_lib.Oracle(to_blob(m), m, 64)
+    ident = [1.0, 0, 0, 0]
+    # crossed: A along x at z = 0, B along y at z = 0.08 -> penetration 0.01 along z at (0, 0, ~0.045)
+    q = np.array([0, 0, 0] + ident + [0, 0, 0.08] + ident, float)
+    r = o.forward_debug(q, np.zeros(12), np.zeros(0), np.zeros(0))
+    assert r["ncon"] == 1
+    c = r["contact"][0]
+    np.testing.assert_allclose(c[0], 0.08 - 0.05 - 0.04, atol=1e-12)
+    np.testing.assert_allclose(c[1:4], [0, 0, 0.05 + 0.5 * (0.08 - 0.09)], atol=1e-12)
+    np.testing.assert_allclose(np.abs(c[4:7]), [0, 0, 1], atol=1e-12)
+    # equal and opposite: total linear momentum change is zero (free bodies, no gravity)
+    acc = r["qacc"]
+    np.testing.assert_allclose(1.0 * acc[0:3] + 2.0 * acc[6:9], 0, atol=1e-9)
+    assert acc[2] < 0 < acc[8]                                   # A pushed down, B pushed up
+    # parallel: both along x (B rotated onto x), B shifted by 0.25 in x and 0.085 in z -> overlap x in [0.05, 0.3]
+    s = np.sqrt(0.5)
+    qb = [s, 0, 0, -s]                                           # undo the geom's y-orientation: rotate -90 deg about z
+    q = np.array([0, 0, 0] + ident + [0.25, 0, 0.085] + qb, float)
+    r = o.forward_debug(q, np.zeros(12), np.zeros(0), np.zeros(0))
+    assert r["ncon"] == 2
+    xs = sorted(r["contact"][k][1] for k in range(2))
+    np.testing.assert_allclose(xs, [0.05, 0.3], atol=1e-9)       # ends of the overlap: B's lower end, A's upper end
+    for k in range(2):
+        np.testing.assert_allclose(r["contact"][k][0], 0.085 - 0.09, atol=1e-12)
+    # separated beyond the margin: nothing
+    q = np.array([0, 0, 0] + ident + [0, 0, 0.2] + ident, float)
+    assert o.forward_debug(q, np.zeros(12), np.zeros(0), np.zeros(0))["ncon"] == 0
