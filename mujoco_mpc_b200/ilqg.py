@@ -144,6 +144,8 @@ class ILQGPlanner:
         c = self.cand
         previous_return = c["total_return"]
         steps = self._steps()
+        if c["residual"] is None:
+            return False                 # no nominal rollout succeeded yet: nothing to differentiate
         A, B, C, D = self.backend.model_derivatives(c["states"], c["actions"], c["times"], self.mocap, s.fd_tolerance,
                                                     skip=s.derivative_skip, mode=s.fd_mode)
         cx, cu, cxx, cuu, cxu = self.backend.cost_derivatives(c["residual"], C, D)
