@@ -1236,6 +1236,7 @@ __device__ __forceinline__ void hessian_dense_reg(Ctx& c) {
   for (int w = lane; w < NV * NV; w += 32) H[w] = 0.f;   // entries outside the pattern (the factor fills them)
   {
     const float* cdof = DF(cdof);
+    const int* dbody2 = MI(dof_bodyid);
 #pragma unroll
     for (int q = 0; q < NQ; q++) {
       int e = lane + 32 * q;
@@ -1243,9 +1244,16 @@ __device__ __forceinline__ void hessian_dense_reg(Ctx& c) {
       const int r = hi[e];
       er[q] = r; es[q] = hj[e];
       float a = qM[er[q] * NV + es[q]];
+      // the composite form holds for (dof, ancestor dof) pairs only - the pattern of M itself; entries that exist in
+      // the Hessian pattern because a pair of moving bodies CAN touch (e.g. two legs) get nothing from one-sided contacts
+      const int br = dbody2[r];
+      const unsigned mlo_r = (unsigned)MI(body_dofmask_lo)[br], mhi_r = (unsigned)MI(body_dofmask_hi)[br];
+      const bool anc = es[q] < 32 ? ((mlo_r >> es[q]) & 1u) : ((mhi_r >> (es[q] - 32)) & 1u);
       const float *gr = g + 6 * r, *cs = cdof + 6 * es[q];
+      float dsum = 0.f;
 #pragma unroll
-      for (int l = 0; l < 6; l++) a += gr[l] * cs[l];
+      for (int l = 0; l < 6; l++) dsum += gr[l] * cs[l];
+      a += anc ? dsum : 0.f;
       if (er[q] == es[q]) {
         const int fr = frow[r];
         if (fr >= 0) a += hw[fr];
