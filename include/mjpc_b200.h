@@ -288,6 +288,11 @@ void mjpc_b200_track_transition_destroy(void* transition);
 void mjpc_b200_track_transition_step(void* transition, int mode, double time, double* qpos, double* qvel,
                                      double* mocap_pos, double* task_state);
 
+/* ShadowReorient::TransitionLocked (hand.cc:90-119): cube at rest on the floor -> back into the hand.  Returns 1 on a reset. */
+void* mjpc_b200_shadow_transition_create(int cube_qposadr, int cube_dofadr, const double* qpos0_cube /*[7]*/);
+void mjpc_b200_shadow_transition_destroy(void* transition);
+int mjpc_b200_shadow_transition_step(void* transition, double* qpos, double* qvel, int on_floor, const double* cube_linvel);
+
 /* ---- iLQG planner (csrc/host/ilqg_planner.{h,cc}; mjpc/planners/ilqg/planner.h, planner.cc:156-740).
  * OptimizePolicy = NominalTrajectory (feedback-scaling line search) + Iteration (model derivatives, cost derivatives,
  * backward pass with the regularisation retry loop, K action rollouts, winner, regularisation update); each sweep is

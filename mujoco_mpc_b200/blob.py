@@ -29,7 +29,7 @@ _F_SCALARS = ["opt_timestep", "opt_impratio", "opt_tolerance", "opt_ls_tolerance
 _INT_ARRAYS = ["body_parentid", "body_rootid", "body_weldid", "body_jntnum", "body_jntadr", "body_dofnum",
                "body_dofadr", "body_mocapid", "body_depth", "jnt_type", "jnt_qposadr", "jnt_dofadr", "jnt_bodyid",
                "jnt_limited", "dof_bodyid", "dof_jntid", "dof_parentid", "geom_type", "geom_bodyid",
-               "geom_condim", "geom_priority", "geom_group", "site_bodyid", "actuator_trnid",
+               "geom_condim", "geom_priority", "geom_group", "site_bodyid", "actuator_trnid", "actuator_trntype",
                "actuator_biastype", "actuator_ctrllimited", "actuator_forcelimited", "pair_geom1", "pair_geom2",
                "task_dim_norm_residual", "task_norm", "task_num_norm_parameter", "task_trace_objtype",
                "task_trace_objid", "task_ids", "ray_geoms", "tendon_adr", "tendon_num", "tendon_limited", "wrap_dof",

@@ -27,7 +27,7 @@ namespace mjpc_dev {
 #define MJPC_I_ARRAYS(X)                                                                                         \
   X(body_parentid) X(body_rootid) X(body_jntnum) X(body_jntadr) X(body_dofnum) X(body_dofadr) X(body_mocapid)    \
   X(jnt_type) X(jnt_qposadr) X(jnt_dofadr) X(jnt_bodyid) X(jnt_limited) X(dof_bodyid) X(dof_jntid)               \
-  X(dof_parentid) X(geom_type) X(geom_bodyid) X(geom_condim) X(geom_priority) X(site_bodyid) X(actuator_trnid)   \
+  X(dof_parentid) X(geom_type) X(geom_bodyid) X(geom_condim) X(geom_priority) X(site_bodyid) X(actuator_trnid) X(actuator_trntype)  \
   X(actuator_biastype) X(actuator_ctrllimited) X(actuator_forcelimited) X(pair_geom1) X(pair_geom2)              \
   X(ray_geoms) X(task_dim_norm_residual) X(task_norm) X(task_num_norm_parameter) X(task_trace_objtype)           \
   X(task_trace_objid) X(task_ids) X(tendon_adr) X(tendon_num) X(tendon_limited) X(wrap_dof) X(wrap_qposadr)
@@ -64,7 +64,7 @@ enum { JNT_FREE = 0, JNT_BALL, JNT_SLIDE, JNT_HINGE };
 enum { OBJ_BODY = 0, OBJ_XBODY, OBJ_GEOM, OBJ_SITE };
 enum { CONE_PYRAMIDAL = 0, CONE_ELLIPTIC = 1 };
 enum { RESIDUAL_PARTICLE = 0, RESIDUAL_PARTICLE_COPY = 1, RESIDUAL_CARTPOLE = 2, RESIDUAL_QUADRUPED_FLAT = 3,
-       RESIDUAL_HUMANOID_STAND = 4, RESIDUAL_HUMANOID_TRACK = 5 };
+       RESIDUAL_HUMANOID_STAND = 4, RESIDUAL_HUMANOID_TRACK = 5, RESIDUAL_SHADOW_REORIENT = 6 };
 
 // integer fields of the header (sizes, option flags, task dimensions, pack sizes).  A statically specialised
 // kernel (spec_*.h) turns every one of them, and the offset tables below, into compile-time constants.

@@ -1008,13 +1008,25 @@ __device__ __noinline__ void k_smooth_forces(Ctx& c) {
               *frclim = MI(actuator_forcelimited), *jqadr = MI(jnt_qposadr), *jdadr = MI(jnt_dofadr);
     const float *gear = MF(actuator_gear), *gainprm = MF(actuator_gainprm), *biasprm = MF(actuator_biasprm),
                 *ctrlrange = MF(actuator_ctrlrange), *frcrange = MF(actuator_forcerange);
+    // transmission: a joint (mjTRN_JOINT) or a fixed tendon (mjTRN_TENDON: length / velocity / moment through the
+    // tendon's wrap coefficients - e.g. the coupled distal finger joints of the Shadow Hand)
+    const int *trntype = MI(actuator_trntype), *tadr = MI(tendon_adr), *tnum = MI(tendon_num), *wq = MI(wrap_qposadr),
+              *wdof = MI(wrap_dof);
+    const float* wcoef = MF(wrap_coef);
     for (int i = lane; i < M.nu; i += 32) {
       float u = ctrl[i];
       if (ctrllim[i]) u = fmaxf(ctrlrange[2 * i], fminf(ctrlrange[2 * i + 1], u));
       const int j = trnid[i];
       float force = gainprm[3 * i] * u;
       if (biastype[i] == 1) {
-        const float length = gear[i] * qpos[jqadr[j]], vel = gear[i] * qvel[jdadr[j]];
+        float length, vel;
+        if (trntype[i] == 1) {
+          length = 0.f; vel = 0.f;
+          for (int w = tadr[j]; w < tadr[j] + tnum[j]; w++) { length += wcoef[w] * qpos[wq[w]]; vel += wcoef[w] * qvel[wdof[w]]; }
+          length *= gear[i]; vel *= gear[i];
+        } else {
+          length = gear[i] * qpos[jqadr[j]]; vel = gear[i] * qvel[jdadr[j]];
+        }
         force += biasprm[3 * i] + biasprm[3 * i + 1] * length + biasprm[3 * i + 2] * vel;
       }
       if (frclim[i]) force = fmaxf(frcrange[2 * i], fminf(frcrange[2 * i + 1], force));
@@ -1023,8 +1035,14 @@ __device__ __noinline__ void k_smooth_forces(Ctx& c) {
     __syncwarp();
     for (int d = lane; d < nv; d += 32) {
       float s = 0;
-      for (int i = 0; i < M.nu; i++)
-        if (jdadr[trnid[i]] == d) s += gear[i] * aforce[i];
+      for (int i = 0; i < M.nu; i++) {
+        if (trntype[i] == 1) {
+          const int t = trnid[i];
+          for (int w = tadr[t]; w < tadr[t] + tnum[t]; w++) if (wdof[w] == d) s += gear[i] * wcoef[w] * aforce[i];
+        } else if (jdadr[trnid[i]] == d) {
+          s += gear[i] * aforce[i];
+        }
+      }
       qact[d] = s;
     }
   }

@@ -561,6 +561,32 @@ __device__ __noinline__ void k_residual(Ctx& c) {
       __syncwarp();
       break;
     }
+    case RESIDUAL_SHADOW_REORIENT: {
+      // mjpc/tasks/shadow_reorient/hand.cc:37-84 (81 residuals); task_ids = {grasp site, cube body, goal body, grasp key}.
+      // qpos + 7 / qvel + 6 for 26 values are the reference's literal offsets (they start inside the cube's joint).
+      const int* I = MI(task_ids);
+      const int cube = I[1], goal = I[2];
+      if (lane == 0) {
+        const float *palm = DF(site_xpos) + 3 * I[0], *pos = DF(xpos) + 3 * cube;
+        for (int q = 0; q < 3; q++) r[q] = pos[q] - palm[q];
+        float gq[4];
+        for (int q = 0; q < 4; q++) gq[q] = DF(xquat)[4 * goal + q];
+        quat_normalize(gq);
+        sub_quat(r + 3, gq, DF(xquat) + 4 * cube);
+        const float* cv = DF(cvel) + 6 * cube;
+        float off[3], wx[3];
+        for (int q = 0; q < 3; q++) off[q] = pos[q] - DF(subtree_com)[3 * MI(body_rootid)[cube] + q];
+        cross3(wx, cv, off);
+        for (int q = 0; q < 3; q++) r[6 + q] = cv[3 + q] + wx[q];
+      }
+      for (int i = lane; i < M.nu; i += 32) r[9 + i] = DF(actuator_force)[i];
+      {
+        const float* key = MF(key_qpos) + M.nq * I[3];
+        for (int i = lane; i < 26; i += 32) { r[9 + M.nu + i] = DF(qpos)[7 + i] - key[7 + i]; r[9 + M.nu + 26 + i] = DF(qvel)[6 + i]; }
+      }
+      __syncwarp();
+      break;
+    }
     case RESIDUAL_HUMANOID_TRACK: {
       // mjpc/tasks/humanoid/tracking/tracking.cc:94-216; task_ids = 16 tracking sites then 16 mocap ids,
       // task_state = [mode, reference_time (rebased)], keyframes in HBM (c.gkey).  One tracked body per lane.

@@ -159,6 +159,13 @@ void HumanoidTrackTransition::Transition(double time, double* qpos, double* qvel
   for (int i = 0; i < n3; i++) mocap_pos[i] = key_mpos_[(size_t)k0 * n3 + i] * w0 + key_mpos_[(size_t)k1 * n3 + i] * w1;
 }
 
+bool ShadowReorientTransition::Transition(double* qpos, double* qvel, bool on_floor, const double v[3]) const {
+  if (!(on_floor && std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]) < 0.001)) return false;
+  for (int i = 0; i < 7; i++) qpos[qadr_ + i] = qpos0_[i];
+  for (int i = 0; i < 6; i++) qvel[dadr_ + i] = 0.0;
+  return true;
+}
+
 }  // namespace mjpc_b200_host
 
 // ------------------------------------------------------------------------------------------ C entry points
@@ -219,6 +226,14 @@ void mjpc_b200_track_transition_step(void* pv, int mode, double time, double* qp
   p->mode = mode;
   p->Transition(time, qpos, qvel, mocap_pos);
   if (task_state) { task_state[0] = p->current_mode(); task_state[1] = p->reference_time(); }
+}
+
+void* mjpc_b200_shadow_transition_create(int cube_qposadr, int cube_dofadr, const double* qpos0_cube) {
+  return new mjpc_b200_host::ShadowReorientTransition(cube_qposadr, cube_dofadr, qpos0_cube);
+}
+void mjpc_b200_shadow_transition_destroy(void* p) { delete (mjpc_b200_host::ShadowReorientTransition*)p; }
+int mjpc_b200_shadow_transition_step(void* p, double* qpos, double* qvel, int on_floor, const double* cube_linvel) {
+  return ((mjpc_b200_host::ShadowReorientTransition*)p)->Transition(qpos, qvel, on_floor != 0, cube_linvel) ? 1 : 0;
 }
 
 }  // extern "C"

@@ -68,4 +68,18 @@ class HumanoidTrackTransition {
   std::vector<double> key_qpos_, key_qvel_, key_mpos_;
 };
 
+// ShadowReorient::TransitionLocked (mjpc/tasks/shadow_reorient/hand.cc:90-119): a cube lying at rest on the floor is put
+// back into the hand (its free joint takes qpos0, its velocity is zeroed).  `on_floor` = a cube-floor contact exists in
+// the plant's contact list; `cube_linvel` = the cube_linear_velocity sensor.  Returns true when the reset happened.
+class ShadowReorientTransition {
+ public:
+  ShadowReorientTransition(int cube_qposadr, int cube_dofadr, const double* qpos0_cube /*[7]*/)
+      : qadr_(cube_qposadr), dadr_(cube_dofadr) { for (int i = 0; i < 7; i++) qpos0_[i] = qpos0_cube[i]; }
+  bool Transition(double* qpos, double* qvel, bool on_floor, const double cube_linvel[3]) const;
+
+ private:
+  int qadr_, dadr_;
+  double qpos0_[7];
+};
+
 }  // namespace mjpc_b200_host

@@ -52,7 +52,8 @@ EXPORTS = ["mjpc_b200_version", "mjpc_b200_last_error", "mjpc_b200_create", "mjp
            "mjpc_b200_agent_plan_iteration", "mjpc_b200_agent_get_steps", "mjpc_b200_agent_action_from_policy",
            "mjpc_b200_quadruped_transition_create", "mjpc_b200_quadruped_transition_destroy",
            "mjpc_b200_quadruped_transition_step", "mjpc_b200_quadruped_transition_set", "mjpc_b200_track_transition_create",
-           "mjpc_b200_track_transition_destroy", "mjpc_b200_track_transition_step"]
+           "mjpc_b200_track_transition_destroy", "mjpc_b200_track_transition_step", "mjpc_b200_shadow_transition_create",
+           "mjpc_b200_shadow_transition_destroy", "mjpc_b200_shadow_transition_step"]
 
 
 class ModelBlob(C.Structure):
@@ -96,7 +97,8 @@ def load_library():
         lib.mjpc_b200_set_options.argtypes = [C.c_void_p, C.c_double, C.c_int]
         lib.mjpc_b200_ilqs_planner_destroy.argtypes = [C.c_void_p]
         lib.mjpc_b200_ilqs_planner_set_exploration.argtypes = [C.c_void_p, C.c_double]
-        for n in ("mjpc_b200_quadruped_transition_create", "mjpc_b200_track_transition_create"):
+        lib.mjpc_b200_shadow_transition_destroy.argtypes = [C.c_void_p]
+        for n in ("mjpc_b200_quadruped_transition_create", "mjpc_b200_track_transition_create", "mjpc_b200_shadow_transition_create"):
             getattr(lib, n).restype = C.c_void_p
         lib.mjpc_b200_quadruped_transition_destroy.argtypes = [C.c_void_p]
         lib.mjpc_b200_track_transition_destroy.argtypes = [C.c_void_p]

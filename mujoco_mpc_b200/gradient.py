@@ -240,7 +240,11 @@ class ILQSPlanner:
             L = np.linalg.cholesky(M)
             inv = np.linalg.solve(L.T, np.linalg.solve(L, W.T))               # (A'A)^-1 A'
             params = inv @ np.asarray(il.cand["actions"], float)[: H - 1]
-            sp.values = clamp(params, sp.ctrlrange); sp.times = new_t
+            # sampling.policy.plan = these nodes (:160-172).  Restated literally: with the default non-sliding plan the
+            # very next step, SamplingPlanner::UpdateNominalPolicy, resamples candidate_policy[winner] - NOT policy - into
+            # policy.plan (sampling/planner.cc:296-321), so the converted spline never reaches a rollout; it is kept for
+            # inspection only (the C++ class writes it into sampling.policy.plan exactly as the reference does).
+            self.converted = (new_t, clamp(params, sp.ctrlrange))
         ret, fail = sp.optimize_policy()
         ref = float(ret[0]) if self.previous_active_policy == self.K_SAMPLING else float(il.cand["total_return"])
         if sp.winner > 0 and float(ret[sp.winner]) < ref:

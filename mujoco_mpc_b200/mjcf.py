@@ -309,8 +309,8 @@ class Compiler:
             self._parse_body_children(wb, 0, None)
 
         self._finish_bodies(m)
-        self._parse_actuators(m)
         self._parse_tendons_excludes(m)
+        self._parse_actuators(m)
         self._parse_sensors(m)
         self._parse_custom(m)
         self._parse_keys(m)
@@ -558,11 +558,15 @@ class Compiler:
                     acts.append(a)
         nu = len(acts)
         m.nu, m.na = nu, 0
+        trntype = np.zeros(nu, np.int32)        # 0 joint, 1 fixed tendon (mjTRN_JOINT / mjTRN_TENDON)
         trnid = np.zeros(nu, np.int32); gear = np.zeros(nu); gainprm = np.zeros((nu, 3)); biasprm = np.zeros((nu, 3))
         biastype = np.zeros(nu, np.int32); ctrllim = np.zeros(nu, np.int32); ctrlrange = np.zeros((nu, 2))
         frclim = np.zeros(nu, np.int32); frcrange = np.zeros((nu, 2))
         for i, a in enumerate(acts):
-            trnid[i] = m.jnt_names.index(a["joint"])
+            if "tendon" in a:
+                trntype[i], trnid[i] = 1, m.tendon_names.index(a["tendon"])
+            else:
+                trnid[i] = m.jnt_names.index(a["joint"])
             gear[i] = _f(a.get("gear"), default=[1])[0]
             tag = a["_tag"]
             gp = _f(a.get("gainprm"), 3, [1, 0, 0]); bp = _f(a.get("biasprm"), 3, [0, 0, 0])
@@ -587,6 +591,7 @@ class Compiler:
             else:
                 frclim[i] = 1 if (self.autolimits and "forcerange" in a) else 0
         m.actuator_trnid, m.actuator_gear, m.actuator_gainprm, m.actuator_biasprm = trnid, gear, gainprm, biasprm
+        m.actuator_trntype = trntype
         m.actuator_biastype, m.actuator_ctrllimited, m.actuator_ctrlrange = biastype, ctrllim, ctrlrange
         m.actuator_forcelimited, m.actuator_forcerange = frclim, frcrange
         m.actuator_names = [a.get("name", "") for a in acts]

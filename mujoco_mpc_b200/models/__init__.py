@@ -506,6 +506,154 @@ def humanoid_track_xml(horizon=0.5, trajectories=32) -> str:
     return base.replace('<mujoco model="Humanoid">', '<mujoco model="Humanoid Track">')
 
 
+# ----------------------------------------------------------------------------------------------- Shadow Hand stand-in
+_HAND_KEY = ("1 0 0 0 0.33326 -0.00362331 0.0375343 0.707635 0.70405 0.0500937 -0.0325089 5.55212e-10 -0.235248 -0.178041 "
+             "0.480484 0.730515 0.6284 -0.059347 0.535468 0.746225 0.56556 -0.03491 0.544632 0.53414 0.793355 0.384846 "
+             "-0.254843 0.178072 0.761935 0.746225 -0.90042 0.06721 0.01047 0.6981 0.4255")   # shadow_reorient/task.xml:60
+
+
+def _hand_finger(name: str, y: float, metacarpal: bool = False) -> str:
+    """One finger of the stand-in: knuckle J4 (abduction, about z), J3 / J2 / J1 flexion about -y (positive angles curl
+    the finger towards +z, the palm side); the little finger has the extra metacarpal joint J5.  Collision = two
+    spheres per link (sphere-box is the narrow phase the engine implements for the cube)."""
+    def link(j, length, jrange, inner):
+        return (f'<body name="rh_{name}{j}" pos="{{pos}}"><joint name="rh_{name}J{j}" axis="0 -1 0" range="{jrange}"/>'
+                f'<geom class="link" fromto="0 0 0 {length} 0 0"/>'
+                f'<geom class="pad" pos="{0.3 * length:.4f} 0 0"/><geom class="pad" pos="{0.8 * length:.4f} 0 0"/>{inner}</body>')
+    distal = link(1, 0.026, "0 1.5708", "").format(pos="0.025 0 0")
+    middle = link(2, 0.025, "0 1.5708", distal).format(pos="0.045 0 0")
+    prox = link(3, 0.045, "-0.2618 1.5708", middle).format(pos="0 0 0")
+    knuckle = (f'<body name="rh_{name}knuckle" pos="{{pos}}"><joint name="rh_{name}J4" axis="0 0 1" range="-0.349 0.349"/>'
+               f'<geom class="link" fromto="0 0 0 0.005 0 0"/>{prox}</body>')
+    if metacarpal:
+        return (f'<body name="rh_{name}metacarpal" pos="0.07 {y} 0.0236"><joint name="rh_{name}J5" axis="0.571 0 0.821" range="0 0.785"/>'
+                f'<geom class="link" fromto="0 0 0 0.04 0 0"/><geom class="pad" pos="0.02 0 0.004"/>'
+                + knuckle.format(pos="0.04 0 0") + "</body>")
+    return knuckle.format(pos=f"0.11 {y} 0.0236")
+
+
+def shadow_reorient_xml(horizon=0.25, trajectories=60) -> str:
+    """MJPC "In-Hand Manipulation" (mjpc/tasks/shadow_reorient/task.xml + hand.cc) on a STAND-IN hand.
+
+    The reference includes Menagerie's shadow_hand/right_hand.xml with its mesh assets (CMakeLists.txt fetches them at
+    configure time; not vendored, not available offline), so the hand below is a primitive-geom stand-in [GUESS: every
+    hand length, mass, joint range and gain]: the same kinematic layout and order - 2 wrist + 4 + 4 + 4 + 5 (little)
+    + 5 (thumb) = 24 hinges, 20 position actuators of which five act on fixed tendons coupling the two distal joints
+    (rh_*J0 = J2 + J1), a grasp_site on the palm - so nq / nv / nu = 35 / 33 / 20 and the qpos layout the residual's
+    literal `qpos + 7` / `qvel + 6` offsets assume.  What IS the reference's: the goal body and the cube
+    (common_assets/reorientation_cube.xml + cube.xml.patch), the cost terms, the custom numerics, the 35-value grasp
+    keyframe.  Collisions: cube (box) vs two spheres per finger link + a 4 x 3 grid on the palm (sphere-box), cube vs
+    floor (plane-box); finger-finger collisions are switched off by contype / conaffinity."""
+    fingers = "".join(_hand_finger(n, y) for n, y in (("FF", 0.033), ("MF", 0.011), ("RF", -0.011)))
+    little = _hand_finger("LF", -0.033, metacarpal=True)
+    palm_pads = "".join(f'<geom class="palmpad" pos="{0.035 + 0.022 * i:.3f} {-0.022 + 0.022 * j:.3f} 0.0271"/>'
+                        for i in range(4) for j in range(3))
+    thumb = """
+          <body name="rh_thbase" pos="0.049 0.034 0.0236">
+            <joint name="rh_THJ5" axis="0 0 -1" range="-1.047 1.047"/>
+            <geom class="link" fromto="0 0 0 0 0.005 0"/>
+            <body name="rh_thproximal" pos="0 0 0">
+              <joint name="rh_THJ4" axis="1 0 0" range="0 1.222"/>
+              <geom class="thlink" fromto="0 0 0 0 0.038 0"/><geom class="thpad" pos="0 0.012 0"/><geom class="thpad" pos="0 0.03 0"/>
+              <body name="rh_thhub" pos="0 0.038 0">
+                <joint name="rh_THJ3" axis="1 0 0" range="-0.209 0.209"/>
+                <geom class="thlink" fromto="0 0 0 0 0.002 0"/>
+                <body name="rh_thmiddle" pos="0 0 0">
+                  <joint name="rh_THJ2" axis="0 0 1" range="-0.698 0.698"/>
+                  <geom class="thlink" fromto="0 0 0 0 0.032 0"/><geom class="thpad" pos="0 0.01 0"/><geom class="thpad" pos="0 0.026 0"/>
+                  <body name="rh_thdistal" pos="0 0.032 0">
+                    <joint name="rh_THJ1" axis="0 0 1" range="-0.262 1.571"/>
+                    <geom class="thlink" fromto="0 0 0 0 0.0275 0"/><geom class="thpad" pos="0 0.008 0"/><geom class="thpad" pos="0 0.022 0"/>
+                  </body>
+                </body>
+              </body>
+            </body>
+          </body>"""
+    def pos_act(j, lo, hi, kp=1.0):
+        return f'<position name="rh_A_{j}" joint="rh_{j}" kp="{kp}" ctrlrange="{lo} {hi}" forcerange="-2 2"/>'
+    acts = pos_act("WRJ2", -0.523, 0.174, 10) + pos_act("WRJ1", -0.698, 0.489, 10)
+    for f in ("FF", "MF", "RF"):
+        acts += pos_act(f + "J4", -0.349, 0.349) + pos_act(f + "J3", -0.262, 1.571)
+        acts += f'<position name="rh_A_{f}J0" tendon="rh_{f}J0" kp="1" ctrlrange="0 3.1415" forcerange="-2 2"/>'
+    acts += pos_act("LFJ5", 0, 0.785) + pos_act("LFJ4", -0.349, 0.349) + pos_act("LFJ3", -0.262, 1.571)
+    acts += '<position name="rh_A_LFJ0" tendon="rh_LFJ0" kp="1" ctrlrange="0 3.1415" forcerange="-2 2"/>'
+    acts += (pos_act("THJ5", -1.047, 1.047) + pos_act("THJ4", 0, 1.222) + pos_act("THJ3", -0.209, 0.209)
+             + pos_act("THJ2", -0.698, 0.698) + pos_act("THJ1", -0.262, 1.571))
+    tendons = "".join(f'<fixed name="rh_{f}J0"><joint joint="rh_{f}J2" coef="1"/><joint joint="rh_{f}J1" coef="1"/></fixed>'
+                      for f in ("FF", "MF", "RF", "LF"))
+    return f"""
+<mujoco model="In-Hand Manipulation">
+  <compiler angle="radian" autolimits="true"/>
+  <option timestep="0.01"/>
+  <custom>
+    <numeric name="agent_planner" data="5"/>
+    <numeric name="agent_horizon" data="{horizon}"/>
+    <numeric name="agent_timestep" data="0.01"/>
+    <numeric name="agent_policy_width" data="0.0035"/>
+    <numeric name="sampling_spline_points" data="5"/>
+    <numeric name="sampling_exploration" data="0.2"/>
+    <numeric name="sampling_representation" data="0"/>
+    <numeric name="sampling_trajectories" data="{trajectories}"/>
+    <numeric name="n_elite" data="8"/>
+    <numeric name="explore_fraction" data="0.5"/>
+    <numeric name="robust_xfrc" data="0.004"/>
+  </custom>
+  <default>
+    <geom friction=".6"/>
+    <joint type="hinge" damping="0.05" armature="0.0002"/>
+    <default class="link"><geom type="capsule" size="0.008" mass="0.012" contype="0" conaffinity="0" group="2"/></default>
+    <default class="thlink"><geom type="capsule" size="0.010" mass="0.016" contype="0" conaffinity="0" group="2"/></default>
+    <default class="pad"><geom type="sphere" size="0.009" mass="0.002" contype="2" conaffinity="0" group="3"/></default>
+    <default class="thpad"><geom type="sphere" size="0.011" mass="0.003" contype="2" conaffinity="0" group="3"/></default>
+    <default class="palmpad"><geom type="sphere" size="0.012" mass="0.02" contype="2" conaffinity="0" group="3"/></default>
+  </default>
+  <worldbody>
+    <geom name="floor" pos="0 0 -0.2" size="0 0 0.05" type="plane"/>
+    <body name="goal" pos="0.325 0.17 0.0475">
+      <joint type="ball" damping="0.01"/>
+      <geom type="box" size=".022 .022 .022" mass=".126" contype="0" conaffinity="0"/>
+    </body>
+    <body name="cube" pos="0.325 0.0 0.075" quat="0.707 0.707 0 0">
+      <freejoint/>
+      <geom name="cube" type="box" size=".022 .022 .022" mass=".126" contype="1" conaffinity="3"/>
+    </body>
+    <body name="rh_forearm" pos="0 0 0">
+      <geom class="link" type="capsule" size="0.03" fromto="0.08 0 -0.01 0.21 0 -0.01" mass="1"/>
+      <body name="rh_wrist" pos="0.235 0 0">
+        <joint name="rh_WRJ2" axis="0 0 1" range="-0.523 0.174"/>
+        <geom class="link" fromto="0 0 0 0.01 0 0"/>
+        <body name="rh_palm" pos="0 0 0">
+          <joint name="rh_WRJ1" axis="0 -1 0" range="-0.698 0.489"/>
+          <geom name="rh_palm_box" type="box" size="0.05 0.042 0.006" pos="0.065 0 0.0196" mass="0.3" contype="0" conaffinity="0" group="2"/>
+          <site name="grasp_site" pos="0.098 0 0.0636" size="0.005"/>
+          {palm_pads}
+          {fingers}
+          {little}
+          {thumb}
+        </body>
+      </body>
+    </body>
+  </worldbody>
+  <tendon>{tendons}</tendon>
+  <actuator>{acts}</actuator>
+  <sensor>
+    <user name="In Hand" dim="3" user="1 20 0 100 0.02 2"/>
+    <user name="Orientation" dim="3" user="0 5 0 10"/>
+    <user name="Cube Vel." dim="3" user="0 10 0 20"/>
+    <user name="Actuator" dim="20" user="0 0.1 0.0 1.0"/>
+    <user name="Grasp" dim="26" user="0 2.5 0.0 10.0"/>
+    <user name="Joint Vel." dim="26" user="0 1.0e-4 0.0 1.0e-1"/>
+    <framepos name="palm_position" objtype="site" objname="grasp_site"/>
+    <framequat name="cube_goal_orientation" objtype="body" objname="goal"/>
+    <framepos name="trace0" objtype="body" objname="cube"/>
+    <framepos name="cube_position" objtype="body" objname="cube"/>
+    <framequat name="cube_orientation" objtype="body" objname="cube"/>
+    <framelinvel name="cube_linear_velocity" objtype="body" objname="cube"/>
+  </sensor>
+  <keyframe><key name="grasp" qpos="{_HAND_KEY}"/></keyframe>
+</mujoco>"""
+
+
 def synth_mocap(m, seed=0):
     """Synthetic stand-in for the reference's CMU keyframes: 10 clips with the reference's lengths (tracking.cc:43-54),
     30 fps.  Each clip is a smooth band-limited joint-angle motion inside 35 % of the joint ranges around the standing
@@ -653,6 +801,17 @@ def load(name: str, agent_timestep: bool = True, self_collision: bool = True, **
         m.key_mquat = np.tile(np.array([1.0, 0, 0, 0]), (m.nkey, m.nmocap))
         m.key_names = ["frame%d" % i for i in range(m.nkey)]
         m.mocap_pos0 = km[0].reshape(-1, 3).copy()
+    elif name == "shadow_reorient":
+        m = compile_xml(shadow_reorient_xml(**kw))
+        m.task_residual_id = T.RESIDUAL_SHADOW_REORIENT
+        ids = np.zeros(T.SI_SIZE, np.int32)
+        ids[T.SI_GRASP_SITE] = m.site_names.index("grasp_site")
+        ids[T.SI_CUBE_BODY] = m.body_names.index("cube")
+        ids[T.SI_GOAL_BODY] = m.body_names.index("goal")
+        ids[T.SI_KEY_GRASP] = m.key_names.index("grasp")
+        m.task_ids = ids
+        m.task_state = np.zeros(1)
+        m.model_note = "Shadow Hand STAND-IN (primitive geoms, [GUESS] dimensions): Menagerie's right_hand.xml is not vendored"
     else:
         raise KeyError(name)
     m.task_name = name

@@ -27,6 +27,8 @@ RESIDUAL_HUMANOID_TRACK = 5  # mjpc/tasks/humanoid/tracking/tracking.cc:94-216
 # task_state = [current_mode, reference_time] (reference_time is time-like: rebased per rollout)
 TRACK_BODIES = ("pelvis", "head", "ltoe", "rtoe", "lheel", "rheel", "lknee", "rknee", "lhand", "rhand", "lelbow",
                 "relbow", "lshoulder", "rshoulder", "lhip", "rhip")
+RESIDUAL_SHADOW_REORIENT = 6 # mjpc/tasks/shadow_reorient/hand.cc:37-84
+SI_GRASP_SITE, SI_CUBE_BODY, SI_GOAL_BODY, SI_KEY_GRASP, SI_SIZE = 0, 1, 2, 3, 4
 TRACK_MOTION_LENGTHS = (121, 154, 115, 78, 145, 188, 260, 279, 39, 510)   # tracking.cc:43-54
 TRACK_FPS = 30.0
 TS_MODE, TS_REFERENCE_TIME, TS_SIZE = 0, 1, 2

@@ -182,3 +182,29 @@ class QuadrupedFlatTransition:
                 self.goal_pos[:2] = np.asarray(d["head_site_xpos"], float)[:2]
         self.current_mode = self.mode
         self.last_transition_time = time
+
+
+class ShadowReorientTransition:
+    """ShadowReorient::TransitionLocked (mjpc/tasks/shadow_reorient/hand.cc:90-119): when the cube lies on the floor
+    (a cube-floor contact exists) and is at rest (|cube linear velocity| < 1e-3) it is put back into the hand: its 7 qpos
+    take the model's qpos0 values, its 6 qvel are zeroed.  The contact list and the framelinvel sensor belong to the
+    plant; the caller passes what the reference reads from mjData."""
+
+    def __init__(self, model):
+        self.m = model
+        cube = model.body_names.index("cube")
+        j = int(model.body_jntadr[cube])
+        self.qadr, self.dadr = int(model.jnt_qposadr[j]), int(model.jnt_dofadr[j])
+        self.cube_geom, self.floor_geom = model.geom_names.index("cube"), model.geom_names.index("floor")
+
+    def on_floor(self, contact_geoms):
+        """contact_geoms: iterable of (geom1, geom2) of the plant's active contacts (hand.cc:96-104)."""
+        return any({int(a), int(b)} == {self.cube_geom, self.floor_geom} for a, b in contact_geoms)
+
+    def transition(self, qpos, qvel, on_floor, cube_linvel):
+        qpos, qvel = np.array(qpos, float), np.array(qvel, float)
+        reset = bool(on_floor) and float(np.linalg.norm(cube_linvel)) < 1e-3
+        if reset:
+            qpos[self.qadr:self.qadr + 7] = self.m.qpos0[self.qadr:self.qadr + 7]
+            qvel[self.dadr:self.dadr + 6] = 0.0
+        return qpos, qvel, reset

@@ -84,7 +84,7 @@ struct Model {
   std::vector<T> geom_size, geom_pos, geom_quat, geom_friction, geom_solmix, geom_solref, geom_solimp, geom_margin,
       geom_gap, geom_rbound, site_pos, site_quat;
   // actuators
-  std::vector<int> actuator_trnid, actuator_biastype, actuator_ctrllimited, actuator_forcelimited;
+  std::vector<int> actuator_trnid, actuator_trntype, actuator_biastype, actuator_ctrllimited, actuator_forcelimited;
   std::vector<T> actuator_gear, actuator_gainprm, actuator_biasprm, actuator_ctrlrange, actuator_forcerange;
   // collision candidates, ray-cast set
   std::vector<int> pair_geom1, pair_geom2, ray_geoms;
@@ -129,7 +129,7 @@ struct Model {
     LI(geom_type); LI(geom_bodyid); LI(geom_condim); LI(geom_priority); LI(geom_group); LI(site_bodyid);
     LR(geom_size); LR(geom_pos); LR(geom_quat); LR(geom_friction); LR(geom_solmix); LR(geom_solref);
     LR(geom_solimp); LR(geom_margin); LR(geom_gap); LR(geom_rbound); LR(site_pos); LR(site_quat);
-    LI(actuator_trnid); LI(actuator_biastype); LI(actuator_ctrllimited); LI(actuator_forcelimited);
+    LI(actuator_trnid); LI(actuator_trntype); LI(actuator_biastype); LI(actuator_ctrllimited); LI(actuator_forcelimited);
     LR(actuator_gear); LR(actuator_gainprm); LR(actuator_biasprm); LR(actuator_ctrlrange); LR(actuator_forcerange);
     LI(pair_geom1); LI(pair_geom2); LI(ray_geoms);
     LR(key_qpos); LR(key_qvel); LR(key_ctrl); LR(key_mpos); LR(key_mquat);

@@ -921,17 +921,30 @@ void actuation(const Model<T>& m, Data<T>& d) {
     T ctrl = d.ctrl[i];
     if (m.actuator_ctrllimited[i])
       ctrl = mm::max(m.actuator_ctrlrange[2 * i], mm::min(m.actuator_ctrlrange[2 * i + 1], ctrl));
-    int j = m.actuator_trnid[i];
+    const int j = m.actuator_trnid[i];
+    const bool tendon = m.actuator_trntype[i] == 1;    // mjTRN_TENDON: length / moment through the fixed tendon's coefficients
     T gear = m.actuator_gear[i];
     T force = m.actuator_gainprm[3 * i] * ctrl;
     if (m.actuator_biastype[i] == 1) {
-      T length = gear * d.qpos[m.jnt_qposadr[j]], vel = gear * d.qvel[m.jnt_dofadr[j]];
+      T length = 0, vel = 0;
+      if (tendon) {
+        for (int w = m.tendon_adr[j]; w < m.tendon_adr[j] + m.tendon_num[j]; w++) {
+          length += m.wrap_coef[w] * d.qpos[m.wrap_qposadr[w]]; vel += m.wrap_coef[w] * d.qvel[m.wrap_dof[w]];
+        }
+        length *= gear; vel *= gear;
+      } else {
+        length = gear * d.qpos[m.jnt_qposadr[j]]; vel = gear * d.qvel[m.jnt_dofadr[j]];
+      }
       force += m.actuator_biasprm[3 * i] + m.actuator_biasprm[3 * i + 1] * length + m.actuator_biasprm[3 * i + 2] * vel;
     }
     if (m.actuator_forcelimited[i])
       force = mm::max(m.actuator_forcerange[2 * i], mm::min(m.actuator_forcerange[2 * i + 1], force));
     d.actuator_force[i] = force;
-    d.qfrc_actuator[m.jnt_dofadr[j]] += gear * force;
+    if (tendon) {
+      for (int w = m.tendon_adr[j]; w < m.tendon_adr[j] + m.tendon_num[j]; w++) d.qfrc_actuator[m.wrap_dof[w]] += gear * m.wrap_coef[w] * force;
+    } else {
+      d.qfrc_actuator[m.jnt_dofadr[j]] += gear * force;
+    }
   }
 }
 

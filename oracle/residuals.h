@@ -13,7 +13,8 @@
 namespace oracle {
 
 enum { RESIDUAL_PARTICLE = 0, RESIDUAL_PARTICLE_COPY = 1, RESIDUAL_CARTPOLE = 2, RESIDUAL_QUADRUPED_FLAT = 3,
-       RESIDUAL_HUMANOID_STAND = 4, RESIDUAL_HUMANOID_TRACK = 5 };
+       RESIDUAL_HUMANOID_STAND = 4, RESIDUAL_HUMANOID_TRACK = 5, RESIDUAL_SHADOW_REORIENT = 6 };
+enum { SI_GRASP_SITE = 0, SI_CUBE_BODY = 1, SI_GOAL_BODY = 2, SI_KEY_GRASP = 3 };
 enum { QS_MODE = 0, QS_MODE_START_TIME = 1, QS_POSITION = 2, QS_HEADING = 5, QS_SPEED = 7, QS_ANGVEL = 8, QS_GROUND = 9,
        QS_ORIENTATION = 10, QS_GAIT = 14, QS_PHASE_START = 15, QS_PHASE_START_TIME = 16, QS_PHASE_VELOCITY = 17,
        QS_JUMP_VEL = 18, QS_FLIGHT_TIME = 19, QS_JUMP_ACC = 20, QS_CROUCH_TIME = 21, QS_LEAP_TIME = 22,
@@ -392,6 +393,37 @@ void residual_quadruped(const Model<T>& m, Data<T>& d, T* r) {
   QuadrupedFn<T>(m).Residual(d, r);
 }
 
+// Shadow Hand cube reorientation <- mjpc/tasks/shadow_reorient/hand.cc:37-84 (81 residuals).  Sensors restated:
+// palm_position = grasp_site xpos, cube_position / cube_orientation = cube body frame, cube_goal_orientation = goal body
+// frame, cube_linear_velocity = world-frame velocity of the cube body origin (framelinvel -> mj_objectVelocity).
+// The posture / velocity terms read qpos + 7 and qvel + 6 for 26 values LITERALLY: with the goal ball joint first
+// (4 qpos / 3 qvel) and the cube free joint second they start at the cube QUATERNION and at the cube's ANGULAR
+// velocity, not at the first hand joint.
+template <class T>
+void residual_shadow_reorient(const Model<T>& m, Data<T>& d, T* r) {
+  const int* I = m.task_ids.data();
+  const int cube = I[SI_CUBE_BODY], goal = I[SI_GOAL_BODY];
+  int counter = 0;
+  const T* palm = &d.site_xpos[3 * I[SI_GRASP_SITE]];
+  const T* pos = &d.xpos[3 * cube];
+  for (int c = 0; c < 3; c++) r[counter++] = pos[c] - palm[c];
+  T gq[4] = {d.xquat[4 * goal], d.xquat[4 * goal + 1], d.xquat[4 * goal + 2], d.xquat[4 * goal + 3]};
+  quat_normalize(gq);
+  sub_quat(r + counter, gq, &d.xquat[4 * cube]);
+  counter += 3;
+  {
+    const T* cv = &d.cvel[6 * cube];
+    T off[3], wx[3];
+    for (int c = 0; c < 3; c++) off[c] = d.xpos[3 * cube + c] - d.subtree_com[3 * m.body_rootid[cube] + c];
+    cross3(wx, cv, off);
+    for (int c = 0; c < 3; c++) r[counter++] = cv[3 + c] + wx[c];
+  }
+  for (int i = 0; i < m.nu; i++) r[counter++] = d.actuator_force[i];
+  const T* key = &m.key_qpos[m.nq * I[SI_KEY_GRASP]];
+  for (int i = 0; i < 26; i++) r[counter++] = d.qpos[7 + i] - key[7 + i];
+  for (int i = 0; i < 26; i++) r[counter++] = d.qvel[6 + i];
+}
+
 template <class T>
 ResidualCallback<T> residual_by_id(int id) {
   switch (id) {
@@ -401,6 +433,7 @@ ResidualCallback<T> residual_by_id(int id) {
     case RESIDUAL_QUADRUPED_FLAT: return residual_quadruped<T>;
     case RESIDUAL_HUMANOID_STAND: return residual_humanoid_stand<T>;
     case RESIDUAL_HUMANOID_TRACK: return residual_humanoid_track<T>;
+    case RESIDUAL_SHADOW_REORIENT: return residual_shadow_reorient<T>;
   }
   return nullptr;
 }
