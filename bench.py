@@ -250,6 +250,67 @@ def humanoid_probe():
     return out
 
 
+def shadow_probe(cpu_threads):
+    """BASELINE config 5 task (Shadow Hand cube reorientation, PS 512 x 48, 5 cubic knots, dt 0.01) on the documented
+    primitive-geom stand-in hand (mujoco_menagerie's meshes are not in the tree): generic kernels, device-timed, with
+    the fp64 oracle on a 128-candidate share beside it."""
+    from conftest import get_model
+    from mujoco_mpc_b200.blob import to_blob
+    from mujoco_mpc_b200.engine import Engine
+    from mujoco_mpc_b200.planner import candidate_knots
+    from oracle import pyoracle
+    m = get_model("shadow_reorient")
+    N, H, P = 512, 48, 5
+    q0 = m.key_qpos[0]
+    hold = np.zeros(m.nu)
+    for i in range(m.nu):
+        if m.actuator_trntype[i] == 0:
+            hold[i] = q0[m.jnt_qposadr[m.actuator_trnid[i]]]
+        else:
+            t = m.actuator_trnid[i]
+            hold[i] = sum(m.wrap_coef[w] * q0[m.wrap_qposadr[w]] for w in range(m.tendon_adr[t], m.tendon_adr[t] + m.tendon_num[t]))
+    knots = candidate_knots(np.tile(hold, (P, 1)), 0.1, np.asarray(m.actuator_ctrlrange, float), 0, N, seed=7).astype(np.float32)
+    kt = np.linspace(0.0, (H - 1) * m.opt_timestep, P)
+    state = np.concatenate([q0, np.zeros(m.nv)])
+    mocap = np.zeros(7 * m.nmocap)
+    e = Engine(m, N, H)
+    ms = []
+    for i in range(6):
+        ret, fail, _ = e.rollout_spline(state, 0.0, mocap, knots, kt, 2, H)
+        if i >= 2:
+            ms.append(e.last_kernel_ms)
+    o = pyoracle.Oracle(to_blob(m), m, 64)
+    o.rollout_spline(state, 0.0, mocap, knots[:16], kt, 2, H, nthreads=cpu_threads, full=False)
+    t0 = time.perf_counter()
+    r = o.rollout_spline(state, 0.0, mocap, knots[:128], kt, 2, H, nthreads=cpu_threads, full=False)
+    cpu_s = time.perf_counter() - t0
+    rel = np.abs(ret[:128] - r["returns"]) / np.abs(r["returns"])
+    out = {"workload": "Shadow-Hand-shaped cube reorientation PS (STAND-IN hand: primitive geoms, same tree / dof / actuator / "
+                       "tendon structure and task as shadow_reorient/task.xml), 512 candidates x 48 steps, 5 cubic knots, dt 0.01, fp32",
+           "nq_nv_nu": [int(m.nq), int(m.nv), int(m.nu)], "residuals": int(m.task_num_residual),
+           "kernel_ms": float(np.mean(ms)), "env_steps_per_s": N * H / (float(np.mean(ms)) * 1e-3),
+           "static_kernel": bool(e.last_kernel_static), "failures": int(fail.sum()),
+           "cpu_oracle_fp64": {"value": 128 * H / cpu_s, "threads": cpu_threads, "sample": "128 of the 512 candidates x 48 steps"},
+           "parity_vs_fp64_oracle_128": {"median_rel": float(np.median(rel)), "max_rel": float(rel.max()), "above_1e-4": int((rel > 1e-4).sum())}}
+    e.close()
+    return out
+
+
+def model_fidelity(m):
+    """What of the reference model the compiled model keeps (recorded in the bench line so that the workload is auditable)."""
+    import collections
+    names = {0: "plane", 2: "sphere", 3: "capsule", 4: "ellipsoid", 5: "cylinder", 6: "box"}
+    kept, dropped = collections.Counter(), collections.Counter()
+    for a, b in zip(m.pair_geom1, m.pair_geom2):
+        kept["-".join(sorted((names[int(m.geom_type[a])], names[int(m.geom_type[b])])))] += 1
+    for a, b in getattr(m, "pairs_dropped", []):
+        dropped["-".join(sorted((names[int(m.geom_type[a])], names[int(m.geom_type[b])])))] += 1
+    return {"nq": int(m.nq), "nv": int(m.nv), "nu": int(m.nu), "ngeom": int(m.ngeom), "collision_pairs": dict(kept),
+            "collision_pairs_dropped_no_narrow_phase": dict(dropped),
+            "note": "pairs MuJoCo's filters keep; dropped types have no narrow phase here (cylinder / box against capsule, "
+                    "cylinder, box - MuJoCo's convex / box-box routines) and are dropped on BOTH the device and the oracle"}
+
+
 def hbm_peak():
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -446,6 +507,7 @@ def main():
     probes = world == 1 and not args.no_probes
     ilqg = ilqg_probe(m, eng, mocap, cores) if probes else None
     config3 = humanoid_probe() if probes else None
+    config5 = shadow_probe(cores) if probes else None
     cpu = None
     parity = None
     if not args.no_cpu_baseline and world == 1:     # the CPU arm is reported at N = 1 only
@@ -504,7 +566,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": WORKLOAD if world == 1 else WORKLOAD + "; N GPUs: one planning problem, %d candidates sharded %d per GPU" % (n_total, N_CAND),
-                       "candidates_per_gpu": N_CAND, "candidates_total": n_total, "horizon": HORIZON, "spline_points": P,
+                       "model": model_fidelity(m), "candidates_per_gpu": N_CAND, "candidates_total": n_total, "horizon": HORIZON, "spline_points": P,
                        "nominal": "steady-state policy after %d planning iterations from the zero policy (return %.4f)" % (BURN_IN, nominal_return),
                        "l2": "flushed between timed iterations (256 MB memset)",
                        "sharding": "one problem, contiguous candidate ranges, one ncclAllGather of returns per iteration" if world > 1 else "single GPU",
@@ -512,7 +574,7 @@ def main():
                                     "Engine.rollout_spline_sharded (mjpc_b200_rollout_spline_sharded: H2D, kernel, ncclAllGather, rank, D2H) + "
                                     "fetch_trajectory_sharded(winner: ncclBroadcast), host buffers")},
             "clocks": clk, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(gpu_launches), "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "ilqg": ilqg, "humanoid_track": config3,
+            "gpu_launches": int(gpu_launches), "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "ilqg": ilqg, "humanoid_track": config3, "shadow_reorient_standin": config5,
             "multi_gpu": multi, "wall_s_timed_region": wall}
     print(json.dumps(line), flush=True)
     if world > 1:
