@@ -219,6 +219,13 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& A) {
         A.stats[12 * cand + 4 + k] = 0;
 #endif
       }
+#ifndef MJPC_PHASE_TIMING
+      // placement diagnostics (profiles/placement.py): which SM and which hardware warp slot ran this candidate
+      unsigned smid, warpid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      asm volatile("mov.u32 %0, %%warpid;" : "=r"(warpid));
+      A.stats[12 * cand + 4] = smid; A.stats[12 * cand + 5] = warpid;
+#endif
     }
   }
 }
