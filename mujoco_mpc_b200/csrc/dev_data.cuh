@@ -7,6 +7,19 @@
 
 #include "dev_model.h"
 
+// Code-footprint control (profiles/README.md "code footprint"): with one warp per scheduler every instruction-cache
+// miss is exposed, and the Newton loop's straight-line code (fully unrolled by default) streams from L2 on every
+// iteration.  MJPC_ROLL marks loops whose unrolling buys no ILP worth its code size.
+#ifndef MJPC_NO_COMPACT   // -DMJPC_NO_COMPACT restores the fully unrolled build (profiles/r02_code_footprint.txt compares them)
+#define MJPC_COMPACT 1
+#endif
+#ifdef MJPC_COMPACT
+#define MJPC_ROLL _Pragma("unroll 1")
+#define MJPC_HESS_ROLLED 1
+#else
+#define MJPC_ROLL
+#endif
+
 namespace mjpc_dev {
 
 constexpr int kMaxSplinePoints = 64;  // knot_times has a fixed capacity so that only the LAST array depends on P
@@ -338,14 +351,66 @@ __device__ __forceinline__ void warp_chol_factor_solve_reg(float* A, float* x, c
   __syncwarp();
 }
 
+// ---- rolled left-looking variant for compile-time N <= 32 (experiment MJPC_CHOL_ROLLED2, code footprint): lane i owns
+// row i in shared memory; column j is one dot product over the finished columns (8-byte loads when rows are 8-byte
+// aligned), a shuffle broadcast of the pivot and one store per lane.  ~1 KB of code instead of 13 KB.
+template <int N>
+__device__ __forceinline__ void warp_chol_factor_solve_rolled(float* A, float* inv, float* x, const float* b, int lane) {
+  const int li = lane < N ? lane : N - 1;
+  float y = b[li];
+  __syncwarp();   // x == b callers
+  float* rowi = A + li * N;
+#pragma unroll 1
+  for (int j = 0; j < N; j++) {
+    const float* rowj = A + j * N;
+    float s = rowi[j];
+    int k = 0;
+    if (N % 2 == 0) {
+#pragma unroll 2
+      for (; k + 1 < j; k += 2) {
+        const float2 a = *reinterpret_cast<const float2*>(rowi + k), bb = *reinterpret_cast<const float2*>(rowj + k);
+        s -= a.x * bb.x; s -= a.y * bb.y;
+      }
+    }
+#pragma unroll 1
+    for (; k < j; k++) s -= rowi[k] * rowj[k];
+    float p = __shfl_sync(kFull, s, j);
+    if (p < kMinVal) p = kMinVal;
+    const float l = sqrtf(p), il = 1.0f / l;
+    if (lane >= j && lane < N) rowi[j] = (lane == j) ? l : s * il;
+    if (lane == j) inv[j] = il;
+    __syncwarp();
+  }
+#pragma unroll 1
+  for (int i = 0; i < N; i++) {  // forward: L y = b
+    const float yi = __shfl_sync(kFull, y, i) * inv[i];
+    const float lij = rowi[i];
+    y = (lane == i) ? yi : (lane > i ? y - lij * yi : y);
+  }
+#pragma unroll 1
+  for (int i = N - 1; i >= 0; i--) {  // backward: L^T x = y
+    const float xi = __shfl_sync(kFull, y, i) * inv[i];
+    const float lji = A[i * N + li];
+    y = (lane == i) ? xi : (lane < i ? y - lji * xi : y);
+  }
+  if (lane < N) x[lane] = y;
+  __syncwarp();
+}
+
 // factor A (destroyed, holds L afterwards) and solve A x = b; dispatches to the register variant for the
 // dof counts of the built-in models
 // NS > 0: the size is a compile-time constant of a static spec (register-resident path, no dispatch)
 template <int NS>
 __device__ __noinline__ void warp_chol_factor_solve(float* A, float* inv, float* x, const float* b, int n, int lane) {
+#ifdef MJPC_CHOL_ROLLED2
+  if constexpr (NS > 0 && NS <= 32) { warp_chol_factor_solve_rolled<NS>(A, inv, x, b, lane); return; }
+  if (n == 18) { warp_chol_factor_solve_rolled<18>(A, inv, x, b, lane); return; }
+#endif
+#ifndef MJPC_CHOL_ROLLED   // experiment (profiles/README.md, code footprint): rolled shared-memory factorisation everywhere
   if constexpr (NS > 0 && NS <= 32) { warp_chol_factor_solve_reg<NS>(A, x, b, lane); return; }
   if (n == 18) { warp_chol_factor_solve_reg<18>(A, x, b, lane); return; }
   if (n == 2) { warp_chol_factor_solve_reg<2>(A, x, b, lane); return; }
+#endif
   warp_chol(A, inv, n, lane);
   warp_chol_solve(x, A, inv, b, n, lane);
 }

@@ -7,6 +7,8 @@
 
 namespace mjpc_dev {
 
+
+
 // ------------------------------------------------------------------------------------------ position stage
 template <class SP>
 __device__ __noinline__ void k_kinematics(Ctx& c) {
@@ -125,6 +127,7 @@ __device__ __noinline__ void k_com_pos(Ctx& c) {
     if (submass[b] < kMinVal) {
       for (int k = 0; k < 3; k++) s[k] = xipos[3 * b + k];
     } else {
+      MJPC_ROLL
       for (int q = subend[b] - 1; q >= b; q--)
         for (int k = 0; k < 3; k++) s[k] += mass[q] * xipos[3 * q + k];
       for (int k = 0; k < 3; k++) s[k] /= submass[b];
@@ -194,6 +197,7 @@ __device__ __noinline__ void k_crb(Ctx& c) {
   for (int b = 1 + lane; b < M.nbody; b += 32) {
     float s[10];
     for (int k = 0; k < 10; k++) s[k] = 0;
+    MJPC_ROLL
     for (int q = subend[b] - 1; q >= b; q--)
       for (int k = 0; k < 10; k++) s[k] += cinert[10 * q + k];
     for (int k = 0; k < 10; k++) crb[10 * b + k] = s[k];
@@ -446,12 +450,14 @@ __device__ __noinline__ void k_collision(Ctx& c) {
         else if (t1 == GEOM_SPHERE && t2 == GEOM_BOX) n = collide_sphere_box(raw, p1, s1[0], p2, m2, s2);
         else if (t1 == GEOM_CAPSULE && t2 == GEOM_CAPSULE) n = collide_capsule_capsule(raw, p1, m1, s1, p2, m2, s2, margin);
       }
+      MJPC_ROLL
       for (int k = 0; k < n; k++)
         if (raw[k].dist < margin) { if (cnt != k) raw[cnt] = raw[k]; cnt++; }
     }
     const int incl = warp_incl_scan(cnt, lane);
     const int total = __shfl_sync(kFull, incl, 31);
     const int excl = incl - cnt;
+    MJPC_ROLL
     for (int k = 0; k < cnt; k++) {
       const int idx = ncon + excl + k;
       if (idx >= M.maxcon) break;  // capacity (warning raised below)
@@ -704,6 +710,7 @@ __device__ __noinline__ void k_make_constraint(Ctx& c) {
     // dense copies of the contact rows feed the register-blocked Hessian assembly (zeros off the chains)
     float* Jd = DF(efc_Jd);
     const int nvp = (nv + 3) & ~3;   // dense row stride, 16-byte aligned for vector loads
+    MJPC_ROLL
     for (int w = lane + (M.nfloss + c.nlim) * nvp; w < ne * nvp; w += 32) Jd[w] = 0.f;
     __syncwarp();
     // compact Jacobian entries: one (contact, local dof) pair per lane
@@ -719,6 +726,7 @@ __device__ __noinline__ void k_make_constraint(Ctx& c) {
       if (g1a[ci] < 0) {   // tendon limit: J = -side * coef on the wrapped dofs
         const int t = -g1a[ci] - 1;
         float v = 0.f;
+        MJPC_ROLL
         for (int w2 = tadr2[t]; w2 < tadr2[t] + tnum2[t]; w2++) if (wdof2[w2] == i) v += -DF(con_mu)[ci] * wcoef[w2];
         J[adr * kL + l] = v;
         Jd[adr * nvp + i] = v;
@@ -837,6 +845,7 @@ __device__ __noinline__ void k_make_constraint(Ctx& c) {
         // all edges share R = 2 mu^2 R_first; from here on con_dim is the contact's ROW count
         const float mu = fr[0] * sqrtf(1.f / fmaxf(kMinVal, CM(c).impratio));
         const float Rpy = 2.f * mu * mu * R[a];
+        MJPC_ROLL
         for (int j = 0; j < 2 * (dim - 1); j++) R[a + j] = Rpy;
         DF(con_mu)[ci] = mu;
         cdim[ci] = 2 * (dim - 1);
@@ -844,10 +853,12 @@ __device__ __noinline__ void k_make_constraint(Ctx& c) {
       }
       R[a + 1] = R[a] / fmaxf(kMinVal, CM(c).impratio);
       DF(con_mu)[ci] = fr[0] * sqrtf(R[a + 1] / R[a]);
+      MJPC_ROLL
       for (int j = 1; j < dim - 1; j++) R[a + j + 1] = R[a + 1] * fr[0] * fr[0] / (fr[j] * fr[j]);
     }
     __syncwarp();
     float* D = DF(efc_D);
+    MJPC_ROLL
     for (int i = lane; i < ne; i += 32) D[i] = 1 / R[i];
   }
   // --- wrench-space form of the rows of ONE-SIDED contacts (one geom on a body without dofs): J[row][i] = w_row . cdof_i
@@ -965,6 +976,7 @@ __device__ __noinline__ void k_com_vel(Ctx& c) {
   __syncwarp();
   for (int b = lane; b < M.nbody; b += 32) {
     float s[3] = {0, 0, 0};
+    MJPC_ROLL
     for (int q = subend[b] - 1; q >= b; q--)
       for (int k = 0; k < 3; k++) s[k] += blin[3 * q + k];
     for (int k = 0; k < 3; k++) slin[3 * b + k] = s[k] / fmaxf(kMinVal, submass[b]);
@@ -1049,6 +1061,7 @@ __device__ __noinline__ void k_smooth_forces(Ctx& c) {
         float length, vel;
         if (trntype[i] == 1) {
           length = 0.f; vel = 0.f;
+          MJPC_ROLL
           for (int w = tadr[j]; w < tadr[j] + tnum[j]; w++) { length += wcoef[w] * qpos[wq[w]]; vel += wcoef[w] * qvel[wdof[w]]; }
           length *= gear[i]; vel *= gear[i];
         } else {
@@ -1062,9 +1075,11 @@ __device__ __noinline__ void k_smooth_forces(Ctx& c) {
     __syncwarp();
     for (int d = lane; d < nv; d += 32) {
       float s = 0;
+      MJPC_ROLL
       for (int i = 0; i < M.nu; i++) {
         if (trntype[i] == 1) {
           const int t = trnid[i];
+          MJPC_ROLL
           for (int w = tadr[t]; w < tadr[t] + tnum[t]; w++) if (wdof[w] == d) s += gear[i] * wcoef[w] * aforce[i];
         } else if (jdadr[trnid[i]] == d) {
           s += gear[i] * aforce[i];
@@ -1085,6 +1100,7 @@ __device__ __noinline__ void k_smooth_forces(Ctx& c) {
       const int b0 = dbody[i];
       const float* cd = cdof + 6 * i;
       float a = 0.f;
+      MJPC_ROLL
       for (int b = b0; b < subend[b0]; b++) {
         float off[3], t[3];
         for (int q = 0; q < 3; q++) off[q] = xipos[3 * b + q] - scom[3 * rootid[b] + q];
@@ -1213,6 +1229,7 @@ __device__ __forceinline__ void hessian_dense_reg(Ctx& c) {
   {
     // cone effective rows in wrench space: V = sum_a q_a w_a, U = sum_a q_{6+a} w_a  -> efc_hc[36 ci + 14 ..]
     float* xwm = DF(efc_hc);
+    MJPC_ROLL
     for (int w = lane; w < ncon * 6; w += 32) {
       const int ci = w / 6, p = w - 6 * ci;
       const int a0 = cadr[ci];
@@ -1230,6 +1247,7 @@ __device__ __forceinline__ void hessian_dense_reg(Ctx& c) {
     constexpr int kMaxRows = 10;   // pyramidal condim 6; elliptic contacts have <= 6 rows
     const bool pyr = M.cone == CONE_PYRAMIDAL;
     const int nwork = ncon * 21;
+    MJPC_ROLL
     for (int base = 0; base < nwork; base += 32) {
       const int w = min(base + lane, nwork - 1);
       const int ci = w / 21, e = w - 21 * ci;
@@ -1240,7 +1258,11 @@ __device__ __forceinline__ void hessian_dense_reg(Ctx& c) {
       const int a0 = max(a0r, 0);
       const int nrows = on ? cdim[ci] : 0;
       float acc = 0.f;
+#ifdef MJPC_HESS_ROLLED
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
       for (int a = 0; a < kMaxRows; a++) {
         if (a >= 6 && !pyr) break;                       // compile-time for a static spec
         const int r = min(a0 + a, M.maxefc - 1);
@@ -1256,6 +1278,7 @@ __device__ __forceinline__ void hessian_dense_reg(Ctx& c) {
     // g_i = (sum of W_c over the contacts on bodies in the subtree of dof i's body) cdof_i, one (dof, component) per lane
     const int *subend = MI(body_subtreeend), *cmb = DI(con_mbody), *dbody = MI(dof_bodyid);
     const float* cdof = DF(cdof);
+    MJPC_ROLL
     for (int w = lane; w < NV * 6; w += 32) {
       const int i = w / 6, k = w - 6 * i;
       const int b = dbody[i], se = subend[b];
@@ -1264,6 +1287,7 @@ __device__ __forceinline__ void hessian_dense_reg(Ctx& c) {
 #pragma unroll
       for (int l = 0; l < 6; l++) { idx[l] = k >= l ? k * (k + 1) / 2 + l : l * (l + 1) / 2 + k; cd[l] = cdof[6 * i + l]; }
       float a = 0.f;
+      MJPC_ROLL
       for (int ci = 0; ci < ncon; ci++) {
         const int mb = cmb[ci];                       // -1 for two-sided / dropped contacts
         const float* Wk = Wc + 21 * ci;
@@ -1276,6 +1300,60 @@ __device__ __forceinline__ void hessian_dense_reg(Ctx& c) {
     }
     __syncwarp();
   }
+#ifdef MJPC_HESS_ROLLED
+  // experiment (code footprint): one rolled loop over the pattern entries, H written directly, the rare rank-1 rows
+  // of two-sided contacts added in shared memory afterwards
+  if (NE != NV * (NV + 1) / 2) {   // entries outside the pattern (the dense factor reads them); nothing to clear for a full pattern
+    MJPC_ROLL
+    for (int w = lane; w < NV * NV; w += 32) H[w] = 0.f;
+    __syncwarp();
+  }
+  {
+    const float* cdof = DF(cdof);
+    const int* dbody2 = MI(dof_bodyid);
+    const int* drow = DI(efc_drow);
+#pragma unroll 1
+    for (int e0 = 0; e0 < NE; e0 += 32) {
+      const int e = min(e0 + lane, NE - 1);
+      const int r = hi[e], sdof = hj[e];
+      float a = qM[r * NV + sdof];
+      const int br = dbody2[r];
+      const unsigned mlo_r = (unsigned)MI(body_dofmask_lo)[br], mhi_r = (unsigned)MI(body_dofmask_hi)[br];
+      const bool anc = sdof < 32 ? ((mlo_r >> sdof) & 1u) : ((mhi_r >> (sdof - 32)) & 1u);
+      const float *gr = g + 6 * r, *cs = cdof + 6 * sdof;
+      float dsum = 0.f;
+#pragma unroll
+      for (int l = 0; l < 6; l++) dsum += gr[l] * cs[l];
+      a += anc ? dsum : 0.f;
+      if (r == sdof) {
+        const int fr = frow[r];
+        if (fr >= 0) a += hw[fr];
+        MJPC_ROLL
+        for (int k = M.nfloss; k < M.nfloss + c.nlim; k++) { const float hk = hw[k]; a += edof[k] == r ? hk : 0.f; }
+      }
+      MJPC_ROLL
+      for (int k = 0; k < c.ndrow; k++) {
+        const int row = drow[k];
+        const float* j = Jd + row * NVP;
+        a += hw[row] * j[r] * j[sdof];
+      }
+      if (c.ndrow > 0) {
+        MJPC_ROLL
+        for (int ci = 0; ci < ncon; ci++) {
+          const int a0 = cadr[ci];
+          if (a0 < 0 || cside[ci] != 0 || state[a0] != STATE_CONE) continue;   // warp-uniform
+          const float wv = xw[36 * ci + 12], wu = xw[36 * ci + 13];
+          const float* xv = Xd + (2 * ci) * NVP;
+          const float* xu = xv + NVP;
+          a += wv * xv[r] * xv[sdof] + wu * xu[r] * xu[sdof];
+        }
+      }
+      if (e0 + lane < NE) { H[r * NV + sdof] = a; H[sdof * NV + r] = a; }
+    }
+  }
+  __syncwarp();
+}
+#else
   int er[NQ], es[NQ];
   float acc[NQ];
   for (int w = lane; w < NV * NV; w += 32) H[w] = 0.f;   // entries outside the pattern (the factor fills them)
@@ -1334,6 +1412,7 @@ __device__ __forceinline__ void hessian_dense_reg(Ctx& c) {
     if (lane + 32 * q < NE) { H[er[q] * NV + es[q]] = acc[q]; H[es[q] * NV + er[q]] = acc[q]; }
   __syncwarp();
 }
+#endif
 
 // row i of (NV x NV row-major matrix) times vector, compile-time NV, 8-byte vector loads (NV even)
 template <int NV>
@@ -1718,13 +1797,23 @@ __device__ __forceinline__ LsPoint ls_eval_cached(const LsItem& it, float g0, fl
   return p;
 }
 
+#ifdef MJPC_COMPACT
+// one shared copy of the evaluation for the ~6 call sites of the line search (the item travels by value in registers)
+__device__ __noinline__ LsPoint ls_eval_cached_shared(LsItem it, float g0, float g1, float g2, float alpha) {
+  return ls_eval_cached(it, g0, g1, g2, alpha);
+}
+#define LS_EVAL_CACHED ls_eval_cached_shared
+#else
+#define LS_EVAL_CACHED ls_eval_cached
+#endif
+
 template <class SP>
 __device__ __noinline__ float k_line_search(Ctx& c, float g0, float g1, float g2, float snorm, float scale_inv) {
   auto&& M = SP::model(c);
   if (snorm < kMinVal) return 0.f;
   const bool cached = c.nitem <= 32;   // one work item per lane: the usual case
   const LsItem item = ls_load_item<SP>(c);
-  auto ev = [&](float alpha) { return cached ? ls_eval_cached(item, g0, g1, g2, alpha) : k_ls_eval<SP>(c, g0, g1, g2, alpha); };
+  auto ev = [&](float alpha) { return cached ? LS_EVAL_CACHED(item, g0, g1, g2, alpha) : k_ls_eval<SP>(c, g0, g1, g2, alpha); };
   const LsPoint p0 = ev(0.f);
   const float gtol = fmaxf(fmaxf(CM(c).tolerance, kTolFloor) * CM(c).ls_tolerance * snorm * scale_inv, 64 * 1.1920929e-7f * fabsf(p0.d1));
   if (p0.d2 <= kMinVal) return 0.f;
@@ -1800,7 +1889,11 @@ __device__ __forceinline__ void jt_force(Ctx& c, float* out_or_null) {
 }
 
 template <class SP>
+#ifdef MJPC_COMPACT
+__device__ __noinline__ void jt_force_any(Ctx& c, float* out, int nv) {
+#else
 __device__ __forceinline__ void jt_force_any(Ctx& c, float* out, int nv) {
+#endif
   if constexpr (SP::kNV > 0) jt_force_dense<SP, SP::kNV>(c, out);
   else { if (nv == 18) jt_force_dense<SP, 18>(c, out); else jt_force<SP>(c, out); }
 }
@@ -1942,6 +2035,7 @@ __device__ __noinline__ void k_euler(Ctx& c) {
   if (M.any_damping && !M.disable_eulerdamp) {
     float *H = DF(qH), *qM = DF(qM), *smooth = DF(qfrc_smooth), *qfc = DF(qfrc_constraint);
     const float* damping = MF(dof_damping);
+    MJPC_ROLL
     for (int w = lane; w < nv * nv; w += 32) {
       const int r = w / nv, s = w - r * nv;
       H[w] = qM[w] + (r == s ? h * damping[r] : 0.f);

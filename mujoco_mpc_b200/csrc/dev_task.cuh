@@ -31,11 +31,13 @@ __device__ __forceinline__ float norm_value(const float* x, const float* params,
   switch (type) {
     case kNull: y = x[0]; break;
     case kQuadratic:
+      MJPC_ROLL
       for (int i = 0; i < n; i++) y += x[i] * x[i];
       y *= 0.5f;
       break;
     case kL22: {
       float cc = 0;
+      MJPC_ROLL
       for (int i = 0; i < n; i++) cc += x[i] * x[i];
       const float a = powf(cc, q / 2) + powf(p, q);
       y = powf(a, 1 / q) - p;
@@ -43,23 +45,29 @@ __device__ __forceinline__ float norm_value(const float* x, const float* params,
     }
     case kL2: {
       float s = 0;
+      MJPC_ROLL
       for (int i = 0; i < n; i++) s += x[i] * x[i];
       y = sqrtf(s + p * p) - p;
       break;
     }
     case kCosh:
+      MJPC_ROLL
       for (int i = 0; i < n; i++) y += p * p * (coshf(x[i] / p) - 1);
       break;
     case kPowerLoss:
+      MJPC_ROLL
       for (int i = 0; i < n; i++) y += powf(fabsf(x[i]), p);
       break;
     case kSmoothAbsLoss:
+      MJPC_ROLL
       for (int i = 0; i < n; i++) y += sqrtf(x[i] * x[i] + p * p) - p;
       break;
     case kSmoothAbs2Loss:
+      MJPC_ROLL
       for (int i = 0; i < n; i++) y += powf(powf(fabsf(x[i]), q) + powf(p, q), 1 / q) - p;
       break;
     case kRectifyLoss:
+      MJPC_ROLL
       for (int i = 0; i < n; i++) y += p > 0 ? p * logf(1 + expf(x[i] / p)) : fmaxf(x[i], 0.f);
       break;
   }
@@ -80,11 +88,13 @@ __device__ __noinline__ float k_cost_value(Ctx& c) {
     float term = 0;
     if (k < M.num_term) {
       int f = 0, p = 0;
+      MJPC_ROLL
       for (int q = 0; q < k; q++) { f += dimr[q]; p += npar[q]; }
       float pr[2] = {npar[k] > 0 ? prm[p] : 0.f, npar[k] > 1 ? prm[p + 1] : 0.f};
       term = w[k] * norm_value(res + f, pr, dimr[k], ntype[k]);
     }
     const int cnt = min(32, M.num_term - base);
+    MJPC_ROLL
     for (int q = 0; q < cnt; q++) cost += __shfl_sync(kFull, term, q);
   }
   if (fabsf(CM(c).risk) < 1e-6f) return cost;

@@ -13,6 +13,8 @@ for i in range(int(sys.argv[1]) if len(sys.argv) > 1 else 2):
     ret, fail, order = e.rollout_spline(state, 0.0, mocap, knots, kt, 2, 64)
     ms.append(e.last_kernel_ms)
 print("kernel ms", ms[-1], "min", min(ms), "static", e.last_kernel_static)
+if len(sys.argv) > 2:
+    np.save(sys.argv[2], ret)   # returns of this build (compared across experiment builds)
 st = e.fetch_stats()
 cyc = st[:, 0] / 1.965e6
 print("per-candidate ms: min %.2f median %.2f max %.2f ; newton iters/step mean %.2f max-cand %.2f ; ncon/step %.2f nefc/step %.2f" % (
