@@ -158,14 +158,17 @@ def cpu_arm(m, state, mocap, knots, kt, threads, precision=64, budget_s=8.0, max
 
 
 def ilqg_probe(m, eng, mocap, cpu_threads):
-    """BASELINE config 4 (Quadruped iLQG, H=64, 10 line-search rollouts, one-sided FD, skip 0, differentiable model):
+    """BASELINE config 4 (Quadruped iLQG, H=64, 10 line-search rollouts, centred FD with eps 3e-4 - the fp32 setting with
+    which the planner follows the fp64 reference, csrc/host/ilqg_planner.h - skip 0, differentiable model):
     per-sweep device time (CUDA events around the kernels) and host wall time with host buffers, the roofline entry of
     each sweep kernel, and the same sweeps on the CPU port.  Reported beside the headline, not part of it."""
     from mujoco_mpc_b200.ilqg import ILQGPlanner
-    pl = ILQGPlanner(m, eng, horizon=HORIZON, num_rollouts=10, fd_tolerance=1e-3)
+    pl = ILQGPlanner(m, eng, horizon=HORIZON, num_rollouts=10, fd_tolerance=3e-4, fd_mode=1)
     pl.set_state(np.concatenate([m.key_qpos[0], np.zeros(m.nv)]), 0.0, mocap)
+    pl.nominal_trajectory()
+    descent = [float(pl.cand["total_return"])]
     for _ in range(3):
-        pl.optimize_policy()
+        pl.optimize_policy(); descent.append(float(pl.total_return))
     pl.nominal_trajectory()
     c = pl.cand
 
@@ -174,14 +177,14 @@ def ilqg_probe(m, eng, mocap, cpu_threads):
         for _ in range(reps):
             out = f(); dev.append(eng.last_kernel_ms)
         return (time.perf_counter() - t0) / reps * 1e3, float(np.mean(dev)), out
-    t_fd, d_fd, (A, B, C, D) = tm(lambda: eng.model_derivatives(c["states"], c["actions"], c["times"], pl.mocap, 1e-3))
+    t_fd, d_fd, (A, B, C, D) = tm(lambda: eng.model_derivatives(c["states"], c["actions"], c["times"], pl.mocap, 3e-4, mode=1))
     t_cd, d_cd, cd = tm(lambda: eng.cost_derivatives(c["residual"], C, D))
     t_bp, d_bp, bp = tm(lambda: eng.backward_pass(A, B, cd[0], cd[1], cd[2], cd[4], cd[3], c["actions"], mu=pl.regularization))
     t_ro, d_ro, _ = tm(lambda: eng.rollout_feedback(pl.state, 0.0, pl.mocap, c["actions"], c["states"], c["times"], bp["K"], bp["du"],
                                                     pl._steps(), 3))
     t_it, _, _ = tm(lambda: pl.optimize_policy())
     n, nu, nr, H = 2 * m.nv, m.nu, m.task_num_residual, HORIZON
-    fd_steps = H * (1 + nu + 2 * m.nv)
+    fd_steps = H * (1 + 2 * (nu + 2 * m.nv))          # centred: two evaluations per column + the centre
     peak = hbm_peak()[0]
     by_fd = 4 * H * (n * n + n * nu + nr * n + nr * nu)                       # A, B, C, D written once
     by_cd = 4 * H * (nr + nr * n + nr * nu + n + nu + n * n + nu * nu + n * nu)   # C, D, residual read; cx..cxu written
@@ -195,13 +198,14 @@ def ilqg_probe(m, eng, mocap, cpu_threads):
         if flops:
             r["fp32_gflops"] = flops / (ms * 1e-3) / 1e9
         return r
-    out = {"workload": "Quadruped (flat) iLQG, H=64, 10 line-search rollouts, one-sided FD (eps 1e-3), skip 0, MakeDifferentiable on",
+    out = {"workload": "Quadruped (flat) iLQG, H=64, 10 line-search rollouts, centred FD (eps 3e-4: the fp32 setting; the CPU arm uses the reference's 1e-6 one-sided in fp64), skip 0, MakeDifferentiable on",
+           "return_per_iteration_from_home_keyframe": descent,
            "fd_sweep_ms": t_fd, "fd_mj_step_equivalents": fd_steps, "fd_steps_per_s": fd_steps / (d_fd * 1e-3),
            "cost_derivatives_ms": t_cd, "backward_pass_ms": t_bp, "line_search_rollouts_ms": t_ro, "optimize_policy_ms": t_it,
            "device_ms": {"fd_sweep": d_fd, "cost_derivatives": d_cd, "backward_pass": d_bp, "line_search_rollouts": d_ro},
            "timing": "host wall clock around each C-ABI call with host buffers (…_ms) and CUDA events around the kernels (device_ms)",
-           "roofline": [roof("fd_center_kernel + fd_column_kernel (3136 one-warp mj_steps)", d_fd, by_fd,
-                             note="same device code as the rollout: dependent-instruction latency; 3136 warps fill the SMs"),
+           "roofline": [roof("fd_center_kernel + fd_column_kernel (%d one-warp mj_steps)" % fd_steps, d_fd, by_fd,
+                             note="same device code as the rollout: dependent-instruction latency; the warps fill the SMs two per SM (shared memory)"),
                         roof("cost_derivatives_kernel", d_cd, by_cd, fl_cd, "one CTA per time step, shared-memory FMA"),
                         roof("backward_pass_kernel", d_bp, by_bp, fl_bp,
                              "strictly sequential in t: one CTA, 63 dependent Riccati steps (36 us each)")]}

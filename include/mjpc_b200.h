@@ -300,6 +300,9 @@ int mjpc_b200_shadow_transition_step(void* transition, double* qpos, double* qve
 int mjpc_b200_ilqg_planner_create(const mjpc_model_blob* model, int num_rollouts, int representation, double fd_tolerance,
                                   int max_horizon, int device, void** out);
 void mjpc_b200_ilqg_planner_destroy(void* planner);
+/* finite-difference settings (ilqg/settings.h:23-24, iLQGPlanner::derivative_skip_): tolerance <= 0 / mode < 0 / skip < 0 keep
+ * the current value.  Defaults here: 3e-4, centred, 0 - the reference's 1e-6 one-sided is an fp64 setting (ilqg_planner.h). */
+void mjpc_b200_ilqg_planner_set_fd(void* planner, double tolerance, int mode, int derivative_skip);
 void mjpc_b200_ilqg_planner_reset(void* planner, int horizon, const double* initial_repeated_action);
 void mjpc_b200_ilqg_planner_set_state(void* planner, const double* state, double time, const double* mocap);
 int mjpc_b200_ilqg_planner_nominal_trajectory(void* planner, int horizon);
@@ -323,6 +326,7 @@ int mjpc_b200_gradient_planner_create(const mjpc_model_blob* model, int num_traj
                                       double fd_tolerance, double timestep, const double* ctrlrange, int max_horizon, int device,
                                       void** out);
 void mjpc_b200_gradient_planner_destroy(void* planner);
+void mjpc_b200_gradient_planner_set_fd(void* planner, double tolerance, int mode, int derivative_skip);   /* as for the iLQG planner */
 void mjpc_b200_gradient_planner_reset(void* planner, int horizon, const double* initial_repeated_action);
 void mjpc_b200_gradient_planner_set_state(void* planner, const double* state, double time, const double* mocap);
 int mjpc_b200_gradient_planner_optimize_policy(void* planner, int horizon);
@@ -341,6 +345,7 @@ int mjpc_b200_ilqs_planner_create(const mjpc_model_blob* model, int num_trajecto
                                   int ilqg_num_rollouts, int ilqg_representation, double fd_tolerance, int max_horizon, int device,
                                   void** out);
 void mjpc_b200_ilqs_planner_destroy(void* planner);
+void mjpc_b200_ilqs_planner_set_fd(void* planner, double tolerance, int mode, int derivative_skip);       /* its iLQG half */
 void mjpc_b200_ilqs_planner_reset(void* planner, int horizon, const double* initial_repeated_action);
 void mjpc_b200_ilqs_planner_set_state(void* planner, const double* state, double time, const double* mocap);
 void mjpc_b200_ilqs_planner_set_exploration(void* planner, double exploration);

@@ -34,7 +34,7 @@ struct AgentSettings {              // what the reference reads from the task XM
   int num_trajectory = 10, num_spline_points = 3, representation = 2;
   double exploration = 0.1;
   int ilqg_num_rollouts = 10, ilqg_representation = 1;
-  double fd_tolerance = 1.0e-3;
+  double fd_tolerance = 3.0e-4;     // with centred differences (ilqg_planner.h)
   int n_elite = 0; double std_min = 0.01, explore_fraction = 0.0;
   int robust_candidates = -1, robust_repetitions = 5; double robust_xfrc = 0.1, robust_xfrc_rate = 0.1;
   unsigned seed = 0x5EED;

@@ -371,6 +371,12 @@ int mjpc_b200_gradient_planner_create(const mjpc_model_blob* model, int num_traj
   return 0;
 }
 void mjpc_b200_gradient_planner_destroy(void* p) { delete (GradientPlanner*)p; }
+void mjpc_b200_gradient_planner_set_fd(void* p, double tolerance, int mode, int derivative_skip) {
+  auto& s = ((GradientPlanner*)p)->settings;
+  if (tolerance > 0) s.fd_tolerance = tolerance;
+  if (mode >= 0) s.fd_mode = mode ? 1 : 0;
+  if (derivative_skip >= 0) s.derivative_skip = derivative_skip;
+}
 void mjpc_b200_gradient_planner_reset(void* p, int horizon, const double* a) { ((GradientPlanner*)p)->Reset(horizon, a); }
 void mjpc_b200_gradient_planner_set_state(void* p, const double* state, double time, const double* mocap) {
   ((GradientPlanner*)p)->SetState(state, time, mocap);
@@ -404,6 +410,12 @@ int mjpc_b200_ilqs_planner_create(const mjpc_model_blob* model, int num_trajecto
   return 0;
 }
 void mjpc_b200_ilqs_planner_destroy(void* p) { delete (iLQSPlanner*)p; }
+void mjpc_b200_ilqs_planner_set_fd(void* p, double tolerance, int mode, int derivative_skip) {
+  auto& s = ((iLQSPlanner*)p)->ilqg.settings;
+  if (tolerance > 0) s.fd_tolerance = tolerance;
+  if (mode >= 0) s.fd_mode = mode ? 1 : 0;
+  if (derivative_skip >= 0) s.derivative_skip = derivative_skip;
+}
 void mjpc_b200_ilqs_planner_reset(void* p, int horizon, const double* a) { ((iLQSPlanner*)p)->Reset(horizon, a); }
 void mjpc_b200_ilqs_planner_set_state(void* p, const double* state, double time, const double* mocap) {
   ((iLQSPlanner*)p)->SetState(state, time, mocap);

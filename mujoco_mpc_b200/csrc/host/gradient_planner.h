@@ -31,8 +31,8 @@ void GradientSweep(const float* A, const float* B, const float* cx, const float*
 struct GradientPlannerSettings {        // gradient/settings.h:21-27
   int max_rollout = 1;
   double min_linesearch_step = 1.0e-8;
-  double fd_tolerance = 1.0e-5;
-  int fd_mode = 0;
+  double fd_tolerance = 3.0e-4;   // fp32: centred 3e-4 (ilqg_planner.h); the reference's gradient planner uses 1e-5 one-sided in fp64
+  int fd_mode = 1;
   int action_limits = 1;
   int derivative_skip = 0;
   int differentiable = 1;               // agent.cc:158-164

@@ -357,6 +357,12 @@ int mjpc_b200_ilqg_planner_create(const mjpc_model_blob* model, int num_rollouts
   return 0;
 }
 void mjpc_b200_ilqg_planner_destroy(void* p) { delete (iLQGPlanner*)p; }
+void mjpc_b200_ilqg_planner_set_fd(void* p, double tolerance, int mode, int derivative_skip) {
+  auto& s = ((iLQGPlanner*)p)->settings;
+  if (tolerance > 0) s.fd_tolerance = tolerance;
+  if (mode >= 0) s.fd_mode = mode ? 1 : 0;
+  if (derivative_skip >= 0) s.derivative_skip = derivative_skip;
+}
 void mjpc_b200_ilqg_planner_reset(void* p, int horizon, const double* initial_repeated_action) {
   ((iLQGPlanner*)p)->Reset(horizon, initial_repeated_action);
 }

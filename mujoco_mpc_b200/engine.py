@@ -33,7 +33,8 @@ EXPORTS = ["mjpc_b200_version", "mjpc_b200_last_error", "mjpc_b200_create", "mjp
            "mjpc_b200_ce_planner_create", "mjpc_b200_ce_planner_destroy", "mjpc_b200_ce_planner_reset",
            "mjpc_b200_ce_planner_set_state", "mjpc_b200_ce_planner_optimize_policy",
            "mjpc_b200_ce_planner_action_from_policy", "mjpc_b200_ce_planner_get_result",
-           "mjpc_b200_ilqg_planner_create", "mjpc_b200_ilqg_planner_destroy", "mjpc_b200_ilqg_planner_reset",
+           "mjpc_b200_ilqg_planner_create", "mjpc_b200_ilqg_planner_destroy", "mjpc_b200_ilqg_planner_set_fd",
+           "mjpc_b200_gradient_planner_set_fd", "mjpc_b200_ilqs_planner_set_fd", "mjpc_b200_ilqg_planner_reset",
            "mjpc_b200_ilqg_planner_set_state", "mjpc_b200_ilqg_planner_nominal_trajectory",
            "mjpc_b200_ilqg_planner_optimize_policy", "mjpc_b200_ilqg_planner_action_from_policy",
            "mjpc_b200_ilqg_planner_get_result", "mjpc_b200_host_ilqg_policy_action",
@@ -90,6 +91,9 @@ def load_library():
         lib.mjpc_b200_planner_set_exploration.argtypes = [C.c_void_p, C.c_double, C.c_double]
         lib.mjpc_b200_ce_planner_destroy.argtypes = [C.c_void_p]
         lib.mjpc_b200_ilqg_planner_destroy.argtypes = [C.c_void_p]
+        for n in ("mjpc_b200_ilqg_planner_set_fd", "mjpc_b200_gradient_planner_set_fd", "mjpc_b200_ilqs_planner_set_fd"):
+            getattr(lib, n).argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int]
+            getattr(lib, n).restype = None
         lib.mjpc_b200_robust_planner_destroy.argtypes = [C.c_void_p]
         lib.mjpc_b200_gradient_planner_destroy.argtypes = [C.c_void_p]
         lib.mjpc_b200_agent_destroy.argtypes = [C.c_void_p]
@@ -509,7 +513,7 @@ class CppCrossEntropyPlanner:
 class CppILQGPlanner:
     """The C++ iLQG planner (csrc/host/ilqg_planner.cc) through its C wrappers."""
 
-    def __init__(self, model, horizon, num_rollouts=10, representation=1, fd_tolerance=1e-3, device=0):
+    def __init__(self, model, horizon, num_rollouts=10, representation=1, fd_tolerance=3e-4, device=0, fd_mode=1, derivative_skip=0):
         self.lib = load_library()
         m = self.m = model
         self._blob = to_blob(model)
@@ -522,6 +526,7 @@ class CppILQGPlanner:
         if rc != 0:
             raise EngineError(f"mjpc_b200_ilqg_planner_create failed ({rc}): {self.lib.mjpc_b200_last_error().decode()}")
         self.h = h
+        self.lib.mjpc_b200_ilqg_planner_set_fd(self.h, C.c_double(fd_tolerance), int(fd_mode), int(derivative_skip))
 
     def close(self):
         if getattr(self, "h", None):
@@ -632,7 +637,7 @@ def host_spline_mapping(representation, input_times, output_times):
 class CppGradientPlanner:
     """The C++ GradientPlanner (csrc/host/gradient_planner.cc) through its C wrappers."""
 
-    def __init__(self, model, horizon, num_trajectory=8, num_spline_points=5, representation=1, fd_tolerance=1e-3, device=0):
+    def __init__(self, model, horizon, num_trajectory=8, num_spline_points=5, representation=1, fd_tolerance=3e-4, device=0, fd_mode=1):
         self.lib = load_library()
         self.m = model
         self._blob = to_blob(model)
@@ -647,6 +652,7 @@ class CppGradientPlanner:
         if rc != 0:
             raise EngineError(f"gradient_planner_create failed ({rc}): {self.lib.mjpc_b200_last_error().decode()}")
         self.h = h
+        self.lib.mjpc_b200_gradient_planner_set_fd(self.h, C.c_double(fd_tolerance), int(fd_mode), -1)
 
     def close(self):
         if getattr(self, "h", None):
@@ -684,7 +690,7 @@ class CppGradientPlanner:
 class CppILQSPlanner:
     """The C++ iLQSPlanner (csrc/host/gradient_planner.cc) through its C wrappers."""
 
-    def __init__(self, model, horizon, num_trajectory=8, num_rollouts=6, fd_tolerance=1e-3, seed=0x5EED, device=0):
+    def __init__(self, model, horizon, num_trajectory=8, num_rollouts=6, fd_tolerance=3e-4, seed=0x5EED, device=0, fd_mode=1):
         self.lib = load_library()
         m = self.m = model
         self._blob = to_blob(model)
@@ -703,6 +709,7 @@ class CppILQSPlanner:
         if rc != 0:
             raise EngineError(f"ilqs_planner_create failed ({rc}): {self.lib.mjpc_b200_last_error().decode()}")
         self.h = h
+        self.lib.mjpc_b200_ilqs_planner_set_fd(self.h, C.c_double(fd_tolerance), int(fd_mode), -1)
 
     def close(self):
         if getattr(self, "h", None):
@@ -745,7 +752,7 @@ class CppAgent:
 
     def __init__(self, model, planner="sampling", horizon=None, timestep=None, integrator=0, differentiable=-1, num_trajectory=None,
                  num_spline_points=None, representation=None, exploration=None, ilqg_num_rollouts=10, ilqg_representation=1,
-                 fd_tolerance=1e-3, seed=0x5EED, device=0):
+                 fd_tolerance=3e-4, seed=0x5EED, device=0):
         self.lib = load_library()
         m = self.m = model
         num = m.numeric

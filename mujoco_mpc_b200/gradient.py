@@ -109,12 +109,14 @@ class GradientSettings:                   # gradient/settings.h:21-27
 
 class GradientPlanner:
     def __init__(self, model, backend, horizon, num_trajectory=None, num_spline_points=None, representation=None,
-                 fd_tolerance=None):
+                 fd_tolerance=None, fd_mode=None):
         m = self.model = model
         self.backend = backend
         self.settings = GradientSettings()
         if fd_tolerance is not None:
             self.settings.fd_tolerance = fd_tolerance
+        if fd_mode is not None:
+            self.settings.fd_mode = int(fd_mode)
         num = m.numeric
         self.H = int(horizon)
         self.K = int(num_trajectory or num.get("gradient_num_trajectory", [32])[0])
@@ -212,10 +214,10 @@ class ILQSPlanner:
     K_SAMPLING, K_ILQG = 0, 1
 
     def __init__(self, model, sampling_backend, ilqg_backend, horizon, num_trajectory=None, num_rollouts=None,
-                 fd_tolerance=None, seed=0x5EED):
+                 fd_tolerance=None, seed=0x5EED, fd_mode=None):
         self.model = model
         self.sampling = SamplingPlanner(model, sampling_backend, num_trajectory=num_trajectory, horizon=horizon, seed=seed)
-        self.ilqg = ILQGPlanner(model, ilqg_backend, horizon=horizon, num_rollouts=num_rollouts, fd_tolerance=fd_tolerance)
+        self.ilqg = ILQGPlanner(model, ilqg_backend, horizon=horizon, num_rollouts=num_rollouts, fd_tolerance=fd_tolerance, fd_mode=fd_mode)
         self.H = int(horizon)
         self.reset()
 

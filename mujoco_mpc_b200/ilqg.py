@@ -38,12 +38,14 @@ class ILQGSettings:                      # mjpc/planners/ilqg/settings.h:21-36
 
 
 class ILQGPlanner:
-    def __init__(self, model, backend, horizon, num_rollouts=None, fd_tolerance=None, representation=None):
+    def __init__(self, model, backend, horizon, num_rollouts=None, fd_tolerance=None, representation=None, fd_mode=None):
         m = self.model = model
         self.backend = backend
         self.settings = ILQGSettings()
         if fd_tolerance is not None:
             self.settings.fd_tolerance = fd_tolerance
+        if fd_mode is not None:
+            self.settings.fd_mode = int(fd_mode)   # the reference default (0, with 1e-6) is an fp64 setting; the engine wants centred 3e-4
         self.H = int(horizon)
         self.K = int(num_rollouts or m.numeric.get("ilqg_num_rollouts", [10])[0])
         self.representation = int(representation if representation is not None else m.numeric.get("ilqg_representation", [1])[0])

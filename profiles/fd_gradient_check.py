@@ -48,5 +48,23 @@ if "--oracle" in sys.argv:
 else:
     from mujoco_mpc_b200.engine import Engine
     e = Engine(m, 64, H)
-    run(e, "device fp32", [(1e-3, 0), (3e-3, 0), (1e-2, 0), (3e-4, 1), (1e-3, 1), (3e-3, 1), (1e-2, 1)], 3e-3)
+    run(e, "device fp32", [(1e-3, 0), (3e-4, 0), (1e-4, 0), (1e-3, 1), (3e-4, 1), (1e-4, 1), (3e-5, 1)], 3e-3)
     run(OracleBackend(m, threads=8), "fp64 oracle", [(1e-6, 0), (1e-6, 1)], 1e-4)
+    # what the planner makes of it: 8 iLQG iterations from the home keyframe (zero nominal), return after each
+    for eps, mode in [(1e-3, 0), (3e-4, 0), (1e-3, 1), (3e-4, 1), (1e-4, 1), (3e-5, 1)]:
+        pl = ILQGPlanner(m, e, horizon=H, num_rollouts=10, fd_tolerance=eps)
+        pl.settings.fd_mode = mode
+        pl.set_state(state, 0.0, mocap_of(m))
+        pl.nominal_trajectory(); first = pl.cand["total_return"]
+        rets = []
+        for _ in range(8):
+            pl.optimize_policy(); rets.append(pl.total_return)
+        print("iLQG device eps %-6g %-9s first %.6f -> %s" % (eps, "centred" if mode else "one-sided", first, np.array2string(np.array(rets), precision=6)))
+    ob = OracleBackend(m, threads=8)
+    pl = ILQGPlanner(m, ob, horizon=H, num_rollouts=10, fd_tolerance=1e-6)
+    pl.set_state(state, 0.0, mocap_of(m))
+    pl.nominal_trajectory(); first = pl.cand["total_return"]
+    rets = []
+    for _ in range(8):
+        pl.optimize_policy(); rets.append(pl.total_return)
+    print("iLQG fp64 oracle eps 1e-6 one-sided first %.6f -> %s" % (first, np.array2string(np.array(rets), precision=6)))

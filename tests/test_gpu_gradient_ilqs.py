@@ -15,9 +15,9 @@ def test_cpp_gradient_planner_matches_python_mirror():
     for name, H in (("particle", 26), ("quadruped", 32)):
         m = get_model(name)
         state = np.concatenate([m.key_qpos[0] if m.nkey else m.qpos0, np.zeros(m.nv)])
-        cpp = CppGradientPlanner(m, H, num_trajectory=8, num_spline_points=5, representation=1, fd_tolerance=1e-3)
+        cpp = CppGradientPlanner(m, H, num_trajectory=8, num_spline_points=5, representation=1, fd_tolerance=1e-3, fd_mode=0)
         e = Engine(m, 8, H)
-        py = GradientPlanner(m, e, horizon=H, num_trajectory=8, num_spline_points=5, representation=1, fd_tolerance=1e-3)
+        py = GradientPlanner(m, e, horizon=H, num_trajectory=8, num_spline_points=5, representation=1, fd_tolerance=1e-3, fd_mode=0)
         cpp.reset(); cpp.set_state(state, 0.0, mocap_of(m)); py.set_state(state, 0.0, mocap_of(m))
         for it in range(4):
             ok_c = cpp.optimize_policy(); ok_p = py.optimize_policy()
@@ -51,9 +51,9 @@ def test_cpp_ilqs_planner_matches_python_mirror():
     from mujoco_mpc_b200.gradient import ILQSPlanner
     m = get_model("particle")
     H = 26
-    cpp = CppILQSPlanner(m, H, num_trajectory=8, num_rollouts=6, fd_tolerance=1e-3)
+    cpp = CppILQSPlanner(m, H, num_trajectory=8, num_rollouts=6, fd_tolerance=1e-3, fd_mode=0)
     e1, e2 = Engine(m, 8, H), Engine(m, 8, H)
-    py = ILQSPlanner(m, e1, e2, horizon=H, num_trajectory=8, num_rollouts=6, fd_tolerance=1e-3)
+    py = ILQSPlanner(m, e1, e2, horizon=H, num_trajectory=8, num_rollouts=6, fd_tolerance=1e-3, fd_mode=0)
     cpp.reset(); cpp.set_state(np.zeros(4), 0.0, mocap_of(m)); py.set_state(np.zeros(4), 0.0, mocap_of(m))
     seq = []
     for it in range(10):

@@ -247,26 +247,47 @@ def test_ilqg_planner_on_device(ctx):
 
 
 def test_ilqg_quadruped_iteration_improves(ctx):
-    """BASELINE config 4 shape (Quadruped, iLQG, H=64): a few iterations lower the nominal return."""
+    """BASELINE config 4 (Quadruped, iLQG, H=64, MakeDifferentiable on): the planner must actually descend.  With the
+    engine's FD settings (centred, 3e-4; csrc/host/ilqg_planner.h) eight iterations from the home keyframe take the
+    return from 0.324 to 0.124 on the device; the fp64 oracle with the reference's own settings (1e-6, one-sided) reaches
+    0.115 (profiles/r02_fd_gradient.txt).  One-sided 1e-3 - the round-1 setting - does not improve it at all: the
+    perturbation crosses contact kinks and the gradient is noise (profiles/fd_gradient_check.py)."""
     from mujoco_mpc_b200.ilqg import ILQGPlanner
     m, e, _ = ctx["quadruped"]
-    pl = ILQGPlanner(m, e, horizon=64, num_rollouts=10, fd_tolerance=1e-3)
+    pl = ILQGPlanner(m, e, horizon=64, num_rollouts=10, fd_tolerance=3e-4, fd_mode=1)
     pl.set_state(np.concatenate([m.key_qpos[0], np.zeros(m.nv)]), 0.0, mocap_of(m))
     pl.nominal_trajectory()
     first = pl.cand["total_return"]          # candidate_policy[0]: the live policy is only published by an Iteration
-    ok = 0
-    for _ in range(6):
-        ok += bool(pl.optimize_policy())
-    assert ok >= 3 and np.isfinite(pl.total_return)
-    assert pl.total_return < first
+    ok, rets = 0, []
+    for _ in range(8):
+        ok += bool(pl.optimize_policy()); rets.append(pl.total_return)
+    print("iLQG quadruped returns:", first, "->", np.round(rets, 5))
+    assert ok >= 6 and np.isfinite(pl.total_return)
+    assert all(b <= a * (1 + 1e-6) for a, b in zip([first] + rets, rets))      # never worse than the nominal (line search includes step 0)
+    assert pl.total_return < 0.75 * first                                          # measured 0.38 x first
     assert (np.abs(pl.actions) <= 1.0 + 1e-6).all()
+
+
+def test_cpp_ilqg_quadruped_descends_with_default_settings():
+    """the C++ planner with its own defaults (centred 3e-4) on the same problem"""
+    from mujoco_mpc_b200.engine import CppILQGPlanner
+    m = get_model("quadruped")
+    pl = CppILQGPlanner(m, 64, num_rollouts=10, representation=1)
+    pl.reset()
+    pl.set_state(np.concatenate([m.key_qpos[0], np.zeros(m.nv)]), 0.0, mocap_of(m))
+    rets = []
+    for _ in range(8):
+        pl.optimize_policy(); rets.append(pl.result()["total_return"])
+    print("C++ iLQG quadruped returns:", np.round(rets, 5))
+    assert rets[-1] < 0.75 * rets[0] or rets[-1] < 0.25
+    pl.close()
 
 
 def test_ilqg_humanoid_iteration_improves(ctx):
     """iLQG on the humanoid (Stand task, nv = 27, pyramidal cones, tendon limits) through the generic FD kernels."""
     from mujoco_mpc_b200.ilqg import ILQGPlanner
     m, e, _ = ctx["humanoid"]
-    pl = ILQGPlanner(m, e, horizon=24, num_rollouts=10, fd_tolerance=1e-3)
+    pl = ILQGPlanner(m, e, horizon=24, num_rollouts=10, fd_tolerance=3e-4, fd_mode=1)
     pl.set_state(np.concatenate([m.qpos0, np.zeros(m.nv)]), 0.0, mocap_of(m))
     pl.nominal_trajectory()
     first = pl.cand["total_return"]
@@ -285,9 +306,9 @@ def test_cpp_ilqg_planner_matches_python_mirror(ctx):
     m = get_model("quadruped")
     H = 32
     state = np.concatenate([m.key_qpos[0], np.zeros(m.nv)])
-    cpp = CppILQGPlanner(m, H, num_rollouts=10, representation=1, fd_tolerance=1e-3)
+    cpp = CppILQGPlanner(m, H, num_rollouts=10, representation=1, fd_tolerance=3e-4, fd_mode=1)
     e = Engine(m, 16, H)
-    py = ILQGPlanner(m, e, horizon=H, num_rollouts=10, fd_tolerance=1e-3, representation=1)
+    py = ILQGPlanner(m, e, horizon=H, num_rollouts=10, fd_tolerance=3e-4, representation=1, fd_mode=1)
     cpp.reset(); cpp.set_state(state, 0.0, mocap_of(m)); py.set_state(state, 0.0, mocap_of(m))
     for it in range(4):
         ok_c = cpp.optimize_policy()
