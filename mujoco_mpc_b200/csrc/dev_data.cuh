@@ -74,7 +74,10 @@ constexpr unsigned kFull = 0xffffffffu;
 constexpr float kMinVal = 1e-15f;
 constexpr float kMaxVal = 1e10f;
 constexpr float kTolFloor = 1e-6f;
-constexpr float kGradFloor = 16.f;   // the fp32 gradient cannot be driven below kGradFloor * eps * |its terms| (k_solve)  // fp32 floor on opt.tolerance (same rule as the oracle's fp32 instantiation)
+#ifndef MJPC_GRAD_FLOOR
+#define MJPC_GRAD_FLOOR 16.f
+#endif
+constexpr float kGradFloor = MJPC_GRAD_FLOOR;   // the fp32 gradient cannot be driven below kGradFloor * eps * |its terms| (k_solve)  // fp32 floor on opt.tolerance (same rule as the oracle's fp32 instantiation)
 constexpr float kMinImp = 0.0001f, kMaxImp = 0.9999f, kMinMu = 1e-5f;
 enum { CNSTR_FRICTION_DOF = 0, CNSTR_LIMIT_JOINT, CNSTR_CONTACT_FRICTIONLESS, CNSTR_CONTACT_ELLIPTIC };
 enum { STATE_SATISFIED = 0, STATE_QUADRATIC, STATE_LINEARNEG, STATE_LINEARPOS, STATE_CONE };
