@@ -124,6 +124,7 @@ constexpr int kLayWords = (int)((sizeof(DevLayout) + 15) / 16) * 4;
 struct DynSpec {
   static constexpr bool kStatic = false;
   static constexpr int kNV = 0, kNHPair = 0;
+  static constexpr int kWide = 1, kTask = 0;
   static __device__ __forceinline__ const DevModel& hdr(const Ctx& c) { return *reinterpret_cast<const DevModel*>(g_smem + c.hdr); }
   static __device__ __forceinline__ const DevModel& model(const Ctx& c) { return hdr(c); }
   template <int ID> static __device__ __forceinline__ float* mf(const Ctx& c) { return g_smem + hdr(c).fo[ID]; }
@@ -135,9 +136,13 @@ struct DynSpec {
   }
 };
 
-template <class K>
+// W > 1: the CTA holds W warps for ONE trajectory - warp 0 runs the pipeline, warps 1..W-1 are helpers that join it for
+// the phases with more independent work items than one warp has lanes (wide_* below)
+// T = 1: one more warp (index W) runs the phases that do not depend on the constraint pipeline concurrently with it
+template <class K, int W = 1, int T = 0>
 struct StaticSpec {
   static constexpr bool kStatic = true;
+  static constexpr int kWide = W, kTask = T;
   static __host__ __device__ constexpr int w(size_t byte_off, int i = 0) { return K::kModelWords[byte_off / 4 + i]; }
   struct View {
 #define X(n) static constexpr int n = w(offsetof(DevModel, n));
@@ -165,6 +170,34 @@ struct StaticSpec {
 #define MI(n) (SP::template mi<I_##n>(c))
 #define DF(n) (SP::template df<D_##n>(c))
 #define DI(n) (reinterpret_cast<int*>(SP::template df<D_##n>(c)))
+
+// ---------------------------------------------------------------------------------------- helper warps
+// One trajectory is a chain of dependent phases; at 256 candidates every warp has an issue port to itself and the
+// kernel's duration is that chain's latency.  Phases whose work items outnumber the 32 lanes (Hessian entries, ...)
+// are therefore spread over W warps of the same CTA: the main warp posts a command and its scalar context to a
+// mailbox, all W warps meet on a named barrier, run the phase with a stride of 32*W items, and meet again.  The
+// per-item arithmetic is unchanged, so results are bitwise those of the one-warp kernel.
+enum { WIDE_EXIT = 0, WIDE_HESSIAN = 1 };
+struct WideBox { int cmd, ncon, nlim, ndrow, nefc; int task_exit, task_warn; float task_cost; };
+__device__ __forceinline__ WideBox& wide_box() { __shared__ WideBox box; return box; }
+template <class SP>
+__device__ __forceinline__ void wide_bar() {
+  if constexpr (SP::kWide > 1) asm volatile("bar.sync 1, %0;" ::"n"(32 * SP::kWide) : "memory");
+  else __syncwarp();
+}
+// main warp <-> task warp (fork / join points of the step, rollout_kernels.cuh)
+__device__ __forceinline__ void task_bar() { asm volatile("bar.sync 2, 64;" ::: "memory"); }
+// lane index / lane count of the trajectory's thread group
+template <class SP> __device__ __forceinline__ int wide_lane(const Ctx& c) { return SP::kWide > 1 ? (int)threadIdx.x : c.lane; }
+// main warp: publish the command and the scalar context the phase reads, then release the helpers
+template <class SP>
+__device__ __forceinline__ void wide_post(const Ctx& c, int cmd) {
+  if constexpr (SP::kWide > 1) {
+    WideBox& b = wide_box();
+    if (c.lane == 0) { b.cmd = cmd; b.ncon = c.ncon; b.nlim = c.nlim; b.ndrow = c.ndrow; b.nefc = c.nefc; }
+    wide_bar<SP>();
+  }
+}
 
 // ---------------------------------------------------------------------------------------- small math
 __device__ __forceinline__ float dot3(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }

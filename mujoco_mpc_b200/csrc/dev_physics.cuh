@@ -1213,7 +1213,8 @@ __device__ __noinline__ float k_update_constraint(Ctx& c, bool hess) {
 template <class SP, int NV, int NQ>
 __device__ __forceinline__ void hessian_dense_reg(Ctx& c) {
   auto&& M = SP::model(c);
-  const int lane = c.lane;
+  const int lane = wide_lane<SP>(c);   // index within the trajectory's thread group (the warp, or W warps: dev_data.cuh)
+  constexpr int WN = 32 * SP::kWide;
   constexpr int NVP = (NV + 3) / 4 * 4;
   const float *qM = DF(qM), *hw = DF(efc_hw), *Jd = DF(efc_Jd), *Xd = DF(efc_Xd), *xw = DF(efc_hc);
   float* H = DF(qH);
@@ -1230,7 +1231,7 @@ __device__ __forceinline__ void hessian_dense_reg(Ctx& c) {
     // cone effective rows in wrench space: V = sum_a q_a w_a, U = sum_a q_{6+a} w_a  -> efc_hc[36 ci + 14 ..]
     float* xwm = DF(efc_hc);
     MJPC_ROLL
-    for (int w = lane; w < ncon * 6; w += 32) {
+    for (int w = lane; w < ncon * 6; w += WN) {
       const int ci = w / 6, p = w - 6 * ci;
       const int a0 = cadr[ci];
       float v = 0.f, u = 0.f;
@@ -1241,14 +1242,14 @@ __device__ __forceinline__ void hessian_dense_reg(Ctx& c) {
       }
       xwm[36 * ci + 14 + p] = v; xwm[36 * ci + 20 + p] = u;   // zeros for non-cone contacts: read (times 0) below
     }
-    __syncwarp();
+    wide_bar<SP>();
     // (straight-line: clamped indices, weights selected to zero instead of branches - every taken branch costs a
     // reconvergence (BSSY/BSYNC ~30 cycles) with a single resident warp)
     constexpr int kMaxRows = 10;   // pyramidal condim 6; elliptic contacts have <= 6 rows
     const bool pyr = M.cone == CONE_PYRAMIDAL;
     const int nwork = ncon * 21;
     MJPC_ROLL
-    for (int base = 0; base < nwork; base += 32) {
+    for (int base = 0; base < nwork; base += WN) {
       const int w = min(base + lane, nwork - 1);
       const int ci = w / 21, e = w - 21 * ci;
       const int p = (e >= 1) + (e >= 3) + (e >= 6) + (e >= 10) + (e >= 15);
@@ -1274,12 +1275,12 @@ __device__ __forceinline__ void hessian_dense_reg(Ctx& c) {
       acc += (on && state[a0] == STATE_CONE) ? tc : 0.f;
       if (base + lane < nwork) Wc[w] = acc;
     }
-    __syncwarp();
+    wide_bar<SP>();
     // g_i = (sum of W_c over the contacts on bodies in the subtree of dof i's body) cdof_i, one (dof, component) per lane
     const int *subend = MI(body_subtreeend), *cmb = DI(con_mbody), *dbody = MI(dof_bodyid);
     const float* cdof = DF(cdof);
     MJPC_ROLL
-    for (int w = lane; w < NV * 6; w += 32) {
+    for (int w = lane; w < NV * 6; w += WN) {
       const int i = w / 6, k = w - 6 * i;
       const int b = dbody[i], se = subend[b];
       int idx[6];
@@ -1298,22 +1299,22 @@ __device__ __forceinline__ void hessian_dense_reg(Ctx& c) {
       }
       g[w] = a;
     }
-    __syncwarp();
+    wide_bar<SP>();
   }
 #ifdef MJPC_HESS_ROLLED
   // experiment (code footprint): one rolled loop over the pattern entries, H written directly, the rare rank-1 rows
   // of two-sided contacts added in shared memory afterwards
   if (NE != NV * (NV + 1) / 2) {   // entries outside the pattern (the dense factor reads them); nothing to clear for a full pattern
     MJPC_ROLL
-    for (int w = lane; w < NV * NV; w += 32) H[w] = 0.f;
-    __syncwarp();
+    for (int w = lane; w < NV * NV; w += WN) H[w] = 0.f;
+    wide_bar<SP>();
   }
   {
     const float* cdof = DF(cdof);
     const int* dbody2 = MI(dof_bodyid);
     const int* drow = DI(efc_drow);
 #pragma unroll 1
-    for (int e0 = 0; e0 < NE; e0 += 32) {
+    for (int e0 = 0; e0 < NE; e0 += WN) {
       const int e = min(e0 + lane, NE - 1);
       const int r = hi[e], sdof = hj[e];
       float a = qM[r * NV + sdof];
@@ -1351,7 +1352,7 @@ __device__ __forceinline__ void hessian_dense_reg(Ctx& c) {
       if (e0 + lane < NE) { H[r * NV + sdof] = a; H[sdof * NV + r] = a; }
     }
   }
-  __syncwarp();
+  wide_bar<SP>();
 }
 #else
   int er[NQ], es[NQ];
@@ -1578,6 +1579,7 @@ __device__ __noinline__ void k_hessian(Ctx& c) {
     __syncwarp();
   }
   if constexpr (SP::kNV > 0) {
+    wide_post<SP>(c, WIDE_HESSIAN);   // helper warps (if the kernel has them) join for the assembly
     hessian_dense_reg<SP, SP::kNV, (SP::kNHPair + 31) / 32>(c);
     return;
   }
@@ -1658,6 +1660,24 @@ __device__ __noinline__ void k_hessian(Ctx& c) {
     }
     for (int e = lane; e < M.nhpair; e += 32) { const int r = hi[e], s2 = hj[e]; H[s2 * nv + r] = H[r * nv + s2]; }
     __syncwarp();
+  }
+}
+
+// Helper warps of a W-warp trajectory group (dev_data.cuh): wait for the main warp's command, run the phase with it.
+template <class SP>
+__device__ __noinline__ void wide_helper_loop(Ctx& c) {
+  if constexpr (SP::kWide > 1) {
+#ifndef MJPC_HESS_ROLLED
+    static_assert(SP::kWide == 1, "helper warps need the rolled Hessian assembly (MJPC_COMPACT)");
+#endif
+    for (;;) {
+      wide_bar<SP>();
+      const WideBox& b = wide_box();
+      const int cmd = b.cmd;
+      if (cmd == WIDE_EXIT) return;
+      c.ncon = b.ncon; c.nlim = b.nlim; c.ndrow = b.ndrow; c.nefc = b.nefc;
+      if (cmd == WIDE_HESSIAN) hessian_dense_reg<SP, SP::kNV, (SP::kNHPair + 31) / 32>(c);
+    }
   }
 }
 
@@ -1963,8 +1983,11 @@ __device__ __noinline__ void k_solve(Ctx& c) {
     }
     if (iter == M.iterations) break;
     // Newton direction: assemble + factorise the Hessian only now that another iteration is taken
+    PHASE(c, 4);
     k_hessian<SP>(c);
+    PHASE(c, 5);
     warp_chol_factor_solve<SP::kNV>(DF(qH), DF(hinv), search, grad, nv, lane);
+    PHASE(c, 6);
     for (int b0 = 0; b0 < nv; b0 += 32) { const int i = min(b0 + lane, nv - 1); const float v = -search[i]; __syncwarp(); if (b0 + lane < nv) search[i] = v; }
     __syncwarp();
     float q1 = 0, q2 = 0, sn = 0;

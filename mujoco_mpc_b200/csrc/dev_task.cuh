@@ -127,8 +127,9 @@ __device__ __forceinline__ float spline_sample1(const float* times, const float*
   return c0 * p0 + c1 * m0 + c2 * p1 + c3 * m1;
 }
 // ctrl <- clamp(spline(time)); one actuator per lane
+// (out of line: the main warp and the task warp of a rollout CTA must evaluate it with the very same instructions)
 template <class SP>
-__device__ __forceinline__ void k_policy_spline(Ctx& c, int P, int interp) {
+__device__ __noinline__ void k_policy_spline(Ctx& c, int P, int interp) {
   auto&& M = SP::model(c);
   const float* range = MF(actuator_ctrlrange);
   for (int i = c.lane; i < M.nu; i += 32) {

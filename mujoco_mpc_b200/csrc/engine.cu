@@ -46,6 +46,7 @@ struct mjpc_b200 {
   ModelPack pack;
   int maxN = 0, maxH = 0, maxP = 64;
   int warps_per_cta = 1;
+  int num_sms = 148;
   int static_spec = 0;   // 1 / 2: the model equals spec_quadruped.h / spec_humanoid_track.h -> static rollout kernel
   float* d_pack = nullptr;
   // inputs
@@ -149,10 +150,19 @@ int launch_rollout(mjpc_b200* h, const RolloutArgs& A) {
   // static instance: same arguments, same shared-memory image; MJPC_B200_NO_STATIC=1 forces the generic kernel
   const char* ns = std::getenv("MJPC_B200_NO_STATIC");
   const bool use_static = h->static_spec != 0 && wpc == 1 && !(ns && ns[0] == '1');
-  if (use_static && h->static_spec == 1) rollout_kernel_quadruped<<<grid, 32, smem, h->stream>>>(A);
-  else if (use_static && h->static_spec == 2) rollout_kernel_humanoid_track<<<grid, 32, smem, h->stream>>>(A);
-  else rollout_kernel<<<grid, 32 * wpc, smem, h->stream>>>(A);
-  h->last_static = use_static ? 1 : 0;
+  // solo shape (more helper warps) when every candidate gets an SM to itself; MJPC_B200_SHAPE=pair|solo overrides
+  bool solo = A.N <= h->num_sms;
+  if (const char* sh = std::getenv("MJPC_B200_SHAPE")) solo = sh[0] == 's' ? true : sh[0] == 'p' ? false : solo;
+  if (use_static && h->static_spec == 1) {
+    if (solo) rollout_kernel_quadruped_solo<<<grid, kSoloThreads, smem, h->stream>>>(A);
+    else rollout_kernel_quadruped<<<grid, kPairThreads, smem, h->stream>>>(A);
+  } else if (use_static && h->static_spec == 2) {
+    if (solo) rollout_kernel_humanoid_track_solo<<<grid, kSoloThreads, smem, h->stream>>>(A);
+    else rollout_kernel_humanoid_track<<<grid, kPairThreads, smem, h->stream>>>(A);
+  } else {
+    rollout_kernel<<<grid, 32 * wpc, smem, h->stream>>>(A);
+  }
+  h->last_static = use_static ? (solo ? 2 : 1) : 0;
   rank_kernel<<<(A.N + 255) / 256, 256, 0, h->stream>>>(A.returns, A.N, h->d_order);
   CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
   CUDA_TRY(cudaGetLastError());
@@ -304,6 +314,7 @@ int mjpc_b200_create(const mjpc_model_blob* model, int max_candidates, int max_h
   CREATE_TRY(cudaEventCreate(&h->ev1));
   cudaDeviceProp prop;
   CREATE_TRY(cudaGetDeviceProperties(&prop, device));
+  h->num_sms = prop.multiProcessorCount;
   const size_t smem_need = h->smem_bytes(h->maxP, 1);
   if (smem_need > (size_t)prop.sharedMemPerBlockOptin) {
     mjpc_b200_destroy(h);
@@ -340,9 +351,11 @@ int mjpc_b200_create(const mjpc_model_blob* model, int max_candidates, int max_h
   if (spec_matches<SpecQuadruped>(M, make_layout(M, 1))) {
     h->static_spec = 1;
     if (int rc = set_smem((const void*)rollout_kernel_quadruped, h->smem_bytes(h->maxP, 1))) { mjpc_b200_destroy(h); return rc; }
+    if (int rc = set_smem((const void*)rollout_kernel_quadruped_solo, h->smem_bytes(h->maxP, 1))) { mjpc_b200_destroy(h); return rc; }
   } else if (spec_matches<SpecHumanoidTrack>(M, make_layout(M, 1))) {
     h->static_spec = 2;
     if (int rc = set_smem((const void*)rollout_kernel_humanoid_track, h->smem_bytes(h->maxP, 1))) { mjpc_b200_destroy(h); return rc; }
+    if (int rc = set_smem((const void*)rollout_kernel_humanoid_track_solo, h->smem_bytes(h->maxP, 1))) { mjpc_b200_destroy(h); return rc; }
   }
   if (int rc = ilqg_init(h->ilqg, h->pack.M, (int)H, h->smem_bytes(1, 1))) {
     mjpc_b200_destroy(h);

@@ -121,15 +121,54 @@ __device__ __forceinline__ float xfrc_normal(unsigned seed, unsigned step, unsig
   return sqrtf(-2.0f * logf(fmaxf(u1, 1e-12f))) * cospif(2.0f * u2);
 }
 
+// The task warp of a rollout CTA (StaticSpec<K, W, 1>): per step, between the main warp's fork / join barriers,
+//   fork .. join 1 : composite inertia, velocities, smooth forces  (main: collision + constraint rows)
+//   join 1 .. join 2: residual, trace, cost, the next step's spline action  (main: reference + Newton solve)
+// None of these reads anything the main warp writes in the same interval (the arrays are listed per function in
+// DESIGN.md section 5); every value is computed by the same code on the same inputs as in the one-warp order.
+template <class SP>
+__device__ __noinline__ void task_warp_loop(Ctx& c, const RolloutArgs& A, int cand) {
+  auto&& M = SP::model(c);
+  const int lane = c.lane, nu = M.nu, nr = M.num_residual, ntr = 3 * M.num_trace, H = A.H;
+  (void)nu;
+  c.xfrc_on = A.xfrc_std > 0.f ? 1 : 0;
+  float* o_res = A.residual + (size_t)cand * H * nr;
+  float* o_trace = A.trace + (size_t)cand * H * ntr;
+  for (int t = 0; t < H; t++) {
+    const bool last = t == H - 1;
+    task_bar();   // fork (the main warp has written the state, the action and the poses of step t)
+    if (wide_box().task_exit) return;
+    k_crb<SP>(c);
+    k_com_vel<SP>(c);
+    k_smooth_forces<SP>(c);
+    task_bar();   // join 1
+    k_residual<SP>(c);
+    for (int i = lane; i < nr; i += 32) o_res[(size_t)t * nr + i] = DF(residual)[i];
+    write_traces<SP>(c, o_trace + (size_t)t * ntr);
+    const float cost = k_cost_value<SP>(c);
+    if (lane == 0) { wide_box().task_cost = cost; wide_box().task_warn = c.warn; }   // (a residual can raise a warning)
+    if (!last) {
+      c.time += CM(c).timestep;   // the same sum k_euler forms on the main warp
+      if (A.policy_kind == 0 && t + 1 < H - 1) k_policy_spline<SP>(c, A.P, A.interp);
+    }
+    task_bar();   // join 2
+  }
+}
+
 template <class SP>
 __device__ __forceinline__ void rollout_body(const RolloutArgs& A) {
   float* smem = g_smem;
   stage_model_pack(smem, A.pack, (unsigned)((A.M.nf + A.M.ni) * 4));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cand = blockIdx.x * (blockDim.x >> 5) + warp;
+  // SP::kWide > 1: the whole CTA is ONE candidate (warp 0 runs the pipeline, the others help with the wide phases)
+  const int cand = (SP::kWide > 1 || SP::kTask > 0) ? (int)blockIdx.x : blockIdx.x * (blockDim.x >> 5) + warp;
   Ctx c;
-  init_ctx(c, &A.M, &A.L, smem, warp, lane, A.pack);
+  init_ctx(c, &A.M, &A.L, smem, (SP::kWide > 1 || SP::kTask > 0) ? 0 : warp, lane, A.pack);
   if (cand >= A.N) return;
+  if (SP::kWide > 1 && warp > 0 && warp < SP::kWide) { wide_helper_loop<SP>(c); return; }
+  if (SP::kTask > 0 && warp == SP::kWide) { task_warp_loop<SP>(c, A, cand); return; }
+  constexpr bool kTask = SP::kTask > 0;
+  if (kTask && lane == 0) wide_box().task_exit = 0;
   auto&& M = SP::model(c);
   const int nq = M.nq, nv = M.nv, nu = M.nu, ds = nq + nv, nr = M.num_residual, ntr = 3 * M.num_trace, H = A.H;
   // per-iteration task state (time-rebased) overrides the packed copy: the pack in shared memory is per CTA,
@@ -173,8 +212,9 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& A) {
   long long n_newton = 0, n_con = 0, n_efc = 0;
   for (int t = 0; t < H; t++) {
     const bool last = t == H - 1;
+    // (with a task warp the spline action of step t > 0 was evaluated by it during step t-1's constraint solve)
     if (!last) {
-      if (A.policy_kind == 0) k_policy_spline<SP>(c, A.P, A.interp);
+      if (A.policy_kind == 0) { if (!kTask || t == 0) k_policy_spline<SP>(c, A.P, A.interp); }
       else k_policy_feedback<SP>(c, A.fb, step_size, t);
     }
     // action record (the last row repeats the previous action; H == 1 -> zeros; trajectory.cc:190-196)
@@ -182,21 +222,55 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& A) {
       if (H == 1) DF(ctrl)[i] = 0;
       o_actions[(size_t)t * nu + i] = DF(ctrl)[i];
     }
-    if (!last && (k_bad(c, DF(qpos), nq) || k_bad(c, DF(qvel), nv))) { failed = true; break; }
+    if (!last && (k_bad(c, DF(qpos), nq) || k_bad(c, DF(qvel), nv))) {
+      failed = true;
+      if (kTask) { if (lane == 0) wide_box().task_exit = 1; task_bar(); }   // the task warp waits at the fork
+      break;
+    }
     if (noisy && !last) {   // Ornstein-Uhlenbeck perturbation in discrete time (trajectory.cc:147-155)
       float* xf = DF(xfrc);
       for (int i = lane; i < 6 * M.nbody; i += 32)
         xf[i] = ou_rate * xf[i] + ou_scale * xfrc_normal(A.noise_seed, (unsigned)t, (unsigned)(A.cand0 + cand), (unsigned)i);
       __syncwarp();
     }
-    k_forward<SP>(c);
-    n_newton += c.niter; n_con += c.ncon - c.npseudo; n_efc += c.nefc;
-    k_residual<SP>(c);
-    if (!last && k_bad(c, DF(qacc), nv)) c.warn = 1;
-    for (int i = lane; i < nr; i += 32) o_res[(size_t)t * nr + i] = DF(residual)[i];
-    write_traces<SP>(c, o_trace + (size_t)t * ntr);
-    if (c.warn) { failed = true; break; }
-    const float cost = k_cost_value<SP>(c);
+    float cost;
+    if constexpr (kTask) {
+      // the step as a fork / join graph (the one-warp order is k_forward, dev_physics.cuh):
+      //   main: kinematics, com | collision, constraint rows        | reference, Newton solve           | Euler
+      //   task:                 | CRB, velocities, smooth forces    | residual, cost, next spline action |
+      PHASE(c, 7);
+      k_kinematics<SP>(c);
+      k_com_pos<SP>(c);
+      PHASE(c, 0);
+      task_bar();   // fork
+      k_collision<SP>(c);
+      PHASE(c, 1);
+      k_make_constraint<SP>(c);
+      PHASE(c, 2);
+      task_bar();   // join: qM, qfrc_smooth, qacc_smooth are in place
+      k_reference<SP>(c);
+      PHASE(c, 3);
+      k_solve<SP>(c);
+      PHASE(c, 4);
+      n_newton += c.niter; n_con += c.ncon - c.npseudo; n_efc += c.nefc;
+      if (!last && k_bad(c, DF(qacc), nv)) c.warn = 1;
+      task_bar();   // join: residual, trace and cost of this step are written, ctrl holds the next action
+      cost = wide_box().task_cost;
+      if (wide_box().task_warn) c.warn = 1;
+    } else {
+      k_forward<SP>(c);
+      n_newton += c.niter; n_con += c.ncon - c.npseudo; n_efc += c.nefc;
+      k_residual<SP>(c);
+      if (!last && k_bad(c, DF(qacc), nv)) c.warn = 1;
+      for (int i = lane; i < nr; i += 32) o_res[(size_t)t * nr + i] = DF(residual)[i];
+      write_traces<SP>(c, o_trace + (size_t)t * ntr);
+    }
+    if (c.warn) {
+      failed = true;
+      if (kTask && !last) { if (lane == 0) wide_box().task_exit = 1; task_bar(); }
+      break;
+    }
+    if constexpr (!kTask) cost = k_cost_value<SP>(c);
     if (lane == 0) o_costs[t] = cost;
     total += cost;
     if (last) break;
@@ -206,6 +280,7 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& A) {
     for (int i = lane; i < nv; i += 32) o_states[(size_t)(t + 1) * ds + nq + i] = DF(qvel)[i];
     if (lane == 0) o_times[t + 1] = A.time0 + (double)c.time;
   }
+  wide_post<SP>(c, WIDE_EXIT);   // releases the helper warps
   if (lane == 0) {
     A.returns[cand] = failed ? 1.0e6f : total / (float)max(H, 1);
     A.failure[cand] = failed ? 1 : 0;
@@ -234,12 +309,37 @@ extern "C" __global__ void __launch_bounds__(128) rollout_kernel(const __grid_co
   rollout_body<DynSpec>(A);
 }
 // statically specialised instance for the Quadruped (flat) task model (spec_quadruped.h); one warp per CTA
-extern "C" __global__ void __launch_bounds__(32) rollout_kernel_quadruped(const __grid_constant__ RolloutArgs A) {
-  rollout_body<StaticSpec<SpecQuadruped>>(A);
+// Static instances come in two shapes ("helper warps"):
+//   *_quadruped / *_humanoid_track   kPairWide warps per candidate (main + wide helpers).  Used when candidates share SMs
+//                                    (N > number of SMs): every additional resident warp running different code costs the
+//                                    others instruction-cache hits, so only the Hessian helpers are kept.
+//   *_solo                           kSoloWide wide warps + the task warp.  Used when every candidate has an SM to itself.
+#ifndef MJPC_WIDE
+#define MJPC_WIDE 2
+#endif
+#ifndef MJPC_TASK
+#define MJPC_TASK 0
+#endif
+#ifndef MJPC_SOLO_WIDE
+#define MJPC_SOLO_WIDE 4
+#endif
+#ifndef MJPC_SOLO_TASK
+#define MJPC_SOLO_TASK 1
+#endif
+constexpr int kPairWide = MJPC_WIDE, kPairTask = MJPC_TASK, kPairThreads = 32 * (kPairWide + kPairTask);
+constexpr int kSoloWide = MJPC_SOLO_WIDE, kSoloTask = MJPC_SOLO_TASK, kSoloThreads = 32 * (kSoloWide + kSoloTask);
+extern "C" __global__ void __launch_bounds__(kPairThreads) rollout_kernel_quadruped(const __grid_constant__ RolloutArgs A) {
+  rollout_body<StaticSpec<SpecQuadruped, kPairWide, kPairTask>>(A);
+}
+extern "C" __global__ void __launch_bounds__(kSoloThreads) rollout_kernel_quadruped_solo(const __grid_constant__ RolloutArgs A) {
+  rollout_body<StaticSpec<SpecQuadruped, kSoloWide, kSoloTask>>(A);
 }
 // ... and for the Humanoid Track task model (spec_humanoid_track.h)
-extern "C" __global__ void __launch_bounds__(32) rollout_kernel_humanoid_track(const __grid_constant__ RolloutArgs A) {
-  rollout_body<StaticSpec<SpecHumanoidTrack>>(A);
+extern "C" __global__ void __launch_bounds__(kPairThreads) rollout_kernel_humanoid_track(const __grid_constant__ RolloutArgs A) {
+  rollout_body<StaticSpec<SpecHumanoidTrack, kPairWide, kPairTask>>(A);
+}
+extern "C" __global__ void __launch_bounds__(kSoloThreads) rollout_kernel_humanoid_track_solo(const __grid_constant__ RolloutArgs A) {
+  rollout_body<StaticSpec<SpecHumanoidTrack, kSoloWide, kSoloTask>>(A);
 }
 
 // host: does the live model header / state layout equal the table a static kernel was compiled from?

@@ -393,6 +393,12 @@ class Engine:
         """True if the last rollout launch ran a statically specialised kernel instance (csrc/spec_*.h)."""
         return bool(self.lib.mjpc_b200_last_kernel_static(self.h))
 
+    @property
+    def last_kernel_shape(self):
+        """0 generic kernel, 1 static instance for candidates that share SMs (main warp + Hessian helper warps),
+        2 static instance for N <= number of SMs (more helper warps + the task warp); include/mjpc_b200.h."""
+        return int(self.lib.mjpc_b200_last_kernel_static(self.h))
+
 
 class CppSamplingPlanner:
     """The C++ host planner (csrc/host/sampling_planner.cc) through its C wrappers."""

@@ -1,6 +1,6 @@
 import csv, io, subprocess, sys, re, collections, bisect
 rep=sys.argv[1]
-so='/root/repo/mujoco_mpc_b200/csrc/libmjpc_b200.so'
+import os; so=os.environ.get('MJPC_B200_SO') or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'mujoco_mpc_b200', 'csrc', 'libmjpc_b200.so')
 elf=subprocess.run(["cuobjdump","-elf",so],capture_output=True,text=True).stdout
 fns=[]
 for l in elf.splitlines():

@@ -262,6 +262,57 @@ def test_static_and_generic_kernels_agree(name, monkeypatch):
     e.close()
 
 
+@pytest.mark.parametrize("name", ["quadruped", "humanoid_track"])
+def test_kernel_shapes_are_bitwise_identical(name, monkeypatch):
+    """The two shapes of a static rollout instance (include/mjpc_b200.h, mjpc_b200_last_kernel_static) spread the SAME
+    per-item arithmetic over different numbers of warps (wide Hessian assembly; fork / join of the phases that do not
+    depend on the constraint pipeline): every recorded array must be bitwise equal between them - for spline rollouts,
+    NoisyRollout, and the iLQG feedback policy (whose action depends on the next state and stays on the main warp)."""
+    from mujoco_mpc_b200.engine import Engine
+    m = get_model(name)
+    N = 24
+    if name == "quadruped":
+        H = 40
+        state, mocap, knots, kt = quadruped_inputs(m, N=N, H=H)
+    else:
+        rng = np.random.default_rng(3)
+        H, P = 32, 8
+        state = np.concatenate([m.key_qpos[0], np.zeros(m.nv)])
+        mocap = _track_mocap(m)
+        knots = np.clip(0.05 * rng.standard_normal((N, P, m.nu)), -1, 1)
+        kt = np.arange(P) * (H - 1) * 0.005 / (P - 1)
+    e = Engine(m, N, H)
+
+    def both(run):
+        out = {}
+        for shape, code in (("pair", 1), ("solo", 2)):
+            monkeypatch.setenv("MJPC_B200_SHAPE", shape)
+            ret, fail, _ = run()
+            assert e.last_kernel_shape == code
+            out[shape] = dict(e.fetch_all(), returns=ret, failure=fail)
+        for k in out["pair"]:
+            assert np.array_equal(out["pair"][k], out["solo"][k]), k
+        return out["pair"]
+
+    clean = both(lambda: e.rollout_spline(state, 0.0, mocap, knots, kt, 2, H))
+    assert not clean["failure"].any()
+    e.set_xfrc_noise(1.0, 0.1, 5)
+    try:
+        noisy = both(lambda: e.rollout_spline(state, 0.0, mocap, knots, kt, 2, H))
+    finally:
+        e.set_xfrc_noise(0.0)
+    assert np.abs(noisy["returns"] - clean["returns"]).max() > 1e-5
+    # feedback policy around candidate 0's trajectory (discrete and time-interpolated modes)
+    n = 2 * m.nv
+    gains = 0.01 * np.random.default_rng(4).standard_normal((H, m.nu, n)).astype(np.float32)
+    du = np.zeros((H, m.nu), np.float32)
+    steps = np.linspace(0.0, 1.0, 6)
+    for mode in (0, 3):
+        both(lambda: e.rollout_feedback(state, 0.0, mocap, clean["actions"][0], clean["states"][0], clean["times"][0],
+                                        gains, du, steps, mode))
+    e.close()
+
+
 def test_set_task_and_time_rebasing(engines, oracles, quadruped):
     """mjpc_b200_set_task (the per-iteration residual snapshot, agent.cc:316-319) and the host-side time rebasing."""
     from mujoco_mpc_b200 import task as T
