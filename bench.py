@@ -496,7 +496,8 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "kernel": "rollout_kernel_quadruped" if eng.last_kernel_static else "rollout_kernel", "kernel_ms": kernel_ms, "peak_source": peak_src,
                 "algorithmic_bytes_per_env_step": algorithmic_bytes_per_env_step(m, P),
-                "note": "latency/occupancy-bound by construction: 256 warps, 64 dependent steps each (DESIGN.md)"}
+                "note": "latency/occupancy-bound by construction: 256 candidates, 64 dependent steps each; one main warp per candidate plus helper warps for the wide phases (DESIGN.md section 5)",
+                "kernel_shape": int(eng.last_kernel_shape)}
     for prof in ("traffic_r02.json", "traffic_r01.json"):
         pp = os.path.join(ROOT, "profiles", prof)
         if os.path.exists(pp):
@@ -504,7 +505,8 @@ def main():
             roofline["traffic"] = pj.get("dram_bytes_per_launch")
             # what actually bounds the kernel (from the committed ncu capture of the same launch): issue-slot use and stalls
             roofline["latency_bound_evidence"] = {k: pj[k] for k in ("smsp__issue_active_pct", "sm__warps_active_pct_of_peak",
-                                                                     "warp_instructions_per_env_step", "stall_mix_pct",
+                                                                     "warp_instructions_per_env_step", "warp_instructions_per_env_step_main_warp",
+                                                                     "stall_mix_pct", "stall_mix_pct_main_warp",
                                                                      "counters_from") if k in pj}
             break
     cores = usable_cores()

@@ -352,13 +352,18 @@ __device__ __forceinline__ void warp_chol_factor_solve_reg(float* A, float* x, c
   for (int k = 0; k < N; k++) row[k] = A[li * N + k];
   float y = b[li];
   __syncwarp();   // lanes >= N read row N-1 / b[N-1], which lane N-1 (and x == b callers) overwrite below
+  // The factorisation is a chain of N dependent (broadcast pivot -> scale column -> broadcast column -> update) steps
+  // and the warp has the issue port to itself: the forward substitution L y = b rides along as one more "column"
+  // (y is updated by column j as soon as that column exists) instead of a second N-step chain of its own.
 #pragma unroll
   for (int j = 0; j < N; j++) {
     float p = __shfl_sync(kFull, row[j], j);
     if (p < kMinVal) p = kMinVal;
-    const float l = sqrtf(p);
+    const float l = sqrtf(p);   // (rsqrt instead of sqrt + reciprocal was measured: no change in kernel time)
     il[j] = 1.0f / l;
+    const float yj = __shfl_sync(kFull, y, j) * il[j];
     row[j] = (lane == j) ? l : row[j] * il[j];
+    y = (lane == j) ? yj : (lane > j ? y - row[j] * yj : y);
 #pragma unroll
     for (int k = j + 1; k < N; k++) {
       const float lkj = __shfl_sync(kFull, row[j], k);
@@ -369,12 +374,6 @@ __device__ __forceinline__ void warp_chol_factor_solve_reg(float* A, float* x, c
 #pragma unroll
     for (int k = 0; k < N; k++)
       if (k <= lane) A[lane * N + k] = row[k];
-  }
-#pragma unroll
-  for (int i = 0; i < N; i++) {  // forward: L y = b
-    const float yi = __shfl_sync(kFull, y, i) * il[i];
-    if (lane == i) y = yi;
-    if (lane > i) y -= row[i] * yi;
   }
   __syncwarp();
 #pragma unroll

@@ -10,6 +10,8 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <limits>
 #include <vector>
 
@@ -1143,6 +1145,8 @@ T line_search(const Model<T>& m, const Data<T>& d, const SolverCtx<T>& s, const 
   return best.cost < p0.cost ? best.alpha : (T)0;
 }
 
+inline bool solver_trace() { static const bool on = std::getenv("ORACLE_SOLVER_TRACE") != nullptr; return on; }
+
 template <class T>
 void solve_constraints(const Model<T>& m, Data<T>& d) {
   int nv = m.nv, ne = d.nefc;
@@ -1216,6 +1220,12 @@ void solve_constraints(const Model<T>& m, Data<T>& d) {
     for (int i = 0; i < nv; i++) gn += s.grad[i] * s.grad[i];
     T improvement = (old - s.cost) / scale_inv, gradient = mm::sqrt(gn) / scale_inv;
     const T tol = mm::max(m.tolerance, kTolFloor<T>());
+    if (solver_trace()) {   // ORACLE_SOLVER_TRACE=1: one line per Newton iteration (diagnostics only)
+      int ncone = 0, nquad = 0;
+      for (int r = 0; r < ne; r++) { ncone += d.efc_state[r] == 4; nquad += d.efc_state[r] == 1; }
+      std::fprintf(stderr, "  newton %2d  alpha %.4f  cost %.10g  improvement %.3e  gradient %.3e  (tol %.1e)  rows %d quad %d cone %d\n",
+                   iter + 1, (double)alpha, (double)s.cost, (double)improvement, (double)gradient, (double)tol, ne, nquad, ncone);
+    }
     if (sizeof(T) == 4) {
       // reduced precision: a cost decrease below the rounding of the cost itself is not evidence of convergence
       // (the gradient can still be 1e4 x tol there); such an iteration only stops the solver when the gradient no
