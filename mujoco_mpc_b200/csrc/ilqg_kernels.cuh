@@ -604,7 +604,14 @@ __device__ inline int box_qp_warp(float* res, float* R, int* index, const float*
 
 // dynamic smem layout (floats): At[n*n] Bt[n*m] W[n*n] T1[n*n] Qxx[n*n] Qxu[n*m] Quu[m*m] QxuR[n*m] QuuR[m*m]
 //   K[m*n] Wx[n] Qx[n] Qu[m] du[m] Qd[m] qp_res[m] qp_R[m*m] qp_lo[m] qp_hi[m] scratch[8m] + index[m] ints
-extern "C" __global__ void __launch_bounds__(256) backward_pass_kernel(const __grid_constant__ BackwardArgs P) {
+// One CTA walks the 63 dependent Riccati steps; within a step the 36x36x36 products are spread over all threads.  The
+// thread count is a latency knob, not a throughput one: with 8 warps (2 per scheduler) the shared-memory load -> FMA
+// chains of the products were exposed (68.7 k cycles per step, profiles/r02_ilqg_ncu.txt); measured 256 / 512 / 1024
+// threads: 2.28 / 2.06 / 2.16 ms per sweep - the rest is the serial box-QP and gain solves between the barriers.
+#ifndef MJPC_BP_THREADS
+#define MJPC_BP_THREADS 512
+#endif
+extern "C" __global__ void __launch_bounds__(MJPC_BP_THREADS) backward_pass_kernel(const __grid_constant__ BackwardArgs P) {
   extern __shared__ __align__(16) float sm[];
   const int n = P.n, m = P.m, H = P.H, tid = threadIdx.x, nt = blockDim.x;
   float* At = sm; float* Bt = At + n * n; float* W = Bt + n * m; float* T1 = W + n * n; float* Qxx = T1 + n * n;
@@ -932,7 +939,7 @@ inline int ilqg_backward_pass(IlqgBuffers& b, const DevModel& M, const float* d_
   const size_t smem = (4 * n * n + 3 * n * m + 3 * m * m + m * n + 2 * n + 12 * m + 9 * m + 16) * 4;
   ILQG_TRY(raise_smem_limit((const void*)backward_pass_kernel, smem));
   if (e0) ILQG_TRY(cudaEventRecord(e0, st));
-  backward_pass_kernel<<<1, 256, smem, st>>>(a);
+  backward_pass_kernel<<<1, MJPC_BP_THREADS, smem, st>>>(a);
   if (e1) ILQG_TRY(cudaEventRecord(e1, st));
   *launches += 1;
   ILQG_TRY(cudaGetLastError());
