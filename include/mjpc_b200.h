@@ -176,9 +176,9 @@ int64_t mjpc_b200_launch_count(const mjpc_b200_t* h);
 /* Device time (ms, CUDA events on the engine's stream) of the kernels of the last call. */
 float mjpc_b200_last_kernel_ms(const mjpc_b200_t* h);
 /* Non-zero if the last rollout launch used a statically specialised kernel instance (model == a shipped task model,
- * csrc/spec_*.h): 1 = the shape for candidates that share SMs (N > number of SMs: one main warp + Hessian helper warps
- * per candidate), 2 = the shape for N <= number of SMs (more helper warps + a task warp); 0 = the generic kernel.
- * Environment: MJPC_B200_NO_STATIC=1 forces the generic kernel, MJPC_B200_SHAPE=pair|solo forces a shape. */
+ * csrc/spec_*.h): 1 = the shipped instance (one CTA per candidate: main warp + Hessian helper warps + task warp),
+ * 2 = its one-warp-per-candidate twin (same source, selected only by MJPC_B200_SHAPE=plain: the bitwise reference of
+ * the tests and the baseline of the profiles); 0 = the generic kernel (MJPC_B200_NO_STATIC=1 forces it). */
 int mjpc_b200_last_kernel_static(const mjpc_b200_t* h);
 /* Host-only: header + state-layout words of a model ({n_model, n_layout, model words, layout offsets}); what
  * mujoco_mpc_b200/gen_spec.py writes into csrc/spec_*.h.  Returns the number of ints written or <0. */

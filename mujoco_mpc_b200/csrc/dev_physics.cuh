@@ -1534,6 +1534,13 @@ __device__ __noinline__ float k_total_cost(Ctx& c, const float* qacc, bool hess,
 // Newton Hessian H = M + J^T diag(hw) J + cone blocks at the point last evaluated by k_total_cost(.., hess=true)
 // (which leaves the row weights hw and the per-cone coefficients in efc_hc).  Kept apart from the cost evaluation
 // so that the solver only assembles and factorises H when another iteration is actually taken.
+// ONE out-of-line copy of the static-spec assembly: the main warp (k_hessian) and the helper warps (wide_helper_loop)
+// execute the very same instructions, so which warp computes an entry cannot change its value.
+template <class SP>
+__device__ __noinline__ void hessian_static(Ctx& c) {
+  hessian_dense_reg<SP, SP::kNV, (SP::kNHPair + 31) / 32>(c);
+}
+
 template <class SP>
 __device__ __noinline__ void k_hessian(Ctx& c) {
   auto&& M = SP::model(c);
@@ -1580,7 +1587,7 @@ __device__ __noinline__ void k_hessian(Ctx& c) {
   }
   if constexpr (SP::kNV > 0) {
     wide_post<SP>(c, WIDE_HESSIAN);   // helper warps (if the kernel has them) join for the assembly
-    hessian_dense_reg<SP, SP::kNV, (SP::kNHPair + 31) / 32>(c);
+    hessian_static<SP>(c);
     return;
   }
   if (nv == 18 && M.nhpair <= 128) {
@@ -1676,7 +1683,7 @@ __device__ __noinline__ void wide_helper_loop(Ctx& c) {
       const int cmd = b.cmd;
       if (cmd == WIDE_EXIT) return;
       c.ncon = b.ncon; c.nlim = b.nlim; c.ndrow = b.ndrow; c.nefc = b.nefc;
-      if (cmd == WIDE_HESSIAN) hessian_dense_reg<SP, SP::kNV, (SP::kNHPair + 31) / 32>(c);
+      if (cmd == WIDE_HESSIAN) hessian_static<SP>(c);
     }
   }
 }

@@ -150,19 +150,19 @@ int launch_rollout(mjpc_b200* h, const RolloutArgs& A) {
   // static instance: same arguments, same shared-memory image; MJPC_B200_NO_STATIC=1 forces the generic kernel
   const char* ns = std::getenv("MJPC_B200_NO_STATIC");
   const bool use_static = h->static_spec != 0 && wpc == 1 && !(ns && ns[0] == '1');
-  // solo shape (more helper warps) when every candidate gets an SM to itself; MJPC_B200_SHAPE=pair|solo overrides
-  bool solo = A.N <= h->num_sms;
-  if (const char* sh = std::getenv("MJPC_B200_SHAPE")) solo = sh[0] == 's' ? true : sh[0] == 'p' ? false : solo;
+  // MJPC_B200_SHAPE=plain selects the one-warp-per-candidate static instance (tests / profiling: the bitwise reference)
+  const char* sh = std::getenv("MJPC_B200_SHAPE");
+  const bool plain = sh && sh[0] == 'p' && sh[1] == 'l';
   if (use_static && h->static_spec == 1) {
-    if (solo) rollout_kernel_quadruped_solo<<<grid, kSoloThreads, smem, h->stream>>>(A);
-    else rollout_kernel_quadruped<<<grid, kPairThreads, smem, h->stream>>>(A);
+    if (plain) rollout_kernel_quadruped_plain<<<grid, 32, smem, h->stream>>>(A);
+    else rollout_kernel_quadruped<<<grid, kRolloutThreads, smem, h->stream>>>(A);
   } else if (use_static && h->static_spec == 2) {
-    if (solo) rollout_kernel_humanoid_track_solo<<<grid, kSoloThreads, smem, h->stream>>>(A);
-    else rollout_kernel_humanoid_track<<<grid, kPairThreads, smem, h->stream>>>(A);
+    if (plain) rollout_kernel_humanoid_track_plain<<<grid, 32, smem, h->stream>>>(A);
+    else rollout_kernel_humanoid_track<<<grid, kRolloutThreads, smem, h->stream>>>(A);
   } else {
     rollout_kernel<<<grid, 32 * wpc, smem, h->stream>>>(A);
   }
-  h->last_static = use_static ? (solo ? 2 : 1) : 0;
+  h->last_static = use_static ? (plain ? 2 : 1) : 0;
   rank_kernel<<<(A.N + 255) / 256, 256, 0, h->stream>>>(A.returns, A.N, h->d_order);
   CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
   CUDA_TRY(cudaGetLastError());
@@ -351,11 +351,11 @@ int mjpc_b200_create(const mjpc_model_blob* model, int max_candidates, int max_h
   if (spec_matches<SpecQuadruped>(M, make_layout(M, 1))) {
     h->static_spec = 1;
     if (int rc = set_smem((const void*)rollout_kernel_quadruped, h->smem_bytes(h->maxP, 1))) { mjpc_b200_destroy(h); return rc; }
-    if (int rc = set_smem((const void*)rollout_kernel_quadruped_solo, h->smem_bytes(h->maxP, 1))) { mjpc_b200_destroy(h); return rc; }
+    if (int rc = set_smem((const void*)rollout_kernel_quadruped_plain, h->smem_bytes(h->maxP, 1))) { mjpc_b200_destroy(h); return rc; }
   } else if (spec_matches<SpecHumanoidTrack>(M, make_layout(M, 1))) {
     h->static_spec = 2;
     if (int rc = set_smem((const void*)rollout_kernel_humanoid_track, h->smem_bytes(h->maxP, 1))) { mjpc_b200_destroy(h); return rc; }
-    if (int rc = set_smem((const void*)rollout_kernel_humanoid_track_solo, h->smem_bytes(h->maxP, 1))) { mjpc_b200_destroy(h); return rc; }
+    if (int rc = set_smem((const void*)rollout_kernel_humanoid_track_plain, h->smem_bytes(h->maxP, 1))) { mjpc_b200_destroy(h); return rc; }
   }
   if (int rc = ilqg_init(h->ilqg, h->pack.M, (int)H, h->smem_bytes(1, 1))) {
     mjpc_b200_destroy(h);

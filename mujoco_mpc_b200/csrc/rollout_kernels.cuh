@@ -309,37 +309,29 @@ extern "C" __global__ void __launch_bounds__(128) rollout_kernel(const __grid_co
   rollout_body<DynSpec>(A);
 }
 // statically specialised instance for the Quadruped (flat) task model (spec_quadruped.h); one warp per CTA
-// Static instances come in two shapes ("helper warps"):
-//   *_quadruped / *_humanoid_track   kPairWide warps per candidate (main + wide helpers).  Used when candidates share SMs
-//                                    (N > number of SMs): every additional resident warp running different code costs the
-//                                    others instruction-cache hits, so only the Hessian helpers are kept.
-//   *_solo                           kSoloWide wide warps + the task warp.  Used when every candidate has an SM to itself.
+// Static instances: the shipped one holds kRolloutWide + kRolloutTask warps per candidate (main warp, Hessian helper warps,
+// task warp: DESIGN.md section 5 "helper warps"; 6 + 1 measured best at 128 and at 256 candidates).  The *_plain instance is
+// the same source with ONE warp per candidate: the reference the helper-warp kernel must equal bit for bit
+// (tests/test_gpu_parity.py, MJPC_B200_SHAPE=plain) and the baseline of the profiles.
 #ifndef MJPC_WIDE
-#define MJPC_WIDE 2
+#define MJPC_WIDE 6
 #endif
 #ifndef MJPC_TASK
-#define MJPC_TASK 0
+#define MJPC_TASK 1
 #endif
-#ifndef MJPC_SOLO_WIDE
-#define MJPC_SOLO_WIDE 4
-#endif
-#ifndef MJPC_SOLO_TASK
-#define MJPC_SOLO_TASK 1
-#endif
-constexpr int kPairWide = MJPC_WIDE, kPairTask = MJPC_TASK, kPairThreads = 32 * (kPairWide + kPairTask);
-constexpr int kSoloWide = MJPC_SOLO_WIDE, kSoloTask = MJPC_SOLO_TASK, kSoloThreads = 32 * (kSoloWide + kSoloTask);
-extern "C" __global__ void __launch_bounds__(kPairThreads) rollout_kernel_quadruped(const __grid_constant__ RolloutArgs A) {
-  rollout_body<StaticSpec<SpecQuadruped, kPairWide, kPairTask>>(A);
+constexpr int kRolloutWide = MJPC_WIDE, kRolloutTask = MJPC_TASK, kRolloutThreads = 32 * (kRolloutWide + kRolloutTask);
+extern "C" __global__ void __launch_bounds__(kRolloutThreads) rollout_kernel_quadruped(const __grid_constant__ RolloutArgs A) {
+  rollout_body<StaticSpec<SpecQuadruped, kRolloutWide, kRolloutTask>>(A);
 }
-extern "C" __global__ void __launch_bounds__(kSoloThreads) rollout_kernel_quadruped_solo(const __grid_constant__ RolloutArgs A) {
-  rollout_body<StaticSpec<SpecQuadruped, kSoloWide, kSoloTask>>(A);
+extern "C" __global__ void __launch_bounds__(32) rollout_kernel_quadruped_plain(const __grid_constant__ RolloutArgs A) {
+  rollout_body<StaticSpec<SpecQuadruped, 1, 0>>(A);
 }
 // ... and for the Humanoid Track task model (spec_humanoid_track.h)
-extern "C" __global__ void __launch_bounds__(kPairThreads) rollout_kernel_humanoid_track(const __grid_constant__ RolloutArgs A) {
-  rollout_body<StaticSpec<SpecHumanoidTrack, kPairWide, kPairTask>>(A);
+extern "C" __global__ void __launch_bounds__(kRolloutThreads) rollout_kernel_humanoid_track(const __grid_constant__ RolloutArgs A) {
+  rollout_body<StaticSpec<SpecHumanoidTrack, kRolloutWide, kRolloutTask>>(A);
 }
-extern "C" __global__ void __launch_bounds__(kSoloThreads) rollout_kernel_humanoid_track_solo(const __grid_constant__ RolloutArgs A) {
-  rollout_body<StaticSpec<SpecHumanoidTrack, kSoloWide, kSoloTask>>(A);
+extern "C" __global__ void __launch_bounds__(32) rollout_kernel_humanoid_track_plain(const __grid_constant__ RolloutArgs A) {
+  rollout_body<StaticSpec<SpecHumanoidTrack, 1, 0>>(A);
 }
 
 // host: does the live model header / state layout equal the table a static kernel was compiled from?

@@ -395,8 +395,8 @@ class Engine:
 
     @property
     def last_kernel_shape(self):
-        """0 generic kernel, 1 static instance for candidates that share SMs (main warp + Hessian helper warps),
-        2 static instance for N <= number of SMs (more helper warps + the task warp); include/mjpc_b200.h."""
+        """0 generic kernel, 1 static helper-warp instance (shipped), 2 its one-warp twin (MJPC_B200_SHAPE=plain);
+        include/mjpc_b200.h."""
         return int(self.lib.mjpc_b200_last_kernel_static(self.h))
 
 

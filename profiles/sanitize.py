@@ -10,10 +10,10 @@ m = get_model("quadruped")
 e = Engine(m, 8, 12)
 state, mocap, knots, kt = quadruped_inputs(m, N=4, H=10)
 if which in ("all", "rollout"):
-    for shape in ("pair", "solo"):                                             # static instances, both shapes (helper warps)
+    for shape in ("wide", "plain"):                                            # static instances: helper warps / one warp
         os.environ["MJPC_B200_SHAPE"] = shape
         e.rollout_spline(state, 0.0, mocap, knots, kt, 2, 10)
-        assert e.last_kernel_shape == (1 if shape == "pair" else 2)
+        assert e.last_kernel_shape == (1 if shape == "wide" else 2)
     del os.environ["MJPC_B200_SHAPE"]
     os.environ["MJPC_B200_NO_STATIC"] = "1"
     e.rollout_spline(state, 0.0, mocap, knots, kt, 2, 10)                      # generic instance
@@ -29,7 +29,7 @@ if which in ("all", "humanoid"):
     mc = np.concatenate([mh.key_mpos[0].reshape(-1, 3), np.tile([1.0, 0, 0, 0], (mh.nmocap, 1))], 1).reshape(-1)
     sh = np.concatenate([mh.key_qpos[0], np.zeros(mh.nv)])
     kh = np.clip(0.1 * np.random.default_rng(0).standard_normal((2, 16, mh.nu)), -1, 1)
-    for shape in ("pair", "solo"):
+    for shape in ("wide", "plain"):
         os.environ["MJPC_B200_SHAPE"] = shape
         eh.rollout_spline(sh, 0.0, mc, kh, np.arange(16) * 0.003, 2, 8)
     del os.environ["MJPC_B200_SHAPE"]

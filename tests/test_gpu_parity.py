@@ -263,11 +263,12 @@ def test_static_and_generic_kernels_agree(name, monkeypatch):
 
 
 @pytest.mark.parametrize("name", ["quadruped", "humanoid_track"])
-def test_kernel_shapes_are_bitwise_identical(name, monkeypatch):
-    """The two shapes of a static rollout instance (include/mjpc_b200.h, mjpc_b200_last_kernel_static) spread the SAME
-    per-item arithmetic over different numbers of warps (wide Hessian assembly; fork / join of the phases that do not
-    depend on the constraint pipeline): every recorded array must be bitwise equal between them - for spline rollouts,
-    NoisyRollout, and the iLQG feedback policy (whose action depends on the next state and stays on the main warp)."""
+def test_helper_warp_kernel_equals_one_warp_kernel_bitwise(name, monkeypatch):
+    """The shipped static rollout instance spreads one candidate over several warps (wide Hessian assembly; fork / join
+    of the phases that do not depend on the constraint pipeline - DESIGN.md section 5).  That only moves work between
+    warps, so every recorded array must be BITWISE equal to the one-warp-per-candidate instance of the same source
+    (MJPC_B200_SHAPE=plain) - for spline rollouts, NoisyRollout, and the iLQG feedback policy (whose action depends on
+    the next state and stays on the main warp)."""
     from mujoco_mpc_b200.engine import Engine
     m = get_model(name)
     N = 24
@@ -285,14 +286,14 @@ def test_kernel_shapes_are_bitwise_identical(name, monkeypatch):
 
     def both(run):
         out = {}
-        for shape, code in (("pair", 1), ("solo", 2)):
+        for shape, code in (("wide", 1), ("plain", 2)):
             monkeypatch.setenv("MJPC_B200_SHAPE", shape)
             ret, fail, _ = run()
             assert e.last_kernel_shape == code
             out[shape] = dict(e.fetch_all(), returns=ret, failure=fail)
-        for k in out["pair"]:
-            assert np.array_equal(out["pair"][k], out["solo"][k]), k
-        return out["pair"]
+        for k in out["wide"]:
+            assert np.array_equal(out["wide"][k], out["plain"][k]), k
+        return out["wide"]
 
     clean = both(lambda: e.rollout_spline(state, 0.0, mocap, knots, kt, 2, H))
     assert not clean["failure"].any()
