@@ -102,6 +102,10 @@ struct Ctx {
   int npseudo;  // tendon-limit pseudo-contacts at the tail of the contact list (included in ncon)
   int warn;
   float time;
+  // co-resident pair synchronisation (pair_sync_* below); sync == nullptr: off.  Only lane 0 of the main warp uses these.
+  unsigned* sync;        // HBM: this SM's record (32 words)
+  int sync_slot;         // 0 / 1: which of the SM's two candidates this one is; -1: not paired
+  int sync_mode;         // bit 0: meet at every time step, bit 1: also before every constraint solve
 #ifdef MJPC_PHASE_TIMING
   long long tph[8], tlast;   // profiling build only: SM cycles per pipeline phase
 #endif
@@ -197,6 +201,54 @@ __device__ __forceinline__ void wide_post(const Ctx& c, int cmd) {
     if (c.lane == 0) { b.cmd = cmd; b.ncon = c.ncon; b.nlim = c.nlim; b.ndrow = c.ndrow; b.nefc = c.nefc; }
     wide_bar<SP>();
   }
+}
+
+// ---------------------------------------------------------------------------------------- co-resident pairs
+// At 256 candidates 108 of the 148 SMs run two candidates, and the measured cost of sharing an SM is instruction
+// fetch: two candidates at different places of the 124 KB-per-step code evict each other's lines, while two that
+// run the SAME code at the same time cost each other almost nothing (profiles/icache_probe.py).  The main warps of
+// the two candidates of an SM therefore keep in step through a 128-byte record in HBM (they are different CTAs):
+// they start every time step together (and, mode bit 1, every constraint solve); the one that needs more Newton
+// iterations finishes its solve while the other waits at the next meeting point - and a waiting warp fetches nothing.
+// Timing only: no data crosses, results are bitwise those of unsynchronised runs; every wait is bounded (partner
+// finished / time-out), so nothing can deadlock.  Meeting at every Newton iteration as well was measured and is slower
+// (an HBM flag round trip per iteration plus the waits), profiles/ab_pairsync.py.
+//   record words: [0] registration count | [8 + 8 s + {0, 1}] alive flag, meeting-point sequence number of slot s
+constexpr long long kPairTimeout = 400000;   // SM cycles
+__device__ __forceinline__ unsigned ld_vol(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_vol(unsigned* p, unsigned v) { asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void pair_sync_init(Ctx& c, unsigned* table, int mode) {
+  c.sync = nullptr; c.sync_slot = -1; c.sync_mode = mode;
+  if (!table) return;
+  unsigned smid;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  c.sync = table + 32 * (smid & 255u);
+  if (c.lane == 0) {
+    const unsigned slot = atomicAdd(c.sync, 1u);
+    c.sync_slot = slot < 2u ? (int)slot : -1;
+    if (c.sync_slot >= 0) st_vol(c.sync + 8 + 8 * c.sync_slot, 1u);   // alive
+  }
+}
+__device__ __forceinline__ void pair_sync_done(Ctx& c) {   // the SM's other candidate stops waiting for this one
+  if (c.sync && c.lane == 0 && c.sync_slot >= 0) st_vol(c.sync + 8 + 8 * c.sync_slot, 0u);
+}
+// meeting point number seq (increasing along the trajectory): wait until the partner has reached it too (or is gone)
+__device__ __noinline__ void pair_sync_meet(Ctx& c, int seq) {
+  if (!c.sync) return;
+  if (c.lane == 0 && c.sync_slot >= 0) {
+    unsigned* me = c.sync + 8 + 8 * c.sync_slot;
+    const unsigned* ot = c.sync + 8 + 8 * (1 - c.sync_slot);
+    st_vol(me + 1, (unsigned)seq);
+    if (seq > 0 && ld_vol(c.sync) >= 2u) {
+      const long long t0 = clock64();
+      while (ld_vol(ot + 1) < (unsigned)seq && ld_vol(ot) != 0u && clock64() - t0 < kPairTimeout) __nanosleep(200);
+    }
+  }
+  __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------- small math

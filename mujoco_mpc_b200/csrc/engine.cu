@@ -59,6 +59,7 @@ struct mjpc_b200 {
   unsigned char* d_failure = nullptr;
   int* d_order = nullptr;
   long long* d_stats = nullptr;
+  unsigned* d_pair_sync = nullptr;   // [256][32]: per-SM records of the co-resident pair synchronisation (dev_data.cuh)
   // debug + ilqg scratch
   float* d_dbg = nullptr;
   IlqgBuffers ilqg;
@@ -142,7 +143,8 @@ Staged stage_common(mjpc_b200* h, const float* state, double time, const float* 
   return s;
 }
 
-int launch_rollout(mjpc_b200* h, const RolloutArgs& A) {
+int launch_rollout(mjpc_b200* h, const RolloutArgs& A_in) {
+  RolloutArgs A = A_in;
   const int wpc = h->warps_per_cta;
   const size_t smem = h->smem_bytes(A.P, wpc);
   const int grid = (A.N + wpc - 1) / wpc;
@@ -150,6 +152,15 @@ int launch_rollout(mjpc_b200* h, const RolloutArgs& A) {
   // static instance: same arguments, same shared-memory image; MJPC_B200_NO_STATIC=1 forces the generic kernel
   const char* ns = std::getenv("MJPC_B200_NO_STATIC");
   const bool use_static = h->static_spec != 0 && wpc == 1 && !(ns && ns[0] == '1');
+  // co-resident pair synchronisation: only when at most two candidates can ever be resident per SM and all are resident
+  // at once (one wave); MJPC_B200_PAIR_SYNC=0 switches it off (profiling)
+  {
+    const char* ps = std::getenv("MJPC_B200_PAIR_SYNC");
+    const bool on = !(ps && ps[0] == '0') && A.N > h->num_sms && A.N <= 2 * h->num_sms;
+    A.pair_sync = on ? h->d_pair_sync : nullptr;
+    A.pair_sync_mode = (ps && ps[0] >= '1' && ps[0] <= '3') ? ps[0] - '0' : 1;   // 1: meet per step (default), 3: and before the solve
+    if (on) CUDA_TRY(cudaMemsetAsync(h->d_pair_sync, 0, (size_t)256 * 32 * sizeof(unsigned), h->stream));
+  }
   // MJPC_B200_SHAPE=plain selects the one-warp-per-candidate static instance (tests / profiling: the bitwise reference)
   const char* sh = std::getenv("MJPC_B200_SHAPE");
   const bool plain = sh && sh[0] == 'p' && sh[1] == 'l';
@@ -341,6 +352,7 @@ int mjpc_b200_create(const mjpc_model_blob* model, int max_candidates, int max_h
   CREATE_TRY(dalloc(&h->d_times, N * H)); CREATE_TRY(dalloc(&h->d_residual, N * H * nr));
   CREATE_TRY(dalloc(&h->d_costs, N * H)); CREATE_TRY(dalloc(&h->d_trace, N * H * 3 * (size_t)M.num_trace));
   CREATE_TRY(dalloc(&h->d_returns, N)); CREATE_TRY(dalloc(&h->d_failure, N)); CREATE_TRY(dalloc(&h->d_order, N)); CREATE_TRY(dalloc(&h->d_stats, 12 * N));
+  CREATE_TRY(dalloc(&h->d_pair_sync, (size_t)256 * 32));
   CREATE_TRY(dalloc(&h->d_dbg, 4 * ds + 2 * nu + (size_t)M.nv * M.nv + nr + 256 + 64 + 7 * (size_t)M.nmocap));
   h->h_in_floats = ds + 7 * M.nmocap + M.task_state_size + N * h->maxP * nu + h->maxP + H * (nu + ds + 1 + nu * n + nu) + N + 64;
   CREATE_TRY(cudaMallocHost((void**)&h->h_in, h->h_in_floats * 4));
@@ -374,7 +386,7 @@ void mjpc_b200_destroy(mjpc_b200_t* h) {
   for (void* p : mbufs) if (p) cudaFree(p);
   void* bufs[] = {h->d_pack, h->d_state, h->d_mocap, h->d_task_state, h->d_knots, h->d_knot_times, h->d_unom, h->d_xnom,
                   h->d_tnom, h->d_gains, h->d_du, h->d_steps, h->d_states, h->d_actions, h->d_times, h->d_residual,
-                  h->d_costs, h->d_trace, h->d_returns, h->d_failure, h->d_order, h->d_dbg, h->d_stats};
+                  h->d_costs, h->d_trace, h->d_returns, h->d_failure, h->d_order, h->d_dbg, h->d_stats, h->d_pair_sync};
   for (void* p : bufs) if (p) cudaFree(p);
   ilqg_free(h->ilqg);
   if (h->h_in) cudaFreeHost(h->h_in);

@@ -36,6 +36,8 @@ struct RolloutArgs {
   double time0;
   float* states; float* actions; double* times; float* residual; float* costs; float* trace;
   float* returns; unsigned char* failure;
+  int pair_sync_mode;       // bit 0: meet at every time step, bit 1: also before every constraint solve
+  unsigned* pair_sync;      // HBM [256][32] zeroed before the launch, or nullptr: co-resident pair synchronisation (dev_data.cuh)
   long long* stats;         // [N][12]: cycles, Newton iterations, contacts, constraint rows (summed over steps), 8 phase timers
 };
 
@@ -87,6 +89,7 @@ __device__ __forceinline__ void init_ctx(Ctx& c, const DevModel* M, const DevLay
   c.lane = lane;
   c.gkey = pack + M->nf + M->ni;   // the keyframe table follows the staged part of the pack in HBM
   c.ncon = 0; c.npseudo = 0; c.xfrc_on = 0; c.nefc = 0; c.ndrow = 0; c.nitem = 0; c.niter = 0; c.nlim = 0; c.warn = 0; c.time = 0.f;
+  c.sync = nullptr; c.sync_slot = -1; c.sync_mode = 0;
 #ifdef MJPC_PHASE_TIMING
   for (int k = 0; k < 8; k++) c.tph[k] = 0;
   c.tlast = clock64();
@@ -169,6 +172,7 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& A) {
   if (SP::kTask > 0 && warp == SP::kWide) { task_warp_loop<SP>(c, A, cand); return; }
   constexpr bool kTask = SP::kTask > 0;
   if (kTask && lane == 0) wide_box().task_exit = 0;
+  if constexpr (SP::kWide > 1) pair_sync_init(c, A.pair_sync, A.pair_sync_mode);
   auto&& M = SP::model(c);
   const int nq = M.nq, nv = M.nv, nu = M.nu, ds = nq + nv, nr = M.num_residual, ntr = 3 * M.num_trace, H = A.H;
   // per-iteration task state (time-rebased) overrides the packed copy: the pack in shared memory is per CTA,
@@ -212,6 +216,7 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& A) {
   long long n_newton = 0, n_con = 0, n_efc = 0;
   for (int t = 0; t < H; t++) {
     const bool last = t == H - 1;
+    if (c.sync_mode & 1) pair_sync_meet(c, 2 * t);
     // (with a task warp the spline action of step t > 0 was evaluated by it during step t-1's constraint solve)
     if (!last) {
       if (A.policy_kind == 0) { if (!kTask || t == 0) k_policy_spline<SP>(c, A.P, A.interp); }
@@ -250,6 +255,7 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& A) {
       task_bar();   // join: qM, qfrc_smooth, qacc_smooth are in place
       k_reference<SP>(c);
       PHASE(c, 3);
+      if (c.sync_mode & 2) pair_sync_meet(c, 2 * t + 1);
       k_solve<SP>(c);
       PHASE(c, 4);
       n_newton += c.niter; n_con += c.ncon - c.npseudo; n_efc += c.nefc;
@@ -280,6 +286,7 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& A) {
     for (int i = lane; i < nv; i += 32) o_states[(size_t)(t + 1) * ds + nq + i] = DF(qvel)[i];
     if (lane == 0) o_times[t + 1] = A.time0 + (double)c.time;
   }
+  pair_sync_done(c);
   wide_post<SP>(c, WIDE_EXIT);   // releases the helper warps
   if (lane == 0) {
     A.returns[cand] = failed ? 1.0e6f : total / (float)max(H, 1);
