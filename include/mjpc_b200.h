@@ -178,7 +178,9 @@ float mjpc_b200_last_kernel_ms(const mjpc_b200_t* h);
 /* Non-zero if the last rollout launch used a statically specialised kernel instance (model == a shipped task model,
  * csrc/spec_*.h): 1 = the shipped instance (one CTA per candidate: main warp + Hessian helper warps + task warp),
  * 2 = its one-warp-per-candidate twin (same source, selected only by MJPC_B200_SHAPE=plain: the bitwise reference of
- * the tests and the baseline of the profiles); 0 = the generic kernel (MJPC_B200_NO_STATIC=1 forces it). */
+ * the tests and the baseline of the profiles); 0 = the generic kernel (MJPC_B200_NO_STATIC=1 forces it).
+ * MJPC_B200_PAIR_SYNC=0 disables the step-by-step synchronisation of the two candidates that share an SM when
+ * #SMs < N <= 2 #SMs (a scheduling aid: it never changes a result). */
 int mjpc_b200_last_kernel_static(const mjpc_b200_t* h);
 /* Host-only: header + state-layout words of a model ({n_model, n_layout, model words, layout offsets}); what
  * mujoco_mpc_b200/gen_spec.py writes into csrc/spec_*.h.  Returns the number of ints written or <0. */
