@@ -158,7 +158,7 @@ int launch_rollout(mjpc_b200* h, const RolloutArgs& A_in) {
     const char* ps = std::getenv("MJPC_B200_PAIR_SYNC");
     const bool on = !(ps && ps[0] == '0') && A.N > h->num_sms && A.N <= 2 * h->num_sms;
     A.pair_sync = on ? h->d_pair_sync : nullptr;
-    A.pair_sync_mode = (ps && ps[0] >= '1' && ps[0] <= '3') ? ps[0] - '0' : 1;   // 1: meet per step (default), 3: and before the solve
+    A.pair_sync_mode = (ps && ps[0] >= '1' && ps[0] <= '9') ? std::atoi(ps) : 1;   // 1: meet per step (default), 3: and before the solve; + 16 k: only at steps with (t & k) == 0
     if (on) CUDA_TRY(cudaMemsetAsync(h->d_pair_sync, 0, (size_t)256 * 32 * sizeof(unsigned), h->stream));
   }
   // MJPC_B200_SHAPE=plain selects the one-warp-per-candidate static instance (tests / profiling: the bitwise reference)

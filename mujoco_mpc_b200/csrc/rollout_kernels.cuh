@@ -216,7 +216,7 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& A) {
   long long n_newton = 0, n_con = 0, n_efc = 0;
   for (int t = 0; t < H; t++) {
     const bool last = t == H - 1;
-    if (c.sync_mode & 1) pair_sync_meet(c, 2 * t);
+    if ((c.sync_mode & 1) && (t & (c.sync_mode >> 4)) == 0) pair_sync_meet(c, 2 * t);   // bits 4..: step mask (0 = every step)
     // (with a task warp the spline action of step t > 0 was evaluated by it during step t-1's constraint solve)
     if (!last) {
       if (A.policy_kind == 0) { if (!kTask || t == 0) k_policy_spline<SP>(c, A.P, A.interp); }
