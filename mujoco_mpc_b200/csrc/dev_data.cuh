@@ -1,5 +1,6 @@
 // dev_data.cuh - per-trajectory simulation state ("mjData") as it lives in shared memory, one block of
-// floats per warp, plus the small device math kit.  One warp owns one trajectory: every array below is
+// floats per trajectory, plus the small device math kit.  One (main) warp owns one trajectory - the static rollout
+// instances add helper warps that work on the same block between barriers ("helper warps" below): every array below is
 // private to that warp, phases are separated by __syncwarp(), and lanes split work by body / dof /
 // constraint row / matrix entry.
 #pragma once

@@ -1789,14 +1789,19 @@ __device__ __forceinline__ LsItem ls_load_item(Ctx& c) {
 // Straight-line evaluation (selects, no branches): the three constraint kinds sit on different lanes, so a branchy
 // version executes every path anyway and pays a reconvergence per path on top.  Divisions by Tn = 0 produce inf / NaN
 // in lanes whose result is then selected away (never multiplied by zero).
+// (selection by bit masks, not by ?: - the compiler turns chains of selects over the three kinds into divergent
+// branches with a reconvergence point each (5 BSSY/BSYNC pairs in the first version of this function), and with the
+// kinds spread over the lanes every branch is taken by somebody; the selected VALUES are the same, so are the results)
+__device__ __forceinline__ float ls_pick(float a, bool ma, float b, bool mb, float c2, bool mc) {
+  return __int_as_float((__float_as_int(a) & (ma ? -1 : 0)) | (__float_as_int(b) & (mb ? -1 : 0)) | (__float_as_int(c2) & (mc ? -1 : 0)));
+}
 __device__ __forceinline__ LsPoint ls_eval_cached(const LsItem& it, float g0, float g1, float g2, float alpha) {
   // kinds 1, 2: scalar row
   const float x = it.x0 + alpha * it.jv;
   const float qc = 0.5f * it.D * x * x, qd1 = it.D * x * it.jv, qd2 = it.D * it.jv * it.jv;
-  const bool neg = x <= -it.rf, pos = x >= it.rf;
-  const float c1 = neg ? it.f * (-0.5f * it.rf - x) : pos ? it.f * (-0.5f * it.rf + x) : qc;
-  const float d11 = neg ? -it.f * it.jv : pos ? it.f * it.jv : qd1;
-  const float d21 = (neg || pos) ? 0.f : qd2;
+  const bool neg = x <= -it.rf, pos = x >= it.rf, mid = !(neg || pos);
+  const float c1 = ls_pick(it.f * (-0.5f * it.rf - x), neg, it.f * (-0.5f * it.rf + x), pos && !neg, qc, mid);
+  const float d11 = ls_pick(-it.f * it.jv, neg, it.f * it.jv, pos && !neg, qd1, mid);
   const bool act2 = x < 0.f;
   // kind 3: elliptic cone
   const float mu = it.mu;
@@ -1805,17 +1810,17 @@ __device__ __forceinline__ LsPoint ls_eval_cached(const LsItem& it, float g0, fl
   const float Tn = Tsqr <= 0 ? 0.f : sqrtf(Tsqr);
   const bool top = N >= mu * Tn || (Tn <= 0 && N >= 0);
   const bool bottom = !top && (mu * N + Tn <= 0 || (Tn <= 0 && N < 0));
+  const bool middle = !top && !bottom;
   const float iT = 1.0f / Tn;
   const float N1 = it.V0, T1 = (it.UV + alpha * it.VV) * iT;
   const float T2 = it.VV * iT - (it.UV + alpha * it.VV) * T1 * iT * iT;
   const float NmT = N - mu * Tn, s1 = N1 - mu * T1;
-  const float c3 = top ? 0.f : bottom ? 0.5f * (it.Q0 + alpha * (2 * it.Q1 + alpha * it.Q2)) : 0.5f * it.Dm * NmT * NmT;
-  const float d13 = top ? 0.f : bottom ? it.Q1 + alpha * it.Q2 : it.Dm * NmT * s1;
-  const float d23 = top ? 0.f : bottom ? it.Q2 : it.Dm * (s1 * s1 + NmT * (-mu * T2));
   const int k = it.kind;
-  const float cost = k == 1 ? c1 : k == 2 ? (act2 ? qc : 0.f) : k == 3 ? c3 : 0.f;
-  const float d1 = k == 1 ? d11 : k == 2 ? (act2 ? qd1 : 0.f) : k == 3 ? d13 : 0.f;
-  const float d2 = k == 1 ? d21 : k == 2 ? (act2 ? qd2 : 0.f) : k == 3 ? d23 : 0.f;
+  const bool k1 = k == 1, k2 = (k == 2) && act2, k3b = (k == 3) && bottom, k3m = (k == 3) && middle;
+  // (kind 3 contributes through exactly one of the bottom / middle zones or not at all; kinds 1 and 2 are exclusive)
+  const float cost = ls_pick(c1, k1, qc, k2, ls_pick(0.5f * (it.Q0 + alpha * (2 * it.Q1 + alpha * it.Q2)), k3b, 0.5f * it.Dm * NmT * NmT, k3m, 0.f, false), k3b || k3m);
+  const float d1 = ls_pick(d11, k1, qd1, k2, ls_pick(it.Q1 + alpha * it.Q2, k3b, it.Dm * NmT * s1, k3m, 0.f, false), k3b || k3m);
+  const float d2 = ls_pick(qd2, k1 && mid, qd2, k2, ls_pick(it.Q2, k3b, it.Dm * (s1 * s1 + NmT * (-mu * T2)), k3m, 0.f, false), k3b || k3m);
   LsPoint p;
   p.alpha = alpha;
   p.cost = g0 + alpha * g1 + alpha * alpha * g2 + warp_sum(cost);

@@ -1,6 +1,7 @@
 // rollout_kernels.cuh - the CUDA kernels of the hot path (sm_100a).
 //
-//   rollout_kernel      one warp = one candidate trajectory (Trajectory::Rollout / RolloutDiscrete,
+//   rollout_kernel      one candidate trajectory per warp (generic) or per CTA of main + helper warps (static instances)
+//                       (Trajectory::Rollout / RolloutDiscrete,
 //                       mjpc/trajectory.cc:92-309) incl. policy, mj_step restatement, residual, cost, return
 //   rank_kernel         order of candidates by return (partial_sort, sampling/planner.cc:184-188)
 //   step_debug_kernel   a single forward+Euler step through the same device functions (parity hook)
