@@ -394,6 +394,13 @@ __device__ __noinline__ void warp_chol_solve(float* x, const float* Lm, const fl
   if (lane + 32 < n) x[lane + 32] = r1;
   __syncwarp();
 }
+// select by bit masks (exactly one of the conditions holds): never compiled into a branch
+__device__ __forceinline__ float mask_pick(float a, bool ma, float b, bool mb) {
+  return __int_as_float((__float_as_int(a) & (ma ? -1 : 0)) | (__float_as_int(b) & (mb ? -1 : 0)));
+}
+__device__ __forceinline__ float mask_pick3(float a, bool ma, float b, bool mb, float c2, bool mc) {
+  return __int_as_float((__float_as_int(a) & (ma ? -1 : 0)) | (__float_as_int(b) & (mb ? -1 : 0)) | (__float_as_int(c2) & (mc ? -1 : 0)));
+}
 // ---- register-resident variant for compile-time N <= 32: lane i keeps row i of the matrix in registers,
 // columns are broadcast with shuffles (N(N-1)/2 SHFL + FMA), then L is written back to shared memory and
 // L L^T x = b is solved (forward substitution from registers, backward substitution from shared memory rows).
@@ -415,8 +422,10 @@ __device__ __forceinline__ void warp_chol_factor_solve_reg(float* A, float* x, c
     const float l = sqrtf(p);   // (rsqrt instead of sqrt + reciprocal was measured: no change in kernel time)
     il[j] = 1.0f / l;
     const float yj = __shfl_sync(kFull, y, j) * il[j];
-    row[j] = (lane == j) ? l : row[j] * il[j];
-    y = (lane == j) ? yj : (lane > j ? y - row[j] * yj : y);
+    // (bit-mask selection: written with ?: the compiler makes a divergent branch region of every column step)
+    const float scaled = row[j] * il[j];
+    row[j] = mask_pick(l, lane == j, scaled, lane != j);
+    y = mask_pick3(yj, lane == j, y - scaled * yj, lane > j, y, lane < j);
 #pragma unroll
     for (int k = j + 1; k < N; k++) {
       const float lkj = __shfl_sync(kFull, row[j], k);
