@@ -7,7 +7,7 @@ from conftest import get_model, quadruped_inputs
 from mujoco_mpc_b200.engine import Engine
 m = get_model("quadruped")
 e = Engine(m, 1024, 64)
-for N in (32, 74, 148, 200, 256, 296, 444, 592):
+for N in (32, 74, 148, 200, 256, 296, 444, 592, 1024):
     state, mocap, knots, kt = quadruped_inputs(m, N=N, H=64)
     ms = []
     for i in range(4):
