@@ -1,4 +1,4 @@
-"""Kernel ms of one static shape at N candidates (12 launches, first two dropped): python profiles/time_shape.py pair|solo [N]"""
+"""Kernel ms of one static shape at N candidates (12 launches, first two dropped): python profiles/time_shape.py wide|plain [N]"""
 import os, sys, numpy as np
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tests"))
 from conftest import get_model
