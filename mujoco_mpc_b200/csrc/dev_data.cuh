@@ -215,7 +215,10 @@ __device__ __forceinline__ void wide_post(const Ctx& c, int cmd) {
 // finished / time-out), so nothing can deadlock.  Meeting at every Newton iteration as well was measured and is slower
 // (an HBM flag round trip per iteration plus the waits), profiles/ab_pairsync.py.
 //   record words: [0] registration count | [8 + 8 s + {0, 1}] alive flag, meeting-point sequence number of slot s
-constexpr long long kPairTimeout = 400000;   // SM cycles
+#ifndef MJPC_PAIR_TIMEOUT
+#define MJPC_PAIR_TIMEOUT 400000
+#endif
+constexpr long long kPairTimeout = MJPC_PAIR_TIMEOUT;   // SM cycles (shorter time-outs were measured: profiles/README.md)
 __device__ __forceinline__ unsigned ld_vol(const unsigned* p) {
   unsigned v;
   asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
