@@ -22,4 +22,4 @@ for rep in range(12):
         print("   (sync on) per-candidate ms min %.2f median %.2f max %.2f" % (c.min(), np.median(c), c.max()))
 for k, v in ms.items():
     print("N=%d pair sync %s: kernel ms min %.3f median %.3f max %.3f" % (N, k, min(v), np.median(v), max(v)))
-print("returns bitwise equal:", all(np.array_equal(ret["0"], ret[k]) for k in modes))
+print("returns bitwise equal:", all(np.array_equal(ret[modes[0]], ret[k]) for k in modes))
